@@ -1,0 +1,938 @@
+/*
+ * pp_oracle.c — CPU oracle (TEST INFRASTRUCTURE ONLY; see pp_oracle.h).
+ *
+ * Restates the arithmetic of PeaBrane/peapods v0.2.1 `spin-sim` for the
+ * single-spin-flip sweep path.  Build with -ffp-contract=off -fno-fast-math so
+ * that every f32 operation is the single IEEE operation the Rust source performs.
+ * Citations are file:line under /root/reference/.
+ */
+#include "pp_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static __thread char g_err[256];
+const char *orc_last_error(void) { return g_err; }
+static void set_err(const char *m) { snprintf(g_err, sizeof g_err, "%s", m); }
+
+/* ======================================================================
+ * RNG primitives
+ * ====================================================================== */
+
+/* simulation/realization.rs:9-15 and src/lib.rs:22-28 (identical bodies). */
+uint64_t orc_splitmix64(uint64_t value) {
+    value += 0x9E3779B97F4A7C15ull;
+    uint64_t mixed = value;
+    mixed = (mixed ^ (mixed >> 30)) * 0xBF58476D1CE4E5B9ull;
+    mixed = (mixed ^ (mixed >> 27)) * 0x94D049BB133111EBull;
+    return mixed ^ (mixed >> 31);
+}
+
+/* simulation/realization.rs:17-19 */
+uint64_t orc_child_seed(uint64_t root, uint64_t domain, uint64_t index) {
+    return orc_splitmix64(root ^ domain ^ orc_splitmix64(index));
+}
+
+/* src/lib.rs:30-32 */
+uint64_t orc_realization_seed(uint64_t root, uint64_t r) {
+    return orc_splitmix64(root ^ orc_splitmix64(r));
+}
+
+#define SYSTEM_SEED_DOMAIN 0x53A917E14C2D8B6Full /* realization.rs:6 */
+
+/* rand_xoshiro 0.6.0 (Cargo.lock:654), Xoshiro256StarStar::seed_from_u64: the four state
+ * words are successive SplitMix64 outputs (state += golden; mix).  Third-party, unpinned. */
+void orc_xoshiro_seed_from_u64(uint64_t s[4], uint64_t seed) {
+    uint64_t state = seed;
+    for (int i = 0; i < 4; i++) {
+        state += 0x9E3779B97F4A7C15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        s[i] = z ^ (z >> 31);
+    }
+}
+
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+/* xoshiro256** 1.0 (Blackman & Vigna), as implemented by rand_xoshiro 0.6.0. */
+uint64_t orc_xoshiro_next_u64(uint64_t s[4]) {
+    uint64_t result = rotl64(s[1] * 5, 7) * 9;
+    uint64_t t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl64(s[3], 45);
+    return result;
+}
+
+/* rand_xoshiro: next_u32 takes the upper half of next_u64. */
+static inline uint32_t xo_next_u32(uint64_t s[4]) { return (uint32_t)(orc_xoshiro_next_u64(s) >> 32); }
+
+/* rand 0.8.5 Standard for f32: 24 high bits of one u32 times 2^-24 (mcmc/sweep.rs:179-181). */
+static inline uint32_t xo_draw24(uint64_t s[4]) { return xo_next_u32(s) >> 8; }
+static inline float u24_to_f32(uint32_t d) { return (float)d * (1.0f / 16777216.0f); }
+
+/* rand 0.8.5 UniformInt<usize>::sample_single (widening multiply + rejection zone). */
+static uint64_t xo_gen_range_usize(uint64_t s[4], uint64_t low, uint64_t high) {
+    uint64_t range = high - low; /* caller guarantees high > low */
+    int lz = __builtin_clzll(range);
+    uint64_t zone = (range << lz) - 1;
+    for (;;) {
+        uint64_t v = orc_xoshiro_next_u64(s);
+        __uint128_t m = (__uint128_t)v * range;
+        uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+        if (lo <= zone) return low + hi;
+    }
+}
+
+/* Philox4x32-10 (Salmon et al., SC'11), the RNG-SPEC generator. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int round = 0; round < 10; round++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* RNG-SPEC: 24-bit draw number `index` of the (c1, c2, c3) stream:
+ * one Philox call serves four consecutive indices. */
+uint32_t orc_draw24(uint64_t key, uint32_t index, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t ctr[4] = {index >> 2, c1, c2, c3};
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    uint32_t out[4];
+    orc_philox4x32_10(ctr, k, out);
+    return out[index & 3] >> 8;
+}
+
+/* ======================================================================
+ * Lattice  (geometry/lattice.rs:9-109, geometry/offsets.rs:4-13)
+ * ====================================================================== */
+struct orc_lattice {
+    int n_dims, n_neighbors;
+    int64_t n_spins;
+    int64_t shape[ORC_MAX_DIMS], strides[ORC_MAX_DIMS];
+    uint32_t *fwd, *bwd;
+};
+
+static int64_t rem_euclid(int64_t a, int64_t m) {
+    int64_t r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+orc_lattice *orc_lattice_new(int n_dims, const int64_t *shape, int n_offsets, const int64_t *offsets) {
+    if (n_dims < 1 || n_dims > ORC_MAX_DIMS) { set_err("bad n_dims"); return NULL; }
+    orc_lattice *lat = calloc(1, sizeof *lat);
+    lat->n_dims = n_dims;
+    int64_t *hyper = NULL;
+    if (!offsets) { /* geometry/offsets.rs:4-13 */
+        n_offsets = n_dims;
+        hyper = calloc((size_t)n_dims * n_dims, sizeof(int64_t));
+        for (int d = 0; d < n_dims; d++) hyper[d * n_dims + d] = 1;
+        offsets = hyper;
+    }
+    lat->n_neighbors = n_offsets;
+    lat->n_spins = 1;
+    for (int d = 0; d < n_dims; d++) { lat->shape[d] = shape[d]; lat->n_spins *= shape[d]; }
+    /* lattice.rs:58-61 row-major strides */
+    for (int d = 0; d < n_dims; d++) lat->strides[d] = 1;
+    for (int d = n_dims - 2; d >= 0; d--) lat->strides[d] = lat->strides[d + 1] * shape[d + 1];
+    size_t tab = (size_t)lat->n_spins * n_offsets;
+    lat->fwd = malloc(tab * sizeof(uint32_t) + 4);
+    lat->bwd = malloc(tab * sizeof(uint32_t) + 4);
+    /* lattice.rs:66-82 */
+    for (int64_t i = 0; i < lat->n_spins; i++) {
+        int64_t coords[ORC_MAX_DIMS];
+        for (int d = 0; d < n_dims; d++) coords[d] = (i / lat->strides[d]) % lat->shape[d];
+        for (int k = 0; k < n_offsets; k++) {
+            for (int sgn = 0; sgn < 2; sgn++) {
+                int64_t sign = sgn == 0 ? 1 : -1;
+                int64_t flat = 0;
+                for (int d = 0; d < n_dims; d++) {
+                    int64_t c = rem_euclid(coords[d] + sign * offsets[k * n_dims + d], lat->shape[d]);
+                    flat += c * lat->strides[d];
+                }
+                (sgn == 0 ? lat->fwd : lat->bwd)[i * n_offsets + k] = (uint32_t)flat;
+            }
+        }
+    }
+    free(hyper);
+    return lat;
+}
+
+void orc_lattice_free(orc_lattice *lat) {
+    if (!lat) return;
+    free(lat->fwd); free(lat->bwd); free(lat);
+}
+int64_t orc_lattice_n_spins(const orc_lattice *lat) { return lat->n_spins; }
+int orc_lattice_n_neighbors(const orc_lattice *lat) { return lat->n_neighbors; }
+int64_t orc_lattice_stride(const orc_lattice *lat, int d) { return lat->strides[d]; }
+uint32_t orc_neighbor_fwd(const orc_lattice *lat, int64_t i, int d) { return lat->fwd[i * lat->n_neighbors + d]; }
+uint32_t orc_neighbor_bwd(const orc_lattice *lat, int64_t i, int d) { return lat->bwd[i * lat->n_neighbors + d]; }
+
+int orc_colouring_is_valid(const orc_lattice *lat, const uint16_t *colour) {
+    int z = lat->n_neighbors;
+    for (int64_t i = 0; i < lat->n_spins; i++)
+        for (int d = 0; d < z; d++) {
+            if (colour[lat->fwd[i * z + d]] == colour[i]) return 0;
+            if (colour[lat->bwd[i * z + d]] == colour[i]) return 0;
+        }
+    return 1;
+}
+
+/* ======================================================================
+ * Acceptance rules  (mcmc/sweep.rs:8-19, 35-48, 99-185, 247-257, 271-283)
+ * ====================================================================== */
+#define F32_UNIFORM_VALUES (1u << 24) /* sweep.rs:99-100 */
+
+/* sweep.rs:161-165 */
+int orc_metropolis_legacy_accepts(float temperature, int32_t energy_change, uint32_t draw) {
+    float uniform = (float)draw / (float)F32_UNIFORM_VALUES;
+    return (float)energy_change >= (temperature / 2.0f) * logf(uniform);
+}
+
+/* sweep.rs:147-159 */
+uint32_t orc_metropolis_accepted_count(float temperature, int32_t energy_change) {
+    uint32_t low = 0, high = F32_UNIFORM_VALUES;
+    while (low < high) {
+        uint32_t mid = low + (high - low) / 2;
+        if (orc_metropolis_legacy_accepts(temperature, energy_change, mid)) low = mid + 1;
+        else high = mid;
+    }
+    return low;
+}
+
+/* heat-bath rule of sweep.rs:279-282 on the same 24-bit grid */
+int orc_gibbs_legacy_accepts(float temperature, int32_t energy_change, uint32_t draw) {
+    float u = (float)draw / (float)F32_UNIFORM_VALUES;
+    return (float)energy_change >= (temperature / 2.0f) * logf(u / (1.0f - u));
+}
+
+uint32_t orc_gibbs_accepted_count(float temperature, int32_t energy_change) {
+    uint32_t low = 0, high = F32_UNIFORM_VALUES;
+    while (low < high) {
+        uint32_t mid = low + (high - low) / 2;
+        if (orc_gibbs_legacy_accepts(temperature, energy_change, mid)) low = mid + 1;
+        else high = mid;
+    }
+    return low;
+}
+
+/* sweep.rs:108-145: eligibility gate + table build; -1 = None (fail closed) */
+int orc_metropolis_lookup(const float *couplings, int64_t n_couplings, const float *temps, int n_temps,
+                          int n_neighbors, uint32_t *table) {
+    for (int64_t i = 0; i < n_couplings; i++) {
+        float c = couplings[i];
+        if (!(c == -1.0f || c == 0.0f || c == 1.0f)) return -1;
+    }
+    for (int t = 0; t < n_temps; t++)
+        if (!(isfinite(temps[t]) && temps[t] / 2.0f > 0.0f)) return -1;
+    int offset = 2 * n_neighbors;
+    int width = 2 * offset + 1;
+    if (table)
+        for (int t = 0; t < n_temps; t++)
+            for (int ec = -offset; ec <= offset; ec++)
+                table[t * width + ec + offset] = orc_metropolis_accepted_count(temps[t], ec);
+    return 0;
+}
+
+/* sweep.rs:8-19 */
+static inline float local_field(const orc_lattice *lat, const int8_t *s, const float *J, int64_t i) {
+    int z = lat->n_neighbors;
+    float h = 0.0f;
+    for (int d = 0; d < z; d++) {
+        uint32_t jf = lat->fwd[i * z + d];
+        h += (float)s[jf] * J[i * z + d];
+        uint32_t jb = lat->bwd[i * z + d];
+        h += (float)s[jb] * J[(int64_t)jb * z + d];
+    }
+    return h;
+}
+
+/* One attempt given the 24-bit draw.  lookup != NULL: sweep.rs:170-185; else the log forms
+ * sweep.rs:35-48 with thresholds sweep.rs:256 (Metropolis) / sweep.rs:279-282 (Gibbs). */
+static inline void attempt(int8_t *s, int64_t i, float h, uint32_t draw, float temp, int sweep_mode,
+                           const uint32_t *lookup_row, int offset) {
+    if (lookup_row) {
+        int32_t ec = (int32_t)((float)(-s[i]) * h);
+        if (draw < lookup_row[ec + offset]) s[i] = -s[i];
+        return;
+    }
+    float si = (float)s[i];
+    float eng_change = -si * h;
+    float u = u24_to_f32(draw);
+    float thr = sweep_mode == ORC_SWEEP_METROPOLIS ? (temp / 2.0f) * logf(u)
+                                                   : (temp / 2.0f) * logf(u / (1.0f - u));
+    if (eng_change >= thr) s[i] = -s[i];
+}
+
+/* mcmc/sweep.rs:220-284 through parallel.rs:27-33, typewriter order (sweep.rs:51-97; the
+ * canonical-square fast path is bit-identical to the table path, sweep.rs:293-343). */
+void orc_sweep_xoshiro(const orc_lattice *lat, int8_t *spins, const float *couplings,
+                       const float *temperatures, const int64_t *system_ids, int64_t n_systems,
+                       uint64_t *rng_states, int sweep_mode, int use_lookup) {
+    int z = lat->n_neighbors, offset = 2 * z, width = 4 * z + 1;
+    uint32_t *table = NULL;
+    if (use_lookup && sweep_mode == ORC_SWEEP_METROPOLIS) {
+        table = malloc(sizeof(uint32_t) * (size_t)n_systems * width);
+        if (orc_metropolis_lookup(couplings, lat->n_spins * z, temperatures, (int)n_systems, z, table) != 0) {
+            free(table); table = NULL;
+        }
+    }
+    for (int64_t slot = 0; slot < n_systems; slot++) {
+        int64_t sys = system_ids[slot];
+        int8_t *s = spins + sys * lat->n_spins;
+        uint64_t *rng = rng_states + sys * 4;
+        float temp = temperatures[slot];
+        const uint32_t *row = table ? table + slot * width : NULL;
+        for (int64_t i = 0; i < lat->n_spins; i++) {
+            float h = local_field(lat, s, couplings, i);
+            attempt(s, i, h, xo_draw24(rng), temp, sweep_mode, row, offset);
+        }
+    }
+    free(table);
+}
+
+/* colour-ordered site list + rank-within-colour (RNG-SPEC) */
+static void colour_order(const orc_lattice *lat, const uint16_t *colour, int64_t **order_out,
+                         uint32_t **rank_out, int *n_colours_out) {
+    int64_t n = lat->n_spins;
+    int nc = 0;
+    for (int64_t i = 0; i < n; i++) if (colour[i] + 1 > nc) nc = colour[i] + 1;
+    int64_t *start = calloc((size_t)nc + 1, sizeof(int64_t));
+    for (int64_t i = 0; i < n; i++) start[colour[i] + 1]++;
+    for (int c = 0; c < nc; c++) start[c + 1] += start[c];
+    int64_t *order = malloc(sizeof(int64_t) * (size_t)n);
+    uint32_t *rank = malloc(sizeof(uint32_t) * (size_t)n);
+    int64_t *fill = calloc((size_t)nc, sizeof(int64_t));
+    for (int64_t i = 0; i < n; i++) {
+        int c = colour[i];
+        rank[i] = (uint32_t)fill[c];
+        order[start[c] + fill[c]++] = i;
+    }
+    free(start); free(fill);
+    *order_out = order; *rank_out = rank; *n_colours_out = nc;
+}
+
+static void sweep_philox_impl(const orc_lattice *lat, int8_t *spins, const float *couplings,
+                              const float *temperatures, const int64_t *system_ids, int64_t n_systems,
+                              const uint16_t *colour, const int64_t *order, const uint32_t *rank,
+                              uint64_t key, uint32_t sweep_index, int sweep_mode,
+                              const uint32_t *table, int stream_is_slot) {
+    int z = lat->n_neighbors, offset = 2 * z, width = 4 * z + 1;
+    uint32_t tag = stream_is_slot ? ORC_TAG_SWEEP_MSC : ORC_TAG_SWEEP;
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    for (int64_t slot = 0; slot < n_systems; slot++) {
+        int64_t sys = system_ids[slot];
+        int8_t *s = spins + sys * lat->n_spins;
+        float temp = temperatures[slot];
+        const uint32_t *row = table ? table + slot * width : NULL;
+        uint32_t stream = (uint32_t)(stream_is_slot ? slot : sys);
+        uint32_t cached_c0 = 0xFFFFFFFFu, cached_c3 = 0, out[4] = {0, 0, 0, 0};
+        for (int64_t p = 0; p < lat->n_spins; p++) {
+            int64_t i = order[p];
+            uint32_t c3 = tag | colour[i];
+            uint32_t r = rank[i];
+            if ((r >> 2) != cached_c0 || c3 != cached_c3) {
+                uint32_t ctr[4] = {r >> 2, sweep_index, stream, c3};
+                orc_philox4x32_10(ctr, k, out);
+                cached_c0 = r >> 2; cached_c3 = c3;
+            }
+            float h = local_field(lat, s, couplings, i);
+            attempt(s, i, h, out[r & 3] >> 8, temp, sweep_mode, row, offset);
+        }
+    }
+}
+
+/* +-J Gibbs uses the integer heat-bath table (same rule as the log form on the 24-bit grid) */
+static uint32_t *build_table(const float *couplings, int64_t n_couplings, const float *temps,
+                             int64_t n_systems, int z, int sweep_mode) {
+    int width = 4 * z + 1, offset = 2 * z;
+    if (orc_metropolis_lookup(couplings, n_couplings, temps, (int)n_systems, z, NULL) != 0) return NULL;
+    uint32_t *table = malloc(sizeof(uint32_t) * (size_t)n_systems * width);
+    for (int64_t t = 0; t < n_systems; t++)
+        for (int ec = -offset; ec <= offset; ec++)
+            table[t * width + ec + offset] = sweep_mode == ORC_SWEEP_METROPOLIS
+                                                 ? orc_metropolis_accepted_count(temps[t], ec)
+                                                 : orc_gibbs_accepted_count(temps[t], ec);
+    return table;
+}
+
+void orc_sweep_philox(const orc_lattice *lat, int8_t *spins, const float *couplings,
+                      const float *temperatures, const int64_t *system_ids, int64_t n_systems,
+                      const uint16_t *colour, uint64_t key, uint32_t sweep_index, int sweep_mode,
+                      int use_lookup, int stream_is_slot) {
+    int64_t *order; uint32_t *rank; int nc;
+    colour_order(lat, colour, &order, &rank, &nc);
+    uint32_t *table = use_lookup ? build_table(couplings, lat->n_spins * lat->n_neighbors, temperatures,
+                                               n_systems, lat->n_neighbors, sweep_mode)
+                                 : NULL;
+    sweep_philox_impl(lat, spins, couplings, temperatures, system_ids, n_systems, colour, order, rank,
+                      key, sweep_index, sweep_mode, table, stream_is_slot);
+    free(table); free(order); free(rank);
+}
+
+/* ======================================================================
+ * Energy / magnetisation  (spins/energy.rs:78-110)
+ * ====================================================================== */
+void orc_energies_mags(const orc_lattice *lat, const int8_t *spins, const float *couplings,
+                       int64_t n_systems, float *energies, int64_t *mags) {
+    int64_t n = lat->n_spins;
+    int z = lat->n_neighbors;
+    for (int64_t r = 0; r < n_systems; r++) {
+        const int8_t *s = spins + r * n;
+        float total = 0.0f;
+        int64_t m = 0;
+        for (int64_t i = 0; i < n; i++) {
+            int8_t spin = s[i];
+            m += spin;
+            float si = (float)spin;
+            for (int d = 0; d < z; d++) {
+                uint32_t j = lat->fwd[i * z + d];
+                float sj = (float)s[j];
+                float c = couplings[i * z + d];
+                float interaction = si * sj * c;
+                total += interaction;
+            }
+        }
+        energies[r] = total / (float)n;
+        if (mags) mags[r] = m;
+    }
+}
+
+/* statistics/overlap.rs:259-281 */
+void orc_overlap_dots(const orc_lattice *lat, const int8_t *a, const int8_t *b, int64_t *dot_spin,
+                      int64_t *dot_link) {
+    int64_t ds = 0, dl = 0;
+    int z = lat->n_neighbors;
+    for (int64_t j = 0; j < lat->n_spins; j++) {
+        int64_t q = (int64_t)a[j] * (int64_t)b[j];
+        ds += q;
+        for (int d = 0; d < z; d++) {
+            uint32_t k = lat->fwd[j * z + d];
+            int64_t nq = (int64_t)a[k] * (int64_t)b[k];
+            dl += q * nq;
+        }
+    }
+    *dot_spin = ds; *dot_link = dl;
+}
+
+/* mcmc/tempering.rs:59-70 */
+int orc_full_ladder_edges(int n_temps, int first_parity, int32_t *edges_out) {
+    int n = 0;
+    if (n_temps < 2) return 0;
+    int parities[2] = {first_parity, 1 - first_parity};
+    for (int pi = 0; pi < 2; pi++)
+        for (int edge = parities[pi]; edge < n_temps - 1; edge += 2) edges_out[n++] = edge;
+    return n;
+}
+
+/* ======================================================================
+ * Realization state  (simulation/realization.rs:21-246)
+ * ====================================================================== */
+typedef struct {
+    uint64_t *edge_attempts, *edge_acceptances, *round_trips;
+    uint8_t *trip_state;
+    int next_parity, cold_slot, hot_slot;
+} pt_state;
+
+typedef struct {
+    const float *couplings; /* [N*z'] borrowed from sim->couplings */
+    int8_t *spins;          /* [S*N] */
+    float *temperatures;    /* [S] = temps repeated R times (realization.rs:166) */
+    int64_t *system_ids;    /* [S] slot -> system */
+    uint64_t *rngs;         /* [S][4] xoshiro states */
+    float *energies;        /* [S] by system */
+    pt_state pt;
+    uint64_t base_seed;
+} realization;
+
+struct orc_sim {
+    orc_lattice *lat;
+    int64_t n_real;
+    int n_replicas, n_temps, rng_mode;
+    float *couplings; /* [D][N*z'] */
+    float *temps;     /* [T] */
+    uint64_t ctor_seed, cur_seed;
+    realization *reals;
+    uint16_t *colour;
+    int64_t *order;
+    uint32_t *rank;
+    int n_colours;
+    uint32_t sweep_counter, pt_event_counter; /* RNG-SPEC counters; persist across sample() */
+};
+
+/* realization.rs:59-67, 92-107 */
+static void pt_reset(pt_state *pt, int n_replicas, int n_temps, const int64_t *system_ids,
+                     const float *temperatures) {
+    int n_edges = n_temps > 0 ? n_temps - 1 : 0;
+    memset(pt->edge_attempts, 0, sizeof(uint64_t) * (size_t)n_edges);
+    memset(pt->edge_acceptances, 0, sizeof(uint64_t) * (size_t)n_edges);
+    memset(pt->round_trips, 0, sizeof(uint64_t) * (size_t)n_replicas * n_temps);
+    memset(pt->trip_state, 0, (size_t)n_replicas * n_temps);
+    pt->next_parity = 0;
+    pt->cold_slot = pt->hot_slot = 0;
+    for (int slot = 1; slot < n_temps; slot++) {
+        if (temperatures[slot] < temperatures[pt->cold_slot]) pt->cold_slot = slot;
+        if (temperatures[slot] > temperatures[pt->hot_slot]) pt->hot_slot = slot;
+    }
+    if (n_temps == 0) return;
+    for (int r = 0; r < n_replicas; r++) pt->trip_state[system_ids[r * n_temps + pt->hot_slot]] = 1;
+}
+
+/* realization.rs:109-120 */
+static void pt_record_arrival(pt_state *pt, int64_t system, int slot) {
+    if (slot == pt->hot_slot) {
+        if (pt->trip_state[system] == 2) pt->round_trips[system] += 1;
+        pt->trip_state[system] = 1;
+        return;
+    }
+    if (slot == pt->cold_slot && pt->trip_state[system] == 1) pt->trip_state[system] = 2;
+}
+
+/* realization.rs:73-82 */
+static void pt_record_attempt(pt_state *pt, int edge, int accepted, int64_t left, int64_t right) {
+    pt->edge_attempts[edge] += 1;
+    if (!accepted) return;
+    pt->edge_acceptances[edge] += 1;
+    pt_record_arrival(pt, left, edge + 1);
+    pt_record_arrival(pt, right, edge);
+}
+
+/* Replays a list of attempts through PtState exactly as realization.rs:73-120 does
+ * (used by the hot->cold->hot KAT, realization.rs:285-302). */
+void orc_pt_replay(int n_replicas, int n_temps, const float *temps, int n_attempts, const int32_t *edges,
+                   const int32_t *accepted, const int64_t *left, const int64_t *right,
+                   uint64_t *edge_attempts, uint64_t *edge_acceptances, uint64_t *round_trips) {
+    int S = n_replicas * n_temps;
+    pt_state pt;
+    pt.edge_attempts = edge_attempts; pt.edge_acceptances = edge_acceptances; pt.round_trips = round_trips;
+    pt.trip_state = calloc((size_t)S + 1, 1);
+    int64_t *ids = malloc(sizeof(int64_t) * (size_t)(S + 1));
+    float *tt = malloc(sizeof(float) * (size_t)(S + 1));
+    for (int i = 0; i < S; i++) { ids[i] = i; tt[i] = temps[i % n_temps]; }
+    pt_reset(&pt, n_replicas, n_temps, ids, tt);
+    for (int a = 0; a < n_attempts; a++) pt_record_attempt(&pt, edges[a], accepted[a], left[a], right[a]);
+    free(pt.trip_state); free(ids); free(tt);
+}
+
+/* realization.rs:166-207 (new) and :213-246 (reset): seed, draw spins, identity ids, energies */
+static void realization_init(orc_sim *sim, realization *re, uint64_t base_seed) {
+    const orc_lattice *lat = sim->lat;
+    int64_t n = lat->n_spins;
+    int S = sim->n_replicas * sim->n_temps;
+    re->base_seed = base_seed;
+    for (int i = 0; i < S; i++) {
+        if (sim->rng_mode == ORC_RNG_XOSHIRO) {
+            uint64_t *rng = re->rngs + 4 * i;
+            orc_xoshiro_seed_from_u64(rng, orc_child_seed(base_seed, SYSTEM_SEED_DOMAIN, (uint64_t)i));
+            /* realization.rs:177-182: gen::<f32>() < 0.5 -> -1 */
+            for (int64_t j = 0; j < n; j++)
+                re->spins[i * n + j] = u24_to_f32(xo_draw24(rng)) < 0.5f ? -1 : 1;
+        } else {
+            /* RNG-SPEC INIT: same rule on the Philox draw of (system, site) */
+            for (int64_t j = 0; j < n; j++)
+                re->spins[i * n + j] =
+                    u24_to_f32(orc_draw24(base_seed, (uint32_t)j, 0u, (uint32_t)i, ORC_TAG_INIT)) < 0.5f ? -1 : 1;
+        }
+    }
+    for (int i = 0; i < S; i++) re->system_ids[i] = i;
+    orc_energies_mags(lat, re->spins, re->couplings, S, re->energies, NULL);
+    pt_reset(&re->pt, sim->n_replicas, sim->n_temps, re->system_ids, re->temperatures);
+}
+
+orc_sim *orc_sim_new(int n_dims, const int64_t *shape, int n_offsets, const int64_t *offsets,
+                     const float *couplings, int64_t n_real, const float *temps, int n_temps,
+                     int n_replicas, uint64_t seed, int rng_mode, const uint16_t *colour) {
+    orc_lattice *lat = orc_lattice_new(n_dims, shape, n_offsets, offsets);
+    if (!lat) return NULL;
+    if (rng_mode != ORC_RNG_XOSHIRO) {
+        if (!colour || !orc_colouring_is_valid(lat, colour)) {
+            set_err("PHILOX modes need a valid colouring");
+            orc_lattice_free(lat);
+            return NULL;
+        }
+    }
+    orc_sim *sim = calloc(1, sizeof *sim);
+    sim->lat = lat;
+    sim->n_real = n_real; sim->n_replicas = n_replicas; sim->n_temps = n_temps; sim->rng_mode = rng_mode;
+    int64_t n = lat->n_spins;
+    int z = lat->n_neighbors;
+    int S = n_replicas * n_temps;
+    size_t chunk = (size_t)n * z;
+    sim->couplings = malloc(sizeof(float) * chunk * (size_t)n_real);
+    memcpy(sim->couplings, couplings, sizeof(float) * chunk * (size_t)n_real);
+    sim->temps = malloc(sizeof(float) * (size_t)(n_temps > 0 ? n_temps : 1));
+    memcpy(sim->temps, temps, sizeof(float) * (size_t)n_temps);
+    sim->ctor_seed = sim->cur_seed = seed;
+    if (colour) {
+        sim->colour = malloc(sizeof(uint16_t) * (size_t)n);
+        memcpy(sim->colour, colour, sizeof(uint16_t) * (size_t)n);
+        colour_order(lat, sim->colour, &sim->order, &sim->rank, &sim->n_colours);
+    }
+    sim->reals = calloc((size_t)n_real, sizeof(realization));
+    for (int64_t r = 0; r < n_real; r++) {
+        realization *re = &sim->reals[r];
+        re->couplings = sim->couplings + chunk * (size_t)r;
+        re->spins = malloc((size_t)S * n);
+        re->temperatures = malloc(sizeof(float) * (size_t)(S > 0 ? S : 1));
+        for (int k = 0; k < S; k++) re->temperatures[k] = temps[k % n_temps];
+        re->system_ids = malloc(sizeof(int64_t) * (size_t)(S > 0 ? S : 1));
+        re->rngs = calloc((size_t)(S > 0 ? S : 1) * 4, sizeof(uint64_t));
+        re->energies = calloc((size_t)(S > 0 ? S : 1), sizeof(float));
+        int n_edges = n_temps > 0 ? n_temps - 1 : 0;
+        re->pt.edge_attempts = calloc((size_t)n_edges + 1, sizeof(uint64_t));
+        re->pt.edge_acceptances = calloc((size_t)n_edges + 1, sizeof(uint64_t));
+        re->pt.round_trips = calloc((size_t)S + 1, sizeof(uint64_t));
+        re->pt.trip_state = calloc((size_t)S + 1, 1);
+        realization_init(sim, re, orc_realization_seed(seed, (uint64_t)r)); /* lib.rs:158-164 */
+    }
+    return sim;
+}
+
+void orc_sim_free(orc_sim *sim) {
+    if (!sim) return;
+    for (int64_t r = 0; r < sim->n_real; r++) {
+        realization *re = &sim->reals[r];
+        free(re->spins); free(re->temperatures); free(re->system_ids); free(re->rngs); free(re->energies);
+        free(re->pt.edge_attempts); free(re->pt.edge_acceptances); free(re->pt.round_trips);
+        free(re->pt.trip_state);
+    }
+    free(sim->reals); free(sim->couplings); free(sim->temps); free(sim->colour); free(sim->order);
+    free(sim->rank);
+    orc_lattice_free(sim->lat);
+    free(sim);
+}
+
+/* src/lib.rs:624-633 */
+void orc_sim_reset(orc_sim *sim, int has_seed, uint64_t seed) {
+    uint64_t base = has_seed ? seed : sim->ctor_seed;
+    sim->cur_seed = base;
+    sim->sweep_counter = 0;
+    sim->pt_event_counter = 0;
+    for (int64_t r = 0; r < sim->n_real; r++)
+        realization_init(sim, &sim->reals[r], orc_realization_seed(base, (uint64_t)r));
+}
+
+const int8_t *orc_sim_spins(const orc_sim *sim, int64_t r) { return sim->reals[r].spins; }
+const int64_t *orc_sim_system_ids(const orc_sim *sim, int64_t r) { return sim->reals[r].system_ids; }
+const float *orc_sim_energies(const orc_sim *sim, int64_t r) { return sim->reals[r].energies; }
+
+/* ======================================================================
+ * Sweep loop for one realization  (simulation/mod.rs:177-863, hot-path lines only)
+ * ====================================================================== */
+typedef struct {
+    double *mags, *mags2, *mags4, *energies, *energies2; /* averages [T] */
+    double *ov[6];                                        /* averages [T] */
+    uint64_t *hist;                                       /* [T][N+1] */
+    double *ql, *ql2;                                     /* [T][N+1] */
+} real_result;
+
+/* mcmc/tempering.rs:73-102 with the draw supplied by the caller */
+static int attempt_edge(const float *energies, const float *temperatures, int64_t *system_ids,
+                        int64_t n_spins, float log_rand, int temp_id, int64_t *left, int64_t *right) {
+    float temp_1 = temperatures[temp_id];
+    float temp_2 = temperatures[temp_id + 1];
+    float energy_1 = energies[system_ids[temp_id]];
+    float energy_2 = energies[system_ids[temp_id + 1]];
+    *left = system_ids[temp_id];
+    *right = system_ids[temp_id + 1];
+    float delta = (float)n_spins * (energy_2 - energy_1) * (1.0f / temp_1 - 1.0f / temp_2);
+    int accepted = delta >= log_rand;
+    if (accepted) {
+        int64_t t = system_ids[temp_id];
+        system_ids[temp_id] = system_ids[temp_id + 1];
+        system_ids[temp_id + 1] = t;
+    }
+    return accepted;
+}
+
+static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, real_result *res,
+                            uint32_t sweep0, uint32_t pt_event0) {
+    realization *re = &sim->reals[ridx];
+    const orc_lattice *lat = sim->lat;
+    int T = sim->n_temps, R = sim->n_replicas, S = T * R, z = lat->n_neighbors;
+    int64_t N = lat->n_spins;
+    int n_pairs = R / 2;
+    int64_t bins = N + 1;
+    int philox = sim->rng_mode != ORC_RNG_XOSHIRO;
+    int msc = sim->rng_mode == ORC_RNG_PHILOX_MSC;
+    /* MSC layout: the 32 samples of a word share one key (RNG-SPEC) */
+    uint64_t sweep_key = msc ? orc_splitmix64(sim->cur_seed ^ orc_splitmix64(ORC_MSC_KEY_DOMAIN ^ (uint64_t)(ridx >> 5)))
+                             : re->base_seed;
+
+    /* simulation/mod.rs:190-198: lookup only for Metropolis (reference); the Philox modes also use the
+     * integer heat-bath table for +-J Gibbs (identical decisions to the log form on the 24-bit grid). */
+    uint32_t *table = NULL;
+    if (!cfg->force_log_form && (cfg->sweep_mode == ORC_SWEEP_METROPOLIS || philox))
+        table = build_table(re->couplings, N * z, re->temperatures, S, z, cfg->sweep_mode);
+
+    double *s_m = calloc((size_t)T * 5, sizeof(double));
+    double *s_m2 = s_m + T, *s_m4 = s_m + 2 * T, *s_e = s_m + 3 * T, *s_e2 = s_m + 4 * T;
+    int64_t stat_count = 0;
+    double *s_ov = calloc((size_t)T * 6 + 1, sizeof(double));
+    int64_t ov_count = 0;
+    int64_t *msums = calloc((size_t)S + 1, sizeof(int64_t));
+    uint32_t pt_event = pt_event0;
+
+    for (int64_t sweep_id = 0; sweep_id < cfg->n_sweeps; sweep_id++) {
+        int record = sweep_id >= cfg->warmup_sweeps; /* mod.rs:410 */
+        uint32_t sweep_index = sweep0 + (uint32_t)sweep_id;
+
+        /* mod.rs:412-432 */
+        if (!philox) {
+            int z_ = z, offset = 2 * z_, width = 4 * z_ + 1;
+            for (int slot = 0; slot < S; slot++) {
+                int64_t sys = re->system_ids[slot];
+                int8_t *s = re->spins + sys * N;
+                uint64_t *rng = re->rngs + sys * 4;
+                const uint32_t *row = table ? table + (size_t)slot * width : NULL;
+                for (int64_t i = 0; i < N; i++) {
+                    float h = local_field(lat, s, re->couplings, i);
+                    attempt(s, i, h, xo_draw24(rng), re->temperatures[slot], cfg->sweep_mode, row, offset);
+                }
+            }
+        } else {
+            sweep_philox_impl(lat, re->spins, re->couplings, re->temperatures, re->system_ids, S, sim->colour,
+                              sim->order, sim->rank, sweep_key, sweep_index, cfg->sweep_mode, table, msc);
+        }
+
+        int pt_this_sweep = cfg->pt_interval > 0 && sweep_id % cfg->pt_interval == 0; /* mod.rs:486-488 */
+
+        /* mod.rs:492-509 */
+        if (record || pt_this_sweep) orc_energies_mags(lat, re->spins, re->couplings, S, re->energies, record ? msums : NULL);
+
+        /* mod.rs:527-529 -> statistics/overlap.rs:251-333 (system_ids BEFORE this sweep's PT) */
+        if (record && n_pairs > 0) {
+            for (int p = 0; p < n_pairs; p++) {
+                for (int t = 0; t < T; t++) {
+                    int64_t sa = re->system_ids[(2 * p) * T + t];
+                    int64_t sb = re->system_ids[(2 * p + 1) * T + t];
+                    int64_t dot_spin, dot_link;
+                    orc_overlap_dots(lat, re->spins + sa * N, re->spins + sb * N, &dot_spin, &dot_link);
+                    float ql = (float)dot_link / (float)(N * z);
+                    float q = (float)dot_spin / (float)N;
+                    float q2 = q * q;
+                    float ql2 = ql * ql;
+                    s_ov[0 * T + t] += (double)q;
+                    s_ov[1 * T + t] += (double)q2;
+                    s_ov[2 * T + t] += (double)(q2 * q2);
+                    s_ov[3 * T + t] += (double)ql;
+                    s_ov[4 * T + t] += (double)ql2;
+                    s_ov[5 * T + t] += (double)(ql2 * ql2);
+                    int64_t idx = (dot_spin + N) / 2;
+                    res->hist[t * bins + idx] += 1;
+                    res->ql[t * bins + idx] += (double)ql;
+                    res->ql2[t * bins + idx] += (double)(ql * ql);
+                }
+                ov_count++;
+            }
+        }
+
+        /* mod.rs:543-578 + statistics/stats.rs:17-27 */
+        if (record) {
+            for (int r = 0; r < R; r++) {
+                for (int t = 0; t < T; t++) {
+                    int64_t sys = re->system_ids[r * T + t];
+                    float mag = (float)msums[sys] / (float)N;
+                    float m2 = mag * mag;
+                    float m4 = m2 * m2;
+                    float e = re->energies[sys];
+                    s_m[t] += (double)mag;
+                    s_m2[t] += (double)m2;
+                    s_m4[t] += (double)m4;
+                    s_e[t] += (double)e;
+                    s_e2[t] += (double)e * (double)e; /* powi(2) in f64 */
+                }
+                stat_count++;
+            }
+        }
+
+        /* mod.rs:748-796 */
+        if (pt_this_sweep) {
+            int first_parity = re->pt.next_parity;
+            for (int r = 0; r < R; r++) {
+                int off = r * T;
+                int64_t *sid = re->system_ids + off;
+                const float *tsl = re->temperatures + off;
+                if (T < 2) continue;
+                if (cfg->pt_schedule == ORC_PT_SINGLE_RANDOM_EDGE) {
+                    int edge; float log_rand;
+                    if (!philox) { /* tempering.rs:33, :89 with rngs[offset] (mod.rs:779) */
+                        uint64_t *rng = re->rngs + (size_t)off * 4;
+                        edge = (int)xo_gen_range_usize(rng, 0, (uint64_t)(T - 1));
+                        log_rand = logf(u24_to_f32(xo_draw24(rng)));
+                    } else { /* RNG-SPEC PT domain */
+                        uint32_t ctr[4] = {0xFFFFFFFFu, pt_event, (uint32_t)r, ORC_TAG_PT};
+                        uint32_t k[2] = {(uint32_t)re->base_seed, (uint32_t)(re->base_seed >> 32)}, o[4];
+                        orc_philox4x32_10(ctr, k, o);
+                        edge = (int)(((uint64_t)o[1] * (uint64_t)(T - 1)) >> 32);
+                        log_rand = logf(u24_to_f32(o[0] >> 8));
+                    }
+                    int64_t left, right;
+                    int acc = attempt_edge(re->energies, tsl, sid, N, log_rand, edge, &left, &right);
+                    pt_record_attempt(&re->pt, edge, acc, left, right);
+                } else {
+                    int parities[2] = {first_parity, 1 - first_parity};
+                    for (int pi = 0; pi < 2; pi++)
+                        for (int edge = parities[pi]; edge < T - 1; edge += 2) {
+                            float log_rand;
+                            if (!philox) {
+                                log_rand = logf(u24_to_f32(xo_draw24(re->rngs + (size_t)off * 4)));
+                            } else {
+                                uint32_t ctr[4] = {(uint32_t)edge, pt_event, (uint32_t)r, ORC_TAG_PT};
+                                uint32_t k[2] = {(uint32_t)re->base_seed, (uint32_t)(re->base_seed >> 32)}, o[4];
+                                orc_philox4x32_10(ctr, k, o);
+                                log_rand = logf(u24_to_f32(o[0] >> 8));
+                            }
+                            int64_t left, right;
+                            int acc = attempt_edge(re->energies, tsl, sid, N, log_rand, edge, &left, &right);
+                            pt_record_attempt(&re->pt, edge, acc, left, right);
+                        }
+                }
+            }
+            if (cfg->pt_schedule == ORC_PT_FULL_LADDER) re->pt.next_parity = 1 - re->pt.next_parity; /* mod.rs:793-795 */
+            pt_event++;
+        }
+    }
+
+    /* statistics/stats.rs:29-35: average = aggregate / count (aggregate itself if count == 0) */
+    double c = stat_count > 0 ? (double)stat_count : 1.0;
+    for (int t = 0; t < T; t++) {
+        res->mags[t] = s_m[t] / c; res->mags2[t] = s_m2[t] / c; res->mags4[t] = s_m4[t] / c;
+        res->energies[t] = s_e[t] / c; res->energies2[t] = s_e2[t] / c;
+    }
+    double oc = ov_count > 0 ? (double)ov_count : 1.0;
+    for (int k = 0; k < 6; k++)
+        for (int t = 0; t < T; t++) res->ov[k][t] = s_ov[k * T + t] / oc;
+    free(s_m); free(s_ov); free(msums); free(table);
+}
+
+typedef struct {
+    orc_sim *sim;
+    const orc_config *cfg;
+    real_result *rr;
+    uint32_t sweep0, pt0;
+    int64_t D;
+    int64_t next; /* dynamic schedule: one realization per grab */
+} worker_ctx;
+
+static void *worker_main(void *arg) {
+    worker_ctx *ctx = arg;
+    for (;;) {
+        int64_t d = __atomic_fetch_add(&ctx->next, 1, __ATOMIC_RELAXED);
+        if (d >= ctx->D) break;
+        run_realization(ctx->sim, d, ctx->cfg, &ctx->rr[d], ctx->sweep0, ctx->pt0);
+    }
+    return NULL;
+}
+
+/* config.rs:180-247 (hot-path subset) */
+static int validate(const orc_config *cfg) {
+    if (cfg->n_sweeps < 1) { set_err("n_sweeps must be >= 1"); return -1; }
+    if (cfg->warmup_sweeps > cfg->n_sweeps) { set_err("warmup_sweeps must be <= n_sweeps"); return -1; }
+    if (cfg->pt_interval < 0) { set_err("pt_interval must be >= 1"); return -1; }
+    return 0;
+}
+
+/* simulation/mod.rs:865-939 + statistics/results.rs:165-180, 250-259 + statistics/overlap.rs:106-152 */
+int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
+    if (validate(cfg) != 0) return -1;
+    int T = sim->n_temps, R = sim->n_replicas;
+    int64_t N = sim->lat->n_spins, bins = N + 1, D = sim->n_real;
+    int n_pairs = R / 2;
+    real_result *rr = calloc((size_t)D, sizeof(real_result));
+    for (int64_t d = 0; d < D; d++) {
+        rr[d].mags = calloc((size_t)T * 11 + 1, sizeof(double));
+        rr[d].mags2 = rr[d].mags + T; rr[d].mags4 = rr[d].mags + 2 * T;
+        rr[d].energies = rr[d].mags + 3 * T; rr[d].energies2 = rr[d].mags + 4 * T;
+        for (int k = 0; k < 6; k++) rr[d].ov[k] = rr[d].mags + (5 + k) * T;
+        if (n_pairs > 0) {
+            if (out->ps_hist) {
+                rr[d].hist = out->ps_hist + (size_t)d * T * bins;
+                rr[d].ql = out->ps_ql_at_q_sum + (size_t)d * T * bins;
+                rr[d].ql2 = out->ps_ql2_at_q_sum + (size_t)d * T * bins;
+                memset(rr[d].hist, 0, sizeof(uint64_t) * (size_t)T * bins);
+                memset(rr[d].ql, 0, sizeof(double) * (size_t)T * bins);
+                memset(rr[d].ql2, 0, sizeof(double) * (size_t)T * bins);
+            } else {
+                rr[d].hist = calloc((size_t)T * bins, sizeof(uint64_t));
+                rr[d].ql = calloc((size_t)T * bins, sizeof(double));
+                rr[d].ql2 = calloc((size_t)T * bins, sizeof(double));
+            }
+        }
+    }
+    uint32_t sweep0 = sim->sweep_counter, pt0 = sim->pt_event_counter;
+    /* mod.rs:887-903: threads over realizations (rayon par_iter_mut there; pthreads here) */
+    int nthreads = cfg->n_threads > 1 ? cfg->n_threads : 1;
+    if (nthreads > D) nthreads = (int)D;
+    worker_ctx ctx = {sim, cfg, rr, sweep0, pt0, D, 0};
+    if (nthreads <= 1) {
+        worker_main(&ctx);
+    } else {
+        pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
+        for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, worker_main, &ctx);
+        for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+        free(th);
+    }
+
+    sim->sweep_counter += (uint32_t)cfg->n_sweeps;
+    if (cfg->pt_interval > 0) sim->pt_event_counter += (uint32_t)((cfg->n_sweeps + cfg->pt_interval - 1) / cfg->pt_interval);
+
+    /* results.rs:165-180 then :250-259: sum over realizations in order, divide by D */
+    double n = (double)D;
+    double *dst[5] = {out->mags, out->mags2, out->mags4, out->energies, out->energies2};
+    for (int k = 0; k < 5; k++) {
+        for (int t = 0; t < T; t++) dst[k][t] = 0.0;
+        for (int64_t d = 0; d < D; d++)
+            for (int t = 0; t < T; t++) dst[k][t] += rr[d].mags[k * T + t];
+        for (int t = 0; t < T; t++) dst[k][t] /= n;
+    }
+    if (n_pairs > 0) {
+        double *od[6] = {out->overlap, out->overlap2, out->overlap4, out->link_overlap, out->link_overlap2,
+                         out->link_overlap4};
+        for (int k = 0; k < 6; k++) {
+            for (int t = 0; t < T; t++) od[k][t] = 0.0;
+            for (int64_t d = 0; d < D; d++)
+                for (int t = 0; t < T; t++) od[k][t] += rr[d].ov[k][t];
+            for (int t = 0; t < T; t++) od[k][t] /= n;
+        }
+        memset(out->hist, 0, sizeof(uint64_t) * (size_t)T * bins);
+        memset(out->ql_at_q_sum, 0, sizeof(double) * (size_t)T * bins);
+        memset(out->ql2_at_q_sum, 0, sizeof(double) * (size_t)T * bins);
+        for (int64_t d = 0; d < D; d++)
+            for (int64_t i = 0; i < (int64_t)T * bins; i++) {
+                out->hist[i] += rr[d].hist[i];
+                out->ql_at_q_sum[i] += rr[d].ql[i];
+                out->ql2_at_q_sum[i] += rr[d].ql2[i];
+            }
+    }
+    if (out->edge_attempts) {
+        int n_edges = T > 0 ? T - 1 : 0;
+        for (int64_t d = 0; d < D; d++) {
+            memcpy(out->edge_attempts + d * n_edges, sim->reals[d].pt.edge_attempts, sizeof(uint64_t) * (size_t)n_edges);
+            memcpy(out->edge_acceptances + d * n_edges, sim->reals[d].pt.edge_acceptances, sizeof(uint64_t) * (size_t)n_edges);
+            memcpy(out->round_trips + d * R * T, sim->reals[d].pt.round_trips, sizeof(uint64_t) * (size_t)R * T);
+        }
+    }
+    for (int64_t d = 0; d < D; d++) {
+        free(rr[d].mags);
+        if (n_pairs > 0 && !out->ps_hist) { free(rr[d].hist); free(rr[d].ql); free(rr[d].ql2); }
+    }
+    free(rr);
+    return 0;
+}

@@ -1,0 +1,158 @@
+/*
+ * pp_oracle.h — CPU oracle for the peapods spin-sim sweep path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's
+ * (PeaBrane/peapods v0.2.1, Rust) single-spin-flip sweep engine.  It is the
+ * checker the CUDA path is compared against and the CPU baseline bench.py
+ * times; nothing under peapods_b200/ may link, import or call it.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/).
+ *
+ * Parity status
+ *   pinned   : lattice tables, energy/magnetisation, LUT cut-offs, PT edge order,
+ *              round-trip counter, seeding replay — against the reference's own
+ *              KATs (geometry/lattice.rs:116-184, spins/energy.rs:117-147,
+ *              mcmc/sweep.rs:346-380, mcmc/tempering.rs:110-138,
+ *              simulation/realization.rs:267-302).
+ *   unpinned : the raw xoshiro256** / rand-0.8.5 stream ("parity unpinned":
+ *              rand 0.8.5, rand_core 0.6.4, rand_xoshiro 0.6.0 are not vendored
+ *              under /root/reference and no reference test records a raw draw
+ *              or a golden spin configuration).  xoshiro256** itself is checked
+ *              against its authors' published vector; rand's adaptor semantics
+ *              are restated from the crate's documented algorithm.
+ *
+ * Two visit-order / RNG modes:
+ *   ORC_RNG_XOSHIRO     reference-faithful: typewriter order, one xoshiro256**
+ *                       stream per system (mcmc/sweep.rs:51-97, parallel.rs:27-33).
+ *   ORC_RNG_PHILOX      the build's deterministic contract (RNG-SPEC):
+ *                       colour classes ascending, counter-based Philox4x32-10
+ *                       keyed by (seed, sweep, site-rank, stream); per-site
+ *                       arithmetic and acceptance rule are the reference's.
+ *   ORC_RNG_PHILOX_MSC  as PHILOX but one draw shared by the 32 disorder samples
+ *                       of a multispin word (stream = replica*T + slot).
+ */
+#ifndef PP_ORACLE_H
+#define PP_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_DIMS 8
+
+enum { ORC_RNG_XOSHIRO = 0, ORC_RNG_PHILOX = 1, ORC_RNG_PHILOX_MSC = 2 };
+enum { ORC_SWEEP_METROPOLIS = 0, ORC_SWEEP_GIBBS = 1 };
+enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
+
+/* RNG-SPEC domain tags (counter word 3; low 16 bits carry the colour). */
+#define ORC_TAG_INIT      0x00010000u
+#define ORC_TAG_SWEEP     0x00020000u
+#define ORC_TAG_PT        0x00030000u
+#define ORC_TAG_SWEEP_MSC 0x00040000u
+#define ORC_MSC_KEY_DOMAIN 0x6D73635F67726F75ull
+
+typedef struct orc_lattice orc_lattice;
+typedef struct orc_sim orc_sim;
+
+typedef struct {
+    int64_t n_sweeps;
+    int64_t warmup_sweeps;
+    int32_t sweep_mode;   /* ORC_SWEEP_* */
+    int64_t pt_interval;  /* 0 = no parallel tempering */
+    int32_t pt_schedule;  /* ORC_PT_* */
+    int32_t n_threads;    /* threads over realizations (<=1: sequential) */
+    int32_t force_log_form; /* 1: never use the +-J lookup (test of LUT == log form) */
+} orc_config;
+
+typedef struct {
+    /* f64[T] each */
+    double *mags, *mags2, *mags4, *energies, *energies2;
+    /* f64[T] each; only written when n_replicas >= 2 */
+    double *overlap, *overlap2, *overlap4, *link_overlap, *link_overlap2, *link_overlap4;
+    /* [T][N+1]; summed over realizations */
+    uint64_t *hist;
+    double *ql_at_q_sum, *ql2_at_q_sum;
+    /* [D][T][N+1]; may be NULL */
+    uint64_t *ps_hist;
+    double *ps_ql_at_q_sum, *ps_ql2_at_q_sum;
+    /* [D][T-1], [D][T-1], [D][R][T]; may be NULL */
+    uint64_t *edge_attempts, *edge_acceptances, *round_trips;
+} orc_results;
+
+/* ---- RNG primitives ---------------------------------------------------- */
+uint64_t orc_splitmix64(uint64_t v);                       /* realization.rs:9-15 */
+uint64_t orc_child_seed(uint64_t root, uint64_t domain, uint64_t index); /* realization.rs:17-19 */
+uint64_t orc_realization_seed(uint64_t root, uint64_t r);  /* src/lib.rs:30-32 */
+void orc_xoshiro_seed_from_u64(uint64_t s[4], uint64_t seed);
+uint64_t orc_xoshiro_next_u64(uint64_t s[4]);
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint32_t orc_draw24(uint64_t key, uint32_t c0_index, uint32_t c1, uint32_t c2, uint32_t c3);
+
+/* ---- lattice (geometry/lattice.rs:44-109) ------------------------------ */
+orc_lattice *orc_lattice_new(int n_dims, const int64_t *shape, int n_offsets,
+                             const int64_t *offsets /* NULL: hypercubic */);
+void orc_lattice_free(orc_lattice *lat);
+int64_t orc_lattice_n_spins(const orc_lattice *lat);
+int orc_lattice_n_neighbors(const orc_lattice *lat);
+int64_t orc_lattice_stride(const orc_lattice *lat, int d);
+uint32_t orc_neighbor_fwd(const orc_lattice *lat, int64_t i, int d);
+uint32_t orc_neighbor_bwd(const orc_lattice *lat, int64_t i, int d);
+/* 1 iff no site shares a colour with any of its 2z' neighbours */
+int orc_colouring_is_valid(const orc_lattice *lat, const uint16_t *colour);
+
+/* ---- acceptance tables (mcmc/sweep.rs:99-167) -------------------------- */
+/* returns 0 and fills table[n_temps*(4z'+1)] iff eligible, else -1 (fail closed) */
+int orc_metropolis_lookup(const float *couplings, int64_t n_couplings, const float *temps,
+                          int n_temps, int n_neighbors, uint32_t *table);
+uint32_t orc_metropolis_accepted_count(float temperature, int32_t energy_change);
+int orc_metropolis_legacy_accepts(float temperature, int32_t energy_change, uint32_t draw);
+/* heat-bath analogue for integer fields: #{draw : ec >= (T/2) ln(u/(1-u))} */
+uint32_t orc_gibbs_accepted_count(float temperature, int32_t energy_change);
+int orc_gibbs_legacy_accepts(float temperature, int32_t energy_change, uint32_t draw);
+
+/* ---- operator-level restatements --------------------------------------- */
+/* spins/energy.rs:78-110: e[sys] = (sum_i sum_d s_i s_fwd J)/N (f32 sequential), M = sum s_i */
+void orc_energies_mags(const orc_lattice *lat, const int8_t *spins, const float *couplings,
+                       int64_t n_systems, float *energies, int64_t *mags /* may be NULL */);
+/* statistics/overlap.rs:259-281: integer dots for one (a, b) configuration pair */
+void orc_overlap_dots(const orc_lattice *lat, const int8_t *spins_a, const int8_t *spins_b,
+                      int64_t *dot_spin, int64_t *dot_link);
+/* mcmc/sweep.rs:220-284 with xoshiro streams in typewriter order. rng_states: u64[S][4] */
+void orc_sweep_xoshiro(const orc_lattice *lat, int8_t *spins, const float *couplings,
+                       const float *temperatures, const int64_t *system_ids, int64_t n_systems,
+                       uint64_t *rng_states, int sweep_mode, int use_lookup);
+/* same per-site arithmetic, colour order + Philox draws (RNG-SPEC).
+ * stream_is_slot = 0: stream id = system id (int8 layout); 1: stream id = slot (MSC layout) */
+void orc_sweep_philox(const orc_lattice *lat, int8_t *spins, const float *couplings,
+                      const float *temperatures, const int64_t *system_ids, int64_t n_systems,
+                      const uint16_t *colour, uint64_t key, uint32_t sweep_index,
+                      int sweep_mode, int use_lookup, int stream_is_slot);
+/* mcmc/tempering.rs:45-70: order in which full-ladder attempts edges */
+int orc_full_ladder_edges(int n_temps, int first_parity, int32_t *edges_out);
+
+/* simulation/realization.rs:73-120 replayed over a caller-supplied attempt list */
+void orc_pt_replay(int n_replicas, int n_temps, const float *temps, int n_attempts, const int32_t *edges,
+                   const int32_t *accepted, const int64_t *left, const int64_t *right,
+                   uint64_t *edge_attempts, uint64_t *edge_acceptances, uint64_t *round_trips);
+
+/* ---- full simulation (simulation/mod.rs:405-796, 865-939) -------------- */
+orc_sim *orc_sim_new(int n_dims, const int64_t *shape, int n_offsets, const int64_t *offsets,
+                     const float *couplings, int64_t n_realizations, const float *temps,
+                     int n_temps, int n_replicas, uint64_t seed, int rng_mode,
+                     const uint16_t *colour /* required for PHILOX modes */);
+void orc_sim_free(orc_sim *sim);
+void orc_sim_reset(orc_sim *sim, int has_seed, uint64_t seed); /* src/lib.rs:624-633 */
+/* 0 ok; -1 invalid config (message via orc_last_error) */
+int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out);
+const int8_t *orc_sim_spins(const orc_sim *sim, int64_t realization);       /* [S*N] */
+const int64_t *orc_sim_system_ids(const orc_sim *sim, int64_t realization); /* [S] */
+const float *orc_sim_energies(const orc_sim *sim, int64_t realization);     /* [S] by system */
+const char *orc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

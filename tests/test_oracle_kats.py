@@ -1,0 +1,285 @@
+"""T0: the oracle against every known-answer test the reference holds for the hot path
+(SURVEY.md §4 / §8c).  Each test cites the reference test it re-expresses."""
+import numpy as np
+import pytest
+
+F24 = 1 << 24
+
+
+# ---------------------------------------------------------------- RNG primitives
+def test_splitmix64_first_output(oracle):
+    # published first output of SplitMix64 seeded with 0 (Vigna's reference code)
+    assert oracle.lib().orc_splitmix64(0) == 0xE220A8397B1DCDAF
+
+
+def test_xoshiro256starstar_published_vector(oracle):
+    # authors' vector, state {1,2,3,4} (also rand_xoshiro's own unit test for this generator)
+    s = np.array([1, 2, 3, 4], dtype=np.uint64)
+    got = [oracle.lib().orc_xoshiro_next_u64(s.ctypes.data) for _ in range(10)]
+    assert got == [
+        11520, 0, 1509978240, 1215971899390074240, 1216172134540287360,
+        607988272756665600, 16172922978634559625, 8476171486693032832,
+        10595114339597558777, 2904607092377533576,
+    ]
+
+
+def test_philox4x32_10_random123_kats(oracle):
+    # Random123 kat_vectors: philox4x32 10 rounds
+    assert oracle.philox4x32_10([0, 0, 0, 0], [0, 0]).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = 0xFFFFFFFF
+    assert oracle.philox4x32_10([f, f, f, f], [f, f]).tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert oracle.philox4x32_10([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]).tolist() == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_draw24_serves_four_indices_per_call(oracle):
+    key = 0x0123456789ABCDEF
+    out = oracle.philox4x32_10([5, 7, 9, oracle.TAG_SWEEP | 1], [key & 0xFFFFFFFF, key >> 32])
+    for lane in range(4):
+        assert oracle.lib().orc_draw24(key, 20 + lane, 7, 9, oracle.TAG_SWEEP | 1) == int(out[lane]) >> 8
+
+
+# ---------------------------------------------------------------- lattice (geometry/lattice.rs:116-184)
+def test_2d_neighbors(oracle):
+    lat = oracle.Lattice([3, 4])
+    assert lat.n_spins == 12 and lat.strides() == [4, 1]
+    assert (lat.fwd(0, 0), lat.fwd(0, 1)) == (4, 1)
+    assert (lat.bwd(0, 0), lat.bwd(0, 1)) == (8, 3)
+    assert (lat.fwd(11, 0), lat.fwd(11, 1)) == (3, 8)
+
+
+def test_3d_neighbors(oracle):
+    lat = oracle.Lattice([2, 3, 4])
+    assert lat.n_spins == 24 and lat.strides() == [12, 4, 1]
+    assert [lat.fwd(0, d) for d in range(3)] == [12, 4, 1]
+
+
+def test_triangular_neighbors(oracle):
+    lat = oracle.Lattice([4, 4], [[1, 0], [0, 1], [1, -1]])
+    assert lat.n_neighbors == 3 and lat.n_spins == 16
+    assert [lat.fwd(0, d) for d in range(3)] == [4, 1, 7]
+    assert [lat.bwd(0, d) for d in range(3)] == [12, 3, 13]
+    assert lat.fwd(5, 2) == 8 and lat.bwd(5, 2) == 2
+    assert [lat.fwd(15, d) for d in range(3)] == [3, 12, 2]
+
+
+def test_l2_forward_equals_backward_and_both_are_counted(oracle):
+    # L=2 -> fwd == bwd neighbour, two distinct bonds (sweep.rs:11-17)
+    lat = oracle.Lattice([2, 2])
+    for i in range(4):
+        for d in range(2):
+            assert lat.fwd(i, d) == lat.bwd(i, d)
+
+
+# ---------------------------------------------------------------- energy (spins/energy.rs:117-147)
+def test_energy_and_magnetisation_kat(oracle):
+    lat = oracle.Lattice([2, 3])
+    J = np.ones((6, 2), dtype=np.float32)
+    spins = np.array([[1, 1, 1, 1, 1, 1], [1, -1, 1, -1, 1, -1]], dtype=np.int8)
+    e, m = lat.energies_mags(spins, J)
+    assert m.tolist() == [6, 0]
+    fwd = lat.fwd_table()
+    for r in range(2):
+        inter = [float(spins[r, i]) * float(spins[r, fwd[i, d]]) * 1.0 for i in range(6) for d in range(2)]
+        assert e[r] == np.float32(np.float32(sum(inter)) / np.float32(6))
+    assert e[0] == np.float32(2.0)
+
+
+# ---------------------------------------------------------------- LUT (mcmc/sweep.rs:346-380)
+def test_unit_lookup_is_fail_closed(oracle):
+    ok = oracle.metropolis_lookup
+    assert ok([-1.0, 0.0, 1.0], [0.5, 2.0], 2) is not None
+    assert ok([-2.0, 2.0], [1.0], 2) is None
+    assert ok([-1.0, np.nan], [1.0], 2) is None
+    assert ok([-1.0, 1.0], [0.0], 2) is None
+    assert ok([-1.0, 1.0], [np.frombuffer(np.uint32(1).tobytes(), dtype=np.float32)[0]], 2) is None
+
+
+def test_unit_lookup_cutoffs_match_legacy_boundaries(oracle):
+    temps = np.array([0.7, 2.0, 5.0], dtype=np.float32)
+    table = oracle.metropolis_lookup([-1.0, 0.0, 1.0], temps, 3)
+    L = oracle.lib()
+    for t, temp in enumerate(temps):
+        for ec in range(-6, 7):
+            count = int(table[t, ec + 6])
+            if count > 0:
+                assert L.orc_metropolis_legacy_accepts(temp, ec, count - 1)
+            if count < F24:
+                assert not L.orc_metropolis_legacy_accepts(temp, ec, count)
+            if ec >= 0:
+                assert count == F24
+
+
+def test_lookup_example_row_matches_exp_rule(oracle):
+    # SURVEY §3.2 example: P(accept) = exp(2 ec / T)
+    table = oracle.metropolis_lookup([1.0], [0.8], 3)
+    for ec in range(-6, 1):
+        assert abs(int(table[0, ec + 6]) - F24 * np.exp(2 * ec / np.float32(0.8))) <= 2
+
+
+@pytest.mark.parametrize("temp", [0.5, 1.0, 2.269, 7.5])
+def test_gibbs_counts_match_log_rule_boundaries(oracle, temp):
+    L = oracle.lib()
+    for ec in range(-6, 7):
+        count = L.orc_gibbs_accepted_count(temp, ec)
+        if count > 0:
+            assert L.orc_gibbs_legacy_accepts(temp, ec, count - 1)
+        if count < F24:
+            assert not L.orc_gibbs_legacy_accepts(temp, ec, count)
+        # heat-bath probability 1/(1+exp(-2 ec/T))
+        assert abs(count / F24 - 1.0 / (1.0 + np.exp(-2.0 * ec / temp))) < 1e-6
+
+
+def test_gibbs_rule_is_monotone_on_a_dense_draw_sample(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    for temp, ec in [(1.1, -2), (3.64, 4), (0.9, 0)]:
+        count = L.orc_gibbs_accepted_count(temp, ec)
+        draws = np.concatenate([rng.integers(0, F24, 4000), np.arange(max(count - 300, 0), min(count + 300, F24))])
+        for d in draws:
+            assert bool(L.orc_gibbs_legacy_accepts(temp, ec, int(d))) == (d < count)
+
+
+def _lookup_vs_log(oracle, lat, mode):
+    n = lat.n_spins
+    z = lat.n_neighbors
+    J = np.array([(-1.0, 0.0, 1.0)[i % 3] for i in range(n * z)], dtype=np.float32)
+    temps = np.array([0.7, 2.0, 5.0], dtype=np.float32)
+    sid = [2, 0, 1]
+    init = np.array([-1 if i % 5 == 0 else 1 for i in range(3 * n)], dtype=np.int8).reshape(3, n)
+    if mode == "xoshiro":
+        def rngs():
+            st = np.zeros((3, 4), dtype=np.uint64)
+            for k, seed in enumerate((71, 72, 73)):
+                oracle.lib().orc_xoshiro_seed_from_u64(st[k].ctypes.data, seed)
+            return st
+        a, b, ra, rb = init.copy(), init.copy(), rngs(), rngs()
+        for _ in range(20):
+            lat.sweep_xoshiro(a, J, temps, sid, ra, oracle.SWEEP_METROPOLIS, True)
+            lat.sweep_xoshiro(b, J, temps, sid, rb, oracle.SWEEP_METROPOLIS, False)
+        assert np.array_equal(ra, rb)
+    else:
+        shape = lat.shape
+        colour = (np.indices(tuple(shape)).sum(axis=0) % 2).astype(np.uint16).reshape(-1)
+        assert lat.colouring_is_valid(colour)
+        a, b = init.copy(), init.copy()
+        for sweep in range(20):
+            for sm in (oracle.SWEEP_METROPOLIS, oracle.SWEEP_GIBBS):
+                lat.sweep_philox(a, J, temps, sid, colour, 99, 2 * sweep + sm, sm, use_lookup=True)
+                lat.sweep_philox(b, J, temps, sid, colour, 99, 2 * sweep + sm, sm, use_lookup=False)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, init)
+
+
+def test_unit_lookup_matches_log_with_permuted_systems(oracle):
+    # mcmc/sweep.rs:382-442
+    _lookup_vs_log(oracle, oracle.Lattice([8, 8]), "xoshiro")
+    _lookup_vs_log(oracle, oracle.Lattice([8, 8], [[1, 0], [0, 1]]), "xoshiro")
+
+
+def test_philox_lookup_matches_log_form_metropolis_and_gibbs(oracle):
+    _lookup_vs_log(oracle, oracle.Lattice([8, 8]), "philox")
+    _lookup_vs_log(oracle, oracle.Lattice([4, 6, 4]), "philox")
+
+
+# ---------------------------------------------------------------- PT (mcmc/tempering.rs:110-138)
+def test_full_ladder_attempts_every_edge_in_requested_parity_order(oracle):
+    assert oracle.full_ladder_edges(5, 0) == [0, 2, 1, 3]
+    assert oracle.full_ladder_edges(5, 1) == [1, 3, 0, 2]
+    assert oracle.full_ladder_edges(1, 0) == []
+    assert oracle.full_ladder_edges(2, 1) == [0]
+
+
+def test_tracks_hot_cold_hot_across_attempts(oracle):
+    # simulation/realization.rs:285-302
+    ea, eacc, rt = oracle.pt_replay(1, [0.5, 1.0, 2.0], [(1, True, 1, 2), (0, True, 0, 2), (0, True, 2, 0), (1, True, 2, 1)])
+    assert ea.tolist() == [2, 2] and eacc.tolist() == [2, 2]
+    assert rt[2] == 1 and rt.sum() == 1
+
+
+# ---------------------------------------------------------------- realization (realization.rs:267-283) + interface
+@pytest.mark.parametrize("mode", ["xoshiro", "philox"])
+def test_reset_replays_spins_and_pt_state(oracle, mode):
+    J = np.ones((3, 3, 2), dtype=np.float32)
+    kw = {}
+    if mode == "philox":
+        # 3x3 has odd extents: a proper colouring needs 3 colours, c = (x + y) mod 3
+        kw = dict(rng_mode=oracle.RNG_PHILOX, colour=(np.indices((3, 3)).sum(axis=0) % 3))
+    sim = oracle.Sim([3, 3], J, [1.0, 2.0], n_replicas=2, seed=17, **kw)
+    first = sim.spins()
+    assert set(np.unique(first)) <= {-1, 1}
+    r = sim.sample(3, pt_interval=1, pt_schedule="full_ladder", warmup_ratio=0)
+    assert np.all(r["per_disorder"]["parallel_tempering"]["edge_attempts"] == 6)
+    sim.reset()
+    assert np.array_equal(sim.spins(), first)
+    assert sim.system_ids().tolist() == [0, 1, 2, 3]
+    r = sim.sample(1, pt_interval=1, pt_schedule="full_ladder", warmup_ratio=0)
+    assert np.all(r["per_disorder"]["parallel_tempering"]["edge_attempts"] == 2)
+    sim.reset(seed=99)
+    other = sim.spins()
+    sim.reset(seed=99)
+    assert np.array_equal(sim.spins(), other) and not np.array_equal(other, first)
+
+
+def test_pt_counters_accumulate_across_calls(oracle):
+    # tests/test_sampling_interfaces.py:75-118 (PT part)
+    rng = np.random.default_rng(11)
+    J = (2 * rng.integers(0, 2, size=(4, 4, 2)) - 1).astype(np.float32)
+    sim = oracle.Sim([4, 4], J, [1.0, 2.0, 4.0], n_replicas=2, seed=11)
+    r = sim.sample(2, pt_interval=1, pt_schedule="full_ladder", warmup_ratio=0)
+    pt = r["per_disorder"]["parallel_tempering"]
+    assert pt["edge_attempts"].shape == (1, 2) and np.all(pt["edge_attempts"] == 4)
+    assert pt["round_trips"].shape == (1, 2, 3)
+    r = sim.sample(1, pt_interval=1, pt_schedule="full_ladder", warmup_ratio=0)
+    assert np.all(r["per_disorder"]["parallel_tempering"]["edge_attempts"] == 6)
+
+
+def test_result_keys_shapes_and_disorder_aggregation(oracle):
+    rng = np.random.default_rng(3)
+    J = (2 * rng.integers(0, 2, size=(3, 4, 4, 2)) - 1).astype(np.float32)
+    temps = np.array([1.0, 2.0], dtype=np.float32)
+    sim = oracle.Sim([4, 4], J, temps, n_replicas=2, seed=5)
+    r = sim.sample(8, pt_interval=2, warmup_ratio=0.25)
+    for k in ("mags", "mags2", "mags4", "energies", "energies2", "overlap", "overlap2", "overlap4",
+              "link_overlap", "link_overlap2", "link_overlap4"):
+        assert r[k].shape == (2,) and r[k].dtype == np.float64
+    assert r["overlap_histogram"].shape == (2, 17)
+    assert r["per_sample_overlap_histogram"].shape == (3, 2, 17)
+    # 6 recorded sweeps x 1 pair per sample
+    assert np.all(r["per_sample_overlap_histogram"].sum(axis=2) == 6)
+    assert np.array_equal(r["per_sample_overlap_histogram"].sum(axis=0), r["overlap_histogram"])
+    # disorder mean == mean of single-realization runs (results.rs:165-180, 250-259)
+    singles = [oracle.Sim([4, 4], J[d], temps, n_replicas=2, seed=5) for d in range(3)]
+    # realization seeds differ by index (lib.rs:158-164): rebuild sample d as realization 0 would differ,
+    # so only check the exact arithmetic identity on energies2 >= energies^2 and mags2 bounds here
+    assert np.all(r["energies2"] >= r["energies"] ** 2 - 1e-12)
+    assert np.all((r["mags2"] >= 0) & (r["mags2"] <= 1))
+    del singles
+
+
+def test_threads_do_not_change_results(oracle):
+    rng = np.random.default_rng(8)
+    J = rng.standard_normal((6, 4, 4, 4, 3)).astype(np.float32)
+    temps = np.linspace(0.8, 1.8, 4).astype(np.float32)
+    a = oracle.Sim([4, 4, 4], J, temps, n_replicas=2, seed=1).sample(10, pt_interval=1, n_threads=1)
+    b = oracle.Sim([4, 4, 4], J, temps, n_replicas=2, seed=1).sample(10, pt_interval=1, n_threads=4)
+    for k in a:
+        if k != "per_disorder":
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_invalid_config_is_rejected(oracle):
+    sim = oracle.Sim([4, 4], np.ones((4, 4, 2), np.float32), [2.0])
+    before = sim.spins()
+    with pytest.raises(ValueError, match="n_sweeps must be >= 1"):
+        sim.sample(0)
+    assert np.array_equal(sim.spins(), before)
+
+
+def test_ferromagnet_orders_below_tc_and_not_above(oracle):
+    # physics sanity for the reference-faithful mode: 2-D Ising, T_c = 2.269
+    J = np.ones((16, 16, 2), dtype=np.float32)
+    r = oracle.Sim([16, 16], J, [1.5, 3.5], seed=42).sample(600, warmup_ratio=0.5)
+    assert r["mags2"][0] > 0.9 and r["mags2"][1] < 0.1
+    # exact 2-D energy at T=1.5: e = +sum J s s / N ~ 1.951 (Onsager), sign convention energy.rs:103-108
+    assert abs(r["energies"][0] - 1.951) < 0.01
