@@ -1,0 +1,147 @@
+/*
+ * peapods_b200.h — C ABI of the B200-native spin-sim sweep engine.
+ *
+ * This is the drop-in boundary for the hot path of PeaBrane/peapods v0.2.1
+ * (`spin-sim` single-spin-flip sweeps + parallel tempering + per-sweep energy /
+ * magnetisation / overlap reductions).  Plain pointers and sizes only; every
+ * buffer in a signature is HOST memory owned by the caller, the library copies
+ * what it keeps.  No exceptions cross the boundary: every call returns a
+ * pp_status and pp_last_error() gives the thread-local message.
+ *
+ * Reference interfaces replaced (paths under /root/reference/):
+ *   pp_create        <- IsingSimulation::new          src/lib.rs:106-174
+ *                       (Lattice::new/with_offsets    spin-sim/src/geometry/lattice.rs:31-93,
+ *                        Realization::new             spin-sim/src/simulation/realization.rs:155-210)
+ *   pp_sample        <- IsingSimulation::sample       src/lib.rs:176-333
+ *                       -> run_sweep_parallel         spin-sim/src/simulation/mod.rs:865-939
+ *                       -> run_sweep_loop_impl        spin-sim/src/simulation/mod.rs:405-796
+ *   pp_get_spins     <- IsingSimulation::get_spins    src/lib.rs:620-622
+ *   pp_reset         <- IsingSimulation::reset        src/lib.rs:624-633
+ *   pp_op_sweep      <- metropolis_sweep / gibbs_sweep        spin-sim/src/mcmc/sweep.rs:220-284
+ *   pp_op_energies_mags <- compute_energies_and_magnetizations_into  spin-sim/src/spins/energy.rs:59-76
+ *   pp_op_overlap    <- OverlapAccum::collect (integer dots)  spin-sim/src/statistics/overlap.rs:259-281
+ *   pp_op_pt         <- parallel_tempering(_full_ladder)      spin-sim/src/mcmc/tempering.rs:20-102
+ *   pp_colouring     <- (no reference equivalent: the visit order of the checkerboard sweep)
+ *   pp_metropolis_lookup <- UnitCouplingMetropolisLookup::new spin-sim/src/mcmc/sweep.rs:102-159
+ *
+ * A handle is NOT thread-safe: one caller at a time (the reference takes &mut self).
+ */
+#ifndef PEAPODS_B200_H
+#define PEAPODS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+#define PP_MAX_DIMS 8
+
+typedef enum {
+    PP_OK = 0,
+    PP_ERR_INVALID = 1,     /* bad argument / config (reference: ValueError)            */
+    PP_ERR_UNSUPPORTED = 2, /* valid in the reference, not on this path; nothing mutated */
+    PP_ERR_INTERRUPTED = 3, /* interrupt flag seen (reference: KeyboardInterrupt)        */
+    PP_ERR_CUDA = 4,
+    PP_ERR_NCCL = 5,
+    PP_ERR_OOM = 6
+} pp_status;
+
+enum { PP_SWEEP_METROPOLIS = 0, PP_SWEEP_GIBBS = 1 };              /* config.rs:3-20   */
+enum { PP_PT_SINGLE_RANDOM_EDGE = 0, PP_PT_FULL_LADDER = 1 };      /* config.rs:61-79  */
+enum { PP_LAYOUT_AUTO = 0, PP_LAYOUT_INT8 = 1, PP_LAYOUT_MSC = 2 };
+enum { PP_COUPLINGS_ARRAY = 0, PP_COUPLINGS_FERRO = 1 };
+
+typedef struct pp_sim pp_sim;
+
+/* Constructor arguments (src/lib.rs:106-174). */
+typedef struct {
+    int32_t n_dims;
+    const int64_t *shape;        /* [n_dims] */
+    int32_t n_offsets;           /* 0: hypercubic (Lattice::new) */
+    const int64_t *offsets;      /* [n_offsets][n_dims] forward neighbour offsets, or NULL */
+    int32_t coupling_kind;       /* PP_COUPLINGS_ARRAY: `couplings` given; PP_COUPLINGS_FERRO: all +1, never materialised */
+    const float *couplings;      /* [n_disorder][n_spins][n_neighbors], bond (i,d) owned by the lower site (lattice.rs:4-8) */
+    int64_t n_disorder;          /* realizations held by THIS handle */
+    int64_t sample_offset;       /* global index of this handle's first realization (multi-GPU shard; seeds use global indices) */
+    const float *temperatures;   /* [n_temps] */
+    int32_t n_temps;
+    int32_t n_replicas;
+    uint64_t seed;               /* dynamics seed (lib.rs:155; realization r uses splitmix64(seed ^ splitmix64(r)), lib.rs:30-32) */
+    int32_t layout;              /* PP_LAYOUT_* ; AUTO = MSC when eligible (>=32 realizations, all couplings +-1) */
+    int32_t device;              /* CUDA device ordinal */
+} pp_model_desc;
+
+/* sample() arguments (src/lib.rs:176-284). Zero means "None" for the optional intervals. */
+typedef struct {
+    int64_t n_sweeps;
+    int64_t warmup_sweeps;                   /* caller computes round(n_sweeps*warmup_ratio), lib.rs:219-220 */
+    int32_t sweep_mode;                      /* PP_SWEEP_* */
+    int64_t pt_interval;                     /* 0 = None */
+    int32_t pt_schedule;                     /* PP_PT_* */
+    /* options of the reference that this path does not implement: must be 0, else
+     * PP_ERR_UNSUPPORTED is returned before any state mutation */
+    int64_t cluster_update_interval;
+    int64_t overlap_cluster_update_interval;
+    int64_t autocorrelation_max_lag;
+    int64_t snapshot_interval;
+    int32_t equilibration_diagnostic;
+    /* 1: fp32-coupling / Gibbs log thresholds are read from a host-libm logf table so that spin
+     * trajectories are bit-identical to the CPU rule; 0: device logf (results agree to tolerance) */
+    int32_t exact_log;
+} pp_sample_cfg;
+
+/* Result buffers; every pointer may be NULL (that output is skipped).
+ * Shapes use T = n_temps, R = n_replicas, D = n_disorder of this handle, N = n_spins. */
+typedef struct {
+    double *mags, *mags2, *mags4, *energies, *energies2;                  /* [T]: mean over this handle's realizations */
+    double *overlap, *overlap2, *overlap4;                                /* [T], R >= 2 */
+    double *link_overlap, *link_overlap2, *link_overlap4;                 /* [T], R >= 2 */
+    uint64_t *overlap_histogram;                                          /* [T][N+1] summed over realizations */
+    double *ql_at_q_sum, *ql2_at_q_sum;                                   /* [T][N+1] summed over realizations */
+    uint64_t *per_sample_overlap_histogram;                               /* [D][T][N+1] */
+    double *per_sample_ql_at_q_sum, *per_sample_ql2_at_q_sum;             /* [D][T][N+1] */
+    uint64_t *pt_edge_attempts, *pt_edge_acceptances;                     /* [D][T-1] */
+    uint64_t *pt_round_trips;                                             /* [D][R][T] */
+    double *per_sample_means;  /* [D][11][T]: per-realization averages in the order mags, mags2, mags4, energies,
+                                  energies2, overlap, overlap2, overlap4, link_overlap, link_overlap2, link_overlap4;
+                                  lets a multi-GPU caller do the reference's ordered sum over realizations */
+    double sweep_loop_ms;      /* out: device time of the sweep loop (CUDA events on the launch stream) */
+    int64_t kernel_launches;   /* out: kernels launched by this call */
+} pp_results;
+
+const char *pp_last_error(void);
+int32_t pp_abi_version(void);
+
+/* host-only helpers (no GPU needed) */
+pp_status pp_colouring(int32_t n_dims, const int64_t *shape, int32_t n_offsets, const int64_t *offsets,
+                       uint16_t *colour_out /* [n_spins] */, int32_t *n_colours_out);
+pp_status pp_metropolis_lookup(const float *temperatures, int32_t n_temps, int32_t n_neighbors, int32_t sweep_mode,
+                               uint32_t *table_out /* [n_temps][4*n_neighbors+1] */);
+uint64_t pp_realization_seed(uint64_t root, uint64_t realization);
+
+/* state-owning engine */
+pp_status pp_create(const pp_model_desc *desc, pp_sim **out);
+void pp_destroy(pp_sim *sim);
+pp_status pp_sample(pp_sim *sim, const pp_sample_cfg *cfg, pp_results *out, const volatile int32_t *interrupt,
+                    void (*on_sweep)(void *user, uint64_t sweep_id), void *user);
+pp_status pp_reset(pp_sim *sim, int32_t has_seed, uint64_t seed);
+pp_status pp_get_spins(pp_sim *sim, int64_t realization, int8_t *out /* [S*N], system-major */);
+pp_status pp_get_system_ids(pp_sim *sim, int64_t realization, int64_t *out /* [S] */);
+pp_status pp_get_energies(pp_sim *sim, int64_t realization, float *out /* [S] by system */);
+int32_t pp_get_layout(const pp_sim *sim);
+
+/* operator-level entry points with the reference's slice semantics (unit-level parity tests):
+ * H2D -> kernel -> D2H on the handle's state. */
+pp_status pp_set_spins(pp_sim *sim, int64_t realization, const int8_t *spins /* [S*N] */);
+pp_status pp_set_system_ids(pp_sim *sim, int64_t realization, const int64_t *ids /* [S] */);
+pp_status pp_op_sweep(pp_sim *sim, int32_t sweep_mode, uint32_t sweep_index, int32_t exact_log);
+pp_status pp_op_energies_mags(pp_sim *sim, float *energies /* [D][S] */, int64_t *mags /* [D][S] */);
+pp_status pp_op_overlap(pp_sim *sim, int64_t *dot_spin /* [D][P][T] */, int64_t *dot_link /* [D][P][T] */);
+pp_status pp_op_pt(pp_sim *sim, int32_t pt_schedule, uint32_t pt_event);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

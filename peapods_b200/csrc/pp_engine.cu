@@ -1,0 +1,885 @@
+// pp_engine.cu — C ABI + host driver of the B200 sweep engine (see include/peapods_b200.h).
+//
+// The host driver restates the sequencing of run_sweep_loop_impl
+// (spin-sim/src/simulation/mod.rs:405-432, 486-509, 527-529, 543-578, 748-796): per sweep
+//   sweep -> energies(+mags) if record||pt -> overlap (pre-swap system_ids) if record
+//         -> fold if record -> parallel tempering if pt_this_sweep
+// and enqueues one kernel per step on a single stream; no spin data crosses PCIe during sample().
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/peapods_b200.h"
+#include "pp_device.cuh"
+#include "pp_kernels_int8.cuh"
+#include "pp_kernels_msc.cuh"
+#include "pp_kernels_msc3d.cuh"
+#include "pp_kernels_stats.cuh"
+#include "pp_plan.h"
+
+using namespace pp;
+
+// ------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_last_error;
+static pp_status fail(pp_status st, const std::string &msg) {
+    g_last_error = msg;
+    return st;
+}
+extern "C" const char *pp_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t pp_abi_version(void) { return PP_ABI_VERSION; }
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(_e == cudaErrorMemoryAllocation ? PP_ERR_OOM : PP_ERR_CUDA,                  \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// host-side acceptance tables (mcmc/sweep.rs:141-165 restated with the host libm logf)
+static const uint32_t F24 = 1u << 24;
+
+static bool metropolis_accepts(float temperature, int32_t ec, uint32_t draw) {  // sweep.rs:161-165
+    volatile float uniform = (float)draw / (float)F24;
+    volatile float half_t = temperature / 2.0f;
+    volatile float rhs = half_t * logf(uniform);
+    return (float)ec >= rhs;
+}
+static bool gibbs_accepts(float temperature, int32_t ec, uint32_t draw) {  // sweep.rs:279-282 on the 24-bit grid
+    volatile float u = (float)draw / (float)F24;
+    volatile float one_minus = 1.0f - u;
+    volatile float ratio = u / one_minus;
+    volatile float half_t = temperature / 2.0f;
+    volatile float rhs = half_t * logf(ratio);
+    return (float)ec >= rhs;
+}
+static uint32_t accepted_count(float temperature, int32_t ec, bool gibbs) {  // sweep.rs:147-159
+    uint32_t low = 0, high = F24;
+    while (low < high) {
+        uint32_t mid = low + (high - low) / 2;
+        bool acc = gibbs ? gibbs_accepts(temperature, ec, mid) : metropolis_accepts(temperature, ec, mid);
+        if (acc) low = mid + 1;
+        else high = mid;
+    }
+    return low;
+}
+static bool temps_eligible(const float *t, int n) {  // sweep.rs:114-117
+    for (int i = 0; i < n; i++)
+        if (!(std::isfinite(t[i]) && t[i] / 2.0f > 0.0f)) return false;
+    return true;
+}
+
+extern "C" pp_status pp_metropolis_lookup(const float *temperatures, int32_t n_temps, int32_t n_neighbors,
+                                          int32_t sweep_mode, uint32_t *table_out) {
+    if (!temperatures || !table_out || n_temps < 0 || n_neighbors < 1) return fail(PP_ERR_INVALID, "bad arguments");
+    if (!temps_eligible(temperatures, n_temps))
+        return fail(PP_ERR_INVALID, "temperatures must be finite with T/2 > 0 for the integer lookup");
+    const int off = 2 * n_neighbors, width = 4 * n_neighbors + 1;
+    for (int t = 0; t < n_temps; t++)
+        for (int ec = -off; ec <= off; ec++)
+            table_out[t * width + ec + off] = accepted_count(temperatures[t], ec, sweep_mode == PP_SWEEP_GIBBS);
+    return PP_OK;
+}
+
+extern "C" uint64_t pp_realization_seed(uint64_t root, uint64_t r) { return realization_seed(root, r); }
+
+extern "C" pp_status pp_colouring(int32_t n_dims, const int64_t *shape, int32_t n_offsets, const int64_t *offsets,
+                                  uint16_t *colour_out, int32_t *n_colours_out) {
+    if (!shape) return fail(PP_ERR_INVALID, "shape is NULL");
+    LatticePlan plan;
+    std::string err = build_plan(n_dims, shape, n_offsets, offsets, plan);
+    if (!err.empty()) return fail(PP_ERR_UNSUPPORTED, err);
+    if (colour_out) memcpy(colour_out, plan.colour.data(), sizeof(uint16_t) * (size_t)plan.n_spins);
+    if (n_colours_out) *n_colours_out = plan.n_colours;
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-libm log tables (bit-exact thresholds): logtab[d] = logf(d/2^24), glogtab[d] = logf(u/(1-u))
+struct LogTables {
+    float *logtab = nullptr, *glogtab = nullptr;
+};
+static std::mutex g_tab_mutex;
+static std::map<int, LogTables> g_tabs;
+
+static pp_status get_log_table(int device, bool gibbs, const float **out) {
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    LogTables &lt = g_tabs[device];
+    float *&slot = gibbs ? lt.glogtab : lt.logtab;
+    if (!slot) {
+        std::vector<float> host(F24);
+        unsigned nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (unsigned w = 0; w < nthreads; w++)
+            pool.emplace_back([&, w]() {
+                for (uint32_t d = w; d < F24; d += nthreads) {
+                    volatile float u = (float)d / (float)F24;
+                    if (gibbs) {
+                        volatile float om = 1.0f - u;
+                        volatile float ratio = u / om;
+                        host[d] = logf(ratio);
+                    } else {
+                        host[d] = logf(u);
+                    }
+                }
+            });
+        for (auto &th : pool) th.join();
+        CUDA_TRY(cudaMalloc(&slot, sizeof(float) * (size_t)F24));
+        CUDA_TRY(cudaMemcpy(slot, host.data(), sizeof(float) * (size_t)F24, cudaMemcpyHostToDevice));
+    }
+    *out = slot;
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+struct pp_sim {
+    LatticePlan plan;
+    ModelView mv{};
+    int layout = PP_LAYOUT_INT8;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<float> temps;
+    uint64_t ctor_seed = 0;
+    uint32_t sweep_counter = 0, pt_event_counter = 0;  // RNG-SPEC counters; persist across sample()
+    int next_parity = 0;                               // realization.rs:84-90
+    int64_t G = 0;                                     // word groups (MSC)
+    bool msc3d = false;                                // specialised 3-D hypercubic MSC kernel usable
+    // owned device buffers
+    uint32_t *d_nbr = nullptr, *d_order = nullptr, *d_colour_start = nullptr;
+    int8_t *d_J8 = nullptr;
+    float *d_Jf = nullptr;
+    uint32_t *d_Jw = nullptr;
+    int8_t *d_spins = nullptr;
+    uint32_t *d_words = nullptr, *d_words_alt = nullptr;
+    int32_t *d_sid = nullptr;
+    float *d_energies = nullptr, *d_temps = nullptr;
+    long long *d_mags = nullptr;
+    uint32_t *d_lut_metro = nullptr, *d_lut_gibbs = nullptr;
+    // PT
+    PtView pt{};
+    // stats
+    StatsView st{};
+    long long *d_dot_spin = nullptr, *d_dot_link = nullptr;
+    bool hist_allocated = false;
+    int64_t launches = 0;
+};
+
+static void free_sim(pp_sim *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    void *ptrs[] = {s->d_nbr, s->d_order, s->d_colour_start, s->d_J8, s->d_Jf, s->d_Jw, s->d_spins, s->d_words,
+                    s->d_words_alt, s->d_sid, s->d_energies, s->d_temps, s->d_mags, s->d_lut_metro, s->d_lut_gibbs,
+                    s->pt.edge_attempts, s->pt.edge_acceptances, s->pt.round_trips, s->pt.trip_state, s->pt.swap_mask,
+                    s->st.sums, s->st.hist, s->st.ql_at_q, s->st.ql2_at_q, s->d_dot_spin, s->d_dot_link};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" void pp_destroy(pp_sim *sim) { free_sim(sim); }
+extern "C" int32_t pp_get_layout(const pp_sim *sim) { return sim ? sim->layout : 0; }
+
+// coupling classification: flags[0] non-unit value, flags[1] zero, flags[2] negative
+__global__ void classify_couplings_kernel(const float *J, int64_t n, int *flags) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int f0 = 0, f1 = 0, f2 = 0;
+    for (int64_t i = gid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float c = J[i];
+        if (!(c == -1.0f || c == 0.0f || c == 1.0f)) f0 = 1;  // sweep.rs:110-112 (NaN fails closed)
+        if (c == 0.0f) f1 = 1;
+        if (c < 0.0f) f2 = 1;
+    }
+    if (f0) atomicOr(&flags[0], 1);
+    if (f1) atomicOr(&flags[1], 1);
+    if (f2) atomicOr(&flags[2], 1);
+}
+__global__ void couplings_to_int8_kernel(const float *J, int8_t *out, int64_t n) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) out[gid] = (int8_t)J[gid];
+}
+__global__ void iota_sid_kernel(int32_t *sid, int64_t n, int S) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) sid[gid] = (int32_t)(gid % S);
+}
+__global__ void pt_mark_hot_kernel(ModelView m, PtView pt) {  // realization.rs:64-66
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m.D * m.R) return;
+    int64_t d = gid / m.R;
+    int r = (int)(gid % m.R);
+    pt.trip_state[d * m.S + m.system_ids[d * m.S + r * m.T + pt.hot_slot]] = 1;
+}
+
+static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- kernel launch helpers ------------------------------------------------------------------
+static pp_status launch_energy(pp_sim *s, bool want_mags);
+
+static pp_status launch_sweeps(pp_sim *s, int sweep_mode, uint32_t sweep_index, int n_sweeps, int exact_log,
+                               bool want_energy, bool want_mags) {
+    ModelView m = s->mv;
+    m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
+    if (s->layout == PP_LAYOUT_MSC) {
+        if (s->msc3d && n_sweeps > 0) {
+            pp_status st = launch_msc3d(m, s->stream, sweep_index, n_sweeps, want_energy, want_mags,
+                                        s->mv.sample_offset / 32, &s->launches);
+            if (st != PP_OK) return fail(st, "msc3d launch failed");
+            CUDA_TRY(cudaGetLastError());
+            return PP_OK;
+        }
+        const size_t smem = sizeof(uint32_t) * (size_t)m.N;
+        const unsigned grid = (unsigned)(s->G * m.S);
+        if (smem <= 200 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(msc_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            msc_sweep_kernel<true><<<grid, MSC_BLOCK, smem, s->stream>>>(m, sweep_index, n_sweeps, want_energy, want_mags,
+                                                                        s->mv.sample_offset / 32);
+        } else {
+            msc_sweep_kernel<false><<<grid, MSC_BLOCK, 0, s->stream>>>(m, sweep_index, n_sweeps, want_energy, want_mags,
+                                                                      s->mv.sample_offset / 32);
+        }
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return PP_OK;
+    }
+    for (int sw = 0; sw < n_sweeps; sw++) {
+        for (int c = 0; c < m.n_colours; c++) {
+            const uint32_t nsite = s->plan.colour_start[c + 1] - s->plan.colour_start[c];
+            if (nsite == 0) continue;
+            dim3 grid((unsigned)(m.D * m.S), blocks_for((nsite + 3) / 4, SWEEP_BLOCK));
+            switch (m.coupling_class) {
+                case COUP_FERRO:
+                    sweep_colour_int8_kernel<COUP_FERRO><<<grid, SWEEP_BLOCK, 0, s->stream>>>(m, c, sweep_index + sw, sweep_mode, exact_log);
+                    break;
+                case COUP_UNIT:
+                    sweep_colour_int8_kernel<COUP_UNIT><<<grid, SWEEP_BLOCK, 0, s->stream>>>(m, c, sweep_index + sw, sweep_mode, exact_log);
+                    break;
+                default:
+                    sweep_colour_int8_kernel<COUP_F32><<<grid, SWEEP_BLOCK, 0, s->stream>>>(m, c, sweep_index + sw, sweep_mode, exact_log);
+            }
+            s->launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (want_energy) return launch_energy(s, want_mags);
+    return PP_OK;
+}
+
+static pp_status launch_energy(pp_sim *s, bool want_mags) {
+    ModelView m = s->mv;
+    if (s->layout == PP_LAYOUT_MSC) {
+        m.lut = s->d_lut_metro;
+        return launch_sweeps(s, PP_SWEEP_METROPOLIS, 0, 0, 0, true, want_mags) == PP_OK ? PP_OK : PP_ERR_CUDA;
+    }
+    const unsigned grid = (unsigned)(m.D * m.S);
+    switch (m.coupling_class) {
+        case COUP_FERRO: energy_mag_int8_kernel<COUP_FERRO><<<grid, 256, 0, s->stream>>>(m, want_mags); break;
+        case COUP_UNIT: energy_mag_int8_kernel<COUP_UNIT><<<grid, 256, 0, s->stream>>>(m, want_mags); break;
+        default: energy_mag_int8_kernel<COUP_F32><<<grid, 256, 0, s->stream>>>(m, want_mags);
+    }
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+static pp_status launch_overlap(pp_sim *s) {
+    ModelView m = s->mv;
+    if (m.P == 0) return PP_OK;
+    if (s->layout == PP_LAYOUT_MSC)
+        msc_overlap_kernel<<<(unsigned)(s->G * m.P * m.T), MSC_BLOCK, 0, s->stream>>>(m, s->d_dot_spin, s->d_dot_link);
+    else
+        overlap_dots_int8_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, s->stream>>>(m, s->d_dot_spin, s->d_dot_link);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+static pp_status launch_pt(pp_sim *s, int schedule, uint32_t pt_event) {
+    ModelView m = s->mv;
+    if (m.T < 2) return PP_OK;
+    const bool msc = s->layout == PP_LAYOUT_MSC;
+    if (msc) CUDA_TRY(cudaMemsetAsync(s->pt.swap_mask, 0, sizeof(uint32_t) * (size_t)(s->G * m.R * (m.T - 1)), s->stream));
+    pt_exchange_kernel<<<blocks_for(m.D * m.R, 128), 128, 0, s->stream>>>(m, s->pt, schedule, s->next_parity, pt_event, msc);
+    s->launches++;
+    if (msc) {
+        dim3 grid((unsigned)(s->G * m.R), blocks_for(m.N, 256));
+        msc_apply_swaps_kernel<<<grid, 256, 0, s->stream>>>(m, s->pt.swap_mask, schedule, s->next_parity);
+        s->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (schedule == PP_PT_FULL_LADDER) s->next_parity = 1 - s->next_parity;  // mod.rs:793-795
+    return PP_OK;
+}
+
+// Realization::new / reset (realization.rs:166-207, 213-246) on the device
+static pp_status do_reset(pp_sim *s, uint64_t seed) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    s->mv.seed = seed;
+    s->sweep_counter = 0;
+    s->pt_event_counter = 0;
+    s->next_parity = 0;
+    ModelView m = s->mv;
+    const int64_t DS = m.D * m.S;
+    iota_sid_kernel<<<blocks_for(DS, 256), 256, 0, s->stream>>>(s->d_sid, DS, m.S);
+    if (s->layout == PP_LAYOUT_MSC) {
+        dim3 grid((unsigned)(s->G * m.S), blocks_for((m.N + 3) / 4, 128));
+        msc_init_kernel<<<grid, 128, 0, s->stream>>>(m);
+    } else {
+        dim3 grid((unsigned)DS, blocks_for((m.N + 3) / 4, 128));
+        init_spins_int8_kernel<<<grid, 128, 0, s->stream>>>(m);
+    }
+    CUDA_TRY(cudaGetLastError());
+    pp_status stt = launch_energy(s, false);
+    if (stt != PP_OK) return stt;
+    if (m.T > 1) {
+        CUDA_TRY(cudaMemsetAsync(s->pt.edge_attempts, 0, sizeof(uint64_t) * (size_t)(m.D * (m.T - 1)), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->pt.edge_acceptances, 0, sizeof(uint64_t) * (size_t)(m.D * (m.T - 1)), s->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(s->pt.round_trips, 0, sizeof(uint64_t) * (size_t)DS, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->pt.trip_state, 0, (size_t)DS, s->stream));
+    pt_mark_hot_kernel<<<blocks_for(m.D * m.R, 128), 128, 0, s->stream>>>(m, s->pt);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PP_OK;
+}
+
+extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
+    if (!desc || !out) return fail(PP_ERR_INVALID, "desc/out is NULL");
+    *out = nullptr;
+    if (!desc->shape || !desc->temperatures) return fail(PP_ERR_INVALID, "shape/temperatures is NULL");
+    if (desc->n_temps < 1) return fail(PP_ERR_INVALID, "n_temps must be >= 1");
+    if (desc->n_replicas < 1) return fail(PP_ERR_INVALID, "n_replicas must be >= 1");
+    if (desc->n_disorder < 1) return fail(PP_ERR_INVALID, "n_disorder must be >= 1");
+    if (desc->coupling_kind == PP_COUPLINGS_ARRAY && !desc->couplings) return fail(PP_ERR_INVALID, "couplings is NULL");
+    if ((int64_t)desc->n_temps * desc->n_replicas > (1 << 20)) return fail(PP_ERR_INVALID, "too many systems per realization");
+
+    pp_sim *s = new pp_sim();
+    std::string err = build_plan(desc->n_dims, desc->shape, desc->n_offsets, desc->offsets, s->plan);
+    if (!err.empty()) {
+        delete s;
+        return fail(PP_ERR_UNSUPPORTED, err);
+    }
+    s->device = desc->device;
+    s->ctor_seed = desc->seed;
+    s->temps.assign(desc->temperatures, desc->temperatures + desc->n_temps);
+    ModelView &m = s->mv;
+    m.N = s->plan.n_spins;
+    m.z = s->plan.z;
+    m.T = desc->n_temps;
+    m.R = desc->n_replicas;
+    m.S = m.T * m.R;
+    m.P = m.R / 2;
+    m.D = desc->n_disorder;
+    m.sample_offset = desc->sample_offset;
+    m.n_colours = s->plan.n_colours;
+    m.seed = desc->seed;
+
+#define CREATE_TRY(expr)                                                          \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            std::string msg = std::string(#expr) + ": " + cudaGetErrorString(_e); \
+            free_sim(s);                                                          \
+            return fail(_e == cudaErrorMemoryAllocation ? PP_ERR_OOM : PP_ERR_CUDA, msg); \
+        }                                                                         \
+    } while (0)
+
+    CREATE_TRY(cudaSetDevice(s->device));
+    CREATE_TRY(cudaStreamCreate(&s->stream));
+    CREATE_TRY(cudaEventCreate(&s->ev0));
+    CREATE_TRY(cudaEventCreate(&s->ev1));
+
+    const int64_t N = m.N;
+    const int z = m.z;
+    // geometry tables
+    CREATE_TRY(cudaMalloc(&s->d_nbr, sizeof(uint32_t) * (size_t)N * 2 * z));
+    CREATE_TRY(cudaMemcpy(s->d_nbr, s->plan.nbr.data(), sizeof(uint32_t) * (size_t)N * 2 * z, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&s->d_order, sizeof(uint32_t) * (size_t)N));
+    CREATE_TRY(cudaMemcpy(s->d_order, s->plan.order.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&s->d_colour_start, sizeof(uint32_t) * (size_t)(m.n_colours + 1)));
+    CREATE_TRY(cudaMemcpy(s->d_colour_start, s->plan.colour_start.data(), sizeof(uint32_t) * (size_t)(m.n_colours + 1),
+                          cudaMemcpyHostToDevice));
+    m.nbr = s->d_nbr;
+    m.order = s->d_order;
+    m.colour_start = s->d_colour_start;
+
+    // couplings: classify exactly like the reference's lookup gate (sweep.rs:109-118)
+    const bool t_ok = temps_eligible(s->temps.data(), m.T);
+    const int64_t n_coup = m.D * N * z;
+    int flags[3] = {0, 0, 0};
+    if (desc->coupling_kind == PP_COUPLINGS_FERRO) {
+        if (!t_ok) {
+            free_sim(s);
+            return fail(PP_ERR_UNSUPPORTED, "ferro couplings with non-positive or non-finite temperatures: pass an explicit coupling array");
+        }
+        m.coupling_class = COUP_FERRO;
+    } else {
+        CREATE_TRY(cudaMalloc(&s->d_Jf, sizeof(float) * (size_t)n_coup));
+        CREATE_TRY(cudaMemcpy(s->d_Jf, desc->couplings, sizeof(float) * (size_t)n_coup, cudaMemcpyHostToDevice));
+        int *d_flags = nullptr;
+        CREATE_TRY(cudaMalloc(&d_flags, sizeof(int) * 3));
+        CREATE_TRY(cudaMemset(d_flags, 0, sizeof(int) * 3));
+        classify_couplings_kernel<<<1184, 256, 0, s->stream>>>(s->d_Jf, n_coup, d_flags);
+        CREATE_TRY(cudaStreamSynchronize(s->stream));
+        CREATE_TRY(cudaMemcpy(flags, d_flags, sizeof(int) * 3, cudaMemcpyDeviceToHost));
+        cudaFree(d_flags);
+        if (flags[0] || !t_ok) m.coupling_class = COUP_F32;
+        else if (!flags[1] && !flags[2]) m.coupling_class = COUP_FERRO;
+        else m.coupling_class = COUP_UNIT;
+    }
+
+    // layout
+    const bool msc_ok = m.coupling_class != COUP_F32 && !flags[1] && z <= 7;
+    if (desc->layout == PP_LAYOUT_MSC) {
+        if (!msc_ok) {
+            free_sim(s);
+            return fail(PP_ERR_UNSUPPORTED, "multispin layout needs +-1 couplings (no zeros), eligible temperatures and <= 7 forward directions");
+        }
+        if (desc->sample_offset % 32 != 0) {
+            free_sim(s);
+            return fail(PP_ERR_INVALID, "multispin layout needs sample_offset to be a multiple of 32");
+        }
+        s->layout = PP_LAYOUT_MSC;
+    } else if (desc->layout == PP_LAYOUT_AUTO) {
+        s->layout = (msc_ok && m.D >= 32 && desc->sample_offset % 32 == 0) ? PP_LAYOUT_MSC : PP_LAYOUT_INT8;
+    } else if (desc->layout == PP_LAYOUT_INT8) {
+        s->layout = PP_LAYOUT_INT8;
+    } else {
+        free_sim(s);
+        return fail(PP_ERR_INVALID, "unknown layout");
+    }
+
+    if (s->layout == PP_LAYOUT_MSC) {
+        s->G = (m.D + 31) / 32;
+        if (m.coupling_class == COUP_UNIT) {
+            CREATE_TRY(cudaMalloc(&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
+            msc_pack_couplings_kernel<<<blocks_for(s->G * z * N, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_Jw, m.D, N, z);
+            CREATE_TRY(cudaStreamSynchronize(s->stream));
+        }
+        if (s->d_Jf) { cudaFree(s->d_Jf); s->d_Jf = nullptr; }
+        CREATE_TRY(cudaMalloc(&s->d_words, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
+        s->msc3d = msc3d_supported(s->plan);
+    } else {
+        if (m.coupling_class == COUP_UNIT) {
+            CREATE_TRY(cudaMalloc(&s->d_J8, (size_t)n_coup));
+            couplings_to_int8_kernel<<<blocks_for(n_coup, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_J8, n_coup);
+            CREATE_TRY(cudaStreamSynchronize(s->stream));
+        }
+        if (m.coupling_class != COUP_F32 && s->d_Jf) { cudaFree(s->d_Jf); s->d_Jf = nullptr; }
+        CREATE_TRY(cudaMalloc(&s->d_spins, (size_t)(m.D * m.S * N)));
+    }
+    m.J8 = s->d_J8;
+    m.Jf = s->d_Jf;
+    m.Jw = s->d_Jw;
+    m.spins = s->d_spins;
+    m.words = s->d_words;
+
+    const int64_t DS = m.D * m.S;
+    CREATE_TRY(cudaMalloc(&s->d_sid, sizeof(int32_t) * (size_t)DS));
+    CREATE_TRY(cudaMalloc(&s->d_energies, sizeof(float) * (size_t)DS));
+    CREATE_TRY(cudaMalloc(&s->d_mags, sizeof(long long) * (size_t)DS));
+    CREATE_TRY(cudaMemset(s->d_mags, 0, sizeof(long long) * (size_t)DS));
+    CREATE_TRY(cudaMalloc(&s->d_temps, sizeof(float) * (size_t)m.T));
+    CREATE_TRY(cudaMemcpy(s->d_temps, s->temps.data(), sizeof(float) * (size_t)m.T, cudaMemcpyHostToDevice));
+    m.system_ids = s->d_sid;
+    m.energies = s->d_energies;
+    m.mags = s->d_mags;
+    m.temps = s->d_temps;
+
+    if (m.coupling_class != COUP_F32) {
+        const int width = 4 * z + 1;
+        std::vector<uint32_t> lut((size_t)m.T * width);
+        for (int mode = 0; mode < 2; mode++) {
+            pp_metropolis_lookup(s->temps.data(), m.T, z, mode, lut.data());
+            uint32_t *&dst = mode == 0 ? s->d_lut_metro : s->d_lut_gibbs;
+            CREATE_TRY(cudaMalloc(&dst, sizeof(uint32_t) * lut.size()));
+            CREATE_TRY(cudaMemcpy(dst, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice));
+        }
+    }
+
+    // PT state (realization.rs:21-67)
+    const int n_edges = m.T - 1;
+    CREATE_TRY(cudaMalloc(&s->pt.edge_attempts, sizeof(uint64_t) * (size_t)(m.D * std::max(n_edges, 1))));
+    CREATE_TRY(cudaMalloc(&s->pt.edge_acceptances, sizeof(uint64_t) * (size_t)(m.D * std::max(n_edges, 1))));
+    CREATE_TRY(cudaMalloc(&s->pt.round_trips, sizeof(uint64_t) * (size_t)DS));
+    CREATE_TRY(cudaMalloc(&s->pt.trip_state, (size_t)DS));
+    if (s->layout == PP_LAYOUT_MSC)
+        CREATE_TRY(cudaMalloc(&s->pt.swap_mask, sizeof(uint32_t) * (size_t)(s->G * m.R * std::max(n_edges, 1))));
+    s->pt.cold_slot = s->pt.hot_slot = 0;  // realization.rs:92-107
+    for (int slot = 1; slot < m.T; slot++) {
+        if (s->temps[slot] < s->temps[s->pt.cold_slot]) s->pt.cold_slot = slot;
+        if (s->temps[slot] > s->temps[s->pt.hot_slot]) s->pt.hot_slot = slot;
+    }
+
+    // stats
+    CREATE_TRY(cudaMalloc(&s->st.sums, sizeof(double) * (size_t)(m.D * 11 * m.T)));
+    if (m.P > 0) {
+        CREATE_TRY(cudaMalloc(&s->d_dot_spin, sizeof(long long) * (size_t)(m.D * m.P * m.T)));
+        CREATE_TRY(cudaMalloc(&s->d_dot_link, sizeof(long long) * (size_t)(m.D * m.P * m.T)));
+        s->st.dot_spin = s->d_dot_spin;
+        s->st.dot_link = s->d_dot_link;
+    }
+#undef CREATE_TRY
+    pp_status st = do_reset(s, desc->seed);
+    if (st != PP_OK) {
+        std::string keep = g_last_error;
+        free_sim(s);
+        return fail(st, keep);
+    }
+    *out = s;
+    return PP_OK;
+}
+
+extern "C" pp_status pp_reset(pp_sim *sim, int32_t has_seed, uint64_t seed) {
+    if (!sim) return fail(PP_ERR_INVALID, "sim is NULL");
+    return do_reset(sim, has_seed ? seed : sim->ctor_seed);  // lib.rs:626
+}
+
+// config.rs:180-247 (messages kept: the reference's tests match on them)
+static pp_status validate_cfg(const pp_sample_cfg *c) {
+    if (c->n_sweeps < 1) return fail(PP_ERR_INVALID, "n_sweeps must be >= 1");
+    if (c->warmup_sweeps > c->n_sweeps || c->warmup_sweeps < 0) return fail(PP_ERR_INVALID, "warmup_sweeps must be <= n_sweeps");
+    if (c->pt_interval < 0) return fail(PP_ERR_INVALID, "pt_interval must be >= 1");
+    if (c->sweep_mode != PP_SWEEP_METROPOLIS && c->sweep_mode != PP_SWEEP_GIBBS)
+        return fail(PP_ERR_INVALID, "unknown sweep_mode, expected 'metropolis' or 'gibbs'");
+    if (c->pt_schedule != PP_PT_SINGLE_RANDOM_EDGE && c->pt_schedule != PP_PT_FULL_LADDER)
+        return fail(PP_ERR_INVALID, "unknown pt_schedule, expected 'single_random_edge' or 'full_ladder'");
+    if (c->cluster_update_interval != 0)
+        return fail(PP_ERR_UNSUPPORTED, "cluster updates (cluster_update_interval) are not implemented on the GPU sweep path");
+    if (c->overlap_cluster_update_interval != 0)
+        return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep path");
+    if (c->autocorrelation_max_lag != 0)
+        return fail(PP_ERR_UNSUPPORTED, "autocorrelation_max_lag is not implemented on the GPU sweep path");
+    if (c->snapshot_interval != 0) return fail(PP_ERR_UNSUPPORTED, "snapshot_interval is not implemented on the GPU sweep path");
+    if (c->equilibration_diagnostic != 0)
+        return fail(PP_ERR_UNSUPPORTED, "equilibration_diagnostic is not implemented on the GPU sweep path");
+    return PP_OK;
+}
+
+static pp_status ensure_tables(pp_sim *s, bool need_log, bool need_glog) {
+    if (need_log && !s->mv.logtab) {
+        pp_status st = get_log_table(s->device, false, &s->mv.logtab);
+        if (st != PP_OK) return st;
+    }
+    if (need_glog && !s->mv.glogtab) {
+        pp_status st = get_log_table(s->device, true, &s->mv.glogtab);
+        if (st != PP_OK) return st;
+    }
+    return PP_OK;
+}
+
+static pp_status ensure_hist(pp_sim *s) {
+    if (s->hist_allocated || s->mv.P == 0) return PP_OK;
+    const size_t n = (size_t)s->mv.D * s->mv.T * (s->mv.N + 1);
+    CUDA_TRY(cudaMalloc(&s->st.hist, sizeof(uint32_t) * n));
+    CUDA_TRY(cudaMalloc(&s->st.ql_at_q, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc(&s->st.ql2_at_q, sizeof(double) * n));
+    s->hist_allocated = true;
+    return PP_OK;
+}
+
+extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *out, const volatile int32_t *interrupt,
+                               void (*on_sweep)(void *, uint64_t), void *user) {
+    if (!s || !cfg) return fail(PP_ERR_INVALID, "sim/cfg is NULL");
+    pp_status st = validate_cfg(cfg);  // before any mutation (tests/test_sampling_interfaces.py:145-156)
+    if (st != PP_OK) return st;
+    CUDA_TRY(cudaSetDevice(s->device));
+    ModelView &m = s->mv;
+    const bool f32 = m.coupling_class == COUP_F32;
+    st = ensure_tables(s, cfg->pt_interval > 0 || (f32 && cfg->exact_log && cfg->sweep_mode == PP_SWEEP_METROPOLIS),
+                       f32 && cfg->exact_log && cfg->sweep_mode == PP_SWEEP_GIBBS);
+    if (st != PP_OK) return st;
+    const int64_t n_rec = cfg->n_sweeps - cfg->warmup_sweeps;
+    if (n_rec > 0) {
+        st = ensure_hist(s);
+        if (st != PP_OK) return st;
+    }
+    // fresh accumulators per call (simulation/mod.rs:331-335: Statistics::new per run)
+    CUDA_TRY(cudaMemsetAsync(s->st.sums, 0, sizeof(double) * (size_t)(m.D * 11 * m.T), s->stream));
+    if (s->hist_allocated) {
+        const size_t n = (size_t)m.D * m.T * (m.N + 1);
+        CUDA_TRY(cudaMemsetAsync(s->st.hist, 0, sizeof(uint32_t) * n, s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->st.ql_at_q, 0, sizeof(double) * n, s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->st.ql2_at_q, 0, sizeof(double) * n, s->stream));
+    }
+    const int64_t launches0 = s->launches;
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+
+    const bool msc = s->layout == PP_LAYOUT_MSC;
+    int64_t sweep_id = 0;
+    while (sweep_id < cfg->n_sweeps) {
+        // how many sweeps until (and including) the next one that needs a reduction or PT
+        int64_t batch = 1;
+        if (msc) {
+            while (sweep_id + batch - 1 < cfg->n_sweeps - 1) {
+                const int64_t last = sweep_id + batch - 1;
+                const bool rec = last >= cfg->warmup_sweeps;
+                const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
+                if (rec || ptl || batch >= 64) break;
+                batch++;
+            }
+        }
+        for (int64_t b = 0; b < batch; b++) {
+            if (interrupt && *interrupt) {  // mod.rs:406-408
+                cudaStreamSynchronize(s->stream);
+                return fail(PP_ERR_INTERRUPTED, "interrupted");
+            }
+            if (on_sweep) on_sweep(user, (uint64_t)(sweep_id + b));  // mod.rs:409
+        }
+        const int64_t last = sweep_id + batch - 1;
+        const bool record = last >= cfg->warmup_sweeps;                                   // mod.rs:410
+        const bool pt_this = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;        // mod.rs:486-488
+        st = launch_sweeps(s, cfg->sweep_mode, s->sweep_counter, (int)batch, cfg->exact_log, record || pt_this, record);
+        if (st != PP_OK) return st;
+        s->sweep_counter += (uint32_t)batch;
+        if (record) {
+            st = launch_overlap(s);                                                         // mod.rs:527-529
+            if (st != PP_OK) return st;
+            fold_kernel<<<blocks_for(m.D * m.T, 128), 128, 0, s->stream>>>(m, s->st, m.P > 0);  // mod.rs:543-578
+            s->launches++;
+        }
+        if (pt_this) {                                                                      // mod.rs:748-796
+            st = launch_pt(s, cfg->pt_schedule, s->pt_event_counter);
+            if (st != PP_OK) return st;
+            s->pt_event_counter++;
+        }
+        sweep_id += batch;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    if (!out) return PP_OK;
+    out->sweep_loop_ms = ms;
+    out->kernel_launches = s->launches - launches0;
+
+    // ---- results (statistics/stats.rs:29-35, results.rs:165-180, 250-259, overlap.rs:106-152)
+    const int T = m.T;
+    std::vector<double> sums((size_t)m.D * 11 * T);
+    CUDA_TRY(cudaMemcpy(sums.data(), s->st.sums, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost));
+    const double c_stat = n_rec > 0 ? (double)(n_rec * m.R) : 1.0;
+    const double c_ov = (n_rec > 0 && m.P > 0) ? (double)(n_rec * m.P) : 1.0;
+    for (int64_t d = 0; d < m.D; d++)
+        for (int k = 0; k < 11; k++)
+            for (int t = 0; t < T; t++) sums[((size_t)d * 11 + k) * T + t] /= (k < 5 ? c_stat : c_ov);
+    if (out->per_sample_means) memcpy(out->per_sample_means, sums.data(), sizeof(double) * sums.size());
+    double *dst[11] = {out->mags, out->mags2, out->mags4, out->energies, out->energies2, out->overlap, out->overlap2,
+                       out->overlap4, out->link_overlap, out->link_overlap2, out->link_overlap4};
+    for (int k = 0; k < 11; k++) {
+        if (!dst[k] || (k >= 5 && m.P == 0)) continue;
+        for (int t = 0; t < T; t++) {
+            double acc = 0.0;
+            for (int64_t d = 0; d < m.D; d++) acc += sums[((size_t)d * 11 + k) * T + t];
+            dst[k][t] = acc / (double)m.D;
+        }
+    }
+    if (m.P > 0) {
+        const int64_t per = (int64_t)T * (m.N + 1);
+        if (out->overlap_histogram || out->ql_at_q_sum || out->ql2_at_q_sum) {
+            if (!s->hist_allocated) {
+                if (out->overlap_histogram) memset(out->overlap_histogram, 0, sizeof(uint64_t) * (size_t)per);
+                if (out->ql_at_q_sum) memset(out->ql_at_q_sum, 0, sizeof(double) * (size_t)per);
+                if (out->ql2_at_q_sum) memset(out->ql2_at_q_sum, 0, sizeof(double) * (size_t)per);
+            } else {
+                unsigned long long *d_h = nullptr;
+                double *d_a = nullptr, *d_b = nullptr;
+                CUDA_TRY(cudaMalloc(&d_h, sizeof(uint64_t) * (size_t)per));
+                CUDA_TRY(cudaMalloc(&d_a, sizeof(double) * (size_t)per));
+                CUDA_TRY(cudaMalloc(&d_b, sizeof(double) * (size_t)per));
+                reduce_hist_kernel<<<blocks_for(per, 256), 256, 0, s->stream>>>(m, s->st, d_h, d_a, d_b);
+                CUDA_TRY(cudaStreamSynchronize(s->stream));
+                if (out->overlap_histogram) CUDA_TRY(cudaMemcpy(out->overlap_histogram, d_h, sizeof(uint64_t) * (size_t)per, cudaMemcpyDeviceToHost));
+                if (out->ql_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql_at_q_sum, d_a, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
+                if (out->ql2_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql2_at_q_sum, d_b, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
+                cudaFree(d_h); cudaFree(d_a); cudaFree(d_b);
+            }
+        }
+        const size_t all = (size_t)m.D * per;
+        if (out->per_sample_overlap_histogram) {
+            if (!s->hist_allocated) memset(out->per_sample_overlap_histogram, 0, sizeof(uint64_t) * all);
+            else {
+                const int64_t chunk = std::min<int64_t>((int64_t)all, int64_t(1) << 26);
+                unsigned long long *d_w = nullptr;
+                CUDA_TRY(cudaMalloc(&d_w, sizeof(uint64_t) * (size_t)chunk));
+                for (int64_t off = 0; off < (int64_t)all; off += chunk) {
+                    const int64_t n = std::min<int64_t>(chunk, (int64_t)all - off);
+                    widen_u32_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->st.hist + off, d_w, n);
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    CUDA_TRY(cudaMemcpy(out->per_sample_overlap_histogram + off, d_w, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+                }
+                cudaFree(d_w);
+            }
+        }
+        if (out->per_sample_ql_at_q_sum) {
+            if (!s->hist_allocated) memset(out->per_sample_ql_at_q_sum, 0, sizeof(double) * all);
+            else CUDA_TRY(cudaMemcpy(out->per_sample_ql_at_q_sum, s->st.ql_at_q, sizeof(double) * all, cudaMemcpyDeviceToHost));
+        }
+        if (out->per_sample_ql2_at_q_sum) {
+            if (!s->hist_allocated) memset(out->per_sample_ql2_at_q_sum, 0, sizeof(double) * all);
+            else CUDA_TRY(cudaMemcpy(out->per_sample_ql2_at_q_sum, s->st.ql2_at_q, sizeof(double) * all, cudaMemcpyDeviceToHost));
+        }
+    }
+    if (T > 1) {
+        if (out->pt_edge_attempts)
+            CUDA_TRY(cudaMemcpy(out->pt_edge_attempts, s->pt.edge_attempts, sizeof(uint64_t) * (size_t)(m.D * (T - 1)), cudaMemcpyDeviceToHost));
+        if (out->pt_edge_acceptances)
+            CUDA_TRY(cudaMemcpy(out->pt_edge_acceptances, s->pt.edge_acceptances, sizeof(uint64_t) * (size_t)(m.D * (T - 1)), cudaMemcpyDeviceToHost));
+    }
+    if (out->pt_round_trips)
+        CUDA_TRY(cudaMemcpy(out->pt_round_trips, s->pt.round_trips, sizeof(uint64_t) * (size_t)(m.D * m.S), cudaMemcpyDeviceToHost));
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// state access
+extern "C" pp_status pp_get_spins(pp_sim *s, int64_t r, int8_t *out) {
+    if (!s || !out) return fail(PP_ERR_INVALID, "sim/out is NULL");
+    if (r < 0 || r >= s->mv.D) return fail(PP_ERR_INVALID, "realization index out of range");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const ModelView &m = s->mv;
+    const size_t n = (size_t)m.S * m.N;
+    if (s->layout == PP_LAYOUT_MSC) {
+        int8_t *tmp = nullptr;
+        CUDA_TRY(cudaMalloc(&tmp, n));
+        msc_unpack_kernel<<<blocks_for((int64_t)n, 256), 256, 0, s->stream>>>(m, r, tmp);
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaMemcpy(out, tmp, n, cudaMemcpyDeviceToHost));
+        cudaFree(tmp);
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaMemcpy(out, m.spins + (size_t)r * n, n, cudaMemcpyDeviceToHost));
+    }
+    return PP_OK;
+}
+
+extern "C" pp_status pp_set_spins(pp_sim *s, int64_t r, const int8_t *spins) {
+    if (!s || !spins) return fail(PP_ERR_INVALID, "sim/spins is NULL");
+    if (r < 0 || r >= s->mv.D) return fail(PP_ERR_INVALID, "realization index out of range");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const ModelView &m = s->mv;
+    const size_t n = (size_t)m.S * m.N;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->layout == PP_LAYOUT_MSC) {
+        int8_t *tmp = nullptr;
+        CUDA_TRY(cudaMalloc(&tmp, n));
+        CUDA_TRY(cudaMemcpy(tmp, spins, n, cudaMemcpyHostToDevice));
+        msc_pack_kernel<<<blocks_for((int64_t)n, 256), 256, 0, s->stream>>>(m, r, tmp);
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        cudaFree(tmp);
+    } else {
+        CUDA_TRY(cudaMemcpy(m.spins + (size_t)r * n, spins, n, cudaMemcpyHostToDevice));
+    }
+    return PP_OK;
+}
+
+extern "C" pp_status pp_get_system_ids(pp_sim *s, int64_t r, int64_t *out) {
+    if (!s || !out) return fail(PP_ERR_INVALID, "sim/out is NULL");
+    if (r < 0 || r >= s->mv.D) return fail(PP_ERR_INVALID, "realization index out of range");
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<int32_t> tmp((size_t)s->mv.S);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(tmp.data(), s->d_sid + r * s->mv.S, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); i++) out[i] = tmp[i];
+    return PP_OK;
+}
+
+// With the multispin layout the words are slot-major, so re-labelling slots means moving lanes:
+// unpack with the old labels, store the new labels, pack again.
+extern "C" pp_status pp_set_system_ids(pp_sim *s, int64_t r, const int64_t *ids) {
+    if (!s || !ids) return fail(PP_ERR_INVALID, "sim/ids is NULL");
+    if (r < 0 || r >= s->mv.D) return fail(PP_ERR_INVALID, "realization index out of range");
+    const ModelView &m = s->mv;
+    std::vector<int32_t> tmp((size_t)m.S);
+    std::vector<char> seen((size_t)m.S, 0);
+    for (int k = 0; k < m.S; k++) {
+        // parallel.rs:13-14: each replica's slice must stay a permutation of its own systems
+        if (ids[k] < 0 || ids[k] >= m.S || seen[(size_t)ids[k]] || ids[k] / m.T != k / m.T)
+            return fail(PP_ERR_INVALID, "system_ids must permute the systems of each replica ladder");
+        seen[(size_t)ids[k]] = 1;
+        tmp[(size_t)k] = (int32_t)ids[k];
+    }
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<int8_t> spins;
+    if (s->layout == PP_LAYOUT_MSC) {
+        spins.resize((size_t)m.S * m.N);
+        pp_status st = pp_get_spins(s, r, spins.data());
+        if (st != PP_OK) return st;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(s->d_sid + r * m.S, tmp.data(), sizeof(int32_t) * tmp.size(), cudaMemcpyHostToDevice));
+    if (s->layout == PP_LAYOUT_MSC) return pp_set_spins(s, r, spins.data());
+    return PP_OK;
+}
+
+extern "C" pp_status pp_get_energies(pp_sim *s, int64_t r, float *out) {
+    if (!s || !out) return fail(PP_ERR_INVALID, "sim/out is NULL");
+    if (r < 0 || r >= s->mv.D) return fail(PP_ERR_INVALID, "realization index out of range");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(out, s->d_energies + r * s->mv.S, sizeof(float) * (size_t)s->mv.S, cudaMemcpyDeviceToHost));
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// operator-level entry points
+extern "C" pp_status pp_op_sweep(pp_sim *s, int32_t sweep_mode, uint32_t sweep_index, int32_t exact_log) {
+    if (!s) return fail(PP_ERR_INVALID, "sim is NULL");
+    if (sweep_mode != PP_SWEEP_METROPOLIS && sweep_mode != PP_SWEEP_GIBBS) return fail(PP_ERR_INVALID, "unknown sweep_mode");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const bool f32 = s->mv.coupling_class == COUP_F32;
+    pp_status st = ensure_tables(s, f32 && exact_log && sweep_mode == PP_SWEEP_METROPOLIS, f32 && exact_log && sweep_mode == PP_SWEEP_GIBBS);
+    if (st != PP_OK) return st;
+    st = launch_sweeps(s, sweep_mode, sweep_index, 1, exact_log, false, false);
+    if (st != PP_OK) return st;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PP_OK;
+}
+
+extern "C" pp_status pp_op_energies_mags(pp_sim *s, float *energies, int64_t *mags) {
+    if (!s) return fail(PP_ERR_INVALID, "sim is NULL");
+    CUDA_TRY(cudaSetDevice(s->device));
+    pp_status st = launch_energy(s, true);
+    if (st != PP_OK) return st;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const size_t n = (size_t)s->mv.D * s->mv.S;
+    if (energies) CUDA_TRY(cudaMemcpy(energies, s->d_energies, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (mags) CUDA_TRY(cudaMemcpy(mags, s->d_mags, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+    return PP_OK;
+}
+
+extern "C" pp_status pp_op_overlap(pp_sim *s, int64_t *dot_spin, int64_t *dot_link) {
+    if (!s) return fail(PP_ERR_INVALID, "sim is NULL");
+    if (s->mv.P == 0) return fail(PP_ERR_INVALID, "overlap needs n_replicas >= 2");
+    CUDA_TRY(cudaSetDevice(s->device));
+    pp_status st = launch_overlap(s);
+    if (st != PP_OK) return st;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const size_t n = (size_t)s->mv.D * s->mv.P * s->mv.T;
+    if (dot_spin) CUDA_TRY(cudaMemcpy(dot_spin, s->d_dot_spin, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+    if (dot_link) CUDA_TRY(cudaMemcpy(dot_link, s->d_dot_link, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+    return PP_OK;
+}
+
+extern "C" pp_status pp_op_pt(pp_sim *s, int32_t pt_schedule, uint32_t pt_event) {
+    if (!s) return fail(PP_ERR_INVALID, "sim is NULL");
+    if (pt_schedule != PP_PT_SINGLE_RANDOM_EDGE && pt_schedule != PP_PT_FULL_LADDER) return fail(PP_ERR_INVALID, "unknown pt_schedule");
+    CUDA_TRY(cudaSetDevice(s->device));
+    pp_status st = ensure_tables(s, true, false);
+    if (st != PP_OK) return st;
+    st = launch_pt(s, pt_schedule, pt_event);
+    if (st != PP_OK) return st;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PP_OK;
+}

@@ -1,0 +1,164 @@
+// pp_kernels_stats.cuh — scalar bookkeeping kernels shared by both spin layouts.
+//
+// K8 pt_exchange   <- spin-sim/src/mcmc/tempering.rs:20-102 + PtState simulation/realization.rs:73-120
+// K9 fold          <- spin-sim/src/simulation/mod.rs:543-578 + statistics/stats.rs:17-27
+//    + K7 overlap moments / histogram scatter <- statistics/overlap.rs:283-306, 318-324
+// reduce_hist      <- statistics/overlap.rs:128-142 (sum over realizations, realization order)
+//
+// One thread per (realization, temperature) or (realization, replica) walks its items
+// sequentially so that every f64 accumulation happens in the reference's order.
+#pragma once
+#include "pp_device.cuh"
+
+namespace pp {
+
+struct StatsView {
+    double *sums;          // [D][11][T]: mags, mags2, mags4, energies, energies2, q, q2, q4, ql, ql2, ql4
+    uint32_t *hist;        // [D][T][N+1]
+    double *ql_at_q;       // [D][T][N+1]
+    double *ql2_at_q;      // [D][T][N+1]
+    const long long *dot_spin, *dot_link;  // [D][P][T]
+};
+
+struct PtView {
+    unsigned long long *edge_attempts, *edge_acceptances;  // [D][T-1]
+    unsigned long long *round_trips;                       // [D][S] by system
+    uint8_t *trip_state;                                   // [D][S] by system
+    uint32_t *swap_mask;   // MSC only: [G][R][T-1] lanes whose configurations swap across that edge
+    int cold_slot, hot_slot;
+};
+
+// K9 (+K7): fold one recorded sweep.  One thread per (realization d, temperature t).
+__global__ void fold_kernel(ModelView m, StatsView st, int with_overlap) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m.D * m.T) return;
+    const int64_t d = gid / m.T;
+    const int t = (int)(gid % m.T);
+    const float nf = (float)m.N;
+    double *sums = st.sums + d * 11 * m.T + t;
+    // simulation/mod.rs:555-578: replica-inner order
+    double s0 = sums[0], s1 = sums[1 * m.T], s2 = sums[2 * m.T], s3 = sums[3 * m.T], s4 = sums[4 * m.T];
+    for (int r = 0; r < m.R; r++) {
+        const int sys = m.system_ids[d * m.S + r * m.T + t];
+        const float mag = __fdiv_rn((float)m.mags[d * m.S + sys], nf);
+        const float m2 = __fmul_rn(mag, mag);
+        const float m4 = __fmul_rn(m2, m2);
+        const float e = m.energies[d * m.S + sys];
+        s0 = __dadd_rn(s0, (double)mag);
+        s1 = __dadd_rn(s1, (double)m2);
+        s2 = __dadd_rn(s2, (double)m4);
+        s3 = __dadd_rn(s3, (double)e);
+        s4 = __dadd_rn(s4, __dmul_rn((double)e, (double)e));  // stats.rs:23: powi(2) in f64
+    }
+    sums[0] = s0; sums[1 * m.T] = s1; sums[2 * m.T] = s2; sums[3 * m.T] = s3; sums[4 * m.T] = s4;
+    if (!with_overlap) return;
+    // statistics/overlap.rs:283-306 + :318-324, pair order
+    const float nb = (float)(m.N * m.z);
+    const int64_t bins = m.N + 1;
+    double o0 = sums[5 * m.T], o1 = sums[6 * m.T], o2 = sums[7 * m.T], o3 = sums[8 * m.T], o4 = sums[9 * m.T],
+           o5 = sums[10 * m.T];
+    for (int p = 0; p < m.P; p++) {
+        const long long dsp = st.dot_spin[(d * m.P + p) * m.T + t];
+        const long long dlk = st.dot_link[(d * m.P + p) * m.T + t];
+        const float ql = __fdiv_rn((float)dlk, nb);
+        const float q = __fdiv_rn((float)dsp, nf);
+        const float q2 = __fmul_rn(q, q);
+        const float ql2 = __fmul_rn(ql, ql);
+        o0 = __dadd_rn(o0, (double)q);
+        o1 = __dadd_rn(o1, (double)q2);
+        o2 = __dadd_rn(o2, (double)__fmul_rn(q2, q2));
+        o3 = __dadd_rn(o3, (double)ql);
+        o4 = __dadd_rn(o4, (double)ql2);
+        o5 = __dadd_rn(o5, (double)__fmul_rn(ql2, ql2));
+        const int64_t idx = (dsp + m.N) / 2;
+        const int64_t h = (d * m.T + t) * bins + idx;
+        st.hist[h] += 1u;
+        st.ql_at_q[h] = __dadd_rn(st.ql_at_q[h], (double)ql);
+        st.ql2_at_q[h] = __dadd_rn(st.ql2_at_q[h], (double)ql2);
+    }
+    sums[5 * m.T] = o0; sums[6 * m.T] = o1; sums[7 * m.T] = o2; sums[8 * m.T] = o3; sums[9 * m.T] = o4;
+    sums[10 * m.T] = o5;
+}
+
+// realization.rs:109-120
+__device__ __forceinline__ void pt_record_arrival(const PtView &pt, int64_t base, int system, int slot) {
+    if (slot == pt.hot_slot) {
+        if (pt.trip_state[base + system] == 2) pt.round_trips[base + system] += 1ull;
+        pt.trip_state[base + system] = 1;
+        return;
+    }
+    if (slot == pt.cold_slot && pt.trip_state[base + system] == 1) pt.trip_state[base + system] = 2;
+}
+
+// tempering.rs:73-102; logtab[draw] = host-libm logf(draw / 2^24) so the decision is the CPU's bit for bit
+__device__ __forceinline__ void pt_attempt_edge(const ModelView &m, const PtView &pt, int64_t d, int r, int edge,
+                                                uint32_t draw, bool msc) {
+    int32_t *sid = m.system_ids + d * m.S + r * m.T;
+    const float temp_1 = m.temps[edge], temp_2 = m.temps[edge + 1];
+    const int left = sid[edge], right = sid[edge + 1];
+    const float energy_1 = m.energies[d * m.S + left], energy_2 = m.energies[d * m.S + right];
+    const float delta = __fmul_rn(__fmul_rn((float)m.N, __fsub_rn(energy_2, energy_1)),
+                                  __fsub_rn(__fdiv_rn(1.0f, temp_1), __fdiv_rn(1.0f, temp_2)));
+    const bool accepted = delta >= m.logtab[draw];
+    const int64_t eb = d * (m.T - 1);
+    // the T-1 edge counters of a realization are shared by its R replica threads
+    atomicAdd(&pt.edge_attempts[eb + edge], 1ull);
+    if (!accepted) return;
+    sid[edge] = right;
+    sid[edge + 1] = left;
+    atomicAdd(&pt.edge_acceptances[eb + edge], 1ull);
+    pt_record_arrival(pt, d * m.S, left, edge + 1);   // realization.rs:80-81
+    pt_record_arrival(pt, d * m.S, right, edge);
+    if (msc) {
+        const int64_t g = d >> 5;
+        atomicOr(&pt.swap_mask[(g * m.R + r) * (m.T - 1) + edge], 1u << (d & 31));
+    }
+}
+
+// K8: one thread per (realization, replica).  RNG-SPEC PT domain: key = realization key,
+// counter = {edge | 0xFFFFFFFF, pt_event, replica, TAG_PT}.
+__global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int first_parity, uint32_t pt_event, int msc) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m.D * m.R || m.T < 2) return;
+    const int64_t d = gid / m.R;
+    const int r = (int)(gid % m.R);
+    const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    if (schedule == 0) {  // tempering.rs:20-42
+        const u32x4 o = philox4x32_10(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+        const int edge = (int)(((uint64_t)o.y * (uint64_t)(m.T - 1)) >> 32);
+        pt_attempt_edge(m, pt, d, r, edge, o.x >> 8, msc != 0);
+    } else {  // tempering.rs:45-70
+        for (int pi = 0; pi < 2; pi++) {
+            const int parity = pi == 0 ? first_parity : 1 - first_parity;
+            for (int edge = parity; edge < m.T - 1; edge += 2) {
+                const u32x4 o = philox4x32_10((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+                pt_attempt_edge(m, pt, d, r, edge, o.x >> 8, msc != 0);
+            }
+        }
+    }
+}
+
+// overlap.rs:128-142: per-(t, bin) sums over realizations, in realization order
+__global__ void reduce_hist_kernel(ModelView m, StatsView st, unsigned long long *hist_out, double *ql_out, double *ql2_out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)m.T * (m.N + 1);
+    if (gid >= per) return;
+    unsigned long long h = 0;
+    double a = 0.0, b = 0.0;
+    for (int64_t d = 0; d < m.D; d++) {
+        h += st.hist[d * per + gid];
+        a = __dadd_rn(a, st.ql_at_q[d * per + gid]);
+        b = __dadd_rn(b, st.ql2_at_q[d * per + gid]);
+    }
+    hist_out[gid] = h;
+    ql_out[gid] = a;
+    ql2_out[gid] = b;
+}
+
+__global__ void widen_u32_kernel(const uint32_t *in, unsigned long long *out, int64_t n) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) out[gid] = in[gid];
+}
+
+}  // namespace pp

@@ -1,0 +1,228 @@
+"""T2/T3: the CUDA path (through the C ABI) against the oracle under the shared Philox draws (RNG-SPEC).
+Bit-exact: spins, system_ids, +-J energies, magnetisations, overlap dots, histograms, PT counters, f64 means.
+fp32 couplings: bit-exact spins with exact_log (host-libm log table), energies within 1e-5 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TRI = [[1, 0], [0, 1], [1, -1]]
+FCC = [[1, 1, 0], [1, 0, 1], [0, 1, 1], [1, -1, 0], [1, 0, -1], [0, 1, -1]]
+
+
+def couplings(kind, shape, z, D, seed):
+    rng = np.random.default_rng(seed)
+    full = (D,) + tuple(shape) + (z,)
+    if kind == "ferro":
+        J = np.ones(full, np.float32)
+    elif kind == "bimodal":
+        J = (2 * rng.integers(0, 2, size=full) - 1).astype(np.float32)
+    elif kind == "diluted":  # {-1, 0, +1}: lookup-eligible with odd fields (sweep.rs:110-112)
+        J = rng.integers(-1, 2, size=full).astype(np.float32)
+    else:
+        J = rng.standard_normal(full).astype(np.float32)
+    return J[0] if D == 1 else J
+
+
+def make_pair(oracle, shape, kind, temps, R, D, offsets=None, layout="int8", seed=1234, jseed=7):
+    import peapods_b200 as pb
+
+    z = len(shape) if offsets is None else len(offsets)
+    J = couplings(kind, shape, z, D, jseed)
+    temps = np.asarray(temps, np.float32)
+    colour, _ = pb.colouring(shape, offsets)
+    gpu = pb.IsingSimulation(list(shape), J, temps, R, offsets, seed, layout=layout)
+    assert gpu.layout == layout
+    mode = oracle.RNG_PHILOX_MSC if layout == "msc" else oracle.RNG_PHILOX
+    cpu = oracle.Sim(shape, J, temps, n_replicas=R, offsets=offsets, seed=seed, rng_mode=mode, colour=colour)
+    return gpu, cpu
+
+
+def assert_state_equal(gpu, cpu, D):
+    for d in range(D):
+        assert np.array_equal(gpu.get_spins(d), cpu.spins(d)), f"spins differ, realization {d}"
+        assert np.array_equal(gpu.get_system_ids(d), cpu.system_ids(d)), f"system_ids differ, realization {d}"
+
+
+def assert_results_equal(rg, rc, exact=True, rtol=0.0):
+    keys = [k for k in rc if k != "per_disorder"]
+    for k in keys:
+        a, b = rg[k], rc[k]
+        if k == "overlap_histogram":
+            a = np.stack(a)
+        if exact:
+            assert np.array_equal(np.asarray(a), np.asarray(b)), k
+        else:
+            np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=1e-7, err_msg=k)
+    if "per_disorder" in rc:
+        for k, v in rc["per_disorder"]["parallel_tempering"].items():
+            assert np.array_equal(rg["per_disorder"]["parallel_tempering"][k], v), k
+
+
+CASES_INT8 = [
+    # shape, kind, offsets, temps, R, D
+    ((8, 8), "ferro", None, [1.5, 2.27, 3.0], 2, 1),
+    ((32, 32), "ferro", None, np.linspace(1.5, 3.0, 16), 2, 1),        # BASELINE config 1 geometry
+    ((8, 8), "bimodal", None, [0.7, 2.0, 5.0], 2, 3),
+    ((4, 4, 4), "bimodal", None, [0.8, 1.1, 1.4], 4, 2),
+    ((8, 8, 8), "bimodal", None, np.linspace(0.8, 1.4, 4), 2, 2),
+    ((16, 16, 16), "bimodal", None, [0.8, 1.4], 2, 1),                  # BASELINE config 2 geometry
+    ((6, 6), "ferro", TRI, [3.0, 3.64, 4.2], 2, 1),
+    ((8, 8), "bimodal", TRI, [1.0, 3.64], 2, 2),
+    ((2, 2), "bimodal", None, [1.0, 2.0], 2, 2),                        # L=2: fwd == bwd neighbour
+    ((2, 2, 2), "ferro", None, [4.5], 2, 1),
+    ((5, 7), "bimodal", None, [0.8, 2.5], 2, 1),                        # odd extents: greedy colouring
+    ((3, 3), "diluted", None, [1.0, 2.0], 2, 2),
+    ((6, 6), "diluted", None, [0.9, 1.7, 2.9], 3, 2),                   # zeros -> odd local fields
+    ((4, 4, 4), "bimodal", FCC, [2.0, 9.8], 2, 1),
+    ((4, 6, 2, 2), "bimodal", None, [1.5, 6.0], 2, 1),                  # 4-D
+]
+
+
+@pytest.mark.parametrize("shape,kind,offsets,temps,R,D", CASES_INT8)
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+def test_int8_trajectory_is_bit_exact(oracle, shape, kind, offsets, temps, R, D, mode):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
+    assert_state_equal(gpu, cpu, D)  # INIT domain
+    for n_sweeps in (1, 2, 17):
+        rg = gpu.sample(n_sweeps, mode, warmup_ratio=0.25)
+        rc = cpu.sample(n_sweeps, mode, warmup_ratio=0.25)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+
+
+@pytest.mark.parametrize("schedule", ["single_random_edge", "full_ladder"])
+@pytest.mark.parametrize("shape,kind,offsets,temps,R,D", [
+    ((8, 8), "ferro", None, np.linspace(1.5, 3.0, 6), 2, 1),
+    ((4, 4, 4), "bimodal", None, np.linspace(0.8, 1.6, 5), 4, 3),
+    ((6, 6), "bimodal", TRI, [1.0, 1.5, 2.5], 3, 2),
+    ((4, 4), "bimodal", None, [1.3], 2, 2),                            # single temperature: PT is a no-op
+])
+def test_int8_sample_with_pt_and_overlap_is_bit_exact(oracle, shape, kind, offsets, temps, R, D, schedule):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
+    for n_sweeps, interval in ((100, 1), (23, 3)):
+        rg = gpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule)
+        rc = cpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        for d in range(D):
+            assert np.array_equal(gpu.get_energies(d), cpu.energies(d))
+
+
+@pytest.mark.parametrize("shape,D,R,temps", [
+    ((4, 4, 4), 32, 2, [0.8, 1.1, 1.4]),
+    ((4, 4, 4), 45, 4, [0.9, 1.3]),            # padded second word group
+    ((8, 8, 8), 64, 2, np.linspace(0.8, 1.4, 4)),
+    ((8, 8), 40, 2, [0.7, 2.0, 5.0]),          # 2-D: 4 bond words per site
+    ((16, 16, 16), 32, 2, [0.8, 1.4]),
+])
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+def test_msc_trajectory_is_bit_exact(oracle, shape, D, R, temps, mode):
+    gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, D, layout="msc")
+    assert_state_equal(gpu, cpu, D)
+    for n_sweeps in (1, 2, 9):
+        rg = gpu.sample(n_sweeps, mode, warmup_ratio=0.25)
+        rc = cpu.sample(n_sweeps, mode, warmup_ratio=0.25)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+
+
+@pytest.mark.parametrize("schedule", ["single_random_edge", "full_ladder"])
+@pytest.mark.parametrize("shape,kind,offsets,D,R,temps", [
+    ((4, 4, 4), "bimodal", None, 40, 4, np.linspace(0.8, 1.6, 5)),
+    ((8, 8, 8), "bimodal", None, 32, 2, np.linspace(0.8, 1.4, 6)),
+    ((6, 6), "bimodal", TRI, 33, 2, [1.0, 1.5, 2.5]),
+    ((8, 8), "ferro", None, 32, 2, [1.5, 2.27, 3.0]),
+])
+def test_msc_sample_with_pt_and_overlap_is_bit_exact(oracle, shape, kind, offsets, D, R, temps, schedule):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets, layout="msc")
+    for n_sweeps, interval in ((60, 1), (23, 3)):
+        rg = gpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule)
+        rc = cpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+
+
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+@pytest.mark.parametrize("shape,offsets,D", [((4, 4, 4), None, 2), ((8, 8, 8), None, 1), ((6, 6), TRI, 2)])
+def test_gaussian_couplings_exact_log_spins_and_energy_tolerance(oracle, shape, offsets, D, mode):
+    temps = [0.8, 1.3, 1.8]
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, 2, D, offsets)
+    for n_sweeps in (1, 12):
+        rg = gpu.sample(n_sweeps, mode, warmup_ratio=0.25, exact_log=True)
+        rc = cpu.sample(n_sweeps, mode, warmup_ratio=0.25)
+        assert_state_equal(gpu, cpu, D)  # same spins => the energy comparison is on identical states
+        e_g, m_g = gpu.op_energies_mags()
+        for d in range(D):
+            lat = oracle.Lattice(shape, offsets)
+            Jd = gpu_couplings(shape, offsets, D)[d]
+            e_c, m_c = lat.energies_mags(cpu.spins(d).reshape(-1, lat.n_spins), Jd)
+            np.testing.assert_allclose(e_g[d], e_c, rtol=1e-5, atol=1e-6)
+            assert np.array_equal(m_g[d], m_c)
+        # integer observables are exact, f32-energy-derived ones within tolerance
+        for k in ("mags", "mags2", "mags4", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2", "link_overlap4"):
+            assert np.array_equal(rg[k], rc[k]), k
+        np.testing.assert_allclose(rg["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(rg["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
+
+
+def gpu_couplings(shape, offsets, D):
+    z = len(shape) if offsets is None else len(offsets)
+    J = couplings("gaussian", shape, z, D, 7)
+    return J.reshape((D, -1))
+
+
+def test_gaussian_device_logf_agrees_statistically(oracle):
+    # production mode (device logf): trajectories may differ in rare last-ulp cases, observables must not
+    shape, temps = (6, 6, 6), np.linspace(0.9, 1.8, 4)
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, 2, 4)
+    rg = gpu.sample(400, "metropolis", exact_log=False)
+    rc = cpu.sample(400, "metropolis")
+    np.testing.assert_allclose(rg["energies"], rc["energies"], atol=0.02)
+
+
+def test_operator_entry_points_match_oracle(oracle):
+    shape, temps, R, D = (6, 6, 6), [0.9, 1.2, 1.5], 4, 3
+    for layout, kind, DD in (("int8", "bimodal", D), ("int8", "gaussian", D), ("msc", "bimodal", 37)):
+        gpu, cpu = make_pair(oracle, shape, kind, temps, R, DD, layout=layout)
+        lat = oracle.Lattice(shape)
+        J = couplings(kind, shape, 3, DD, 7)
+        colour = __import__("peapods_b200").colouring(shape)[0]
+        rng = np.random.default_rng(5)
+        S, N = R * len(temps), lat.n_spins
+        spins = (2 * rng.integers(0, 2, size=(DD, S, N)) - 1).astype(np.int8)
+        ids = np.stack([np.concatenate([r * len(temps) + rng.permutation(len(temps)) for r in range(R)]) for _ in range(DD)])
+        for d in range(DD):
+            gpu.set_system_ids(ids[d], d)
+            gpu.set_spins(spins[d], d)
+            assert np.array_equal(gpu.get_spins(d), spins[d].reshape(-1))
+            assert np.array_equal(gpu.get_system_ids(d), ids[d])
+        # energies / magnetisations (spins/energy.rs:59-76)
+        e_g, m_g = gpu.op_energies_mags()
+        for d in range(DD):
+            e_c, m_c = lat.energies_mags(spins[d], J[d])
+            assert np.array_equal(m_g[d], m_c)
+            if kind == "gaussian":
+                np.testing.assert_allclose(e_g[d], e_c, rtol=1e-5, atol=1e-6)
+            else:
+                assert np.array_equal(e_g[d], e_c)
+        # overlap dots (statistics/overlap.rs:259-281)
+        ds, dl = gpu.op_overlap()
+        T = len(temps)
+        for d in range(DD):
+            for p in range(R // 2):
+                for t in range(T):
+                    a, b = ids[d][(2 * p) * T + t], ids[d][(2 * p + 1) * T + t]
+                    assert (ds[d, p, t], dl[d, p, t]) == lat.overlap_dots(spins[d][a], spins[d][b])
+        # one sweep with a caller-chosen sweep index (mcmc/sweep.rs:220-284)
+        temps_full = np.tile(np.asarray(temps, np.float32), R)
+        for sweep_mode, code in (("metropolis", oracle.SWEEP_METROPOLIS), ("gibbs", oracle.SWEEP_GIBBS)):
+            gpu.op_sweep(sweep_mode, 77, exact_log=True)
+            for d in range(DD):
+                if layout == "msc":
+                    key = oracle.lib().orc_splitmix64(1234 ^ oracle.lib().orc_splitmix64(0x6D73635F67726F75 ^ (d >> 5)))
+                else:
+                    key = oracle.lib().orc_realization_seed(1234, d)
+                lat.sweep_philox(spins[d], J[d], temps_full, ids[d], colour, key, 77, code, use_lookup=True,
+                                 stream_is_slot=(layout == "msc"))
+                assert np.array_equal(gpu.get_spins(d), spins[d].reshape(-1)), (layout, kind, sweep_mode, d)
