@@ -90,6 +90,9 @@ typedef struct {
     /* 1: fp32-coupling / Gibbs log thresholds are read from a host-libm logf table so that spin
      * trajectories are bit-identical to the CPU rule; 0: device logf (results agree to tolerance) */
     int32_t exact_log;
+    /* 1: bracket every sweep-kernel launch with CUDA events on the launch stream and report the summed
+     * duration in pp_results.sweep_kernel_ms (measurement hook for the roofline figure) */
+    int32_t profile;
 } pp_sample_cfg;
 
 /* Result buffers; every pointer may be NULL (that output is skipped).
@@ -109,6 +112,8 @@ typedef struct {
                                   lets a multi-GPU caller do the reference's ordered sum over realizations */
     double sweep_loop_ms;      /* out: device time of the sweep loop (CUDA events on the launch stream) */
     int64_t kernel_launches;   /* out: kernels launched by this call */
+    double sweep_kernel_ms;    /* out (cfg.profile): summed device time of the sweep-kernel launches */
+    int64_t sweep_kernel_launches; /* out (cfg.profile): how many launches that sum covers */
 } pp_results;
 
 const char *pp_last_error(void);

@@ -85,7 +85,7 @@ class IsingSimulation:
                overlap_cluster_mode=None, overlap_cluster_action=None, warmup_ratio=None, collect_cluster_stats=None,
                autocorrelation_max_lag=None, autocorrelation_backend=None, sequential=None,
                equilibration_diagnostic=None, snapshot_interval=None, *, exact_log=False, per_sample=True,
-               on_sweep=None, interrupt=None):
+               on_sweep=None, interrupt=None, profile=False):
         warmup = 0.25 if warmup_ratio is None else float(warmup_ratio)
         n_sweeps = int(n_sweeps)
         if sweep_mode not in _lib.SWEEP_MODES:  # config.rs:9-20
@@ -123,6 +123,7 @@ class IsingSimulation:
         cfg.snapshot_interval = 0 if snapshot_interval is None else max(int(snapshot_interval), 1)
         cfg.equilibration_diagnostic = int(bool(equilibration_diagnostic))
         cfg.exact_log = int(bool(exact_log))
+        cfg.profile = int(bool(profile))
 
         T, R, D, N = self.n_temps, self.n_replicas, self.n_realizations, self.n_spins
         out = {}
@@ -170,6 +171,8 @@ class IsingSimulation:
         _lib.check(status)
         self.last_sweep_loop_ms = float(res.sweep_loop_ms)
         self.last_kernel_launches = int(res.kernel_launches)
+        self.last_sweep_kernel_ms = float(res.sweep_kernel_ms)
+        self.last_sweep_kernel_launches = int(res.sweep_kernel_launches)
         self.last_per_sample_means = means
         if R >= 2:
             out["overlap_histogram"] = [hist[t].copy() for t in range(T)]  # list of u64[N+1], src/lib.rs:358-366

@@ -52,6 +52,7 @@ class SampleCfg(C.Structure):
         ("snapshot_interval", C.c_int64),
         ("equilibration_diagnostic", C.c_int32),
         ("exact_log", C.c_int32),
+        ("profile", C.c_int32),
     ]
 
 
@@ -65,7 +66,8 @@ class Results(C.Structure):
         + [("overlap_histogram", _PU64), ("ql_at_q_sum", _PD), ("ql2_at_q_sum", _PD)]
         + [("per_sample_overlap_histogram", _PU64), ("per_sample_ql_at_q_sum", _PD), ("per_sample_ql2_at_q_sum", _PD)]
         + [("pt_edge_attempts", _PU64), ("pt_edge_acceptances", _PU64), ("pt_round_trips", _PU64)]
-        + [("per_sample_means", _PD), ("sweep_loop_ms", C.c_double), ("kernel_launches", C.c_int64)]
+        + [("per_sample_means", _PD), ("sweep_loop_ms", C.c_double), ("kernel_launches", C.c_int64),
+           ("sweep_kernel_ms", C.c_double), ("sweep_kernel_launches", C.c_int64)]
     )
 
 

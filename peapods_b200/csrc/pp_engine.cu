@@ -172,7 +172,22 @@ struct pp_sim {
     long long *d_dot_spin = nullptr, *d_dot_link = nullptr;
     bool hist_allocated = false;
     int64_t launches = 0;
+    // measurement hook: event pairs around sweep-kernel launches
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
 };
+
+static void prof_mark(pp_sim *s) {
+    if (!s->profile) return;
+    if (s->prof_used == s->prof_events.size()) {
+        if (s->prof_events.size() >= 8192) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        s->prof_events.push_back(e);
+    }
+    cudaEventRecord(s->prof_events[s->prof_used++], s->stream);
+}
 
 static void free_sim(pp_sim *s) {
     if (!s) return;
@@ -183,6 +198,7 @@ static void free_sim(pp_sim *s) {
                     s->st.sums, s->st.hist, s->st.ql_at_q, s->st.ql2_at_q, s->d_dot_spin, s->d_dot_link};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -232,10 +248,13 @@ static pp_status launch_sweeps(pp_sim *s, int sweep_mode, uint32_t sweep_index, 
     ModelView m = s->mv;
     m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
     if (s->layout == PP_LAYOUT_MSC) {
+        const bool timed = n_sweeps > 0;
+        if (timed) prof_mark(s);
         if (s->msc3d && n_sweeps > 0) {
             pp_status st = launch_msc3d(m, s->stream, sweep_index, n_sweeps, want_energy, want_mags,
                                         s->mv.sample_offset / 32, &s->launches);
             if (st != PP_OK) return fail(st, "msc3d launch failed");
+            prof_mark(s);
             CUDA_TRY(cudaGetLastError());
             return PP_OK;
         }
@@ -250,9 +269,11 @@ static pp_status launch_sweeps(pp_sim *s, int sweep_mode, uint32_t sweep_index, 
                                                                       s->mv.sample_offset / 32);
         }
         s->launches++;
+        if (timed) prof_mark(s);
         CUDA_TRY(cudaGetLastError());
         return PP_OK;
     }
+    if (n_sweeps > 0) prof_mark(s);
     for (int sw = 0; sw < n_sweeps; sw++) {
         for (int c = 0; c < m.n_colours; c++) {
             const uint32_t nsite = s->plan.colour_start[c + 1] - s->plan.colour_start[c];
@@ -271,6 +292,7 @@ static pp_status launch_sweeps(pp_sim *s, int sweep_mode, uint32_t sweep_index, 
             s->launches++;
         }
     }
+    if (n_sweeps > 0) prof_mark(s);
     CUDA_TRY(cudaGetLastError());
     if (want_energy) return launch_energy(s, want_mags);
     return PP_OK;
@@ -614,6 +636,8 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemsetAsync(s->st.ql2_at_q, 0, sizeof(double) * n, s->stream));
     }
     const int64_t launches0 = s->launches;
+    s->profile = cfg->profile != 0;
+    s->prof_used = 0;
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
 
     const bool msc = s->layout == PP_LAYOUT_MSC;
@@ -661,9 +685,18 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     float ms = 0.0f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    double prof_ms = 0.0;
+    for (size_t i = 0; i + 1 < s->prof_used; i += 2) {
+        float one = 0.0f;
+        if (cudaEventElapsedTime(&one, s->prof_events[i], s->prof_events[i + 1]) == cudaSuccess) prof_ms += one;
+    }
+    const int64_t prof_n = (int64_t)(s->prof_used / 2);
+    s->profile = false;
     if (!out) return PP_OK;
     out->sweep_loop_ms = ms;
     out->kernel_launches = s->launches - launches0;
+    out->sweep_kernel_ms = prof_ms;
+    out->sweep_kernel_launches = prof_n;
 
     // ---- results (statistics/stats.rs:29-35, results.rs:165-180, 250-259, overlap.rs:106-152)
     const int T = m.T;
