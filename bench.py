@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — spin-flip attempts/ns of the sweep path on BASELINE.json's headline config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): 3-D Edwards-Anderson +-J, L=16, 32 temperatures 0.8-1.4,
+4 replicas, 4096 disorder samples per GPU, Metropolis + parallel tempering every sweep + overlap,
+couplings from the reference's own generator (seed 42, python/peapods/spin_models.py:104-126),
+warmup_ratio 0.25 (3/4 of the sweeps pay the energy / magnetisation / overlap reductions).
+
+A "step" is one `sample(n_sweeps=SWEEPS_PER_STEP)` call.  Three measurements:
+  value   device-resident: a persistent engine handle, K `pp_sample` calls, device time of the sweep
+          loops (CUDA events on the launch stream), max over ranks.
+  e2e     through the reference-facing API with host buffers: every step constructs
+          `IsingSimulation` from the pinned host coupling array (H2D), samples, and reads the result
+          dict back (D2H); wall clock bracketed by synchronize, max over ranks.
+  roofline  the sweep kernel alone: algorithmic bytes per launch / its mean launch duration,
+          measured live with CUDA events around every sweep-kernel launch (separate, untimed pass).
+`--impl reference` times the CPU restatement of the reference's rayon path (oracle, typewriter order +
+xoshiro streams, threads over realizations) on the box's host cores, on a bounded sample of the same
+workload.  The Rust crate itself cannot be built in this image (no cargo/rustc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "spin_flip_attempts_per_ns"
+UNIT = "attempts/ns"
+SHAPE = (16, 16, 16)
+N_TEMPS, T_LO, T_HI, N_REPLICAS = 32, 0.8, 1.4, 4
+SAMPLES_PER_GPU = 4096
+Z = 3
+SEED = 42
+B_ALG_MSC = 0.125 + 0.125 + (Z / 8.0) / (N_TEMPS * N_REPLICAS)  # bytes per attempt
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def temperatures():
+    return np.linspace(T_LO, T_HI, N_TEMPS).astype(np.float32)
+
+
+def make_couplings(first_sample: int, n_samples: int, total: int, out: np.ndarray | None = None) -> np.ndarray:
+    """The reference generator (spin_models.py:107-126): realization r draws from child r of the coupling
+    SeedSequence, so a shard of samples equals the same slice of the unsharded run."""
+    from peapods_b200.spin_models import seed_material
+
+    coupling_seq, _ = seed_material(SEED)
+    children = coupling_seq.spawn(total)[first_sample:first_sample + n_samples]
+    single = SHAPE + (Z,)
+    if out is None:
+        out = np.empty((n_samples,) + single, dtype=np.float32)
+    for i, child in enumerate(children):
+        out[i] = 2 * np.random.default_rng(child).integers(0, 2, size=single) - 1
+    return out
+
+
+def dynamics_seed() -> int:
+    from peapods_b200.spin_models import seed_material
+
+    return seed_material(SEED)[1]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_run(n_samples: int, n_sweeps: int, n_threads: int, repeats: int = 1):
+    """Reference-faithful CPU path (oracle: typewriter order, xoshiro per system, +-J lookup, energies +
+    overlap recomputed per recorded sweep, PT label swaps; threads over realizations like
+    simulation/mod.rs:887-903).  Returns (attempts/ns, seconds)."""
+    import oracle
+
+    temps = temperatures()
+    J = make_couplings(0, n_samples, SAMPLES_PER_GPU)
+    sim = oracle.Sim(SHAPE, J, temps, n_replicas=N_REPLICAS, seed=dynamics_seed(), rng_mode=oracle.RNG_XOSHIRO)
+    attempts = float(np.prod(SHAPE)) * N_TEMPS * N_REPLICAS * n_samples * n_sweeps
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        sim.sample(n_sweeps, "metropolis", pt_interval=1, pt_schedule="single_random_edge", warmup_ratio=0.25,
+                   n_threads=n_threads, per_sample=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return attempts / (best * 1e9), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n_samples = max(cores, 16) * 2
+    n_sweeps = args.sweeps_per_step
+    # bounded: scale the sample so one step stays near a few seconds
+    for _ in range(args.warmup):
+        cpu_baseline_run(n_samples, max(2, n_sweeps // 8), cores)
+    times, vals = [], []
+    for _ in range(args.steps):
+        v, dt = cpu_baseline_run(n_samples, n_sweeps, cores)
+        vals.append(v)
+        times.append(dt)
+    attempts = float(np.prod(SHAPE)) * N_TEMPS * N_REPLICAS * n_samples * n_sweeps
+    value = attempts * len(times) / (sum(times) * 1e9)
+    sample = (f"{n_samples} of {SAMPLES_PER_GPU} disorder samples x {n_sweeps} sweeps per step, "
+              f"same lattice/temperatures/replicas/PT/overlap")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 multispin words / int8 spins (CPU: int8 + f32)",
+        "data": "synthetic", "config": workload_config(args, n_samples),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C restatement of the reference CPU path (oracle/pp_oracle.c); the Rust crate cannot be built here",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, samples_per_gpu):
+    return {
+        "workload": "C2: 3-D EA +-J L=16, 32 temps 0.8-1.4, 4 replicas, Metropolis + PT(single_random_edge, every sweep) + overlap",
+        "lattice": list(SHAPE), "n_temps": N_TEMPS, "n_replicas": N_REPLICAS, "samples_per_gpu": samples_per_gpu,
+        "sweeps_per_step": args.sweeps_per_step, "warmup_ratio": 0.25, "pt_interval": 1, "layout": "msc (32 samples / u32 word)",
+        "sharding": "disorder samples split across GPUs, no data-path collective",
+        "l2": "working set (256 MiB spin words + per-sample histograms) exceeds the 126 MB L2; no flush needed",
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import peapods_b200 as pb
+    from peapods_b200 import _lib
+
+    _lib.load()  # fails loudly if the CUDA extension is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise RuntimeError("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    D = args.samples_per_gpu
+    temps = temperatures()
+    first = rank * D
+    # pinned host coupling buffer (the e2e leg copies from it every step)
+    Jt = torch.empty((D,) + SHAPE + (Z,), dtype=torch.float32, pin_memory=True)
+    J = Jt.numpy()
+    make_couplings(first, D, D * world, out=J)
+    seed = dynamics_seed()
+    n_sweeps = args.sweeps_per_step
+    attempts_step = float(np.prod(SHAPE)) * N_TEMPS * N_REPLICAS * D * n_sweeps
+    kw = dict(pt_interval=1, pt_schedule="single_random_edge", warmup_ratio=0.25, per_sample=False)
+
+    # ---- device-resident leg -------------------------------------------------------------------
+    sim = pb.IsingSimulation(list(SHAPE), J, temps, N_REPLICAS, None, seed, layout="msc", device=local_rank,
+                             sample_offset=first)
+    assert sim.layout == "msc"
+    for _ in range(args.warmup):
+        sim.sample(n_sweeps, "metropolis", **kw)
+    barrier()
+    dev_ms, launches = 0.0, 0
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.sample(n_sweeps, "metropolis", **kw)
+            dev_ms += sim.last_sweep_loop_ms
+            launches += sim.last_kernel_launches
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+    total_attempts = sum_over_ranks(attempts_step * args.steps)
+    value = total_attempts / (dev_ms * 1e6)
+    clock_summary = clocks.summary()
+
+    # ---- roofline pass (untimed): CUDA events around every sweep-kernel launch ------------------
+    res = sim.sample(n_sweeps, "metropolis", profile=True, **kw)
+    del res
+    k_ms, k_n = sim.last_sweep_kernel_ms, max(sim.last_sweep_kernel_launches, 1)
+    peak, peak_src = peaks()
+    alg_bytes_per_launch = B_ALG_MSC * attempts_step / k_n
+    achieved = alg_bytes_per_launch / (k_ms / k_n * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": args.traffic, "kernel": "msc sweep kernel", "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes_per_launch, "launches_timed": k_n, "kernel_ms_mean": k_ms / k_n,
+                "kernel_share_of_step": k_ms / max(sim.last_sweep_loop_ms, 1e-9)}
+    del sim
+
+    # ---- end-to-end leg: host buffers in, result dict out, every step ----------------------------
+    def e2e_step():
+        s = pb.IsingSimulation(list(SHAPE), J, temps, N_REPLICAS, None, seed, layout="msc", device=local_rank,
+                               sample_offset=first)
+        out = s.sample(n_sweeps, "metropolis", **kw)
+        nb = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray))
+        nb += sum(h.nbytes for h in out["overlap_histogram"])
+        nb += sum(v.nbytes for v in out["per_disorder"]["parallel_tempering"].values())
+        nb += s.last_per_sample_means.nbytes
+        del s
+        return nb
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        d2h = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    e2e_value = total_attempts / (e2e_ms * 1e6)
+    h2d = J.nbytes + temps.nbytes
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ns, nsw = 2 * max(cores, 16), 12
+        v, dt = cpu_baseline_run(ns, nsw, cores)
+        if dt < 4.0:  # aim for 10-30 s of CPU work
+            nsw = int(min(200, max(nsw, nsw * 12.0 / max(dt, 1e-3))))
+            v, dt = cpu_baseline_run(ns, nsw, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{ns} of {D} disorder samples x {nsw} sweeps ({dt:.1f} s), same lattice/temps/replicas/PT/overlap"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (multispin words, 32 samples/word; integer acceptance table)", "data": "synthetic",
+            "config": workload_config(args, D),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps, "clocks": clock_summary,
+            "roofline": roofline, "hbm_roofline_frac_whole_step": value * B_ALG_MSC / (world * peak),
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--sweeps-per-step", type=int, default=64)
+    ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 0)
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
