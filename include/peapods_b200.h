@@ -136,6 +136,8 @@ pp_status pp_get_spins(pp_sim *sim, int64_t realization, int8_t *out /* [S*N], s
 pp_status pp_get_system_ids(pp_sim *sim, int64_t realization, int64_t *out /* [S] */);
 pp_status pp_get_energies(pp_sim *sim, int64_t realization, float *out /* [S] by system */);
 int32_t pp_get_layout(const pp_sim *sim);
+/* 1 when sweeps run through the stride-based 3-D multispin kernel (pp_kernels_msc3d.cuh), else 0 */
+int32_t pp_uses_msc3d(const pp_sim *sim);
 
 /* operator-level entry points with the reference's slice semantics (unit-level parity tests):
  * H2D -> kernel -> D2H on the handle's state. */

@@ -70,6 +70,7 @@ class IsingSimulation:
         desc.device = int(device)
         _lib.check(lib.pp_create(C.byref(desc), C.byref(self._h)))
         self.layout = _lib.LAYOUT_NAMES[lib.pp_get_layout(self._h)]
+        self.uses_msc3d = bool(lib.pp_uses_msc3d(self._h))
         self.last_sweep_loop_ms = 0.0
         self.last_kernel_launches = 0
 

@@ -88,6 +88,7 @@ SIGNATURES = {
     "pp_get_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_get_energies": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_get_layout": (C.c_int32, [C.c_void_p]),
+    "pp_uses_msc3d": (C.c_int32, [C.c_void_p]),
     "pp_set_spins": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_set_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_op_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32]),

@@ -27,6 +27,8 @@ struct ModelView {
     const uint32_t *nbr;          // [N][2z] fwd/bwd interleaved
     const uint32_t *order;        // [N] colour-sorted sites
     const uint32_t *colour_start; // [n_colours+1]
+    const uint32_t *perm;         // [N] site -> storage index of the multispin words (nullptr: identity); when set,
+                                  // nbr / order / Jw are expressed in storage space
     // couplings
     const int8_t *J8;   // [D][N][z]   (COUP_UNIT, int8 layout)
     const float *Jf;    // [D][N][z]   (COUP_F32)

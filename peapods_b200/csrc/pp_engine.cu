@@ -154,6 +154,13 @@ struct pp_sim {
     int next_parity = 0;                               // realization.rs:84-90
     int64_t G = 0;                                     // word groups (MSC)
     bool msc3d = false;                                // specialised 3-D hypercubic MSC kernel usable
+    bool msc3d_metro = false;                          // Metropolis counts for unsat >= 3 are all 2^24
+    int msc3d_nt = 128;                                // threads per CTA of the msc3d kernel
+    size_t msc3d_smem = 0;
+    Msc3dPlan m3;
+    Msc3dView gv{};
+    uint32_t *d_perm = nullptr;
+    uint4 *d_items = nullptr;
     // owned device buffers
     uint32_t *d_nbr = nullptr, *d_order = nullptr, *d_colour_start = nullptr;
     int8_t *d_J8 = nullptr;
@@ -192,7 +199,7 @@ static void prof_mark(pp_sim *s) {
 static void free_sim(pp_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *ptrs[] = {s->d_nbr, s->d_order, s->d_colour_start, s->d_J8, s->d_Jf, s->d_Jw, s->d_spins, s->d_words,
+    void *ptrs[] = {s->d_perm, s->d_items, s->d_nbr, s->d_order, s->d_colour_start, s->d_J8, s->d_Jf, s->d_Jw, s->d_spins, s->d_words,
                     s->d_words_alt, s->d_sid, s->d_energies, s->d_temps, s->d_mags, s->d_lut_metro, s->d_lut_gibbs,
                     s->pt.edge_attempts, s->pt.edge_acceptances, s->pt.round_trips, s->pt.trip_state, s->pt.swap_mask,
                     s->st.sums, s->st.hist, s->st.ql_at_q, s->st.ql2_at_q, s->d_dot_spin, s->d_dot_link};
@@ -207,6 +214,7 @@ static void free_sim(pp_sim *s) {
 
 extern "C" void pp_destroy(pp_sim *sim) { free_sim(sim); }
 extern "C" int32_t pp_get_layout(const pp_sim *sim) { return sim ? sim->layout : 0; }
+extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 
 // coupling classification: flags[0] non-unit value, flags[1] zero, flags[2] negative
 __global__ void classify_couplings_kernel(const float *J, int64_t n, int *flags) {
@@ -243,19 +251,48 @@ static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs
 // ---- kernel launch helpers ------------------------------------------------------------------
 static pp_status launch_energy(pp_sim *s, bool want_mags);
 
+template <int RPC, bool METRO>
+static pp_status launch_msc3d_t(pp_sim *s, const ModelView &m, uint32_t sweep_index, int n_sweeps, bool want_energy,
+                                bool want_mags, bool want_overlap) {
+    CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->msc3d_smem));
+    msc3d_kernel<RPC, METRO><<<(unsigned)(s->G * m.T), s->msc3d_nt, s->msc3d_smem, s->stream>>>(
+        m, s->gv, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, m.sample_offset / 32, s->d_dot_spin, s->d_dot_link);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+static pp_status launch_msc3d(pp_sim *s, const ModelView &m, int sweep_mode, uint32_t sweep_index, int n_sweeps,
+                              bool want_energy, bool want_mags, bool want_overlap) {
+    const bool metro = sweep_mode == PP_SWEEP_METROPOLIS && s->msc3d_metro;
+#define PP_M3(R_)                                                                                              \
+    return metro ? launch_msc3d_t<R_, true>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap) \
+                 : launch_msc3d_t<R_, false>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap)
+    switch (m.R) {
+        case 1: PP_M3(1);
+        case 2: PP_M3(2);
+        case 4: PP_M3(4);
+    }
+#undef PP_M3
+    return fail(PP_ERR_UNSUPPORTED, "msc3d: unsupported replica count");
+}
+
+// want_overlap: the caller wants the replica-pair dots of the post-sweep state; *overlap_done is set when the
+// sweep kernel produced them itself (fused epilogue), otherwise the caller launches launch_overlap().
 static pp_status launch_sweeps(pp_sim *s, int sweep_mode, uint32_t sweep_index, int n_sweeps, int exact_log,
-                               bool want_energy, bool want_mags) {
+                               bool want_energy, bool want_mags, bool want_overlap = false, bool *overlap_done = nullptr) {
     ModelView m = s->mv;
     m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
+    if (overlap_done) *overlap_done = false;
     if (s->layout == PP_LAYOUT_MSC) {
         const bool timed = n_sweeps > 0;
         if (timed) prof_mark(s);
-        if (s->msc3d && n_sweeps > 0) {
-            pp_status st = launch_msc3d(m, s->stream, sweep_index, n_sweeps, want_energy, want_mags,
-                                        s->mv.sample_offset / 32, &s->launches);
-            if (st != PP_OK) return fail(st, "msc3d launch failed");
-            prof_mark(s);
-            CUDA_TRY(cudaGetLastError());
+        if (s->msc3d) {
+            const bool ov = want_overlap && m.P > 0;
+            pp_status st = launch_msc3d(s, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags, ov);
+            if (st != PP_OK) return st;
+            if (overlap_done) *overlap_done = ov;
+            if (timed) prof_mark(s);
             return PP_OK;
         }
         const size_t smem = sizeof(uint32_t) * (size_t)m.N;
@@ -318,6 +355,10 @@ static pp_status launch_energy(pp_sim *s, bool want_mags) {
 static pp_status launch_overlap(pp_sim *s) {
     ModelView m = s->mv;
     if (m.P == 0) return PP_OK;
+    if (s->layout == PP_LAYOUT_MSC && s->msc3d) {
+        m.lut = s->d_lut_metro;
+        return launch_msc3d(s, m, PP_SWEEP_METROPOLIS, 0, 0, false, false, true);
+    }
     if (s->layout == PP_LAYOUT_MSC)
         msc_overlap_kernel<<<(unsigned)(s->G * m.P * m.T), MSC_BLOCK, 0, s->stream>>>(m, s->d_dot_spin, s->d_dot_link);
     else
@@ -424,18 +465,6 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
 
     const int64_t N = m.N;
     const int z = m.z;
-    // geometry tables
-    CREATE_TRY(cudaMalloc(&s->d_nbr, sizeof(uint32_t) * (size_t)N * 2 * z));
-    CREATE_TRY(cudaMemcpy(s->d_nbr, s->plan.nbr.data(), sizeof(uint32_t) * (size_t)N * 2 * z, cudaMemcpyHostToDevice));
-    CREATE_TRY(cudaMalloc(&s->d_order, sizeof(uint32_t) * (size_t)N));
-    CREATE_TRY(cudaMemcpy(s->d_order, s->plan.order.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice));
-    CREATE_TRY(cudaMalloc(&s->d_colour_start, sizeof(uint32_t) * (size_t)(m.n_colours + 1)));
-    CREATE_TRY(cudaMemcpy(s->d_colour_start, s->plan.colour_start.data(), sizeof(uint32_t) * (size_t)(m.n_colours + 1),
-                          cudaMemcpyHostToDevice));
-    m.nbr = s->d_nbr;
-    m.order = s->d_order;
-    m.colour_start = s->d_colour_start;
-
     // couplings: classify exactly like the reference's lookup gate (sweep.rs:109-118)
     const bool t_ok = temps_eligible(s->temps.data(), m.T);
     const int64_t n_coup = m.D * N * z;
@@ -482,16 +511,39 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         return fail(PP_ERR_INVALID, "unknown layout");
     }
 
+    // geometry tables; the multispin layout stores words in the plan's compact order (pp_plan.h)
+    {
+        const bool storage_space = s->layout == PP_LAYOUT_MSC && s->plan.compact;
+        std::vector<uint32_t> nbr_s, order_s;
+        if (storage_space) storage_tables(s->plan, nbr_s, order_s);
+        const std::vector<uint32_t> &nbr = storage_space ? nbr_s : s->plan.nbr;
+        const std::vector<uint32_t> &order = storage_space ? order_s : s->plan.order;
+        CREATE_TRY(cudaMalloc(&s->d_nbr, sizeof(uint32_t) * (size_t)N * 2 * z));
+        CREATE_TRY(cudaMemcpy(s->d_nbr, nbr.data(), sizeof(uint32_t) * (size_t)N * 2 * z, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&s->d_order, sizeof(uint32_t) * (size_t)N));
+        CREATE_TRY(cudaMemcpy(s->d_order, order.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&s->d_colour_start, sizeof(uint32_t) * (size_t)(m.n_colours + 1)));
+        CREATE_TRY(cudaMemcpy(s->d_colour_start, s->plan.colour_start.data(), sizeof(uint32_t) * (size_t)(m.n_colours + 1),
+                              cudaMemcpyHostToDevice));
+        if (storage_space) {
+            CREATE_TRY(cudaMalloc(&s->d_perm, sizeof(uint32_t) * (size_t)N));
+            CREATE_TRY(cudaMemcpy(s->d_perm, s->plan.perm.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice));
+        }
+        m.nbr = s->d_nbr;
+        m.order = s->d_order;
+        m.colour_start = s->d_colour_start;
+        m.perm = s->d_perm;
+    }
+
     if (s->layout == PP_LAYOUT_MSC) {
         s->G = (m.D + 31) / 32;
         if (m.coupling_class == COUP_UNIT) {
             CREATE_TRY(cudaMalloc(&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
-            msc_pack_couplings_kernel<<<blocks_for(s->G * z * N, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_Jw, m.D, N, z);
+            msc_pack_couplings_kernel<<<blocks_for(s->G * z * N, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_Jw, m.D, N, z, s->d_perm);
             CREATE_TRY(cudaStreamSynchronize(s->stream));
         }
         if (s->d_Jf) { cudaFree(s->d_Jf); s->d_Jf = nullptr; }
         CREATE_TRY(cudaMalloc(&s->d_words, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
-        s->msc3d = msc3d_supported(s->plan);
     } else {
         if (m.coupling_class == COUP_UNIT) {
             CREATE_TRY(cudaMalloc(&s->d_J8, (size_t)n_coup));
@@ -527,6 +579,35 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             uint32_t *&dst = mode == 0 ? s->d_lut_metro : s->d_lut_gibbs;
             CREATE_TRY(cudaMalloc(&dst, sizeof(uint32_t) * lut.size()));
             CREATE_TRY(cudaMemcpy(dst, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice));
+        }
+    }
+
+    // specialised 3-D multispin kernel (pp_kernels_msc3d.cuh)
+    if (s->layout == PP_LAYOUT_MSC && z == 3 && (m.R == 1 || m.R == 2 || m.R == 4)) {
+        s->m3 = msc3d_plan(s->plan);
+        if (s->m3.ok) {
+            int nt = 128;
+            auto cap_ok = [&](int n) { return 3 * (N / (n / m.R)) < (1 << MSC3D_KE) - 8 && N / (n / m.R) < (1 << MSC3D_KM) - 8; };
+            if (!cap_ok(nt)) nt = 256;
+            const size_t smem = sizeof(uint32_t) * ((size_t)m.R * N + 4 + (size_t)m.R * 4 * (nt / m.R / 32) * 32);
+            if (cap_ok(nt) && smem <= 227 * 1024) {
+                CREATE_TRY(cudaMalloc(&s->d_items, sizeof(uint16_t) * s->m3.items.size()));
+                CREATE_TRY(cudaMemcpy(s->d_items, s->m3.items.data(), sizeof(uint16_t) * s->m3.items.size(), cudaMemcpyHostToDevice));
+                s->gv.items = s->d_items;
+                s->gv.n_items = s->m3.n_items;
+                s->gv.N = (uint32_t)N;
+                s->gv.N2 = (uint32_t)(N / 2);
+                s->msc3d = true;
+                s->msc3d_nt = nt;
+                s->msc3d_smem = smem;
+                // Metropolis: energy_change >= 0 always accepts (sweep.rs:141-145), i.e. counts for unsat >= 3 are 2^24
+                std::vector<uint32_t> lut((size_t)m.T * 13);
+                pp_metropolis_lookup(s->temps.data(), m.T, 3, PP_SWEEP_METROPOLIS, lut.data());
+                s->msc3d_metro = true;
+                for (int t = 0; t < m.T; t++)
+                    for (int u = 3; u <= 6; u++)
+                        if (lut[(size_t)t * 13 + 2 * u] != F24) s->msc3d_metro = false;
+            }
         }
     }
 
@@ -664,11 +745,13 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         const int64_t last = sweep_id + batch - 1;
         const bool record = last >= cfg->warmup_sweeps;                                   // mod.rs:410
         const bool pt_this = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;        // mod.rs:486-488
-        st = launch_sweeps(s, cfg->sweep_mode, s->sweep_counter, (int)batch, cfg->exact_log, record || pt_this, record);
+        bool overlap_done = false;
+        st = launch_sweeps(s, cfg->sweep_mode, s->sweep_counter, (int)batch, cfg->exact_log, record || pt_this, record,
+                           record, &overlap_done);
         if (st != PP_OK) return st;
         s->sweep_counter += (uint32_t)batch;
         if (record) {
-            st = launch_overlap(s);                                                         // mod.rs:527-529
+            if (!overlap_done) st = launch_overlap(s);                                      // mod.rs:527-529
             if (st != PP_OK) return st;
             fold_kernel<<<blocks_for(m.D * m.T, 128), 128, 0, s->stream>>>(m, s->st, m.P > 0);  // mod.rs:543-578
             s->launches++;

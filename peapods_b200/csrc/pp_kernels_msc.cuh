@@ -121,7 +121,7 @@ __global__ void msc_init_kernel(ModelView m) {
     uint32_t *dst = m.words + wsys * m.N;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if (q * 4 + j < m.N) dst[q * 4 + j] = w[j];
+        if (q * 4 + j < m.N) dst[m.perm ? m.perm[q * 4 + j] : (uint32_t)(q * 4 + j)] = w[j];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,7 +293,7 @@ __global__ void msc_unpack_kernel(ModelView m, int64_t d, int8_t *out /* [S][N] 
     const int pos = (int)(gid / m.N);
     const int64_t i = gid % m.N;
     const int sys = m.system_ids[d * m.S + pos];
-    const uint32_t w = m.words[((d >> 5) * m.S + pos) * m.N + i];
+    const uint32_t w = m.words[((d >> 5) * m.S + pos) * m.N + (m.perm ? m.perm[i] : (uint32_t)i)];
     out[(int64_t)sys * m.N + i] = ((w >> (d & 31)) & 1u) ? (int8_t)-1 : (int8_t)1;
 }
 
@@ -303,13 +303,13 @@ __global__ void msc_pack_kernel(ModelView m, int64_t d, const int8_t *in /* [S][
     const int pos = (int)(gid / m.N);
     const int64_t i = gid % m.N;
     const int sys = m.system_ids[d * m.S + pos];
-    uint32_t *w = &m.words[((d >> 5) * m.S + pos) * m.N + i];
+    uint32_t *w = &m.words[((d >> 5) * m.S + pos) * m.N + (m.perm ? m.perm[i] : (uint32_t)i)];
     const uint32_t bit = 1u << (d & 31);
     *w = in[(int64_t)sys * m.N + i] < 0 ? (*w | bit) : (*w & ~bit);
 }
 
 // couplings: float [D][N][z] -> sign words [G][z][N]; one thread per word
-__global__ void msc_pack_couplings_kernel(const float *Jf, uint32_t *Jw, int64_t D, int64_t N, int z) {
+__global__ void msc_pack_couplings_kernel(const float *Jf, uint32_t *Jw, int64_t D, int64_t N, int z, const uint32_t *perm) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t G = (D + 31) / 32;
     if (gid >= G * z * N) return;
@@ -321,7 +321,7 @@ __global__ void msc_pack_couplings_kernel(const float *Jf, uint32_t *Jw, int64_t
         const int64_t d = g * 32 + l;
         if (d < D && Jf[(d * N + i) * z + k] < 0.0f) w |= 1u << l;
     }
-    Jw[gid] = w;
+    Jw[(g * z + k) * N + (perm ? perm[i] : (uint32_t)i)] = w;
 }
 
 }  // namespace pp

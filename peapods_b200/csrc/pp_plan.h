@@ -32,6 +32,11 @@ struct LatticePlan {
     std::vector<uint16_t> colour;       // [n_spins]
     std::vector<uint32_t> order;        // sites sorted by (colour, index)
     std::vector<uint32_t> colour_start; // [n_colours+1] into order
+    // "compact" storage order (used by the multispin layout): when there are two colours and the sites
+    // 2j, 2j+1 always differ in colour, site i is stored at perm[i] = colour(i)*N/2 + (i>>1), i.e. the two
+    // colour classes are contiguous halves and the storage index inside a half is the RNG-SPEC colour rank.
+    bool compact = false;
+    std::vector<uint32_t> perm;         // [n_spins] site -> storage index (identity when !compact)
 };
 
 inline int64_t rem_euclid(int64_t a, int64_t m) {
@@ -159,7 +164,26 @@ inline std::string build_plan(int n_dims, const int64_t *shape, int n_offsets, c
     p.order.assign((size_t)p.n_spins, 0);
     std::vector<uint32_t> fill(p.colour_start.begin(), p.colour_start.end() - 1);
     for (int64_t i = 0; i < p.n_spins; i++) p.order[fill[p.colour[(size_t)i]]++] = (uint32_t)i;
+    // compact storage order
+    p.compact = p.n_colours == 2 && p.n_spins % 2 == 0;
+    for (int64_t i = 0; i + 1 < p.n_spins && p.compact; i += 2)
+        if (p.colour[(size_t)i] == p.colour[(size_t)i + 1]) p.compact = false;
+    p.perm.assign((size_t)p.n_spins, 0);
+    for (int64_t i = 0; i < p.n_spins; i++)
+        p.perm[(size_t)i] = p.compact ? (uint32_t)(p.colour[(size_t)i] * (p.n_spins / 2) + (i >> 1)) : (uint32_t)i;
     return "";
+}
+
+// neighbour / order tables re-expressed in storage space (identity when !compact)
+inline void storage_tables(const LatticePlan &p, std::vector<uint32_t> &nbr_s, std::vector<uint32_t> &order_s) {
+    const int z2 = 2 * p.z;
+    nbr_s.assign(p.nbr.size(), 0);
+    order_s.assign(p.order.size(), 0);
+    for (int64_t i = 0; i < p.n_spins; i++) {
+        const uint32_t si = p.perm[(size_t)i];
+        for (int k = 0; k < z2; k++) nbr_s[(size_t)si * z2 + k] = p.perm[p.nbr[(size_t)i * z2 + k]];
+    }
+    for (int64_t q = 0; q < p.n_spins; q++) order_s[(size_t)q] = p.perm[p.order[(size_t)q]];
 }
 
 }  // namespace pp

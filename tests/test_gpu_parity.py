@@ -143,6 +143,54 @@ def test_msc_sample_with_pt_and_overlap_is_bit_exact(oracle, shape, kind, offset
         assert_results_equal(rg, rc)
 
 
+MSC3D_CASES = [
+    # shape, kind, D, R, temps  -- all taken by the stride-based 3-D multispin kernel
+    ((8, 8, 8), "bimodal", 32, 1, [0.8, 1.1, 1.4]),
+    ((8, 8, 8), "bimodal", 45, 4, np.linspace(0.8, 1.6, 5)),          # padded second word group
+    ((4, 6, 8), "bimodal", 33, 2, [0.9, 1.3, 2.0]),                   # non-cubic, one quad per row
+    ((2, 2, 8), "bimodal", 32, 4, [1.0, 2.0]),                        # extent 2: forward == backward neighbour
+    ((6, 4, 16), "bimodal", 64, 2, [0.8, 1.2]),
+    ((8, 8, 8), "ferro", 32, 2, [3.5, 4.5, 5.5]),                     # no coupling words
+    ((16, 16, 16), "bimodal", 64, 4, np.linspace(0.8, 1.4, 3)),       # BASELINE config 2 geometry, R = 4
+]
+
+
+@pytest.mark.parametrize("schedule", ["single_random_edge", "full_ladder"])
+@pytest.mark.parametrize("shape,kind,D,R,temps", MSC3D_CASES)
+def test_msc3d_sample_is_bit_exact(oracle, shape, kind, D, R, temps, schedule):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, layout="msc")
+    assert gpu.uses_msc3d
+    assert_state_equal(gpu, cpu, D)
+    for n_sweeps, interval, mode in ((1, None, "metropolis"), (24, 1, "metropolis"), (11, 3, "metropolis"), (7, 2, "gibbs")):
+        rg = gpu.sample(n_sweeps, mode, pt_interval=interval, pt_schedule=schedule)
+        rc = cpu.sample(n_sweeps, mode, pt_interval=interval, pt_schedule=schedule)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        for d in range(0, D, 7):
+            assert np.array_equal(gpu.get_energies(d), cpu.energies(d))
+
+
+def test_msc3d_operator_entry_points_match_oracle(oracle):
+    shape, temps, R, DD = (4, 4, 8), [0.9, 1.2, 1.5], 4, 37
+    gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, DD, layout="msc")
+    assert gpu.uses_msc3d
+    lat = oracle.Lattice(shape)
+    J = couplings("bimodal", shape, 3, DD, 7)
+    rng = np.random.default_rng(11)
+    S, N, T = R * len(temps), lat.n_spins, len(temps)
+    spins = (2 * rng.integers(0, 2, size=(DD, S, N)) - 1).astype(np.int8)
+    for d in range(DD):
+        gpu.set_spins(spins[d], d)
+    e_g, m_g = gpu.op_energies_mags()
+    ds, dl = gpu.op_overlap()
+    for d in range(DD):
+        e_c, m_c = lat.energies_mags(spins[d], J[d])
+        assert np.array_equal(m_g[d], m_c) and np.array_equal(e_g[d], e_c)
+        for p in range(R // 2):
+            for t in range(T):
+                assert (ds[d, p, t], dl[d, p, t]) == lat.overlap_dots(spins[d][(2 * p) * T + t], spins[d][(2 * p + 1) * T + t])
+
+
 @pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
 @pytest.mark.parametrize("shape,offsets,D", [((4, 4, 4), None, 2), ((8, 8, 8), None, 1), ((6, 6), TRI, 2)])
 def test_gaussian_couplings_exact_log_spins_and_energy_tolerance(oracle, shape, offsets, D, mode):
