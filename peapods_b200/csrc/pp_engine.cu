@@ -155,7 +155,7 @@ struct pp_sim {
     int64_t G = 0;                                     // word groups (MSC)
     bool msc3d = false;                                // specialised 3-D hypercubic MSC kernel usable
     bool msc3d_metro = false;                          // Metropolis counts for unsat >= 3 are all 2^24
-    int msc3d_nt = 128;                                // threads per CTA of the msc3d kernel
+    int msc3d_nh = 2;                                  // temperature slots (256-thread halves) per CTA of the msc3d kernel
     size_t msc3d_smem = 0;
     Msc3dPlan m3;
     Msc3dView gv{};
@@ -251,11 +251,12 @@ static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs
 // ---- kernel launch helpers ------------------------------------------------------------------
 static pp_status launch_energy(pp_sim *s, bool want_mags);
 
-template <int RPC, bool METRO>
+template <int RPC, bool METRO, int NH>
 static pp_status launch_msc3d_t(pp_sim *s, const ModelView &m, uint32_t sweep_index, int n_sweeps, bool want_energy,
                                 bool want_mags, bool want_overlap) {
-    CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->msc3d_smem));
-    msc3d_kernel<RPC, METRO><<<(unsigned)(s->G * m.T), s->msc3d_nt, s->msc3d_smem, s->stream>>>(
+    CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->msc3d_smem));
+    const unsigned grid = (unsigned)(s->G * ((m.T + NH - 1) / NH));
+    msc3d_kernel<RPC, METRO, NH><<<grid, MSC3D_NTH * NH, s->msc3d_smem, s->stream>>>(
         m, s->gv, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, m.sample_offset / 32, s->d_dot_spin, s->d_dot_link);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -265,9 +266,12 @@ static pp_status launch_msc3d_t(pp_sim *s, const ModelView &m, uint32_t sweep_in
 static pp_status launch_msc3d(pp_sim *s, const ModelView &m, int sweep_mode, uint32_t sweep_index, int n_sweeps,
                               bool want_energy, bool want_mags, bool want_overlap) {
     const bool metro = sweep_mode == PP_SWEEP_METROPOLIS && s->msc3d_metro;
-#define PP_M3(R_)                                                                                              \
-    return metro ? launch_msc3d_t<R_, true>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap) \
-                 : launch_msc3d_t<R_, false>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap)
+    const bool two = s->msc3d_nh == 2;
+#define PP_M3(R_)                                                                                                         \
+    return metro ? (two ? launch_msc3d_t<R_, true, 2>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap)   \
+                        : launch_msc3d_t<R_, true, 1>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap))  \
+                 : (two ? launch_msc3d_t<R_, false, 2>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap)  \
+                        : launch_msc3d_t<R_, false, 1>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap))
     switch (m.R) {
         case 1: PP_M3(1);
         case 2: PP_M3(2);
@@ -586,11 +590,18 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     if (s->layout == PP_LAYOUT_MSC && z == 3 && (m.R == 1 || m.R == 2 || m.R == 4)) {
         s->m3 = msc3d_plan(s->plan);
         if (s->m3.ok) {
-            int nt = 128;
-            auto cap_ok = [&](int n) { return 3 * (N / (n / m.R)) < (1 << MSC3D_KE) - 8 && N / (n / m.R) < (1 << MSC3D_KM) - 8; };
-            if (!cap_ok(nt)) nt = 256;
-            const size_t smem = sizeof(uint32_t) * ((size_t)m.R * N + 4 + (size_t)m.R * 4 * (nt / m.R / 32) * 32);
-            if (cap_ok(nt) && smem <= 227 * 1024) {
+            // two temperature slots per CTA when they fit next to the coupling words, else one
+            auto smem_words = [&](int nh) {
+                return (size_t)(m.coupling_class == COUP_UNIT ? 3 * N : 0) + 4 * (size_t)s->m3.n_items + (size_t)nh * m.R * N + 8 +
+                       (size_t)nh * 512;
+            };
+            int nh = 2;
+            if (smem_words(nh) * 4 > 227 * 1024 - 1024) nh = 1;
+            // per-thread counter capacity of the epilogue (MSC3D_KE / MSC3D_KM planes)
+            const int64_t sites_em = N / (32 * (4 / m.R)), sites_pair = m.P > 0 ? N / (32 * (4 / m.P)) : 0;
+            const bool cap_ok = 3 * sites_em < (1 << MSC3D_KE) - 8 && sites_em < (1 << MSC3D_KM) - 8 &&
+                                3 * sites_pair < (1 << MSC3D_KE) - 8;
+            if (cap_ok && smem_words(nh) * 4 <= 227 * 1024 - 1024) {
                 CREATE_TRY(cudaMalloc(&s->d_items, sizeof(uint16_t) * s->m3.items.size()));
                 CREATE_TRY(cudaMemcpy(s->d_items, s->m3.items.data(), sizeof(uint16_t) * s->m3.items.size(), cudaMemcpyHostToDevice));
                 s->gv.items = s->d_items;
@@ -598,15 +609,18 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 s->gv.N = (uint32_t)N;
                 s->gv.N2 = (uint32_t)(N / 2);
                 s->msc3d = true;
-                s->msc3d_nt = nt;
-                s->msc3d_smem = smem;
-                // Metropolis: energy_change >= 0 always accepts (sweep.rs:141-145), i.e. counts for unsat >= 3 are 2^24
+                s->msc3d_nh = nh;
+                s->msc3d_smem = smem_words(nh) * 4;
+                // Metropolis fast path: counts for unsat >= 3 (energy_change >= 0) are 2^24 (sweep.rs:141-145) and the
+                // others are below 2^24, so (draw < count) == (raw32 < count << 8)
                 std::vector<uint32_t> lut((size_t)m.T * 13);
                 pp_metropolis_lookup(s->temps.data(), m.T, 3, PP_SWEEP_METROPOLIS, lut.data());
                 s->msc3d_metro = true;
                 for (int t = 0; t < m.T; t++)
-                    for (int u = 3; u <= 6; u++)
-                        if (lut[(size_t)t * 13 + 2 * u] != F24) s->msc3d_metro = false;
+                    for (int u = 0; u <= 6; u++) {
+                        const uint32_t c = lut[(size_t)t * 13 + 2 * u];
+                        if (u >= 3 ? c != F24 : c >= F24) s->msc3d_metro = false;
+                    }
             }
         }
     }

@@ -14,8 +14,9 @@
 // every neighbour of such a quad is again a 128-bit group of the other colour (plus one extra word for
 // the +-x2 neighbour that crosses the segment).  A CTA owns temperature slot t of word group g for all
 // R replicas: the R*N words live in shared memory for the whole launch (one bulk-async load, one
-// bulk-async store per system = exactly the algorithmic 2 x 4 B per word), the sign words of the
-// couplings are read through L1 once per quad and reused by the R replicas.
+// bulk-async store per system = exactly the algorithmic 2 x 4 B per word); two such slots share one CTA
+// (two independent 256-thread halves) together with one shared-memory copy of the group's coupling sign
+// words, which are read once per quad and reused by the R replicas.
 //
 // Per word update (Metropolis): 6 three-input XORs (bond words), two bit-sliced full adders and five
 // LOP3s give the masks [unsat >= 1], [>= 2], [>= 3]; the 24-bit draw (one Philox4x32-10 call per quad
@@ -50,19 +51,27 @@ inline Msc3dPlan msc3d_plan(const LatticePlan &p) {
     q.QPR = q.LXH / 4;
     q.n_items = q.L0 * q.L1 * q.QPR;
     q.items.resize((size_t)q.n_items * 8);
-    for (int it = 0; it < q.n_items; it++) {
-        const int row = it / q.QPR, h = it % q.QPR, x0 = row / q.L1, x1 = row % q.L1;
-        auto at = [&](int a, int b, int j) { return (uint16_t)((a * q.L1 + b) * q.LXH + j); };
-        uint16_t *d = &q.items[(size_t)it * 8];
-        d[0] = at(x0, x1, 4 * h);
-        d[1] = at((x0 + 1) % q.L0, x1, 4 * h);
-        d[2] = at((x0 + q.L0 - 1) % q.L0, x1, 4 * h);
-        d[3] = at(x0, (x1 + 1) % q.L1, 4 * h);
-        d[4] = at(x0, (x1 + q.L1 - 1) % q.L1, 4 * h);
-        d[5] = at(x0, x1, (4 * h + q.LXH - 1) % q.LXH);
-        d[6] = at(x0, x1, (4 * h + 4) % q.LXH);
-        d[7] = (uint16_t)((x0 + x1) & 1);
-    }
+    // Item order: all segments of rows with (x0 + x1) even first, then the odd ones, so that the 32 items a warp takes
+    // together share the x2-parity of their sites (no divergence on it); inside a parity class walk (x0>>1, x1, h), which
+    // alternates between the two x0 planes of a pair and keeps the 128-bit shared-memory accesses of a quarter-warp
+    // on distinct banks for the usual power-of-two extents.
+    int it = 0;
+    for (int par = 0; par < 2; par++)
+        for (int zb = 0; zb < q.L0 / 2; zb++)
+            for (int x1 = 0; x1 < q.L1; x1++)
+                for (int h = 0; h < q.QPR; h++, it++) {
+                    const int x0 = 2 * zb + ((x1 + par) & 1);
+                    auto at = [&](int a, int b, int j) { return (uint16_t)((a * q.L1 + b) * q.LXH + j); };
+                    uint16_t *d = &q.items[(size_t)it * 8];
+                    d[0] = at(x0, x1, 4 * h);
+                    d[1] = at((x0 + 1) % q.L0, x1, 4 * h);
+                    d[2] = at((x0 + q.L0 - 1) % q.L0, x1, 4 * h);
+                    d[3] = at(x0, (x1 + 1) % q.L1, 4 * h);
+                    d[4] = at(x0, (x1 + q.L1 - 1) % q.L1, 4 * h);
+                    d[5] = at(x0, x1, (4 * h + q.LXH - 1) % q.LXH);
+                    d[6] = at(x0, x1, (4 * h + 4) % q.LXH);
+                    d[7] = (uint16_t)par;
+                }
     q.ok = true;
     return q;
 }
@@ -80,6 +89,37 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { r
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D bulk-async copy global -> shared (TMA engine), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void half_barrier(int half, int nthreads) {  // named barrier of one half of the CTA
+    asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "r"(nthreads) : "memory");
+}
 
 // bit-sliced vertical counter: plane b holds bit b of 32 independent per-lane counts
 template <int K>
@@ -106,7 +146,6 @@ struct VAcc {
         p[LVL] = xor3(p[LVL], a, b);
         return c;
     }
-    // one word into plane LVL, return the carry
     template <int LVL>
     __device__ __forceinline__ uint32_t half(uint32_t a) {
         const uint32_t c = p[LVL] & a;
@@ -132,8 +171,7 @@ struct VAcc {
     }
 };
 
-// Sum the K-plane counters of the 32 threads of a warp (bit-sliced butterfly), then thread l returns
-// the total of lane l.
+// Sum the K-plane counters of the 32 threads of a warp (bit-sliced butterfly); thread l returns the total of lane l.
 template <int K>
 __device__ __forceinline__ uint32_t warp_lane_total(const VAcc<K> &v) {
     constexpr int KW = K + 5;
@@ -169,274 +207,322 @@ __device__ __forceinline__ void unpack_item(const uint4 d, uint32_t &self, uint3
 }
 
 __device__ __forceinline__ uint4 lds4(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ uint4 ldg4(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ void to_arr(const uint4 v, uint32_t *a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
-constexpr int MSC3D_KE = 10;  // planes of the per-thread unsatisfied-bond counter   (3*sites_per_thread < 1024)
-constexpr int MSC3D_KM = 9;   // planes of the per-thread down-spin / q counters     (sites_per_thread   < 512)
+constexpr int MSC3D_KE = 10;  // planes of the per-thread unsatisfied-bond counters (3*sites_per_thread < 1016)
+constexpr int MSC3D_KM = 9;   // planes of the per-thread down-spin / q counters     (sites_per_thread   < 504)
+constexpr int MSC3D_NTH = 256;  // threads per half
+
+// One quad (four same-colour sites of one row segment) of all RPC replicas.  P = the quad's sites sit at x2 = 2j + P.
+//   sp: the half's [RPC][N] words; J: [3][N] coupling sign words in shared memory or nullptr (all +1)
+template <int RPC, bool METRO, bool P>
+__device__ __forceinline__ void msc3d_sweep_item(uint32_t *sp, const uint32_t *J, const uint32_t N, const uint32_t so,
+                                                 const uint32_t oo, const uint4 desc, const uint32_t (&thr)[7],
+                                                 const uint32_t sweep, const uint32_t pos0, const uint32_t pos_stride,
+                                                 const uint32_t tag, const uint32_t k0, const uint32_t k1) {
+    uint32_t self, zp, zm, yp, ym, eL, eR, par;
+    unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
+    (void)par;
+    // coupling sign words (bit = 1: J = -1); bond (i, d) is stored at its lower site i
+    uint32_t Jf0[4], Jf1[4], Jf2[4], Jb0[4], Jb1[4], Jb2[4];
+    if (J) {
+        to_arr(lds4(J + 0 * N + so + self), Jf0);
+        to_arr(lds4(J + 1 * N + so + self), Jf1);
+        to_arr(lds4(J + 2 * N + so + self), Jf2);
+        to_arr(lds4(J + 0 * N + oo + zm), Jb0);
+        to_arr(lds4(J + 1 * N + oo + ym), Jb1);
+        const uint4 v = lds4(J + 2 * N + oo + self);
+        if (P) { Jb2[0] = v.x; Jb2[1] = v.y; Jb2[2] = v.z; Jb2[3] = v.w; }
+        else   { Jb2[0] = J[2 * N + oo + eL]; Jb2[1] = v.x; Jb2[2] = v.y; Jb2[3] = v.z; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) Jf0[j] = Jf1[j] = Jf2[j] = Jb0[j] = Jb1[j] = Jb2[j] = 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; r++) {
+        uint32_t *sys = sp + (size_t)r * N;
+        const u32x4 rnd = philox4x32_10(self >> 2, sweep, pos0 + (uint32_t)r * pos_stride, tag, k0, k1);
+        uint32_t s[4], zpv[4], zmv[4], ypv[4], ymv[4], xr[4], xl[4];
+        to_arr(lds4(sys + so + self), s);
+        to_arr(lds4(sys + oo + zp), zpv);
+        to_arr(lds4(sys + oo + zm), zmv);
+        to_arr(lds4(sys + oo + yp), ypv);
+        to_arr(lds4(sys + oo + ym), ymv);
+        const uint4 O = lds4(sys + oo + self);
+        const uint32_t E = sys[oo + (P ? eR : eL)];
+        if (P) { xl[0] = O.x; xl[1] = O.y; xl[2] = O.z; xl[3] = O.w; xr[0] = O.y; xr[1] = O.z; xr[2] = O.w; xr[3] = E; }
+        else   { xl[0] = E;   xl[1] = O.x; xl[2] = O.y; xl[3] = O.z; xr[0] = O.x; xr[1] = O.y; xr[2] = O.z; xr[3] = O.w; }
+        const uint32_t raw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b0 = xor3(s[j], zpv[j], Jf0[j]), b1 = xor3(s[j], zmv[j], Jb0[j]);
+            const uint32_t b2 = xor3(s[j], ypv[j], Jf1[j]), b3 = xor3(s[j], ymv[j], Jb1[j]);
+            const uint32_t b4 = xor3(s[j], xr[j], Jf2[j]), b5 = xor3(s[j], xl[j], Jb2[j]);
+            const uint32_t s1 = xor3(b0, b1, b2), c1 = maj3(b0, b1, b2);
+            const uint32_t s2 = xor3(b3, b4, b5), c2 = maj3(b3, b4, b5);
+            const uint32_t kk = s1 & s2, oo2 = s1 | s2;
+            uint32_t flip;
+            if (METRO) {
+                // thr[u] = count[u] << 8 with count[u] < 2^24 for unsat u = 0..2 and count = 2^24 (always accept,
+                // sweep.rs:141-145) for u >= 3:  (raw >> 8) < count  <=>  raw < thr
+                const uint32_t ge1 = oo2 | c1 | c2, ge2 = kk | c1 | c2, ge3 = maj3(c1, c2, oo2);
+                flip = ge3;
+                if (raw[j] < thr[2]) flip = ge2;
+                if (raw[j] < thr[1]) flip = ge1;
+                if (raw[j] < thr[0]) flip = 0xFFFFFFFFu;
+            } else {  // thr[u] = count[u]
+                const uint32_t x0 = s1 ^ s2, y1 = xor3(c1, c2, kk), y2 = maj3(c1, c2, kk);
+                const uint32_t draw = raw[j] >> 8;
+                flip = 0u;
+#pragma unroll
+                for (int u = 0; u < 7; u++) {
+                    const uint32_t eq = ((u & 1) ? x0 : ~x0) & ((u & 2) ? y1 : ~y1) & ((u & 4) ? y2 : ~y2);
+                    if (draw < thr[u]) flip |= eq;
+                }
+            }
+            s[j] ^= flip;
+        }
+        *reinterpret_cast<uint4 *>(sys + so + self) = make_uint4(s[0], s[1], s[2], s[3]);
+    }
+}
+
+// the 8 sites of one row segment of system A: words 0..3 colour 0, 4..7 colour 1, with their +x0, +x1, +x2 neighbours
+template <bool PAR>
+__device__ __forceinline__ void msc3d_load_segment(const uint32_t *A, const uint32_t N2, const uint32_t self,
+                                                   const uint32_t zp, const uint32_t yp, const uint32_t eR, uint32_t *a,
+                                                   uint32_t *az, uint32_t *ay, uint32_t *ax) {
+    const uint4 s0 = lds4(A + self), s1 = lds4(A + N2 + self);
+    to_arr(s0, a); to_arr(s1, a + 4);
+    to_arr(lds4(A + N2 + zp), az); to_arr(lds4(A + zp), az + 4);
+    to_arr(lds4(A + N2 + yp), ay); to_arr(lds4(A + yp), ay + 4);
+    // colour c sites sit at x2 = 2j + (PAR ^ c); their +x2 neighbour is word j of the other colour when that is 0, word j+1 when 1
+    if (!PAR) {
+        ax[0] = s1.x; ax[1] = s1.y; ax[2] = s1.z; ax[3] = s1.w;
+        ax[4] = s0.y; ax[5] = s0.z; ax[6] = s0.w; ax[7] = A[eR];
+    } else {
+        ax[0] = s1.y; ax[1] = s1.z; ax[2] = s1.w; ax[3] = A[N2 + eR];
+        ax[4] = s0.x; ax[5] = s0.y; ax[6] = s0.z; ax[7] = s0.w;
+    }
+}
+
+template <bool PAR>
+__device__ __forceinline__ void msc3d_em_item(const uint32_t *A, const uint32_t *J, const uint32_t N, const uint32_t N2,
+                                              const uint4 desc, const int want_energy, const int want_mags,
+                                              VAcc<MSC3D_KE> &ve, VAcc<MSC3D_KM> &vm) {
+    uint32_t self, zp, zm, yp, ym, eL, eR, par;
+    unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
+    (void)zm; (void)ym; (void)eL; (void)par;
+    uint32_t a[8], az[8], ay[8], ax[8];
+    msc3d_load_segment<PAR>(A, N2, self, zp, yp, eR, a, az, ay, ax);
+    if (want_mags) vm.add8(a);
+    if (want_energy) {
+        uint32_t j0[8], j1[8], j2[8];
+        if (J) {
+            to_arr(lds4(J + 0 * N + self), j0); to_arr(lds4(J + 0 * N + N2 + self), j0 + 4);
+            to_arr(lds4(J + 1 * N + self), j1); to_arr(lds4(J + 1 * N + N2 + self), j1 + 4);
+            to_arr(lds4(J + 2 * N + self), j2); to_arr(lds4(J + 2 * N + N2 + self), j2 + 4);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) j0[j] = j1[j] = j2[j] = 0u;
+        }
+        uint32_t sb[8], cb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {  // energy.rs:99-107: forward bonds only, each bond once
+            const uint32_t b0 = xor3(a[j], az[j], j0[j]), b1 = xor3(a[j], ay[j], j1[j]), b2 = xor3(a[j], ax[j], j2[j]);
+            sb[j] = xor3(b0, b1, b2);
+            cb[j] = maj3(b0, b1, b2);
+        }
+        ve.add8_8(sb, cb);
+    }
+}
+
+template <bool PAR>
+__device__ __forceinline__ void msc3d_pair_item(const uint32_t *A, const uint32_t *B, const uint32_t N2, const uint4 desc,
+                                                VAcc<MSC3D_KE> &vl, VAcc<MSC3D_KM> &vq) {
+    uint32_t self, zp, zm, yp, ym, eL, eR, par;
+    unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
+    (void)zm; (void)ym; (void)eL; (void)par;
+    uint32_t a[8], az[8], ay[8], ax[8], b[8], bz[8], by[8], bx[8];
+    msc3d_load_segment<PAR>(A, N2, self, zp, yp, eR, a, az, ay, ax);
+    msc3d_load_segment<PAR>(B, N2, self, zp, yp, eR, b, bz, by, bx);
+    uint32_t x[8], sb[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {  // overlap.rs:266-276: x = 1 where q_i = -1; link word = x_i ^ x_fwd
+        x[j] = a[j] ^ b[j];
+        const uint32_t l0 = xor3(x[j], az[j], bz[j]), l1 = xor3(x[j], ay[j], by[j]), l2 = xor3(x[j], ax[j], bx[j]);
+        sb[j] = xor3(l0, l1, l2);
+        cb[j] = maj3(l0, l1, l2);
+    }
+    vq.add8(x);
+    vl.add8_8(sb, cb);
+}
 
 // ------------------------------------------------------------------------------------------------
-// grid.x = G*T (word group, temperature slot); block = NT threads, NT % (32*RPC) == 0.
-// dynamic smem: RPC*N words + 16 B (mbarrier) + RPC*4*(NT/RPC/32)*32 words (reduction scratch)
-template <int RPC, bool METRO>
-__global__ void __launch_bounds__(256, 2)
+// grid.x = G * ceil(T / NH); block = NH * 256 threads.  Half h of CTA (g, tp) owns temperature slot t = tp*NH + h of
+// word group g for all RPC replicas; the halves share the coupling words and the item table in shared memory and
+// otherwise run independently (named barriers), so one half can stage data while the other computes.
+// dynamic smem (words): [3N coupling words | 4*n_items item table | NH*RPC*N spins | 8 (mbarriers) | NH*512 scratch]
+template <int RPC, bool METRO, int NH>
+__global__ void __launch_bounds__(MSC3D_NTH *NH, 1)
 msc3d_kernel(ModelView m, Msc3dView gv, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags,
              int want_overlap, int64_t group_offset, long long *dot_spin, long long *dot_link) {
     extern __shared__ __align__(128) uint32_t smem[];
     const uint32_t N = gv.N, N2 = gv.N2;
-    uint32_t *sp = smem;                                                    // [RPC][N]
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + (size_t)RPC * N);
-    uint32_t *red = smem + (size_t)RPC * N + 4;                             // reduction scratch
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int64_t g = blockIdx.x / m.T;
-    const int t = blockIdx.x % m.T;
+    const bool has_J = m.Jw != nullptr;
+    uint32_t *Jsm = smem;
+    uint4 *items = reinterpret_cast<uint4 *>(smem + (has_J ? 3 * N : 0));
+    uint32_t *sp_all = reinterpret_cast<uint32_t *>(items + gv.n_items);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp_all + (size_t)NH * RPC * N);
+    uint32_t *red_all = reinterpret_cast<uint32_t *>(bars + 4);
+    const int tid = threadIdx.x;
+    const int half = NH == 1 ? 0 : tid / MSC3D_NTH, ht = tid - half * MSC3D_NTH;
+    const int TP = (m.T + NH - 1) / NH;
+    const int64_t g = blockIdx.x / TP;
+    const int t = (int)(blockIdx.x % TP) * NH + half;
     const uint32_t bytes = N * 4u;
+    uint32_t *sp = sp_all + (size_t)half * RPC * N;
+    uint32_t *red = red_all + half * 512;
+    const uint32_t *J = has_J ? Jsm : nullptr;
 
-    // ---- stage in: one bulk-async copy per system, completion on an mbarrier
+    // ---- stage in: bulk-async copies, completion on mbarriers (bars[0]: couplings + item table, bars[1+h]: spins)
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        mbar_init(&bars[0], 1);
+        for (int h = 0; h < NH; h++) mbar_init(&bars[1 + h], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes * RPC) : "memory");
-#pragma unroll
-        for (int r = 0; r < RPC; r++) {
-            const uint32_t *src = m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(sp + (size_t)r * N)),
-                         "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                         : "memory");
-        }
     }
-    // acceptance counts of this temperature: cnt[u] = table[t][2u]  (sweep.rs:162-166, index ec + 2z' = 2*unsat)
-    uint32_t cnt[7];
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], (has_J ? 3u * bytes : 0u) + (uint32_t)gv.n_items * 16u);
+        if (has_J) bulk_g2s(Jsm, m.Jw + g * 3 * (int64_t)N, 3u * bytes, &bars[0]);
+        bulk_g2s(items, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
+    }
+    if (t >= m.T) return;  // odd T: the last CTA of a group has an idle half
+    if (ht == 0) {
+        mbar_expect_tx(&bars[1 + half], bytes * RPC);
 #pragma unroll
-    for (int u = 0; u < 7; u++) cnt[u] = m.lut[t * 13 + 2 * u];
+        for (int r = 0; r < RPC; r++)
+            bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, &bars[1 + half]);
+    }
+    // acceptance thresholds of this temperature: count[u] = table[t][2u]  (sweep.rs:162-166, index ec + 2z' = 2*unsat)
+    uint32_t thr[7];
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+        const uint32_t cnt = m.lut[t * 13 + 2 * u];
+        thr[u] = METRO ? (cnt << 8) : cnt;
+    }
     const uint64_t key = msc_group_key(m.seed, (uint64_t)(group_offset + g));
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-    const uint32_t *Jg = m.Jw ? m.Jw + g * 3 * (int64_t)N : nullptr;
-    __syncthreads();  // mbarrier init visible to all waiters
-    {
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(done)
-                : "r"(smem_u32(bar))
-                : "memory");
-        }
-    }
+    mbar_wait(&bars[0], 0);
+    mbar_wait(&bars[1 + half], 0);
 
     // ---- sweeps: colour 0 then colour 1 (RNG-SPEC visit order)
     for (int sw = 0; sw < n_sweeps; sw++) {
 #pragma unroll 1
         for (int c = 0; c < 2; c++) {
             const uint32_t so = c * N2, oo = (1 - c) * N2;  // word offsets of the updated / the other colour half
+            const uint32_t tag = TAG_SWEEP_MSC | (uint32_t)c;
 #pragma unroll 1
-            for (int it = tid; it < gv.n_items; it += NT) {
-                uint32_t self, zp, zm, yp, ym, eL, eR, par;
-                unpack_item(__ldg(gv.items + it), self, zp, zm, yp, ym, eL, eR, par);
-                const bool p = ((par ^ (uint32_t)c) & 1u) != 0;  // sites of this colour in the row sit at x2 = 2j + p
-                // coupling sign words (bit = 1: J = -1); bond (i, d) is stored at its lower site i
-                uint32_t Jf0[4], Jf1[4], Jf2[4], Jb0[4], Jb1[4], Jb2[4];
-                if (Jg) {
-                    uint4 v;
-                    v = ldg4(Jg + 0 * N + so + self); Jf0[0] = v.x; Jf0[1] = v.y; Jf0[2] = v.z; Jf0[3] = v.w;
-                    v = ldg4(Jg + 1 * N + so + self); Jf1[0] = v.x; Jf1[1] = v.y; Jf1[2] = v.z; Jf1[3] = v.w;
-                    v = ldg4(Jg + 2 * N + so + self); Jf2[0] = v.x; Jf2[1] = v.y; Jf2[2] = v.z; Jf2[3] = v.w;
-                    v = ldg4(Jg + 0 * N + oo + zm);   Jb0[0] = v.x; Jb0[1] = v.y; Jb0[2] = v.z; Jb0[3] = v.w;
-                    v = ldg4(Jg + 1 * N + oo + ym);   Jb1[0] = v.x; Jb1[1] = v.y; Jb1[2] = v.z; Jb1[3] = v.w;
-                    v = ldg4(Jg + 2 * N + oo + self);
-                    if (p) { Jb2[0] = v.x; Jb2[1] = v.y; Jb2[2] = v.z; Jb2[3] = v.w; }
-                    else   { Jb2[0] = __ldg(Jg + 2 * N + oo + eL); Jb2[1] = v.x; Jb2[2] = v.y; Jb2[3] = v.z; }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) Jf0[j] = Jf1[j] = Jf2[j] = Jb0[j] = Jb1[j] = Jb2[j] = 0u;
-                }
-#pragma unroll
-                for (int r = 0; r < RPC; r++) {
-                    uint32_t *sys = sp + (size_t)r * N;
-                    const u32x4 rnd = philox4x32_10(self >> 2, sweep_index + (uint32_t)sw, (uint32_t)(r * m.T + t),
-                                                    TAG_SWEEP_MSC | (uint32_t)c, k0, k1);
-                    const uint4 S = lds4(sys + so + self);
-                    const uint4 ZP = lds4(sys + oo + zp), ZM = lds4(sys + oo + zm);
-                    const uint4 YP = lds4(sys + oo + yp), YM = lds4(sys + oo + ym);
-                    const uint4 O = lds4(sys + oo + self);
-                    const uint32_t E = sys[oo + (p ? eR : eL)];
-                    uint32_t s[4] = {S.x, S.y, S.z, S.w};
-                    const uint32_t zpv[4] = {ZP.x, ZP.y, ZP.z, ZP.w}, zmv[4] = {ZM.x, ZM.y, ZM.z, ZM.w};
-                    const uint32_t ypv[4] = {YP.x, YP.y, YP.z, YP.w}, ymv[4] = {YM.x, YM.y, YM.z, YM.w};
-                    uint32_t xr[4], xl[4];
-                    if (p) { xl[0] = O.x; xl[1] = O.y; xl[2] = O.z; xl[3] = O.w; xr[0] = O.y; xr[1] = O.z; xr[2] = O.w; xr[3] = E; }
-                    else   { xl[0] = E;   xl[1] = O.x; xl[2] = O.y; xl[3] = O.z; xr[0] = O.x; xr[1] = O.y; xr[2] = O.z; xr[3] = O.w; }
-                    const uint32_t draw[4] = {rnd.x >> 8, rnd.y >> 8, rnd.z >> 8, rnd.w >> 8};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t b0 = xor3(s[j], zpv[j], Jf0[j]), b1 = xor3(s[j], zmv[j], Jb0[j]);
-                        const uint32_t b2 = xor3(s[j], ypv[j], Jf1[j]), b3 = xor3(s[j], ymv[j], Jb1[j]);
-                        const uint32_t b4 = xor3(s[j], xr[j], Jf2[j]), b5 = xor3(s[j], xl[j], Jb2[j]);
-                        const uint32_t s1 = xor3(b0, b1, b2), c1 = maj3(b0, b1, b2);
-                        const uint32_t s2 = xor3(b3, b4, b5), c2 = maj3(b3, b4, b5);
-                        const uint32_t kk = s1 & s2, oo2 = s1 | s2;
-                        uint32_t flip;
-                        if (METRO) {  // counts for unsat >= 3 are 2^24 (ec >= 0 always accepts, sweep.rs:141-145)
-                            const uint32_t ge1 = oo2 | c1 | c2, ge2 = kk | c1 | c2, ge3 = maj3(c1, c2, oo2);
-                            flip = ge3;
-                            if (draw[j] < cnt[2]) flip = ge2;
-                            if (draw[j] < cnt[1]) flip = ge1;
-                            if (draw[j] < cnt[0]) flip = 0xFFFFFFFFu;
-                        } else {
-                            const uint32_t x0 = s1 ^ s2, y1 = xor3(c1, c2, kk), y2 = maj3(c1, c2, kk);
-                            flip = 0u;
-#pragma unroll
-                            for (int u = 0; u < 7; u++) {
-                                const uint32_t eq = ((u & 1) ? x0 : ~x0) & ((u & 2) ? y1 : ~y1) & ((u & 4) ? y2 : ~y2);
-                                if (draw[j] < cnt[u]) flip |= eq;
-                            }
-                        }
-                        s[j] ^= flip;
-                    }
-                    *reinterpret_cast<uint4 *>(sys + so + self) = make_uint4(s[0], s[1], s[2], s[3]);
-                }
+            for (int it = ht; it < gv.n_items; it += MSC3D_NTH) {
+                const uint4 desc = items[it];
+                if (((desc.w >> 16) ^ (uint32_t)c) & 1u)
+                    msc3d_sweep_item<RPC, METRO, true>(sp, J, N, so, oo, desc, thr, sweep_index + (uint32_t)sw, (uint32_t)t,
+                                                       (uint32_t)m.T, tag, k0, k1);
+                else
+                    msc3d_sweep_item<RPC, METRO, false>(sp, J, N, so, oo, desc, thr, sweep_index + (uint32_t)sw, (uint32_t)t,
+                                                        (uint32_t)m.T, tag, k0, k1);
             }
-            __syncthreads();
+            half_barrier(half, MSC3D_NTH);
         }
     }
 
     // ---- stage out (asynchronous; the epilogue below only reads shared memory)
     if (n_sweeps > 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
+        half_barrier(half, MSC3D_NTH);
+        if (ht == 0) {
 #pragma unroll
-            for (int r = 0; r < RPC; r++) {
-                uint32_t *dst = m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                             "r"(smem_u32(sp + (size_t)r * N)), "r"(bytes)
-                             : "memory");
-            }
+            for (int r = 0; r < RPC; r++)
+                bulk_s2g(m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), sp + (size_t)r * N, bytes);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
 
-    // ---- epilogue: per-lane unsatisfied forward bonds, down spins, replica-pair overlaps
+    // ---- epilogue: per-lane unsatisfied forward bonds, down spins, replica-pair overlaps.
+    // Warps 0..3 of the half: energy + magnetisation, 4/RPC warps per replica; warps 4..7: the P replica pairs,
+    // 4/P warps per pair.  Each warp strides over the row segments, accumulates bit-sliced counters and reduces them
+    // with a bit-sliced butterfly; partial lane totals meet in shared memory.
     if (want_energy || want_mags || want_overlap) {
-        const int TPR = NT / RPC;          // threads per replica (multiple of 32)
-        const int r = tid / TPR, jt = tid % TPR;
-        const int wpr = TPR >> 5, wr = jt >> 5, lane = tid & 31;
-        const uint32_t *A = sp + (size_t)r * N;
-        const uint32_t *B = sp + (size_t)(r ^ 1) * N;
-        const bool paired = want_overlap && (r ^ 1) < RPC && (r | 1) < 2 * m.P;
-        VAcc<MSC3D_KE> ve, vl;
-        VAcc<MSC3D_KM> vm, vq;
-        ve.clear(); vl.clear(); vm.clear(); vq.clear();
-        int iter = 0;
+        constexpr int WPE = 4 / RPC;             // warps per replica (energy / magnetisation)
+        constexpr int NP = RPC / 2;              // replica pairs
+        constexpr int WPP = NP > 0 ? 4 / NP : 1; // warps per pair
+        const int w = ht >> 5, lane = ht & 31;
+        // red layout: [replica r][E, M][WPE][32] then [pair p][q, ql][WPP][32]
+        uint32_t *red_p = red + RPC * 2 * WPE * 32;
+        if (w < 4) {
+            if (want_energy || want_mags) {
+                const int r = w / WPE, sub = w % WPE;
+                const uint32_t *A = sp + (size_t)r * N;
+                VAcc<MSC3D_KE> ve;
+                VAcc<MSC3D_KM> vm;
+                ve.clear(); vm.clear();
 #pragma unroll 1
-        for (int it = jt; it < gv.n_items; it += TPR, iter++) {
-            uint32_t self, zp, zm, yp, ym, eL, eR, par;
-            unpack_item(__ldg(gv.items + it), self, zp, zm, yp, ym, eL, eR, par);
-            (void)zm; (void)ym; (void)eL;
-            // the 8 sites of the segment: words 0..3 colour 0, 4..7 colour 1
-            uint32_t a[8], az[8], ay[8], ax[8];
-            {
-                const uint4 s0 = lds4(A + self), s1 = lds4(A + N2 + self);
-                const uint4 z0 = lds4(A + N2 + zp), z1 = lds4(A + zp);    // +x0 neighbours of colour-0 / colour-1 sites
-                const uint4 y0 = lds4(A + N2 + yp), y1 = lds4(A + yp);
-                a[0] = s0.x; a[1] = s0.y; a[2] = s0.z; a[3] = s0.w; a[4] = s1.x; a[5] = s1.y; a[6] = s1.z; a[7] = s1.w;
-                az[0] = z0.x; az[1] = z0.y; az[2] = z0.z; az[3] = z0.w; az[4] = z1.x; az[5] = z1.y; az[6] = z1.z; az[7] = z1.w;
-                ay[0] = y0.x; ay[1] = y0.y; ay[2] = y0.z; ay[3] = y0.w; ay[4] = y1.x; ay[5] = y1.y; ay[6] = y1.z; ay[7] = y1.w;
-                // +x2 neighbour: colour c sites sit at x2 = 2j + (par^c); the neighbour 2j + (par^c) + 1 is word j of
-                // the other colour when par^c == 0, word j+1 when par^c == 1
-                if (par == 0) {  // colour 0: p = 0, colour 1: p = 1
-                    ax[0] = s1.x; ax[1] = s1.y; ax[2] = s1.z; ax[3] = s1.w;
-                    ax[4] = s0.y; ax[5] = s0.z; ax[6] = s0.w; ax[7] = A[eR];
-                } else {         // colour 0: p = 1, colour 1: p = 0
-                    ax[0] = s1.y; ax[1] = s1.z; ax[2] = s1.w; ax[3] = A[N2 + eR];
-                    ax[4] = s0.x; ax[5] = s0.y; ax[6] = s0.z; ax[7] = s0.w;
+                for (int it = lane + 32 * sub; it < gv.n_items; it += 32 * WPE) {
+                    const uint4 desc = items[it];
+                    if ((desc.w >> 16) & 1u) msc3d_em_item<true>(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
+                    else msc3d_em_item<false>(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
                 }
+                if (want_energy) red[((r * 2 + 0) * WPE + sub) * 32 + lane] = warp_lane_total(ve);
+                if (want_mags) red[((r * 2 + 1) * WPE + sub) * 32 + lane] = warp_lane_total(vm);
             }
-            if (want_mags) vm.add8(a);
-            if (want_energy) {
-                uint32_t j0[8], j1[8], j2[8];
-                if (Jg) {
-                    uint4 v;
-                    v = ldg4(Jg + 0 * N + self);      j0[0] = v.x; j0[1] = v.y; j0[2] = v.z; j0[3] = v.w;
-                    v = ldg4(Jg + 0 * N + N2 + self); j0[4] = v.x; j0[5] = v.y; j0[6] = v.z; j0[7] = v.w;
-                    v = ldg4(Jg + 1 * N + self);      j1[0] = v.x; j1[1] = v.y; j1[2] = v.z; j1[3] = v.w;
-                    v = ldg4(Jg + 1 * N + N2 + self); j1[4] = v.x; j1[5] = v.y; j1[6] = v.z; j1[7] = v.w;
-                    v = ldg4(Jg + 2 * N + self);      j2[0] = v.x; j2[1] = v.y; j2[2] = v.z; j2[3] = v.w;
-                    v = ldg4(Jg + 2 * N + N2 + self); j2[4] = v.x; j2[5] = v.y; j2[6] = v.z; j2[7] = v.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) j0[j] = j1[j] = j2[j] = 0u;
+        } else if (NP > 0 && want_overlap) {
+            const int pw = w - 4, p = pw / WPP, sub = pw % WPP;
+            if (p < m.P) {
+                const uint32_t *A = sp + (size_t)(2 * p) * N, *B = sp + (size_t)(2 * p + 1) * N;
+                VAcc<MSC3D_KE> vl;
+                VAcc<MSC3D_KM> vq;
+                vl.clear(); vq.clear();
+#pragma unroll 1
+                for (int it = lane + 32 * sub; it < gv.n_items; it += 32 * WPP) {
+                    const uint4 desc = items[it];
+                    if ((desc.w >> 16) & 1u) msc3d_pair_item<true>(A, B, N2, desc, vl, vq);
+                    else msc3d_pair_item<false>(A, B, N2, desc, vl, vq);
                 }
-                uint32_t sb[8], cb[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {  // energy.rs:99-107: forward bonds only, each bond once
-                    const uint32_t b0 = xor3(a[j], az[j], j0[j]), b1 = xor3(a[j], ay[j], j1[j]), b2 = xor3(a[j], ax[j], j2[j]);
-                    sb[j] = xor3(b0, b1, b2);
-                    cb[j] = maj3(b0, b1, b2);
-                }
-                ve.add8_8(sb, cb);
-            }
-            if (paired && ((iter & 1) == (r & 1))) {  // the two replicas of a pair split the items between them
-                uint32_t x[8], sb[8], cb[8];
-                const uint4 s0 = lds4(B + self), s1 = lds4(B + N2 + self);
-                const uint4 z0 = lds4(B + N2 + zp), z1 = lds4(B + zp);
-                const uint4 y0 = lds4(B + N2 + yp), y1 = lds4(B + yp);
-                const uint32_t b[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const uint32_t bz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-                const uint32_t by[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-                uint32_t bx[8];
-                if (par == 0) {
-                    bx[0] = s1.x; bx[1] = s1.y; bx[2] = s1.z; bx[3] = s1.w;
-                    bx[4] = s0.y; bx[5] = s0.z; bx[6] = s0.w; bx[7] = B[eR];
-                } else {
-                    bx[0] = s1.y; bx[1] = s1.z; bx[2] = s1.w; bx[3] = B[N2 + eR];
-                    bx[4] = s0.x; bx[5] = s0.y; bx[6] = s0.z; bx[7] = s0.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) {  // overlap.rs:266-276: x = 1 where q_i = -1; link word = x_i ^ x_fwd
-                    x[j] = a[j] ^ b[j];
-                    const uint32_t l0 = xor3(x[j], az[j], bz[j]), l1 = xor3(x[j], ay[j], by[j]), l2 = xor3(x[j], ax[j], bx[j]);
-                    sb[j] = xor3(l0, l1, l2);
-                    cb[j] = maj3(l0, l1, l2);
-                }
-                vq.add8(x);
-                vl.add8_8(sb, cb);
+                red_p[((p * 2 + 0) * WPP + sub) * 32 + lane] = warp_lane_total(vq);
+                red_p[((p * 2 + 1) * WPP + sub) * 32 + lane] = warp_lane_total(vl);
             }
         }
-        // cross-thread: warp butterfly, then per-replica combine through shared memory
-        uint32_t *mine = red + ((size_t)(r * 4) * wpr + wr) * 32;  // [r][quantity][warp][lane]
-        if (want_energy) mine[(size_t)0 * wpr * 32 + lane] = warp_lane_total(ve);
-        if (want_mags) mine[(size_t)1 * wpr * 32 + lane] = warp_lane_total(vm);
-        if (want_overlap) {
-            mine[(size_t)2 * wpr * 32 + lane] = paired ? warp_lane_total(vq) : 0u;
-            mine[(size_t)3 * wpr * 32 + lane] = paired ? warp_lane_total(vl) : 0u;
-        }
-        __syncthreads();
-        if (wr == 0) {
-            const int64_t d = g * 32 + lane;
-            if (d < m.D) {
-                const int pos = r * m.T + t;
-                auto total = [&](int rr, int q) {
-                    uint32_t acc = 0;
-                    for (int w = 0; w < wpr; w++) acc += red[(((size_t)rr * 4 + q) * wpr + w) * 32 + lane];
-                    return acc;
-                };
-                const int sys = m.system_ids[d * m.S + pos];
+        half_barrier(half, MSC3D_NTH);
+        const int64_t d = g * 32 + lane;
+        if (d < m.D) {
+            if (w < RPC && (want_energy || want_mags)) {
+                const int r = w;
+                const int sys = m.system_ids[d * m.S + r * m.T + t];
+                uint32_t e = 0, dn = 0;
+#pragma unroll
+                for (int k = 0; k < WPE; k++) {
+                    e += red[((r * 2 + 0) * WPE + k) * 32 + lane];
+                    dn += red[((r * 2 + 1) * WPE + k) * 32 + lane];
+                }
                 if (want_energy) {  // sum_i sum_d s s J = (#bonds) - 2 * unsatisfied   (energy.rs:103-108)
-                    const long long e_int = 3ll * N - 2ll * total(r, 0);
+                    const long long e_int = 3ll * N - 2ll * e;
                     m.energies[d * m.S + sys] = __fdiv_rn((float)e_int, (float)N);
                 }
-                if (want_mags) m.mags[d * m.S + sys] = (long long)N - 2ll * total(r, 1);
-                if (want_overlap && (r & 1) == 0 && r + 1 < 2 * m.P) {
-                    const int pr = r >> 1;
-                    const int64_t o = (d * m.P + pr) * m.T + t;
-                    dot_spin[o] = (long long)N - 2ll * (total(r, 2) + total(r + 1, 2));
-                    dot_link[o] = 3ll * N - 2ll * (total(r, 3) + total(r + 1, 3));
+                if (want_mags) m.mags[d * m.S + sys] = (long long)N - 2ll * dn;
+            } else if (NP > 0 && want_overlap && w >= 4 && w - 4 < m.P) {
+                const int p = w - 4;
+                uint32_t cs = 0, cl = 0;
+#pragma unroll
+                for (int k = 0; k < WPP; k++) {
+                    cs += red_p[((p * 2 + 0) * WPP + k) * 32 + lane];
+                    cl += red_p[((p * 2 + 1) * WPP + k) * 32 + lane];
                 }
+                const int64_t o = (d * m.P + p) * m.T + t;
+                dot_spin[o] = (long long)N - 2ll * cs;
+                dot_link[o] = 3ll * N - 2ll * cl;
             }
         }
     }
-    if (n_sweeps > 0 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (n_sweeps > 0 && ht == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #endif  // __CUDACC__
 
