@@ -5,8 +5,10 @@
 //   sweep -> energies(+mags) if record||pt -> overlap (pre-swap system_ids) if record
 //         -> fold if record -> parallel tempering if pt_this_sweep
 // and enqueues one kernel per step on a single stream; no spin data crosses PCIe during sample().
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -179,13 +181,20 @@ struct pp_sim {
     long long *d_dot_spin = nullptr, *d_dot_link = nullptr;
     bool hist_allocated = false;
     int64_t launches = 0;
+    // chunked multi-stream execution of the msc3d path (see pp_sample)
+    int n_streams = 3;
+    int64_t chunk_bytes = int64_t(24) << 20;
+    int64_t macro_batch = 16;
+    int64_t chunk_groups = 0;                          // > 0: word groups per chunk (overrides chunk_bytes; tests)
+    std::vector<cudaStream_t> xstreams;
+    std::vector<cudaEvent_t> xevents;
     // measurement hook: event pairs around sweep-kernel launches
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
 };
 
-static void prof_mark(pp_sim *s) {
+static void prof_mark(pp_sim *s, cudaStream_t stream) {
     if (!s->profile) return;
     if (s->prof_used == s->prof_events.size()) {
         if (s->prof_events.size() >= 8192) return;
@@ -193,7 +202,7 @@ static void prof_mark(pp_sim *s) {
         if (cudaEventCreate(&e) != cudaSuccess) return;
         s->prof_events.push_back(e);
     }
-    cudaEventRecord(s->prof_events[s->prof_used++], s->stream);
+    cudaEventRecord(s->prof_events[s->prof_used++], stream);
 }
 
 static void free_sim(pp_sim *s) {
@@ -206,6 +215,8 @@ static void free_sim(pp_sim *s) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->xevents) cudaEventDestroy(e);
+    for (cudaStream_t x : s->xstreams) cudaStreamDestroy(x);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -249,143 +260,247 @@ __global__ void pt_mark_hot_kernel(ModelView m, PtView pt) {  // realization.rs:
 static inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // ---- kernel launch helpers ------------------------------------------------------------------
-static pp_status launch_energy(pp_sim *s, bool want_mags);
+// A Ctx is a view of a contiguous block of realizations (a "chunk": whole word groups for the multispin layout) plus
+// the stream its kernels go to.  All device arrays are indexed by realization / word group, so a chunk is the same
+// structs with advanced base pointers; seeds use sample_offset + d, so results do not depend on the chunking.
+struct Ctx {
+    ModelView m;
+    StatsView st;
+    PtView pt;
+    long long *dot_spin, *dot_link;
+    int64_t G;
+    cudaStream_t stream;
+    // msc3d ping-pong / deferred parallel-tempering swaps (see msc3d_kernel): m.words is the current buffer
+    uint32_t *words_alt = nullptr;
+    int flips = 0;
+    bool swap_pending = false;
+    int pend_schedule = 0, pend_parity = 0;
+};
+
+static Ctx whole_ctx(pp_sim *s) {
+    Ctx c;
+    c.words_alt = s->d_words_alt;
+    c.m = s->mv;
+    c.st = s->st;
+    c.pt = s->pt;
+    c.dot_spin = s->d_dot_spin;
+    c.dot_link = s->d_dot_link;
+    c.G = s->G;
+    c.stream = s->stream;
+    return c;
+}
+
+// realizations [d0, d0 + D) of the handle; for the multispin layout d0 is a multiple of 32
+static Ctx chunk_ctx(pp_sim *s, int64_t d0, int64_t D, cudaStream_t stream) {
+    Ctx c = whole_ctx(s);
+    ModelView &m = c.m;
+    const int64_t N = m.N, S = m.S, T = m.T, g0 = d0 / 32;
+    m.D = D;
+    m.sample_offset = s->mv.sample_offset + d0;
+    if (m.J8) m.J8 += d0 * N * m.z;
+    if (m.Jf) m.Jf += d0 * N * m.z;
+    if (m.Jw) m.Jw += g0 * m.z * N;
+    if (m.spins) m.spins += d0 * S * N;
+    if (m.words) m.words += g0 * S * N;
+    if (c.words_alt) c.words_alt += g0 * S * N;
+    m.system_ids += d0 * S;
+    m.energies += d0 * S;
+    m.mags += d0 * S;
+    c.st.sums += d0 * 11 * T;
+    if (c.st.hist) {
+        c.st.hist += d0 * T * (N + 1);
+        c.st.ql_at_q += d0 * T * (N + 1);
+        c.st.ql2_at_q += d0 * T * (N + 1);
+    }
+    if (c.dot_spin) {
+        c.dot_spin += d0 * m.P * T;
+        c.dot_link += d0 * m.P * T;
+        c.st.dot_spin = c.dot_spin;
+        c.st.dot_link = c.dot_link;
+    }
+    c.pt.edge_attempts += d0 * (T > 1 ? T - 1 : 1);
+    c.pt.edge_acceptances += d0 * (T > 1 ? T - 1 : 1);
+    c.pt.round_trips += d0 * S;
+    c.pt.trip_state += d0 * S;
+    if (c.pt.swap_mask) c.pt.swap_mask += g0 * m.R * (T > 1 ? T - 1 : 1);
+    c.G = (D + 31) / 32;
+    c.stream = stream;
+    return c;
+}
+
+static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags);
 
 template <int RPC, bool METRO, int NH>
-static pp_status launch_msc3d_t(pp_sim *s, const ModelView &m, uint32_t sweep_index, int n_sweeps, bool want_energy,
-                                bool want_mags, bool want_overlap) {
-    CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->msc3d_smem));
-    const unsigned grid = (unsigned)(s->G * ((m.T + NH - 1) / NH));
-    msc3d_kernel<RPC, METRO, NH><<<grid, MSC3D_NTH * NH, s->msc3d_smem, s->stream>>>(
-        m, s->gv, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, m.sample_offset / 32, s->d_dot_spin, s->d_dot_link);
+static pp_status launch_msc3d_t(pp_sim *s, Ctx &c, const ModelView &m, uint32_t sweep_index, int n_sweeps,
+                                bool want_energy, bool want_mags, bool want_overlap, bool want_fold) {
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const unsigned grid = (unsigned)(c.G * ((m.T + NH - 1) / NH));
+    msc3d_kernel<RPC, METRO, NH><<<grid, MSC3D_NTH * NH, s->msc3d_smem, c.stream>>>(
+        m, s->gv, c.st, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold, m.sample_offset / 32, c.dot_spin,
+        c.dot_link, c.words_alt, c.swap_pending ? c.pt.swap_mask : nullptr, c.pend_schedule, c.pend_parity);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (n_sweeps > 0) {  // the sweep consumed the pending exchange and wrote the other buffer
+        std::swap(c.m.words, c.words_alt);
+        c.flips++;
+        c.swap_pending = false;
+    }
     return PP_OK;
 }
 
-static pp_status launch_msc3d(pp_sim *s, const ModelView &m, int sweep_mode, uint32_t sweep_index, int n_sweeps,
-                              bool want_energy, bool want_mags, bool want_overlap) {
+// make the handle's current-buffer pointer follow the launches issued through a context
+static void commit_ctx(pp_sim *s, const Ctx &c) {
+    if (c.flips & 1) {
+        std::swap(s->d_words, s->d_words_alt);
+        s->mv.words = s->d_words;
+    }
+}
+
+static pp_status launch_msc3d(pp_sim *s, Ctx &c, const ModelView &m, int sweep_mode, uint32_t sweep_index, int n_sweeps,
+                              bool want_energy, bool want_mags, bool want_overlap, bool want_fold) {
     const bool metro = sweep_mode == PP_SWEEP_METROPOLIS && s->msc3d_metro;
     const bool two = s->msc3d_nh == 2;
-#define PP_M3(R_)                                                                                                         \
-    return metro ? (two ? launch_msc3d_t<R_, true, 2>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap)   \
-                        : launch_msc3d_t<R_, true, 1>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap))  \
-                 : (two ? launch_msc3d_t<R_, false, 2>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap)  \
-                        : launch_msc3d_t<R_, false, 1>(s, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap))
+#define PP_M3A(R_, M_, H_) launch_msc3d_t<R_, M_, H_>(s, c, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold)
+#define PP_M3(R_) return metro ? (two ? PP_M3A(R_, true, 2) : PP_M3A(R_, true, 1)) : (two ? PP_M3A(R_, false, 2) : PP_M3A(R_, false, 1))
     switch (m.R) {
         case 1: PP_M3(1);
         case 2: PP_M3(2);
         case 4: PP_M3(4);
     }
 #undef PP_M3
+#undef PP_M3A
     return fail(PP_ERR_UNSUPPORTED, "msc3d: unsupported replica count");
 }
 
-// want_overlap: the caller wants the replica-pair dots of the post-sweep state; *overlap_done is set when the
-// sweep kernel produced them itself (fused epilogue), otherwise the caller launches launch_overlap().
-static pp_status launch_sweeps(pp_sim *s, int sweep_mode, uint32_t sweep_index, int n_sweeps, int exact_log,
-                               bool want_energy, bool want_mags, bool want_overlap = false, bool *overlap_done = nullptr) {
-    ModelView m = s->mv;
+// want_overlap / want_fold: the caller wants the replica-pair dots of the post-sweep state / the recorded-sweep fold;
+// *fused is set when the sweep kernel did both itself (msc3d epilogue), otherwise the caller launches
+// launch_overlap() and fold_kernel.
+static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep_index, int n_sweeps, int exact_log,
+                               bool want_energy, bool want_mags, bool want_overlap = false, bool want_fold = false,
+                               bool *fused = nullptr) {
+    ModelView m = c.m;
     m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
-    if (overlap_done) *overlap_done = false;
+    if (fused) *fused = false;
     if (s->layout == PP_LAYOUT_MSC) {
         const bool timed = n_sweeps > 0;
-        if (timed) prof_mark(s);
+        if (timed) prof_mark(s, c.stream);
         if (s->msc3d) {
             const bool ov = want_overlap && m.P > 0;
-            pp_status st = launch_msc3d(s, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags, ov);
+            pp_status st = launch_msc3d(s, c, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags, ov, want_fold);
             if (st != PP_OK) return st;
-            if (overlap_done) *overlap_done = ov;
-            if (timed) prof_mark(s);
+            if (fused) *fused = true;
+            if (timed) prof_mark(s, c.stream);
             return PP_OK;
         }
         const size_t smem = sizeof(uint32_t) * (size_t)m.N;
-        const unsigned grid = (unsigned)(s->G * m.S);
+        const unsigned grid = (unsigned)(c.G * m.S);
         if (smem <= 200 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(msc_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msc_sweep_kernel<true><<<grid, MSC_BLOCK, smem, s->stream>>>(m, sweep_index, n_sweeps, want_energy, want_mags,
-                                                                        s->mv.sample_offset / 32);
+            msc_sweep_kernel<true><<<grid, MSC_BLOCK, smem, c.stream>>>(m, sweep_index, n_sweeps, want_energy, want_mags,
+                                                                       m.sample_offset / 32);
         } else {
-            msc_sweep_kernel<false><<<grid, MSC_BLOCK, 0, s->stream>>>(m, sweep_index, n_sweeps, want_energy, want_mags,
-                                                                      s->mv.sample_offset / 32);
+            msc_sweep_kernel<false><<<grid, MSC_BLOCK, 0, c.stream>>>(m, sweep_index, n_sweeps, want_energy, want_mags,
+                                                                     m.sample_offset / 32);
         }
         s->launches++;
-        if (timed) prof_mark(s);
+        if (timed) prof_mark(s, c.stream);
         CUDA_TRY(cudaGetLastError());
         return PP_OK;
     }
-    if (n_sweeps > 0) prof_mark(s);
+    if (n_sweeps > 0) prof_mark(s, c.stream);
     for (int sw = 0; sw < n_sweeps; sw++) {
-        for (int c = 0; c < m.n_colours; c++) {
-            const uint32_t nsite = s->plan.colour_start[c + 1] - s->plan.colour_start[c];
+        for (int col = 0; col < m.n_colours; col++) {
+            const uint32_t nsite = s->plan.colour_start[col + 1] - s->plan.colour_start[col];
             if (nsite == 0) continue;
             dim3 grid((unsigned)(m.D * m.S), blocks_for((nsite + 3) / 4, SWEEP_BLOCK));
             switch (m.coupling_class) {
                 case COUP_FERRO:
-                    sweep_colour_int8_kernel<COUP_FERRO><<<grid, SWEEP_BLOCK, 0, s->stream>>>(m, c, sweep_index + sw, sweep_mode, exact_log);
+                    sweep_colour_int8_kernel<COUP_FERRO><<<grid, SWEEP_BLOCK, 0, c.stream>>>(m, col, sweep_index + sw, sweep_mode, exact_log);
                     break;
                 case COUP_UNIT:
-                    sweep_colour_int8_kernel<COUP_UNIT><<<grid, SWEEP_BLOCK, 0, s->stream>>>(m, c, sweep_index + sw, sweep_mode, exact_log);
+                    sweep_colour_int8_kernel<COUP_UNIT><<<grid, SWEEP_BLOCK, 0, c.stream>>>(m, col, sweep_index + sw, sweep_mode, exact_log);
                     break;
                 default:
-                    sweep_colour_int8_kernel<COUP_F32><<<grid, SWEEP_BLOCK, 0, s->stream>>>(m, c, sweep_index + sw, sweep_mode, exact_log);
+                    sweep_colour_int8_kernel<COUP_F32><<<grid, SWEEP_BLOCK, 0, c.stream>>>(m, col, sweep_index + sw, sweep_mode, exact_log);
             }
             s->launches++;
         }
     }
-    if (n_sweeps > 0) prof_mark(s);
+    if (n_sweeps > 0) prof_mark(s, c.stream);
     CUDA_TRY(cudaGetLastError());
-    if (want_energy) return launch_energy(s, want_mags);
+    if (want_energy) return launch_energy(s, c, want_mags);
     return PP_OK;
 }
 
-static pp_status launch_energy(pp_sim *s, bool want_mags) {
-    ModelView m = s->mv;
-    if (s->layout == PP_LAYOUT_MSC) {
-        m.lut = s->d_lut_metro;
-        return launch_sweeps(s, PP_SWEEP_METROPOLIS, 0, 0, 0, true, want_mags) == PP_OK ? PP_OK : PP_ERR_CUDA;
-    }
+static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
+    const ModelView &m = c.m;
+    if (s->layout == PP_LAYOUT_MSC) return launch_sweeps(s, c, PP_SWEEP_METROPOLIS, 0, 0, 0, true, want_mags);
     const unsigned grid = (unsigned)(m.D * m.S);
     switch (m.coupling_class) {
-        case COUP_FERRO: energy_mag_int8_kernel<COUP_FERRO><<<grid, 256, 0, s->stream>>>(m, want_mags); break;
-        case COUP_UNIT: energy_mag_int8_kernel<COUP_UNIT><<<grid, 256, 0, s->stream>>>(m, want_mags); break;
-        default: energy_mag_int8_kernel<COUP_F32><<<grid, 256, 0, s->stream>>>(m, want_mags);
+        case COUP_FERRO: energy_mag_int8_kernel<COUP_FERRO><<<grid, 256, 0, c.stream>>>(m, want_mags); break;
+        case COUP_UNIT: energy_mag_int8_kernel<COUP_UNIT><<<grid, 256, 0, c.stream>>>(m, want_mags); break;
+        default: energy_mag_int8_kernel<COUP_F32><<<grid, 256, 0, c.stream>>>(m, want_mags);
     }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return PP_OK;
 }
 
-static pp_status launch_overlap(pp_sim *s) {
-    ModelView m = s->mv;
+static pp_status launch_overlap(pp_sim *s, Ctx &c) {
+    ModelView m = c.m;
     if (m.P == 0) return PP_OK;
     if (s->layout == PP_LAYOUT_MSC && s->msc3d) {
         m.lut = s->d_lut_metro;
-        return launch_msc3d(s, m, PP_SWEEP_METROPOLIS, 0, 0, false, false, true);
+        return launch_msc3d(s, c, m, PP_SWEEP_METROPOLIS, 0, 0, false, false, true, false);
     }
     if (s->layout == PP_LAYOUT_MSC)
-        msc_overlap_kernel<<<(unsigned)(s->G * m.P * m.T), MSC_BLOCK, 0, s->stream>>>(m, s->d_dot_spin, s->d_dot_link);
+        msc_overlap_kernel<<<(unsigned)(c.G * m.P * m.T), MSC_BLOCK, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
     else
-        overlap_dots_int8_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, s->stream>>>(m, s->d_dot_spin, s->d_dot_link);
+        overlap_dots_int8_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return PP_OK;
 }
 
-static pp_status launch_pt(pp_sim *s, int schedule, uint32_t pt_event) {
-    ModelView m = s->mv;
-    if (m.T < 2) return PP_OK;
-    const bool msc = s->layout == PP_LAYOUT_MSC;
-    if (msc) CUDA_TRY(cudaMemsetAsync(s->pt.swap_mask, 0, sizeof(uint32_t) * (size_t)(s->G * m.R * (m.T - 1)), s->stream));
-    pt_exchange_kernel<<<blocks_for(m.D * m.R, 128), 128, 0, s->stream>>>(m, s->pt, schedule, s->next_parity, pt_event, msc);
+// one parallel-tempering event (mod.rs:748-796); first_parity is the caller's PtState.next_parity
+// exchange the lanes of a pending parallel-tempering event in place (the msc3d sweep kernel normally does this while
+// staging its input; this is the path for everything else that looks at the words)
+static pp_status flush_swaps(pp_sim *s, Ctx &c) {
+    if (!c.swap_pending) return PP_OK;
+    const ModelView &m = c.m;
+    dim3 grid((unsigned)(c.G * m.R), blocks_for(m.N, 256));
+    msc_apply_swaps_kernel<<<grid, 256, 0, c.stream>>>(m, c.pt.swap_mask, c.pend_schedule, c.pend_parity);
     s->launches++;
-    if (msc) {
-        dim3 grid((unsigned)(s->G * m.R), blocks_for(m.N, 256));
-        msc_apply_swaps_kernel<<<grid, 256, 0, s->stream>>>(m, s->pt.swap_mask, schedule, s->next_parity);
+    c.swap_pending = false;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+// defer = the caller guarantees that the next kernel touching the words is an msc3d sweep (or flush_swaps)
+static pp_status launch_pt(pp_sim *s, Ctx &c, int schedule, uint32_t pt_event, int first_parity, bool defer = false) {
+    const ModelView &m = c.m;
+    if (m.T < 2) return PP_OK;
+    if (s->layout == PP_LAYOUT_MSC) {
+        pp_status st = flush_swaps(s, c);
+        if (st != PP_OK) return st;
+        pt_exchange_msc_kernel<<<blocks_for(c.G * m.R * 32, 128), 128, 0, c.stream>>>(m, c.pt, schedule, first_parity, pt_event);
+        s->launches++;
+        c.swap_pending = true;
+        c.pend_schedule = schedule;
+        c.pend_parity = first_parity;
+        if (!(defer && s->msc3d)) {
+            st = flush_swaps(s, c);
+            if (st != PP_OK) return st;
+        }
+    } else {
+        pt_exchange_kernel<<<blocks_for(m.D * m.R, 128), 128, 0, c.stream>>>(m, c.pt, schedule, first_parity, pt_event);
         s->launches++;
     }
     CUDA_TRY(cudaGetLastError());
-    if (schedule == PP_PT_FULL_LADDER) s->next_parity = 1 - s->next_parity;  // mod.rs:793-795
     return PP_OK;
 }
 
@@ -407,7 +522,8 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
         init_spins_int8_kernel<<<grid, 128, 0, s->stream>>>(m);
     }
     CUDA_TRY(cudaGetLastError());
-    pp_status stt = launch_energy(s, false);
+    Ctx wc = whole_ctx(s);
+    pp_status stt = launch_energy(s, wc, false);
     if (stt != PP_OK) return stt;
     if (m.T > 1) {
         CUDA_TRY(cudaMemsetAsync(s->pt.edge_attempts, 0, sizeof(uint64_t) * (size_t)(m.D * (m.T - 1)), s->stream));
@@ -439,6 +555,10 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     }
     s->device = desc->device;
     s->ctor_seed = desc->seed;
+    if (const char *e = getenv("PP_STREAMS")) s->n_streams = std::max(1, atoi(e));
+    if (const char *e = getenv("PP_CHUNK_MIB")) s->chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("PP_MACRO_BATCH")) s->macro_batch = std::max(1, atoi(e));
+    if (const char *e = getenv("PP_CHUNK_GROUPS")) s->chunk_groups = std::max(0, atoi(e));
     s->temps.assign(desc->temperatures, desc->temperatures + desc->n_temps);
     ModelView &m = s->mv;
     m.N = s->plan.n_spins;
@@ -609,6 +729,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 s->gv.N = (uint32_t)N;
                 s->gv.N2 = (uint32_t)(N / 2);
                 s->msc3d = true;
+                CREATE_TRY(cudaMalloc(&s->d_words_alt, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
                 s->msc3d_nh = nh;
                 s->msc3d_smem = smem_words(nh) * 4;
                 // Metropolis fast path: counts for unsat >= 3 (energy_change >= 0) are 2^24 (sweep.rs:141-145) and the
@@ -696,6 +817,18 @@ static pp_status ensure_tables(pp_sim *s, bool need_log, bool need_glog) {
     return PP_OK;
 }
 
+static pp_status ensure_streams(pp_sim *s, int n) {
+    while ((int)s->xstreams.size() < n) {
+        cudaStream_t x;
+        cudaEvent_t e;
+        CUDA_TRY(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        s->xstreams.push_back(x);
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->xevents.push_back(e);
+    }
+    return PP_OK;
+}
+
 static pp_status ensure_hist(pp_sim *s) {
     if (s->hist_allocated || s->mv.P == 0) return PP_OK;
     const size_t n = (size_t)s->mv.D * s->mv.T * (s->mv.N + 1);
@@ -736,46 +869,116 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
 
     const bool msc = s->layout == PP_LAYOUT_MSC;
+    // ---- chunk plan.  The msc3d path splits the realizations into chunks of whole word groups whose spin words fit
+    // the L2 cache a few times over, runs `macro_batch` sweeps of one chunk back to back (so its words stay L2-resident
+    // between the sweep, exchange and swap kernels) and spreads the chunks over a few streams, so that the
+    // latency-/bandwidth-bound exchange and swap kernels of one chunk overlap the ALU-bound sweep kernel of another.
+    // Realizations are independent (mod.rs:887-903 runs them on different threads), so results do not depend on this.
+    std::vector<Ctx> chunks;
+    int64_t macro_batch = 1;
+    if (msc && s->msc3d && !s->profile && s->n_streams > 1) {
+        const int64_t group_bytes = (int64_t)m.S * m.N * 4;
+        const int64_t gpc = s->chunk_groups > 0 ? s->chunk_groups : std::max<int64_t>(1, s->chunk_bytes / group_bytes);
+        const int64_t n_chunks = (s->G + gpc - 1) / gpc;
+        if (n_chunks > 1) {
+            pp_status stx = ensure_streams(s, (int)std::min<int64_t>(n_chunks, s->n_streams));
+            if (stx != PP_OK) return stx;
+            for (int64_t c = 0; c < n_chunks; c++) {
+                const int64_t d0 = c * gpc * 32, D = std::min<int64_t>(m.D - d0, gpc * 32);
+                chunks.push_back(chunk_ctx(s, d0, D, s->xstreams[(size_t)(c % (int64_t)s->xstreams.size())]));
+            }
+            for (cudaStream_t xs : s->xstreams) CUDA_TRY(cudaStreamWaitEvent(xs, s->ev0, 0));
+            macro_batch = s->macro_batch;
+        }
+    }
+    if (chunks.empty()) chunks.push_back(whole_ctx(s));
+
+    struct Step {
+        uint32_t sweep_index;
+        int batch;
+        bool record, pt_this;
+        uint32_t pt_event;
+        int parity;
+    };
+    std::vector<Step> steps;
     int64_t sweep_id = 0;
     while (sweep_id < cfg->n_sweeps) {
-        // how many sweeps until (and including) the next one that needs a reduction or PT
-        int64_t batch = 1;
-        if (msc) {
-            while (sweep_id + batch - 1 < cfg->n_sweeps - 1) {
-                const int64_t last = sweep_id + batch - 1;
-                const bool rec = last >= cfg->warmup_sweeps;
-                const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
-                if (rec || ptl || batch >= 64) break;
-                batch++;
+        if (interrupt && *interrupt) {  // mod.rs:406-408 (polled once per macro batch)
+            for (Ctx &c : chunks) flush_swaps(s, c);
+            commit_ctx(s, chunks[0]);
+            cudaDeviceSynchronize();
+            return fail(PP_ERR_INTERRUPTED, "interrupted");
+        }
+        // the sequence of kernel steps of this macro batch (mod.rs:405-432, 486-509, 748-796), identical for every chunk
+        const int64_t mb_end = std::min<int64_t>(cfg->n_sweeps, sweep_id + macro_batch);
+        steps.clear();
+        uint32_t sweep_counter = s->sweep_counter, pt_event = s->pt_event_counter;
+        int parity = s->next_parity;
+        for (int64_t sid = sweep_id; sid < mb_end;) {
+            // how many sweeps until (and including) the next one that needs a reduction or PT
+            int64_t batch = 1;
+            if (msc) {
+                while (sid + batch - 1 < mb_end - 1) {
+                    const int64_t last = sid + batch - 1;
+                    const bool rec = last >= cfg->warmup_sweeps;
+                    const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
+                    if (rec || ptl || batch >= 64) break;
+                    batch++;
+                }
+            }
+            const int64_t last = sid + batch - 1;
+            Step stp;
+            stp.sweep_index = sweep_counter;
+            stp.batch = (int)batch;
+            stp.record = last >= cfg->warmup_sweeps;                                  // mod.rs:410
+            stp.pt_this = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;       // mod.rs:486-488
+            stp.pt_event = pt_event;
+            stp.parity = parity;
+            steps.push_back(stp);
+            sweep_counter += (uint32_t)batch;
+            if (stp.pt_this && m.T >= 2) {
+                pt_event++;
+                if (cfg->pt_schedule == PP_PT_FULL_LADDER) parity = 1 - parity;       // mod.rs:793-795
+            } else if (stp.pt_this) {
+                pt_event++;
+            }
+            sid += batch;
+        }
+        for (Ctx &c : chunks) {
+            for (const Step &stp : steps) {
+                bool fused = false;
+                st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, stp.record || stp.pt_this,
+                                   stp.record, stp.record, stp.record, &fused);
+                if (st != PP_OK) return st;
+                if (stp.record && !fused) {
+                    st = launch_overlap(s, c);                                         // mod.rs:527-529
+                    if (st != PP_OK) return st;
+                    fold_kernel<<<blocks_for(c.m.D * c.m.T, 128), 128, 0, c.stream>>>(c.m, c.st, c.m.P > 0);  // mod.rs:543-578
+                    s->launches++;
+                }
+                if (stp.pt_this) {                                                     // mod.rs:748-796
+                    st = launch_pt(s, c, cfg->pt_schedule, stp.pt_event, stp.parity, true);
+                    if (st != PP_OK) return st;
+                }
             }
         }
-        for (int64_t b = 0; b < batch; b++) {
-            if (interrupt && *interrupt) {  // mod.rs:406-408
-                cudaStreamSynchronize(s->stream);
-                return fail(PP_ERR_INTERRUPTED, "interrupted");
-            }
-            if (on_sweep) on_sweep(user, (uint64_t)(sweep_id + b));  // mod.rs:409
-        }
-        const int64_t last = sweep_id + batch - 1;
-        const bool record = last >= cfg->warmup_sweeps;                                   // mod.rs:410
-        const bool pt_this = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;        // mod.rs:486-488
-        bool overlap_done = false;
-        st = launch_sweeps(s, cfg->sweep_mode, s->sweep_counter, (int)batch, cfg->exact_log, record || pt_this, record,
-                           record, &overlap_done);
+        s->sweep_counter = sweep_counter;
+        s->pt_event_counter = pt_event;
+        s->next_parity = parity;
+        if (on_sweep)
+            for (int64_t sid = sweep_id; sid < mb_end; sid++) on_sweep(user, (uint64_t)sid);  // mod.rs:409
+        sweep_id = mb_end;
+    }
+    for (Ctx &c : chunks) {  // leave the canonical state behind: no pending exchange, handle pointer on the current buffer
+        st = flush_swaps(s, c);
         if (st != PP_OK) return st;
-        s->sweep_counter += (uint32_t)batch;
-        if (record) {
-            if (!overlap_done) st = launch_overlap(s);                                      // mod.rs:527-529
-            if (st != PP_OK) return st;
-            fold_kernel<<<blocks_for(m.D * m.T, 128), 128, 0, s->stream>>>(m, s->st, m.P > 0);  // mod.rs:543-578
-            s->launches++;
+    }
+    commit_ctx(s, chunks[0]);
+    if (chunks.size() > 1) {
+        for (size_t i = 0; i < s->xstreams.size(); i++) {
+            CUDA_TRY(cudaEventRecord(s->xevents[i], s->xstreams[i]));
+            CUDA_TRY(cudaStreamWaitEvent(s->stream, s->xevents[i], 0));
         }
-        if (pt_this) {                                                                      // mod.rs:748-796
-            st = launch_pt(s, cfg->pt_schedule, s->pt_event_counter);
-            if (st != PP_OK) return st;
-            s->pt_event_counter++;
-        }
-        sweep_id += batch;
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -971,7 +1174,9 @@ extern "C" pp_status pp_op_sweep(pp_sim *s, int32_t sweep_mode, uint32_t sweep_i
     const bool f32 = s->mv.coupling_class == COUP_F32;
     pp_status st = ensure_tables(s, f32 && exact_log && sweep_mode == PP_SWEEP_METROPOLIS, f32 && exact_log && sweep_mode == PP_SWEEP_GIBBS);
     if (st != PP_OK) return st;
-    st = launch_sweeps(s, sweep_mode, sweep_index, 1, exact_log, false, false);
+    Ctx wc = whole_ctx(s);
+    st = launch_sweeps(s, wc, sweep_mode, sweep_index, 1, exact_log, false, false);
+    commit_ctx(s, wc);
     if (st != PP_OK) return st;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return PP_OK;
@@ -980,7 +1185,8 @@ extern "C" pp_status pp_op_sweep(pp_sim *s, int32_t sweep_mode, uint32_t sweep_i
 extern "C" pp_status pp_op_energies_mags(pp_sim *s, float *energies, int64_t *mags) {
     if (!s) return fail(PP_ERR_INVALID, "sim is NULL");
     CUDA_TRY(cudaSetDevice(s->device));
-    pp_status st = launch_energy(s, true);
+    Ctx wc = whole_ctx(s);
+    pp_status st = launch_energy(s, wc, true);
     if (st != PP_OK) return st;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     const size_t n = (size_t)s->mv.D * s->mv.S;
@@ -993,7 +1199,8 @@ extern "C" pp_status pp_op_overlap(pp_sim *s, int64_t *dot_spin, int64_t *dot_li
     if (!s) return fail(PP_ERR_INVALID, "sim is NULL");
     if (s->mv.P == 0) return fail(PP_ERR_INVALID, "overlap needs n_replicas >= 2");
     CUDA_TRY(cudaSetDevice(s->device));
-    pp_status st = launch_overlap(s);
+    Ctx wc = whole_ctx(s);
+    pp_status st = launch_overlap(s, wc);
     if (st != PP_OK) return st;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     const size_t n = (size_t)s->mv.D * s->mv.P * s->mv.T;
@@ -1008,7 +1215,9 @@ extern "C" pp_status pp_op_pt(pp_sim *s, int32_t pt_schedule, uint32_t pt_event)
     CUDA_TRY(cudaSetDevice(s->device));
     pp_status st = ensure_tables(s, true, false);
     if (st != PP_OK) return st;
-    st = launch_pt(s, pt_schedule, pt_event);
+    Ctx wc = whole_ctx(s);
+    st = launch_pt(s, wc, pt_schedule, pt_event, s->next_parity);
+    if (pt_schedule == PP_PT_FULL_LADDER) s->next_parity = 1 - s->next_parity;  // mod.rs:793-795
     if (st != PP_OK) return st;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return PP_OK;

@@ -28,6 +28,7 @@
 
 #include "../../include/peapods_b200.h"
 #include "pp_device.cuh"
+#include "pp_kernels_stats.cuh"
 #include "pp_plan.h"
 
 namespace pp {
@@ -364,8 +365,9 @@ __device__ __forceinline__ void msc3d_pair_item(const uint32_t *A, const uint32_
 // dynamic smem (words): [3N coupling words | 4*n_items item table | NH*RPC*N spins | 8 (mbarriers) | NH*512 scratch]
 template <int RPC, bool METRO, int NH>
 __global__ void __launch_bounds__(MSC3D_NTH *NH, 1)
-msc3d_kernel(ModelView m, Msc3dView gv, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags,
-             int want_overlap, int64_t group_offset, long long *dot_spin, long long *dot_link) {
+msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags,
+             int want_overlap, int want_fold, int64_t group_offset, long long *dot_spin, long long *dot_link,
+             uint32_t *words_out, const uint32_t *swap_mask, int pt_schedule, int pt_parity) {
     extern __shared__ __align__(128) uint32_t smem[];
     const uint32_t N = gv.N, N2 = gv.N2;
     const bool has_J = m.Jw != nullptr;
@@ -397,11 +399,85 @@ msc3d_kernel(ModelView m, Msc3dView gv, uint32_t sweep_index, int n_sweeps, int 
         bulk_g2s(items, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
     }
     if (t >= m.T) return;  // odd T: the last CTA of a group has an idle half
+    // Spin words: m.words is the input buffer, words_out the output buffer (ping-pong, so that a CTA may still read its
+    // neighbours' pre-sweep words while they are being rewritten).  When a parallel-tempering event is pending
+    // (swap_mask != nullptr) the lanes that crossed an edge are gathered from the neighbouring slots while loading:
+    //   single_random_edge: out = a ^ ((a ^ w[t-1]) & mask[t-1]) ^ ((a ^ w[t+1]) & mask[t])   (a lane attempts one edge)
+    //   full_ladder:        the same exchange applied for the edges of the first parity, then of the second
+    // (mcmc/tempering.rs:20-70: labels move there, lanes move here).  Systems without a crossing lane take the bulk path.
+    uint32_t bulk_mask = 0;  // bit r: replica r is staged by a bulk-async copy
+    uint32_t mk[RPC][3];     // schedule 0: {mask[t-1], mask[t], -}; schedule 1: {m1(t), m2(t), m1(t2)}
+    int t1 = -1, t2 = -1, t21 = -1;  // full ladder: first-pass partner of t, second-pass partner of t, first-pass partner of t2
+    {
+        auto partner = [&](int x, int q) {  // slot exchanging with x over an edge of parity q (edges q, q+2, ...), or -1
+            if (x >= q && ((x - q) & 1) == 0 && x + 1 < m.T) return x + 1;
+            if (x - 1 >= q && ((x - 1 - q) & 1) == 0) return x - 1;
+            return -1;
+        };
+        if (swap_mask && pt_schedule == 1) {
+            t1 = partner(t, pt_parity);
+            t2 = partner(t, 1 - pt_parity);
+            t21 = t2 >= 0 ? partner(t2, pt_parity) : -1;
+        }
+#pragma unroll
+        for (int r = 0; r < RPC; r++) {
+            mk[r][0] = mk[r][1] = mk[r][2] = 0u;
+            if (swap_mask) {
+                const uint32_t *mrow = swap_mask + (g * m.R + r) * (int64_t)(m.T - 1);
+                if (pt_schedule == 0) {
+                    if (t > 0) mk[r][0] = __ldg(mrow + t - 1);
+                    if (t + 1 < m.T) mk[r][1] = __ldg(mrow + t);
+                } else {
+                    if (t1 >= 0) mk[r][0] = __ldg(mrow + min(t, t1));
+                    if (t2 >= 0) mk[r][1] = __ldg(mrow + min(t, t2));
+                    if (t21 >= 0 && mk[r][1]) mk[r][2] = __ldg(mrow + min(t2, t21));
+                }
+            }
+            if ((mk[r][0] | mk[r][1]) == 0u) bulk_mask |= 1u << r;
+        }
+    }
     if (ht == 0) {
-        mbar_expect_tx(&bars[1 + half], bytes * RPC);
+        mbar_expect_tx(&bars[1 + half], bytes * (uint32_t)__popc(bulk_mask));
 #pragma unroll
         for (int r = 0; r < RPC; r++)
-            bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, &bars[1 + half]);
+            if (bulk_mask >> r & 1u)
+                bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, &bars[1 + half]);
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; r++) {
+        if (bulk_mask >> r & 1u) continue;
+        const uint32_t *base = m.words + (g * m.S + (int64_t)r * m.T) * (int64_t)N;  // slot 0 of this replica's ladder
+        const uint4 *wa = reinterpret_cast<const uint4 *>(base + (int64_t)t * N);
+        uint4 *dst = reinterpret_cast<uint4 *>(sp + (size_t)r * N);
+        if (pt_schedule == 0) {
+            const uint32_t mL = mk[r][0], mR = mk[r][1];
+            const uint4 *wl = reinterpret_cast<const uint4 *>(base + (int64_t)(t - 1) * N);
+            const uint4 *wr = reinterpret_cast<const uint4 *>(base + (int64_t)(t + 1) * N);
+#pragma unroll 8
+            for (uint32_t i = ht; i < N / 4; i += MSC3D_NTH) {
+                const uint4 a = __ldg(wa + i);
+                uint4 o = a;
+                if (mL) { const uint4 b = __ldg(wl + i); o.x ^= (a.x ^ b.x) & mL; o.y ^= (a.y ^ b.y) & mL; o.z ^= (a.z ^ b.z) & mL; o.w ^= (a.w ^ b.w) & mL; }
+                if (mR) { const uint4 c = __ldg(wr + i); o.x ^= (a.x ^ c.x) & mR; o.y ^= (a.y ^ c.y) & mR; o.z ^= (a.z ^ c.z) & mR; o.w ^= (a.w ^ c.w) & mR; }
+                dst[i] = o;
+            }
+        } else {
+            const uint32_t m1 = mk[r][0], m2 = mk[r][1], m12 = mk[r][2];
+            const uint4 *w1p = reinterpret_cast<const uint4 *>(base + (int64_t)max(t1, 0) * N);
+            const uint4 *w2p = reinterpret_cast<const uint4 *>(base + (int64_t)max(t2, 0) * N);
+            const uint4 *w21p = reinterpret_cast<const uint4 *>(base + (int64_t)max(t21, 0) * N);
+#pragma unroll 8
+            for (uint32_t i = ht; i < N / 4; i += MSC3D_NTH) {
+                uint4 a = __ldg(wa + i);
+                if (m1) { const uint4 b = __ldg(w1p + i); a.x ^= (a.x ^ b.x) & m1; a.y ^= (a.y ^ b.y) & m1; a.z ^= (a.z ^ b.z) & m1; a.w ^= (a.w ^ b.w) & m1; }
+                if (m2) {
+                    uint4 c = __ldg(w2p + i);
+                    if (m12) { const uint4 e = __ldg(w21p + i); c.x ^= (c.x ^ e.x) & m12; c.y ^= (c.y ^ e.y) & m12; c.z ^= (c.z ^ e.z) & m12; c.w ^= (c.w ^ e.w) & m12; }
+                    a.x ^= (a.x ^ c.x) & m2; a.y ^= (a.y ^ c.y) & m2; a.z ^= (a.z ^ c.z) & m2; a.w ^= (a.w ^ c.w) & m2;
+                }
+                dst[i] = a;
+            }
+        }
     }
     // acceptance thresholds of this temperature: count[u] = table[t][2u]  (sweep.rs:162-166, index ec + 2z' = 2*unsat)
     uint32_t thr[7];
@@ -414,6 +490,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, uint32_t sweep_index, int n_sweeps, int 
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     mbar_wait(&bars[0], 0);
     mbar_wait(&bars[1 + half], 0);
+    if (bulk_mask != (1u << RPC) - 1u) half_barrier(half, MSC3D_NTH);  // gathered words were written with plain stores
 
     // ---- sweeps: colour 0 then colour 1 (RNG-SPEC visit order)
     for (int sw = 0; sw < n_sweeps; sw++) {
@@ -442,7 +519,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, uint32_t sweep_index, int n_sweeps, int 
         if (ht == 0) {
 #pragma unroll
             for (int r = 0; r < RPC; r++)
-                bulk_s2g(m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), sp + (size_t)r * N, bytes);
+                bulk_s2g(words_out + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), sp + (size_t)r * N, bytes);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
@@ -492,33 +569,46 @@ msc3d_kernel(ModelView m, Msc3dView gv, uint32_t sweep_index, int n_sweeps, int 
             }
         }
         half_barrier(half, MSC3D_NTH);
+        // warp 0 of the half: lane l finishes realization 32g + l at slot t -- per-system energy / magnetisation, pair
+        // dots, and (want_fold) the recorded-sweep fold of simulation/mod.rs:543-578 + statistics/overlap.rs:283-306
         const int64_t d = g * 32 + lane;
-        if (d < m.D) {
-            if (w < RPC && (want_energy || want_mags)) {
-                const int r = w;
-                const int sys = m.system_ids[d * m.S + r * m.T + t];
+        if (w == 0 && d < m.D) {
+            float Ev[RPC];
+            long long Mv[RPC], Sv[NP > 0 ? NP : 1], Lv[NP > 0 ? NP : 1];
+#pragma unroll
+            for (int r = 0; r < RPC; r++) {
                 uint32_t e = 0, dn = 0;
 #pragma unroll
                 for (int k = 0; k < WPE; k++) {
-                    e += red[((r * 2 + 0) * WPE + k) * 32 + lane];
-                    dn += red[((r * 2 + 1) * WPE + k) * 32 + lane];
+                    if (want_energy) e += red[((r * 2 + 0) * WPE + k) * 32 + lane];
+                    if (want_mags) dn += red[((r * 2 + 1) * WPE + k) * 32 + lane];
                 }
-                if (want_energy) {  // sum_i sum_d s s J = (#bonds) - 2 * unsatisfied   (energy.rs:103-108)
-                    const long long e_int = 3ll * N - 2ll * e;
-                    m.energies[d * m.S + sys] = __fdiv_rn((float)e_int, (float)N);
-                }
-                if (want_mags) m.mags[d * m.S + sys] = (long long)N - 2ll * dn;
-            } else if (NP > 0 && want_overlap && w >= 4 && w - 4 < m.P) {
-                const int p = w - 4;
-                uint32_t cs = 0, cl = 0;
+                // sum_i sum_d s s J = (#bonds) - 2 * unsatisfied, e = that / N in f32   (energy.rs:103-108)
+                Ev[r] = __fdiv_rn((float)(3ll * N - 2ll * e), (float)N);
+                Mv[r] = (long long)N - 2ll * dn;
+                const int sys = m.system_ids[d * m.S + r * m.T + t];
+                if (want_energy) m.energies[d * m.S + sys] = Ev[r];
+                if (want_mags) m.mags[d * m.S + sys] = Mv[r];
+            }
+            if (NP > 0 && want_overlap) {
 #pragma unroll
-                for (int k = 0; k < WPP; k++) {
-                    cs += red_p[((p * 2 + 0) * WPP + k) * 32 + lane];
-                    cl += red_p[((p * 2 + 1) * WPP + k) * 32 + lane];
+                for (int p = 0; p < NP; p++) {
+                    uint32_t cs = 0, cl = 0;
+#pragma unroll
+                    for (int k = 0; k < WPP; k++) {
+                        cs += red_p[((p * 2 + 0) * WPP + k) * 32 + lane];
+                        cl += red_p[((p * 2 + 1) * WPP + k) * 32 + lane];
+                    }
+                    Sv[p] = (long long)N - 2ll * cs;
+                    Lv[p] = 3ll * N - 2ll * cl;
+                    const int64_t o = (d * m.P + p) * m.T + t;
+                    dot_spin[o] = Sv[p];
+                    dot_link[o] = Lv[p];
                 }
-                const int64_t o = (d * m.P + p) * m.T + t;
-                dot_spin[o] = (long long)N - 2ll * cs;
-                dot_link[o] = 3ll * N - 2ll * cl;
+            }
+            if (want_fold) {
+                if (NP > 0 && want_overlap) fold_red<RPC, NP>(m, st, d, t, Mv, Ev, Sv, Lv);
+                else fold_red<RPC, 0>(m, st, d, t, Mv, Ev, Sv, Lv);
             }
         }
     }

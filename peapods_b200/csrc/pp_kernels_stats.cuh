@@ -28,22 +28,24 @@ struct PtView {
     int cold_slot, hot_slot;
 };
 
-// K9 (+K7): fold one recorded sweep.  One thread per (realization d, temperature t).
-__global__ void fold_kernel(ModelView m, StatsView st, int with_overlap) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= m.D * m.T) return;
-    const int64_t d = gid / m.T;
-    const int t = (int)(gid % m.T);
+// K9 (+K7): fold one recorded sweep for (realization d, temperature t).
+// Mv / Ev: magnetisation sums and energies of the R systems sitting at slot t (replica order);
+// dsp / dlk: the P pair dots at slot t.  All f64 accumulations in the reference's order.
+// RFIX > 0: the replica count is the compile-time constant RFIX (loops unroll, the getters may index registers).
+template <int RFIX, typename GetM, typename GetE, typename GetS, typename GetL>
+__device__ __forceinline__ void fold_one(const ModelView &m, const StatsView &st, int64_t d, int t, int with_overlap,
+                                         GetM get_m, GetE get_e, GetS get_ds, GetL get_dl) {
     const float nf = (float)m.N;
     double *sums = st.sums + d * 11 * m.T + t;
     // simulation/mod.rs:555-578: replica-inner order
     double s0 = sums[0], s1 = sums[1 * m.T], s2 = sums[2 * m.T], s3 = sums[3 * m.T], s4 = sums[4 * m.T];
-    for (int r = 0; r < m.R; r++) {
-        const int sys = m.system_ids[d * m.S + r * m.T + t];
-        const float mag = __fdiv_rn((float)m.mags[d * m.S + sys], nf);
+    const int R = RFIX > 0 ? RFIX : m.R, P = RFIX > 0 ? RFIX / 2 : m.P;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float mag = __fdiv_rn((float)get_m(r), nf);
         const float m2 = __fmul_rn(mag, mag);
         const float m4 = __fmul_rn(m2, m2);
-        const float e = m.energies[d * m.S + sys];
+        const float e = get_e(r);
         s0 = __dadd_rn(s0, (double)mag);
         s1 = __dadd_rn(s1, (double)m2);
         s2 = __dadd_rn(s2, (double)m4);
@@ -57,9 +59,10 @@ __global__ void fold_kernel(ModelView m, StatsView st, int with_overlap) {
     const int64_t bins = m.N + 1;
     double o0 = sums[5 * m.T], o1 = sums[6 * m.T], o2 = sums[7 * m.T], o3 = sums[8 * m.T], o4 = sums[9 * m.T],
            o5 = sums[10 * m.T];
-    for (int p = 0; p < m.P; p++) {
-        const long long dsp = st.dot_spin[(d * m.P + p) * m.T + t];
-        const long long dlk = st.dot_link[(d * m.P + p) * m.T + t];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const long long dsp = get_ds(p);
+        const long long dlk = get_dl(p);
         const float ql = __fdiv_rn((float)dlk, nb);
         const float q = __fdiv_rn((float)dsp, nf);
         const float q2 = __fmul_rn(q, q);
@@ -80,6 +83,63 @@ __global__ void fold_kernel(ModelView m, StatsView st, int with_overlap) {
     sums[10 * m.T] = o5;
 }
 
+// Same fold as fire-and-forget reductions (RED.ADD.F64 / RED.ADD.U32): no load, so the warp that finishes 32
+// realizations in the fused msc3d epilogue never waits on memory.  Every accumulator is touched by exactly one thread
+// per kernel and kernels of one chunk are stream-ordered, so each f64 cell still receives the reference's additions in
+// the reference's order (IEEE round-to-nearest adds, same-address reductions of one thread stay in program order):
+// the sums are bit-identical to the sequential fold.
+template <int R, int NP>
+__device__ __forceinline__ void fold_red(const ModelView &m, const StatsView &st, int64_t d, int t, const long long *Mv,
+                                         const float *Ev, const long long *Sv, const long long *Lv) {
+    const float nf = (float)m.N;
+    double *sums = st.sums + d * 11 * m.T + t;
+#pragma unroll
+    for (int r = 0; r < R; r++) {  // simulation/mod.rs:555-578
+        const float mag = __fdiv_rn((float)Mv[r], nf);
+        const float m2 = __fmul_rn(mag, mag);
+        const float m4 = __fmul_rn(m2, m2);
+        const float e = Ev[r];
+        atomicAdd(sums + 0 * m.T, (double)mag);
+        atomicAdd(sums + 1 * m.T, (double)m2);
+        atomicAdd(sums + 2 * m.T, (double)m4);
+        atomicAdd(sums + 3 * m.T, (double)e);
+        atomicAdd(sums + 4 * m.T, __dmul_rn((double)e, (double)e));
+    }
+    const float nb = (float)(m.N * m.z);
+    const int64_t bins = m.N + 1;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {  // statistics/overlap.rs:283-306 + :318-324
+        const float ql = __fdiv_rn((float)Lv[p], nb);
+        const float q = __fdiv_rn((float)Sv[p], nf);
+        const float q2 = __fmul_rn(q, q);
+        const float ql2 = __fmul_rn(ql, ql);
+        atomicAdd(sums + 5 * m.T, (double)q);
+        atomicAdd(sums + 6 * m.T, (double)q2);
+        atomicAdd(sums + 7 * m.T, (double)__fmul_rn(q2, q2));
+        atomicAdd(sums + 8 * m.T, (double)ql);
+        atomicAdd(sums + 9 * m.T, (double)ql2);
+        atomicAdd(sums + 10 * m.T, (double)__fmul_rn(ql2, ql2));
+        const int64_t h = (d * m.T + t) * bins + (Sv[p] + m.N) / 2;
+        atomicAdd(st.hist + h, 1u);
+        atomicAdd(st.ql_at_q + h, (double)ql);
+        atomicAdd(st.ql2_at_q + h, (double)ql2);
+    }
+}
+
+// standalone: one thread per (realization d, temperature t), inputs from the per-system arrays
+__global__ void fold_kernel(ModelView m, StatsView st, int with_overlap) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m.D * m.T) return;
+    const int64_t d = gid / m.T;
+    const int t = (int)(gid % m.T);
+    fold_one<0>(
+        m, st, d, t, with_overlap,
+        [&](int r) { return m.mags[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
+        [&](int r) { return m.energies[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
+        [&](int p) { return st.dot_spin[(d * m.P + p) * m.T + t]; },
+        [&](int p) { return st.dot_link[(d * m.P + p) * m.T + t]; });
+}
+
 // realization.rs:109-120
 __device__ __forceinline__ void pt_record_arrival(const PtView &pt, int64_t base, int system, int slot) {
     if (slot == pt.hot_slot) {
@@ -91,8 +151,8 @@ __device__ __forceinline__ void pt_record_arrival(const PtView &pt, int64_t base
 }
 
 // tempering.rs:73-102; logtab[draw] = host-libm logf(draw / 2^24) so the decision is the CPU's bit for bit
-__device__ __forceinline__ void pt_attempt_edge(const ModelView &m, const PtView &pt, int64_t d, int r, int edge,
-                                                uint32_t draw, bool msc) {
+__device__ __forceinline__ bool pt_attempt_edge(const ModelView &m, const PtView &pt, int64_t d, int r, int edge,
+                                                uint32_t draw) {
     int32_t *sid = m.system_ids + d * m.S + r * m.T;
     const float temp_1 = m.temps[edge], temp_2 = m.temps[edge + 1];
     const int left = sid[edge], right = sid[edge + 1];
@@ -103,21 +163,18 @@ __device__ __forceinline__ void pt_attempt_edge(const ModelView &m, const PtView
     const int64_t eb = d * (m.T - 1);
     // the T-1 edge counters of a realization are shared by its R replica threads
     atomicAdd(&pt.edge_attempts[eb + edge], 1ull);
-    if (!accepted) return;
+    if (!accepted) return false;
     sid[edge] = right;
     sid[edge + 1] = left;
     atomicAdd(&pt.edge_acceptances[eb + edge], 1ull);
     pt_record_arrival(pt, d * m.S, left, edge + 1);   // realization.rs:80-81
     pt_record_arrival(pt, d * m.S, right, edge);
-    if (msc) {
-        const int64_t g = d >> 5;
-        atomicOr(&pt.swap_mask[(g * m.R + r) * (m.T - 1) + edge], 1u << (d & 31));
-    }
+    return true;
 }
 
 // K8: one thread per (realization, replica).  RNG-SPEC PT domain: key = realization key,
 // counter = {edge | 0xFFFFFFFF, pt_event, replica, TAG_PT}.
-__global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int first_parity, uint32_t pt_event, int msc) {
+__global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int first_parity, uint32_t pt_event) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= m.D * m.R || m.T < 2) return;
     const int64_t d = gid / m.R;
@@ -127,13 +184,61 @@ __global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int fir
     if (schedule == 0) {  // tempering.rs:20-42
         const u32x4 o = philox4x32_10(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
         const int edge = (int)(((uint64_t)o.y * (uint64_t)(m.T - 1)) >> 32);
-        pt_attempt_edge(m, pt, d, r, edge, o.x >> 8, msc != 0);
+        pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
     } else {  // tempering.rs:45-70
         for (int pi = 0; pi < 2; pi++) {
             const int parity = pi == 0 ? first_parity : 1 - first_parity;
             for (int edge = parity; edge < m.T - 1; edge += 2) {
                 const u32x4 o = philox4x32_10((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
-                pt_attempt_edge(m, pt, d, r, edge, o.x >> 8, msc != 0);
+                pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
+            }
+        }
+    }
+}
+
+// K8, multispin layout: one warp per (word group g, replica r) ladder, lane l = realization 32g + l.  Same decisions
+// and counters as pt_exchange_kernel; the per-edge lane masks are produced with warp votes (plain stores, no
+// pre-zeroing): swap_mask[(g*R + r)*(T-1) + edge] = lanes whose configurations cross that edge.
+__global__ void __launch_bounds__(128) pt_exchange_msc_kernel(ModelView m, PtView pt, int schedule, int first_parity, uint32_t pt_event) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t G = (m.D + 31) >> 5;
+    if (wid >= G * m.R || m.T < 2) return;
+    const int64_t g = wid / m.R;
+    const int r = (int)(wid % m.R);
+    const int64_t d = g * 32 + lane;
+    const bool live = d < m.D;
+    uint32_t *mask = pt.swap_mask + wid * (m.T - 1);
+    uint32_t k0 = 0, k1 = 0;
+    if (live) {
+        const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
+        k0 = (uint32_t)key;
+        k1 = (uint32_t)(key >> 32);
+    }
+    if (schedule == 0) {  // tempering.rs:20-42: every lane draws its own edge
+        for (int e = lane; e < m.T - 1; e += 32) mask[e] = 0u;
+        __syncwarp();
+        int edge = -1;
+        bool acc = false;
+        if (live) {
+            const u32x4 o = philox4x32_10(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+            edge = (int)(((uint64_t)o.y * (uint64_t)(m.T - 1)) >> 32);
+            acc = pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
+        }
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, edge);
+        const uint32_t accepted = __ballot_sync(0xFFFFFFFFu, acc);
+        if (live && lane == __ffs(same) - 1) mask[edge] = same & accepted;
+    } else {  // tempering.rs:45-70
+        for (int pi = 0; pi < 2; pi++) {
+            const int parity = pi == 0 ? first_parity : 1 - first_parity;
+            for (int edge = parity; edge < m.T - 1; edge += 2) {
+                bool acc = false;
+                if (live) {
+                    const u32x4 o = philox4x32_10((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+                    acc = pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
+                }
+                const uint32_t accepted = __ballot_sync(0xFFFFFFFFu, acc);
+                if (lane == 0) mask[edge] = accepted;
             }
         }
     }

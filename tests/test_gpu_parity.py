@@ -170,6 +170,24 @@ def test_msc3d_sample_is_bit_exact(oracle, shape, kind, D, R, temps, schedule):
             assert np.array_equal(gpu.get_energies(d), cpu.energies(d))
 
 
+@pytest.mark.parametrize("streams,groups,macro", [(2, 1, 4), (3, 2, 16), (1, 1, 1)])
+def test_msc3d_chunked_multistream_execution_is_bit_exact(oracle, monkeypatch, streams, groups, macro):
+    """The chunk / stream / macro-batch plan of pp_sample must not change any result."""
+    monkeypatch.setenv("PP_STREAMS", str(streams))
+    monkeypatch.setenv("PP_CHUNK_GROUPS", str(groups))
+    monkeypatch.setenv("PP_MACRO_BATCH", str(macro))
+    shape, temps, R, D = (4, 4, 8), np.linspace(0.8, 1.6, 5), 4, 150   # 5 word groups, the last one padded
+    gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, D, layout="msc")
+    assert gpu.uses_msc3d
+    seen = []
+    for n_sweeps, interval, schedule in ((37, 1, "single_random_edge"), (21, 2, "full_ladder"), (9, None, "full_ladder")):
+        rg = gpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule, on_sweep=seen.append)
+        rc = cpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+    assert seen == list(range(37)) + list(range(21)) + list(range(9))
+
+
 def test_msc3d_operator_entry_points_match_oracle(oracle):
     shape, temps, R, DD = (4, 4, 8), [0.9, 1.2, 1.5], 4, 37
     gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, DD, layout="msc")
