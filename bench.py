@@ -297,6 +297,7 @@ def run_ours(args):
         del s
         return nb
 
+    last = None
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -308,14 +309,25 @@ def run_ours(args):
     e2e_value = total_attempts / (e2e_ms * 1e6)
     h2d = J.nbytes + temps.nbytes
 
+    # ---- the end-of-run reduction across ranks (untimed): ordered sum over realizations on rank 0 ----------------
+    if world > 1:
+        from peapods_b200.sharded import gather_merge
+
+        s = pb.IsingSimulation(list(SHAPE), J, temps, N_REPLICAS, None, seed, layout="msc", device=local_rank,
+                               sample_offset=first)
+        merged = gather_merge(s.sample(8, "metropolis", **kw), s.last_per_sample_means, N_REPLICAS)
+        if rank == 0:
+            assert np.all(np.isfinite(merged["energies"])) and len(merged["overlap_histogram"]) == N_TEMPS
+        del s
+
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns, nsw = 2 * max(cores, 16), 12
+        ns, nsw = 4 * max(cores, 16), 12
         v, dt = cpu_baseline_run(ns, nsw, cores)
-        if dt < 4.0:  # aim for 10-30 s of CPU work
-            nsw = int(min(200, max(nsw, nsw * 12.0 / max(dt, 1e-3))))
+        if dt < 6.0:  # aim for 10-30 s of CPU work
+            nsw = int(min(600, max(nsw, nsw * 15.0 / max(dt, 1e-3))))
             v, dt = cpu_baseline_run(ns, nsw, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{ns} of {D} disorder samples x {nsw} sweeps ({dt:.1f} s), same lattice/temps/replicas/PT/overlap"}
@@ -344,7 +356,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--sweeps-per-step", type=int, default=64)
+    ap.add_argument("--sweeps-per-step", type=int, default=128)
     ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")

@@ -53,6 +53,7 @@ class _Results(C.Structure):
         + [("hist", _PU64), ("ql_at_q_sum", _PD), ("ql2_at_q_sum", _PD)]
         + [("ps_hist", _PU64), ("ps_ql_at_q_sum", _PD), ("ps_ql2_at_q_sum", _PD)]
         + [("edge_attempts", _PU64), ("edge_acceptances", _PU64), ("round_trips", _PU64)]
+        + [("ps_means", _PD)]
     )
 
 
@@ -97,6 +98,7 @@ def lib():
         "orc_sim_new": (vp, [i32, vp, i32, vp, vp, i64, vp, i32, i32, u64, i32, vp]),
         "orc_sim_free": (None, [vp]),
         "orc_sim_reset": (None, [vp, i32, u64]),
+        "orc_sim_set_sample_offset": (None, [vp, i64]),
         "orc_sim_sample": (i32, [vp, C.POINTER(_Config), C.POINTER(_Results)]),
         "orc_sim_spins": (vp, [vp, i64]),
         "orc_sim_system_ids": (vp, [vp, i64]),
@@ -228,7 +230,7 @@ class Sim:
     """simulation/mod.rs:865-939 driven like src/lib.rs:106-174 / 176-333 / 620-633."""
 
     def __init__(self, shape, couplings, temperatures, n_replicas=1, offsets=None, seed=42, rng_mode=RNG_XOSHIRO,
-                 colour=None):
+                 colour=None, sample_offset=0):
         self.shape = np.asarray(shape, dtype=np.int64)
         self.offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
         n_off = 0 if self.offsets is None else len(self.offsets)
@@ -249,6 +251,8 @@ class Sim:
                                    self.T, self.R, int(seed), rng_mode, _p(self.colour))
         if not self.h:
             raise ValueError(lib().orc_last_error().decode())
+        if sample_offset:
+            lib().orc_sim_set_sample_offset(self.h, int(sample_offset))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -310,6 +314,8 @@ class Sim:
             res.edge_acceptances = pt["edge_acceptances"].ctypes.data_as(_PU64)
             res.round_trips = pt["round_trips"].ctypes.data_as(_PU64)
             out["per_disorder"] = {"parallel_tempering": pt}
+        self.last_per_sample_means = np.zeros((D, 11, T), dtype=np.float64)
+        res.ps_means = self.last_per_sample_means.ctypes.data_as(_PD)
         rc = lib().orc_sim_sample(self.h, C.byref(cfg), C.byref(res))
         del keep
         if rc != 0:

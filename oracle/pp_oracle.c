@@ -468,6 +468,7 @@ struct orc_sim {
     float *couplings; /* [D][N*z'] */
     float *temps;     /* [T] */
     uint64_t ctor_seed, cur_seed;
+    int64_t sample_offset; /* global index of realization 0 (a shard of a larger run); seeds use global indices */
     realization *reals;
     uint16_t *colour;
     int64_t *order;
@@ -599,7 +600,7 @@ orc_sim *orc_sim_new(int n_dims, const int64_t *shape, int n_offsets, const int6
         re->pt.edge_acceptances = calloc((size_t)n_edges + 1, sizeof(uint64_t));
         re->pt.round_trips = calloc((size_t)S + 1, sizeof(uint64_t));
         re->pt.trip_state = calloc((size_t)S + 1, 1);
-        realization_init(sim, re, orc_realization_seed(seed, (uint64_t)r)); /* lib.rs:158-164 */
+        realization_init(sim, re, orc_realization_seed(seed, (uint64_t)(sim->sample_offset + r))); /* lib.rs:158-164 */
     }
     return sim;
 }
@@ -625,7 +626,13 @@ void orc_sim_reset(orc_sim *sim, int has_seed, uint64_t seed) {
     sim->sweep_counter = 0;
     sim->pt_event_counter = 0;
     for (int64_t r = 0; r < sim->n_real; r++)
-        realization_init(sim, &sim->reals[r], orc_realization_seed(base, (uint64_t)r));
+        realization_init(sim, &sim->reals[r], orc_realization_seed(base, (uint64_t)(sim->sample_offset + r)));
+}
+
+/* shard support: this sim holds realizations [offset, offset + D) of a larger run; re-initialises the state */
+void orc_sim_set_sample_offset(orc_sim *sim, int64_t offset) {
+    sim->sample_offset = offset;
+    orc_sim_reset(sim, 1, sim->cur_seed);
 }
 
 const int8_t *orc_sim_spins(const orc_sim *sim, int64_t r) { return sim->reals[r].spins; }
@@ -672,7 +679,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
     int philox = sim->rng_mode != ORC_RNG_XOSHIRO;
     int msc = sim->rng_mode == ORC_RNG_PHILOX_MSC;
     /* MSC layout: the 32 samples of a word share one key (RNG-SPEC) */
-    uint64_t sweep_key = msc ? orc_splitmix64(sim->cur_seed ^ orc_splitmix64(ORC_MSC_KEY_DOMAIN ^ (uint64_t)(ridx >> 5)))
+    uint64_t sweep_key = msc ? orc_splitmix64(sim->cur_seed ^ orc_splitmix64(ORC_MSC_KEY_DOMAIN ^ (uint64_t)((sim->sample_offset + ridx) >> 5)))
                              : re->base_seed;
 
     /* simulation/mod.rs:190-198: lookup only for Metropolis (reference); the Philox modes also use the
@@ -929,6 +936,8 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
             memcpy(out->round_trips + d * R * T, sim->reals[d].pt.round_trips, sizeof(uint64_t) * (size_t)R * T);
         }
     }
+    if (out->ps_means) /* [D][11][T]: rr[d].mags is one block of 11 rows (mags..energies2, then the six overlap rows) */
+        for (int64_t d = 0; d < D; d++) memcpy(out->ps_means + (size_t)d * 11 * T, rr[d].mags, sizeof(double) * 11 * (size_t)T);
     for (int64_t d = 0; d < D; d++) {
         free(rr[d].mags);
         if (n_pairs > 0 && !out->ps_hist) { free(rr[d].hist); free(rr[d].ql); free(rr[d].ql2); }

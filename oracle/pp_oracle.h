@@ -80,6 +80,8 @@ typedef struct {
     double *ps_ql_at_q_sum, *ps_ql2_at_q_sum;
     /* [D][T-1], [D][T-1], [D][R][T]; may be NULL */
     uint64_t *edge_attempts, *edge_acceptances, *round_trips;
+    /* [D][11][T] per-realization averages (mags, mags2, mags4, energies, energies2, q, q2, q4, ql, ql2, ql4); may be NULL */
+    double *ps_means;
 } orc_results;
 
 /* ---- RNG primitives ---------------------------------------------------- */
@@ -145,6 +147,8 @@ orc_sim *orc_sim_new(int n_dims, const int64_t *shape, int n_offsets, const int6
                      const uint16_t *colour /* required for PHILOX modes */);
 void orc_sim_free(orc_sim *sim);
 void orc_sim_reset(orc_sim *sim, int has_seed, uint64_t seed); /* src/lib.rs:624-633 */
+/* this sim holds realizations [offset, offset + D) of a larger run (seeds use global indices); re-initialises */
+void orc_sim_set_sample_offset(orc_sim *sim, int64_t offset);
 /* 0 ok; -1 invalid config (message via orc_last_error) */
 int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out);
 const int8_t *orc_sim_spins(const orc_sim *sim, int64_t realization);       /* [S*N] */

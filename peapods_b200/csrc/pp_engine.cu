@@ -135,7 +135,7 @@ static pp_status get_log_table(int device, bool gibbs, const float **out) {
                 }
             });
         for (auto &th : pool) th.join();
-        CUDA_TRY(cudaMalloc(&slot, sizeof(float) * (size_t)F24));
+        CUDA_TRY(cudaMalloc((void **)&slot, sizeof(float) * (size_t)F24)); /*static*/
         CUDA_TRY(cudaMemcpy(slot, host.data(), sizeof(float) * (size_t)F24, cudaMemcpyHostToDevice));
     }
     *out = slot;
@@ -205,6 +205,29 @@ static void prof_mark(pp_sim *s, cudaStream_t stream) {
     cudaEventRecord(s->prof_events[s->prof_used++], stream);
 }
 
+// Stream-ordered allocations from the device's default memory pool with an unlimited release threshold: buffers of a
+// destroyed handle stay cached in the pool, so constructing the next handle (the reference API builds one
+// IsingSimulation per model) does not pay cudaMalloc / cudaFree again.
+static cudaError_t pool_alloc(pp_sim *s, void **p, size_t bytes) {
+    static std::mutex mu;
+    static std::map<int, bool> configured;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[s->device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            configured[s->device] = true;
+        }
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, s->stream);
+}
+static void pool_free(pp_sim *s, void *p) {
+    if (p) cudaFreeAsync(p, s->stream);
+}
+
 static void free_sim(pp_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
@@ -213,7 +236,8 @@ static void free_sim(pp_sim *s) {
                     s->pt.edge_attempts, s->pt.edge_acceptances, s->pt.round_trips, s->pt.trip_state, s->pt.swap_mask,
                     s->st.sums, s->st.hist, s->st.ql_at_q, s->st.ql2_at_q, s->d_dot_spin, s->d_dot_link};
     for (void *p : ptrs)
-        if (p) cudaFree(p);
+        if (p) pool_free(s, p);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : s->xevents) cudaEventDestroy(e);
     for (cudaStream_t x : s->xstreams) cudaStreamDestroy(x);
@@ -600,15 +624,15 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         }
         m.coupling_class = COUP_FERRO;
     } else {
-        CREATE_TRY(cudaMalloc(&s->d_Jf, sizeof(float) * (size_t)n_coup));
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_Jf, sizeof(float) * (size_t)n_coup));
         CREATE_TRY(cudaMemcpy(s->d_Jf, desc->couplings, sizeof(float) * (size_t)n_coup, cudaMemcpyHostToDevice));
         int *d_flags = nullptr;
-        CREATE_TRY(cudaMalloc(&d_flags, sizeof(int) * 3));
+        CREATE_TRY(pool_alloc(s, (void **)&d_flags, sizeof(int) * 3));
         CREATE_TRY(cudaMemset(d_flags, 0, sizeof(int) * 3));
         classify_couplings_kernel<<<1184, 256, 0, s->stream>>>(s->d_Jf, n_coup, d_flags);
         CREATE_TRY(cudaStreamSynchronize(s->stream));
         CREATE_TRY(cudaMemcpy(flags, d_flags, sizeof(int) * 3, cudaMemcpyDeviceToHost));
-        cudaFree(d_flags);
+        pool_free(s, d_flags);
         if (flags[0] || !t_ok) m.coupling_class = COUP_F32;
         else if (!flags[1] && !flags[2]) m.coupling_class = COUP_FERRO;
         else m.coupling_class = COUP_UNIT;
@@ -642,15 +666,15 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         if (storage_space) storage_tables(s->plan, nbr_s, order_s);
         const std::vector<uint32_t> &nbr = storage_space ? nbr_s : s->plan.nbr;
         const std::vector<uint32_t> &order = storage_space ? order_s : s->plan.order;
-        CREATE_TRY(cudaMalloc(&s->d_nbr, sizeof(uint32_t) * (size_t)N * 2 * z));
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_nbr, sizeof(uint32_t) * (size_t)N * 2 * z));
         CREATE_TRY(cudaMemcpy(s->d_nbr, nbr.data(), sizeof(uint32_t) * (size_t)N * 2 * z, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMalloc(&s->d_order, sizeof(uint32_t) * (size_t)N));
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_order, sizeof(uint32_t) * (size_t)N));
         CREATE_TRY(cudaMemcpy(s->d_order, order.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMalloc(&s->d_colour_start, sizeof(uint32_t) * (size_t)(m.n_colours + 1)));
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_colour_start, sizeof(uint32_t) * (size_t)(m.n_colours + 1)));
         CREATE_TRY(cudaMemcpy(s->d_colour_start, s->plan.colour_start.data(), sizeof(uint32_t) * (size_t)(m.n_colours + 1),
                               cudaMemcpyHostToDevice));
         if (storage_space) {
-            CREATE_TRY(cudaMalloc(&s->d_perm, sizeof(uint32_t) * (size_t)N));
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_perm, sizeof(uint32_t) * (size_t)N));
             CREATE_TRY(cudaMemcpy(s->d_perm, s->plan.perm.data(), sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice));
         }
         m.nbr = s->d_nbr;
@@ -662,20 +686,20 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     if (s->layout == PP_LAYOUT_MSC) {
         s->G = (m.D + 31) / 32;
         if (m.coupling_class == COUP_UNIT) {
-            CREATE_TRY(cudaMalloc(&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
             msc_pack_couplings_kernel<<<blocks_for(s->G * z * N, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_Jw, m.D, N, z, s->d_perm);
             CREATE_TRY(cudaStreamSynchronize(s->stream));
         }
-        if (s->d_Jf) { cudaFree(s->d_Jf); s->d_Jf = nullptr; }
-        CREATE_TRY(cudaMalloc(&s->d_words, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
+        if (s->d_Jf) { pool_free(s, s->d_Jf); s->d_Jf = nullptr; }
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_words, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
     } else {
         if (m.coupling_class == COUP_UNIT) {
-            CREATE_TRY(cudaMalloc(&s->d_J8, (size_t)n_coup));
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_J8, (size_t)n_coup));
             couplings_to_int8_kernel<<<blocks_for(n_coup, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_J8, n_coup);
             CREATE_TRY(cudaStreamSynchronize(s->stream));
         }
-        if (m.coupling_class != COUP_F32 && s->d_Jf) { cudaFree(s->d_Jf); s->d_Jf = nullptr; }
-        CREATE_TRY(cudaMalloc(&s->d_spins, (size_t)(m.D * m.S * N)));
+        if (m.coupling_class != COUP_F32 && s->d_Jf) { pool_free(s, s->d_Jf); s->d_Jf = nullptr; }
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_spins, (size_t)(m.D * m.S * N)));
     }
     m.J8 = s->d_J8;
     m.Jf = s->d_Jf;
@@ -684,11 +708,11 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     m.words = s->d_words;
 
     const int64_t DS = m.D * m.S;
-    CREATE_TRY(cudaMalloc(&s->d_sid, sizeof(int32_t) * (size_t)DS));
-    CREATE_TRY(cudaMalloc(&s->d_energies, sizeof(float) * (size_t)DS));
-    CREATE_TRY(cudaMalloc(&s->d_mags, sizeof(long long) * (size_t)DS));
+    CREATE_TRY(pool_alloc(s, (void **)&s->d_sid, sizeof(int32_t) * (size_t)DS));
+    CREATE_TRY(pool_alloc(s, (void **)&s->d_energies, sizeof(float) * (size_t)DS));
+    CREATE_TRY(pool_alloc(s, (void **)&s->d_mags, sizeof(long long) * (size_t)DS));
     CREATE_TRY(cudaMemset(s->d_mags, 0, sizeof(long long) * (size_t)DS));
-    CREATE_TRY(cudaMalloc(&s->d_temps, sizeof(float) * (size_t)m.T));
+    CREATE_TRY(pool_alloc(s, (void **)&s->d_temps, sizeof(float) * (size_t)m.T));
     CREATE_TRY(cudaMemcpy(s->d_temps, s->temps.data(), sizeof(float) * (size_t)m.T, cudaMemcpyHostToDevice));
     m.system_ids = s->d_sid;
     m.energies = s->d_energies;
@@ -701,7 +725,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         for (int mode = 0; mode < 2; mode++) {
             pp_metropolis_lookup(s->temps.data(), m.T, z, mode, lut.data());
             uint32_t *&dst = mode == 0 ? s->d_lut_metro : s->d_lut_gibbs;
-            CREATE_TRY(cudaMalloc(&dst, sizeof(uint32_t) * lut.size()));
+            CREATE_TRY(pool_alloc(s, (void **)&dst, sizeof(uint32_t) * lut.size()));
             CREATE_TRY(cudaMemcpy(dst, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice));
         }
     }
@@ -722,14 +746,14 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             const bool cap_ok = 3 * sites_em < (1 << MSC3D_KE) - 8 && sites_em < (1 << MSC3D_KM) - 8 &&
                                 3 * sites_pair < (1 << MSC3D_KE) - 8;
             if (cap_ok && smem_words(nh) * 4 <= 227 * 1024 - 1024) {
-                CREATE_TRY(cudaMalloc(&s->d_items, sizeof(uint16_t) * s->m3.items.size()));
+                CREATE_TRY(pool_alloc(s, (void **)&s->d_items, sizeof(uint16_t) * s->m3.items.size()));
                 CREATE_TRY(cudaMemcpy(s->d_items, s->m3.items.data(), sizeof(uint16_t) * s->m3.items.size(), cudaMemcpyHostToDevice));
                 s->gv.items = s->d_items;
                 s->gv.n_items = s->m3.n_items;
                 s->gv.N = (uint32_t)N;
                 s->gv.N2 = (uint32_t)(N / 2);
                 s->msc3d = true;
-                CREATE_TRY(cudaMalloc(&s->d_words_alt, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
+                CREATE_TRY(pool_alloc(s, (void **)&s->d_words_alt, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
                 s->msc3d_nh = nh;
                 s->msc3d_smem = smem_words(nh) * 4;
                 // Metropolis fast path: counts for unsat >= 3 (energy_change >= 0) are 2^24 (sweep.rs:141-145) and the
@@ -748,12 +772,12 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
 
     // PT state (realization.rs:21-67)
     const int n_edges = m.T - 1;
-    CREATE_TRY(cudaMalloc(&s->pt.edge_attempts, sizeof(uint64_t) * (size_t)(m.D * std::max(n_edges, 1))));
-    CREATE_TRY(cudaMalloc(&s->pt.edge_acceptances, sizeof(uint64_t) * (size_t)(m.D * std::max(n_edges, 1))));
-    CREATE_TRY(cudaMalloc(&s->pt.round_trips, sizeof(uint64_t) * (size_t)DS));
-    CREATE_TRY(cudaMalloc(&s->pt.trip_state, (size_t)DS));
+    CREATE_TRY(pool_alloc(s, (void **)&s->pt.edge_attempts, sizeof(uint64_t) * (size_t)(m.D * std::max(n_edges, 1))));
+    CREATE_TRY(pool_alloc(s, (void **)&s->pt.edge_acceptances, sizeof(uint64_t) * (size_t)(m.D * std::max(n_edges, 1))));
+    CREATE_TRY(pool_alloc(s, (void **)&s->pt.round_trips, sizeof(uint64_t) * (size_t)DS));
+    CREATE_TRY(pool_alloc(s, (void **)&s->pt.trip_state, (size_t)DS));
     if (s->layout == PP_LAYOUT_MSC)
-        CREATE_TRY(cudaMalloc(&s->pt.swap_mask, sizeof(uint32_t) * (size_t)(s->G * m.R * std::max(n_edges, 1))));
+        CREATE_TRY(pool_alloc(s, (void **)&s->pt.swap_mask, sizeof(uint32_t) * (size_t)(s->G * m.R * std::max(n_edges, 1))));
     s->pt.cold_slot = s->pt.hot_slot = 0;  // realization.rs:92-107
     for (int slot = 1; slot < m.T; slot++) {
         if (s->temps[slot] < s->temps[s->pt.cold_slot]) s->pt.cold_slot = slot;
@@ -761,10 +785,10 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     }
 
     // stats
-    CREATE_TRY(cudaMalloc(&s->st.sums, sizeof(double) * (size_t)(m.D * 11 * m.T)));
+    CREATE_TRY(pool_alloc(s, (void **)&s->st.sums, sizeof(double) * (size_t)(m.D * 11 * m.T)));
     if (m.P > 0) {
-        CREATE_TRY(cudaMalloc(&s->d_dot_spin, sizeof(long long) * (size_t)(m.D * m.P * m.T)));
-        CREATE_TRY(cudaMalloc(&s->d_dot_link, sizeof(long long) * (size_t)(m.D * m.P * m.T)));
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_dot_spin, sizeof(long long) * (size_t)(m.D * m.P * m.T)));
+        CREATE_TRY(pool_alloc(s, (void **)&s->d_dot_link, sizeof(long long) * (size_t)(m.D * m.P * m.T)));
         s->st.dot_spin = s->d_dot_spin;
         s->st.dot_link = s->d_dot_link;
     }
@@ -832,9 +856,9 @@ static pp_status ensure_streams(pp_sim *s, int n) {
 static pp_status ensure_hist(pp_sim *s) {
     if (s->hist_allocated || s->mv.P == 0) return PP_OK;
     const size_t n = (size_t)s->mv.D * s->mv.T * (s->mv.N + 1);
-    CUDA_TRY(cudaMalloc(&s->st.hist, sizeof(uint32_t) * n));
-    CUDA_TRY(cudaMalloc(&s->st.ql_at_q, sizeof(double) * n));
-    CUDA_TRY(cudaMalloc(&s->st.ql2_at_q, sizeof(double) * n));
+    CUDA_TRY(pool_alloc(s, (void **)&s->st.hist, sizeof(uint32_t) * n));
+    CUDA_TRY(pool_alloc(s, (void **)&s->st.ql_at_q, sizeof(double) * n));
+    CUDA_TRY(pool_alloc(s, (void **)&s->st.ql2_at_q, sizeof(double) * n));
     s->hist_allocated = true;
     return PP_OK;
 }
@@ -1028,15 +1052,15 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             } else {
                 unsigned long long *d_h = nullptr;
                 double *d_a = nullptr, *d_b = nullptr;
-                CUDA_TRY(cudaMalloc(&d_h, sizeof(uint64_t) * (size_t)per));
-                CUDA_TRY(cudaMalloc(&d_a, sizeof(double) * (size_t)per));
-                CUDA_TRY(cudaMalloc(&d_b, sizeof(double) * (size_t)per));
+                CUDA_TRY(pool_alloc(s, (void **)&d_h, sizeof(uint64_t) * (size_t)per));
+                CUDA_TRY(pool_alloc(s, (void **)&d_a, sizeof(double) * (size_t)per));
+                CUDA_TRY(pool_alloc(s, (void **)&d_b, sizeof(double) * (size_t)per));
                 reduce_hist_kernel<<<blocks_for(per, 256), 256, 0, s->stream>>>(m, s->st, d_h, d_a, d_b);
                 CUDA_TRY(cudaStreamSynchronize(s->stream));
                 if (out->overlap_histogram) CUDA_TRY(cudaMemcpy(out->overlap_histogram, d_h, sizeof(uint64_t) * (size_t)per, cudaMemcpyDeviceToHost));
                 if (out->ql_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql_at_q_sum, d_a, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
                 if (out->ql2_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql2_at_q_sum, d_b, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
-                cudaFree(d_h); cudaFree(d_a); cudaFree(d_b);
+                pool_free(s, d_h); pool_free(s, d_a); pool_free(s, d_b);
             }
         }
         const size_t all = (size_t)m.D * per;
@@ -1045,14 +1069,14 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             else {
                 const int64_t chunk = std::min<int64_t>((int64_t)all, int64_t(1) << 26);
                 unsigned long long *d_w = nullptr;
-                CUDA_TRY(cudaMalloc(&d_w, sizeof(uint64_t) * (size_t)chunk));
+                CUDA_TRY(pool_alloc(s, (void **)&d_w, sizeof(uint64_t) * (size_t)chunk));
                 for (int64_t off = 0; off < (int64_t)all; off += chunk) {
                     const int64_t n = std::min<int64_t>(chunk, (int64_t)all - off);
                     widen_u32_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->st.hist + off, d_w, n);
                     CUDA_TRY(cudaStreamSynchronize(s->stream));
                     CUDA_TRY(cudaMemcpy(out->per_sample_overlap_histogram + off, d_w, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
                 }
-                cudaFree(d_w);
+                pool_free(s, d_w);
             }
         }
         if (out->per_sample_ql_at_q_sum) {
@@ -1085,11 +1109,11 @@ extern "C" pp_status pp_get_spins(pp_sim *s, int64_t r, int8_t *out) {
     const size_t n = (size_t)m.S * m.N;
     if (s->layout == PP_LAYOUT_MSC) {
         int8_t *tmp = nullptr;
-        CUDA_TRY(cudaMalloc(&tmp, n));
+        CUDA_TRY(pool_alloc(s, (void **)&tmp, n));
         msc_unpack_kernel<<<blocks_for((int64_t)n, 256), 256, 0, s->stream>>>(m, r, tmp);
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         CUDA_TRY(cudaMemcpy(out, tmp, n, cudaMemcpyDeviceToHost));
-        cudaFree(tmp);
+        pool_free(s, tmp);
     } else {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         CUDA_TRY(cudaMemcpy(out, m.spins + (size_t)r * n, n, cudaMemcpyDeviceToHost));
@@ -1106,11 +1130,11 @@ extern "C" pp_status pp_set_spins(pp_sim *s, int64_t r, const int8_t *spins) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->layout == PP_LAYOUT_MSC) {
         int8_t *tmp = nullptr;
-        CUDA_TRY(cudaMalloc(&tmp, n));
+        CUDA_TRY(pool_alloc(s, (void **)&tmp, n));
         CUDA_TRY(cudaMemcpy(tmp, spins, n, cudaMemcpyHostToDevice));
         msc_pack_kernel<<<blocks_for((int64_t)n, 256), 256, 0, s->stream>>>(m, r, tmp);
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        cudaFree(tmp);
+        pool_free(s, tmp);
     } else {
         CUDA_TRY(cudaMemcpy(m.spins + (size_t)r * n, spins, n, cudaMemcpyHostToDevice));
     }

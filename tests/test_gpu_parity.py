@@ -188,6 +188,35 @@ def test_msc3d_chunked_multistream_execution_is_bit_exact(oracle, monkeypatch, s
     assert seen == list(range(37)) + list(range(21)) + list(range(9))
 
 
+def test_shards_with_sample_offset_equal_the_unsharded_run(oracle):
+    """Multi-GPU sharding = handles over blocks of realizations with their global sample_offset (one per GPU in
+    production; here both on cuda:0).  Merged through peapods_b200.sharded it must equal the single handle."""
+    import peapods_b200 as pb
+    from peapods_b200.sharded import merge_results, shard_bounds
+
+    shape, temps, R, D = (4, 4, 8), np.linspace(0.8, 1.6, 4).astype(np.float32), 2, 96
+    J = couplings("bimodal", shape, 3, D, 3)
+    whole = pb.IsingSimulation(list(shape), J, temps, R, None, 99, layout="msc")
+    kw = dict(pt_interval=1, pt_schedule="single_random_edge")
+    ref = whole.sample(25, "metropolis", **kw)
+    parts = []
+    for rank in range(2):
+        first, count = shard_bounds(D, 2, rank)
+        sim = pb.IsingSimulation(list(shape), J[first:first + count], temps, R, None, 99, layout="msc", sample_offset=first)
+        res = sim.sample(25, "metropolis", **kw)
+        parts.append({"result": res, "per_sample_means": sim.last_per_sample_means, "n_replicas": R})
+        for d in range(count):
+            assert np.array_equal(sim.get_spins(d), whole.get_spins(first + d))
+    merged = merge_results(parts)
+    for k in ("mags", "mags2", "mags4", "energies", "energies2", "overlap", "overlap2", "overlap4", "link_overlap2"):
+        assert np.array_equal(merged[k], ref[k]), k
+    assert np.array_equal(np.stack(merged["overlap_histogram"]), np.stack(ref["overlap_histogram"]))
+    assert np.array_equal(merged["per_sample_overlap_histogram"], ref["per_sample_overlap_histogram"])
+    np.testing.assert_allclose(merged["ql_at_q_sum"], ref["ql_at_q_sum"], rtol=1e-12)
+    for k, v in ref["per_disorder"]["parallel_tempering"].items():
+        assert np.array_equal(merged["per_disorder"]["parallel_tempering"][k], v), k
+
+
 def test_msc3d_operator_entry_points_match_oracle(oracle):
     shape, temps, R, DD = (4, 4, 8), [0.9, 1.2, 1.5], 4, 37
     gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, DD, layout="msc")

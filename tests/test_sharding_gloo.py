@@ -1,0 +1,84 @@
+"""N > 1 host logic on CPU: two gloo ranks each run their block of realizations (the oracle stands in for the GPU
+engine here -- no CUDA in this container), gather_merge() on rank 0 must rebuild the unsharded run."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+SHAPE, TEMPS, R, D = (4, 4, 4), np.linspace(0.8, 1.6, 4).astype(np.float32), 2, 96
+
+
+def _couplings():
+    rng = np.random.default_rng(5)
+    return (2 * rng.integers(0, 2, size=(D,) + SHAPE + (3,)) - 1).astype(np.float32)
+
+
+def _run_block(first, count):
+    import oracle
+    import peapods_b200  # noqa: F401  (the package must import without a GPU)
+    from peapods_b200 import colouring
+
+    colour, _ = colouring(SHAPE)
+    sim = oracle.Sim(SHAPE, _couplings()[first:first + count], TEMPS, n_replicas=R, seed=77, rng_mode=oracle.RNG_PHILOX_MSC,
+                     colour=colour, sample_offset=first)
+    res = sim.sample(30, "metropolis", pt_interval=1, pt_schedule="full_ladder")
+    res["overlap_histogram"] = [h for h in res["overlap_histogram"]]
+    return res, sim.last_per_sample_means
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from peapods_b200.sharded import gather_merge, shard_bounds
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, count = shard_bounds(D, world, rank)
+    res, means = _run_block(first, count)
+    merged = gather_merge(res, means, R)
+    if rank == 0:
+        np.savez(out_path, **{k: np.asarray(v) for k, v in merged.items() if k != "per_disorder"},
+                 **{"pt_" + k: v for k, v in merged["per_disorder"]["parallel_tempering"].items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything_in_groups_of_32():
+    sys.path.insert(0, str(ROOT))
+    from peapods_b200.sharded import shard_bounds
+
+    for n, world in ((4096, 8), (96, 2), (100, 3), (33, 4), (32, 2)):
+        blocks = [shard_bounds(n, world, r) for r in range(world)]
+        assert sum(c for _, c in blocks) == n
+        pos = 0
+        for first, count in blocks:
+            assert first == pos or count == 0
+            assert first % 32 == 0 or count == 0
+            pos += count
+
+
+def test_two_gloo_ranks_reproduce_the_unsharded_run(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out_path = str(tmp_path / "merged.npz")
+    mp.spawn(_worker, args=(2, port, out_path), nprocs=2, join=True)
+    merged = np.load(out_path)
+    sys.path.insert(0, str(ROOT))
+    ref, _ = _run_block(0, D)
+    for k in ("mags", "mags2", "mags4", "energies", "energies2", "overlap", "overlap2", "overlap4", "link_overlap",
+              "link_overlap2", "link_overlap4"):
+        assert np.array_equal(merged[k], ref[k]), k            # ordered sum over realizations: bit for bit
+    assert np.array_equal(merged["overlap_histogram"], np.stack(ref["overlap_histogram"]))
+    for k in ("ql_at_q_sum", "ql2_at_q_sum"):
+        np.testing.assert_allclose(merged[k], ref[k], rtol=1e-12, atol=0)   # partial sums re-associated
+    for k in ("per_sample_overlap_histogram", "per_sample_ql_at_q_sum"):
+        assert np.array_equal(merged[k], ref[k]), k
+    for k, v in ref["per_disorder"]["parallel_tempering"].items():
+        assert np.array_equal(merged["pt_" + k], v), k
