@@ -186,6 +186,7 @@ struct pp_sim {
     int64_t chunk_bytes = int64_t(24) << 20;
     int64_t macro_batch = 16;
     int64_t chunk_groups = 0;                          // > 0: word groups per chunk (overrides chunk_bytes; tests)
+    bool defer_swaps = true;                           // gather PT lane swaps in the next sweep's stage-in
     std::vector<cudaStream_t> xstreams;
     std::vector<cudaEvent_t> xevents;
     // measurement hook: event pairs around sweep-kernel launches
@@ -516,7 +517,7 @@ static pp_status launch_pt(pp_sim *s, Ctx &c, int schedule, uint32_t pt_event, i
         c.swap_pending = true;
         c.pend_schedule = schedule;
         c.pend_parity = first_parity;
-        if (!(defer && s->msc3d)) {
+        if (!(defer && s->msc3d && s->defer_swaps)) {
             st = flush_swaps(s, c);
             if (st != PP_OK) return st;
         }
@@ -583,6 +584,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     if (const char *e = getenv("PP_CHUNK_MIB")) s->chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("PP_MACRO_BATCH")) s->macro_batch = std::max(1, atoi(e));
     if (const char *e = getenv("PP_CHUNK_GROUPS")) s->chunk_groups = std::max(0, atoi(e));
+    if (const char *e = getenv("PP_DEFER_SWAPS")) s->defer_swaps = atoi(e) != 0;
     s->temps.assign(desc->temperatures, desc->temperatures + desc->n_temps);
     ModelView &m = s->mv;
     m.N = s->plan.n_spins;
@@ -734,18 +736,22 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     if (s->layout == PP_LAYOUT_MSC && z == 3 && (m.R == 1 || m.R == 2 || m.R == 4)) {
         s->m3 = msc3d_plan(s->plan);
         if (s->m3.ok) {
-            // two temperature slots per CTA when they fit next to the coupling words, else one
+            // NH = 1: one temperature slot per CTA, preferred when two such CTAs fit one SM (they run out of phase, so one
+            // stages data while the other computes); NH = 2: two slots per CTA sharing the coupling words
             auto smem_words = [&](int nh) {
-                return (size_t)(m.coupling_class == COUP_UNIT ? 3 * N : 0) + 4 * (size_t)s->m3.n_items + (size_t)nh * m.R * N + 8 +
-                       (size_t)nh * 512;
+                const size_t jw = m.coupling_class == COUP_UNIT ? 3 * (size_t)N : 0;
+                return nh == 2 ? jw + 4 * (size_t)s->m3.n_items + 2 * (size_t)m.R * N + 8 + 2 * 512 : jw + (size_t)m.R * N + 8;
             };
-            int nh = 2;
-            if (smem_words(nh) * 4 > 227 * 1024 - 1024) nh = 1;
+            const size_t sm_total = 227 * 1024, cta_reserved = 1024;
+            int nh = 1;
+            if (2 * (smem_words(1) * 4 + cta_reserved) > sm_total && smem_words(2) * 4 + cta_reserved <= sm_total) nh = 2;
+            if ((size_t)m.R * N < 1024) nh = 2;  // NH = 1 parks its 2 KB reduction scratch in the spin buffer
+            if (const char *e = getenv("PP_MSC3D_NH")) nh = atoi(e) == 2 ? 2 : 1;
             // per-thread counter capacity of the epilogue (MSC3D_KE / MSC3D_KM planes)
             const int64_t sites_em = N / (32 * (4 / m.R)), sites_pair = m.P > 0 ? N / (32 * (4 / m.P)) : 0;
             const bool cap_ok = 3 * sites_em < (1 << MSC3D_KE) - 8 && sites_em < (1 << MSC3D_KM) - 8 &&
                                 3 * sites_pair < (1 << MSC3D_KE) - 8;
-            if (cap_ok && smem_words(nh) * 4 <= 227 * 1024 - 1024) {
+            if (cap_ok && smem_words(nh) * 4 + cta_reserved <= sm_total && (nh == 2 || (size_t)m.R * N >= 1024)) {
                 CREATE_TRY(pool_alloc(s, (void **)&s->d_items, sizeof(uint16_t) * s->m3.items.size()));
                 CREATE_TRY(cudaMemcpy(s->d_items, s->m3.items.data(), sizeof(uint16_t) * s->m3.items.size(), cudaMemcpyHostToDevice));
                 s->gv.items = s->d_items;

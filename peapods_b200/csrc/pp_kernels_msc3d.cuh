@@ -364,7 +364,7 @@ __device__ __forceinline__ void msc3d_pair_item(const uint32_t *A, const uint32_
 // otherwise run independently (named barriers), so one half can stage data while the other computes.
 // dynamic smem (words): [3N coupling words | 4*n_items item table | NH*RPC*N spins | 8 (mbarriers) | NH*512 scratch]
 template <int RPC, bool METRO, int NH>
-__global__ void __launch_bounds__(MSC3D_NTH *NH, 1)
+__global__ void __launch_bounds__(MSC3D_NTH *NH, NH == 1 ? 2 : 1)
 msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags,
              int want_overlap, int want_fold, int64_t group_offset, long long *dot_spin, long long *dot_link,
              uint32_t *words_out, const uint32_t *swap_mask, int pt_schedule, int pt_parity) {
@@ -372,10 +372,15 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     const uint32_t N = gv.N, N2 = gv.N2;
     const bool has_J = m.Jw != nullptr;
     uint32_t *Jsm = smem;
-    uint4 *items = reinterpret_cast<uint4 *>(smem + (has_J ? 3 * N : 0));
-    uint32_t *sp_all = reinterpret_cast<uint32_t *>(items + gv.n_items);
+    // NH == 2: the item table is staged in shared memory and the reduction scratch has its own space.
+    // NH == 1: two CTAs share an SM (the spins and coupling words of one CTA are half of its shared memory to the
+    // byte), so the item table is read through L1/L2 with a one-item register prefetch and the reduction scratch
+    // reuses the spin buffer once the epilogue has consumed it.
+    uint4 *items_sm = reinterpret_cast<uint4 *>(smem + (has_J ? 3 * N : 0));
+    uint32_t *sp_all = NH == 2 ? reinterpret_cast<uint32_t *>(items_sm + gv.n_items) : smem + (has_J ? 3 * N : 0);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp_all + (size_t)NH * RPC * N);
     uint32_t *red_all = reinterpret_cast<uint32_t *>(bars + 4);
+    auto item_at = [&](int it) { return NH == 2 ? items_sm[it] : __ldg(gv.items + it); };
     const int tid = threadIdx.x;
     const int half = NH == 1 ? 0 : tid / MSC3D_NTH, ht = tid - half * MSC3D_NTH;
     const int TP = (m.T + NH - 1) / NH;
@@ -383,7 +388,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     const int t = (int)(blockIdx.x % TP) * NH + half;
     const uint32_t bytes = N * 4u;
     uint32_t *sp = sp_all + (size_t)half * RPC * N;
-    uint32_t *red = red_all + half * 512;
+    uint32_t *red = NH == 2 ? red_all + half * 512 : sp;
     const uint32_t *J = has_J ? Jsm : nullptr;
 
     // ---- stage in: bulk-async copies, completion on mbarriers (bars[0]: couplings + item table, bars[1+h]: spins)
@@ -394,9 +399,9 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bars[0], (has_J ? 3u * bytes : 0u) + (uint32_t)gv.n_items * 16u);
+        mbar_expect_tx(&bars[0], (has_J ? 3u * bytes : 0u) + (NH == 2 ? (uint32_t)gv.n_items * 16u : 0u));
         if (has_J) bulk_g2s(Jsm, m.Jw + g * 3 * (int64_t)N, 3u * bytes, &bars[0]);
-        bulk_g2s(items, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
+        if (NH == 2) bulk_g2s(items_sm, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
     }
     if (t >= m.T) return;  // odd T: the last CTA of a group has an idle half
     // Spin words: m.words is the input buffer, words_out the output buffer (ping-pong, so that a CTA may still read its
@@ -498,9 +503,11 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         for (int c = 0; c < 2; c++) {
             const uint32_t so = c * N2, oo = (1 - c) * N2;  // word offsets of the updated / the other colour half
             const uint32_t tag = TAG_SWEEP_MSC | (uint32_t)c;
+            uint4 next = ht < gv.n_items ? item_at(ht) : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
             for (int it = ht; it < gv.n_items; it += MSC3D_NTH) {
-                const uint4 desc = items[it];
+                const uint4 desc = next;
+                if (it + MSC3D_NTH < gv.n_items) next = item_at(it + MSC3D_NTH);
                 if (((desc.w >> 16) ^ (uint32_t)c) & 1u)
                     msc3d_sweep_item<RPC, METRO, true>(sp, J, N, so, oo, desc, thr, sweep_index + (uint32_t)sw, (uint32_t)t,
                                                        (uint32_t)m.T, tag, k0, k1);
@@ -535,6 +542,8 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         const int w = ht >> 5, lane = ht & 31;
         // red layout: [replica r][E, M][WPE][32] then [pair p][q, ql][WPP][32]
         uint32_t *red_p = red + RPC * 2 * WPE * 32;
+        uint32_t tot0 = 0, tot1 = 0;  // this warp's two lane totals: (E, M) or (q, ql)
+        uint32_t *slot0 = nullptr, *slot1 = nullptr;
         if (w < 4) {
             if (want_energy || want_mags) {
                 const int r = w / WPE, sub = w % WPE;
@@ -544,12 +553,12 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                 ve.clear(); vm.clear();
 #pragma unroll 1
                 for (int it = lane + 32 * sub; it < gv.n_items; it += 32 * WPE) {
-                    const uint4 desc = items[it];
+                    const uint4 desc = item_at(it);
                     if ((desc.w >> 16) & 1u) msc3d_em_item<true>(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
                     else msc3d_em_item<false>(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
                 }
-                if (want_energy) red[((r * 2 + 0) * WPE + sub) * 32 + lane] = warp_lane_total(ve);
-                if (want_mags) red[((r * 2 + 1) * WPE + sub) * 32 + lane] = warp_lane_total(vm);
+                if (want_energy) { tot0 = warp_lane_total(ve); slot0 = red + ((r * 2 + 0) * WPE + sub) * 32 + lane; }
+                if (want_mags) { tot1 = warp_lane_total(vm); slot1 = red + ((r * 2 + 1) * WPE + sub) * 32 + lane; }
             }
         } else if (NP > 0 && want_overlap) {
             const int pw = w - 4, p = pw / WPP, sub = pw % WPP;
@@ -560,14 +569,20 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                 vl.clear(); vq.clear();
 #pragma unroll 1
                 for (int it = lane + 32 * sub; it < gv.n_items; it += 32 * WPP) {
-                    const uint4 desc = items[it];
+                    const uint4 desc = item_at(it);
                     if ((desc.w >> 16) & 1u) msc3d_pair_item<true>(A, B, N2, desc, vl, vq);
                     else msc3d_pair_item<false>(A, B, N2, desc, vl, vq);
                 }
-                red_p[((p * 2 + 0) * WPP + sub) * 32 + lane] = warp_lane_total(vq);
-                red_p[((p * 2 + 1) * WPP + sub) * 32 + lane] = warp_lane_total(vl);
+                tot0 = warp_lane_total(vq); slot0 = red_p + ((p * 2 + 0) * WPP + sub) * 32 + lane;
+                tot1 = warp_lane_total(vl); slot1 = red_p + ((p * 2 + 1) * WPP + sub) * 32 + lane;
             }
         }
+        if (NH == 1) {  // the scratch aliases the spin buffer: every warp must be done reading it, and so must the bulk store
+            if (n_sweeps > 0 && ht == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            half_barrier(half, MSC3D_NTH);
+        }
+        if (slot0) *slot0 = tot0;
+        if (slot1) *slot1 = tot1;
         half_barrier(half, MSC3D_NTH);
         // warp 0 of the half: lane l finishes realization 32g + l at slot t -- per-system energy / magnetisation, pair
         // dots, and (want_fold) the recorded-sweep fold of simulation/mod.rs:543-578 + statistics/overlap.rs:283-306

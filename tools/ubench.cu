@@ -1,0 +1,113 @@
+// ubench.cu — issue-rate microbenchmarks for the integer pipes of one B200 SM sub-partition (SMSP).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench tools/ubench.cu ; run on a B200.
+// Prints warp-instructions per cycle per SMSP for independent-chain loops of each instruction class, which is
+// what bounds the multispin sweep kernel (LOP3-heavy with Philox IMAD.WIDEs).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int CH = 12;     // independent chains per thread
+constexpr int IT = 4096;  // loop iterations
+
+enum { K_LOP3, K_IMADW, K_IMAD, K_IADD3, K_SHF, K_SETSEL, K_MIX_LOP_IMADW_2_1, K_MIX_LOP_IMAD_1_1, K_MIX_LOP_IMADW_1_1, K_LDS128, K_PRMT, K_MIX_LOP_IMADW_4_1, K_IMADHI, K_N };
+const char *NAMES[] = {"lop3", "imad.wide.u32", "imad.lo", "iadd3", "shf", "isetp+sel", "lop3:imad.wide 2:1", "lop3:imad 1:1", "lop3:imad.wide 1:1", "lds.128", "prmt", "lop3:imad.wide 4:1", "imad.hi.s32"};
+
+template <int KIND>
+__global__ void __launch_bounds__(1024, 1) bench(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
+    __shared__ uint4 sm[1024];
+    uint32_t x[CH];
+    unsigned long long w[CH];
+    const uint32_t a = seed | 1u, b = seed * 3u + 7u;
+#pragma unroll
+    for (int c = 0; c < CH; c++) { x[c] = seed + c * 977u + threadIdx.x; w[c] = x[c]; }
+    sm[threadIdx.x] = make_uint4(x[0], x[1], x[2], x[3]);
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < IT; i++) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            if (KIND == K_LOP3) asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            if (KIND == K_IMADW) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+            if (KIND == K_IMAD) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
+            if (KIND == K_IMADHI) asm("mul.hi.s32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
+            if (KIND == K_IADD3) asm("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
+            if (KIND == K_SHF) asm("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[c]) : "r"(a));
+            if (KIND == K_PRMT) asm("prmt.b32 %0, %0, %1, 0x2103;" : "+r"(x[c]) : "r"(a));
+            if (KIND == K_SETSEL) asm("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(x[c]) : "r"(a), "r"(b));
+            if (KIND == K_MIX_LOP_IMADW_2_1) {
+                if (c % 3 == 2) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_IMADW_4_1) {
+                if (c % 5 == 4) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_IMADW_1_1) {
+                if (c % 2) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_IMAD_1_1) {
+                if (c % 2) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_LDS128) {
+                uint4 v = sm[(x[c] + c * 33) & 1023];
+                x[c] = v.x ^ v.w;  // one LOP3 per load keeps the address chain alive
+            }
+        }
+    }
+    const unsigned long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < CH; c++) acc ^= x[c] ^ (uint32_t)w[c] ^ (uint32_t)(w[c] >> 32);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int KIND>
+void run(uint32_t *out, unsigned long long *cyc, int threads) {
+    const int blocks = 148;
+    bench<KIND><<<blocks, threads>>>(out, 12345u, cyc);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    bench<KIND><<<blocks, threads>>>(out, 12345u, cyc);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    unsigned long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double mean = 0;
+    for (int i = 0; i < blocks; i++) mean += (double)h[i];
+    mean /= blocks;
+    const double warps_per_smsp = threads / 32.0 / 4.0;
+    const double inst = (double)IT * CH * warps_per_smsp;  // warp-instructions of the measured class per SMSP
+    printf("%-22s threads=%4d  %.3f warp-inst/cycle/SMSP  (%.0f cycles, %.3f ms)\n", NAMES[KIND], threads, inst / mean, mean, ms);
+}
+
+int main() {
+    uint32_t *out;
+    unsigned long long *cyc;
+    cudaMalloc(&out, 148 * 1024 * 4);
+    cudaMalloc(&cyc, 148 * 8);
+    for (int threads : {256, 512, 1024}) {
+        run<K_LOP3>(out, cyc, threads);
+        run<K_IMADW>(out, cyc, threads);
+        run<K_IMAD>(out, cyc, threads);
+        run<K_IMADHI>(out, cyc, threads);
+        run<K_IADD3>(out, cyc, threads);
+        run<K_SHF>(out, cyc, threads);
+        run<K_PRMT>(out, cyc, threads);
+        run<K_SETSEL>(out, cyc, threads);
+        run<K_MIX_LOP_IMADW_4_1>(out, cyc, threads);
+        run<K_MIX_LOP_IMADW_2_1>(out, cyc, threads);
+        run<K_MIX_LOP_IMADW_1_1>(out, cyc, threads);
+        run<K_MIX_LOP_IMAD_1_1>(out, cyc, threads);
+        run<K_LDS128>(out, cyc, threads);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("status: %s\n", cudaGetErrorString(e));
+    return e != cudaSuccess;
+}
