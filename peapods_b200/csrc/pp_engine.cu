@@ -182,10 +182,11 @@ struct pp_sim {
     bool hist_allocated = false;
     int64_t launches = 0;
     // chunked multi-stream execution of the msc3d path (see pp_sample)
-    int n_streams = 3;
-    int64_t chunk_bytes = int64_t(24) << 20;
+    int n_streams = 4;
+    int64_t chunk_bytes = int64_t(8) << 20;
     int64_t macro_batch = 16;
     int64_t chunk_groups = 0;                          // > 0: word groups per chunk (overrides chunk_bytes; tests)
+    int64_t max_batch = 64;                            // sweeps without reduction / PT fused into one launch (multispin)
     bool defer_swaps = true;                           // gather PT lane swaps in the next sweep's stage-in
     std::vector<cudaStream_t> xstreams;
     std::vector<cudaEvent_t> xevents;
@@ -512,8 +513,12 @@ static pp_status launch_pt(pp_sim *s, Ctx &c, int schedule, uint32_t pt_event, i
     if (s->layout == PP_LAYOUT_MSC) {
         pp_status st = flush_swaps(s, c);
         if (st != PP_OK) return st;
-        pt_exchange_msc_kernel<<<blocks_for(c.G * m.R * 32, 128), 128, 0, c.stream>>>(m, c.pt, schedule, first_parity, pt_event);
-        s->launches++;
+        static const int dbg = getenv("PP_DEBUG_PT") ? atoi(getenv("PP_DEBUG_PT")) : 0;  // timing experiments only
+        if (!(dbg == 1 && pt_event > 2)) {
+            pt_exchange_msc_kernel<<<blocks_for(c.G * m.R * 32, 128), 128, 0, c.stream>>>(m, c.pt, schedule, first_parity, pt_event);
+            s->launches++;
+        }
+        if (dbg == 2) return PP_OK;
         c.swap_pending = true;
         c.pend_schedule = schedule;
         c.pend_parity = first_parity;
@@ -584,6 +589,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     if (const char *e = getenv("PP_CHUNK_MIB")) s->chunk_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("PP_MACRO_BATCH")) s->macro_batch = std::max(1, atoi(e));
     if (const char *e = getenv("PP_CHUNK_GROUPS")) s->chunk_groups = std::max(0, atoi(e));
+    if (const char *e = getenv("PP_MAX_BATCH")) s->max_batch = std::max(1, atoi(e));
     if (const char *e = getenv("PP_DEFER_SWAPS")) s->defer_swaps = atoi(e) != 0;
     s->temps.assign(desc->temperatures, desc->temperatures + desc->n_temps);
     ModelView &m = s->mv;
@@ -691,6 +697,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             CREATE_TRY(pool_alloc(s, (void **)&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
             msc_pack_couplings_kernel<<<blocks_for(s->G * z * N, 256), 256, 0, s->stream>>>(s->d_Jf, s->d_Jw, m.D, N, z, s->d_perm);
             CREATE_TRY(cudaStreamSynchronize(s->stream));
+        } else {  // ferromagnet: all-zero sign words, so that the multispin kernels have one code path
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
+            CREATE_TRY(cudaMemsetAsync(s->d_Jw, 0, sizeof(uint32_t) * (size_t)(s->G * z * N), s->stream));
         }
         if (s->d_Jf) { pool_free(s, s->d_Jf); s->d_Jf = nullptr; }
         CREATE_TRY(pool_alloc(s, (void **)&s->d_words, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
@@ -739,7 +748,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             // NH = 1: one temperature slot per CTA, preferred when two such CTAs fit one SM (they run out of phase, so one
             // stages data while the other computes); NH = 2: two slots per CTA sharing the coupling words
             auto smem_words = [&](int nh) {
-                const size_t jw = m.coupling_class == COUP_UNIT ? 3 * (size_t)N : 0;
+                const size_t jw = 3 * (size_t)N;
                 return nh == 2 ? jw + 4 * (size_t)s->m3.n_items + 2 * (size_t)m.R * N + 8 + 2 * 512 : jw + (size_t)m.R * N + 8;
             };
             const size_t sm_total = 227 * 1024, cta_reserved = 1024;
@@ -758,6 +767,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 s->gv.n_items = s->m3.n_items;
                 s->gv.N = (uint32_t)N;
                 s->gv.N2 = (uint32_t)(N / 2);
+                s->gv.one[0] = s->gv.one[1] = s->gv.one[2] = 1u;
                 s->msc3d = true;
                 CREATE_TRY(pool_alloc(s, (void **)&s->d_words_alt, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
                 s->msc3d_nh = nh;
@@ -952,7 +962,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     const int64_t last = sid + batch - 1;
                     const bool rec = last >= cfg->warmup_sweeps;
                     const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
-                    if (rec || ptl || batch >= 64) break;
+                    if (rec || ptl || batch >= s->max_batch) break;
                     batch++;
                 }
             }

@@ -23,6 +23,9 @@
 // and replica, RNG-SPEC TAG_SWEEP_MSC) selects which of them is the flip mask:
 //   flip lane l  <=>  draw < table[t][2*unsat_l]   (sweep.rs:182-184 with ec + 2z' = 2*unsat).
 #pragma once
+#ifndef PP_M3_VARIANT
+#define PP_M3_VARIANT 2
+#endif
 #include <string>
 #include <vector>
 
@@ -81,6 +84,8 @@ struct Msc3dView {
     const uint4 *items;  // [n_items] packed 8 x u16
     int n_items;
     uint32_t N, N2;
+    uint32_t one[3];     // the constant 1, three times, opaque to the compiler (multipliers of the IMAD.WIDE compares, see lt_mask;
+                         // distinct operands keep ptxas from sharing one product and doing the 64-bit adds on the ALU pipe)
 };
 
 #if defined(__CUDACC__)
@@ -207,6 +212,14 @@ __device__ __forceinline__ void unpack_item(const uint4 d, uint32_t &self, uint3
     eR = d.w & 0xFFFFu;   par = d.w >> 16;
 }
 
+// Word-wide comparison on the FMA pipe: all-ones if raw < thr else 0, as the high half of raw * 1 + (2^64 - thr)
+// (one IMAD.WIDE.U32; the ALU pipe, which the bit-sliced logic saturates, is not touched).  `one` must be 1.
+__device__ __forceinline__ uint32_t lt_mask(const uint32_t raw, const uint32_t one, const uint64_t neg_thr) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(raw), "r"(one), "l"(neg_thr));
+    return (uint32_t)(r >> 32);
+}
+
 __device__ __forceinline__ uint4 lds4(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 __device__ __forceinline__ void to_arr(const uint4 v, uint32_t *a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
@@ -215,29 +228,26 @@ constexpr int MSC3D_KM = 9;   // planes of the per-thread down-spin / q counters
 constexpr int MSC3D_NTH = 256;  // threads per half
 
 // One quad (four same-colour sites of one row segment) of all RPC replicas.  P = the quad's sites sit at x2 = 2j + P.
-//   sp: the half's [RPC][N] words; J: [3][N] coupling sign words in shared memory or nullptr (all +1)
+//   sp: the half's [RPC][N] words; J: [3][N] coupling sign words in shared memory (all-zero words for a ferromagnet)
 template <int RPC, bool METRO, bool P>
 __device__ __forceinline__ void msc3d_sweep_item(uint32_t *sp, const uint32_t *J, const uint32_t N, const uint32_t so,
                                                  const uint32_t oo, const uint4 desc, const uint32_t (&thr)[7],
-                                                 const uint32_t sweep, const uint32_t pos0, const uint32_t pos_stride,
+                                                 const uint64_t (&nthr)[3], const uint32_t (&one)[3], const uint32_t sweep, const uint32_t pos0, const uint32_t pos_stride,
                                                  const uint32_t tag, const uint32_t k0, const uint32_t k1) {
     uint32_t self, zp, zm, yp, ym, eL, eR, par;
     unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
     (void)par;
     // coupling sign words (bit = 1: J = -1); bond (i, d) is stored at its lower site i
     uint32_t Jf0[4], Jf1[4], Jf2[4], Jb0[4], Jb1[4], Jb2[4];
-    if (J) {
-        to_arr(lds4(J + 0 * N + so + self), Jf0);
-        to_arr(lds4(J + 1 * N + so + self), Jf1);
-        to_arr(lds4(J + 2 * N + so + self), Jf2);
-        to_arr(lds4(J + 0 * N + oo + zm), Jb0);
-        to_arr(lds4(J + 1 * N + oo + ym), Jb1);
+    to_arr(lds4(J + 0 * N + so + self), Jf0);
+    to_arr(lds4(J + 1 * N + so + self), Jf1);
+    to_arr(lds4(J + 2 * N + so + self), Jf2);
+    to_arr(lds4(J + 0 * N + oo + zm), Jb0);
+    to_arr(lds4(J + 1 * N + oo + ym), Jb1);
+    {
         const uint4 v = lds4(J + 2 * N + oo + self);
         if (P) { Jb2[0] = v.x; Jb2[1] = v.y; Jb2[2] = v.z; Jb2[3] = v.w; }
         else   { Jb2[0] = J[2 * N + oo + eL]; Jb2[1] = v.x; Jb2[2] = v.y; Jb2[3] = v.z; }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) Jf0[j] = Jf1[j] = Jf2[j] = Jb0[j] = Jb1[j] = Jb2[j] = 0u;
     }
 #pragma unroll
     for (int r = 0; r < RPC; r++) {
@@ -265,12 +275,27 @@ __device__ __forceinline__ void msc3d_sweep_item(uint32_t *sp, const uint32_t *J
             uint32_t flip;
             if (METRO) {
                 // thr[u] = count[u] << 8 with count[u] < 2^24 for unsat u = 0..2 and count = 2^24 (always accept,
-                // sweep.rs:141-145) for u >= 3:  (raw >> 8) < count  <=>  raw < thr
+                // sweep.rs:141-145) for u >= 3:  (raw >> 8) < count  <=>  raw < thr.  The events nest (p0 => p1 => p2), so
+                // with x = s1 + s2, y = c1 + c2, L = #events:  flip <=> x + 2y + L >= 3.
+#if PP_M3_VARIANT == 0
                 const uint32_t ge1 = oo2 | c1 | c2, ge2 = kk | c1 | c2, ge3 = maj3(c1, c2, oo2);
                 flip = ge3;
                 if (raw[j] < thr[2]) flip = ge2;
                 if (raw[j] < thr[1]) flip = ge1;
                 if (raw[j] < thr[0]) flip = 0xFFFFFFFFu;
+#elif PP_M3_VARIANT == 1
+                const uint32_t M2 = lt_mask(raw[j], one[2], nthr[2]), M1 = lt_mask(raw[j], one[1], nthr[1]);
+                const uint32_t M0 = lt_mask(raw[j], one[0], nthr[0]);
+                const uint32_t a3 = maj3(c1, c2, oo2 | M2);  // y = 2, or y = 1 and x + L >= 1
+                const uint32_t b3 = M0 | (oo2 & M1);         // L = 3, or x >= 1 and L >= 2
+                flip = a3 | (kk & M2) | b3;                  // or x = 2 and L >= 1
+#else
+                const bool p2 = raw[j] < thr[2], p1 = raw[j] < thr[1], p0 = raw[j] < thr[0];
+                flip = maj3(c1, c2, p2 ? 0xFFFFFFFFu : oo2);  // y = 2, or y = 1 and x + L >= 1
+                if (p2) flip |= kk;                           // x = 2 and L >= 1
+                if (p1) flip |= oo2;                          // x >= 1 and L >= 2
+                if (p0) flip = 0xFFFFFFFFu;                   // L = 3
+#endif
             } else {  // thr[u] = count[u]
                 const uint32_t x0 = s1 ^ s2, y1 = xor3(c1, c2, kk), y2 = maj3(c1, c2, kk);
                 const uint32_t draw = raw[j] >> 8;
@@ -318,14 +343,9 @@ __device__ __forceinline__ void msc3d_em_item(const uint32_t *A, const uint32_t 
     if (want_mags) vm.add8(a);
     if (want_energy) {
         uint32_t j0[8], j1[8], j2[8];
-        if (J) {
-            to_arr(lds4(J + 0 * N + self), j0); to_arr(lds4(J + 0 * N + N2 + self), j0 + 4);
-            to_arr(lds4(J + 1 * N + self), j1); to_arr(lds4(J + 1 * N + N2 + self), j1 + 4);
-            to_arr(lds4(J + 2 * N + self), j2); to_arr(lds4(J + 2 * N + N2 + self), j2 + 4);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) j0[j] = j1[j] = j2[j] = 0u;
-        }
+        to_arr(lds4(J + 0 * N + self), j0); to_arr(lds4(J + 0 * N + N2 + self), j0 + 4);
+        to_arr(lds4(J + 1 * N + self), j1); to_arr(lds4(J + 1 * N + N2 + self), j1 + 4);
+        to_arr(lds4(J + 2 * N + self), j2); to_arr(lds4(J + 2 * N + N2 + self), j2 + 4);
         uint32_t sb[8], cb[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {  // energy.rs:99-107: forward bonds only, each bond once
@@ -370,14 +390,13 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
              uint32_t *words_out, const uint32_t *swap_mask, int pt_schedule, int pt_parity) {
     extern __shared__ __align__(128) uint32_t smem[];
     const uint32_t N = gv.N, N2 = gv.N2;
-    const bool has_J = m.Jw != nullptr;
     uint32_t *Jsm = smem;
     // NH == 2: the item table is staged in shared memory and the reduction scratch has its own space.
     // NH == 1: two CTAs share an SM (the spins and coupling words of one CTA are half of its shared memory to the
     // byte), so the item table is read through L1/L2 with a one-item register prefetch and the reduction scratch
     // reuses the spin buffer once the epilogue has consumed it.
-    uint4 *items_sm = reinterpret_cast<uint4 *>(smem + (has_J ? 3 * N : 0));
-    uint32_t *sp_all = NH == 2 ? reinterpret_cast<uint32_t *>(items_sm + gv.n_items) : smem + (has_J ? 3 * N : 0);
+    uint4 *items_sm = reinterpret_cast<uint4 *>(smem + 3 * N);
+    uint32_t *sp_all = NH == 2 ? reinterpret_cast<uint32_t *>(items_sm + gv.n_items) : smem + 3 * N;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp_all + (size_t)NH * RPC * N);
     uint32_t *red_all = reinterpret_cast<uint32_t *>(bars + 4);
     auto item_at = [&](int it) { return NH == 2 ? items_sm[it] : __ldg(gv.items + it); };
@@ -389,7 +408,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     const uint32_t bytes = N * 4u;
     uint32_t *sp = sp_all + (size_t)half * RPC * N;
     uint32_t *red = NH == 2 ? red_all + half * 512 : sp;
-    const uint32_t *J = has_J ? Jsm : nullptr;
+    const uint32_t *J = Jsm;
 
     // ---- stage in: bulk-async copies, completion on mbarriers (bars[0]: couplings + item table, bars[1+h]: spins)
     if (tid == 0) {
@@ -399,8 +418,8 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bars[0], (has_J ? 3u * bytes : 0u) + (NH == 2 ? (uint32_t)gv.n_items * 16u : 0u));
-        if (has_J) bulk_g2s(Jsm, m.Jw + g * 3 * (int64_t)N, 3u * bytes, &bars[0]);
+        mbar_expect_tx(&bars[0], 3u * bytes + (NH == 2 ? (uint32_t)gv.n_items * 16u : 0u));
+        bulk_g2s(Jsm, m.Jw + g * 3 * (int64_t)N, 3u * bytes, &bars[0]);
         if (NH == 2) bulk_g2s(items_sm, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
     }
     if (t >= m.T) return;  // odd T: the last CTA of a group has an idle half
@@ -491,6 +510,10 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         const uint32_t cnt = m.lut[t * 13 + 2 * u];
         thr[u] = METRO ? (cnt << 8) : cnt;
     }
+    uint64_t nthr[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++)  // (one - 1) * tid = 0: keeps the addends in per-thread registers, where IMAD.WIDE can take them
+        nthr[u] = 0ull - (uint64_t)thr[u] + (uint64_t)((gv.one[u] - 1u) * (uint32_t)tid);
     const uint64_t key = msc_group_key(m.seed, (uint64_t)(group_offset + g));
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     mbar_wait(&bars[0], 0);
@@ -509,11 +532,11 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                 const uint4 desc = next;
                 if (it + MSC3D_NTH < gv.n_items) next = item_at(it + MSC3D_NTH);
                 if (((desc.w >> 16) ^ (uint32_t)c) & 1u)
-                    msc3d_sweep_item<RPC, METRO, true>(sp, J, N, so, oo, desc, thr, sweep_index + (uint32_t)sw, (uint32_t)t,
-                                                       (uint32_t)m.T, tag, k0, k1);
+                    msc3d_sweep_item<RPC, METRO, true>(sp, J, N, so, oo, desc, thr, nthr, gv.one, sweep_index + (uint32_t)sw,
+                                                       (uint32_t)t, (uint32_t)m.T, tag, k0, k1);
                 else
-                    msc3d_sweep_item<RPC, METRO, false>(sp, J, N, so, oo, desc, thr, sweep_index + (uint32_t)sw, (uint32_t)t,
-                                                        (uint32_t)m.T, tag, k0, k1);
+                    msc3d_sweep_item<RPC, METRO, false>(sp, J, N, so, oo, desc, thr, nthr, gv.one, sweep_index + (uint32_t)sw,
+                                                        (uint32_t)t, (uint32_t)m.T, tag, k0, k1);
             }
             half_barrier(half, MSC3D_NTH);
         }
@@ -536,15 +559,17 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     // 4/P warps per pair.  Each warp strides over the row segments, accumulates bit-sliced counters and reduces them
     // with a bit-sliced butterfly; partial lane totals meet in shared memory.
     if (want_energy || want_mags || want_overlap) {
-        constexpr int WPE = 4 / RPC;             // warps per replica (energy / magnetisation)
         constexpr int NP = RPC / 2;              // replica pairs
         constexpr int WPP = NP > 0 ? 4 / NP : 1; // warps per pair
+        // energy / magnetisation: warps 0..3 when the other four take the replica pairs, else all eight
+        const bool pairs_on = NP > 0 && want_overlap;
+        const int n_em = pairs_on ? 4 : 8, WPE = n_em / RPC;  // warps per replica
         const int w = ht >> 5, lane = ht & 31;
         // red layout: [replica r][E, M][WPE][32] then [pair p][q, ql][WPP][32]
         uint32_t *red_p = red + RPC * 2 * WPE * 32;
         uint32_t tot0 = 0, tot1 = 0;  // this warp's two lane totals: (E, M) or (q, ql)
         uint32_t *slot0 = nullptr, *slot1 = nullptr;
-        if (w < 4) {
+        if (w < n_em) {
             if (want_energy || want_mags) {
                 const int r = w / WPE, sub = w % WPE;
                 const uint32_t *A = sp + (size_t)r * N;
@@ -593,7 +618,6 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll
             for (int r = 0; r < RPC; r++) {
                 uint32_t e = 0, dn = 0;
-#pragma unroll
                 for (int k = 0; k < WPE; k++) {
                     if (want_energy) e += red[((r * 2 + 0) * WPE + k) * 32 + lane];
                     if (want_mags) dn += red[((r * 2 + 1) * WPE + k) * 32 + lane];

@@ -9,8 +9,8 @@
 constexpr int CH = 12;     // independent chains per thread
 constexpr int IT = 4096;  // loop iterations
 
-enum { K_LOP3, K_IMADW, K_IMAD, K_IADD3, K_SHF, K_SETSEL, K_MIX_LOP_IMADW_2_1, K_MIX_LOP_IMAD_1_1, K_MIX_LOP_IMADW_1_1, K_LDS128, K_PRMT, K_MIX_LOP_IMADW_4_1, K_IMADHI, K_N };
-const char *NAMES[] = {"lop3", "imad.wide.u32", "imad.lo", "iadd3", "shf", "isetp+sel", "lop3:imad.wide 2:1", "lop3:imad 1:1", "lop3:imad.wide 1:1", "lds.128", "prmt", "lop3:imad.wide 4:1", "imad.hi.s32"};
+enum { K_LOP3, K_IMADW, K_IMAD, K_IADD3, K_SHF, K_SETSEL, K_MIX_LOP_IMADW_2_1, K_MIX_LOP_IMAD_1_1, K_MIX_LOP_IMADW_1_1, K_LDS128, K_PRMT, K_MIX_LOP_IMADW_4_1, K_IMADHI, K_MIX_LOP_IMAD_2_1, K_MIX_LOP_IMAD_3_1, K_MIX_LOP_VIADD_1_1, K_MIX_LOP_IMADW_3_1, K_LDS128_SEQ, K_N };
+const char *NAMES[] = {"lop3", "imad.wide.u32", "imad.lo", "iadd3", "shf", "isetp+sel", "lop3:imad.wide 2:1", "lop3:imad 1:1", "lop3:imad.wide 1:1", "lds.128", "prmt", "lop3:imad.wide 4:1", "imad.hi.s32", "lop3:imad 2:1", "lop3:imad 3:1", "lop3:add 1:1", "lop3:imad.wide 3:1", "lds.128 conflict-free"};
 
 template <int KIND>
 __global__ void __launch_bounds__(1024, 1) bench(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(1024, 1) bench(uint32_t *out, uint32_t seed, u
 #pragma unroll
         for (int c = 0; c < CH; c++) {
             if (KIND == K_LOP3) asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
-            if (KIND == K_IMADW) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+            if (KIND == K_IMADW) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((uint32_t)w[c]), "r"(b));
             if (KIND == K_IMAD) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
             if (KIND == K_IMADHI) asm("mul.hi.s32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
             if (KIND == K_IADD3) asm("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
@@ -36,24 +36,44 @@ __global__ void __launch_bounds__(1024, 1) bench(uint32_t *out, uint32_t seed, u
             if (KIND == K_PRMT) asm("prmt.b32 %0, %0, %1, 0x2103;" : "+r"(x[c]) : "r"(a));
             if (KIND == K_SETSEL) asm("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(x[c]) : "r"(a), "r"(b));
             if (KIND == K_MIX_LOP_IMADW_2_1) {
-                if (c % 3 == 2) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+                if (c % 3 == 2) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((uint32_t)w[c]), "r"(b));
                 else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
             }
             if (KIND == K_MIX_LOP_IMADW_4_1) {
-                if (c % 5 == 4) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+                if (c % 5 == 4) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((uint32_t)w[c]), "r"(b));
                 else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
             }
             if (KIND == K_MIX_LOP_IMADW_1_1) {
-                if (c % 2) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"(a), "r"(b));
+                if (c % 2) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((uint32_t)w[c]), "r"(b));
                 else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
             }
             if (KIND == K_MIX_LOP_IMAD_1_1) {
                 if (c % 2) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
                 else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
             }
+            if (KIND == K_MIX_LOP_IMAD_2_1) {
+                if (c % 3 == 2) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_IMAD_3_1) {
+                if (c % 4 == 3) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(a), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_IMADW_3_1) {
+                if (c % 4 == 3) asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[c]) : "r"((uint32_t)w[c]), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_VIADD_1_1) {
+                if (c % 2) asm("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_LDS128_SEQ) {
+                uint4 v = sm[(threadIdx.x + (x[c] & 0x3e0)) & 1023];
+                x[c] = (v.x ^ v.y) + (v.z ^ v.w);
+            }
             if (KIND == K_LDS128) {
                 uint4 v = sm[(x[c] + c * 33) & 1023];
-                x[c] = v.x ^ v.w;  // one LOP3 per load keeps the address chain alive
+                x[c] = (v.x ^ v.y) + (v.z ^ v.w);  // keeps all four words and the address chain alive
             }
         }
     }
@@ -92,7 +112,7 @@ int main() {
     unsigned long long *cyc;
     cudaMalloc(&out, 148 * 1024 * 4);
     cudaMalloc(&cyc, 148 * 8);
-    for (int threads : {256, 512, 1024}) {
+    for (int threads : {512, 1024}) {
         run<K_LOP3>(out, cyc, threads);
         run<K_IMADW>(out, cyc, threads);
         run<K_IMAD>(out, cyc, threads);
@@ -105,7 +125,12 @@ int main() {
         run<K_MIX_LOP_IMADW_2_1>(out, cyc, threads);
         run<K_MIX_LOP_IMADW_1_1>(out, cyc, threads);
         run<K_MIX_LOP_IMAD_1_1>(out, cyc, threads);
+        run<K_MIX_LOP_IMAD_2_1>(out, cyc, threads);
+        run<K_MIX_LOP_IMAD_3_1>(out, cyc, threads);
+        run<K_MIX_LOP_IMADW_3_1>(out, cyc, threads);
+        run<K_MIX_LOP_VIADD_1_1>(out, cyc, threads);
         run<K_LDS128>(out, cyc, threads);
+        run<K_LDS128_SEQ>(out, cyc, threads);
     }
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
