@@ -22,6 +22,7 @@
  *   pp_op_overlap    <- OverlapAccum::collect (integer dots)  spin-sim/src/statistics/overlap.rs:259-281
  *   pp_op_pt         <- parallel_tempering(_full_ladder)      spin-sim/src/mcmc/tempering.rs:20-102
  *   pp_colouring     <- (no reference equivalent: the visit order of the checkerboard sweep)
+ *   pp_nccl_unique_id, pp_model_desc.slab_* <- (no reference equivalent: one lattice across GPUs)
  *   pp_metropolis_lookup <- UnitCouplingMetropolisLookup::new spin-sim/src/mcmc/sweep.rs:102-159
  *
  * A handle is NOT thread-safe: one caller at a time (the reference takes &mut self).
@@ -35,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 #define PP_MAX_DIMS 8
 
 typedef enum {
@@ -50,7 +51,9 @@ typedef enum {
 
 enum { PP_SWEEP_METROPOLIS = 0, PP_SWEEP_GIBBS = 1 };              /* config.rs:3-20   */
 enum { PP_PT_SINGLE_RANDOM_EDGE = 0, PP_PT_FULL_LADDER = 1 };      /* config.rs:61-79  */
-enum { PP_LAYOUT_AUTO = 0, PP_LAYOUT_INT8 = 1, PP_LAYOUT_MSC = 2 };
+enum { PP_LAYOUT_AUTO = 0, PP_LAYOUT_INT8 = 1, PP_LAYOUT_MSC = 2,
+       PP_LAYOUT_SLAB = 3 /* one 3-D hypercubic ferromagnet, stride geometry (no tables), slab-decomposed along x0 */ };
+#define PP_NCCL_ID_BYTES 128
 enum { PP_COUPLINGS_ARRAY = 0, PP_COUPLINGS_FERRO = 1 };
 
 typedef struct pp_sim pp_sim;
@@ -71,6 +74,12 @@ typedef struct {
     uint64_t seed;               /* dynamics seed (lib.rs:155; realization r uses splitmix64(seed ^ splitmix64(r)), lib.rs:30-32) */
     int32_t layout;              /* PP_LAYOUT_* ; AUTO = MSC when eligible (>=32 realizations, all couplings +-1) */
     int32_t device;              /* CUDA device ordinal */
+    /* PP_LAYOUT_SLAB only: the lattice is cut along dimension 0 into slab_ranks slabs, one per process / GPU
+     * (shape[0] must be a multiple of 2 * slab_ranks).  0 or 1 = the whole lattice on this device. */
+    int32_t slab_ranks;
+    int32_t slab_rank;           /* this process's slab, or -1: keep all slabs on this device (single-GPU emulation, tests) */
+    const uint8_t *nccl_unique_id; /* [PP_NCCL_ID_BYTES] from pp_nccl_unique_id() on rank 0, broadcast by the host; NULL unless
+                                      slab_ranks > 1 and slab_rank >= 0 */
 } pp_model_desc;
 
 /* sample() arguments (src/lib.rs:176-284). Zero means "None" for the optional intervals. */
@@ -132,7 +141,12 @@ void pp_destroy(pp_sim *sim);
 pp_status pp_sample(pp_sim *sim, const pp_sample_cfg *cfg, pp_results *out, const volatile int32_t *interrupt,
                     void (*on_sweep)(void *user, uint64_t sweep_id), void *user);
 pp_status pp_reset(pp_sim *sim, int32_t has_seed, uint64_t seed);
+/* slab layout: [S][local planes][L1][L2] of this process's slab (the whole lattice when slab_rank = -1 or slab_ranks <= 1) */
 pp_status pp_get_spins(pp_sim *sim, int64_t realization, int8_t *out /* [S*N], system-major */);
+/* spins per system held by this handle (N, or N / slab_ranks for one slab of a decomposed lattice) */
+int64_t pp_local_spin_count(const pp_sim *sim);
+/* NCCL bootstrap for PP_LAYOUT_SLAB across processes: rank 0 calls this, the host broadcasts the bytes */
+pp_status pp_nccl_unique_id(uint8_t *out /* [PP_NCCL_ID_BYTES] */);
 pp_status pp_get_system_ids(pp_sim *sim, int64_t realization, int64_t *out /* [S] */);
 pp_status pp_get_energies(pp_sim *sim, int64_t realization, float *out /* [S] by system */);
 int32_t pp_get_layout(const pp_sim *sim);

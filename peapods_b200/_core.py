@@ -22,7 +22,11 @@ def _rust_round(x: float) -> int:
 
 class IsingSimulation:
     def __init__(self, lattice_shape, couplings, temperatures, n_replicas=None, neighbor_offsets=None, seed=None,
-                 *, layout="auto", device=0, sample_offset=0):
+                 *, layout="auto", device=0, sample_offset=0, slab_ranks=1, slab_rank=0, nccl_unique_id=None):
+        """``layout="slab"`` (or "auto" for one large ferromagnet) keeps ONE 3-D lattice without neighbour tables and
+        can cut it along dimension 0 into ``slab_ranks`` slabs, one per process / GPU: pass this process's
+        ``slab_rank`` and the bytes of ``nccl_unique_id()`` from rank 0 (``slab_rank=-1`` keeps every slab on this
+        device)."""
         lib = _lib.load()
         self._lib = lib
         self._h = C.c_void_p()
@@ -68,7 +72,16 @@ class IsingSimulation:
         desc.seed = 42 if seed is None else int(seed)  # src/lib.rs:155
         desc.layout = _lib.LAYOUTS[layout]
         desc.device = int(device)
+        desc.slab_ranks = int(slab_ranks)
+        desc.slab_rank = int(slab_rank)
+        id_buf = None
+        if nccl_unique_id is not None:
+            id_buf = np.frombuffer(bytes(nccl_unique_id), dtype=np.uint8).copy()
+            if id_buf.size != _lib.NCCL_ID_BYTES:
+                raise ValueError(f"nccl_unique_id must have {_lib.NCCL_ID_BYTES} bytes")
+            desc.nccl_unique_id = id_buf.ctypes.data
         _lib.check(lib.pp_create(C.byref(desc), C.byref(self._h)))
+        self.n_local_spins = int(lib.pp_local_spin_count(self._h))
         self.layout = _lib.LAYOUT_NAMES[lib.pp_get_layout(self._h)]
         self.uses_msc3d = bool(lib.pp_uses_msc3d(self._h))
         self.last_sweep_loop_ms = 0.0
@@ -183,7 +196,7 @@ class IsingSimulation:
 
     # ------------------------------------------------------------------ src/lib.rs:620-633
     def get_spins(self, realization=0):
-        out = np.zeros(self.n_replicas * self.n_temps * self.n_spins, dtype=np.int8)
+        out = np.zeros(self.n_replicas * self.n_temps * self.n_local_spins, dtype=np.int8)
         _lib.check(self._lib.pp_get_spins(self._h, int(realization), out.ctypes.data))
         return out
 
@@ -203,7 +216,7 @@ class IsingSimulation:
 
     def set_spins(self, spins, realization=0):
         a = np.ascontiguousarray(spins, dtype=np.int8).reshape(-1)
-        if a.size != self.n_replicas * self.n_temps * self.n_spins:
+        if a.size != self.n_replicas * self.n_temps * self.n_local_spins:
             raise ValueError("spins must have n_systems * n_spins entries")
         _lib.check(self._lib.pp_set_spins(self._h, int(realization), a.ctypes.data))
 
@@ -232,6 +245,14 @@ class IsingSimulation:
 
     def op_pt(self, pt_schedule, pt_event):
         _lib.check(self._lib.pp_op_pt(self._h, _lib.PT_SCHEDULES[pt_schedule], int(pt_event)))
+
+
+def nccl_unique_id() -> bytes:
+    """Bootstrap token for a slab-decomposed lattice: call on rank 0, broadcast to the other ranks."""
+    lib = _lib.load()
+    buf = np.zeros(_lib.NCCL_ID_BYTES, dtype=np.uint8)
+    _lib.check(lib.pp_nccl_unique_id(buf.ctypes.data))
+    return buf.tobytes()
 
 
 def colouring(lattice_shape, neighbor_offsets=None):

@@ -13,7 +13,8 @@ LIB_PATH = PKG / "lib" / "libpeapods_b200.so"
 PP_OK, PP_ERR_INVALID, PP_ERR_UNSUPPORTED, PP_ERR_INTERRUPTED, PP_ERR_CUDA, PP_ERR_NCCL, PP_ERR_OOM = range(7)
 SWEEP_MODES = {"metropolis": 0, "gibbs": 1}
 PT_SCHEDULES = {"single_random_edge": 0, "full_ladder": 1}
-LAYOUTS = {"auto": 0, "int8": 1, "msc": 2}
+LAYOUTS = {"auto": 0, "int8": 1, "msc": 2, "slab": 3}
+NCCL_ID_BYTES = 128
 LAYOUT_NAMES = {v: k for k, v in LAYOUTS.items()}
 
 _PD = C.POINTER(C.c_double)
@@ -36,6 +37,9 @@ class ModelDesc(C.Structure):
         ("seed", C.c_uint64),
         ("layout", C.c_int32),
         ("device", C.c_int32),
+        ("slab_ranks", C.c_int32),
+        ("slab_rank", C.c_int32),
+        ("nccl_unique_id", C.c_void_p),
     ]
 
 
@@ -88,6 +92,8 @@ SIGNATURES = {
     "pp_get_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_get_energies": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_get_layout": (C.c_int32, [C.c_void_p]),
+    "pp_local_spin_count": (C.c_int64, [C.c_void_p]),
+    "pp_nccl_unique_id": (C.c_int32, [C.c_void_p]),
     "pp_uses_msc3d": (C.c_int32, [C.c_void_p]),
     "pp_set_spins": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_set_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
@@ -114,7 +120,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.pp_abi_version() != 1:
+    if lib.pp_abi_version() != 2:
         raise ImportError("libpeapods_b200.so ABI version mismatch")
     _lib = lib
     return lib

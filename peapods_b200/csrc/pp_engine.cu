@@ -25,6 +25,7 @@
 #include "pp_kernels_msc3d.cuh"
 #include "pp_kernels_stats.cuh"
 #include "pp_plan.h"
+#include "pp_slab.cuh"
 
 using namespace pp;
 
@@ -190,6 +191,7 @@ struct pp_sim {
     bool defer_swaps = true;                           // gather PT lane swaps in the next sweep's stage-in
     std::vector<cudaStream_t> xstreams;
     std::vector<cudaEvent_t> xevents;
+    SlabState *slab = nullptr;                         // PP_LAYOUT_SLAB (pp_slab.cuh)
     // measurement hook: event pairs around sweep-kernel launches
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
@@ -240,6 +242,17 @@ static void free_sim(pp_sim *s) {
     for (void *p : ptrs)
         if (p) pool_free(s, p);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->slab) {
+        SlabState *sl = s->slab;
+        if (sl->comm_stream) cudaStreamSynchronize(sl->comm_stream);
+        if (sl->comm) nccl_api().CommDestroy(sl->comm);
+        for (uint8_t *b : sl->buffers) cudaFree(b);
+        if (sl->d_partial) cudaFree(sl->d_partial);
+        if (sl->ev_boundary) cudaEventDestroy(sl->ev_boundary);
+        if (sl->ev_halo) cudaEventDestroy(sl->ev_halo);
+        if (sl->comm_stream) cudaStreamDestroy(sl->comm_stream);
+        delete sl;
+    }
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : s->xevents) cudaEventDestroy(e);
     for (cudaStream_t x : s->xstreams) cudaStreamDestroy(x);
@@ -252,6 +265,20 @@ static void free_sim(pp_sim *s) {
 extern "C" void pp_destroy(pp_sim *sim) { free_sim(sim); }
 extern "C" int32_t pp_get_layout(const pp_sim *sim) { return sim ? sim->layout : 0; }
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
+extern "C" int64_t pp_local_spin_count(const pp_sim *sim) {
+    if (!sim) return 0;
+    return sim->slab ? sim->slab->local_planes() * sim->slab->plane : sim->mv.N;
+}
+extern "C" pp_status pp_nccl_unique_id(uint8_t *out) {
+    if (!out) return fail(PP_ERR_INVALID, "out is NULL");
+    NcclApi &nc = nccl_api();
+    if (!nc.error.empty()) return fail(PP_ERR_NCCL, nc.error);
+    ncclUniqueId id;
+    ncclResult_t r = nc.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(PP_ERR_NCCL, std::string("ncclGetUniqueId: ") + nc.GetErrorString(r));
+    memcpy(out, &id, PP_NCCL_ID_BYTES);
+    return PP_OK;
+}
 
 // coupling classification: flags[0] non-unit value, flags[1] zero, flags[2] negative
 __global__ void classify_couplings_kernel(const float *J, int64_t n, int *flags) {
@@ -402,6 +429,88 @@ static pp_status launch_msc3d(pp_sim *s, Ctx &c, const ModelView &m, int sweep_m
     return fail(PP_ERR_UNSUPPORTED, "msc3d: unsupported replica count");
 }
 
+// ---- slab layout (pp_slab.cuh) -----------------------------------------------------------------
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t _r = (expr);                                                                   \
+        if (_r != ncclSuccess) return fail(PP_ERR_NCCL, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
+    } while (0)
+
+// boundary planes of every local slab -> the halo planes of their neighbours, enqueued on `stream`
+static pp_status slab_exchange(pp_sim *s, cudaStream_t stream) {
+    SlabState *sl = s->slab;
+    const int S = s->mv.S;
+    const size_t bytes = (size_t)sl->plane;
+    if (sl->rank < 0 || sl->ranks == 1) {  // all slabs local: device copies
+        const int n = (int)sl->parts.size();
+        for (int r = 0; r < n; r++) {
+            const SlabView &me = sl->parts[(size_t)r], &lo = sl->parts[(size_t)((r + n - 1) % n)], &up = sl->parts[(size_t)((r + 1) % n)];
+            for (int sys = 0; sys < S; sys++) {
+                const int64_t o = (int64_t)sys * me.sys_stride;
+                CUDA_TRY(cudaMemcpyAsync(lo.spins + o + (int64_t)(sl->P + 1) * sl->plane, me.spins + o + sl->plane, bytes,
+                                         cudaMemcpyDeviceToDevice, stream));
+                CUDA_TRY(cudaMemcpyAsync(up.spins + o, me.spins + o + (int64_t)sl->P * sl->plane, bytes, cudaMemcpyDeviceToDevice, stream));
+            }
+        }
+        return PP_OK;
+    }
+    NcclApi &nc = nccl_api();
+    const SlabView &me = sl->parts[0];
+    const int lo = (sl->rank + sl->ranks - 1) % sl->ranks, up = (sl->rank + 1) % sl->ranks;
+    NCCL_TRY(nc.GroupStart());
+    for (int sys = 0; sys < S; sys++) {
+        uint8_t *b = me.spins + (int64_t)sys * me.sys_stride;
+        NCCL_TRY(nc.Send(b + sl->plane, bytes, ncclUint8, lo, sl->comm, stream));                             // my first plane
+        NCCL_TRY(nc.Send(b + (int64_t)sl->P * sl->plane, bytes, ncclUint8, up, sl->comm, stream));            // my last plane
+        NCCL_TRY(nc.Recv(b + (int64_t)(sl->P + 1) * sl->plane, bytes, ncclUint8, up, sl->comm, stream));      // upper halo
+        NCCL_TRY(nc.Recv(b, bytes, ncclUint8, lo, sl->comm, stream));                                         // lower halo
+    }
+    NCCL_TRY(nc.GroupEnd());
+    return PP_OK;
+}
+
+static pp_status slab_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream, uint32_t sweep_index, int n_sweeps) {
+    SlabState *sl = s->slab;
+    const unsigned bx = blocks_for(sl->parts[0].chunks_per_plane, 256);
+    for (int sw = 0; sw < n_sweeps; sw++)
+        for (int colour = 0; colour < 2; colour++) {
+            for (const SlabView &v : sl->parts) {  // boundary planes first: they are what the neighbours wait for
+                slab_sweep_kernel<<<dim3(bx, 2, (unsigned)m.S), 256, 0, stream>>>(m, v, colour, sweep_index + (uint32_t)sw, 1, 1, sl->P);
+                s->launches++;
+            }
+            CUDA_TRY(cudaEventRecord(sl->ev_boundary, stream));
+            CUDA_TRY(cudaStreamWaitEvent(sl->comm_stream, sl->ev_boundary, 0));
+            pp_status st = slab_exchange(s, sl->comm_stream);
+            if (st != PP_OK) return st;
+            CUDA_TRY(cudaEventRecord(sl->ev_halo, sl->comm_stream));
+            if (sl->P > 2)
+                for (const SlabView &v : sl->parts) {  // interior planes overlap the halo transfer
+                    slab_sweep_kernel<<<dim3(bx, (unsigned)(sl->P - 2), (unsigned)m.S), 256, 0, stream>>>(m, v, colour, sweep_index + (uint32_t)sw,
+                                                                                                     2, sl->P - 2, 0);
+                    s->launches++;
+                }
+            CUDA_TRY(cudaStreamWaitEvent(stream, sl->ev_halo, 0));
+        }
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+static pp_status slab_energy(pp_sim *s, const ModelView &m, cudaStream_t stream, bool want_mags) {
+    SlabState *sl = s->slab;
+    CUDA_TRY(cudaMemsetAsync(sl->d_partial, 0, sizeof(unsigned long long) * 2 * (size_t)m.S, stream));
+    const unsigned bx = blocks_for(sl->parts[0].chunks_per_plane, 256);
+    for (const SlabView &v : sl->parts) {
+        slab_energy_kernel<<<dim3(bx, (unsigned)sl->P, (unsigned)m.S), 256, 0, stream>>>(v, sl->d_partial);
+        s->launches++;
+    }
+    if (sl->comm)
+        NCCL_TRY(nccl_api().AllReduce(sl->d_partial, sl->d_partial, 2 * (size_t)m.S, ncclUint64, ncclSum, sl->comm, stream));
+    slab_finish_energy_kernel<<<blocks_for(m.S, 128), 128, 0, stream>>>(m, sl->d_partial, want_mags ? 1 : 0);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
 // want_overlap / want_fold: the caller wants the replica-pair dots of the post-sweep state / the recorded-sweep fold;
 // *fused is set when the sweep kernel did both itself (msc3d epilogue), otherwise the caller launches
 // launch_overlap() and fold_kernel.
@@ -411,6 +520,13 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
     ModelView m = c.m;
     m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
     if (fused) *fused = false;
+    if (s->layout == PP_LAYOUT_SLAB) {
+        if (n_sweeps > 0) prof_mark(s, c.stream);
+        pp_status st = slab_sweeps(s, m, c.stream, sweep_index, n_sweeps);
+        if (st != PP_OK) return st;
+        if (n_sweeps > 0) prof_mark(s, c.stream);
+        return want_energy ? slab_energy(s, m, c.stream, want_mags) : PP_OK;
+    }
     if (s->layout == PP_LAYOUT_MSC) {
         const bool timed = n_sweeps > 0;
         if (timed) prof_mark(s, c.stream);
@@ -465,6 +581,7 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
 static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
     const ModelView &m = c.m;
     if (s->layout == PP_LAYOUT_MSC) return launch_sweeps(s, c, PP_SWEEP_METROPOLIS, 0, 0, 0, true, want_mags);
+    if (s->layout == PP_LAYOUT_SLAB) return slab_energy(s, m, c.stream, want_mags);
     const unsigned grid = (unsigned)(m.D * m.S);
     switch (m.coupling_class) {
         case COUP_FERRO: energy_mag_int8_kernel<COUP_FERRO><<<grid, 256, 0, c.stream>>>(m, want_mags); break;
@@ -544,7 +661,12 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
     ModelView m = s->mv;
     const int64_t DS = m.D * m.S;
     iota_sid_kernel<<<blocks_for(DS, 256), 256, 0, s->stream>>>(s->d_sid, DS, m.S);
-    if (s->layout == PP_LAYOUT_MSC) {
+    if (s->layout == PP_LAYOUT_SLAB) {
+        for (const SlabView &v : s->slab->parts)
+            slab_init_kernel<<<dim3(blocks_for(v.chunks_per_plane, 256), (unsigned)v.P, (unsigned)m.S), 256, 0, s->stream>>>(m, v);
+        pp_status stx = slab_exchange(s, s->stream);
+        if (stx != PP_OK) return stx;
+    } else if (s->layout == PP_LAYOUT_MSC) {
         dim3 grid((unsigned)(s->G * m.S), blocks_for((m.N + 3) / 4, 128));
         msc_init_kernel<<<grid, 128, 0, s->stream>>>(m);
     } else {
@@ -577,8 +699,27 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     if (desc->coupling_kind == PP_COUPLINGS_ARRAY && !desc->couplings) return fail(PP_ERR_INVALID, "couplings is NULL");
     if ((int64_t)desc->n_temps * desc->n_replicas > (1 << 20)) return fail(PP_ERR_INVALID, "too many systems per realization");
 
+    // slab layout (pp_slab.cuh): explicit, or chosen for one large ferromagnet whose neighbour tables would not fit
+    const bool slab_shape = desc->n_dims == 3 && (desc->n_offsets <= 0 || !desc->offsets) && desc->shape[0] % 2 == 0 &&
+                            desc->shape[1] % 2 == 0 && desc->shape[2] % 8 == 0;
+    bool want_slab = desc->layout == PP_LAYOUT_SLAB;
+    if (desc->layout == PP_LAYOUT_AUTO && slab_shape && desc->coupling_kind == PP_COUPLINGS_FERRO && desc->n_disorder == 1 &&
+        desc->n_replicas == 1 && desc->shape[0] * desc->shape[1] * desc->shape[2] >= (int64_t(1) << 24))
+        want_slab = true;
+    const int slab_ranks = std::max(1, (int)desc->slab_ranks);
+    if (want_slab) {
+        if (!slab_shape) return fail(PP_ERR_UNSUPPORTED, "slab layout needs a 3-D hypercubic lattice with even extents and shape[2] % 8 == 0");
+        if (desc->coupling_kind != PP_COUPLINGS_FERRO) return fail(PP_ERR_UNSUPPORTED, "slab layout needs couplings='ferro' (never materialised)");
+        if (desc->n_disorder != 1 || desc->n_replicas != 1) return fail(PP_ERR_UNSUPPORTED, "slab layout holds one realization with one replica per temperature");
+        if (desc->shape[0] % (2 * slab_ranks) != 0) return fail(PP_ERR_INVALID, "slab layout needs shape[0] to be a multiple of 2 * slab_ranks");
+        if (desc->slab_rank >= slab_ranks) return fail(PP_ERR_INVALID, "slab_rank out of range");
+        if (slab_ranks > 1 && desc->slab_rank >= 0 && !desc->nccl_unique_id) return fail(PP_ERR_INVALID, "nccl_unique_id is NULL");
+    } else if (desc->slab_ranks > 1) {
+        return fail(PP_ERR_INVALID, "slab_ranks > 1 needs layout = PP_LAYOUT_SLAB");
+    }
+
     pp_sim *s = new pp_sim();
-    std::string err = build_plan(desc->n_dims, desc->shape, desc->n_offsets, desc->offsets, s->plan);
+    std::string err = build_plan(desc->n_dims, desc->shape, desc->n_offsets, desc->offsets, s->plan, !want_slab);
     if (!err.empty()) {
         delete s;
         return fail(PP_ERR_UNSUPPORTED, err);
@@ -648,7 +789,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
 
     // layout
     const bool msc_ok = m.coupling_class != COUP_F32 && !flags[1] && z <= 7;
-    if (desc->layout == PP_LAYOUT_MSC) {
+    if (want_slab) {
+        s->layout = PP_LAYOUT_SLAB;
+    } else if (desc->layout == PP_LAYOUT_MSC) {
         if (!msc_ok) {
             free_sim(s);
             return fail(PP_ERR_UNSUPPORTED, "multispin layout needs +-1 couplings (no zeros), eligible temperatures and <= 7 forward directions");
@@ -668,7 +811,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     }
 
     // geometry tables; the multispin layout stores words in the plan's compact order (pp_plan.h)
-    {
+    if (s->layout != PP_LAYOUT_SLAB) {
         const bool storage_space = s->layout == PP_LAYOUT_MSC && s->plan.compact;
         std::vector<uint32_t> nbr_s, order_s;
         if (storage_space) storage_tables(s->plan, nbr_s, order_s);
@@ -691,7 +834,50 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         m.perm = s->d_perm;
     }
 
-    if (s->layout == PP_LAYOUT_MSC) {
+    if (s->layout == PP_LAYOUT_SLAB) {
+        SlabState *sl = s->slab = new SlabState();
+        sl->ranks = slab_ranks;
+        sl->rank = slab_ranks == 1 ? 0 : desc->slab_rank;
+        sl->L0 = (int)desc->shape[0]; sl->L1 = (int)desc->shape[1]; sl->L2 = (int)desc->shape[2];
+        sl->P = sl->L0 / slab_ranks;
+        sl->plane = (int64_t)sl->L1 * sl->L2;
+        const int n_local = sl->rank < 0 ? slab_ranks : 1;
+        for (int i = 0; i < n_local; i++) {
+            SlabView v{};
+            v.P = sl->P; v.L1 = sl->L1; v.L2 = sl->L2;
+            v.plane = sl->plane;
+            v.sys_stride = (int64_t)(sl->P + 2) * sl->plane;
+            v.first_plane = (int64_t)(sl->rank < 0 ? i : sl->rank) * sl->P;
+            v.chunks_per_plane = sl->plane / 8;
+            uint8_t *buf = nullptr;
+            CREATE_TRY(cudaMalloc((void **)&buf, (size_t)(m.S * v.sys_stride)));
+            sl->buffers.push_back(buf);
+            v.spins = buf;
+            sl->parts.push_back(v);
+        }
+        CREATE_TRY(cudaMalloc((void **)&sl->d_partial, sizeof(unsigned long long) * 2 * (size_t)m.S));
+        CREATE_TRY(cudaStreamCreateWithFlags(&sl->comm_stream, cudaStreamNonBlocking));
+        CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_boundary, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_halo, cudaEventDisableTiming));
+        if (slab_ranks > 1 && sl->rank >= 0) {
+            NcclApi &nc = nccl_api();
+            if (!nc.error.empty()) {
+                std::string msg = nc.error;
+                free_sim(s);
+                return fail(PP_ERR_NCCL, msg);
+            }
+            ncclUniqueId id;
+            static_assert(sizeof(ncclUniqueId) == PP_NCCL_ID_BYTES, "ncclUniqueId size");
+            memcpy(&id, desc->nccl_unique_id, sizeof(id));
+            ncclResult_t r = nc.CommInitRank(&sl->comm, slab_ranks, id, sl->rank);
+            if (r != ncclSuccess) {
+                std::string msg = std::string("ncclCommInitRank: ") + nc.GetErrorString(r);
+                sl->comm = nullptr;
+                free_sim(s);
+                return fail(PP_ERR_NCCL, msg);
+            }
+        }
+    } else if (s->layout == PP_LAYOUT_MSC) {
         s->G = (m.D + 31) / 32;
         if (m.coupling_class == COUP_UNIT) {
             CREATE_TRY(pool_alloc(s, (void **)&s->d_Jw, sizeof(uint32_t) * (size_t)(s->G * z * N)));
@@ -1117,12 +1303,34 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
 
 // ------------------------------------------------------------------------------------------
 // state access
+// slab layout: host [S][local planes][L1][L2] +-1 <-> the slabs' own planes; dir 0 = get, 1 = set
+static pp_status slab_copy_spins(pp_sim *s, int8_t *host, int dir) {
+    SlabState *sl = s->slab;
+    const ModelView &m = s->mv;
+    const int64_t per_sys = sl->local_planes() * sl->plane;
+    const size_t n = (size_t)(m.S * per_sys);
+    int8_t *tmp = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&tmp, n));
+    if (dir == 1) CUDA_TRY(cudaMemcpy(tmp, host, n, cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < sl->parts.size(); i++) {
+        const SlabView &v = sl->parts[i];
+        slab_convert_kernel<<<dim3(blocks_for((int64_t)v.P * v.plane, 256), (unsigned)m.S), 256, 0, s->stream>>>(
+            v, tmp, per_sys, (int64_t)i * v.P * v.plane, dir);
+    }
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess && dir == 0) e = cudaMemcpy(host, tmp, n, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    CUDA_TRY(e);
+    return PP_OK;
+}
+
 extern "C" pp_status pp_get_spins(pp_sim *s, int64_t r, int8_t *out) {
     if (!s || !out) return fail(PP_ERR_INVALID, "sim/out is NULL");
     if (r < 0 || r >= s->mv.D) return fail(PP_ERR_INVALID, "realization index out of range");
     CUDA_TRY(cudaSetDevice(s->device));
     const ModelView &m = s->mv;
     const size_t n = (size_t)m.S * m.N;
+    if (s->layout == PP_LAYOUT_SLAB) return slab_copy_spins(s, out, 0);
     if (s->layout == PP_LAYOUT_MSC) {
         int8_t *tmp = nullptr;
         CUDA_TRY(pool_alloc(s, (void **)&tmp, n));
@@ -1144,6 +1352,14 @@ extern "C" pp_status pp_set_spins(pp_sim *s, int64_t r, const int8_t *spins) {
     const ModelView &m = s->mv;
     const size_t n = (size_t)m.S * m.N;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->layout == PP_LAYOUT_SLAB) {
+        pp_status st = slab_copy_spins(s, const_cast<int8_t *>(spins), 1);
+        if (st != PP_OK) return st;
+        st = slab_exchange(s, s->stream);
+        if (st != PP_OK) return st;
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        return PP_OK;
+    }
     if (s->layout == PP_LAYOUT_MSC) {
         int8_t *tmp = nullptr;
         CUDA_TRY(pool_alloc(s, (void **)&tmp, n));

@@ -1,0 +1,150 @@
+// pp_kernels_slab.cuh — one large 3-D hypercubic ferromagnet, stride geometry, slab-decomposed along x0.
+//
+// The table-driven int8 kernels need 8*z' bytes of neighbour indices per site (24 GiB at 1024^3, like the
+// reference's Lattice: spin-sim/src/geometry/lattice.rs:63-82).  This path has no tables: a thread owns the 8
+// consecutive sites of one row segment, its neighbours are the same segment in the rows x1 +- 1 and the planes
+// x0 +- 1 plus one edge byte, and all six neighbour counts of the 8 sites come from five 64-bit adds (SWAR).
+//
+// Replaces, for this layout,
+//   metropolis_sweep / gibbs_sweep (lookup rule)     spin-sim/src/mcmc/sweep.rs:170-185, 220-284
+//   compute_energies_and_magnetizations_into         spin-sim/src/spins/energy.rs:59-110
+//   Realization::new / reset (spin draw)             spin-sim/src/simulation/realization.rs:177-182
+//
+// Storage: u8 [S][P + 2][L1][L2], one byte per spin, 1 = spin -1, 0 = spin +1.  Planes 1..P are the slab's own
+// planes (global x0 = first_plane + p - 1), planes 0 and P + 1 are halos holding the neighbouring slabs' boundary
+// planes (the periodic images when there is one slab).  P is even, so the checkerboard colour (x0 + x1 + x2) & 1 of
+// a site does not depend on how the lattice is cut.  Draws follow RNG-SPEC exactly as the table-driven int8 kernels
+// (pp_kernels_int8.cuh): colour rank = site >> 1, one Philox call per 8-site segment and colour, stream = system id.
+#pragma once
+#include "pp_device.cuh"
+
+namespace pp {
+
+struct SlabView {
+    uint8_t *spins;            // [S][P + 2][L1][L2]
+    int P, L1, L2;
+    int64_t plane;             // L1 * L2
+    int64_t sys_stride;        // (P + 2) * plane
+    int64_t first_plane;       // global x0 of local plane 1
+    int64_t chunks_per_plane;  // L1 * L2 / 8
+};
+
+__device__ __forceinline__ uint64_t ld8(const uint8_t *p) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    return (uint64_t)v.x | ((uint64_t)v.y << 32);
+}
+
+// grid = (chunk blocks, planes, slots).  The launch covers local planes [pa, pa + na) and, after them, [pb, ...).
+__global__ void __launch_bounds__(256)
+slab_sweep_kernel(ModelView m, SlabView v, int colour, uint32_t sweep_index, int pa, int na, int pb) {
+    __shared__ uint32_t thr[8];
+    const int slot = blockIdx.z;
+    const int t = slot % m.T;  // realization.rs:166: temperatures repeat with period T
+    if (threadIdx.x < 7) thr[threadIdx.x] = m.lut[t * 13 + 2 * threadIdx.x];  // sweep.rs:162-166, index ec + 2z' = 2 * unsat
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.chunks_per_plane) return;
+    const int pi = blockIdx.y;
+    const int p = pi < na ? pa + pi : pb + (pi - na);
+    const int kpr = v.L2 >> 3;
+    const int x1 = (int)(c / kpr), k = (int)(c - (int64_t)x1 * kpr);
+    const uint32_t sys = (uint32_t)m.system_ids[slot];  // parallel.rs:27-33: spins by system, temperature by slot
+    uint8_t *base = v.spins + (int64_t)sys * v.sys_stride;
+    uint8_t *row = base + (int64_t)p * v.plane + (int64_t)x1 * v.L2;
+    const int x1m = x1 ? x1 - 1 : v.L1 - 1, x1p = x1 + 1 == v.L1 ? 0 : x1 + 1;
+    const int64_t dym = (int64_t)(x1m - x1) * v.L2, dyp = (int64_t)(x1p - x1) * v.L2;
+    const uint64_t C = ld8(row + 8 * k);
+    const uint64_t Xm = ld8(row - v.plane + 8 * k), Xp = ld8(row + v.plane + 8 * k);
+    const uint64_t Ym = ld8(row + dym + 8 * k), Yp = ld8(row + dyp + 8 * k);
+    const int64_t gx0 = v.first_plane + p - 1;
+    const int off = (int)((colour ^ gx0 ^ x1) & 1);  // active sites of the segment: x2 = 8k + 2l + off
+    // off = 0: site 0 needs the byte left of the segment; off = 1: site 7 needs the byte right of it
+    const int xe = off ? (8 * k + 8 == v.L2 ? 0 : 8 * k + 8) : (k ? 8 * k - 1 : v.L2 - 1);
+    const uint64_t E = row[xe];
+    const uint64_t left = (C << 8) | (off ? 0ull : E), right = (C >> 8) | (off ? E << 56 : 0ull);
+    const uint64_t down = Xm + Xp + Ym + Yp + left + right;  // per byte: down-spin neighbours (<= 6, no carries)
+    const uint64_t q = ((uint64_t)gx0 * v.L1 + x1) * kpr + k;  // segment index = colour rank >> 2
+    const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
+    const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
+    uint64_t flips = 0;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        const int sh = 8 * (2 * l + off);
+        const uint32_t nd = (uint32_t)(down >> sh) & 0xFFu, sb = (uint32_t)(C >> sh) & 1u;
+        const uint32_t unsat = sb ? 6u - nd : nd;  // ferromagnet: a bond is unsatisfied iff the two spins differ
+        if ((pick(o, l) >> 8) < thr[unsat]) flips |= 1ull << sh;  // sweep.rs:182-184
+    }
+    const uint64_t out = C ^ flips;
+    *reinterpret_cast<uint2 *>(row + 8 * k) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
+}
+
+// K0: spin -1 iff the INIT-domain draw < 2^23 (realization.rs:180); grid = (chunk blocks, P, S)
+__global__ void __launch_bounds__(256) slab_init_kernel(ModelView m, SlabView v) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.chunks_per_plane) return;
+    const int p = blockIdx.y + 1;
+    const uint32_t sys = blockIdx.z;
+    const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
+    const uint64_t seg = ((uint64_t)(v.first_plane + p - 1)) * v.chunks_per_plane + c;  // global site index >> 3
+    uint64_t out = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const u32x4 o = philox4x32_10((uint32_t)(2 * seg + h), 0u, sys, TAG_INIT, (uint32_t)key, (uint32_t)(key >> 32));
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+            if ((pick(o, l) >> 8) < (1u << 23)) out |= 1ull << (8 * (4 * h + l));
+    }
+    uint8_t *dst = v.spins + (int64_t)sys * v.sys_stride + (int64_t)p * v.plane + 8 * c;
+    *reinterpret_cast<uint2 *>(dst) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
+}
+
+// K5: per-system partial sums of this slab: unsatisfied forward bonds and down spins (energy.rs:92-109 counts every
+// bond once through its forward direction).  grid = (chunk blocks, P, S); partial[2*sys] += unsat, [2*sys+1] += down.
+__global__ void __launch_bounds__(256) slab_energy_kernel(SlabView v, unsigned long long *partial) {
+    __shared__ long long sh[32];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y + 1;
+    const uint32_t sys = blockIdx.z;
+    long long unsat = 0, dn = 0;
+    if (c < v.chunks_per_plane) {
+        const int kpr = v.L2 >> 3;
+        const int x1 = (int)(c / kpr), k = (int)(c - (int64_t)x1 * kpr);
+        const uint8_t *row = v.spins + (int64_t)sys * v.sys_stride + (int64_t)p * v.plane + (int64_t)x1 * v.L2;
+        const int x1p = x1 + 1 == v.L1 ? 0 : x1 + 1;
+        const uint64_t C = ld8(row + 8 * k), Xp = ld8(row + v.plane + 8 * k), Yp = ld8(row + (int64_t)(x1p - x1) * v.L2 + 8 * k);
+        const uint64_t E = row[8 * k + 8 == v.L2 ? 0 : 8 * k + 8];
+        const uint64_t right = (C >> 8) | (E << 56);
+        unsat = __popcll(C ^ Xp) + __popcll(C ^ Yp) + __popcll(C ^ right);
+        dn = __popcll(C);
+    }
+    const long long tu = block_sum<long long>(unsat, sh);
+    const long long td = block_sum<long long>(dn, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(&partial[2 * sys], (unsigned long long)tu);
+        atomicAdd(&partial[2 * sys + 1], (unsigned long long)td);
+    }
+}
+
+// totals (summed over slabs) -> e = (sum_bonds s s) / N with the reference's final f32 division (energy.rs:108) and M
+__global__ void slab_finish_energy_kernel(ModelView m, const unsigned long long *total, int want_mags) {
+    const int sys = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sys >= m.S) return;
+    const long long bonds = 3ll * m.N - 2ll * (long long)total[2 * sys];
+    m.energies[sys] = __fdiv_rn((float)bonds, (float)m.N);
+    if (want_mags) m.mags[sys] = (long long)m.N - 2ll * (long long)total[2 * sys + 1];
+}
+
+// own planes <-> +-1 int8 in the reference's order [S][planes][L1][L2]; dir 0: unpack to ext, 1: pack from ext.
+// ext_sys_stride / ext_off place this slab's planes inside the caller's array (whole lattice or local planes only).
+__global__ void slab_convert_kernel(SlabView v, int8_t *ext, int64_t ext_sys_stride, int64_t ext_off, int dir) {
+    const int64_t per_sys = (int64_t)v.P * v.plane;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sys = blockIdx.y;
+    if (i >= per_sys) return;
+    uint8_t *b = v.spins + (int64_t)sys * v.sys_stride + v.plane + i;
+    int8_t *e = ext + (int64_t)sys * ext_sys_stride + ext_off + i;
+    if (dir == 0) *e = *b ? (int8_t)-1 : (int8_t)1;
+    else *b = *e < 0 ? 1 : 0;
+}
+
+}  // namespace pp

@@ -50,7 +50,7 @@ class Ising:
     """Ising model on a periodic Bravais lattice, sampled on the GPU sweep engine."""
 
     def __init__(self, lattice_shape, couplings="ferro", temperatures=np.geomspace(0.1, 10, 32), n_replicas=1,
-                 n_disorder=1, neighbor_offsets=None, geometry=None, seed=None, *, layout="auto", device=0):
+                 n_disorder=1, neighbor_offsets=None, geometry=None, seed=None, *, layout="auto", device=0, **engine_kwargs):
         if geometry is not None:
             if neighbor_offsets is not None:
                 raise ValueError("Cannot specify both geometry and neighbor_offsets")
@@ -69,11 +69,13 @@ class Ising:
         coupling_seq, self._constructor_dynamics_seed = seed_material(seed)
         if isinstance(couplings, np.ndarray):
             coup = couplings.astype(np.float32)
+        elif couplings == "ferro" and n_disorder == 1 and self.n_spins * self.n_neighbors >= (1 << 26):
+            coup = "ferro"  # a large ferromagnet's all-ones array (12 GiB at 1024^3) is never materialised
         else:
             coup = make_couplings(couplings, self.lattice_shape, self.n_neighbors, n_disorder, coupling_seq)
         self.couplings = coup
         self._sim = IsingSimulation(list(lattice_shape), coup, self.temperatures, n_replicas, neighbor_offsets,
-                                    self._constructor_dynamics_seed, layout=layout, device=device)
+                                    self._constructor_dynamics_seed, layout=layout, device=device, **engine_kwargs)
 
     def reset(self, seed=None):
         """Replay the constructor's dynamics, or a one-off seeded reset (spin_models.py:138-144)."""

@@ -321,3 +321,69 @@ def test_operator_entry_points_match_oracle(oracle):
                 lat.sweep_philox(spins[d], J[d], temps_full, ids[d], colour, key, 77, code, use_lookup=True,
                                  stream_is_slot=(layout == "msc"))
                 assert np.array_equal(gpu.get_spins(d), spins[d].reshape(-1)), (layout, kind, sweep_mode, d)
+
+
+# ---- slab layout: one 3-D ferromagnet with stride geometry, cut along x0 (single-GPU emulation of the ranks) ----
+SLAB_CASES = [
+    # shape, temps, ranks
+    ((4, 4, 8), [3.5, 4.51, 5.5], 1),
+    ((8, 6, 16), [4.0, 4.51], 2),
+    ((8, 6, 16), [4.0, 4.51], 4),
+    ((2, 2, 8), [4.51], 1),           # L = 2 along x0 and x1: fwd == bwd neighbour, both counted
+    ((12, 4, 24), [2.0, 4.51, 9.0], 3),
+]
+
+
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+@pytest.mark.parametrize("shape,temps,ranks", SLAB_CASES)
+def test_slab_layout_is_bit_exact(oracle, shape, temps, ranks, mode):
+    import peapods_b200 as pb
+
+    temps = np.asarray(temps, np.float32)
+    colour, n_colours = pb.colouring(shape)
+    assert n_colours == 2
+    gpu = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 4321, layout="slab", slab_ranks=ranks, slab_rank=-1)
+    assert gpu.layout == "slab" and gpu.n_local_spins == int(np.prod(shape))
+    J = np.ones(tuple(shape) + (3,), np.float32)
+    cpu = oracle.Sim(shape, J, temps, n_replicas=1, seed=4321, rng_mode=oracle.RNG_PHILOX, colour=colour)
+    assert_state_equal(gpu, cpu, 1)
+    for n_sweeps, interval in ((1, None), (2, None), (17, 1), (40, 3)):
+        kw = dict(warmup_ratio=0.25, pt_interval=interval, pt_schedule="full_ladder")
+        rg = gpu.sample(n_sweeps, mode, **kw)
+        rc = cpu.sample(n_sweeps, mode, **kw)
+        assert_state_equal(gpu, cpu, 1)
+        assert_results_equal(rg, rc)
+        assert np.array_equal(gpu.get_energies(0), cpu.energies(0))
+    gpu.reset()
+    cpu.reset()
+    assert_state_equal(gpu, cpu, 1)
+
+
+def test_slab_set_spins_and_operator_entry_points(oracle):
+    import peapods_b200 as pb
+
+    shape, temps = (4, 6, 8), np.asarray([4.51], np.float32)
+    gpu = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 5, layout="slab", slab_ranks=2, slab_rank=-1)
+    rng = np.random.default_rng(0)
+    spins = (2 * rng.integers(0, 2, size=int(np.prod(shape))) - 1).astype(np.int8)
+    gpu.set_spins(spins)
+    assert np.array_equal(gpu.get_spins(), spins)
+    e, m = gpu.op_energies_mags()
+    s3 = spins.reshape(shape).astype(np.int64)
+    bonds = sum(int((s3 * np.roll(s3, -1, axis=a)).sum()) for a in range(3))
+    assert m[0, 0] == int(s3.sum())
+    assert e[0, 0] == np.float32(bonds) / np.float32(s3.size)
+
+
+def test_slab_rejects_what_it_cannot_hold():
+    import peapods_b200 as pb
+
+    t = np.asarray([4.5], np.float32)
+    with pytest.raises(ValueError):
+        pb.IsingSimulation([4, 4, 6], "ferro", t, 1, None, 1, layout="slab")          # shape[2] % 8
+    with pytest.raises(ValueError):
+        pb.IsingSimulation([4, 4, 8], "ferro", t, 2, None, 1, layout="slab")          # replicas
+    with pytest.raises(ValueError):
+        pb.IsingSimulation([6, 4, 8], "ferro", t, 1, None, 1, layout="slab", slab_ranks=2, slab_rank=-1)  # 6 % 4
+    with pytest.raises(ValueError):
+        pb.IsingSimulation([4, 4, 8], np.ones((4, 4, 8, 3), np.float32), t, 1, None, 1, layout="slab")
