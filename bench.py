@@ -350,6 +350,119 @@ def run_ours(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# --workload c5: BASELINE configs[4], one 3-D ferromagnet at T_c cut into slabs over the ranks (strong scaling)
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+
+    from peapods_b200 import _lib
+    from peapods_b200.sharded import SlabIsingSimulation
+
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = args.c5_extent
+    shape = (L, L, L)
+    temps = np.asarray([4.511], dtype=np.float32)  # T_c of the 3-D Ising model (tests/utils.py:9 in the reference)
+    n_sweeps = args.sweeps_per_step
+    attempts_step = float(L) ** 3 * n_sweeps
+    kw = dict(warmup_ratio=0.25)
+    sim = SlabIsingSimulation(shape, temps, dynamics_seed())
+    for _ in range(args.warmup):
+        sim.sample(n_sweeps, "metropolis", **kw)
+    barrier()
+    dev_ms, launches = 0.0, 0
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.sample(n_sweeps, "metropolis", **kw)
+            dev_ms += sim.sim.last_sweep_loop_ms
+            launches += sim.sim.last_kernel_launches
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms, wall_ms = max_over_ranks(dev_ms), max_over_ranks(wall_ms)
+    value = attempts_step * args.steps / (dev_ms * 1e6)
+    res = sim.sample(n_sweeps, "metropolis", profile=True, **kw)
+    k_ms, k_n = max_over_ranks(sim.sim.last_sweep_kernel_ms), max(sim.sim.last_sweep_kernel_launches, 1)
+    peak, peak_src = peaks()
+    alg = 2.0 * attempts_step / world  # int8: one byte read + one written per attempt, per rank
+    achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic,
+                "kernel": "slab_sweep_kernel (all launches of one sample() call, halo waits included)", "peak_source": peak_src,
+                "alg_bytes_per_call_per_rank": alg, "sweep_kernel_ms": k_ms}
+    energy = float(res["energies"][0])
+    del sim
+
+    def e2e_step():
+        s = SlabIsingSimulation(shape, temps, dynamics_seed())
+        out = s.sample(n_sweeps, "metropolis", **kw)
+        nb = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray))
+        del s
+        return nb
+
+    for _ in range(max(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        d2h = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        Lc, nsw = 128, 4  # the reference runs one realization with one system on ONE core (mod.rs:874-885, parallel.rs:39)
+        o = oracle.Sim((Lc, Lc, Lc), np.ones((Lc, Lc, Lc, 3), np.float32), temps, n_replicas=1, seed=dynamics_seed(),
+                       rng_mode=oracle.RNG_XOSHIRO)
+        t0 = time.perf_counter()
+        o.sample(nsw, "metropolis", warmup_ratio=0.25, n_threads=1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": float(Lc) ** 3 * nsw / (dt * 1e9), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{Lc}^3 lattice x {nsw} sweeps ({dt:.1f} s): one system = one thread in the reference"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 (one byte per spin, SWAR neighbour counts; integer acceptance table)", "data": "synthetic",
+            "config": {"workload": f"C5: single 3-D Ising ferromagnet {L}^3 at T_c=4.511, checkerboard Metropolis, slab-decomposed along x0 "
+                                   f"over {world} GPU(s) with NCCL halo exchange", "lattice": list(shape), "n_temps": 1, "n_replicas": 1,
+                       "sweeps_per_step": n_sweeps, "warmup_ratio": 0.25, "layout": "slab (u8, stride geometry)",
+                       "l2": f"{L ** 3 / world / 2 ** 20:.0f} MiB of spins per GPU vs 126 MB L2"},
+            "e2e": {"value": attempts_step * args.steps / (e2e_ms * 1e6), "unit": UNIT, "h2d_bytes_per_step": int(temps.nbytes),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks.summary(), "roofline": roofline,
+            "cpu_baseline": cpu, "energy_per_spin_last_step": energy,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -360,9 +473,15 @@ def main():
     ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
+    ap.add_argument("--workload", choices=("c2", "c5"), default="c2", help="c2: BASELINE headline (default); c5: one large lattice in slabs")
+    ap.add_argument("--c5-extent", type=int, default=1024)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 0)
+    if args.workload == "c5" and args.impl == "ours":
+        if args.sweeps_per_step == 256:
+            args.sweeps_per_step = 32
+        return run_c5(args)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 

@@ -472,6 +472,8 @@ static pp_status slab_exchange(pp_sim *s, cudaStream_t stream) {
 static pp_status slab_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream, uint32_t sweep_index, int n_sweeps) {
     SlabState *sl = s->slab;
     const unsigned bx = blocks_for(sl->parts[0].chunks_per_plane, 256);
+    const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
+    for (SlabView &v : sl->parts) { v.k0 = (uint32_t)key; v.k1 = (uint32_t)(key >> 32); }
     for (int sw = 0; sw < n_sweeps; sw++)
         for (int colour = 0; colour < 2; colour++) {
             for (const SlabView &v : sl->parts) {  // boundary planes first: they are what the neighbours wait for
@@ -662,8 +664,12 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
     const int64_t DS = m.D * m.S;
     iota_sid_kernel<<<blocks_for(DS, 256), 256, 0, s->stream>>>(s->d_sid, DS, m.S);
     if (s->layout == PP_LAYOUT_SLAB) {
-        for (const SlabView &v : s->slab->parts)
+        const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
+        for (SlabView &v : s->slab->parts) {
+            v.k0 = (uint32_t)key;
+            v.k1 = (uint32_t)(key >> 32);
             slab_init_kernel<<<dim3(blocks_for(v.chunks_per_plane, 256), (unsigned)v.P, (unsigned)m.S), 256, 0, s->stream>>>(m, v);
+        }
         pp_status stx = slab_exchange(s, s->stream);
         if (stx != PP_OK) return stx;
     } else if (s->layout == PP_LAYOUT_MSC) {
@@ -849,6 +855,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             v.sys_stride = (int64_t)(sl->P + 2) * sl->plane;
             v.first_plane = (int64_t)(sl->rank < 0 ? i : sl->rank) * sl->P;
             v.chunks_per_plane = sl->plane / 8;
+            v.kpr_shift = -1;
+            for (int b = 0; b < 30; b++)
+                if ((sl->L2 >> 3) == (1 << b)) v.kpr_shift = b;
             uint8_t *buf = nullptr;
             CREATE_TRY(cudaMalloc((void **)&buf, (size_t)(m.S * v.sys_stride)));
             sl->buffers.push_back(buf);

@@ -27,7 +27,21 @@ struct SlabView {
     int64_t sys_stride;        // (P + 2) * plane
     int64_t first_plane;       // global x0 of local plane 1
     int64_t chunks_per_plane;  // L1 * L2 / 8
+    int kpr_shift;             // log2(L2 / 8) when that is a power of two, else -1
+    uint32_t k0, k1;           // Philox key of the realization (realization_seed(seed, sample_offset), set per launch)
 };
+
+// segment index inside a plane -> (row x1, segment k of the row)
+__device__ __forceinline__ void slab_split(const SlabView &v, const int64_t c, int &x1, int &k) {
+    const int kpr = v.L2 >> 3;
+    if (v.kpr_shift >= 0) {
+        x1 = (int)(c >> v.kpr_shift);
+        k = (int)c & (kpr - 1);
+    } else {
+        x1 = (int)((uint32_t)c / (uint32_t)kpr);
+        k = (int)c - x1 * kpr;
+    }
+}
 
 __device__ __forceinline__ uint64_t ld8(const uint8_t *p) {
     const uint2 v = *reinterpret_cast<const uint2 *>(p);
@@ -47,35 +61,35 @@ slab_sweep_kernel(ModelView m, SlabView v, int colour, uint32_t sweep_index, int
     const int pi = blockIdx.y;
     const int p = pi < na ? pa + pi : pb + (pi - na);
     const int kpr = v.L2 >> 3;
-    const int x1 = (int)(c / kpr), k = (int)(c - (int64_t)x1 * kpr);
+    int x1, k;
+    slab_split(v, c, x1, k);
     const uint32_t sys = (uint32_t)m.system_ids[slot];  // parallel.rs:27-33: spins by system, temperature by slot
-    uint8_t *base = v.spins + (int64_t)sys * v.sys_stride;
-    uint8_t *row = base + (int64_t)p * v.plane + (int64_t)x1 * v.L2;
+    uint8_t *row = v.spins + (int64_t)sys * v.sys_stride + (int64_t)p * v.plane + (int64_t)x1 * v.L2 + 8 * k;
     const int x1m = x1 ? x1 - 1 : v.L1 - 1, x1p = x1 + 1 == v.L1 ? 0 : x1 + 1;
-    const int64_t dym = (int64_t)(x1m - x1) * v.L2, dyp = (int64_t)(x1p - x1) * v.L2;
-    const uint64_t C = ld8(row + 8 * k);
-    const uint64_t Xm = ld8(row - v.plane + 8 * k), Xp = ld8(row + v.plane + 8 * k);
-    const uint64_t Ym = ld8(row + dym + 8 * k), Yp = ld8(row + dyp + 8 * k);
-    const int64_t gx0 = v.first_plane + p - 1;
-    const int off = (int)((colour ^ gx0 ^ x1) & 1);  // active sites of the segment: x2 = 8k + 2l + off
+    const uint64_t C = ld8(row);
+    const uint64_t Xm = ld8(row - v.plane), Xp = ld8(row + v.plane);
+    const uint64_t Ym = ld8(row + (int64_t)(x1m - x1) * v.L2), Yp = ld8(row + (int64_t)(x1p - x1) * v.L2);
+    const uint32_t gx0 = (uint32_t)(v.first_plane + p - 1);
+    const uint32_t off = (colour ^ gx0 ^ x1) & 1u;  // active sites of the segment: x2 = 8k + 2l + off
     // off = 0: site 0 needs the byte left of the segment; off = 1: site 7 needs the byte right of it
-    const int xe = off ? (8 * k + 8 == v.L2 ? 0 : 8 * k + 8) : (k ? 8 * k - 1 : v.L2 - 1);
+    const int xe = off ? (k + 1 == kpr ? 8 - v.L2 : 8) : (k ? -1 : v.L2 - 1);
     const uint64_t E = row[xe];
     const uint64_t left = (C << 8) | (off ? 0ull : E), right = (C >> 8) | (off ? E << 56 : 0ull);
     const uint64_t down = Xm + Xp + Ym + Yp + left + right;  // per byte: down-spin neighbours (<= 6, no carries)
-    const uint64_t q = ((uint64_t)gx0 * v.L1 + x1) * kpr + k;  // segment index = colour rank >> 2
-    const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
-    const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
-    uint64_t flips = 0;
+    const uint32_t q = (gx0 * (uint32_t)v.L1 + (uint32_t)x1) * (uint32_t)kpr + (uint32_t)k;  // segment index = colour rank >> 2
+    const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, v.k0, v.k1);
+    // bring the four active sites to the even bytes, then work on the two 32-bit halves with constant shifts
+    const uint64_t dsh = down >> (8 * off), csh = C >> (8 * off);
+    const uint32_t d2[2] = {(uint32_t)dsh, (uint32_t)(dsh >> 32)}, c2[2] = {(uint32_t)csh, (uint32_t)(csh >> 32)};
+    uint32_t f2[2] = {0u, 0u};
 #pragma unroll
     for (int l = 0; l < 4; l++) {
-        const int sh = 8 * (2 * l + off);
-        const uint32_t nd = (uint32_t)(down >> sh) & 0xFFu, sb = (uint32_t)(C >> sh) & 1u;
+        const uint32_t nd = (d2[l >> 1] >> (16 * (l & 1))) & 0xFFu, sb = (c2[l >> 1] >> (16 * (l & 1))) & 1u;
         const uint32_t unsat = sb ? 6u - nd : nd;  // ferromagnet: a bond is unsatisfied iff the two spins differ
-        if ((pick(o, l) >> 8) < thr[unsat]) flips |= 1ull << sh;  // sweep.rs:182-184
+        if ((pick(o, l) >> 8) < thr[unsat]) f2[l >> 1] |= 1u << (16 * (l & 1));  // sweep.rs:182-184
     }
-    const uint64_t out = C ^ flips;
-    *reinterpret_cast<uint2 *>(row + 8 * k) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
+    const uint64_t out = C ^ (((uint64_t)f2[0] | ((uint64_t)f2[1] << 32)) << (8 * off));
+    *reinterpret_cast<uint2 *>(row) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
 }
 
 // K0: spin -1 iff the INIT-domain draw < 2^23 (realization.rs:180); grid = (chunk blocks, P, S)
@@ -84,12 +98,11 @@ __global__ void __launch_bounds__(256) slab_init_kernel(ModelView m, SlabView v)
     if (c >= v.chunks_per_plane) return;
     const int p = blockIdx.y + 1;
     const uint32_t sys = blockIdx.z;
-    const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
     const uint64_t seg = ((uint64_t)(v.first_plane + p - 1)) * v.chunks_per_plane + c;  // global site index >> 3
     uint64_t out = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const u32x4 o = philox4x32_10((uint32_t)(2 * seg + h), 0u, sys, TAG_INIT, (uint32_t)key, (uint32_t)(key >> 32));
+        const u32x4 o = philox4x32_10((uint32_t)(2 * seg + h), 0u, sys, TAG_INIT, v.k0, v.k1);
 #pragma unroll
         for (int l = 0; l < 4; l++)
             if ((pick(o, l) >> 8) < (1u << 23)) out |= 1ull << (8 * (4 * h + l));
@@ -107,8 +120,8 @@ __global__ void __launch_bounds__(256) slab_energy_kernel(SlabView v, unsigned l
     const uint32_t sys = blockIdx.z;
     long long unsat = 0, dn = 0;
     if (c < v.chunks_per_plane) {
-        const int kpr = v.L2 >> 3;
-        const int x1 = (int)(c / kpr), k = (int)(c - (int64_t)x1 * kpr);
+        int x1, k;
+        slab_split(v, c, x1, k);
         const uint8_t *row = v.spins + (int64_t)sys * v.sys_stride + (int64_t)p * v.plane + (int64_t)x1 * v.L2;
         const int x1p = x1 + 1 == v.L1 ? 0 : x1 + 1;
         const uint64_t C = ld8(row + 8 * k), Xp = ld8(row + v.plane + 8 * k), Yp = ld8(row + (int64_t)(x1p - x1) * v.L2 + 8 * k);

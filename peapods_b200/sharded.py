@@ -106,3 +106,59 @@ class ShardedIsingSimulation:
         """Every rank samples its block; rank 0 returns the merged dict, the others None."""
         local = self.sim.sample(*args, **kwargs)
         return gather_merge(local, self.sim.last_per_sample_means, self.n_replicas)
+
+
+def slab_plan(extent0: int, world: int, rank: int):
+    """(first plane, planes) of rank ``rank`` when a lattice of ``extent0`` planes is cut into ``world`` slabs
+    (pp_slab.cuh: equal slabs with an even number of planes each, so the checkerboard colour survives the cut)."""
+    if extent0 % (2 * world) != 0:
+        raise ValueError(f"shape[0]={extent0} must be a multiple of 2 * {world} ranks")
+    planes = extent0 // world
+    return rank * planes, planes
+
+
+def broadcast_token(make_token, group=None, n_bytes=128):
+    """Rank 0 calls ``make_token()`` (-> ``n_bytes`` bytes); every rank returns the same bytes (NCCL or gloo group)."""
+    import torch
+    import torch.distributed as dist
+
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    buf = torch.zeros(n_bytes, dtype=torch.uint8, device=dev)
+    if dist.get_rank(group) == 0:
+        buf.copy_(torch.frombuffer(bytearray(make_token()), dtype=torch.uint8))
+    dist.broadcast(buf, src=0, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+class SlabIsingSimulation:
+    """ONE 3-D ferromagnet cut along dimension 0 over the ranks of the initialized ``torch.distributed`` group (one
+    process per GPU; BASELINE config 5).  Rank 0 creates the NCCL bootstrap token, ``torch.distributed`` broadcasts
+    its 128 bytes (plumbing only), and the engine itself exchanges halo planes with ncclSend / ncclRecv, overlapped with
+    the interior update (pp_slab.cuh).  Every rank replays the same parallel-tempering decisions from the all-reduced
+    integer energies, so ``sample()`` returns the same dict on every rank; ``get_spins()`` returns this rank's planes."""
+
+    def __init__(self, lattice_shape, temperatures, seed=None, *, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from ._core import IsingSimulation, nccl_unique_id
+
+        live = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if live else 0
+        self.world = dist.get_world_size(group) if live else 1
+        self.first_plane, self.planes = slab_plan(int(lattice_shape[0]), self.world, self.rank)
+        token = broadcast_token(nccl_unique_id, group) if self.world > 1 else None
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.sim = IsingSimulation(list(lattice_shape), "ferro", temperatures, 1, None, seed, layout="slab", device=device,
+                                   slab_ranks=self.world, slab_rank=self.rank if self.world > 1 else 0, nccl_unique_id=token)
+
+    def sample(self, *args, **kwargs):
+        return self.sim.sample(*args, **kwargs)
+
+    def get_spins(self):
+        return self.sim.get_spins(0)
+
+    def reset(self, seed=None):
+        self.sim.reset(seed)

@@ -82,3 +82,39 @@ def test_two_gloo_ranks_reproduce_the_unsharded_run(tmp_path):
         assert np.array_equal(merged[k], ref[k]), k
     for k, v in ref["per_disorder"]["parallel_tempering"].items():
         assert np.array_equal(merged["pt_" + k], v), k
+
+
+# ---- slab decomposition of one lattice: host-side plan and NCCL-token plumbing (the halo exchange itself is NCCL on
+# GPUs: tests/test_gpu_parity.py emulates the ranks on one device, tools/slab_check.py runs real ranks) ----
+def test_slab_plan_cuts_even_slabs():
+    import pytest
+
+    sys.path.insert(0, str(ROOT))
+    from peapods_b200.sharded import slab_plan
+
+    assert [slab_plan(1024, 8, r) for r in range(8)] == [(128 * r, 128) for r in range(8)]
+    assert slab_plan(8, 2, 1) == (4, 4)
+    with pytest.raises(ValueError):
+        slab_plan(12, 4, 0)   # 3 planes per slab: odd, the colour of a site would depend on the cut
+
+
+def _token_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from peapods_b200.sharded import broadcast_token
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    token = broadcast_token(lambda: bytes(range(128)), None)
+    Path(out_dir, f"token{rank}.bin").write_bytes(token)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_share_the_bootstrap_token(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_token_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "token0.bin").read_bytes() == (tmp_path / "token1.bin").read_bytes() == bytes(range(128))
