@@ -23,6 +23,7 @@
 #include "pp_kernels_int8.cuh"
 #include "pp_kernels_msc.cuh"
 #include "pp_kernels_msc3d.cuh"
+#include "pp_kernels_rows.cuh"
 #include "pp_kernels_stats.cuh"
 #include "pp_plan.h"
 #include "pp_slab.cuh"
@@ -192,6 +193,11 @@ struct pp_sim {
     std::vector<cudaStream_t> xstreams;
     std::vector<cudaEvent_t> xevents;
     SlabState *slab = nullptr;                         // PP_LAYOUT_SLAB (pp_slab.cuh)
+    bool rows = false;                                 // int8 layout through the per-row stride tables (pp_kernels_rows.cuh)
+    RowsView rv{};
+    std::vector<void *> rows_bufs;
+    std::vector<uint32_t> rows_class_start;
+    uint64_t *d_keys = nullptr;
     // measurement hook: event pairs around sweep-kernel launches
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
@@ -242,6 +248,8 @@ static void free_sim(pp_sim *s) {
     for (void *p : ptrs)
         if (p) pool_free(s, p);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void *b : s->rows_bufs) pool_free(s, b);
+    if (s->d_keys) pool_free(s, s->d_keys);
     if (s->slab) {
         SlabState *sl = s->slab;
         if (sl->comm_stream) cudaStreamSynchronize(sl->comm_stream);
@@ -556,6 +564,28 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
         return PP_OK;
     }
     if (n_sweeps > 0) prof_mark(s, c.stream);
+    if (s->rows) {
+        RowsView v = s->rv;
+        v.keys = s->d_keys + (c.m.sample_offset - s->mv.sample_offset);
+        const size_t smem = m.coupling_class == COUP_F32 ? 0 : sizeof(uint32_t) * (size_t)m.T * (4 * m.z + 1);
+        const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
+        for (int sw = 0; sw < n_sweeps; sw++)
+            for (int col = 0; col < m.n_colours; col++) {
+                const int cls = col % v.m_half;
+                const uint32_t nseg = (s->rows_class_start[(size_t)cls + 1] - s->rows_class_start[(size_t)cls]) * (uint32_t)v.kpr;
+                dim3 grid((unsigned)(m.D * sblocks), blocks_for(nseg, 128));
+#define PP_ROWS(C_, Z_) rows_sweep_kernel<C_, Z_><<<grid, 128, smem, c.stream>>>(m, v, col, sweep_index + sw, sweep_mode, exact_log)
+                if (m.coupling_class == COUP_FERRO) { if (m.z == 2) PP_ROWS(COUP_FERRO, 2); else if (m.z == 3) PP_ROWS(COUP_FERRO, 3); else PP_ROWS(COUP_FERRO, 0); }
+                else if (m.coupling_class == COUP_UNIT) { if (m.z == 2) PP_ROWS(COUP_UNIT, 2); else if (m.z == 3) PP_ROWS(COUP_UNIT, 3); else PP_ROWS(COUP_UNIT, 0); }
+                else { if (m.z == 2) PP_ROWS(COUP_F32, 2); else if (m.z == 3) PP_ROWS(COUP_F32, 3); else PP_ROWS(COUP_F32, 0); }
+#undef PP_ROWS
+                s->launches++;
+            }
+        if (n_sweeps > 0) prof_mark(s, c.stream);
+        CUDA_TRY(cudaGetLastError());
+        if (want_energy) return launch_energy(s, c, want_mags);
+        return PP_OK;
+    }
     for (int sw = 0; sw < n_sweeps; sw++) {
         for (int col = 0; col < m.n_colours; col++) {
             const uint32_t nsite = s->plan.colour_start[col + 1] - s->plan.colour_start[col];
@@ -585,6 +615,16 @@ static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
     if (s->layout == PP_LAYOUT_MSC) return launch_sweeps(s, c, PP_SWEEP_METROPOLIS, 0, 0, 0, true, want_mags);
     if (s->layout == PP_LAYOUT_SLAB) return slab_energy(s, m, c.stream, want_mags);
     const unsigned grid = (unsigned)(m.D * m.S);
+    if (s->rows) {
+        switch (m.coupling_class) {
+            case COUP_FERRO: rows_energy_kernel<COUP_FERRO><<<grid, 256, 0, c.stream>>>(m, s->rv, want_mags); break;
+            case COUP_UNIT: rows_energy_kernel<COUP_UNIT><<<grid, 256, 0, c.stream>>>(m, s->rv, want_mags); break;
+            default: rows_energy_kernel<COUP_F32><<<grid, 256, 0, c.stream>>>(m, s->rv, want_mags);
+        }
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return PP_OK;
+    }
     switch (m.coupling_class) {
         case COUP_FERRO: energy_mag_int8_kernel<COUP_FERRO><<<grid, 256, 0, c.stream>>>(m, want_mags); break;
         case COUP_UNIT: energy_mag_int8_kernel<COUP_UNIT><<<grid, 256, 0, c.stream>>>(m, want_mags); break;
@@ -604,6 +644,8 @@ static pp_status launch_overlap(pp_sim *s, Ctx &c) {
     }
     if (s->layout == PP_LAYOUT_MSC)
         msc_overlap_kernel<<<(unsigned)(c.G * m.P * m.T), MSC_BLOCK, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
+    else if (s->rows)
+        rows_overlap_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, c.stream>>>(m, s->rv, c.dot_spin, c.dot_link);
     else
         overlap_dots_int8_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
     s->launches++;
@@ -662,6 +704,12 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
     s->next_parity = 0;
     ModelView m = s->mv;
     const int64_t DS = m.D * m.S;
+    if (s->rows) {
+        std::vector<uint64_t> keys((size_t)m.D);
+        for (int64_t d = 0; d < m.D; d++) keys[(size_t)d] = realization_seed(seed, (uint64_t)(m.sample_offset + d));
+        CUDA_TRY(cudaMemcpyAsync(s->d_keys, keys.data(), sizeof(uint64_t) * keys.size(), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
     iota_sid_kernel<<<blocks_for(DS, 256), 256, 0, s->stream>>>(s->d_sid, DS, m.S);
     if (s->layout == PP_LAYOUT_SLAB) {
         const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
@@ -906,6 +954,30 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         }
         if (m.coupling_class != COUP_F32 && s->d_Jf) { pool_free(s, s->d_Jf); s->d_Jf = nullptr; }
         CREATE_TRY(pool_alloc(s, (void **)&s->d_spins, (size_t)(m.D * m.S * N)));
+        // per-row stride tables (pp_kernels_rows.cuh) whenever the colouring alternates along the rows
+        const RowsPlan rp = getenv("PP_NO_ROWS") ? RowsPlan() : rows_plan(s->plan);
+        if (rp.ok && N % 8 == 0 && z <= 16) {
+            auto up = [&](const void *src, size_t bytes, const void **dst) -> cudaError_t {
+                void *p = nullptr;
+                cudaError_t e = pool_alloc(s, &p, bytes);
+                if (e != cudaSuccess) return e;
+                s->rows_bufs.push_back(p);
+                *dst = p;
+                return cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+            };
+            RowsView &v = s->rv;
+            v.L = rp.L; v.kpr = rp.kpr; v.kpr_shift = rp.kpr_shift; v.m_half = rp.m_half; v.n_rows = rp.n_rows;
+            CREATE_TRY(up(rp.row_a.data(), rp.row_a.size(), (const void **)&v.row_a));
+            CREATE_TRY(up(rp.row_ord.data(), rp.row_ord.size() * 4, (const void **)&v.row_ord));
+            CREATE_TRY(up(rp.nbr_row.data(), rp.nbr_row.size() * 4, (const void **)&v.nbr_row));
+            CREATE_TRY(up(rp.dl.data(), rp.dl.size() * 4, (const void **)&v.dl));
+            CREATE_TRY(up(rp.class_rows.data(), rp.class_rows.size() * 4, (const void **)&v.class_rows));
+            CREATE_TRY(up(rp.class_start.data(), rp.class_start.size() * 4, (const void **)&v.class_start));
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_keys, sizeof(uint64_t) * (size_t)m.D));
+            v.keys = s->d_keys;
+            s->rows_class_start = rp.class_start;
+            s->rows = true;
+        }
     }
     m.J8 = s->d_J8;
     m.Jf = s->d_Jf;

@@ -1,0 +1,354 @@
+// pp_kernels_rows.cuh — int8 layout without per-site tables: geometry lowered to per-ROW stride tables.
+//
+// The table-driven kernels (pp_kernels_int8.cuh) read 2z' neighbour indices per attempt and touch spins one byte at a
+// time; ncu shows them bound by the L1 load pipe at 150-230 instructions per attempt.  Whenever the colouring is
+// c(x) = (sum_d a_d x_d) mod m with a_last = m/2 (hypercubic checkerboard, the 4-colour triangular colouring, ...)
+// and the last extent is a multiple of 8, the colour classes alternate along a row, so
+//   * a thread owns the 8 consecutive sites of one row segment: its four active sites are the bytes of one parity,
+//     their colour ranks are 4 consecutive numbers (= one Philox call, RNG-SPEC), rank >> 2 = row_ordinal * L/8 + segment;
+//   * the neighbour in direction k of all 8 sites is one (possibly shifted) 8-byte load from row nbr_row[row][k]:
+//     per-row tables of O(rows * z') entries replace the O(N * z') site tables (lattice.rs:63-82);
+//   * ferromagnets count down-spin neighbours of all 8 sites with 2z' 64-bit adds (SWAR); fp32 / +-1 couplings walk the
+//     four active sites in the reference's order (sweep.rs:8-19), a thread reusing its coupling registers over
+//     ROWS_NS systems of the same realization.
+// Replaces the same reference functions as pp_kernels_int8.cuh; results are bit-identical to those kernels.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pp_device.cuh"
+#include "pp_plan.h"
+
+namespace pp {
+
+constexpr int ROWS_NS = 4;  // systems a sweep thread walks with one set of coupling registers
+
+struct RowsView {
+    int L;                       // last extent
+    int kpr;                     // segments per row = L / 8
+    int kpr_shift;               // log2(kpr) or -1
+    int m_half;                  // m / 2: rows of class (A mod m_half) hold the colours A and A + m_half
+    int64_t n_rows;
+    const uint8_t *row_a;        // [rows] A = sum_{d<last} a_d x_d mod m
+    const uint32_t *row_ord;     // [rows] number of earlier rows of the same class
+    const uint32_t *nbr_row;     // [rows][2z] row of the forward / backward neighbour in direction k
+    const int32_t *dl;           // [z] last-dimension component of offset k
+    const uint32_t *class_rows;  // rows sorted by class
+    const uint32_t *class_start; // [m_half + 1]
+    const uint64_t *keys;        // [D] realization_seed(seed, sample_offset + d)
+};
+
+struct RowsPlan {
+    bool ok = false;
+    int L = 0, kpr = 0, kpr_shift = -1, m_half = 0;
+    int64_t n_rows = 0;
+    std::vector<uint8_t> row_a;
+    std::vector<uint32_t> row_ord, nbr_row, class_rows, class_start;
+    std::vector<int32_t> dl;
+};
+
+// host: per-row tables from the plan's linear colouring (pp_plan.h)
+inline RowsPlan rows_plan(const LatticePlan &p) {
+    RowsPlan q;
+    const int n = p.n_dims;
+    if (!p.linear_colouring || n < 1) return q;
+    const int m = p.colour_mod;
+    if (m % 2 != 0 || p.colour_coef[(size_t)n - 1] != m / 2) return q;
+    const int64_t L = p.shape[(size_t)n - 1];
+    if (L % 8 != 0) return q;
+    for (int k = 0; k < p.z; k++)
+        if (std::abs((long long)p.offsets[(size_t)k * n + n - 1]) >= L) return q;
+    q.L = (int)L;
+    q.kpr = (int)(L / 8);
+    for (int b = 0; b < 30; b++)
+        if (q.kpr == (1 << b)) q.kpr_shift = b;
+    q.m_half = m / 2;
+    q.n_rows = p.n_spins / L;
+    q.row_a.resize((size_t)q.n_rows);
+    q.row_ord.resize((size_t)q.n_rows);
+    q.nbr_row.resize((size_t)q.n_rows * 2 * p.z);
+    q.dl.resize((size_t)p.z);
+    for (int k = 0; k < p.z; k++) q.dl[(size_t)k] = (int32_t)p.offsets[(size_t)k * n + n - 1];
+    std::vector<uint32_t> seen((size_t)q.m_half, 0);
+    std::vector<int64_t> x((size_t)std::max(n - 1, 1), 0);
+    for (int64_t r = 0; r < q.n_rows; r++) {
+        int64_t rem = r, a = 0;
+        for (int d = n - 2; d >= 0; d--) { x[(size_t)d] = rem % p.shape[(size_t)d]; rem /= p.shape[(size_t)d]; }
+        for (int d = 0; d < n - 1; d++) a += p.colour_coef[(size_t)d] * x[(size_t)d];
+        q.row_a[(size_t)r] = (uint8_t)(a % m);
+        q.row_ord[(size_t)r] = seen[(size_t)(a % q.m_half)]++;
+        for (int k = 0; k < p.z; k++)
+            for (int sgn = 0; sgn < 2; sgn++) {
+                int64_t row = 0;
+                for (int d = 0; d < n - 1; d++) {
+                    const int64_t c = rem_euclid(x[(size_t)d] + (sgn ? -1 : 1) * p.offsets[(size_t)k * n + d], p.shape[(size_t)d]);
+                    row = row * p.shape[(size_t)d] + c;
+                }
+                q.nbr_row[((size_t)r * p.z + k) * 2 + sgn] = (uint32_t)row;
+            }
+    }
+    q.class_start.assign((size_t)q.m_half + 1, 0);
+    for (int64_t r = 0; r < q.n_rows; r++) q.class_start[(size_t)(q.row_a[(size_t)r] % q.m_half) + 1]++;
+    for (int c = 0; c < q.m_half; c++) q.class_start[(size_t)c + 1] += q.class_start[(size_t)c];
+    q.class_rows.resize((size_t)q.n_rows);
+    std::vector<uint32_t> fill(q.class_start.begin(), q.class_start.end() - 1);
+    for (int64_t r = 0; r < q.n_rows; r++) q.class_rows[fill[(size_t)(q.row_a[(size_t)r] % q.m_half)]++] = (uint32_t)r;
+    q.ok = true;
+    return q;
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t rows_ld8(const int8_t *p) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    return (uint64_t)v.x | ((uint64_t)v.y << 32);
+}
+
+// bytes j = 0..7: spin at x_last = (8k + j + shift) mod L of row `row` (shift = +-dl of the direction)
+__device__ __forceinline__ uint64_t rows_shifted(const int8_t *row, const int L, const int k, const int shift) {
+    if (shift == 0) return rows_ld8(row + 8 * k);
+    int start = 8 * k + shift;
+    start -= (start >= L) ? L : 0;
+    start += (start < 0) ? L : 0;
+    const int c0 = start >> 3, sh = (start & 7) * 8;
+    const int c1 = (c0 + 1) * 8 == L ? 0 : c0 + 1;
+    const uint64_t lo = rows_ld8(row + 8 * c0);
+    if (sh == 0) return lo;
+    const uint64_t hi = rows_ld8(row + 8 * c1);
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
+__device__ __forceinline__ void rows_split(const RowsView &v, const uint32_t ci, uint32_t &ri, int &k) {
+    if (v.kpr_shift >= 0) {
+        ri = ci >> v.kpr_shift;
+        k = (int)(ci & (uint32_t)(v.kpr - 1));
+    } else {
+        ri = ci / (uint32_t)v.kpr;
+        k = (int)(ci - ri * (uint32_t)v.kpr);
+    }
+}
+
+// One colour class of one sweep.  grid = (D * ceil(S / ROWS_NS), segment blocks); a thread owns one row segment and
+// walks ROWS_NS slots of one realization.  ZT > 0: the number of forward directions is the compile-time constant ZT
+// (everything stays in registers); ZT = 0: any z' <= 16.
+template <int CLASS, int ZT>
+__global__ void __launch_bounds__(128)
+rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int sweep_mode, int exact_log) {
+    extern __shared__ uint32_t lut_sm[];  // FERRO / UNIT: [T][4z + 1] acceptance counts
+    constexpr int ZA = ZT > 0 ? ZT : 16;
+    const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1;
+    if (CLASS != COUP_F32) {
+        for (int i = threadIdx.x; i < m.T * width; i += blockDim.x) lut_sm[i] = m.lut[i];
+        __syncthreads();
+    }
+    const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
+    const int64_t d = blockIdx.x / sblocks;
+    const int slot0 = (int)(blockIdx.x % sblocks) * ROWS_NS;
+    const int cls = colour % v.m_half;
+    const uint32_t n_cls = v.class_start[cls + 1] - v.class_start[cls];
+    const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x;
+    if (ci >= n_cls * (uint32_t)v.kpr) return;
+    uint32_t ri;
+    int k;
+    rows_split(v, ci, ri, k);
+    const uint32_t r = v.class_rows[v.class_start[cls] + ri];
+    const int off = (int)v.row_a[r] == colour ? 0 : 1;  // active sites: x_last = 8k + 2l + off
+    const uint32_t q = v.row_ord[r] * (uint32_t)v.kpr + (uint32_t)k;  // colour rank >> 2
+    const uint64_t key = v.keys[d];
+    const int L = v.L;
+    const int64_t row_off = (int64_t)r * L;
+    int64_t nrf[ZA], nrb[ZA];  // byte offsets of the forward / backward neighbour rows
+    int dls[ZA];
+#pragma unroll
+    for (int kk = 0; kk < ZA; kk++) {
+        if (kk < z) {
+            nrf[kk] = (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L;
+            nrb[kk] = (int64_t)v.nbr_row[((size_t)r * z + kk) * 2 + 1] * L;
+            dls[kk] = v.dl[kk];
+        }
+    }
+    // fp32 / +-1 couplings of the four active sites, reference order: direction-major, forward then backward
+    float Jf[CLASS == COUP_F32 ? 4 : 1][CLASS == COUP_F32 ? 2 * ZA : 1];
+    int Ji[CLASS == COUP_UNIT ? 4 : 1][CLASS == COUP_UNIT ? 2 * ZA : 1];
+    if (CLASS != COUP_FERRO) {
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const int xl = 8 * k + 2 * l + off;
+            const int64_t i = row_off + xl;
+#pragma unroll
+            for (int kk = 0; kk < ZA; kk++) {
+                if (kk < z) {
+                    int xb = xl - dls[kk];
+                    xb -= (xb >= L) ? L : 0;
+                    xb += (xb < 0) ? L : 0;
+                    const int64_t jb = nrb[kk] + xb;
+                    if (CLASS == COUP_F32) {
+                        const float *J = m.Jf + (size_t)d * m.N * z;
+                        Jf[l][2 * kk] = J[(size_t)i * z + kk];
+                        Jf[l][2 * kk + 1] = J[(size_t)jb * z + kk];
+                    } else {
+                        const int8_t *J = m.J8 + (size_t)d * m.N * z;
+                        Ji[l][2 * kk] = J[(size_t)i * z + kk];
+                        Ji[l][2 * kk + 1] = J[(size_t)jb * z + kk];
+                    }
+                }
+            }
+        }
+    }
+    for (int ss = 0; ss < ROWS_NS; ss++) {
+        const int slot = slot0 + ss;
+        if (slot >= m.S) break;
+        const uint32_t sys = (uint32_t)m.system_ids[d * m.S + slot];  // parallel.rs:27-33
+        const int t = slot % m.T;                                     // realization.rs:166
+        int8_t *s = m.spins + (d * m.S + sys) * m.N;
+        const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
+        const uint64_t C = rows_ld8(s + row_off + 8 * k);
+        uint64_t F[ZA], B[ZA];  // byte j: the forward / backward neighbour of site j in direction kk
+#pragma unroll
+        for (int kk = 0; kk < ZA; kk++) {
+            if (kk < z) {
+                F[kk] = rows_shifted(s + nrf[kk], L, k, dls[kk]);
+                B[kk] = rows_shifted(s + nrb[kk], L, k, -dls[kk]);
+            }
+        }
+        uint64_t flips = 0;  // byte j = 0xFE where site j flips (+1 = 0x01 <-> -1 = 0xFF)
+        if (CLASS == COUP_FERRO) {
+            uint64_t down = 0;  // per byte: number of down-spin neighbours
+#pragma unroll
+            for (int kk = 0; kk < ZA; kk++)
+                if (kk < z) down += ((F[kk] >> 1) & 0x0101010101010101ull) + ((B[kk] >> 1) & 0x0101010101010101ull);
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const int sh = 8 * (2 * l + off);
+                const int nd = (int)((down >> sh) & 0xFFu);
+                const bool dn = ((C >> sh) & 0x80u) != 0;
+                const int idx = dn ? 4 * z - 2 * nd : 2 * nd;  // ec + 2z' with ec = -s h, h = 2z' - 2 nd (sweep.rs:178)
+                if ((pick(o, l) >> 8) < lut_sm[t * width + idx]) flips |= 0xFEull << sh;
+            }
+        } else {
+            const float temp = m.temps[t];
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const int sh = 8 * (2 * l + off);
+                const int si = (int)(int8_t)((C >> sh) & 0xFFu);
+                const uint32_t draw = pick(o, l) >> 8;
+                float h = 0.0f;
+                int hi = 0;
+#pragma unroll
+                for (int kk = 0; kk < ZA; kk++) {
+                    if (kk < z) {
+                        const int sf = (int)(int8_t)((F[kk] >> sh) & 0xFFu), sb = (int)(int8_t)((B[kk] >> sh) & 0xFFu);
+                        if (CLASS == COUP_F32) {  // sweep.rs:10-17: forward then backward, no fused multiply-add
+                            h = __fadd_rn(h, __fmul_rn((float)sf, Jf[l][2 * kk]));
+                            h = __fadd_rn(h, __fmul_rn((float)sb, Jf[l][2 * kk + 1]));
+                        } else {
+                            hi += sf * Ji[l][2 * kk] + sb * Ji[l][2 * kk + 1];
+                        }
+                    }
+                }
+                bool flip;
+                if (CLASS == COUP_F32) {
+                    const float eng_change = __fmul_rn(-(float)si, h);  // sweep.rs:43-44
+                    const float u = (float)draw * (1.0f / 16777216.0f);
+                    float lg;
+                    if (sweep_mode == 0)
+                        lg = exact_log ? m.logtab[draw] : logf(u);  // sweep.rs:256
+                    else
+                        lg = exact_log ? m.glogtab[draw] : logf(__fdiv_rn(u, __fsub_rn(1.0f, u)));  // sweep.rs:279-282
+                    flip = eng_change >= __fmul_rn(__fdiv_rn(temp, 2.0f), lg);
+                } else {
+                    flip = draw < lut_sm[t * width + (-si * hi) + 2 * z];  // sweep.rs:178-184
+                }
+                if (flip) flips |= 0xFEull << sh;
+            }
+        }
+        const uint64_t out = C ^ flips;
+        *reinterpret_cast<uint2 *>(s + row_off + 8 * k) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
+    }
+}
+
+// energies (+ magnetisation sums): grid = (D * S, 1); a block strides over the row segments of one system.
+template <int CLASS>
+__global__ void __launch_bounds__(256) rows_energy_kernel(ModelView m, RowsView v, int want_mags) {
+    __shared__ long long sh_ll[32];
+    __shared__ double sh_d[32];
+    const int64_t sysg = blockIdx.x;
+    const int64_t d = sysg / m.S;
+    const int8_t *s = m.spins + sysg * m.N;
+    const int z = m.z, L = v.L;
+    const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);
+    long long unsat = 0, dn = 0, acc_i = 0;
+    double acc_f = 0.0;
+    for (uint32_t ci = threadIdx.x; ci < n_seg; ci += blockDim.x) {
+        uint32_t r;
+        int k;
+        rows_split(v, ci, r, k);
+        const uint64_t C = rows_ld8(s + (int64_t)r * L + 8 * k);
+        dn += __popcll(C & 0x8080808080808080ull);
+        for (int kk = 0; kk < z; kk++) {  // energy.rs:99-107: forward bonds only, each bond once
+            const uint64_t f = rows_shifted(s + (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L, L, k, v.dl[kk]);
+            if (CLASS == COUP_FERRO) {
+                unsat += __popcll((C ^ f) & 0x8080808080808080ull);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int si = (int)(int8_t)((C >> (8 * j)) & 0xFFu), sf = (int)(int8_t)((f >> (8 * j)) & 0xFFu);
+                    const size_t jidx = ((size_t)d * m.N + (size_t)r * L + 8 * k + j) * z + kk;
+                    if (CLASS == COUP_UNIT) acc_i += si * sf * m.J8[jidx];
+                    else acc_f += (double)((float)(si * sf) * m.Jf[jidx]);
+                }
+            }
+        }
+    }
+    if (CLASS == COUP_F32) {
+        const double tot = block_sum<double>(acc_f, sh_d);
+        if (threadIdx.x == 0) m.energies[sysg] = __fdiv_rn((float)tot, (float)m.N);
+    } else if (CLASS == COUP_FERRO) {
+        const long long tu = block_sum<long long>(unsat, sh_ll);
+        if (threadIdx.x == 0) m.energies[sysg] = __fdiv_rn((float)((long long)z * m.N - 2 * tu), (float)m.N);
+    } else {
+        const long long tot = block_sum<long long>(acc_i, sh_ll);
+        if (threadIdx.x == 0) m.energies[sysg] = __fdiv_rn((float)tot, (float)m.N);
+    }
+    if (want_mags) {
+        const long long td = block_sum<long long>(dn, sh_ll);
+        if (threadIdx.x == 0) m.mags[sysg] = m.N - 2 * td;
+    }
+}
+
+// integer overlap dots (overlap.rs:259-281): one block per (realization, pair, temperature slot)
+__global__ void __launch_bounds__(256) rows_overlap_kernel(ModelView m, RowsView v, long long *dot_spin, long long *dot_link) {
+    __shared__ long long sh[32];
+    const int64_t idx = blockIdx.x;  // (d*P + p)*T + t
+    const int t = (int)(idx % m.T);
+    const int p = (int)((idx / m.T) % m.P);
+    const int64_t d = idx / ((int64_t)m.T * m.P);
+    const int sa = m.system_ids[d * m.S + (2 * p) * m.T + t];
+    const int sb = m.system_ids[d * m.S + (2 * p + 1) * m.T + t];
+    const int8_t *a = m.spins + (d * m.S + sa) * m.N;
+    const int8_t *b = m.spins + (d * m.S + sb) * m.N;
+    const int z = m.z, L = v.L;
+    const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);
+    long long neg_q = 0, neg_l = 0;  // sites with q_i = -1, links with q_i q_j = -1
+    for (uint32_t ci = threadIdx.x; ci < n_seg; ci += blockDim.x) {
+        uint32_t r;
+        int k;
+        rows_split(v, ci, r, k);
+        const int64_t o = (int64_t)r * L + 8 * k;
+        const uint64_t x = rows_ld8(a + o) ^ rows_ld8(b + o);  // sign bit set where the replicas differ
+        neg_q += __popcll(x & 0x8080808080808080ull);
+        for (int kk = 0; kk < z; kk++) {
+            const int64_t nro = (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L;
+            const uint64_t xf = rows_shifted(a + nro, L, k, v.dl[kk]) ^ rows_shifted(b + nro, L, k, v.dl[kk]);
+            neg_l += __popcll((x ^ xf) & 0x8080808080808080ull);
+        }
+    }
+    const long long tq = block_sum<long long>(neg_q, sh);
+    const long long tl = block_sum<long long>(neg_l, sh);
+    if (threadIdx.x == 0) {
+        dot_spin[idx] = m.N - 2 * tq;
+        dot_link[idx] = (long long)z * m.N - 2 * tl;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace pp

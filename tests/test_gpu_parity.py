@@ -387,3 +387,38 @@ def test_slab_rejects_what_it_cannot_hold():
         pb.IsingSimulation([6, 4, 8], "ferro", t, 1, None, 1, layout="slab", slab_ranks=2, slab_rank=-1)  # 6 % 4
     with pytest.raises(ValueError):
         pb.IsingSimulation([4, 4, 8], np.ones((4, 4, 8, 3), np.float32), t, 1, None, 1, layout="slab")
+
+
+# ---- per-row stride tables (pp_kernels_rows.cuh): shapes whose last extent is a multiple of 8 take that path; it must
+# be bit-identical to the table-driven kernels (PP_NO_ROWS=1) and to the oracle ----
+ROWS_CASES = [
+    # shape, kind, offsets, temps, R, D
+    ((4, 16), "ferro", TRI, [3.2, 3.64, 4.1], 2, 1),                   # 4-colour triangular, shifted neighbour rows
+    ((8, 8), "bimodal", TRI, [1.0, 3.64], 2, 2),
+    ((6, 4, 8), "gaussian", None, [0.9, 1.4], 2, 2),
+    ((4, 4, 16), "diluted", None, [0.8, 1.7], 3, 2),
+    ((2, 24), "bimodal", None, [1.1, 2.2], 2, 1),                      # L=2 rows: forward == backward neighbour row
+    ((4, 4, 8), "bimodal", FCC, [2.0, 9.8], 2, 1),
+    ((4, 2, 2, 8), "gaussian", None, [1.5, 6.0], 2, 1),                # 4-D
+]
+
+
+@pytest.mark.parametrize("shape,kind,offsets,temps,R,D", ROWS_CASES)
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+def test_row_table_kernels_are_bit_exact(oracle, shape, kind, offsets, temps, R, D, mode):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
+    assert_state_equal(gpu, cpu, D)
+    gaussian = kind == "gaussian"  # f32 energies are tolerance-checked, so PT (which branches on them) stays off there
+    for n_sweeps, interval in ((1, None), (19, 1), (30, 4)):
+        interval = None if gaussian else interval
+        kw = dict(warmup_ratio=0.25, pt_interval=interval, pt_schedule="full_ladder")
+        rg = gpu.sample(n_sweeps, mode, exact_log=True, **kw)
+        rc = cpu.sample(n_sweeps, mode, **kw)
+        assert_state_equal(gpu, cpu, D)
+        if not gaussian:
+            assert_results_equal(rg, rc)
+            continue
+        for k in ("mags", "mags2", "mags4", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2", "link_overlap4"):
+            assert np.array_equal(rg[k], rc[k]), k
+        np.testing.assert_allclose(rg["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(rg["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
