@@ -198,6 +198,9 @@ struct pp_sim {
     std::vector<void *> rows_bufs;
     std::vector<uint32_t> rows_class_start;
     uint64_t *d_keys = nullptr;
+    long long *d_rows_acc = nullptr;                   // [2 * max(D*S, D*P*T)] split-reduction scratch (kept zero between launches)
+    unsigned int *d_rows_arrive = nullptr;
+    int rows_nb = 1;                                   // blocks per system / pair of the split reductions
     // measurement hook: event pairs around sweep-kernel launches
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
@@ -250,6 +253,8 @@ static void free_sim(pp_sim *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (void *b : s->rows_bufs) pool_free(s, b);
     if (s->d_keys) pool_free(s, s->d_keys);
+    if (s->d_rows_acc) pool_free(s, s->d_rows_acc);
+    if (s->d_rows_arrive) pool_free(s, s->d_rows_arrive);
     if (s->slab) {
         SlabState *sl = s->slab;
         if (sl->comm_stream) cudaStreamSynchronize(sl->comm_stream);
@@ -574,10 +579,12 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
                 const int cls = col % v.m_half;
                 const uint32_t nseg = (s->rows_class_start[(size_t)cls + 1] - s->rows_class_start[(size_t)cls]) * (uint32_t)v.kpr;
                 dim3 grid((unsigned)(m.D * sblocks), blocks_for(nseg, 128));
-#define PP_ROWS(C_, Z_) rows_sweep_kernel<C_, Z_><<<grid, 128, smem, c.stream>>>(m, v, col, sweep_index + sw, sweep_mode, exact_log)
+#define PP_ROWS2(C_, Z_, G_) rows_sweep_kernel<C_, Z_, G_><<<grid, 128, smem, c.stream>>>(m, v, col, sweep_index + sw, exact_log)
+#define PP_ROWS(C_, Z_) do { if (sweep_mode == PP_SWEEP_GIBBS) PP_ROWS2(C_, Z_, true); else PP_ROWS2(C_, Z_, false); } while (0)
                 if (m.coupling_class == COUP_FERRO) { if (m.z == 2) PP_ROWS(COUP_FERRO, 2); else if (m.z == 3) PP_ROWS(COUP_FERRO, 3); else PP_ROWS(COUP_FERRO, 0); }
                 else if (m.coupling_class == COUP_UNIT) { if (m.z == 2) PP_ROWS(COUP_UNIT, 2); else if (m.z == 3) PP_ROWS(COUP_UNIT, 3); else PP_ROWS(COUP_UNIT, 0); }
                 else { if (m.z == 2) PP_ROWS(COUP_F32, 2); else if (m.z == 3) PP_ROWS(COUP_F32, 3); else PP_ROWS(COUP_F32, 0); }
+#undef PP_ROWS2
 #undef PP_ROWS
                 s->launches++;
             }
@@ -616,11 +623,16 @@ static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
     if (s->layout == PP_LAYOUT_SLAB) return slab_energy(s, m, c.stream, want_mags);
     const unsigned grid = (unsigned)(m.D * m.S);
     if (s->rows) {
+        const dim3 g2(grid, (unsigned)(m.coupling_class == COUP_F32 ? 1 : s->rows_nb));
+#define PP_RE(C_, Z_) rows_energy_kernel<C_, Z_><<<g2, 256, 0, c.stream>>>(m, s->rv, want_mags, s->d_rows_acc, s->d_rows_arrive)
+#define PP_REZ(C_) do { if (m.z == 2) PP_RE(C_, 2); else if (m.z == 3) PP_RE(C_, 3); else PP_RE(C_, 0); } while (0)
         switch (m.coupling_class) {
-            case COUP_FERRO: rows_energy_kernel<COUP_FERRO><<<grid, 256, 0, c.stream>>>(m, s->rv, want_mags); break;
-            case COUP_UNIT: rows_energy_kernel<COUP_UNIT><<<grid, 256, 0, c.stream>>>(m, s->rv, want_mags); break;
-            default: rows_energy_kernel<COUP_F32><<<grid, 256, 0, c.stream>>>(m, s->rv, want_mags);
+            case COUP_FERRO: PP_REZ(COUP_FERRO); break;
+            case COUP_UNIT: PP_REZ(COUP_UNIT); break;
+            default: PP_REZ(COUP_F32);
         }
+#undef PP_REZ
+#undef PP_RE
         s->launches++;
         CUDA_TRY(cudaGetLastError());
         return PP_OK;
@@ -645,7 +657,8 @@ static pp_status launch_overlap(pp_sim *s, Ctx &c) {
     if (s->layout == PP_LAYOUT_MSC)
         msc_overlap_kernel<<<(unsigned)(c.G * m.P * m.T), MSC_BLOCK, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
     else if (s->rows)
-        rows_overlap_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, c.stream>>>(m, s->rv, c.dot_spin, c.dot_link);
+        rows_overlap_kernel<<<dim3((unsigned)(m.D * m.P * m.T), (unsigned)s->rows_nb), 256, 0, c.stream>>>(m, s->rv, c.dot_spin, c.dot_link,
+                                                                                                   s->d_rows_acc, s->d_rows_arrive);
     else
         overlap_dots_int8_kernel<<<(unsigned)(m.D * m.P * m.T), 256, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
     s->launches++;
@@ -976,6 +989,14 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             CREATE_TRY(pool_alloc(s, (void **)&s->d_keys, sizeof(uint64_t) * (size_t)m.D));
             v.keys = s->d_keys;
             s->rows_class_start = rp.class_start;
+            // split reductions: enough blocks to fill the GPU when there are few systems, each with >= 8 segments per thread
+            const int64_t units = m.D * m.S, n_seg = rp.n_rows * rp.kpr;
+            s->rows_nb = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, (4 * 148 + units - 1) / units), n_seg / (256 * 8)));
+            const size_t n_acc = (size_t)std::max<int64_t>(units, m.D * (int64_t)(m.R / 2) * m.T);
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_rows_acc, sizeof(long long) * 2 * n_acc));
+            CREATE_TRY(pool_alloc(s, (void **)&s->d_rows_arrive, sizeof(unsigned int) * n_acc));
+            CREATE_TRY(cudaMemsetAsync(s->d_rows_acc, 0, sizeof(long long) * 2 * n_acc, s->stream));
+            CREATE_TRY(cudaMemsetAsync(s->d_rows_arrive, 0, sizeof(unsigned int) * n_acc, s->stream));
             s->rows = true;
         }
     }

@@ -130,9 +130,9 @@ __device__ __forceinline__ void rows_split(const RowsView &v, const uint32_t ci,
 // One colour class of one sweep.  grid = (D * ceil(S / ROWS_NS), segment blocks); a thread owns one row segment and
 // walks ROWS_NS slots of one realization.  ZT > 0: the number of forward directions is the compile-time constant ZT
 // (everything stays in registers); ZT = 0: any z' <= 16.
-template <int CLASS, int ZT>
+template <int CLASS, int ZT, bool GIBBS>
 __global__ void __launch_bounds__(128)
-rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int sweep_mode, int exact_log) {
+rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int exact_log) {
     extern __shared__ uint32_t lut_sm[];  // FERRO / UNIT: [T][4z + 1] acceptance counts
     constexpr int ZA = ZT > 0 ? ZT : 16;
     const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1;
@@ -210,91 +210,127 @@ rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int
                 B[kk] = rows_shifted(s + nrb[kk], L, k, -dls[kk]);
             }
         }
-        uint64_t flips = 0;  // byte j = 0xFE where site j flips (+1 = 0x01 <-> -1 = 0xFF)
+        // bring the four active sites to the even bytes: every per-site shift below is a compile-time constant
+        const int osh = 8 * off;
+        const uint64_t Cs = C >> osh;
+        uint32_t fl[2] = {0u, 0u};  // byte 2(l&1) of fl[l>>1] = 0xFE where site l flips (+1 = 0x01 <-> -1 = 0xFF)
         if (CLASS == COUP_FERRO) {
             uint64_t down = 0;  // per byte: number of down-spin neighbours
 #pragma unroll
             for (int kk = 0; kk < ZA; kk++)
                 if (kk < z) down += ((F[kk] >> 1) & 0x0101010101010101ull) + ((B[kk] >> 1) & 0x0101010101010101ull);
+            down >>= osh;
+            const uint32_t dw[2] = {(uint32_t)down, (uint32_t)(down >> 32)}, cw[2] = {(uint32_t)Cs, (uint32_t)(Cs >> 32)};
 #pragma unroll
             for (int l = 0; l < 4; l++) {
-                const int sh = 8 * (2 * l + off);
-                const int nd = (int)((down >> sh) & 0xFFu);
-                const bool dn = ((C >> sh) & 0x80u) != 0;
+                const int nd = (int)((dw[l >> 1] >> (16 * (l & 1))) & 0xFFu);
+                const bool dn = ((cw[l >> 1] >> (16 * (l & 1))) & 0x80u) != 0;
                 const int idx = dn ? 4 * z - 2 * nd : 2 * nd;  // ec + 2z' with ec = -s h, h = 2z' - 2 nd (sweep.rs:178)
-                if ((pick(o, l) >> 8) < lut_sm[t * width + idx]) flips |= 0xFEull << sh;
+                if ((pick(o, l) >> 8) < lut_sm[t * width + idx]) fl[l >> 1] |= 0xFEu << (16 * (l & 1));
             }
         } else {
-            const float temp = m.temps[t];
+            const float half_t = __fdiv_rn(m.temps[t], 2.0f);
+            const uint32_t cw[2] = {(uint32_t)Cs, (uint32_t)(Cs >> 32)};
+            uint32_t fw[ZA][2], bw[ZA][2];
+#pragma unroll
+            for (int kk = 0; kk < ZA; kk++) {
+                if (kk < z) {
+                    const uint64_t f = F[kk] >> osh, b = B[kk] >> osh;
+                    fw[kk][0] = (uint32_t)f; fw[kk][1] = (uint32_t)(f >> 32);
+                    bw[kk][0] = (uint32_t)b; bw[kk][1] = (uint32_t)(b >> 32);
+                }
+            }
 #pragma unroll
             for (int l = 0; l < 4; l++) {
-                const int sh = 8 * (2 * l + off);
-                const int si = (int)(int8_t)((C >> sh) & 0xFFu);
+                const int w = l >> 1, bs = 16 * (l & 1);
+                const uint32_t sbyte = (cw[w] >> bs) & 0xFFu;
                 const uint32_t draw = pick(o, l) >> 8;
                 float h = 0.0f;
                 int hi = 0;
 #pragma unroll
                 for (int kk = 0; kk < ZA; kk++) {
                     if (kk < z) {
-                        const int sf = (int)(int8_t)((F[kk] >> sh) & 0xFFu), sb = (int)(int8_t)((B[kk] >> sh) & 0xFFu);
-                        if (CLASS == COUP_F32) {  // sweep.rs:10-17: forward then backward, no fused multiply-add
-                            h = __fadd_rn(h, __fmul_rn((float)sf, Jf[l][2 * kk]));
-                            h = __fadd_rn(h, __fmul_rn((float)sb, Jf[l][2 * kk + 1]));
+                        const uint32_t fb = (fw[kk][w] >> bs) & 0xFFu, bb = (bw[kk][w] >> bs) & 0xFFu;
+                        if (CLASS == COUP_F32) {
+                            // sweep.rs:10-17: forward then backward, no fused multiply-add; a product with a +-1 spin is
+                            // the coupling with its sign bit flipped, exactly what the f32 multiplication returns
+                            h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[l][2 * kk]) ^ ((fb & 0x80u) << 24)));
+                            h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[l][2 * kk + 1]) ^ ((bb & 0x80u) << 24)));
                         } else {
-                            hi += sf * Ji[l][2 * kk] + sb * Ji[l][2 * kk + 1];
+                            hi += (int)(int8_t)fb * Ji[l][2 * kk] + (int)(int8_t)bb * Ji[l][2 * kk + 1];
                         }
                     }
                 }
                 bool flip;
                 if (CLASS == COUP_F32) {
-                    const float eng_change = __fmul_rn(-(float)si, h);  // sweep.rs:43-44
+                    // eng_change = -s_i * h (sweep.rs:43-44): h with its sign flipped when s_i = +1
+                    const float eng_change = __uint_as_float(__float_as_uint(h) ^ ((~sbyte & 0x80u) << 24));
                     const float u = (float)draw * (1.0f / 16777216.0f);
                     float lg;
-                    if (sweep_mode == 0)
-                        lg = exact_log ? m.logtab[draw] : logf(u);  // sweep.rs:256
-                    else
-                        lg = exact_log ? m.glogtab[draw] : logf(__fdiv_rn(u, __fsub_rn(1.0f, u)));  // sweep.rs:279-282
-                    flip = eng_change >= __fmul_rn(__fdiv_rn(temp, 2.0f), lg);
+                    if (!GIBBS)  // sweep.rs:256; production mode uses the hardware log2 (relative error ~1e-7 on the threshold)
+                        lg = exact_log ? m.logtab[draw] : __logf(u);
+                    else         // sweep.rs:279-282
+                        lg = exact_log ? m.glogtab[draw] : __logf(__fdividef(u, __fsub_rn(1.0f, u)));
+                    flip = eng_change >= __fmul_rn(half_t, lg);
                 } else {
+                    const int si = (int)(int8_t)sbyte;
                     flip = draw < lut_sm[t * width + (-si * hi) + 2 * z];  // sweep.rs:178-184
                 }
-                if (flip) flips |= 0xFEull << sh;
+                if (flip) fl[w] |= 0xFEu << bs;
             }
         }
+        const uint64_t flips = ((uint64_t)fl[0] | ((uint64_t)fl[1] << 32)) << osh;
         const uint64_t out = C ^ flips;
         *reinterpret_cast<uint2 *>(s + row_off + 8 * k) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
     }
 }
 
-// energies (+ magnetisation sums): grid = (D * S, 1); a block strides over the row segments of one system.
-template <int CLASS>
-__global__ void __launch_bounds__(256) rows_energy_kernel(ModelView m, RowsView v, int want_mags) {
+// energies (+ magnetisation sums): grid = (D * S, nb).  Integer classes split a system over nb blocks: partial sums meet
+// in acc[2 * sys + {0, 1}] (64-bit integer atomics: order-independent) and the block that arrives last converts them and
+// re-zeroes the scratch; fp32 couplings keep one block per system (f64 sums in a fixed order: reproducible).
+// e = (sum_i sum_d s_i s_fwd J) / N with the reference's final f32 division (energy.rs:99-108).
+template <int CLASS, int ZT>
+__global__ void __launch_bounds__(256) rows_energy_kernel(ModelView m, RowsView v, int want_mags, long long *acc, unsigned int *arrive) {
     __shared__ long long sh_ll[32];
     __shared__ double sh_d[32];
+    constexpr int ZA = ZT > 0 ? ZT : 16;
     const int64_t sysg = blockIdx.x;
     const int64_t d = sysg / m.S;
     const int8_t *s = m.spins + sysg * m.N;
-    const int z = m.z, L = v.L;
+    const int z = ZT > 0 ? ZT : m.z, L = v.L;
     const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);
-    long long unsat = 0, dn = 0, acc_i = 0;
+    long long isum = 0, dn = 0;  // FERRO: unsatisfied forward bonds; UNIT: sum s s J
     double acc_f = 0.0;
-    for (uint32_t ci = threadIdx.x; ci < n_seg; ci += blockDim.x) {
+    for (uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x; ci < n_seg; ci += gridDim.y * blockDim.x) {
         uint32_t r;
         int k;
         rows_split(v, ci, r, k);
         const uint64_t C = rows_ld8(s + (int64_t)r * L + 8 * k);
         dn += __popcll(C & 0x8080808080808080ull);
-        for (int kk = 0; kk < z; kk++) {  // energy.rs:99-107: forward bonds only, each bond once
-            const uint64_t f = rows_shifted(s + (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L, L, k, v.dl[kk]);
-            if (CLASS == COUP_FERRO) {
-                unsat += __popcll((C ^ f) & 0x8080808080808080ull);
-            } else {
+        uint64_t X[ZA];  // sign bit of byte j set where forward bond (site j, direction kk) joins opposite spins
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int si = (int)(int8_t)((C >> (8 * j)) & 0xFFu), sf = (int)(int8_t)((f >> (8 * j)) & 0xFFu);
-                    const size_t jidx = ((size_t)d * m.N + (size_t)r * L + 8 * k + j) * z + kk;
-                    if (CLASS == COUP_UNIT) acc_i += si * sf * m.J8[jidx];
-                    else acc_f += (double)((float)(si * sf) * m.Jf[jidx]);
+        for (int kk = 0; kk < ZA; kk++)
+            if (kk < z) X[kk] = C ^ rows_shifted(s + (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L, L, k, v.dl[kk]);
+        if (CLASS == COUP_FERRO) {
+#pragma unroll
+            for (int kk = 0; kk < ZA; kk++)
+                if (kk < z) isum += __popcll(X[kk] & 0x8080808080808080ull);
+        } else {
+            const size_t jbase = ((size_t)d * m.N + (size_t)r * L + 8 * k) * z;  // 8 sites x z couplings, contiguous
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+#pragma unroll
+                for (int kk = 0; kk < ZA; kk++) {
+                    if (kk < z) {
+                        const bool opp = ((X[kk] >> (8 * j)) & 0x80u) != 0;
+                        if (CLASS == COUP_UNIT) {
+                            const int J = m.J8[jbase + (size_t)j * z + kk];
+                            isum += opp ? -J : J;
+                        } else {
+                            const float J = m.Jf[jbase + (size_t)j * z + kk];
+                            acc_f += (double)(opp ? -J : J);
+                        }
+                    }
                 }
             }
         }
@@ -302,21 +338,40 @@ __global__ void __launch_bounds__(256) rows_energy_kernel(ModelView m, RowsView 
     if (CLASS == COUP_F32) {
         const double tot = block_sum<double>(acc_f, sh_d);
         if (threadIdx.x == 0) m.energies[sysg] = __fdiv_rn((float)tot, (float)m.N);
-    } else if (CLASS == COUP_FERRO) {
-        const long long tu = block_sum<long long>(unsat, sh_ll);
-        if (threadIdx.x == 0) m.energies[sysg] = __fdiv_rn((float)((long long)z * m.N - 2 * tu), (float)m.N);
-    } else {
-        const long long tot = block_sum<long long>(acc_i, sh_ll);
-        if (threadIdx.x == 0) m.energies[sysg] = __fdiv_rn((float)tot, (float)m.N);
+        if (want_mags) {
+            const long long td = block_sum<long long>(dn, sh_ll);
+            if (threadIdx.x == 0) m.mags[sysg] = m.N - 2 * td;
+        }
+        return;
     }
-    if (want_mags) {
-        const long long td = block_sum<long long>(dn, sh_ll);
-        if (threadIdx.x == 0) m.mags[sysg] = m.N - 2 * td;
+    const long long ti = block_sum<long long>(isum, sh_ll);
+    const long long td = block_sum<long long>(dn, sh_ll);
+    if (threadIdx.x == 0) {
+        long long e_tot = ti, d_tot = td;
+        bool last = true;
+        if (gridDim.y > 1) {
+            atomicAdd((unsigned long long *)&acc[2 * sysg], (unsigned long long)ti);
+            atomicAdd((unsigned long long *)&acc[2 * sysg + 1], (unsigned long long)td);
+            __threadfence();
+            last = atomicAdd(&arrive[sysg], 1u) == gridDim.y - 1;
+            if (last) {
+                __threadfence();
+                e_tot = (long long)atomicExch((unsigned long long *)&acc[2 * sysg], 0ull);
+                d_tot = (long long)atomicExch((unsigned long long *)&acc[2 * sysg + 1], 0ull);
+                arrive[sysg] = 0u;
+            }
+        }
+        if (last) {
+            const long long bonds = CLASS == COUP_FERRO ? (long long)z * m.N - 2 * e_tot : e_tot;
+            m.energies[sysg] = __fdiv_rn((float)bonds, (float)m.N);
+            if (want_mags) m.mags[sysg] = m.N - 2 * d_tot;
+        }
     }
 }
 
-// integer overlap dots (overlap.rs:259-281): one block per (realization, pair, temperature slot)
-__global__ void __launch_bounds__(256) rows_overlap_kernel(ModelView m, RowsView v, long long *dot_spin, long long *dot_link) {
+// integer overlap dots (overlap.rs:259-281): grid = (D * P * T, nb), same split / last-block scheme as the energies
+__global__ void __launch_bounds__(256)
+rows_overlap_kernel(ModelView m, RowsView v, long long *dot_spin, long long *dot_link, long long *acc, unsigned int *arrive) {
     __shared__ long long sh[32];
     const int64_t idx = blockIdx.x;  // (d*P + p)*T + t
     const int t = (int)(idx % m.T);
@@ -329,7 +384,7 @@ __global__ void __launch_bounds__(256) rows_overlap_kernel(ModelView m, RowsView
     const int z = m.z, L = v.L;
     const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);
     long long neg_q = 0, neg_l = 0;  // sites with q_i = -1, links with q_i q_j = -1
-    for (uint32_t ci = threadIdx.x; ci < n_seg; ci += blockDim.x) {
+    for (uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x; ci < n_seg; ci += gridDim.y * blockDim.x) {
         uint32_t r;
         int k;
         rows_split(v, ci, r, k);
@@ -345,8 +400,24 @@ __global__ void __launch_bounds__(256) rows_overlap_kernel(ModelView m, RowsView
     const long long tq = block_sum<long long>(neg_q, sh);
     const long long tl = block_sum<long long>(neg_l, sh);
     if (threadIdx.x == 0) {
-        dot_spin[idx] = m.N - 2 * tq;
-        dot_link[idx] = (long long)z * m.N - 2 * tl;
+        long long q_tot = tq, l_tot = tl;
+        bool last = true;
+        if (gridDim.y > 1) {
+            atomicAdd((unsigned long long *)&acc[2 * idx], (unsigned long long)tq);
+            atomicAdd((unsigned long long *)&acc[2 * idx + 1], (unsigned long long)tl);
+            __threadfence();
+            last = atomicAdd(&arrive[idx], 1u) == gridDim.y - 1;
+            if (last) {
+                __threadfence();
+                q_tot = (long long)atomicExch((unsigned long long *)&acc[2 * idx], 0ull);
+                l_tot = (long long)atomicExch((unsigned long long *)&acc[2 * idx + 1], 0ull);
+                arrive[idx] = 0u;
+            }
+        }
+        if (last) {
+            dot_spin[idx] = m.N - 2 * q_tot;
+            dot_link[idx] = (long long)z * m.N - 2 * l_tot;
+        }
     }
 }
 #endif  // __CUDACC__
