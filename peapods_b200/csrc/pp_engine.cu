@@ -484,13 +484,14 @@ static pp_status slab_exchange(pp_sim *s, cudaStream_t stream) {
 
 static pp_status slab_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream, uint32_t sweep_index, int n_sweeps) {
     SlabState *sl = s->slab;
-    const unsigned bx = blocks_for(sl->parts[0].chunks_per_plane, 256);
+    const SlabView &v0 = sl->parts[0];
+    const unsigned tiles = (unsigned)(((v0.L2 / 8 + v0.tile_x - 1) / v0.tile_x) * ((v0.L1 + 256 / v0.tile_x - 1) / (256 / v0.tile_x)));
     const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
     for (SlabView &v : sl->parts) { v.k0 = (uint32_t)key; v.k1 = (uint32_t)(key >> 32); }
     for (int sw = 0; sw < n_sweeps; sw++)
         for (int colour = 0; colour < 2; colour++) {
-            for (const SlabView &v : sl->parts) {  // boundary planes first: they are what the neighbours wait for
-                slab_sweep_kernel<<<dim3(bx, 2, (unsigned)m.S), 256, 0, stream>>>(m, v, colour, sweep_index + (uint32_t)sw, 1, 1, sl->P);
+            for (const SlabView &v : sl->parts) {  // boundary planes (one launch) first: they are what the neighbours wait for
+                slab_sweep_kernel<<<dim3(tiles, 2, (unsigned)m.S), 256, 0, stream>>>(m, v, colour, sweep_index + (uint32_t)sw, 1, 1, sl->P);
                 s->launches++;
             }
             CUDA_TRY(cudaEventRecord(sl->ev_boundary, stream));
@@ -500,8 +501,8 @@ static pp_status slab_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream,
             CUDA_TRY(cudaEventRecord(sl->ev_halo, sl->comm_stream));
             if (sl->P > 2)
                 for (const SlabView &v : sl->parts) {  // interior planes overlap the halo transfer
-                    slab_sweep_kernel<<<dim3(bx, (unsigned)(sl->P - 2), (unsigned)m.S), 256, 0, stream>>>(m, v, colour, sweep_index + (uint32_t)sw,
-                                                                                                     2, sl->P - 2, 0);
+                    slab_sweep_kernel<<<dim3(tiles, (unsigned)((sl->P - 2 + SLAB_PR - 1) / SLAB_PR), (unsigned)m.S), 256, 0, stream>>>(
+                        m, v, colour, sweep_index + (uint32_t)sw, 2, sl->P - 2, 0);
                     s->launches++;
                 }
             CUDA_TRY(cudaStreamWaitEvent(stream, sl->ev_halo, 0));
@@ -919,6 +920,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             v.kpr_shift = -1;
             for (int b = 0; b < 30; b++)
                 if ((sl->L2 >> 3) == (1 << b)) v.kpr_shift = b;
+            v.tile_x_shift = 0;
+            while (v.tile_x_shift < 5 && (2 << v.tile_x_shift) <= (sl->L2 >> 3)) v.tile_x_shift++;
+            v.tile_x = 1 << v.tile_x_shift;
             uint8_t *buf = nullptr;
             CREATE_TRY(cudaMalloc((void **)&buf, (size_t)(m.S * v.sys_stride)));
             sl->buffers.push_back(buf);

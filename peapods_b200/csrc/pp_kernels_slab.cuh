@@ -28,6 +28,7 @@ struct SlabView {
     int64_t first_plane;       // global x0 of local plane 1
     int64_t chunks_per_plane;  // L1 * L2 / 8
     int kpr_shift;             // log2(L2 / 8) when that is a power of two, else -1
+    int tile_x, tile_x_shift;  // sweep tile: tile_x (a power of two <= 32) segments of a row x 256 / tile_x rows
     uint32_t k0, k1;           // Philox key of the realization (realization_seed(seed, sample_offset), set per launch)
 };
 
@@ -48,48 +49,64 @@ __device__ __forceinline__ uint64_t ld8(const uint8_t *p) {
     return (uint64_t)v.x | ((uint64_t)v.y << 32);
 }
 
-// grid = (chunk blocks, planes, slots).  The launch covers local planes [pa, pa + na) and, after them, [pb, ...).
+constexpr int SLAB_PR = 8;  // planes a sweep thread marches through
+
+// One colour half-step of the local planes [pa, pa + np) (and, when pb > 0, of plane pb as one more range: the two
+// boundary planes go in one launch).  grid = (column tiles, ceil(np / SLAB_PR) [+ 1], slots); block = 256
+// threads = a tile of tile_x row segments x 256 / tile_x rows (tile_x = v.tile_x).  A thread owns one column of segments
+// (x1, k) and marches through SLAB_PR planes with a three-plane register window, so the x0 neighbours cost one new
+// 8-byte load per update and the x1 neighbours are segments other threads of the same tile load at the same time (L1).
 __global__ void __launch_bounds__(256)
-slab_sweep_kernel(ModelView m, SlabView v, int colour, uint32_t sweep_index, int pa, int na, int pb) {
+slab_sweep_kernel(ModelView m, SlabView v, int colour, uint32_t sweep_index, int pa, int np, int pb) {
     __shared__ uint32_t thr[8];
     const int slot = blockIdx.z;
     const int t = slot % m.T;  // realization.rs:166: temperatures repeat with period T
     if (threadIdx.x < 7) thr[threadIdx.x] = m.lut[t * 13 + 2 * threadIdx.x];  // sweep.rs:162-166, index ec + 2z' = 2 * unsat
     __syncthreads();
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= v.chunks_per_plane) return;
-    const int pi = blockIdx.y;
-    const int p = pi < na ? pa + pi : pb + (pi - na);
     const int kpr = v.L2 >> 3;
-    int x1, k;
-    slab_split(v, c, x1, k);
+    const int tiles_x = (kpr + v.tile_x - 1) / v.tile_x, tile_y = 256 / v.tile_x;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int k = tx * v.tile_x + (threadIdx.x & (v.tile_x - 1));
+    const int x1 = ty * tile_y + (threadIdx.x >> v.tile_x_shift);
+    if (k >= kpr || x1 >= v.L1) return;
+    const int n_ranges = (np + SLAB_PR - 1) / SLAB_PR;
+    const bool second = (int)blockIdx.y >= n_ranges;  // the extra range: plane pb alone
+    const int p0 = second ? pb : pa + blockIdx.y * SLAB_PR, p1 = second ? pb + 1 : min(p0 + SLAB_PR, pa + np);
     const uint32_t sys = (uint32_t)m.system_ids[slot];  // parallel.rs:27-33: spins by system, temperature by slot
-    uint8_t *row = v.spins + (int64_t)sys * v.sys_stride + (int64_t)p * v.plane + (int64_t)x1 * v.L2 + 8 * k;
+    uint8_t *col = v.spins + (int64_t)sys * v.sys_stride + (int64_t)x1 * v.L2 + 8 * k;  // plane 0 of this column
     const int x1m = x1 ? x1 - 1 : v.L1 - 1, x1p = x1 + 1 == v.L1 ? 0 : x1 + 1;
-    const uint64_t C = ld8(row);
-    const uint64_t Xm = ld8(row - v.plane), Xp = ld8(row + v.plane);
-    const uint64_t Ym = ld8(row + (int64_t)(x1m - x1) * v.L2), Yp = ld8(row + (int64_t)(x1p - x1) * v.L2);
-    const uint32_t gx0 = (uint32_t)(v.first_plane + p - 1);
-    const uint32_t off = (colour ^ gx0 ^ x1) & 1u;  // active sites of the segment: x2 = 8k + 2l + off
-    // off = 0: site 0 needs the byte left of the segment; off = 1: site 7 needs the byte right of it
-    const int xe = off ? (k + 1 == kpr ? 8 - v.L2 : 8) : (k ? -1 : v.L2 - 1);
-    const uint64_t E = row[xe];
-    const uint64_t left = (C << 8) | (off ? 0ull : E), right = (C >> 8) | (off ? E << 56 : 0ull);
-    const uint64_t down = Xm + Xp + Ym + Yp + left + right;  // per byte: down-spin neighbours (<= 6, no carries)
-    const uint32_t q = (gx0 * (uint32_t)v.L1 + (uint32_t)x1) * (uint32_t)kpr + (uint32_t)k;  // segment index = colour rank >> 2
-    const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, v.k0, v.k1);
-    // bring the four active sites to the even bytes, then work on the two 32-bit halves with constant shifts
-    const uint64_t dsh = down >> (8 * off), csh = C >> (8 * off);
-    const uint32_t d2[2] = {(uint32_t)dsh, (uint32_t)(dsh >> 32)}, c2[2] = {(uint32_t)csh, (uint32_t)(csh >> 32)};
-    uint32_t f2[2] = {0u, 0u};
+    const int64_t dym = (int64_t)(x1m - x1) * v.L2, dyp = (int64_t)(x1p - x1) * v.L2;
+    const int xe_l = k ? -1 : v.L2 - 1, xe_r = k + 1 == kpr ? 8 - v.L2 : 8;  // byte left / right of the segment
+    uint64_t Xm = ld8(col + (int64_t)(p0 - 1) * v.plane), C = ld8(col + (int64_t)p0 * v.plane);
+    for (int p = p0; p < p1; p++) {
+        uint8_t *row = col + (int64_t)p * v.plane;
+        const uint64_t Xp = ld8(row + v.plane);
+        const uint64_t Ym = ld8(row + dym), Yp = ld8(row + dyp);
+        const uint32_t gx0 = (uint32_t)(v.first_plane + p - 1);
+        const uint32_t off = (colour ^ gx0 ^ x1) & 1u;  // active sites of the segment: x2 = 8k + 2l + off
+        // off = 0: site 0 needs the byte left of the segment; off = 1: site 7 needs the byte right of it
+        const uint64_t E = row[off ? xe_r : xe_l];
+        const uint64_t left = (C << 8) | (off ? 0ull : E), right = (C >> 8) | (off ? E << 56 : 0ull);
+        const uint64_t down = Xm + Xp + Ym + Yp + left + right;  // per byte: down-spin neighbours (<= 6, no carries)
+        const uint32_t q = (gx0 * (uint32_t)v.L1 + (uint32_t)x1) * (uint32_t)kpr + (uint32_t)k;  // segment index = colour rank >> 2
+        const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, v.k0, v.k1);
+        // ferromagnet: a bond is unsatisfied iff the two spins differ, so per byte unsat = s ? 6 - down : down
+        // = (down ^ 7s) - s for all 8 sites at once; then the four active sites are brought to the even bytes and the two
+        // 32-bit halves are read with constant shifts
+        const uint64_t unsat8 = (down ^ (C * 7ull)) - C;
+        const uint64_t ush = unsat8 >> (8 * off);
+        const uint32_t u2[2] = {(uint32_t)ush, (uint32_t)(ush >> 32)};
+        uint32_t f2[2] = {0u, 0u};
 #pragma unroll
-    for (int l = 0; l < 4; l++) {
-        const uint32_t nd = (d2[l >> 1] >> (16 * (l & 1))) & 0xFFu, sb = (c2[l >> 1] >> (16 * (l & 1))) & 1u;
-        const uint32_t unsat = sb ? 6u - nd : nd;  // ferromagnet: a bond is unsatisfied iff the two spins differ
-        if ((pick(o, l) >> 8) < thr[unsat]) f2[l >> 1] |= 1u << (16 * (l & 1));  // sweep.rs:182-184
+        for (int l = 0; l < 4; l++) {
+            const uint32_t unsat = (u2[l >> 1] >> (16 * (l & 1))) & 0xFFu;
+            if ((pick(o, l) >> 8) < thr[unsat]) f2[l >> 1] |= 1u << (16 * (l & 1));  // sweep.rs:182-184
+        }
+        const uint64_t out = C ^ (((uint64_t)f2[0] | ((uint64_t)f2[1] << 32)) << (8 * off));
+        *reinterpret_cast<uint2 *>(row) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
+        Xm = C;  // the neighbours' bytes of the other colour are what the next plane reads: unchanged by this update
+        C = Xp;
     }
-    const uint64_t out = C ^ (((uint64_t)f2[0] | ((uint64_t)f2[1] << 32)) << (8 * off));
-    *reinterpret_cast<uint2 *>(row) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
 }
 
 // K0: spin -1 iff the INIT-domain draw < 2^23 (realization.rs:180); grid = (chunk blocks, P, S)
