@@ -317,18 +317,37 @@ __global__ void __launch_bounds__(256) rows_energy_kernel(ModelView m, RowsView 
                 if (kk < z) isum += __popcll(X[kk] & 0x8080808080808080ull);
         } else {
             const size_t jbase = ((size_t)d * m.N + (size_t)r * L + 8 * k) * z;  // 8 sites x z couplings, contiguous
+            if (CLASS == COUP_F32) {
+                // 8z consecutive floats (a multiple of 16 bytes from a 16-byte aligned start): 2z vector loads
+                float Jv[ZT > 0 ? 8 * ZT : 1];
+                const float4 *jp = reinterpret_cast<const float4 *>(m.Jf + jbase);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+                for (int qv = 0; qv < 2 * ZT; qv++) {
+                    {
+                        const float4 t4 = __ldg(jp + qv);
+                        Jv[4 * qv] = t4.x; Jv[4 * qv + 1] = t4.y; Jv[4 * qv + 2] = t4.z; Jv[4 * qv + 3] = t4.w;
+                    }
+                }
 #pragma unroll
-                for (int kk = 0; kk < ZA; kk++) {
-                    if (kk < z) {
-                        const bool opp = ((X[kk] >> (8 * j)) & 0x80u) != 0;
-                        if (CLASS == COUP_UNIT) {
+                for (int j = 0; j < 8; j++) {
+#pragma unroll
+                    for (int kk = 0; kk < ZA; kk++) {
+                        if (kk < z) {
+                            const bool opp = ((X[kk] >> (8 * j)) & 0x80u) != 0;
+                            const float J = ZT > 0 ? Jv[j * ZT + kk] : m.Jf[jbase + (size_t)j * z + kk];
+                            acc_f += (double)(opp ? -J : J);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+#pragma unroll
+                    for (int kk = 0; kk < ZA; kk++) {
+                        if (kk < z) {
+                            const bool opp = ((X[kk] >> (8 * j)) & 0x80u) != 0;
                             const int J = m.J8[jbase + (size_t)j * z + kk];
                             isum += opp ? -J : J;
-                        } else {
-                            const float J = m.Jf[jbase + (size_t)j * z + kk];
-                            acc_f += (double)(opp ? -J : J);
                         }
                     }
                 }
