@@ -46,6 +46,9 @@ SAMPLES_PER_GPU = 4096
 Z = 3
 SEED = 42
 B_ALG_MSC = 0.125 + 0.125 + (Z / 8.0) / (N_TEMPS * N_REPLICAS)  # bytes per attempt
+# dram__bytes_read.sum + dram__bytes_write.sum of one msc3d_kernel launch covering 1024 samples, mean of the three launches of
+# the `ncu --set full` capture summarised in profiles/r1g_msc3d_summary.md; a launch over D samples moves D/1024 times that
+NCU_DRAM_BYTES_PER_1024_SAMPLES = 127.7e6
 
 
 def peaks():
@@ -276,11 +279,14 @@ def run_ours(args):
     res = sim.sample(n_sweeps, "metropolis", profile=True, **kw)
     del res
     k_ms, k_n = sim.last_sweep_kernel_ms, max(sim.last_sweep_kernel_launches, 1)
+    k_n_expected = n_sweeps  # profile mode: one launch per sweep over all samples
     peak, peak_src = peaks()
     alg_bytes_per_launch = B_ALG_MSC * attempts_step / k_n
     achieved = alg_bytes_per_launch / (k_ms / k_n * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": args.traffic, "kernel": "msc sweep kernel", "peak_source": peak_src,
+                "traffic": args.traffic if args.traffic is not None else NCU_DRAM_BYTES_PER_1024_SAMPLES * D / 1024.0 * (k_n_expected / k_n),
+                "traffic_source": "ncu --set full (profiles/r1g_msc3d_summary.md), scaled to this launch size",
+                "kernel": "msc3d_kernel (sweep + energy / magnetisation / overlap / fold)", "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes_per_launch, "launches_timed": k_n, "kernel_ms_mean": k_ms / k_n,
                 "kernel_share_of_step": k_ms / max(sim.last_sweep_loop_ms, 1e-9)}
     del sim
