@@ -161,6 +161,7 @@ struct pp_sim {
     bool msc3d_metro = false;                          // Metropolis counts for unsat >= 3 are all 2^24
     int msc3d_nh = 2;                                  // temperature slots (256-thread halves) per CTA of the msc3d kernel
     size_t msc3d_smem = 0;
+    bool msc3d_esw = false;                            // in-sweep energy counters + pair-only epilogue (see msc3d_kernel)
     Msc3dPlan m3;
     Msc3dView gv{};
     uint32_t *d_perm = nullptr;
@@ -407,7 +408,7 @@ static pp_status launch_msc3d_t(pp_sim *s, Ctx &c, const ModelView &m, uint32_t 
     const unsigned grid = (unsigned)(c.G * ((m.T + NH - 1) / NH));
     msc3d_kernel<RPC, METRO, NH><<<grid, MSC3D_NTH * NH, s->msc3d_smem, c.stream>>>(
         m, s->gv, c.st, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold, m.sample_offset / 32, c.dot_spin,
-        c.dot_link, c.words_alt, c.swap_pending ? c.pt.swap_mask : nullptr, c.pend_schedule, c.pend_parity);
+        c.dot_link, c.words_alt, c.swap_pending ? c.pt.swap_mask : nullptr, c.pend_schedule, c.pend_parity, s->msc3d_esw ? 1 : 0);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     if (n_sweeps > 0) {  // the sweep consumed the pending exchange and wrote the other buffer
@@ -1064,6 +1065,15 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 CREATE_TRY(pool_alloc(s, (void **)&s->d_words_alt, sizeof(uint32_t) * (size_t)(s->G * m.S * N)));
                 s->msc3d_nh = nh;
                 s->msc3d_smem = smem_words(nh) * 4;
+                // in-sweep energy: one slot per CTA, replicas in pairs, at most two quads per thread (MSC3D_KS planes) and
+                // at most four pair items per thread (MSC3D_KQ / MSC3D_KL planes); the coupling-word area must hold the
+                // parked counters (R * KS * 256 words, then 25 planes * 256 words) below its last 512 words
+                {
+                    const int64_t park = std::max<int64_t>((int64_t)m.R * MSC3D_KS * MSC3D_NTH, (3 * MSC3D_KQ + MSC3D_KL) * MSC3D_NTH);
+                    s->msc3d_esw = nh == 1 && (m.R == 2 || m.R == 4) && s->m3.n_items <= 2 * MSC3D_NTH &&
+                                   3 * (int64_t)N - 512 >= park;
+                    if (const char *e = getenv("PP_MSC3D_ESW")) s->msc3d_esw = s->msc3d_esw && atoi(e) != 0;
+                }
                 // Metropolis fast path: counts for unsat >= 3 (energy_change >= 0) are 2^24 (sweep.rs:141-145) and the
                 // others are below 2^24, so (draw < count) == (raw32 < count << 8)
                 std::vector<uint32_t> lut((size_t)m.T * 13);

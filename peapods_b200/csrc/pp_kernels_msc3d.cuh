@@ -158,6 +158,23 @@ struct VAcc {
         p[LVL] ^= a;
         return c;
     }
+    // add a KI-plane bit-sliced number (ripple carry)
+    template <int KI>
+    __device__ __forceinline__ void add_planes(const uint32_t *x) {
+        uint32_t c = 0u;
+#pragma unroll
+        for (int b = 0; b < K; b++) {
+            if (b < KI) {
+                const uint32_t sum = xor3(p[b], x[b], c);
+                c = maj3(p[b], x[b], c);
+                p[b] = sum;
+            } else {
+                const uint32_t t = p[b] & c;
+                p[b] ^= c;
+                c = t;
+            }
+        }
+    }
     // eight words of weight 1
     __device__ __forceinline__ void add8(const uint32_t *w) {
         const uint32_t k0 = csa<0>(w[0], w[1]), k1 = csa<0>(w[2], w[3]), k2 = csa<0>(w[4], w[5]), k3 = csa<0>(w[6], w[7]);
@@ -229,46 +246,82 @@ constexpr int MSC3D_NTH = 256;  // threads per half
 
 // One quad (four same-colour sites of one row segment) of all RPC replicas.  P = the quad's sites sit at x2 = 2j + P.
 //   sp: the half's [RPC][N] words; J: [3][N] coupling sign words in shared memory (all-zero words for a ferromagnet)
-template <int RPC, bool METRO, bool P>
+constexpr int MSC3D_KS = 6;  // planes of the in-sweep unsatisfied-bond counters (two quads per thread: 2 * 4 * 6 = 48)
+
+// Sum of eight words of weight 1 (w1) and eight of weight 2 (w2) as a 5-plane number (<= 24): carry-save tree, 28 LOP3.
+__device__ __forceinline__ void tree_8_8(const uint32_t *w1, const uint32_t *w2, uint32_t *t) {
+    const uint32_t S0 = xor3(w1[0], w1[1], w1[2]), C0 = maj3(w1[0], w1[1], w1[2]);
+    const uint32_t S1 = xor3(w1[3], w1[4], w1[5]), C1 = maj3(w1[3], w1[4], w1[5]);
+    const uint32_t S2 = xor3(S0, S1, w1[6]), C2 = maj3(S0, S1, w1[6]);
+    t[0] = S2 ^ w1[7];
+    const uint32_t C3 = S2 & w1[7];
+    const uint32_t S3 = xor3(w2[0], w2[1], w2[2]), D0 = maj3(w2[0], w2[1], w2[2]);
+    const uint32_t S4 = xor3(w2[3], w2[4], w2[5]), D1 = maj3(w2[3], w2[4], w2[5]);
+    const uint32_t S5 = xor3(w2[6], w2[7], C0), D2 = maj3(w2[6], w2[7], C0);
+    const uint32_t S6 = xor3(C1, C2, C3), D3 = maj3(C1, C2, C3);
+    const uint32_t S7 = xor3(S3, S4, S5), D4 = maj3(S3, S4, S5);
+    t[1] = S7 ^ S6;
+    const uint32_t D5 = S7 & S6;
+    const uint32_t S8 = xor3(D0, D1, D2), E0 = maj3(D0, D1, D2);
+    const uint32_t S9 = xor3(D3, D4, D5), E1 = maj3(D3, D4, D5);
+    t[2] = S8 ^ S9;
+    const uint32_t E2 = S8 & S9;
+    t[3] = xor3(E0, E1, E2);
+    t[4] = maj3(E0, E1, E2);
+}
+
+// ACC: also count, per lane, the unsatisfied bonds of the updated sites AFTER the update into ea[r] (a flip inverts the six
+// bond words of its site, so the two adder outputs of each half are simply XORed with the flip mask).  On a bipartite
+// lattice the six bonds of the colour-1 sites are all bonds, each once: the colour-1 pass of the last sweep yields the
+// energy of energy.rs:99-108 without another pass over the spins.
+//
+// P (runtime, warp-uniform: the item order keeps the quads of one x2-parity together): the quad's sites sit at x2 = 2j + P.
+// Their two x2 neighbours are the aligned quad O of the other colour (the left neighbours if P, the right ones if not) and
+// that quad shifted by one word towards the other side, completed by the row's wrap word.  Both bonds enter the same
+// adder, so only the pairing (spin words, coupling words) matters; parity is a matter of word offsets, not of code.
+template <int RPC, bool METRO, bool ACC>
 __device__ __forceinline__ void msc3d_sweep_item(uint32_t *sp, const uint32_t *J, const uint32_t N, const uint32_t so,
-                                                 const uint32_t oo, const uint4 desc, const uint32_t (&thr)[7],
+                                                 const uint32_t oo, const uint4 desc, const bool P, const uint32_t (&thr)[7],
                                                  const uint64_t (&nthr)[3], const uint32_t (&one)[3], const uint32_t sweep, const uint32_t pos0, const uint32_t pos_stride,
-                                                 const uint32_t tag, const uint32_t k0, const uint32_t k1) {
+                                                 const uint32_t tag, const uint32_t k0, const uint32_t k1,
+                                                 VAcc<MSC3D_KS> *ea) {
     uint32_t self, zp, zm, yp, ym, eL, eR, par;
     unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
     (void)par;
-    // coupling sign words (bit = 1: J = -1); bond (i, d) is stored at its lower site i
-    uint32_t Jf0[4], Jf1[4], Jf2[4], Jb0[4], Jb1[4], Jb2[4];
+    // word offsets of the shifted quad inside the other colour half
+    const uint32_t sh0 = P ? self + 1 : eL, sh1 = self + (P ? 2u : 0u), sh2 = self + (P ? 3u : 1u), sh3 = P ? eR : self + 2;
+    // coupling sign words (bit = 1: J = -1); bond (i, d) is stored at its lower site i: the forward bonds at the quad itself,
+    // the backward bonds at the backward neighbours
+    uint32_t Jf0[4], Jf1[4], Jb0[4], Jb1[4], JO[4], JS[4];
     to_arr(lds4(J + 0 * N + so + self), Jf0);
     to_arr(lds4(J + 1 * N + so + self), Jf1);
-    to_arr(lds4(J + 2 * N + so + self), Jf2);
     to_arr(lds4(J + 0 * N + oo + zm), Jb0);
     to_arr(lds4(J + 1 * N + oo + ym), Jb1);
     {
-        const uint4 v = lds4(J + 2 * N + oo + self);
-        if (P) { Jb2[0] = v.x; Jb2[1] = v.y; Jb2[2] = v.z; Jb2[3] = v.w; }
-        else   { Jb2[0] = J[2 * N + oo + eL]; Jb2[1] = v.x; Jb2[2] = v.y; Jb2[3] = v.z; }
+        const uint32_t *J2 = J + 2 * N;
+        to_arr(lds4(J2 + (P ? oo : so) + self), JO);  // P: O = left neighbours, bond stored there; else O = right, stored here
+        const uint32_t *JSb = J2 + (P ? so : oo);     // P: shifted = right neighbours, bonds stored at the quad itself
+        JS[0] = JSb[P ? self : sh0]; JS[1] = JSb[P ? self + 1 : sh1]; JS[2] = JSb[P ? self + 2 : sh2]; JS[3] = JSb[P ? self + 3 : sh3];
     }
 #pragma unroll
     for (int r = 0; r < RPC; r++) {
         uint32_t *sys = sp + (size_t)r * N;
         const u32x4 rnd = philox4x32_10(self >> 2, sweep, pos0 + (uint32_t)r * pos_stride, tag, k0, k1);
-        uint32_t s[4], zpv[4], zmv[4], ypv[4], ymv[4], xr[4], xl[4];
+        uint32_t s[4], zpv[4], zmv[4], ypv[4], ymv[4], xo[4], xs[4];
         to_arr(lds4(sys + so + self), s);
         to_arr(lds4(sys + oo + zp), zpv);
         to_arr(lds4(sys + oo + zm), zmv);
         to_arr(lds4(sys + oo + yp), ypv);
         to_arr(lds4(sys + oo + ym), ymv);
-        const uint4 O = lds4(sys + oo + self);
-        const uint32_t E = sys[oo + (P ? eR : eL)];
-        if (P) { xl[0] = O.x; xl[1] = O.y; xl[2] = O.z; xl[3] = O.w; xr[0] = O.y; xr[1] = O.z; xr[2] = O.w; xr[3] = E; }
-        else   { xl[0] = E;   xl[1] = O.x; xl[2] = O.y; xl[3] = O.z; xr[0] = O.x; xr[1] = O.y; xr[2] = O.z; xr[3] = O.w; }
+        to_arr(lds4(sys + oo + self), xo);
+        xs[0] = sys[oo + sh0]; xs[1] = sys[oo + sh1]; xs[2] = sys[oo + sh2]; xs[3] = sys[oo + sh3];
         const uint32_t raw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        uint32_t w1[8], w2[8];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t b0 = xor3(s[j], zpv[j], Jf0[j]), b1 = xor3(s[j], zmv[j], Jb0[j]);
             const uint32_t b2 = xor3(s[j], ypv[j], Jf1[j]), b3 = xor3(s[j], ymv[j], Jb1[j]);
-            const uint32_t b4 = xor3(s[j], xr[j], Jf2[j]), b5 = xor3(s[j], xl[j], Jb2[j]);
+            const uint32_t b4 = xor3(s[j], xo[j], JO[j]), b5 = xor3(s[j], xs[j], JS[j]);
             const uint32_t s1 = xor3(b0, b1, b2), c1 = maj3(b0, b1, b2);
             const uint32_t s2 = xor3(b3, b4, b5), c2 = maj3(b3, b4, b5);
             const uint32_t kk = s1 & s2, oo2 = s1 | s2;
@@ -307,45 +360,50 @@ __device__ __forceinline__ void msc3d_sweep_item(uint32_t *sp, const uint32_t *J
                 }
             }
             s[j] ^= flip;
+            if (ACC) {
+                w1[2 * j] = s1 ^ flip; w1[2 * j + 1] = s2 ^ flip;
+                w2[2 * j] = c1 ^ flip; w2[2 * j + 1] = c2 ^ flip;
+            }
         }
         *reinterpret_cast<uint4 *>(sys + so + self) = make_uint4(s[0], s[1], s[2], s[3]);
+        if (ACC) {
+            uint32_t t5[5];
+            tree_8_8(w1, w2, t5);
+            ea[r].template add_planes<5>(t5);
+        }
     }
 }
 
-// the 8 sites of one row segment of system A: words 0..3 colour 0, 4..7 colour 1, with their +x0, +x1, +x2 neighbours
-template <bool PAR>
-__device__ __forceinline__ void msc3d_load_segment(const uint32_t *A, const uint32_t N2, const uint32_t self,
+// The 8 sites of one row segment of system A with their +x0, +x1, +x2 neighbours, as two groups of four:
+//   X = the colour whose sites sit at odd x2 (colour 0 if PAR, else colour 1): its +x2 neighbours are the other colour's quad
+//       shifted by one word (plus the row's wrap word eR);
+//   Y = the other colour: its +x2 neighbours are X's own words.
+// xo / yo = word offsets of the two colour halves (0 or N2).  Words 0..3 of each array = group X, 4..7 = group Y.
+__device__ __forceinline__ void msc3d_load_segment(const uint32_t *A, const uint32_t xo, const uint32_t yo, const uint32_t self,
                                                    const uint32_t zp, const uint32_t yp, const uint32_t eR, uint32_t *a,
                                                    uint32_t *az, uint32_t *ay, uint32_t *ax) {
-    const uint4 s0 = lds4(A + self), s1 = lds4(A + N2 + self);
-    to_arr(s0, a); to_arr(s1, a + 4);
-    to_arr(lds4(A + N2 + zp), az); to_arr(lds4(A + zp), az + 4);
-    to_arr(lds4(A + N2 + yp), ay); to_arr(lds4(A + yp), ay + 4);
-    // colour c sites sit at x2 = 2j + (PAR ^ c); their +x2 neighbour is word j of the other colour when that is 0, word j+1 when 1
-    if (!PAR) {
-        ax[0] = s1.x; ax[1] = s1.y; ax[2] = s1.z; ax[3] = s1.w;
-        ax[4] = s0.y; ax[5] = s0.z; ax[6] = s0.w; ax[7] = A[eR];
-    } else {
-        ax[0] = s1.y; ax[1] = s1.z; ax[2] = s1.w; ax[3] = A[N2 + eR];
-        ax[4] = s0.x; ax[5] = s0.y; ax[6] = s0.z; ax[7] = s0.w;
-    }
+    to_arr(lds4(A + xo + self), a); to_arr(lds4(A + yo + self), a + 4);
+    to_arr(lds4(A + yo + zp), az); to_arr(lds4(A + xo + zp), az + 4);
+    to_arr(lds4(A + yo + yp), ay); to_arr(lds4(A + xo + yp), ay + 4);
+    ax[0] = a[5]; ax[1] = a[6]; ax[2] = a[7]; ax[3] = A[yo + eR];
+    ax[4] = a[0]; ax[5] = a[1]; ax[6] = a[2]; ax[7] = a[3];
 }
 
-template <bool PAR>
 __device__ __forceinline__ void msc3d_em_item(const uint32_t *A, const uint32_t *J, const uint32_t N, const uint32_t N2,
                                               const uint4 desc, const int want_energy, const int want_mags,
                                               VAcc<MSC3D_KE> &ve, VAcc<MSC3D_KM> &vm) {
     uint32_t self, zp, zm, yp, ym, eL, eR, par;
     unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
-    (void)zm; (void)ym; (void)eL; (void)par;
+    (void)zm; (void)ym; (void)eL;
+    const uint32_t xo = (par & 1u) ? 0u : N2, yo = N2 - xo;
     uint32_t a[8], az[8], ay[8], ax[8];
-    msc3d_load_segment<PAR>(A, N2, self, zp, yp, eR, a, az, ay, ax);
+    msc3d_load_segment(A, xo, yo, self, zp, yp, eR, a, az, ay, ax);
     if (want_mags) vm.add8(a);
     if (want_energy) {
         uint32_t j0[8], j1[8], j2[8];
-        to_arr(lds4(J + 0 * N + self), j0); to_arr(lds4(J + 0 * N + N2 + self), j0 + 4);
-        to_arr(lds4(J + 1 * N + self), j1); to_arr(lds4(J + 1 * N + N2 + self), j1 + 4);
-        to_arr(lds4(J + 2 * N + self), j2); to_arr(lds4(J + 2 * N + N2 + self), j2 + 4);
+        to_arr(lds4(J + 0 * N + xo + self), j0); to_arr(lds4(J + 0 * N + yo + self), j0 + 4);
+        to_arr(lds4(J + 1 * N + xo + self), j1); to_arr(lds4(J + 1 * N + yo + self), j1 + 4);
+        to_arr(lds4(J + 2 * N + xo + self), j2); to_arr(lds4(J + 2 * N + yo + self), j2 + 4);
         uint32_t sb[8], cb[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {  // energy.rs:99-107: forward bonds only, each bond once
@@ -357,15 +415,15 @@ __device__ __forceinline__ void msc3d_em_item(const uint32_t *A, const uint32_t 
     }
 }
 
-template <bool PAR>
 __device__ __forceinline__ void msc3d_pair_item(const uint32_t *A, const uint32_t *B, const uint32_t N2, const uint4 desc,
                                                 VAcc<MSC3D_KE> &vl, VAcc<MSC3D_KM> &vq) {
     uint32_t self, zp, zm, yp, ym, eL, eR, par;
     unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
-    (void)zm; (void)ym; (void)eL; (void)par;
+    (void)zm; (void)ym; (void)eL;
+    const uint32_t xo = (par & 1u) ? 0u : N2, yo = N2 - xo;
     uint32_t a[8], az[8], ay[8], ax[8], b[8], bz[8], by[8], bx[8];
-    msc3d_load_segment<PAR>(A, N2, self, zp, yp, eR, a, az, ay, ax);
-    msc3d_load_segment<PAR>(B, N2, self, zp, yp, eR, b, bz, by, bx);
+    msc3d_load_segment(A, xo, yo, self, zp, yp, eR, a, az, ay, ax);
+    msc3d_load_segment(B, xo, yo, self, zp, yp, eR, b, bz, by, bx);
     uint32_t x[8], sb[8], cb[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {  // overlap.rs:266-276: x = 1 where q_i = -1; link word = x_i ^ x_fwd
@@ -378,6 +436,49 @@ __device__ __forceinline__ void msc3d_pair_item(const uint32_t *A, const uint32_
     vl.add8_8(sb, cb);
 }
 
+// the pair item of the in-sweep-energy path: also the down-spin counts of both replicas (their words are loaded anyway)
+constexpr int MSC3D_KQ = 6;  // planes of the per-thread q / down-spin counters of that path (4 items * 8 sites = 32)
+constexpr int MSC3D_KL = 7;  // planes of its link counters (3 * 32 = 96)
+__device__ __forceinline__ void msc3d_pairm_item(const uint32_t *A, const uint32_t *B, const uint32_t N2, const uint4 desc,
+                                                 VAcc<MSC3D_KL> &vl, VAcc<MSC3D_KQ> &vq, VAcc<MSC3D_KQ> &vma,
+                                                 VAcc<MSC3D_KQ> &vmb) {
+    uint32_t self, zp, zm, yp, ym, eL, eR, par;
+    unpack_item(desc, self, zp, zm, yp, ym, eL, eR, par);
+    (void)zm; (void)ym; (void)eL;
+    const uint32_t xo = (par & 1u) ? 0u : N2, yo = N2 - xo;
+    uint32_t a[8], az[8], ay[8], ax[8], b[8], bz[8], by[8], bx[8];
+    msc3d_load_segment(A, xo, yo, self, zp, yp, eR, a, az, ay, ax);
+    msc3d_load_segment(B, xo, yo, self, zp, yp, eR, b, bz, by, bx);
+    vma.add8(a);
+    vmb.add8(b);
+    uint32_t x[8], sb[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        x[j] = a[j] ^ b[j];
+        const uint32_t l0 = xor3(x[j], az[j], bz[j]), l1 = xor3(x[j], ay[j], by[j]), l2 = xor3(x[j], ax[j], bx[j]);
+        sb[j] = xor3(l0, l1, l2);
+        cb[j] = maj3(l0, l1, l2);
+    }
+    vq.add8(x);
+    vl.add8_8(sb, cb);
+}
+
+// Sum the KI-plane counters that `nw` warps parked in shared memory ([plane][nw * 32] words at `src`) lane by lane and
+// return this thread's lane total (thread l: realization l of the word group).
+// One copy of the code for every quantity (KI <= MSC3D_KL planes; the planes a quantity does not have read as zero).
+__device__ __noinline__ uint32_t merge_lane_total(const uint32_t *src, const int ki, const int nw, const int lane) {
+    VAcc<MSC3D_KL + 3> acc;  // nw <= 8
+    acc.clear();
+#pragma unroll 1
+    for (int k = 0; k < nw; k++) {
+        uint32_t x[MSC3D_KL];
+#pragma unroll
+        for (int b = 0; b < MSC3D_KL; b++) x[b] = b < ki ? src[(b * nw + k) * 32 + lane] : 0u;
+        acc.template add_planes<MSC3D_KL>(x);
+    }
+    return warp_lane_total(acc);
+}
+
 // ------------------------------------------------------------------------------------------------
 // grid.x = G * ceil(T / NH); block = NH * 256 threads.  Half h of CTA (g, tp) owns temperature slot t = tp*NH + h of
 // word group g for all RPC replicas; the halves share the coupling words and the item table in shared memory and
@@ -387,7 +488,7 @@ template <int RPC, bool METRO, int NH>
 __global__ void __launch_bounds__(MSC3D_NTH *NH, NH == 1 ? 2 : 1)
 msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags,
              int want_overlap, int want_fold, int64_t group_offset, long long *dot_spin, long long *dot_link,
-             uint32_t *words_out, const uint32_t *swap_mask, int pt_schedule, int pt_parity) {
+             uint32_t *words_out, const uint32_t *swap_mask, int pt_schedule, int pt_parity, int esw) {
     extern __shared__ __align__(128) uint32_t smem[];
     const uint32_t N = gv.N, N2 = gv.N2;
     uint32_t *Jsm = smem;
@@ -521,22 +622,36 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     if (bulk_mask != (1u << RPC) - 1u) half_barrier(half, MSC3D_NTH);  // gathered words were written with plain stores
 
     // ---- sweeps: colour 0 then colour 1 (RNG-SPEC visit order)
+    // In-sweep energy (esw, host-checked: one slot per CTA, an even number of replicas, at most two quads per thread and
+    // room for the counters in the coupling-word area): the colour-1 pass of the last sweep also counts the unsatisfied
+    // bonds, and the epilogue below only has the replica pairs left to walk.
+    constexpr bool ESW_OK = NH == 1 && RPC >= 2;
+    const bool esw_on = ESW_OK && esw && n_sweeps > 0 && want_energy && (want_mags != 0) == (want_overlap != 0);
+    VAcc<MSC3D_KS> ea[RPC];
+#pragma unroll
+    for (int r = 0; r < RPC; r++) ea[r].clear();
     for (int sw = 0; sw < n_sweeps; sw++) {
 #pragma unroll 1
         for (int c = 0; c < 2; c++) {
             const uint32_t so = c * N2, oo = (1 - c) * N2;  // word offsets of the updated / the other colour half
             const uint32_t tag = TAG_SWEEP_MSC | (uint32_t)c;
             uint4 next = ht < gv.n_items ? item_at(ht) : make_uint4(0, 0, 0, 0);
+            if (ESW_OK && esw_on && c == 1 && sw == n_sweeps - 1) {
 #pragma unroll 1
-            for (int it = ht; it < gv.n_items; it += MSC3D_NTH) {
-                const uint4 desc = next;
-                if (it + MSC3D_NTH < gv.n_items) next = item_at(it + MSC3D_NTH);
-                if (((desc.w >> 16) ^ (uint32_t)c) & 1u)
-                    msc3d_sweep_item<RPC, METRO, true>(sp, J, N, so, oo, desc, thr, nthr, gv.one, sweep_index + (uint32_t)sw,
-                                                       (uint32_t)t, (uint32_t)m.T, tag, k0, k1);
-                else
-                    msc3d_sweep_item<RPC, METRO, false>(sp, J, N, so, oo, desc, thr, nthr, gv.one, sweep_index + (uint32_t)sw,
-                                                        (uint32_t)t, (uint32_t)m.T, tag, k0, k1);
+                for (int it = ht; it < gv.n_items; it += MSC3D_NTH) {
+                    const uint4 desc = next;
+                    if (it + MSC3D_NTH < gv.n_items) next = item_at(it + MSC3D_NTH);
+                    msc3d_sweep_item<RPC, METRO, ESW_OK>(sp, J, N, so, oo, desc, (((desc.w >> 16) ^ 1u) & 1u) != 0u, thr, nthr, gv.one,
+                                                         sweep_index + (uint32_t)sw, (uint32_t)t, (uint32_t)m.T, tag, k0, k1, ea);
+                }
+            } else {
+#pragma unroll 1
+                for (int it = ht; it < gv.n_items; it += MSC3D_NTH) {
+                    const uint4 desc = next;
+                    if (it + MSC3D_NTH < gv.n_items) next = item_at(it + MSC3D_NTH);
+                    msc3d_sweep_item<RPC, METRO, false>(sp, J, N, so, oo, desc, (((desc.w >> 16) ^ (uint32_t)c) & 1u) != 0u, thr, nthr,
+                                                        gv.one, sweep_index + (uint32_t)sw, (uint32_t)t, (uint32_t)m.T, tag, k0, k1, nullptr);
+                }
             }
             half_barrier(half, MSC3D_NTH);
         }
@@ -560,11 +675,66 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     // with a bit-sliced butterfly; partial lane totals meet in shared memory.
     if (want_energy || want_mags || want_overlap) {
         constexpr int NP = RPC / 2;              // replica pairs
+        const int w = ht >> 5, lane = ht & 31;
+        // where the final lane totals end up: [replica r][E, M][fin_wpe][32] and [pair p][q, ql][fin_wpp][32]
+        const uint32_t *fin_e = nullptr, *fin_p = nullptr;
+        int fin_wpe = 1, fin_wpp = 1;
+        if (ESW_OK && esw_on) {
+            // ---- in-sweep energy path.  The coupling words are dead after the last pass: their area takes the per-thread
+            // counters (merged across the eight warps with bit-sliced adds, one butterfly per quantity) and the lane totals.
+            constexpr int WPPX = NP > 0 ? 8 / NP : 8;  // warps per pair: all eight warps walk the pairs
+            uint32_t *scr = smem;
+            uint32_t *res = smem + 3 * N - 512;
+            uint32_t *res_p = res + RPC * 2 * 32;
+#pragma unroll
+            for (int r = 0; r < RPC; r++)
+#pragma unroll
+                for (int b = 0; b < MSC3D_KS; b++) scr[(r * MSC3D_KS + b) * MSC3D_NTH + ht] = ea[r].p[b];
+            half_barrier(half, MSC3D_NTH);
+            if (w < RPC) res[(w * 2 + 0) * 32 + lane] = merge_lane_total(scr + w * MSC3D_KS * MSC3D_NTH, MSC3D_KS, 8, lane);
+            if (NP > 0 && want_overlap) {
+                const int p = w / WPPX, sub = w % WPPX;
+                const uint32_t *A = sp + (size_t)(2 * p) * N, *B = sp + (size_t)(2 * p + 1) * N;
+                VAcc<MSC3D_KL> vl;
+                VAcc<MSC3D_KQ> vq, vma, vmb;
+                vl.clear(); vq.clear(); vma.clear(); vmb.clear();
+                const int it0 = lane + 32 * sub;
+                uint4 next = it0 < gv.n_items ? item_at(it0) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+                for (int it = it0; it < gv.n_items; it += 32 * WPPX) {
+                    const uint4 desc = next;
+                    if (it + 32 * WPPX < gv.n_items) next = item_at(it + 32 * WPPX);
+                    msc3d_pairm_item(A, B, N2, desc, vl, vq, vma, vmb);
+                }
+                half_barrier(half, MSC3D_NTH);  // the energy counters have been consumed
+                // park: pair p at scr + p * PW, quantities [q | ql | M_a | M_b], each [plane][WPPX * 32]
+                constexpr int QW = MSC3D_KQ * WPPX * 32, LW = MSC3D_KL * WPPX * 32, PW = 3 * QW + LW;
+                uint32_t *base = scr + p * PW + sub * 32 + lane;
+#pragma unroll
+                for (int b = 0; b < MSC3D_KQ; b++) {
+                    base[b * WPPX * 32] = vq.p[b];
+                    base[QW + LW + b * WPPX * 32] = vma.p[b];
+                    base[2 * QW + LW + b * WPPX * 32] = vmb.p[b];
+                }
+#pragma unroll
+                for (int b = 0; b < MSC3D_KL; b++) base[QW + b * WPPX * 32] = vl.p[b];
+                half_barrier(half, MSC3D_NTH);
+                if (w < NP * 4) {  // one warp per (pair, quantity)
+                    const int p2 = w >> 2, qn = w & 3;
+                    const uint32_t *src = scr + p2 * PW;
+                    // qn: 0 = q, 1 = q_link, 2 = down spins of replica 2p, 3 = of replica 2p + 1
+                    const uint32_t *q_src = src + (qn == 0 ? 0 : qn == 1 ? QW : qn == 2 ? QW + LW : 2 * QW + LW);
+                    uint32_t *q_dst = qn < 2 ? res_p + (p2 * 2 + qn) * 32 : res + ((2 * p2 + qn - 2) * 2 + 1) * 32;
+                    q_dst[lane] = merge_lane_total(q_src, qn == 1 ? MSC3D_KL : MSC3D_KQ, WPPX, lane);
+                }
+            }
+            half_barrier(half, MSC3D_NTH);
+            fin_e = res; fin_p = res_p;
+        } else {
         constexpr int WPP = NP > 0 ? 4 / NP : 1; // warps per pair
         // energy / magnetisation: warps 0..3 when the other four take the replica pairs, else all eight
         const bool pairs_on = NP > 0 && want_overlap;
         const int n_em = pairs_on ? 4 : 8, WPE = n_em / RPC;  // warps per replica
-        const int w = ht >> 5, lane = ht & 31;
         // red layout: [replica r][E, M][WPE][32] then [pair p][q, ql][WPP][32]
         uint32_t *red_p = red + RPC * 2 * WPE * 32;
         uint32_t tot0 = 0, tot1 = 0;  // this warp's two lane totals: (E, M) or (q, ql)
@@ -579,8 +749,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll 1
                 for (int it = lane + 32 * sub; it < gv.n_items; it += 32 * WPE) {
                     const uint4 desc = item_at(it);
-                    if ((desc.w >> 16) & 1u) msc3d_em_item<true>(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
-                    else msc3d_em_item<false>(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
+                    msc3d_em_item(A, J, N, N2, desc, want_energy, want_mags, ve, vm);
                 }
                 if (want_energy) { tot0 = warp_lane_total(ve); slot0 = red + ((r * 2 + 0) * WPE + sub) * 32 + lane; }
                 if (want_mags) { tot1 = warp_lane_total(vm); slot1 = red + ((r * 2 + 1) * WPE + sub) * 32 + lane; }
@@ -595,8 +764,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll 1
                 for (int it = lane + 32 * sub; it < gv.n_items; it += 32 * WPP) {
                     const uint4 desc = item_at(it);
-                    if ((desc.w >> 16) & 1u) msc3d_pair_item<true>(A, B, N2, desc, vl, vq);
-                    else msc3d_pair_item<false>(A, B, N2, desc, vl, vq);
+                    msc3d_pair_item(A, B, N2, desc, vl, vq);
                 }
                 tot0 = warp_lane_total(vq); slot0 = red_p + ((p * 2 + 0) * WPP + sub) * 32 + lane;
                 tot1 = warp_lane_total(vl); slot1 = red_p + ((p * 2 + 1) * WPP + sub) * 32 + lane;
@@ -609,6 +777,8 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         if (slot0) *slot0 = tot0;
         if (slot1) *slot1 = tot1;
         half_barrier(half, MSC3D_NTH);
+        fin_e = red; fin_p = red_p; fin_wpe = WPE; fin_wpp = WPP;
+        }
         // warp 0 of the half: lane l finishes realization 32g + l at slot t -- per-system energy / magnetisation, pair
         // dots, and (want_fold) the recorded-sweep fold of simulation/mod.rs:543-578 + statistics/overlap.rs:283-306
         const int64_t d = g * 32 + lane;
@@ -618,9 +788,9 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll
             for (int r = 0; r < RPC; r++) {
                 uint32_t e = 0, dn = 0;
-                for (int k = 0; k < WPE; k++) {
-                    if (want_energy) e += red[((r * 2 + 0) * WPE + k) * 32 + lane];
-                    if (want_mags) dn += red[((r * 2 + 1) * WPE + k) * 32 + lane];
+                for (int k = 0; k < fin_wpe; k++) {
+                    if (want_energy) e += fin_e[((r * 2 + 0) * fin_wpe + k) * 32 + lane];
+                    if (want_mags) dn += fin_e[((r * 2 + 1) * fin_wpe + k) * 32 + lane];
                 }
                 // sum_i sum_d s s J = (#bonds) - 2 * unsatisfied, e = that / N in f32   (energy.rs:103-108)
                 Ev[r] = __fdiv_rn((float)(3ll * N - 2ll * e), (float)N);
@@ -633,10 +803,9 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll
                 for (int p = 0; p < NP; p++) {
                     uint32_t cs = 0, cl = 0;
-#pragma unroll
-                    for (int k = 0; k < WPP; k++) {
-                        cs += red_p[((p * 2 + 0) * WPP + k) * 32 + lane];
-                        cl += red_p[((p * 2 + 1) * WPP + k) * 32 + lane];
+                    for (int k = 0; k < fin_wpp; k++) {
+                        cs += fin_p[((p * 2 + 0) * fin_wpp + k) * 32 + lane];
+                        cl += fin_p[((p * 2 + 1) * fin_wpp + k) * 32 + lane];
                     }
                     Sv[p] = (long long)N - 2ll * cs;
                     Lv[p] = 3ll * N - 2ll * cl;

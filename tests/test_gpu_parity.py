@@ -151,7 +151,10 @@ MSC3D_CASES = [
     ((2, 2, 8), "bimodal", 32, 4, [1.0, 2.0]),                        # extent 2: forward == backward neighbour
     ((6, 4, 16), "bimodal", 64, 2, [0.8, 1.2]),
     ((8, 8, 8), "ferro", 32, 2, [3.5, 4.5, 5.5]),                     # no coupling words
-    ((16, 16, 16), "bimodal", 64, 4, np.linspace(0.8, 1.4, 3)),       # BASELINE config 2 geometry, R = 4
+    ((16, 16, 16), "bimodal", 64, 4, np.linspace(0.8, 1.4, 3)),       # BASELINE config 2 geometry, R = 4 (in-sweep energy path)
+    ((16, 16, 16), "bimodal", 33, 2, [0.8, 1.1, 1.4, 1.7]),           # the same path with one replica pair, padded group
+    ((16, 16, 16), "ferro", 32, 4, [4.2, 4.5]),
+    ((16, 16, 16), "bimodal", 32, 1, [0.9, 1.3]),                     # R = 1: epilogue walks the spins for E and M
 ]
 
 
