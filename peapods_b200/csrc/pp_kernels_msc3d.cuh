@@ -465,16 +465,30 @@ __device__ __forceinline__ void msc3d_pairm_item(const uint32_t *A, const uint32
 
 // Sum the KI-plane counters that `nw` warps parked in shared memory ([plane][nw * 32] words at `src`) lane by lane and
 // return this thread's lane total (thread l: realization l of the word group).
-// One copy of the code for every quantity (KI <= MSC3D_KL planes; the planes a quantity does not have read as zero).
-__device__ __noinline__ uint32_t merge_lane_total(const uint32_t *src, const int ki, const int nw, const int lane) {
-    VAcc<MSC3D_KL + 3> acc;  // nw <= 8
-    acc.clear();
-#pragma unroll 1
-    for (int k = 0; k < nw; k++) {
-        uint32_t x[MSC3D_KL];
+// One out-of-line copy per (planes, warps) combination; the ripple of the k-th addend stops where its carry can still reach.
+template <int KI, int NW>
+__device__ __noinline__ uint32_t merge_lane_total(const uint32_t *src, const int lane) {
+    constexpr int LG = NW <= 1 ? 0 : NW <= 2 ? 1 : NW <= 4 ? 2 : 3;
+    VAcc<KI + LG> acc;
 #pragma unroll
-        for (int b = 0; b < MSC3D_KL; b++) x[b] = b < ki ? src[(b * nw + k) * 32 + lane] : 0u;
-        acc.template add_planes<MSC3D_KL>(x);
+    for (int b = 0; b < KI + LG; b++) acc.p[b] = b < KI ? src[(b * NW) * 32 + lane] : 0u;
+#pragma unroll
+    for (int k = 1; k < NW; k++) {
+        const int top = KI + (k < 2 ? 1 : k < 4 ? 2 : 3);  // planes of the running sum after this addend
+        uint32_t c = 0u;
+#pragma unroll
+        for (int b = 0; b < KI + LG; b++) {
+            if (b < KI) {
+                const uint32_t x = src[(b * NW + k) * 32 + lane];
+                const uint32_t sum = xor3(acc.p[b], x, c);
+                c = maj3(acc.p[b], x, c);
+                acc.p[b] = sum;
+            } else if (b < top) {
+                const uint32_t t = acc.p[b] & c;
+                acc.p[b] ^= c;
+                c = t;
+            }
+        }
     }
     return warp_lane_total(acc);
 }
@@ -561,46 +575,76 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
             if ((mk[r][0] | mk[r][1]) == 0u) bulk_mask |= 1u << r;
         }
     }
-    if (ht == 0) {
-        mbar_expect_tx(&bars[1 + half], bytes * (uint32_t)__popc(bulk_mask));
+    if (ht == 0) {  // every system arrives by bulk-async copy
+        mbar_expect_tx(&bars[1 + half], bytes * (uint32_t)RPC);
 #pragma unroll
         for (int r = 0; r < RPC; r++)
-            if (bulk_mask >> r & 1u)
-                bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, &bars[1 + half]);
+            bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, &bars[1 + half]);
     }
+    // Systems with crossing lanes: the neighbouring slots' words are read with plain loads (two replicas per round, all loads
+    // of a round in flight together, issued before the wait for the bulk copies) and merged into the staged words.
+    if (bulk_mask != (1u << RPC) - 1u) {
+        const uint32_t n4 = N / 4;
+        bool waited = false;
 #pragma unroll
-    for (int r = 0; r < RPC; r++) {
-        if (bulk_mask >> r & 1u) continue;
-        const uint32_t *base = m.words + (g * m.S + (int64_t)r * m.T) * (int64_t)N;  // slot 0 of this replica's ladder
-        const uint4 *wa = reinterpret_cast<const uint4 *>(base + (int64_t)t * N);
-        uint4 *dst = reinterpret_cast<uint4 *>(sp + (size_t)r * N);
-        if (pt_schedule == 0) {
-            const uint32_t mL = mk[r][0], mR = mk[r][1];
-            const uint4 *wl = reinterpret_cast<const uint4 *>(base + (int64_t)(t - 1) * N);
-            const uint4 *wr = reinterpret_cast<const uint4 *>(base + (int64_t)(t + 1) * N);
-#pragma unroll 8
-            for (uint32_t i = ht; i < N / 4; i += MSC3D_NTH) {
-                const uint4 a = __ldg(wa + i);
-                uint4 o = a;
-                if (mL) { const uint4 b = __ldg(wl + i); o.x ^= (a.x ^ b.x) & mL; o.y ^= (a.y ^ b.y) & mL; o.z ^= (a.z ^ b.z) & mL; o.w ^= (a.w ^ b.w) & mL; }
-                if (mR) { const uint4 c = __ldg(wr + i); o.x ^= (a.x ^ c.x) & mR; o.y ^= (a.y ^ c.y) & mR; o.z ^= (a.z ^ c.z) & mR; o.w ^= (a.w ^ c.w) & mR; }
-                dst[i] = o;
-            }
-        } else {
-            const uint32_t m1 = mk[r][0], m2 = mk[r][1], m12 = mk[r][2];
-            const uint4 *w1p = reinterpret_cast<const uint4 *>(base + (int64_t)max(t1, 0) * N);
-            const uint4 *w2p = reinterpret_cast<const uint4 *>(base + (int64_t)max(t2, 0) * N);
-            const uint4 *w21p = reinterpret_cast<const uint4 *>(base + (int64_t)max(t21, 0) * N);
-#pragma unroll 8
-            for (uint32_t i = ht; i < N / 4; i += MSC3D_NTH) {
-                uint4 a = __ldg(wa + i);
-                if (m1) { const uint4 b = __ldg(w1p + i); a.x ^= (a.x ^ b.x) & m1; a.y ^= (a.y ^ b.y) & m1; a.z ^= (a.z ^ b.z) & m1; a.w ^= (a.w ^ b.w) & m1; }
-                if (m2) {
-                    uint4 c = __ldg(w2p + i);
-                    if (m12) { const uint4 e = __ldg(w21p + i); c.x ^= (c.x ^ e.x) & m12; c.y ^= (c.y ^ e.y) & m12; c.z ^= (c.z ^ e.z) & m12; c.w ^= (c.w ^ e.w) & m12; }
-                    a.x ^= (a.x ^ c.x) & m2; a.y ^= (a.y ^ c.y) & m2; a.z ^= (a.z ^ c.z) & m2; a.w ^= (a.w ^ c.w) & m2;
+        for (int rb = 0; rb < RPC; rb += 2) {
+            if ((((~bulk_mask) >> rb) & 3u) == 0u) continue;
+            for (uint32_t i0 = 0; i0 < n4; i0 += 4 * MSC3D_NTH) {
+                uint4 nb[2][4][3];
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int r = rb + rr;
+                    if (r >= RPC || (bulk_mask >> r & 1u)) continue;
+                    const uint32_t *base = m.words + (g * m.S + (int64_t)r * m.T) * (int64_t)N;  // slot 0 of this replica's ladder
+                    const uint4 *s0, *s1, *s2;
+                    if (pt_schedule == 0) {
+                        s0 = reinterpret_cast<const uint4 *>(base + (int64_t)(t - 1) * N);
+                        s1 = reinterpret_cast<const uint4 *>(base + (int64_t)(t + 1) * N);
+                        s2 = s1;
+                    } else {
+                        s0 = reinterpret_cast<const uint4 *>(base + (int64_t)max(t1, 0) * N);
+                        s1 = reinterpret_cast<const uint4 *>(base + (int64_t)max(t2, 0) * N);
+                        s2 = reinterpret_cast<const uint4 *>(base + (int64_t)max(t21, 0) * N);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t i = i0 + k * MSC3D_NTH + ht;
+                        if (i < n4) {
+                            if (mk[r][0]) nb[rr][k][0] = __ldg(s0 + i);
+                            if (mk[r][1]) nb[rr][k][1] = __ldg(s1 + i);
+                            if (pt_schedule == 1 && mk[r][1] && mk[r][2]) nb[rr][k][2] = __ldg(s2 + i);
+                        }
+                    }
                 }
-                dst[i] = a;
+                if (!waited) { mbar_wait(&bars[1 + half], 0); waited = true; }
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int r = rb + rr;
+                    if (r >= RPC || (bulk_mask >> r & 1u)) continue;
+                    uint4 *dst = reinterpret_cast<uint4 *>(sp + (size_t)r * N);
+                    const uint32_t m0 = mk[r][0], m1 = mk[r][1], m2 = mk[r][2];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t i = i0 + k * MSC3D_NTH + ht;
+                        if (i < n4) {
+                            uint4 a = dst[i];
+                            if (pt_schedule == 0) {
+                                uint4 o = a;
+                                if (m0) { const uint4 b = nb[rr][k][0]; o.x ^= (a.x ^ b.x) & m0; o.y ^= (a.y ^ b.y) & m0; o.z ^= (a.z ^ b.z) & m0; o.w ^= (a.w ^ b.w) & m0; }
+                                if (m1) { const uint4 c = nb[rr][k][1]; o.x ^= (a.x ^ c.x) & m1; o.y ^= (a.y ^ c.y) & m1; o.z ^= (a.z ^ c.z) & m1; o.w ^= (a.w ^ c.w) & m1; }
+                                a = o;
+                            } else {
+                                if (m0) { const uint4 b = nb[rr][k][0]; a.x ^= (a.x ^ b.x) & m0; a.y ^= (a.y ^ b.y) & m0; a.z ^= (a.z ^ b.z) & m0; a.w ^= (a.w ^ b.w) & m0; }
+                                if (m1) {
+                                    uint4 c = nb[rr][k][1];
+                                    if (m2) { const uint4 e = nb[rr][k][2]; c.x ^= (c.x ^ e.x) & m2; c.y ^= (c.y ^ e.y) & m2; c.z ^= (c.z ^ e.z) & m2; c.w ^= (c.w ^ e.w) & m2; }
+                                    a.x ^= (a.x ^ c.x) & m1; a.y ^= (a.y ^ c.y) & m1; a.z ^= (a.z ^ c.z) & m1; a.w ^= (a.w ^ c.w) & m1;
+                                }
+                            }
+                            dst[i] = a;
+                        }
+                    }
+                }
             }
         }
     }
@@ -691,7 +735,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll
                 for (int b = 0; b < MSC3D_KS; b++) scr[(r * MSC3D_KS + b) * MSC3D_NTH + ht] = ea[r].p[b];
             half_barrier(half, MSC3D_NTH);
-            if (w < RPC) res[(w * 2 + 0) * 32 + lane] = merge_lane_total(scr + w * MSC3D_KS * MSC3D_NTH, MSC3D_KS, 8, lane);
+            if (w < RPC) res[(w * 2 + 0) * 32 + lane] = merge_lane_total<MSC3D_KS, 8>(scr + w * MSC3D_KS * MSC3D_NTH, lane);
             if (NP > 0 && want_overlap) {
                 const int p = w / WPPX, sub = w % WPPX;
                 const uint32_t *A = sp + (size_t)(2 * p) * N, *B = sp + (size_t)(2 * p + 1) * N;
@@ -725,7 +769,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                     // qn: 0 = q, 1 = q_link, 2 = down spins of replica 2p, 3 = of replica 2p + 1
                     const uint32_t *q_src = src + (qn == 0 ? 0 : qn == 1 ? QW : qn == 2 ? QW + LW : 2 * QW + LW);
                     uint32_t *q_dst = qn < 2 ? res_p + (p2 * 2 + qn) * 32 : res + ((2 * p2 + qn - 2) * 2 + 1) * 32;
-                    q_dst[lane] = merge_lane_total(q_src, qn == 1 ? MSC3D_KL : MSC3D_KQ, WPPX, lane);
+                    q_dst[lane] = qn == 1 ? merge_lane_total<MSC3D_KL, WPPX>(q_src, lane) : merge_lane_total<MSC3D_KQ, WPPX>(q_src, lane);
                 }
             }
             half_barrier(half, MSC3D_NTH);
