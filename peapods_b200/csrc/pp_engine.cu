@@ -185,8 +185,8 @@ struct pp_sim {
     bool hist_allocated = false;
     int64_t launches = 0;
     // chunked multi-stream execution of the msc3d path (see pp_sample)
-    int n_streams = 4;
-    int64_t chunk_bytes = int64_t(8) << 20;
+    int n_streams = 8;
+    int64_t chunk_bytes = 0;                           // 0: one chunk per stream, between 8 and 32 MiB of spin words (measured best)
     int64_t macro_batch = 16;
     int64_t chunk_groups = 0;                          // > 0: word groups per chunk (overrides chunk_bytes; tests)
     int64_t max_batch = 64;                            // sweeps without reduction / PT fused into one launch (multispin)
@@ -1220,7 +1220,12 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     int64_t macro_batch = 1;
     if (msc && s->msc3d && !s->profile && s->n_streams > 1) {
         const int64_t group_bytes = (int64_t)m.S * m.N * 4;
-        const int64_t gpc = s->chunk_groups > 0 ? s->chunk_groups : std::max<int64_t>(1, s->chunk_bytes / group_bytes);
+        int64_t gpc = s->chunk_groups;
+        if (gpc <= 0 && s->chunk_bytes > 0) gpc = std::max<int64_t>(1, s->chunk_bytes / group_bytes);
+        if (gpc <= 0) {
+            const int64_t lo = std::max<int64_t>(1, (int64_t(8) << 20) / group_bytes), hi = std::max<int64_t>(lo, (int64_t(32) << 20) / group_bytes);
+            gpc = std::min(hi, std::max(lo, (s->G + s->n_streams - 1) / s->n_streams));
+        }
         const int64_t n_chunks = (s->G + gpc - 1) / gpc;
         if (n_chunks > 1) {
             pp_status stx = ensure_streams(s, (int)std::min<int64_t>(n_chunks, s->n_streams));
