@@ -397,16 +397,16 @@ static Ctx chunk_ctx(pp_sim *s, int64_t d0, int64_t D, cudaStream_t stream) {
 
 static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags);
 
-template <int RPC, bool METRO, int NH>
+template <int RPC, bool METRO, int NH, int NFIX = 0>
 static pp_status launch_msc3d_t(pp_sim *s, Ctx &c, const ModelView &m, uint32_t sweep_index, int n_sweeps,
                                 bool want_energy, bool want_mags, bool want_overlap, bool want_fold) {
     static bool configured = false;  // per instantiation
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO, NH, NFIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     const unsigned grid = (unsigned)(c.G * ((m.T + NH - 1) / NH));
-    msc3d_kernel<RPC, METRO, NH><<<grid, MSC3D_NTH * NH, s->msc3d_smem, c.stream>>>(
+    msc3d_kernel<RPC, METRO, NH, NFIX><<<grid, MSC3D_NTH * NH, s->msc3d_smem, c.stream>>>(
         m, s->gv, c.st, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold, m.sample_offset / 32, c.dot_spin,
         c.dot_link, c.words_alt, c.swap_pending ? c.pt.swap_mask : nullptr, c.pend_schedule, c.pend_parity, s->msc3d_esw ? 1 : 0);
     s->launches++;
@@ -433,6 +433,11 @@ static pp_status launch_msc3d(pp_sim *s, Ctx &c, const ModelView &m, int sweep_m
     const bool two = s->msc3d_nh == 2;
 #define PP_M3A(R_, M_, H_) launch_msc3d_t<R_, M_, H_>(s, c, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold)
 #define PP_M3(R_) return metro ? (two ? PP_M3A(R_, true, 2) : PP_M3A(R_, true, 1)) : (two ? PP_M3A(R_, false, 2) : PP_M3A(R_, false, 1))
+    // the 16^3 lattice of the headline configuration with one slot per CTA: site count as a compile-time constant
+    if (m.N == 4096 && !two && metro && (m.R == 2 || m.R == 4)) {
+        if (m.R == 4) return launch_msc3d_t<4, true, 1, 4096>(s, c, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold);
+        return launch_msc3d_t<2, true, 1, 4096>(s, c, m, sweep_index, n_sweeps, want_energy, want_mags, want_overlap, want_fold);
+    }
     switch (m.R) {
         case 1: PP_M3(1);
         case 2: PP_M3(2);

@@ -498,13 +498,14 @@ __device__ __noinline__ uint32_t merge_lane_total(const uint32_t *src, const int
 // word group g for all RPC replicas; the halves share the coupling words and the item table in shared memory and
 // otherwise run independently (named barriers), so one half can stage data while the other computes.
 // dynamic smem (words): [3N coupling words | 4*n_items item table | NH*RPC*N spins | 8 (mbarriers) | NH*512 scratch]
-template <int RPC, bool METRO, int NH>
+// NFIX > 0: the site count is this compile-time constant (replica / direction strides become immediates); 0: gv.N
+template <int RPC, bool METRO, int NH, int NFIX = 0>
 __global__ void __launch_bounds__(MSC3D_NTH *NH, NH == 1 ? 2 : 1)
 msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags,
              int want_overlap, int want_fold, int64_t group_offset, long long *dot_spin, long long *dot_link,
              uint32_t *words_out, const uint32_t *swap_mask, int pt_schedule, int pt_parity, int esw) {
     extern __shared__ __align__(128) uint32_t smem[];
-    const uint32_t N = gv.N, N2 = gv.N2;
+    const uint32_t N = NFIX > 0 ? (uint32_t)NFIX : gv.N, N2 = NFIX > 0 ? (uint32_t)NFIX / 2 : gv.N2;
     uint32_t *Jsm = smem;
     // NH == 2: the item table is staged in shared memory and the reduction scratch has its own space.
     // NH == 1: two CTAs share an SM (the spins and coupling words of one CTA are half of its shared memory to the
