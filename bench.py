@@ -47,8 +47,8 @@ Z = 3
 SEED = 42
 B_ALG_MSC = 0.125 + 0.125 + (Z / 8.0) / (N_TEMPS * N_REPLICAS)  # bytes per attempt
 # dram__bytes_read.sum + dram__bytes_write.sum of one msc3d_kernel launch covering 1024 samples, mean of the three launches of
-# the `ncu --set full` capture summarised in profiles/r1g_msc3d_summary.md; a launch over D samples moves D/1024 times that
-NCU_DRAM_BYTES_PER_1024_SAMPLES = 127.7e6
+# the `ncu --set full` capture summarised in profiles/r1k_msc3d_summary.md; a launch over D samples moves D/1024 times that
+NCU_DRAM_BYTES_PER_1024_SAMPLES = 125.8e6
 
 
 def peaks():
@@ -165,7 +165,7 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     n_samples = max(cores, 16) * 2
-    n_sweeps = args.sweeps_per_step
+    n_sweeps = min(args.sweeps_per_step, 256)  # bounded CPU step (the metric is a rate: attempts per ns)
     # bounded: scale the sample so one step stays near a few seconds
     for _ in range(args.warmup):
         cpu_baseline_run(n_samples, max(2, n_sweeps // 8), cores)
@@ -182,7 +182,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 multispin words / int8 spins (CPU: int8 + f32)",
-        "data": "synthetic", "config": workload_config(args, n_samples),
+        "data": "synthetic", "config": dict(workload_config(args, n_samples), sweeps_per_step=n_sweeps),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C restatement of the reference CPU path (oracle/pp_oracle.c); the Rust crate cannot be built here",
@@ -285,7 +285,7 @@ def run_ours(args):
     achieved = alg_bytes_per_launch / (k_ms / k_n * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": args.traffic if args.traffic is not None else NCU_DRAM_BYTES_PER_1024_SAMPLES * D / 1024.0 * (k_n_expected / k_n),
-                "traffic_source": "ncu --set full (profiles/r1g_msc3d_summary.md), scaled to this launch size",
+                "traffic_source": "ncu --set full (profiles/r1k_msc3d_summary.md), scaled to this launch size",
                 "kernel": "msc3d_kernel (sweep + energy / magnetisation / overlap / fold)", "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes_per_launch, "launches_timed": k_n, "kernel_ms_mean": k_ms / k_n,
                 "kernel_share_of_step": k_ms / max(sim.last_sweep_loop_ms, 1e-9)}
@@ -475,7 +475,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--sweeps-per-step", type=int, default=256)
+    ap.add_argument("--sweeps-per-step", type=int, default=None,
+                    help="sweeps of one sample() call = one step (default: 1024 for c2, 32 for c5; the CPU arm caps its steps at 256)")
     ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
@@ -485,9 +486,11 @@ def main():
     if args.warmup < 3:
         args.warmup = max(args.warmup, 0)
     if args.workload == "c5" and args.impl == "ours":
-        if args.sweeps_per_step == 256:
+        if args.sweeps_per_step is None:
             args.sweeps_per_step = 32
         return run_c5(args)
+    if args.sweeps_per_step is None:
+        args.sweeps_per_step = 1024
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 

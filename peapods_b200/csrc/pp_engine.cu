@@ -219,9 +219,25 @@ static void prof_mark(pp_sim *s, cudaStream_t stream) {
     cudaEventRecord(s->prof_events[s->prof_used++], stream);
 }
 
-// Stream-ordered allocations from the device's default memory pool with an unlimited release threshold: buffers of a
-// destroyed handle stay cached in the pool, so constructing the next handle (the reference API builds one
-// IsingSimulation per model) does not pay cudaMalloc / cudaFree again.
+// Device buffers come from the device's default stream-ordered pool (unlimited release threshold) through an exact-size
+// block cache: the reference API builds one IsingSimulation per model, and a destroyed handle's buffers are handed to
+// the next handle of the same shape without touching the driver (the pool alone re-maps physical memory whenever its
+// best-fit carving of the freed 4 GiB histogram blocks leaves no hole large enough: 60-500 ms per construction).
+// A block enters the cache only after the work that used it has completed (callers synchronise first).
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;  // (device, bytes) -> block
+    std::map<void *, std::pair<int, size_t>> live;              // block -> (device, bytes)
+    size_t cached_bytes = 0, cap_bytes = size_t(64) << 30;
+    BlockCache() {
+        if (const char *e = getenv("PP_CACHE_GIB")) cap_bytes = (size_t)std::max(0, atoi(e)) << 30;
+    }
+};
+static BlockCache &block_cache() {
+    static BlockCache *c = new BlockCache();  // never destroyed: handles may outlive static destructors
+    return *c;
+}
+
 static cudaError_t pool_alloc(pp_sim *s, void **p, size_t bytes) {
     static std::mutex mu;
     static std::map<int, bool> configured;
@@ -236,10 +252,61 @@ static cudaError_t pool_alloc(pp_sim *s, void **p, size_t bytes) {
             configured[s->device] = true;
         }
     }
-    return cudaMallocAsync(p, bytes ? bytes : 1, s->stream);
+    if (bytes == 0) bytes = 1;
+    BlockCache &c = block_cache();
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        auto it = c.free_blocks.find({s->device, bytes});
+        if (it != c.free_blocks.end()) {
+            *p = it->second;
+            c.free_blocks.erase(it);
+            c.cached_bytes -= bytes;
+            c.live[*p] = {s->device, bytes};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t err = cudaMallocAsync(p, bytes, s->stream);
+    if (err != cudaSuccess) {  // out of memory with blocks parked in the cache: release them and retry once
+        cudaGetLastError();
+        std::vector<void *> drop;
+        {
+            std::lock_guard<std::mutex> lock(c.mu);
+            for (auto it = c.free_blocks.begin(); it != c.free_blocks.end();) {
+                if (it->first.first == s->device) {
+                    drop.push_back(it->second);
+                    c.cached_bytes -= it->first.second;
+                    it = c.free_blocks.erase(it);
+                } else ++it;
+            }
+        }
+        for (void *b : drop) cudaFreeAsync(b, s->stream);
+        cudaStreamSynchronize(s->stream);
+        err = cudaMallocAsync(p, bytes, s->stream);
+    }
+    if (err == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        c.live[*p] = {s->device, bytes};
+    }
+    return err;
 }
+// the caller guarantees that no enqueued work still uses p
 static void pool_free(pp_sim *s, void *p) {
-    if (p) cudaFreeAsync(p, s->stream);
+    if (!p) return;
+    BlockCache &c = block_cache();
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        auto it = c.live.find(p);
+        if (it != c.live.end()) {
+            const std::pair<int, size_t> key = it->second;
+            c.live.erase(it);
+            if (c.cached_bytes + key.second <= c.cap_bytes) {
+                c.free_blocks.insert({key, p});
+                c.cached_bytes += key.second;
+                return;
+            }
+        }
+    }
+    cudaFreeAsync(p, s->stream);
 }
 
 static void free_sim(pp_sim *s) {
@@ -249,9 +316,10 @@ static void free_sim(pp_sim *s) {
                     s->d_words_alt, s->d_sid, s->d_energies, s->d_temps, s->d_mags, s->d_lut_metro, s->d_lut_gibbs,
                     s->pt.edge_attempts, s->pt.edge_acceptances, s->pt.round_trips, s->pt.trip_state, s->pt.swap_mask,
                     s->st.sums, s->st.hist, s->st.ql_at_q, s->st.ql2_at_q, s->d_dot_spin, s->d_dot_link};
+    if (s->stream) cudaStreamSynchronize(s->stream);  // pp_sample joins its side streams into this one before it returns
+    for (cudaStream_t x : s->xstreams) cudaStreamSynchronize(x);
     for (void *p : ptrs)
         if (p) pool_free(s, p);
-    if (s->stream) cudaStreamSynchronize(s->stream);
     for (void *b : s->rows_bufs) pool_free(s, b);
     if (s->d_keys) pool_free(s, s->d_keys);
     if (s->d_rows_acc) pool_free(s, s->d_rows_acc);
