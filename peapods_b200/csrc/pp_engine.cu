@@ -195,6 +195,8 @@ struct pp_sim {
     std::vector<cudaEvent_t> xevents;
     SlabState *slab = nullptr;                         // PP_LAYOUT_SLAB (pp_slab.cuh)
     bool rows = false;                                 // int8 layout through the per-row stride tables (pp_kernels_rows.cuh)
+    bool resident = false;                             // small realizations: one CTA per realization, many sweeps per launch
+    size_t resident_smem = 0;
     RowsView rv{};
     std::vector<void *> rows_bufs;
     std::vector<uint32_t> rows_class_start;
@@ -1076,6 +1078,16 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             CREATE_TRY(cudaMemsetAsync(s->d_rows_acc, 0, sizeof(long long) * 2 * n_acc, s->stream));
             CREATE_TRY(cudaMemsetAsync(s->d_rows_arrive, 0, sizeof(unsigned int) * n_acc, s->stream));
             s->rows = true;
+            // resident kernel (rows_resident_kernel): integer classes, the realization's spins + the acceptance table in one
+            // CTA's shared memory, and few enough segments per thread that one CTA is not slower than a grid
+            {
+                const size_t lut_words = ((size_t)m.T * (4 * z + 1) + 3) & ~size_t(3);
+                const size_t need = lut_words * 4 + (size_t)m.S * N;
+                s->resident_smem = need;
+                s->resident = m.coupling_class != COUP_F32 && ((size_t)m.S * N) % 16 == 0 && need <= 200 * 1024 &&
+                              (z == 2 || z == 3);
+                if (const char *e = getenv("PP_RESIDENT")) s->resident = s->resident && atoi(e) != 0;
+            }
         }
     }
     m.J8 = s->d_J8;
@@ -1322,6 +1334,55 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     };
     std::vector<Step> steps;
     int64_t sweep_id = 0;
+    // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel, up to 256 sweeps per launch
+    if (s->rows && s->resident && !s->profile) {
+        Ctx &c = chunks[0];
+        RowsView v = s->rv;
+        v.keys = s->d_keys;
+        ModelView mk = c.m;
+        mk.lut = cfg->sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
+        const bool gibbs = cfg->sweep_mode == PP_SWEEP_GIBBS;
+        while (sweep_id < cfg->n_sweeps) {
+            if (interrupt && *interrupt) {
+                cudaDeviceSynchronize();
+                return fail(PP_ERR_INTERRUPTED, "interrupted");
+            }
+            const int64_t mb_end = std::min<int64_t>(cfg->n_sweeps, sweep_id + 256);
+            ResidentArgs a;
+            a.sweep_id0 = sweep_id;
+            a.n_sweeps = (int)(mb_end - sweep_id);
+            a.warmup_sweeps = cfg->warmup_sweeps;
+            a.pt_interval = cfg->pt_interval > 0 ? cfg->pt_interval : 0;
+            a.pt_schedule = cfg->pt_schedule == PP_PT_FULL_LADDER ? 1 : 0;
+            a.sweep_counter0 = s->sweep_counter;
+            a.pt_event0 = s->pt_event_counter;
+            a.parity0 = s->next_parity;
+            a.spins_in_smem = 1;
+            a.dot_spin = c.dot_spin;
+            a.dot_link = c.dot_link;
+#define PP_RES3(C_, Z_, G_)                                                                                                       \
+    do {                                                                                                                          \
+        CUDA_TRY(cudaFuncSetAttribute(rows_resident_kernel<C_, Z_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->resident_smem)); \
+        rows_resident_kernel<C_, Z_, G_><<<(unsigned)mk.D, RESIDENT_THREADS, s->resident_smem, c.stream>>>(mk, v, c.st, c.pt, a);   \
+    } while (0)
+#define PP_RES2(C_, Z_) do { if (gibbs) PP_RES3(C_, Z_, true); else PP_RES3(C_, Z_, false); } while (0)
+            if (mk.coupling_class == COUP_FERRO) { if (mk.z == 2) PP_RES2(COUP_FERRO, 2); else PP_RES2(COUP_FERRO, 3); }
+            else { if (mk.z == 2) PP_RES2(COUP_UNIT, 2); else PP_RES2(COUP_UNIT, 3); }
+#undef PP_RES2
+#undef PP_RES3
+            s->launches++;
+            CUDA_TRY(cudaGetLastError());
+            for (int64_t sid = sweep_id; sid < mb_end; sid++) {
+                s->sweep_counter++;
+                if (cfg->pt_interval > 0 && sid % cfg->pt_interval == 0) {
+                    s->pt_event_counter++;
+                    if (mk.T >= 2 && cfg->pt_schedule == PP_PT_FULL_LADDER) s->next_parity = 1 - s->next_parity;
+                }
+                if (on_sweep) on_sweep(user, (uint64_t)sid);
+            }
+            sweep_id = mb_end;
+        }
+    }
     while (sweep_id < cfg->n_sweeps) {
         if (interrupt && *interrupt) {  // mod.rs:406-408 (polled once per macro batch)
             for (Ctx &c : chunks) flush_swaps(s, c);

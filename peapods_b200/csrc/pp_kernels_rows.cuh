@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "pp_device.cuh"
+#include "pp_kernels_stats.cuh"
 #include "pp_plan.h"
 
 namespace pp {
@@ -127,26 +128,16 @@ __device__ __forceinline__ void rows_split(const RowsView &v, const uint32_t ci,
     }
 }
 
-// One colour class of one sweep.  grid = (D * ceil(S / ROWS_NS), segment blocks); a thread owns one row segment and
-// walks ROWS_NS slots of one realization.  ZT > 0: the number of forward directions is the compile-time constant ZT
-// (everything stays in registers); ZT = 0: any z' <= 16.
+// One row segment (work item ci of colour `colour`) of ROWS_NS slots of realization d.  spins_d = the realization's
+// [S][N] spins (global memory, or a shared-memory copy in the resident kernel); lut_sm = [T][4z + 1] acceptance counts.
+// ZT > 0: the number of forward directions is the compile-time constant ZT (everything stays in registers); ZT = 0: any z' <= 16.
 template <int CLASS, int ZT, bool GIBBS>
-__global__ void __launch_bounds__(128)
-rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int exact_log) {
-    extern __shared__ uint32_t lut_sm[];  // FERRO / UNIT: [T][4z + 1] acceptance counts
+__device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsView &v, const uint32_t *lut_sm, int8_t *spins_d,
+                                                const int64_t d, const int slot0, const uint32_t ci, const int colour,
+                                                const uint32_t sweep_index, const int exact_log) {
     constexpr int ZA = ZT > 0 ? ZT : 16;
     const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1;
-    if (CLASS != COUP_F32) {
-        for (int i = threadIdx.x; i < m.T * width; i += blockDim.x) lut_sm[i] = m.lut[i];
-        __syncthreads();
-    }
-    const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
-    const int64_t d = blockIdx.x / sblocks;
-    const int slot0 = (int)(blockIdx.x % sblocks) * ROWS_NS;
     const int cls = colour % v.m_half;
-    const uint32_t n_cls = v.class_start[cls + 1] - v.class_start[cls];
-    const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x;
-    if (ci >= n_cls * (uint32_t)v.kpr) return;
     uint32_t ri;
     int k;
     rows_split(v, ci, ri, k);
@@ -199,7 +190,7 @@ rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int
         if (slot >= m.S) break;
         const uint32_t sys = (uint32_t)m.system_ids[d * m.S + slot];  // parallel.rs:27-33
         const int t = slot % m.T;                                     // realization.rs:166
-        int8_t *s = m.spins + (d * m.S + sys) * m.N;
+        int8_t *s = spins_d + (int64_t)sys * m.N;
         const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
         const uint64_t C = rows_ld8(s + row_off + 8 * k);
         uint64_t F[ZA], B[ZA];  // byte j: the forward / backward neighbour of site j in direction kk
@@ -283,6 +274,27 @@ rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int
         const uint64_t out = C ^ flips;
         *reinterpret_cast<uint2 *>(s + row_off + 8 * k) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
     }
+}
+
+// One colour class of one sweep.  grid = (D * ceil(S / ROWS_NS), segment blocks); a thread owns one row segment and
+// walks ROWS_NS slots of one realization.
+template <int CLASS, int ZT, bool GIBBS>
+__global__ void __launch_bounds__(128)
+rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int exact_log) {
+    extern __shared__ uint32_t lut_sm[];  // FERRO / UNIT: [T][4z + 1] acceptance counts
+    const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1;
+    if (CLASS != COUP_F32) {
+        for (int i = threadIdx.x; i < m.T * width; i += blockDim.x) lut_sm[i] = m.lut[i];
+        __syncthreads();
+    }
+    const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
+    const int64_t d = blockIdx.x / sblocks;
+    const int slot0 = (int)(blockIdx.x % sblocks) * ROWS_NS;
+    const int cls = colour % v.m_half;
+    const uint32_t n_cls = v.class_start[cls + 1] - v.class_start[cls];
+    const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x;
+    if (ci >= n_cls * (uint32_t)v.kpr) return;
+    rows_sweep_body<CLASS, ZT, GIBBS>(m, v, lut_sm, m.spins + d * m.S * m.N, d, slot0, ci, colour, sweep_index, exact_log);
 }
 
 // energies (+ magnetisation sums): grid = (D * S, nb).  Integer classes split a system over nb blocks: partial sums meet
@@ -438,6 +450,150 @@ rows_overlap_kernel(ModelView m, RowsView v, long long *dot_spin, long long *dot
             dot_link[idx] = (long long)z * m.N - 2 * l_tot;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resident kernel for small realizations (README quickstart sizes: 32 systems x 1024 spins): ONE launch runs many sweeps.
+// One CTA owns realization d: its [S][N] spins live in shared memory for the whole launch, and the per-sweep sequence of
+// simulation/mod.rs:405-432, 486-509, 527-529, 748-796 -- colour passes, energies (+ magnetisations), overlap dots, fold,
+// parallel tempering -- runs inside the CTA with __syncthreads() where the multi-launch path has kernel boundaries
+// (5.5 launches per sweep made those sizes launch-bound).  Integer coupling classes only (their sums do not depend on the
+// order of addition, so every result is bit-identical to the multi-launch path).
+struct ResidentArgs {
+    int64_t sweep_id0;       // index of the first sweep inside this sample() call
+    int n_sweeps;
+    int64_t warmup_sweeps;   // record = sweep_id >= warmup_sweeps (mod.rs:410)
+    int64_t pt_interval;     // 0: no parallel tempering
+    int pt_schedule;
+    uint32_t sweep_counter0; // RNG-SPEC sweep index of the first sweep
+    uint32_t pt_event0;
+    int parity0;
+    int spins_in_smem;
+    long long *dot_spin, *dot_link;  // [D][P][T] (the StatsView holds the same arrays read-only)
+};
+
+constexpr int RESIDENT_THREADS = 512;
+
+template <int CLASS, int ZT, bool GIBBS>
+__global__ void __launch_bounds__(RESIDENT_THREADS)
+rows_resident_kernel(ModelView m, RowsView v, StatsView st, PtView pt, ResidentArgs a) {
+    extern __shared__ __align__(16) uint32_t res_sm[];
+    const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1, L = v.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RESIDENT_THREADS / 32;
+    const int64_t d = blockIdx.x;
+    uint32_t *lut_sm = res_sm;
+    int8_t *g_spins = m.spins + d * m.S * m.N;
+    const int64_t n_bytes = (int64_t)m.S * m.N;
+    int8_t *spins_d = a.spins_in_smem ? reinterpret_cast<int8_t *>(res_sm + ((m.T * width + 3) & ~3)) : g_spins;
+    for (int i = tid; i < m.T * width; i += RESIDENT_THREADS) lut_sm[i] = m.lut[i];
+    if (a.spins_in_smem)
+        for (int64_t i = tid; i < n_bytes / 16; i += RESIDENT_THREADS)
+            reinterpret_cast<uint4 *>(spins_d)[i] = reinterpret_cast<const uint4 *>(g_spins)[i];
+    __syncthreads();
+    const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
+    const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);
+    uint32_t pt_event = a.pt_event0;
+    int parity = a.parity0;
+    for (int sw = 0; sw < a.n_sweeps; sw++) {
+        const int64_t sid = a.sweep_id0 + sw;
+        const uint32_t sweep_index = a.sweep_counter0 + (uint32_t)sw;
+        for (int col = 0; col < m.n_colours; col++) {
+            const int cls = col % v.m_half;
+            const uint32_t nseg = (v.class_start[cls + 1] - v.class_start[cls]) * (uint32_t)v.kpr;
+            for (uint32_t it = tid; it < (uint32_t)sblocks * nseg; it += RESIDENT_THREADS)
+                rows_sweep_body<CLASS, ZT, GIBBS>(m, v, lut_sm, spins_d, d, (int)(it / nseg) * ROWS_NS, it % nseg, col, sweep_index, 0);
+            __syncthreads();
+        }
+        const bool record = sid >= a.warmup_sweeps;
+        const bool pt_this = a.pt_interval > 0 && sid % a.pt_interval == 0;
+        if (record || pt_this) {  // mod.rs:486-509; energy.rs:99-108 per system, one warp each
+            for (int sys = warp; sys < m.S; sys += n_warps) {
+                const int8_t *s = spins_d + (int64_t)sys * m.N;
+                long long isum = 0, dn = 0;  // FERRO: unsatisfied forward bonds; UNIT: sum s s J
+                for (uint32_t ci = lane; ci < n_seg; ci += 32) {
+                    uint32_t r;
+                    int k;
+                    rows_split(v, ci, r, k);
+                    const uint64_t C = rows_ld8(s + (int64_t)r * L + 8 * k);
+                    dn += __popcll(C & 0x8080808080808080ull);
+                    for (int kk = 0; kk < z; kk++) {
+                        const uint64_t X = C ^ rows_shifted(s + (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L, L, k, v.dl[kk]);
+                        if (CLASS == COUP_FERRO) {
+                            isum += __popcll(X & 0x8080808080808080ull);
+                        } else {
+                            const size_t jbase = ((size_t)d * m.N + (size_t)r * L + 8 * k) * z;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int J = m.J8[jbase + (size_t)j * z + kk];
+                                isum += ((X >> (8 * j)) & 0x80u) ? -J : J;
+                            }
+                        }
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    isum += __shfl_xor_sync(0xFFFFFFFFu, isum, o);
+                    dn += __shfl_xor_sync(0xFFFFFFFFu, dn, o);
+                }
+                if (lane == 0) {
+                    const long long bonds = CLASS == COUP_FERRO ? (long long)z * m.N - 2 * isum : isum;
+                    m.energies[d * m.S + sys] = __fdiv_rn((float)bonds, (float)m.N);
+                    if (record) m.mags[d * m.S + sys] = m.N - 2 * dn;
+                }
+            }
+            __syncthreads();
+        }
+        if (record) {
+            if (m.P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids, one warp per (pair, slot)
+                for (int idx = warp; idx < m.P * m.T; idx += n_warps) {
+                    const int t = idx % m.T, p = idx / m.T;
+                    const int8_t *sa = spins_d + (int64_t)m.system_ids[d * m.S + (2 * p) * m.T + t] * m.N;
+                    const int8_t *sb = spins_d + (int64_t)m.system_ids[d * m.S + (2 * p + 1) * m.T + t] * m.N;
+                    long long neg_q = 0, neg_l = 0;
+                    for (uint32_t ci = lane; ci < n_seg; ci += 32) {
+                        uint32_t r;
+                        int k;
+                        rows_split(v, ci, r, k);
+                        const int64_t o = (int64_t)r * L + 8 * k;
+                        const uint64_t x = rows_ld8(sa + o) ^ rows_ld8(sb + o);
+                        neg_q += __popcll(x & 0x8080808080808080ull);
+                        for (int kk = 0; kk < z; kk++) {
+                            const int64_t nro = (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L;
+                            const uint64_t xf = rows_shifted(sa + nro, L, k, v.dl[kk]) ^ rows_shifted(sb + nro, L, k, v.dl[kk]);
+                            neg_l += __popcll((x ^ xf) & 0x8080808080808080ull);
+                        }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        neg_q += __shfl_xor_sync(0xFFFFFFFFu, neg_q, o);
+                        neg_l += __shfl_xor_sync(0xFFFFFFFFu, neg_l, o);
+                    }
+                    if (lane == 0) {
+                        a.dot_spin[(d * m.P + p) * m.T + t] = m.N - 2 * neg_q;
+                        a.dot_link[(d * m.P + p) * m.T + t] = (long long)z * m.N - 2 * neg_l;
+                    }
+                }
+                __syncthreads();
+            }
+            for (int t = tid; t < m.T; t += RESIDENT_THREADS)  // mod.rs:543-578
+                fold_one<0>(
+                    m, st, d, t, m.P > 0,
+                    [&](int r) { return m.mags[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
+                    [&](int r) { return m.energies[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
+                    [&](int p) { return a.dot_spin[(d * m.P + p) * m.T + t]; },
+                    [&](int p) { return a.dot_link[(d * m.P + p) * m.T + t]; });
+            __syncthreads();
+        }
+        if (pt_this) {  // mod.rs:748-796
+            if (m.T >= 2) {
+                if (tid < m.R) pt_exchange_body(m, pt, d, tid, a.pt_schedule, parity, pt_event);
+                if (a.pt_schedule == 1) parity = 1 - parity;
+                __syncthreads();
+            }
+            pt_event++;
+        }
+    }
+    if (a.spins_in_smem)
+        for (int64_t i = tid; i < n_bytes / 16; i += RESIDENT_THREADS)
+            reinterpret_cast<uint4 *>(g_spins)[i] = reinterpret_cast<const uint4 *>(spins_d)[i];
 }
 #endif  // __CUDACC__
 

@@ -174,11 +174,8 @@ __device__ __forceinline__ bool pt_attempt_edge(const ModelView &m, const PtView
 
 // K8: one thread per (realization, replica).  RNG-SPEC PT domain: key = realization key,
 // counter = {edge | 0xFFFFFFFF, pt_event, replica, TAG_PT}.
-__global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int first_parity, uint32_t pt_event) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= m.D * m.R || m.T < 2) return;
-    const int64_t d = gid / m.R;
-    const int r = (int)(gid % m.R);
+__device__ __forceinline__ void pt_exchange_body(const ModelView &m, const PtView &pt, const int64_t d, const int r, const int schedule,
+                                                 const int first_parity, const uint32_t pt_event) {
     const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     if (schedule == 0) {  // tempering.rs:20-42
@@ -194,6 +191,12 @@ __global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int fir
             }
         }
     }
+}
+
+__global__ void pt_exchange_kernel(ModelView m, PtView pt, int schedule, int first_parity, uint32_t pt_event) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= m.D * m.R || m.T < 2) return;
+    pt_exchange_body(m, pt, gid / m.R, (int)(gid % m.R), schedule, first_parity, pt_event);
 }
 
 // K8, multispin layout: one warp per (word group g, replica r) ladder, lane l = realization 32g + l.  Same decisions

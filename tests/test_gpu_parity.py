@@ -408,7 +408,9 @@ ROWS_CASES = [
 
 @pytest.mark.parametrize("shape,kind,offsets,temps,R,D", ROWS_CASES)
 @pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
-def test_row_table_kernels_are_bit_exact(oracle, shape, kind, offsets, temps, R, D, mode):
+@pytest.mark.parametrize("resident", ["1", "0"])  # one CTA per realization, many sweeps per launch / one launch per colour pass
+def test_row_table_kernels_are_bit_exact(oracle, monkeypatch, shape, kind, offsets, temps, R, D, mode, resident):
+    monkeypatch.setenv("PP_RESIDENT", resident)
     gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
     assert_state_equal(gpu, cpu, D)
     gaussian = kind == "gaussian"  # f32 energies are tolerance-checked, so PT (which branches on them) stays off there
@@ -425,3 +427,24 @@ def test_row_table_kernels_are_bit_exact(oracle, shape, kind, offsets, temps, R,
             assert np.array_equal(rg[k], rc[k]), k
         np.testing.assert_allclose(rg["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(rg["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("schedule", ["single_random_edge", "full_ladder"])
+@pytest.mark.parametrize("shape,kind,offsets,temps,R,D", [
+    ((32, 32), "ferro", None, np.linspace(1.5, 3.0, 16), 2, 1),          # BASELINE config 1 (README quickstart)
+    ((8, 8, 8), "bimodal", None, np.linspace(0.8, 1.6, 6), 4, 3),
+    ((8, 16), "bimodal", TRI, [1.0, 1.5, 2.5], 3, 2),                    # unpaired third replica
+])
+def test_resident_kernel_long_runs_are_bit_exact(oracle, shape, kind, offsets, temps, R, D, schedule):
+    """More sweeps than one resident launch holds (256), PT every sweep and every third sweep, on_sweep, reset replay."""
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
+    seen = []
+    for n_sweeps, interval in ((300, 1), (259, 3)):
+        rg = gpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule, on_sweep=seen.append)
+        rc = cpu.sample(n_sweeps, "metropolis", pt_interval=interval, pt_schedule=schedule)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        for d in range(D):
+            assert np.array_equal(gpu.get_energies(d), cpu.energies(d))
+    assert seen == list(range(300)) + list(range(259))
+    assert gpu.last_kernel_launches <= 3
