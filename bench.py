@@ -483,6 +483,12 @@ def main():
     ap.add_argument("--workload", choices=("c2", "c5"), default="c2", help="c2: BASELINE headline (default); c5: one large lattice in slabs")
     ap.add_argument("--c5-extent", type=int, default=1024)
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: native libraries that write to file descriptor 1 (NCCL prints its version
+    # there when NCCL_DEBUG is set) are sent to stderr, Python's sys.stdout keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.warmup < 3:
         args.warmup = max(args.warmup, 0)
     if args.workload == "c5" and args.impl == "ours":
