@@ -23,6 +23,10 @@
 namespace pp {
 
 constexpr int ROWS_NS = 4;  // systems a sweep thread walks with one set of coupling registers
+// (one system per thread for ferromagnets, which have no coupling registers to reuse, was measured: no gain at C3, a loss
+// in the resident kernel at C1)
+template <int CLASS>
+__host__ __device__ constexpr int rows_ns() { return ROWS_NS; }
 
 struct RowsView {
     int L;                       // last extent
@@ -131,10 +135,16 @@ __device__ __forceinline__ void rows_split(const RowsView &v, const uint32_t ci,
 // One row segment (work item ci of colour `colour`) of ROWS_NS slots of realization d.  spins_d = the realization's
 // [S][N] spins (global memory, or a shared-memory copy in the resident kernel); lut_sm = [T][4z + 1] acceptance counts.
 // ZT > 0: the number of forward directions is the compile-time constant ZT (everything stays in registers); ZT = 0: any z' <= 16.
-template <int CLASS, int ZT, bool GIBBS>
+// EACC (two-colour lattices, last colour pass): also return, per walked slot, the post-update bond sum of the thread's active
+// sites, sum_i s_i h_i (fp32 couplings: in units of 1 / escale, rounded to an integer), and the down spins of its segment.
+// The active sites of the last pass touch every bond exactly once, so these add up to the energy of energy.rs:99-108
+// without another pass over the spins.
+template <int CLASS, int ZT, bool GIBBS, bool EACC = false>
 __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsView &v, const uint32_t *lut_sm, int8_t *spins_d,
                                                 const int64_t d, const int slot0, const uint32_t ci, const int colour,
-                                                const uint32_t sweep_index, const int exact_log) {
+                                                const uint32_t sweep_index, const int exact_log, const float escale = 1.0f,
+                                                long long *e_part = nullptr, int *dn_part = nullptr) {
+    constexpr int NS = rows_ns<CLASS>();
     constexpr int ZA = ZT > 0 ? ZT : 16;
     const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1;
     const int cls = colour % v.m_half;
@@ -149,14 +159,36 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
     const int64_t row_off = (int64_t)r * L;
     int64_t nrf[ZA], nrb[ZA];  // byte offsets of the forward / backward neighbour rows
     int dls[ZA];
+    // the (up to two) 8-byte loads that make up the shifted neighbour segment of every direction, as byte offsets inside a
+    // system and a funnel-shift amount: computed once per thread, reused by every system the thread walks
+    uint32_t fo0[ZA], fo1[ZA], bo0[ZA], bo1[ZA];
+    int fsh[ZA], bsh[ZA];
+    auto seg_plan = [&](const int64_t nrow, const int shift, uint32_t &o0, uint32_t &o1, int &sh) {
+        int start = 8 * k + shift;
+        start -= (start >= L) ? L : 0;
+        start += (start < 0) ? L : 0;
+        const int c0 = start >> 3;
+        const int c1 = (c0 + 1) * 8 == L ? 0 : c0 + 1;
+        sh = (start & 7) * 8;
+        o0 = (uint32_t)(nrow + 8 * c0);
+        o1 = (uint32_t)(nrow + 8 * c1);
+    };
 #pragma unroll
     for (int kk = 0; kk < ZA; kk++) {
         if (kk < z) {
             nrf[kk] = (int64_t)v.nbr_row[((size_t)r * z + kk) * 2] * L;
             nrb[kk] = (int64_t)v.nbr_row[((size_t)r * z + kk) * 2 + 1] * L;
             dls[kk] = v.dl[kk];
+            seg_plan(nrf[kk], dls[kk], fo0[kk], fo1[kk], fsh[kk]);
+            seg_plan(nrb[kk], -dls[kk], bo0[kk], bo1[kk], bsh[kk]);
         }
     }
+    auto seg_load = [&](const int8_t *sp, const uint32_t o0, const uint32_t o1, const int sh) {
+        const uint64_t lo = rows_ld8(sp + o0);
+        if (sh == 0) return lo;  // warp-uniform: the shift depends on the direction only
+        const uint64_t hi = rows_ld8(sp + o1);
+        return (lo >> sh) | (hi << (64 - sh));
+    };
     // fp32 / +-1 couplings of the four active sites, reference order: direction-major, forward then backward
     float Jf[CLASS == COUP_F32 ? 4 : 1][CLASS == COUP_F32 ? 2 * ZA : 1];
     int Ji[CLASS == COUP_UNIT ? 4 : 1][CLASS == COUP_UNIT ? 2 * ZA : 1];
@@ -185,20 +217,49 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
             }
         }
     }
-    for (int ss = 0; ss < ROWS_NS; ss++) {
+#ifndef PP_ROWS_PF
+#define PP_ROWS_PF 1
+#endif
+    // The walked systems are independent, but the compiler cannot move one system's loads above the previous system's store
+    // (same array): PF > 1 loads the segments of PF systems together before updating them.  Measured at C4 (D = 128): PF = 1
+    // 156 attempts/ns, PF = 2 131, PF = 4 125 -- the kernel is issue-bound (0.65 IPC per sub-partition at 24 % occupancy), the
+    // extra registers cost more than the memory-level parallelism gains; constant couplings instead of loads: no change.
+    constexpr int PF = NS < PP_ROWS_PF ? NS : PP_ROWS_PF;
+    uint32_t sysv[PF];
+    uint64_t Cv[PF], Fv[PF][ZA], Bv[PF][ZA];  // byte j: site j / its forward / backward neighbour in direction kk
+#pragma unroll
+    for (int ss = 0; ss < NS; ss++) {
         const int slot = slot0 + ss;
         if (slot >= m.S) break;
-        const uint32_t sys = (uint32_t)m.system_ids[d * m.S + slot];  // parallel.rs:27-33
+        if (ss % PF == 0) {
+#pragma unroll
+            for (int pp = 0; pp < PF; pp++) {
+                if (slot + pp < m.S) {
+                    sysv[pp] = (uint32_t)m.system_ids[d * m.S + slot + pp];  // parallel.rs:27-33
+                    const int8_t *sp = spins_d + (int64_t)sysv[pp] * m.N;
+                    Cv[pp] = rows_ld8(sp + row_off + 8 * k);
+#pragma unroll
+                    for (int kk = 0; kk < ZA; kk++) {
+                        if (kk < z) {
+                            Fv[pp][kk] = seg_load(sp, fo0[kk], fo1[kk], fsh[kk]);
+                            Bv[pp][kk] = seg_load(sp, bo0[kk], bo1[kk], bsh[kk]);
+                        }
+                    }
+                }
+            }
+        }
+        long long e_sum = 0;
+        const uint32_t sys = sysv[ss % PF];
         const int t = slot % m.T;                                     // realization.rs:166
         int8_t *s = spins_d + (int64_t)sys * m.N;
         const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
-        const uint64_t C = rows_ld8(s + row_off + 8 * k);
-        uint64_t F[ZA], B[ZA];  // byte j: the forward / backward neighbour of site j in direction kk
+        const uint64_t C = Cv[ss % PF];
+        uint64_t F[ZA], B[ZA];
 #pragma unroll
         for (int kk = 0; kk < ZA; kk++) {
             if (kk < z) {
-                F[kk] = rows_shifted(s + nrf[kk], L, k, dls[kk]);
-                B[kk] = rows_shifted(s + nrb[kk], L, k, -dls[kk]);
+                F[kk] = Fv[ss % PF][kk];
+                B[kk] = Bv[ss % PF][kk];
             }
         }
         // bring the four active sites to the even bytes: every per-site shift below is a compile-time constant
@@ -217,7 +278,9 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
                 const int nd = (int)((dw[l >> 1] >> (16 * (l & 1))) & 0xFFu);
                 const bool dn = ((cw[l >> 1] >> (16 * (l & 1))) & 0x80u) != 0;
                 const int idx = dn ? 4 * z - 2 * nd : 2 * nd;  // ec + 2z' with ec = -s h, h = 2z' - 2 nd (sweep.rs:178)
-                if ((pick(o, l) >> 8) < lut_sm[t * width + idx]) fl[l >> 1] |= 0xFEu << (16 * (l & 1));
+                const bool flip = (pick(o, l) >> 8) < lut_sm[t * width + idx];
+                if (flip) fl[l >> 1] |= 0xFEu << (16 * (l & 1));
+                if (EACC) e_sum += flip ? idx - 2 * z : 2 * z - idx;  // s h after the update = ec if flipped, -ec if not
             }
         } else {
             const float half_t = __fdiv_rn(m.temps[t], 2.0f);
@@ -241,13 +304,14 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
 #pragma unroll
                 for (int kk = 0; kk < ZA; kk++) {
                     if (kk < z) {
-                        const uint32_t fb = (fw[kk][w] >> bs) & 0xFFu, bb = (bw[kk][w] >> bs) & 0xFFu;
                         if (CLASS == COUP_F32) {
                             // sweep.rs:10-17: forward then backward, no fused multiply-add; a product with a +-1 spin is
-                            // the coupling with its sign bit flipped, exactly what the f32 multiplication returns
-                            h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[l][2 * kk]) ^ ((fb & 0x80u) << 24)));
-                            h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[l][2 * kk + 1]) ^ ((bb & 0x80u) << 24)));
+                            // the coupling with its sign bit flipped, exactly what the f32 multiplication returns.  The spin's
+                            // sign bit (bit bs + 7 of the word) goes straight to bit 31: one shift, one LOP3, one add per term.
+                            h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[l][2 * kk]) ^ ((fw[kk][w] << (24 - bs)) & 0x80000000u)));
+                            h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[l][2 * kk + 1]) ^ ((bw[kk][w] << (24 - bs)) & 0x80000000u)));
                         } else {
+                            const uint32_t fb = (fw[kk][w] >> bs) & 0xFFu, bb = (bw[kk][w] >> bs) & 0xFFu;
                             hi += (int)(int8_t)fb * Ji[l][2 * kk] + (int)(int8_t)bb * Ji[l][2 * kk + 1];
                         }
                     }
@@ -255,7 +319,7 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
                 bool flip;
                 if (CLASS == COUP_F32) {
                     // eng_change = -s_i * h (sweep.rs:43-44): h with its sign flipped when s_i = +1
-                    const float eng_change = __uint_as_float(__float_as_uint(h) ^ ((~sbyte & 0x80u) << 24));
+                    const float eng_change = __uint_as_float(__float_as_uint(h) ^ ((~cw[w] << (24 - bs)) & 0x80000000u));
                     const float u = (float)draw * (1.0f / 16777216.0f);
                     float lg;
                     if (!GIBBS)  // sweep.rs:256; production mode uses the hardware log2 (relative error ~1e-7 on the threshold)
@@ -268,33 +332,99 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
                     flip = draw < lut_sm[t * width + (-si * hi) + 2 * z];  // sweep.rs:178-184
                 }
                 if (flip) fl[w] |= 0xFEu << bs;
+                if (EACC) {
+                    if (CLASS == COUP_F32) {
+                        const float ec = __uint_as_float(__float_as_uint(h) ^ ((~sbyte & 0x80u) << 24));  // -s h before the update
+                        e_sum += __float2ll_rn(__fmul_rn(flip ? ec : -ec, escale));
+                    } else {
+                        const int sh = (int)(int8_t)sbyte * hi;
+                        e_sum += flip ? -sh : sh;
+                    }
+                }
             }
         }
         const uint64_t flips = ((uint64_t)fl[0] | ((uint64_t)fl[1] << 32)) << osh;
         const uint64_t out = C ^ flips;
         *reinterpret_cast<uint2 *>(s + row_off + 8 * k) = make_uint2((uint32_t)out, (uint32_t)(out >> 32));
+        if (EACC) {
+            e_part[ss] = e_sum;
+            dn_part[ss] = __popcll(out & 0x8080808080808080ull);
+        }
     }
 }
 
-// One colour class of one sweep.  grid = (D * ceil(S / ROWS_NS), segment blocks); a thread owns one row segment and
-// walks ROWS_NS slots of one realization.
-template <int CLASS, int ZT, bool GIBBS>
+// One colour class of one sweep.  grid = (D * ceil(S / NS), segment blocks); a thread owns one row segment and walks
+// NS = rows_ns<CLASS>() slots of one realization.  EACC: the pass also delivers energies (+ magnetisation sums) -- warp
+// sums (REDUX) meet in shared memory, block sums in acc[2 * sys + {0, 1}] (64-bit integer atomics: order-independent), and
+// the block of a slot group that arrives last converts them and re-zeroes the scratch (arrive[blockIdx.x]).
+template <int CLASS, int ZT, bool GIBBS, bool EACC>
 __global__ void __launch_bounds__(128)
-rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int exact_log) {
+rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int exact_log, float escale, int want_mags,
+                  long long *acc, unsigned int *arrive) {
     extern __shared__ uint32_t lut_sm[];  // FERRO / UNIT: [T][4z + 1] acceptance counts
+    constexpr int NS = rows_ns<CLASS>();
+    __shared__ unsigned long long blk[NS][2];
+    __shared__ int is_last;
     const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1;
+    if (EACC && threadIdx.x < NS * 2) blk[threadIdx.x >> 1][threadIdx.x & 1] = 0ull;
     if (CLASS != COUP_F32) {
         for (int i = threadIdx.x; i < m.T * width; i += blockDim.x) lut_sm[i] = m.lut[i];
-        __syncthreads();
     }
-    const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
+    if (EACC || CLASS != COUP_F32) __syncthreads();
+    const int sblocks = (m.S + NS - 1) / NS;
     const int64_t d = blockIdx.x / sblocks;
-    const int slot0 = (int)(blockIdx.x % sblocks) * ROWS_NS;
+    const int slot0 = (int)(blockIdx.x % sblocks) * NS;
     const int cls = colour % v.m_half;
     const uint32_t n_cls = v.class_start[cls + 1] - v.class_start[cls];
     const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x;
-    if (ci >= n_cls * (uint32_t)v.kpr) return;
-    rows_sweep_body<CLASS, ZT, GIBBS>(m, v, lut_sm, m.spins + d * m.S * m.N, d, slot0, ci, colour, sweep_index, exact_log);
+    const bool active = ci < n_cls * (uint32_t)v.kpr;
+    if constexpr (!EACC) {
+        if (active) rows_sweep_body<CLASS, ZT, GIBBS, false>(m, v, lut_sm, m.spins + d * m.S * m.N, d, slot0, ci, colour, sweep_index, exact_log);
+    } else {
+    long long e_part[NS];
+    int dn_part[NS];
+#pragma unroll
+    for (int ss = 0; ss < NS; ss++) { e_part[ss] = 0; dn_part[ss] = 0; }
+    if (active)
+        rows_sweep_body<CLASS, ZT, GIBBS, true>(m, v, lut_sm, m.spins + d * m.S * m.N, d, slot0, ci, colour, sweep_index, exact_log, escale,
+                                                e_part, dn_part);
+#pragma unroll
+    for (int ss = 0; ss < NS; ss++) {  // a 64-bit sum as two REDUX: low 16 bits (unsigned) and the rest (signed)
+        const int lo = __reduce_add_sync(0xFFFFFFFFu, (int)(e_part[ss] & 0xFFFF));
+        const int hi = __reduce_add_sync(0xFFFFFFFFu, (int)(e_part[ss] >> 16));
+        const int dn = __reduce_add_sync(0xFFFFFFFFu, dn_part[ss]);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&blk[ss][0], (unsigned long long)(((long long)hi << 16) + (long long)lo));
+            atomicAdd(&blk[ss][1], (unsigned long long)(long long)dn);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NS * 2) {
+        const int ss = threadIdx.x >> 1, slot = slot0 + ss;
+        if (slot < m.S) {
+            const int64_t sysg = d * m.S + m.system_ids[d * m.S + slot];
+            atomicAdd((unsigned long long *)&acc[2 * sysg + (threadIdx.x & 1)], blk[ss][threadIdx.x & 1]);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&arrive[blockIdx.x], 1u) == gridDim.y - 1 ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < NS) {
+        const int slot = slot0 + threadIdx.x;
+        if (slot < m.S) {
+            const int64_t sysg = d * m.S + m.system_ids[d * m.S + slot];
+            const long long e_tot = (long long)atomicExch((unsigned long long *)&acc[2 * sysg], 0ull);
+            const long long d_tot = (long long)atomicExch((unsigned long long *)&acc[2 * sysg + 1], 0ull);
+            if (CLASS == COUP_F32) m.energies[sysg] = __fdiv_rn((float)((double)e_tot / (double)escale), (float)m.N);
+            else m.energies[sysg] = __fdiv_rn((float)e_tot, (float)m.N);
+            if (want_mags) m.mags[sysg] = m.N - 2 * d_tot;
+        }
+    }
+    if (threadIdx.x == 0) arrive[blockIdx.x] = 0u;
+    }
 }
 
 // energies (+ magnetisation sums): grid = (D * S, nb).  Integer classes split a system over nb blocks: partial sums meet
@@ -490,7 +620,8 @@ rows_resident_kernel(ModelView m, RowsView v, StatsView st, PtView pt, ResidentA
         for (int64_t i = tid; i < n_bytes / 16; i += RESIDENT_THREADS)
             reinterpret_cast<uint4 *>(spins_d)[i] = reinterpret_cast<const uint4 *>(g_spins)[i];
     __syncthreads();
-    const int sblocks = (m.S + ROWS_NS - 1) / ROWS_NS;
+    constexpr int NS = rows_ns<CLASS>();
+    const int sblocks = (m.S + NS - 1) / NS;
     const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);
     uint32_t pt_event = a.pt_event0;
     int parity = a.parity0;
@@ -501,7 +632,7 @@ rows_resident_kernel(ModelView m, RowsView v, StatsView st, PtView pt, ResidentA
             const int cls = col % v.m_half;
             const uint32_t nseg = (v.class_start[cls + 1] - v.class_start[cls]) * (uint32_t)v.kpr;
             for (uint32_t it = tid; it < (uint32_t)sblocks * nseg; it += RESIDENT_THREADS)
-                rows_sweep_body<CLASS, ZT, GIBBS>(m, v, lut_sm, spins_d, d, (int)(it / nseg) * ROWS_NS, it % nseg, col, sweep_index, 0);
+                rows_sweep_body<CLASS, ZT, GIBBS>(m, v, lut_sm, spins_d, d, (int)(it / nseg) * NS, it % nseg, col, sweep_index, 0);
             __syncthreads();
         }
         const bool record = sid >= a.warmup_sweeps;

@@ -7,7 +7,13 @@ from pathlib import Path
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import os  # noqa: E402
+
 import peapods_b200 as pb  # noqa: E402
+from peapods_b200 import _lib  # noqa: E402
+
+if os.environ.get("PP_LIB"):  # A/B runs against another build of the library
+    _lib.LIB_PATH = Path(os.environ["PP_LIB"]).resolve()
 
 TRI = [[1, 0], [0, 1], [1, -1]]
 

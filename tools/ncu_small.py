@@ -1,4 +1,4 @@
-"""Small C3 / C4 runs for ncu captures of the table-driven int8 kernels. Usage: ncu_small.py c3|c4"""
+"""Small C3 / C4 runs for ncu captures of the int8 row-table kernels. Usage: ncu_small.py c3|c4 [D]"""
 import sys
 from pathlib import Path
 import numpy as np
@@ -10,6 +10,7 @@ if sys.argv[1] == "c3":
     m = pb.Ising((256, 256), "ferro", np.linspace(tc - 0.4, tc + 0.4, 64), n_replicas=2, neighbor_offsets=TRI, seed=42)
     m.sample(6, "gibbs")
 else:
-    m = pb.Ising((32, 32, 32), "gaussian", np.linspace(0.8, 1.8, 48), n_replicas=4, n_disorder=16, seed=42)
+    D = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    m = pb.Ising((32, 32, 32), "gaussian", np.linspace(0.8, 1.8, 48), n_replicas=4, n_disorder=D, seed=42)
     m.sample(4, "metropolis", pt_interval=1, per_sample=False)
 print("done", m._sim.last_sweep_loop_ms)
