@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 2
+#define PP_ABI_VERSION 3
 #define PP_MAX_DIMS 8
 
 typedef enum {
@@ -93,8 +93,10 @@ typedef struct {
      * PP_ERR_UNSUPPORTED is returned before any state mutation */
     int64_t cluster_update_interval;
     int64_t overlap_cluster_update_interval;
+    /* 0 = None; > 0: integrated autocorrelation times of m^2 and q^2 over the recorded sweeps (statistics/autocorrelation.rs,
+     * ring backend; the lag is clamped to [1, recorded sweeps / 4] as simulation/mod.rs:342-344) */
     int64_t autocorrelation_max_lag;
-    int64_t snapshot_interval;
+    int64_t snapshot_interval;                /* unsupported: must be 0 */
     int32_t equilibration_diagnostic;
     /* 1: fp32-coupling / Gibbs log thresholds are read from a host-libm logf table so that spin
      * trajectories are bit-identical to the CPU rule; 0: device logf (results agree to tolerance) */
@@ -123,6 +125,10 @@ typedef struct {
     int64_t kernel_launches;   /* out: kernels launched by this call */
     double sweep_kernel_ms;    /* out (cfg.profile): summed device time of the sweep-kernel launches */
     int64_t sweep_kernel_launches; /* out (cfg.profile): how many launches that sum covers */
+    /* cfg.autocorrelation_max_lag > 0 (src/lib.rs:545-556): [T] means over this handle's realizations of the per-realization
+     * Sokal-windowed taus (statistics/results.rs:217-231, 269-274); overlap2_tau needs R >= 2 */
+    double *mags2_tau, *overlap2_tau;
+    double *per_sample_taus;   /* [D][2][T]: per-realization taus (m^2 row, q^2 row), for the ordered multi-GPU merge */
 } pp_results;
 
 const char *pp_last_error(void);

@@ -39,6 +39,7 @@ class _Config(C.Structure):
         ("pt_schedule", C.c_int32),
         ("n_threads", C.c_int32),
         ("force_log_form", C.c_int32),
+        ("autocorr_max_lag", C.c_int64),
     ]
 
 
@@ -54,6 +55,7 @@ class _Results(C.Structure):
         + [("ps_hist", _PU64), ("ps_ql_at_q_sum", _PD), ("ps_ql2_at_q_sum", _PD)]
         + [("edge_attempts", _PU64), ("edge_acceptances", _PU64), ("round_trips", _PU64)]
         + [("ps_means", _PD)]
+        + [("mags2_tau", _PD), ("overlap2_tau", _PD), ("ps_taus", _PD)]
     )
 
 
@@ -276,11 +278,12 @@ class Sim:
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(self.T * self.R,)).copy()
 
     def sample(self, n_sweeps, sweep_mode="metropolis", pt_interval=None, pt_schedule="single_random_edge",
-               warmup_ratio=0.25, n_threads=1, force_log_form=False, per_sample=True):
+               warmup_ratio=0.25, n_threads=1, force_log_form=False, per_sample=True, autocorrelation_max_lag=None):
         # src/lib.rs:219-220 (Rust f64::round = half away from zero)
         warm = int(np.floor(n_sweeps * warmup_ratio + 0.5))
         cfg = _Config(n_sweeps, warm, {"metropolis": 0, "gibbs": 1}[sweep_mode], 0 if pt_interval is None else pt_interval,
-                      {"single_random_edge": 0, "full_ladder": 1}[pt_schedule], n_threads, int(force_log_form))
+                      {"single_random_edge": 0, "full_ladder": 1}[pt_schedule], n_threads, int(force_log_form),
+                      0 if autocorrelation_max_lag is None else int(autocorrelation_max_lag))
         T, R, D, N = self.T, self.R, self.D, self.N
         out = {k: np.zeros(T, dtype=np.float64) for k in ("mags", "mags2", "mags4", "energies", "energies2")}
         res = _Results()
@@ -316,8 +319,40 @@ class Sim:
             out["per_disorder"] = {"parallel_tempering": pt}
         self.last_per_sample_means = np.zeros((D, 11, T), dtype=np.float64)
         res.ps_means = self.last_per_sample_means.ctypes.data_as(_PD)
+        if autocorrelation_max_lag is not None:  # src/lib.rs:545-556
+            out["mags2_tau"] = np.zeros(T, dtype=np.float64)
+            res.mags2_tau = out["mags2_tau"].ctypes.data_as(_PD)
+            if R >= 2:
+                out["overlap2_tau"] = np.zeros(T, dtype=np.float64)
+                res.overlap2_tau = out["overlap2_tau"].ctypes.data_as(_PD)
+            self.last_per_sample_taus = np.zeros((D, 2, T), dtype=np.float64)
+            res.ps_taus = self.last_per_sample_taus.ctypes.data_as(_PD)
         rc = lib().orc_sim_sample(self.h, C.byref(cfg), C.byref(res))
         del keep
         if rc != 0:
             raise ValueError(lib().orc_last_error().decode())
         return out
+
+
+def autocorr_gamma(values, max_lag):
+    """AutocorrAccum (ring backend) over rows values[n_samples][n_temps] -> gamma[n_temps][max_lag + 1]
+    (statistics/autocorrelation.rs:24-124, 166-199)."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    if v.ndim == 1:
+        v = v[:, None]
+    n, T = v.shape if v.size else (0, v.shape[1] if v.ndim == 2 else 1)
+    gamma = np.zeros((T, max_lag + 1), dtype=np.float64)
+    f = lib().orc_autocorr_gamma
+    f.restype = None
+    f.argtypes = [_PD, C.c_int64, C.c_int, C.c_int, _PD]
+    f(v.ctypes.data_as(_PD), n, T, max_lag, gamma.ctypes.data_as(_PD))
+    return gamma
+
+
+def sokal_tau(gamma):
+    """statistics/autocorrelation.rs:201-210"""
+    g = np.ascontiguousarray(gamma, dtype=np.float64)
+    f = lib().orc_sokal_tau
+    f.restype = C.c_double
+    f.argtypes = [_PD, C.c_int]
+    return float(f(g.ctypes.data_as(_PD), len(g)))

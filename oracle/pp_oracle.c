@@ -642,11 +642,87 @@ const float *orc_sim_energies(const orc_sim *sim, int64_t r) { return sim->reals
 /* ======================================================================
  * Sweep loop for one realization  (simulation/mod.rs:177-863, hot-path lines only)
  * ====================================================================== */
+/* ---- statistics/autocorrelation.rs: ring backend ------------------------------------------------ */
+typedef struct {
+    int max_lag, n_temps, ring_len, ring_pos;
+    int64_t n_recorded;
+    double *sum_o, *sum_o2, *sum_prod; /* [T], [T], [T][max_lag+1] */
+    float *ring;                       /* [T][ring_len] */
+} autocorr;
+
+static autocorr *ac_new(int max_lag, int n_temps) { /* :33-65 */
+    autocorr *a = calloc(1, sizeof *a);
+    a->max_lag = max_lag; a->n_temps = n_temps; a->ring_len = max_lag + 1;
+    a->sum_o = calloc((size_t)n_temps, sizeof(double));
+    a->sum_o2 = calloc((size_t)n_temps, sizeof(double));
+    a->sum_prod = calloc((size_t)n_temps * (size_t)(max_lag + 1), sizeof(double));
+    a->ring = calloc((size_t)n_temps * (size_t)(max_lag + 1), sizeof(float));
+    return a;
+}
+static void ac_free(autocorr *a) {
+    if (!a) return;
+    free(a->sum_o); free(a->sum_o2); free(a->sum_prod); free(a->ring); free(a);
+}
+static void ac_push(autocorr *a, const double *values) { /* :68-112 */
+    for (int t = 0; t < a->n_temps; t++) {
+        float o = (float)values[t];
+        a->sum_o[t] += (double)o;
+        a->sum_o2[t] += (double)o * (double)o;
+    }
+    int pos = a->ring_pos;
+    int64_t n_back = a->n_recorded < a->max_lag ? a->n_recorded : a->max_lag;
+    for (int t = 0; t < a->n_temps; t++) {
+        float o = (float)values[t];
+        float *ring = a->ring + (size_t)t * a->ring_len;
+        double *sp = a->sum_prod + (size_t)t * (a->max_lag + 1);
+        ring[pos] = o;
+        int64_t no_wrap = pos < n_back ? pos : n_back;
+        for (int64_t delta = 0; delta <= no_wrap; delta++) sp[delta] += (double)o * (double)ring[pos - delta];
+        for (int64_t delta = pos + 1; delta <= n_back; delta++) sp[delta] += (double)o * (double)ring[pos + a->ring_len - delta];
+    }
+    a->ring_pos = (pos + 1) % a->ring_len;
+    a->n_recorded++;
+}
+static void ac_finish(const autocorr *a, double *gamma) { /* :114-124, :166-199; gamma[T][max_lag+1] */
+    int L1 = a->max_lag + 1;
+    for (int t = 0; t < a->n_temps; t++) {
+        double *g = gamma + (size_t)t * L1;
+        int degenerate = a->n_recorded == 0;
+        double mean = 0.0, var = 0.0, m = (double)a->n_recorded;
+        if (!degenerate) {
+            mean = a->sum_o[t] / m;
+            var = a->sum_o2[t] / m - mean * mean;
+            if (var <= 0.0) degenerate = 1;
+        }
+        for (int delta = 0; delta < L1; delta++) {
+            if (degenerate) { g[delta] = delta == 0 ? 1.0 : 0.0; continue; }
+            int64_t cnt = a->n_recorded > delta ? a->n_recorded - delta : 0;
+            if (cnt <= 0) { g[delta] = delta == 0 ? 1.0 : 0.0; continue; }
+            g[delta] = (a->sum_prod[(size_t)t * L1 + delta] / (double)cnt - mean * mean) / var;
+        }
+    }
+}
+double orc_sokal_tau(const double *gamma, int n) { /* :201-210 */
+    double tau = 0.5;
+    for (int w = 1; w < n; w++) {
+        tau += gamma[w];
+        if ((double)w >= 5.0 * tau) return tau;
+    }
+    return tau;
+}
+void orc_autocorr_gamma(const double *values, int64_t n_samples, int n_temps, int max_lag, double *gamma_out) {
+    autocorr *a = ac_new(max_lag, n_temps);
+    for (int64_t i = 0; i < n_samples; i++) ac_push(a, values + (size_t)i * n_temps);
+    ac_finish(a, gamma_out);
+    ac_free(a);
+}
+
 typedef struct {
     double *mags, *mags2, *mags4, *energies, *energies2; /* averages [T] */
     double *ov[6];                                        /* averages [T] */
     uint64_t *hist;                                       /* [T][N+1] */
     double *ql, *ql2;                                     /* [T][N+1] */
+    double *m2_tau, *q2_tau;                              /* [T] each when autocorrelation is on, else NULL */
 } real_result;
 
 /* mcmc/tempering.rs:73-102 with the draw supplied by the caller */
@@ -695,6 +771,17 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
     int64_t ov_count = 0;
     int64_t *msums = calloc((size_t)S + 1, sizeof(int64_t));
     uint32_t pt_event = pt_event0;
+    /* mod.rs:341-371: autocorrelation accumulators over the recorded sweeps */
+    autocorr *m2_acc = NULL, *q2_acc = NULL;
+    double *m2_ac_buf = NULL, *q2_ac_buf = NULL;
+    if (cfg->autocorr_max_lag > 0) {
+        int64_t n_meas = cfg->n_sweeps > cfg->warmup_sweeps ? cfg->n_sweeps - cfg->warmup_sweeps : 0;
+        int64_t k = cfg->autocorr_max_lag < n_meas / 4 ? cfg->autocorr_max_lag : n_meas / 4;
+        if (k < 1) k = 1;
+        m2_acc = ac_new((int)k, T);
+        m2_ac_buf = calloc((size_t)T, sizeof(double));
+        if (n_pairs > 0) { q2_acc = ac_new((int)k, T); q2_ac_buf = calloc((size_t)T, sizeof(double)); }
+    }
 
     for (int64_t sweep_id = 0; sweep_id < cfg->n_sweeps; sweep_id++) {
         int record = sweep_id >= cfg->warmup_sweeps; /* mod.rs:410 */
@@ -725,6 +812,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
 
         /* mod.rs:527-529 -> statistics/overlap.rs:251-333 (system_ids BEFORE this sweep's PT) */
         if (record && n_pairs > 0) {
+            if (q2_ac_buf) for (int t = 0; t < T; t++) q2_ac_buf[t] = 0.0; /* overlap.rs:255-257 */
             for (int p = 0; p < n_pairs; p++) {
                 for (int t = 0; t < T; t++) {
                     int64_t sa = re->system_ids[(2 * p) * T + t];
@@ -745,6 +833,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                     res->hist[t * bins + idx] += 1;
                     res->ql[t * bins + idx] += (double)ql;
                     res->ql2[t * bins + idx] += (double)(ql * ql);
+                    if (q2_ac_buf) q2_ac_buf[t] += (double)q2; /* overlap.rs:314-316 */
                 }
                 ov_count++;
             }
@@ -752,6 +841,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
 
         /* mod.rs:543-578 + statistics/stats.rs:17-27 */
         if (record) {
+            if (m2_ac_buf) for (int t = 0; t < T; t++) m2_ac_buf[t] = 0.0; /* mod.rs:551-553 */
             for (int r = 0; r < R; r++) {
                 for (int t = 0; t < T; t++) {
                     int64_t sys = re->system_ids[r * T + t];
@@ -759,6 +849,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                     float m2 = mag * mag;
                     float m4 = m2 * m2;
                     float e = re->energies[sys];
+                    if (m2_ac_buf) m2_ac_buf[t] += (double)m2; /* mod.rs:568-570 */
                     s_m[t] += (double)mag;
                     s_m2[t] += (double)m2;
                     s_m4[t] += (double)m4;
@@ -766,6 +857,16 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                     s_e2[t] += (double)e * (double)e; /* powi(2) in f64 */
                 }
                 stat_count++;
+            }
+            if (m2_acc) { /* mod.rs:580-586 */
+                double inv = 1.0 / (double)R;
+                for (int t = 0; t < T; t++) m2_ac_buf[t] *= inv;
+                ac_push(m2_acc, m2_ac_buf);
+            }
+            if (q2_acc) { /* mod.rs:588-594 */
+                double inv = 1.0 / (double)n_pairs;
+                for (int t = 0; t < T; t++) q2_ac_buf[t] *= inv;
+                ac_push(q2_acc, q2_ac_buf);
             }
         }
 
@@ -826,6 +927,19 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
     double oc = ov_count > 0 ? (double)ov_count : 1.0;
     for (int k = 0; k < 6; k++)
         for (int t = 0; t < T; t++) res->ov[k][t] = s_ov[k * T + t] / oc;
+    /* mod.rs:825-832: tau[t] = sokal_tau(gamma[t]) */
+    if (m2_acc) {
+        int L1 = m2_acc->max_lag + 1;
+        double *gamma = malloc(sizeof(double) * (size_t)T * L1);
+        ac_finish(m2_acc, gamma);
+        for (int t = 0; t < T; t++) res->m2_tau[t] = orc_sokal_tau(gamma + (size_t)t * L1, L1);
+        if (q2_acc) {
+            ac_finish(q2_acc, gamma);
+            for (int t = 0; t < T; t++) res->q2_tau[t] = orc_sokal_tau(gamma + (size_t)t * L1, L1);
+        }
+        free(gamma);
+    }
+    ac_free(m2_acc); ac_free(q2_acc); free(m2_ac_buf); free(q2_ac_buf);
     free(s_m); free(s_ov); free(msums); free(table);
 }
 
@@ -868,6 +982,10 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
         rr[d].mags2 = rr[d].mags + T; rr[d].mags4 = rr[d].mags + 2 * T;
         rr[d].energies = rr[d].mags + 3 * T; rr[d].energies2 = rr[d].mags + 4 * T;
         for (int k = 0; k < 6; k++) rr[d].ov[k] = rr[d].mags + (5 + k) * T;
+        if (cfg->autocorr_max_lag > 0) {
+            rr[d].m2_tau = calloc((size_t)T * 2, sizeof(double));
+            rr[d].q2_tau = rr[d].m2_tau + T;
+        }
         if (n_pairs > 0) {
             if (out->ps_hist) {
                 rr[d].hist = out->ps_hist + (size_t)d * T * bins;
@@ -936,10 +1054,23 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
             memcpy(out->round_trips + d * R * T, sim->reals[d].pt.round_trips, sizeof(uint64_t) * (size_t)R * T);
         }
     }
+    if (cfg->autocorr_max_lag > 0) { /* results.rs:217-231, 269-274: sum over realizations in order, divide by D */
+        double *td[2] = {out->mags2_tau, n_pairs > 0 ? out->overlap2_tau : NULL};
+        for (int k = 0; k < 2; k++) {
+            if (!td[k]) continue;
+            for (int t = 0; t < T; t++) td[k][t] = 0.0;
+            for (int64_t d = 0; d < D; d++)
+                for (int t = 0; t < T; t++) td[k][t] += rr[d].m2_tau[k * T + t];
+            for (int t = 0; t < T; t++) td[k][t] /= n;
+        }
+        if (out->ps_taus)
+            for (int64_t d = 0; d < D; d++) memcpy(out->ps_taus + (size_t)d * 2 * T, rr[d].m2_tau, sizeof(double) * 2 * (size_t)T);
+    }
     if (out->ps_means) /* [D][11][T]: rr[d].mags is one block of 11 rows (mags..energies2, then the six overlap rows) */
         for (int64_t d = 0; d < D; d++) memcpy(out->ps_means + (size_t)d * 11 * T, rr[d].mags, sizeof(double) * 11 * (size_t)T);
     for (int64_t d = 0; d < D; d++) {
         free(rr[d].mags);
+        free(rr[d].m2_tau);
         if (n_pairs > 0 && !out->ps_hist) { free(rr[d].hist); free(rr[d].ql); free(rr[d].ql2); }
     }
     free(rr);

@@ -65,6 +65,7 @@ typedef struct {
     int32_t pt_schedule;  /* ORC_PT_* */
     int32_t n_threads;    /* threads over realizations (<=1: sequential) */
     int32_t force_log_form; /* 1: never use the +-J lookup (test of LUT == log form) */
+    int64_t autocorr_max_lag; /* 0 = off; simulation/mod.rs:342-344: clamped to [1, recorded sweeps / 4] */
 } orc_config;
 
 typedef struct {
@@ -82,6 +83,11 @@ typedef struct {
     uint64_t *edge_attempts, *edge_acceptances, *round_trips;
     /* [D][11][T] per-realization averages (mags, mags2, mags4, energies, energies2, q, q2, q4, ql, ql2, ql4); may be NULL */
     double *ps_means;
+    /* [T] each: integrated autocorrelation times of m^2 and q^2, mean over realizations (statistics/results.rs:217-272);
+     * written when autocorr_max_lag > 0 (overlap2_tau only when n_replicas >= 2); may be NULL */
+    double *mags2_tau, *overlap2_tau;
+    /* [D][2][T] per-realization taus (m^2 row, q^2 row); may be NULL */
+    double *ps_taus;
 } orc_results;
 
 /* ---- RNG primitives ---------------------------------------------------- */
@@ -139,6 +145,13 @@ int orc_full_ladder_edges(int n_temps, int first_parity, int32_t *edges_out);
 void orc_pt_replay(int n_replicas, int n_temps, const float *temps, int n_attempts, const int32_t *edges,
                    const int32_t *accepted, const int64_t *left, const int64_t *right,
                    uint64_t *edge_attempts, uint64_t *edge_acceptances, uint64_t *round_trips);
+
+/* ---- autocorrelation (statistics/autocorrelation.rs) -------------------- */
+/* AutocorrAccum ring backend (:24-124, :166-199): push n_samples rows values[n_samples][n_temps], then finish():
+ * gamma_out[n_temps][max_lag + 1] */
+void orc_autocorr_gamma(const double *values, int64_t n_samples, int n_temps, int max_lag, double *gamma_out);
+/* sokal_tau (:201-210) over gamma[0..n) */
+double orc_sokal_tau(const double *gamma, int n);
 
 /* ---- full simulation (simulation/mod.rs:405-796, 865-939) -------------- */
 orc_sim *orc_sim_new(int n_dims, const int64_t *shape, int n_offsets, const int64_t *offsets,

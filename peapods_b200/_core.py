@@ -176,6 +176,16 @@ class IsingSimulation:
             res.pt_edge_acceptances = pt["edge_acceptances"].ctypes.data_as(_lib._PU64)
             res.pt_round_trips = pt["round_trips"].ctypes.data_as(_lib._PU64)
 
+        taus = None
+        if autocorrelation_max_lag is not None:  # src/lib.rs:545-556 (ring accumulation for both backends)
+            out["mags2_tau"] = np.zeros(T, dtype=np.float64)
+            res.mags2_tau = out["mags2_tau"].ctypes.data_as(_lib._PD)
+            if R >= 2:
+                out["overlap2_tau"] = np.zeros(T, dtype=np.float64)
+                res.overlap2_tau = out["overlap2_tau"].ctypes.data_as(_lib._PD)
+            taus = np.zeros((D, 2, T), dtype=np.float64)
+            res.per_sample_taus = taus.ctypes.data_as(_lib._PD)
+
         cb = _lib.ON_SWEEP(lambda _user, sweep: on_sweep(int(sweep))) if on_sweep is not None else None
         flag_ptr = None
         if interrupt is not None:  # an int32 numpy scalar array the caller may set to non-zero
@@ -188,6 +198,7 @@ class IsingSimulation:
         self.last_sweep_kernel_ms = float(res.sweep_kernel_ms)
         self.last_sweep_kernel_launches = int(res.sweep_kernel_launches)
         self.last_per_sample_means = means
+        self.last_per_sample_taus = taus
         if R >= 2:
             out["overlap_histogram"] = [hist[t].copy() for t in range(T)]  # list of u64[N+1], src/lib.rs:358-366
         if pt is not None:

@@ -72,6 +72,7 @@ class Results(C.Structure):
         + [("pt_edge_attempts", _PU64), ("pt_edge_acceptances", _PU64), ("pt_round_trips", _PU64)]
         + [("per_sample_means", _PD), ("sweep_loop_ms", C.c_double), ("kernel_launches", C.c_int64),
            ("sweep_kernel_ms", C.c_double), ("sweep_kernel_launches", C.c_int64)]
+        + [("mags2_tau", _PD), ("overlap2_tau", _PD), ("per_sample_taus", _PD)]
     )
 
 
@@ -120,7 +121,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.pp_abi_version() != 2:
+    if lib.pp_abi_version() != 3:
         raise ImportError("libpeapods_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1248,8 +1248,7 @@ static pp_status validate_cfg(const pp_sample_cfg *c) {
         return fail(PP_ERR_UNSUPPORTED, "cluster updates (cluster_update_interval) are not implemented on the GPU sweep path");
     if (c->overlap_cluster_update_interval != 0)
         return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep path");
-    if (c->autocorrelation_max_lag != 0)
-        return fail(PP_ERR_UNSUPPORTED, "autocorrelation_max_lag is not implemented on the GPU sweep path");
+    if (c->autocorrelation_max_lag < 0) return fail(PP_ERR_INVALID, "autocorrelation_max_lag must be >= 1");
     if (c->snapshot_interval != 0) return fail(PP_ERR_UNSUPPORTED, "snapshot_interval is not implemented on the GPU sweep path");
     if (c->equilibration_diagnostic != 0)
         return fail(PP_ERR_UNSUPPORTED, "equilibration_diagnostic is not implemented on the GPU sweep path");
@@ -1314,6 +1313,32 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemsetAsync(s->st.ql_at_q, 0, sizeof(double) * n, s->stream));
         CUDA_TRY(cudaMemsetAsync(s->st.ql2_at_q, 0, sizeof(double) * n, s->stream));
     }
+    // autocorrelation accumulators (mod.rs:341-371): fresh per call, one per (realization, temperature)
+    AutocorrView ac_m{0, nullptr, nullptr, nullptr, nullptr}, ac_q{0, nullptr, nullptr, nullptr, nullptr};
+    double *d_tau = nullptr;
+    const bool want_ac = cfg->autocorrelation_max_lag > 0;
+    auto free_ac = [&]() {
+        pool_free(s, ac_m.ring); pool_free(s, ac_m.sum_prod); pool_free(s, ac_m.sum_o);
+        pool_free(s, ac_q.ring); pool_free(s, ac_q.sum_prod); pool_free(s, ac_q.sum_o);
+        pool_free(s, d_tau);
+    };
+    if (want_ac) {
+        if (s->layout == PP_LAYOUT_SLAB) return fail(PP_ERR_UNSUPPORTED, "autocorrelation_max_lag is not implemented for the slab layout");
+        const int K = (int)std::max<int64_t>(1, std::min<int64_t>(cfg->autocorrelation_max_lag, n_rec / 4));
+        const size_t ndt = (size_t)m.D * m.T, len = (size_t)K + 1;
+        for (AutocorrView *a : {&ac_m, &ac_q}) {
+            if (a == &ac_q && m.P == 0) break;
+            a->K = K;
+            CUDA_TRY(pool_alloc(s, (void **)&a->ring, sizeof(float) * ndt * len));
+            CUDA_TRY(pool_alloc(s, (void **)&a->sum_prod, sizeof(double) * ndt * len));
+            CUDA_TRY(pool_alloc(s, (void **)&a->sum_o, sizeof(double) * ndt * 2));
+            a->sum_o2 = a->sum_o + ndt;
+            CUDA_TRY(cudaMemsetAsync(a->ring, 0, sizeof(float) * ndt * len, s->stream));
+            CUDA_TRY(cudaMemsetAsync(a->sum_prod, 0, sizeof(double) * ndt * len, s->stream));
+            CUDA_TRY(cudaMemsetAsync(a->sum_o, 0, sizeof(double) * ndt * 2, s->stream));
+        }
+        CUDA_TRY(pool_alloc(s, (void **)&d_tau, sizeof(double) * ndt * 2));
+    }
     const int64_t launches0 = s->launches;
     s->profile = cfg->profile != 0;
     s->prof_used = 0;
@@ -1355,11 +1380,12 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         bool record, pt_this;
         uint32_t pt_event;
         int parity;
+        int64_t sid_last;  // index, inside this call, of the batch's last sweep
     };
     std::vector<Step> steps;
     int64_t sweep_id = 0;
     // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel, up to 256 sweeps per launch
-    if (s->rows && s->resident && !s->profile) {
+    if (s->rows && s->resident && !s->profile && !want_ac) {
         Ctx &c = chunks[0];
         RowsView v = s->rv;
         v.keys = s->d_keys;
@@ -1412,6 +1438,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             for (Ctx &c : chunks) flush_swaps(s, c);
             commit_ctx(s, chunks[0]);
             cudaDeviceSynchronize();
+            free_ac();
             return fail(PP_ERR_INTERRUPTED, "interrupted");
         }
         // the sequence of kernel steps of this macro batch (mod.rs:405-432, 486-509, 748-796), identical for every chunk
@@ -1439,6 +1466,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             stp.pt_this = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;       // mod.rs:486-488
             stp.pt_event = pt_event;
             stp.parity = parity;
+            stp.sid_last = last;
             steps.push_back(stp);
             sweep_counter += (uint32_t)batch;
             if (stp.pt_this && m.T >= 2) {
@@ -1459,6 +1487,20 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     st = launch_overlap(s, c);                                         // mod.rs:527-529
                     if (st != PP_OK) return st;
                     fold_kernel<<<blocks_for(c.m.D * c.m.T, 128), 128, 0, c.stream>>>(c.m, c.st, c.m.P > 0);  // mod.rs:543-578
+                    s->launches++;
+                }
+                if (stp.record && want_ac) {                                           // mod.rs:580-594 (pre-exchange system_ids)
+                    const int64_t d0 = c.m.sample_offset - s->mv.sample_offset;
+                    auto shifted = [&](const AutocorrView &a) {
+                        AutocorrView v = a;
+                        if (v.ring) {
+                            const int64_t o1 = d0 * c.m.T, oK = o1 * (a.K + 1);
+                            v.ring += oK; v.sum_prod += oK; v.sum_o += o1; v.sum_o2 += o1;
+                        }
+                        return v;
+                    };
+                    autocorr_push_kernel<<<(unsigned)(c.m.D * c.m.T), 64, 0, c.stream>>>(c.m, c.dot_spin, shifted(ac_m), shifted(ac_q),
+                                                                                         (long long)(stp.sid_last - cfg->warmup_sweeps));
                     s->launches++;
                 }
                 if (stp.pt_this) {                                                     // mod.rs:748-796
@@ -1497,6 +1539,17 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     }
     const int64_t prof_n = (int64_t)(s->prof_used / 2);
     s->profile = false;
+    std::vector<double> taus;  // [2][D][T]: per-realization taus of m^2, then of q^2 (mod.rs:825-832)
+    if (want_ac) {
+        const int64_t ndt = m.D * m.T;
+        autocorr_tau_kernel<<<blocks_for(ndt, 128), 128, 0, s->stream>>>(ndt, ac_m, (long long)std::max<int64_t>(n_rec, 0), d_tau);
+        if (ac_q.ring)
+            autocorr_tau_kernel<<<blocks_for(ndt, 128), 128, 0, s->stream>>>(ndt, ac_q, (long long)std::max<int64_t>(n_rec, 0), d_tau + ndt);
+        taus.assign((size_t)ndt * 2, 0.0);
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaMemcpy(taus.data(), d_tau, sizeof(double) * (size_t)ndt * (ac_q.ring ? 2 : 1), cudaMemcpyDeviceToHost));
+        free_ac();
+    }
     if (!out) return PP_OK;
     out->sweep_loop_ms = ms;
     out->kernel_launches = s->launches - launches0;
@@ -1522,6 +1575,21 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             for (int64_t d = 0; d < m.D; d++) acc += sums[((size_t)d * 11 + k) * T + t];
             dst[k][t] = acc / (double)m.D;
         }
+    }
+    if (want_ac) {  // results.rs:217-231, 269-274: sum over realizations in order, divide by their number
+        double *tdst[2] = {out->mags2_tau, m.P > 0 ? out->overlap2_tau : nullptr};
+        for (int k = 0; k < 2; k++) {
+            if (!tdst[k]) continue;
+            for (int t = 0; t < T; t++) {
+                double acc = 0.0;
+                for (int64_t d = 0; d < m.D; d++) acc += taus[(size_t)k * m.D * T + (size_t)d * T + t];
+                tdst[k][t] = acc / (double)m.D;
+            }
+        }
+        if (out->per_sample_taus)
+            for (int64_t d = 0; d < m.D; d++)
+                for (int k = 0; k < 2; k++)
+                    memcpy(out->per_sample_taus + ((size_t)d * 2 + k) * T, &taus[(size_t)k * m.D * T + (size_t)d * T], sizeof(double) * (size_t)T);
     }
     if (m.P > 0) {
         const int64_t per = (int64_t)T * (m.N + 1);

@@ -140,6 +140,90 @@ __global__ void fold_kernel(ModelView m, StatsView st, int with_overlap) {
         [&](int p) { return st.dot_link[(d * m.P + p) * m.T + t]; });
 }
 
+// ------------------------------------------------------------------------------------------------
+// Integrated autocorrelation times of m^2 and q^2 (statistics/autocorrelation.rs, ring backend; driven from
+// simulation/mod.rs:341-371, 551-594, 825-832).  One accumulator per (realization d, temperature t):
+// ring f32 [K + 1], sum_prod f64 [K + 1], sum_o / sum_o2 f64.  All f64 operations are the reference's, in its order.
+struct AutocorrView {
+    int K;             // max lag (already clamped, mod.rs:342-344)
+    float *ring;       // [D][T][K + 1]
+    double *sum_prod;  // [D][T][K + 1]
+    double *sum_o, *sum_o2;  // [D][T]
+};
+
+// After the fold of one recorded sweep (pre-exchange system_ids): block (d, t) rebuilds this sweep's two measurements from
+// the per-system magnetisation sums and the pair dots -- m2 = (sum_r (f64)(f32)mag_r^2) / R (mod.rs:568-586),
+// q2 = (sum_p (f64)(f32)q_p^2) / P (overlap.rs:314-316, mod.rs:588-594) -- and pushes them (autocorrelation.rs:68-112).
+__global__ void __launch_bounds__(64)
+autocorr_push_kernel(ModelView m, const long long *dot_spin, AutocorrView am, AutocorrView aq, long long n_recorded) {
+    __shared__ float o_sh[2];
+    const int64_t dt = blockIdx.x;
+    const int64_t d = dt / m.T;
+    const int t = (int)(dt % m.T);
+    const float nf = (float)m.N;
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int r = 0; r < m.R; r++) {
+            const float mag = __fdiv_rn((float)m.mags[d * m.S + m.system_ids[d * m.S + r * m.T + t]], nf);
+            acc = __dadd_rn(acc, (double)__fmul_rn(mag, mag));
+        }
+        o_sh[0] = (float)__dmul_rn(acc, __ddiv_rn(1.0, (double)m.R));
+    } else if (threadIdx.x == 32 && aq.ring) {
+        double acc = 0.0;
+        for (int p = 0; p < m.P; p++) {
+            const float q = __fdiv_rn((float)dot_spin[(d * m.P + p) * m.T + t], nf);
+            acc = __dadd_rn(acc, (double)__fmul_rn(q, q));
+        }
+        o_sh[1] = (float)__dmul_rn(acc, __ddiv_rn(1.0, (double)m.P));
+    }
+    __syncthreads();
+    for (int which = 0; which < 2; which++) {
+        const AutocorrView &a = which == 0 ? am : aq;
+        if (!a.ring) continue;
+        const int len = a.K + 1, pos = (int)(n_recorded % len);
+        const long long n_back = n_recorded < a.K ? n_recorded : a.K;
+        const double o = (double)o_sh[which];
+        float *ring = a.ring + dt * len;
+        double *sp = a.sum_prod + dt * len;
+        for (long long delta = threadIdx.x; delta <= n_back; delta += blockDim.x) {
+            const float other = delta == 0 ? o_sh[which] : ring[pos >= delta ? pos - delta : pos + len - delta];
+            sp[delta] = __dadd_rn(sp[delta], __dmul_rn(o, (double)other));
+        }
+        if (threadIdx.x == 0) {
+            a.sum_o[dt] = __dadd_rn(a.sum_o[dt], o);
+            a.sum_o2[dt] = __dadd_rn(a.sum_o2[dt], __dmul_rn(o, o));
+        }
+    }
+    __syncthreads();  // every lag has read the old ring before the newest value lands (the slot at pos is never read above)
+    if (threadIdx.x == 0) am.ring[dt * (am.K + 1) + (int)(n_recorded % (am.K + 1))] = o_sh[0];
+    if (threadIdx.x == 32 && aq.ring) aq.ring[dt * (aq.K + 1) + (int)(n_recorded % (aq.K + 1))] = o_sh[1];
+}
+
+// finish() + sokal_tau (autocorrelation.rs:114-124, 166-210): one thread per (d, t)
+__global__ void autocorr_tau_kernel(int64_t n_dt, AutocorrView a, long long n_recorded, double *tau_out) {
+    const int64_t dt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dt >= n_dt) return;
+    const int len = a.K + 1;
+    bool degenerate = n_recorded == 0;
+    double mm = 0.0, var = 0.0;
+    if (!degenerate) {
+        const double mcount = (double)n_recorded;
+        const double mean = __ddiv_rn(a.sum_o[dt], mcount);
+        mm = __dmul_rn(mean, mean);
+        var = __dsub_rn(__ddiv_rn(a.sum_o2[dt], mcount), mm);
+        if (var <= 0.0) degenerate = true;
+    }
+    double tau = 0.5;
+    for (int w = 1; w < len; w++) {
+        double g = 0.0;
+        const long long cnt = n_recorded > w ? n_recorded - w : 0;
+        if (!degenerate && cnt > 0) g = __ddiv_rn(__dsub_rn(__ddiv_rn(a.sum_prod[dt * len + w], (double)cnt), mm), var);
+        tau = __dadd_rn(tau, g);
+        if ((double)w >= __dmul_rn(5.0, tau)) break;
+    }
+    tau_out[dt] = tau;
+}
+
 // realization.rs:109-120
 __device__ __forceinline__ void pt_record_arrival(const PtView &pt, int64_t base, int system, int slot) {
     if (slot == pt.hot_slot) {

@@ -58,6 +58,15 @@ def merge_results(parts):
         for name in ("per_sample_overlap_histogram", "per_sample_ql_at_q_sum", "per_sample_ql2_at_q_sum"):
             if all(name in p["result"] for p in parts) and D > 1:
                 out[name] = np.concatenate([p["result"][name] for p in parts], axis=0)
+    if all(p.get("per_sample_taus") is not None for p in parts):  # results.rs:217-231, 269-274: ordered mean of the taus
+        taus = np.concatenate([p["per_sample_taus"] for p in parts], axis=0)  # [D, 2, T]
+        for k, name in enumerate(("mags2_tau", "overlap2_tau")):
+            if name not in first:
+                continue
+            acc = np.zeros(T, dtype=np.float64)
+            for d in range(D):
+                acc += taus[d, k]
+            out[name] = acc / float(D)
     if "per_disorder" in first:
         pt = {}
         for name in ("edge_attempts", "edge_acceptances", "round_trips"):
@@ -66,12 +75,13 @@ def merge_results(parts):
     return out
 
 
-def gather_merge(result, per_sample_means, n_replicas, group=None, dst=0):
+def gather_merge(result, per_sample_means, n_replicas, group=None, dst=0, per_sample_taus=None):
     """Collective: gather every rank's part on ``dst`` and merge (returns None elsewhere).  Uses the object
     collectives of ``torch.distributed`` (a few MB of scalars; works on the NCCL and the gloo backend)."""
     import torch.distributed as dist
 
-    part = {"result": result, "per_sample_means": np.asarray(per_sample_means), "n_replicas": int(n_replicas)}
+    part = {"result": result, "per_sample_means": np.asarray(per_sample_means), "n_replicas": int(n_replicas),
+            "per_sample_taus": None if per_sample_taus is None else np.asarray(per_sample_taus)}
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merge_results([part])
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -105,7 +115,8 @@ class ShardedIsingSimulation:
     def sample(self, *args, **kwargs):
         """Every rank samples its block; rank 0 returns the merged dict, the others None."""
         local = self.sim.sample(*args, **kwargs)
-        return gather_merge(local, self.sim.last_per_sample_means, self.n_replicas)
+        return gather_merge(local, self.sim.last_per_sample_means, self.n_replicas,
+                            per_sample_taus=getattr(self.sim, "last_per_sample_taus", None))
 
 
 def slab_plan(extent0: int, world: int, rank: int):

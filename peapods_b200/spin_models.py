@@ -136,6 +136,10 @@ class Ising:
                     "per_sample_ql_at_q_sum", "per_sample_ql2_at_q_sum"):
             if key in result:
                 setattr(self, key, result[key])
+        if "mags2_tau" in result:  # spin_models.py:311-314
+            self.mags2_tau = result["mags2_tau"]
+        if "overlap2_tau" in result:
+            self.overlap2_tau = result["overlap2_tau"]
         self.per_disorder = result.get("per_disorder", {})
         return result
 

@@ -448,3 +448,24 @@ def test_resident_kernel_long_runs_are_bit_exact(oracle, shape, kind, offsets, t
             assert np.array_equal(gpu.get_energies(d), cpu.energies(d))
     assert seen == list(range(300)) + list(range(259))
     assert gpu.last_kernel_launches <= 3
+
+
+# ---- integrated autocorrelation times (statistics/autocorrelation.rs driven from simulation/mod.rs:341-371,
+# 551-594, 825-832): the device accumulators repeat the reference's f64 operations in its order -> bit-exact taus ----
+@pytest.mark.parametrize("layout,shape,kind,offsets,temps,R,D", [
+    ("int8", (8, 8), "ferro", None, np.linspace(1.8, 2.8, 4), 2, 1),
+    ("int8", (4, 4, 4), "bimodal", None, [0.9, 1.3, 1.7], 4, 3),
+    ("int8", (6, 6), "bimodal", TRI, [1.0, 2.5], 3, 2),                 # unpaired replica; table-driven kernels
+    ("int8", (8, 8), "bimodal", None, [1.2, 2.0], 1, 2),                # one replica: no overlap2_tau
+    ("msc", (8, 8, 8), "bimodal", None, np.linspace(0.8, 1.6, 3), 2, 40),
+    ("msc", (16, 16, 16), "bimodal", None, [0.9, 1.3], 4, 33),          # msc3d, in-sweep energy path, chunked streams
+])
+def test_autocorrelation_taus_are_bit_exact(oracle, layout, shape, kind, offsets, temps, R, D):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets, layout=layout)
+    for n_sweeps, lag, interval in ((64, 5, 1), (41, 100, None), (3, 4, 2)):  # ring wraps; lag clamped to recorded / 4; to 1
+        rg = gpu.sample(n_sweeps, "metropolis", pt_interval=interval, autocorrelation_max_lag=lag)
+        rc = cpu.sample(n_sweeps, "metropolis", pt_interval=interval, autocorrelation_max_lag=lag)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        assert ("overlap2_tau" in rg) == (R >= 2) and "mags2_tau" in rg
+        assert np.array_equal(gpu.last_per_sample_taus[:, : (2 if R >= 2 else 1)], cpu.last_per_sample_taus[:, : (2 if R >= 2 else 1)])

@@ -283,3 +283,62 @@ def test_ferromagnet_orders_below_tc_and_not_above(oracle):
     assert r["mags2"][0] > 0.9 and r["mags2"][1] < 0.1
     # exact 2-D energy at T=1.5: e = +sum J s s / N ~ 1.951 (Onsager), sign convention energy.rs:103-108
     assert abs(r["energies"][0] - 1.951) < 0.01
+
+
+# ---- statistics/autocorrelation.rs:214-374 (the reference's own unit tests of the accumulator) ----
+def _deterministic_values(sample):  # autocorrelation.rs:283-288
+    return [float(np.float32((sample * 13 % 31)) / np.float32(8.0) - np.float32(2.0)),
+            float(np.float32((sample * 7 % 23)) / np.float32(4.0) - np.float32(1.5))]
+
+
+def _brute_force_gamma(series, max_lag):  # autocorrelation.rs:290-308
+    series = np.asarray(series, dtype=np.float64)
+    count = len(series)
+    mean = series.sum() / count
+    variance = (series * series).sum() / count - mean * mean
+    out = []
+    for delta in range(max_lag + 1):
+        pairs = max(count - delta, 0)
+        if pairs == 0 or variance <= 0.0:
+            out.append(1.0 if delta == 0 else 0.0)
+            continue
+        product_sum = float(np.sum(series[delta:] * series[:count - delta]))
+        out.append((product_sum / pairs - mean * mean) / variance)
+    return np.asarray(out)
+
+
+def test_autocorr_empty_and_constant_series_are_degenerate(oracle):  # autocorrelation.rs:331-343
+    assert np.array_equal(oracle.autocorr_gamma(np.zeros((0, 1)), 4), [[1.0, 0.0, 0.0, 0.0, 0.0]])
+    assert np.array_equal(oracle.autocorr_gamma(np.full((8, 1), 3.5), 4), [[1.0, 0.0, 0.0, 0.0, 0.0]])
+
+
+def test_autocorr_ring_matches_brute_force_across_wraps(oracle):  # autocorrelation.rs:310-329, 345-373
+    for n, lag in ((41, 7), (128, 40)):
+        values = np.asarray([_deterministic_values(s) for s in range(n)])
+        gamma = oracle.autocorr_gamma(values, lag)
+        for t in range(2):
+            np.testing.assert_allclose(gamma[t], _brute_force_gamma(values[:, t], lag), rtol=0, atol=1e-10)
+        assert gamma[0][0] == pytest.approx(1.0, abs=1e-12)
+
+
+def test_sokal_tau_window(oracle):  # autocorrelation.rs:201-210
+    assert oracle.sokal_tau([1.0]) == 0.5
+    assert oracle.sokal_tau([1.0, 0.0, 0.0]) == 0.5                    # w = 1 >= 5 * 0.5 fails, w = 2 ... runs out
+    g = [1.0] + [0.5 ** w for w in range(1, 40)]
+    tau = oracle.sokal_tau(g)
+    assert 1.4 < tau < 1.5                                              # 0.5 + sum of the geometric tail up to the window
+    assert oracle.sokal_tau([1.0, 0.05, 0.9, 0.9]) == pytest.approx(2.35)        # window never closes: the whole sum
+    assert oracle.sokal_tau([1.0, 0.1, 0.05, 0.0, 0.0, 5.0]) == pytest.approx(0.65)  # closes at w = 4 >= 5 * 0.65: the tail is ignored
+
+
+def test_autocorrelation_keys_and_lag_clamp(oracle):
+    """mod.rs:342-344: the lag is clamped to recorded / 4 (at least 1); taus are means over realizations (results.rs:217-272)."""
+    rng = np.random.default_rng(0)
+    J = (2 * rng.integers(0, 2, size=(2, 4, 4, 2)) - 1).astype(np.float32)
+    sim = oracle.Sim((4, 4), J, np.asarray([1.5, 2.5], np.float32), n_replicas=2, seed=3)
+    res = sim.sample(40, "metropolis", autocorrelation_max_lag=1000)
+    assert res["mags2_tau"].shape == (2,) and res["overlap2_tau"].shape == (2,)
+    assert np.all(np.isfinite(res["mags2_tau"])) and np.all(np.isfinite(res["overlap2_tau"]))
+    assert np.allclose(res["mags2_tau"], sim.last_per_sample_taus[:, 0, :].sum(axis=0) / 2)
+    sim1 = oracle.Sim((4, 4), J[0], np.asarray([1.5, 2.5], np.float32), n_replicas=1, seed=3)
+    assert "overlap2_tau" not in sim1.sample(40, "metropolis", autocorrelation_max_lag=5)

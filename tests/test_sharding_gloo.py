@@ -26,9 +26,9 @@ def _run_block(first, count):
     colour, _ = colouring(SHAPE)
     sim = oracle.Sim(SHAPE, _couplings()[first:first + count], TEMPS, n_replicas=R, seed=77, rng_mode=oracle.RNG_PHILOX_MSC,
                      colour=colour, sample_offset=first)
-    res = sim.sample(30, "metropolis", pt_interval=1, pt_schedule="full_ladder")
+    res = sim.sample(30, "metropolis", pt_interval=1, pt_schedule="full_ladder", autocorrelation_max_lag=4)
     res["overlap_histogram"] = [h for h in res["overlap_histogram"]]
-    return res, sim.last_per_sample_means
+    return res, sim.last_per_sample_means, sim.last_per_sample_taus
 
 
 def _worker(rank, world, port, out_path):
@@ -40,8 +40,8 @@ def _worker(rank, world, port, out_path):
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     first, count = shard_bounds(D, world, rank)
-    res, means = _run_block(first, count)
-    merged = gather_merge(res, means, R)
+    res, means, taus = _run_block(first, count)
+    merged = gather_merge(res, means, R, per_sample_taus=taus)
     if rank == 0:
         np.savez(out_path, **{k: np.asarray(v) for k, v in merged.items() if k != "per_disorder"},
                  **{"pt_" + k: v for k, v in merged["per_disorder"]["parallel_tempering"].items()})
@@ -71,9 +71,9 @@ def test_two_gloo_ranks_reproduce_the_unsharded_run(tmp_path):
     mp.spawn(_worker, args=(2, port, out_path), nprocs=2, join=True)
     merged = np.load(out_path)
     sys.path.insert(0, str(ROOT))
-    ref, _ = _run_block(0, D)
+    ref, _, _ = _run_block(0, D)
     for k in ("mags", "mags2", "mags4", "energies", "energies2", "overlap", "overlap2", "overlap4", "link_overlap",
-              "link_overlap2", "link_overlap4"):
+              "link_overlap2", "link_overlap4", "mags2_tau", "overlap2_tau"):
         assert np.array_equal(merged[k], ref[k]), k            # ordered sum over realizations: bit for bit
     assert np.array_equal(merged["overlap_histogram"], np.stack(ref["overlap_histogram"]))
     for k in ("ql_at_q_sum", "ql2_at_q_sum"):
