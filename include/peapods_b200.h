@@ -97,6 +97,8 @@ typedef struct {
      * ring backend; the lag is clamped to [1, recorded sweeps / 4] as simulation/mod.rs:342-344) */
     int64_t autocorrelation_max_lag;
     int64_t snapshot_interval;                /* unsupported: must be 0 */
+    /* 1: equilibration diagnostic (statistics/equilibration.rs): energies and link overlaps are measured after EVERY sweep and
+     * their running averages reported at the checkpoints of pp_equil_checkpoints(n_sweeps) */
     int32_t equilibration_diagnostic;
     /* 1: fp32-coupling / Gibbs log thresholds are read from a host-libm logf table so that spin
      * trajectories are bit-identical to the CPU rule; 0: device logf (results agree to tolerance) */
@@ -129,6 +131,10 @@ typedef struct {
      * Sokal-windowed taus (statistics/results.rs:217-231, 269-274); overlap2_tau needs R >= 2 */
     double *mags2_tau, *overlap2_tau;
     double *per_sample_taus;   /* [D][2][T]: per-realization taus (m^2 row, q^2 row), for the ordered multi-GPU merge */
+    /* cfg.equilibration_diagnostic (src/lib.rs:559-574): [n_ckpt][T] running averages at the checkpoints, mean over this
+     * handle's realizations (statistics/results.rs:231-247, 275-282) */
+    double *equil_energy_avg, *equil_link_overlap_avg;
+    double *per_sample_equil;  /* [D][n_ckpt][2][T] per-realization checkpoints (energy row, link-overlap row) */
 } pp_results;
 
 const char *pp_last_error(void);
@@ -140,6 +146,8 @@ pp_status pp_colouring(int32_t n_dims, const int64_t *shape, int32_t n_offsets, 
 pp_status pp_metropolis_lookup(const float *temperatures, int32_t n_temps, int32_t n_neighbors, int32_t sweep_mode,
                                uint32_t *table_out /* [n_temps][4*n_neighbors+1] */);
 uint64_t pp_realization_seed(uint64_t root, uint64_t realization);
+/* statistics/equilibration.rs:18-29: 128, 256, ... < n_sweeps, then n_sweeps; returns the count, fills out[0..count) if not NULL */
+int32_t pp_equil_checkpoints(int64_t n_sweeps, int64_t *out);
 
 /* state-owning engine */
 pp_status pp_create(const pp_model_desc *desc, pp_sim **out);

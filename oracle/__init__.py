@@ -40,6 +40,7 @@ class _Config(C.Structure):
         ("n_threads", C.c_int32),
         ("force_log_form", C.c_int32),
         ("autocorr_max_lag", C.c_int64),
+        ("equil_diag", C.c_int32),
     ]
 
 
@@ -56,6 +57,7 @@ class _Results(C.Structure):
         + [("edge_attempts", _PU64), ("edge_acceptances", _PU64), ("round_trips", _PU64)]
         + [("ps_means", _PD)]
         + [("mags2_tau", _PD), ("overlap2_tau", _PD), ("ps_taus", _PD)]
+        + [("equil_energy_avg", _PD), ("equil_link_overlap_avg", _PD), ("ps_equil", _PD)]
     )
 
 
@@ -278,12 +280,13 @@ class Sim:
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(self.T * self.R,)).copy()
 
     def sample(self, n_sweeps, sweep_mode="metropolis", pt_interval=None, pt_schedule="single_random_edge",
-               warmup_ratio=0.25, n_threads=1, force_log_form=False, per_sample=True, autocorrelation_max_lag=None):
+               warmup_ratio=0.25, n_threads=1, force_log_form=False, per_sample=True, autocorrelation_max_lag=None,
+               equilibration_diagnostic=False):
         # src/lib.rs:219-220 (Rust f64::round = half away from zero)
         warm = int(np.floor(n_sweeps * warmup_ratio + 0.5))
         cfg = _Config(n_sweeps, warm, {"metropolis": 0, "gibbs": 1}[sweep_mode], 0 if pt_interval is None else pt_interval,
                       {"single_random_edge": 0, "full_ladder": 1}[pt_schedule], n_threads, int(force_log_form),
-                      0 if autocorrelation_max_lag is None else int(autocorrelation_max_lag))
+                      0 if autocorrelation_max_lag is None else int(autocorrelation_max_lag), int(bool(equilibration_diagnostic)))
         T, R, D, N = self.T, self.R, self.D, self.N
         out = {k: np.zeros(T, dtype=np.float64) for k in ("mags", "mags2", "mags4", "energies", "energies2")}
         res = _Results()
@@ -327,6 +330,15 @@ class Sim:
                 res.overlap2_tau = out["overlap2_tau"].ctypes.data_as(_PD)
             self.last_per_sample_taus = np.zeros((D, 2, T), dtype=np.float64)
             res.ps_taus = self.last_per_sample_taus.ctypes.data_as(_PD)
+        if equilibration_diagnostic:  # src/lib.rs:559-574
+            ck = equil_checkpoints(n_sweeps)
+            out["equil_sweeps"] = np.asarray(ck, dtype=np.uint64)
+            out["equil_energy_avg"] = np.zeros((len(ck), T), dtype=np.float64)
+            out["equil_link_overlap_avg"] = np.zeros((len(ck), T), dtype=np.float64)
+            res.equil_energy_avg = out["equil_energy_avg"].ctypes.data_as(_PD)
+            res.equil_link_overlap_avg = out["equil_link_overlap_avg"].ctypes.data_as(_PD)
+            self.last_per_sample_equil = np.zeros((D, len(ck), 2, T), dtype=np.float64)
+            res.ps_equil = self.last_per_sample_equil.ctypes.data_as(_PD)
         rc = lib().orc_sim_sample(self.h, C.byref(cfg), C.byref(res))
         del keep
         if rc != 0:
@@ -356,3 +368,13 @@ def sokal_tau(gamma):
     f.restype = C.c_double
     f.argtypes = [_PD, C.c_int]
     return float(f(g.ctypes.data_as(_PD), len(g)))
+
+
+def equil_checkpoints(n_sweeps):
+    """statistics/equilibration.rs:18-29"""
+    f = lib().orc_equil_checkpoints
+    f.restype = C.c_int
+    f.argtypes = [C.c_int64, C.POINTER(C.c_int64)]
+    buf = (C.c_int64 * 80)()
+    n = f(int(n_sweeps), buf)
+    return [int(buf[i]) for i in range(n)]

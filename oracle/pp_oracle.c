@@ -717,12 +717,21 @@ void orc_autocorr_gamma(const double *values, int64_t n_samples, int n_temps, in
     ac_free(a);
 }
 
+int orc_equil_checkpoints(int64_t n_sweeps, int64_t *out) { /* equilibration.rs:18-29 */
+    int n = 0;
+    int64_t last = -1;
+    for (int64_t p = 128; p < n_sweeps; p *= 2) { if (out) out[n] = p; last = p; n++; }
+    if (last != n_sweeps) { if (out) out[n] = n_sweeps; n++; }
+    return n;
+}
+
 typedef struct {
     double *mags, *mags2, *mags4, *energies, *energies2; /* averages [T] */
     double *ov[6];                                        /* averages [T] */
     uint64_t *hist;                                       /* [T][N+1] */
     double *ql, *ql2;                                     /* [T][N+1] */
     double *m2_tau, *q2_tau;                              /* [T] each when autocorrelation is on, else NULL */
+    double *equil;                                        /* [n_ckpt][2][T] when the equilibration diagnostic is on */
 } real_result;
 
 /* mcmc/tempering.rs:73-102 with the draw supplied by the caller */
@@ -771,6 +780,13 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
     int64_t ov_count = 0;
     int64_t *msums = calloc((size_t)S + 1, sizeof(int64_t));
     uint32_t pt_event = pt_event0;
+    /* mod.rs:373-383, equilibration.rs: running sums of the replica-mean energy and pair-mean link overlap of EVERY sweep */
+    int equil = cfg->equil_diag != 0;
+    int64_t ckpts[80];
+    int n_ckpt = equil ? orc_equil_checkpoints(cfg->n_sweeps, ckpts) : 0, next_ckpt = 0;
+    int64_t eq_count = 0;
+    double *eq_sum = equil ? calloc((size_t)T * 2, sizeof(double)) : NULL; /* energy row, link-overlap row */
+    float *diag_e = equil ? calloc((size_t)T * 2, sizeof(float)) : NULL, *diag_ql = equil ? diag_e + T : NULL;
     /* mod.rs:341-371: autocorrelation accumulators over the recorded sweeps */
     autocorr *m2_acc = NULL, *q2_acc = NULL;
     double *m2_ac_buf = NULL, *q2_ac_buf = NULL;
@@ -808,11 +824,19 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
         int pt_this_sweep = cfg->pt_interval > 0 && sweep_id % cfg->pt_interval == 0; /* mod.rs:486-488 */
 
         /* mod.rs:492-509 */
-        if (record || pt_this_sweep) orc_energies_mags(lat, re->spins, re->couplings, S, re->energies, record ? msums : NULL);
+        if (record || pt_this_sweep || equil) orc_energies_mags(lat, re->spins, re->couplings, S, re->energies, record ? msums : NULL);
+
+        if (equil) { /* mod.rs:511-525 */
+            for (int t = 0; t < T; t++) { diag_e[t] = 0.0f; diag_ql[t] = 0.0f; }
+            for (int r = 0; r < R; r++)
+                for (int t = 0; t < T; t++) diag_e[t] += re->energies[re->system_ids[r * T + t]];
+            float inv = 1.0f / (float)R;
+            for (int t = 0; t < T; t++) diag_e[t] *= inv;
+        }
 
         /* mod.rs:527-529 -> statistics/overlap.rs:251-333 (system_ids BEFORE this sweep's PT) */
-        if (record && n_pairs > 0) {
-            if (q2_ac_buf) for (int t = 0; t < T; t++) q2_ac_buf[t] = 0.0; /* overlap.rs:255-257 */
+        if ((record || equil) && n_pairs > 0) { /* mod.rs:527-529 */
+            if (q2_ac_buf && record) for (int t = 0; t < T; t++) q2_ac_buf[t] = 0.0; /* overlap.rs:255-257 */
             for (int p = 0; p < n_pairs; p++) {
                 for (int t = 0; t < T; t++) {
                     int64_t sa = re->system_ids[(2 * p) * T + t];
@@ -820,6 +844,8 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                     int64_t dot_spin, dot_link;
                     orc_overlap_dots(lat, re->spins + sa * N, re->spins + sb * N, &dot_spin, &dot_link);
                     float ql = (float)dot_link / (float)(N * z);
+                    if (equil) diag_ql[t] += ql; /* overlap.rs:285-287 */
+                    if (!record) continue;       /* overlap.rs:288-290 */
                     float q = (float)dot_spin / (float)N;
                     float q2 = q * q;
                     float ql2 = ql * ql;
@@ -835,7 +861,20 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                     res->ql2[t * bins + idx] += (double)(ql * ql);
                     if (q2_ac_buf) q2_ac_buf[t] += (double)q2; /* overlap.rs:314-316 */
                 }
-                ov_count++;
+                if (record) ov_count++;
+            }
+            if (equil) { /* overlap.rs:327-332 */
+                float inv = 1.0f / (float)n_pairs;
+                for (int t = 0; t < T; t++) diag_ql[t] *= inv;
+            }
+        }
+        if (equil) { /* mod.rs:531-541 -> equilibration.rs:43-58 */
+            eq_count++;
+            for (int t = 0; t < T; t++) { eq_sum[t] += (double)diag_e[t]; eq_sum[T + t] += (double)diag_ql[t]; }
+            if (next_ckpt < n_ckpt && eq_count == ckpts[next_ckpt]) {
+                double c = (double)eq_count;
+                for (int t = 0; t < 2 * T; t++) res->equil[(size_t)next_ckpt * 2 * T + t] = eq_sum[t] / c;
+                next_ckpt++;
             }
         }
 
@@ -940,6 +979,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
         free(gamma);
     }
     ac_free(m2_acc); ac_free(q2_acc); free(m2_ac_buf); free(q2_ac_buf);
+    free(eq_sum); free(diag_e);
     free(s_m); free(s_ov); free(msums); free(table);
 }
 
@@ -986,6 +1026,7 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
             rr[d].m2_tau = calloc((size_t)T * 2, sizeof(double));
             rr[d].q2_tau = rr[d].m2_tau + T;
         }
+        if (cfg->equil_diag) rr[d].equil = calloc((size_t)orc_equil_checkpoints(cfg->n_sweeps, NULL) * 2 * T, sizeof(double));
         if (n_pairs > 0) {
             if (out->ps_hist) {
                 rr[d].hist = out->ps_hist + (size_t)d * T * bins;
@@ -1066,11 +1107,28 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
         if (out->ps_taus)
             for (int64_t d = 0; d < D; d++) memcpy(out->ps_taus + (size_t)d * 2 * T, rr[d].m2_tau, sizeof(double) * 2 * (size_t)T);
     }
+    if (cfg->equil_diag) { /* results.rs:231-247, 275-282 */
+        int n_ckpt = orc_equil_checkpoints(cfg->n_sweeps, NULL);
+        double *ed[2] = {out->equil_energy_avg, out->equil_link_overlap_avg};
+        for (int k = 0; k < 2; k++) {
+            if (!ed[k]) continue;
+            for (int c = 0; c < n_ckpt; c++)
+                for (int t = 0; t < T; t++) {
+                    double acc = 0.0;
+                    for (int64_t d = 0; d < D; d++) acc += rr[d].equil[((size_t)c * 2 + k) * T + t];
+                    ed[k][(size_t)c * T + t] = acc / n;
+                }
+        }
+        if (out->ps_equil)
+            for (int64_t d = 0; d < D; d++)
+                memcpy(out->ps_equil + (size_t)d * n_ckpt * 2 * T, rr[d].equil, sizeof(double) * (size_t)n_ckpt * 2 * T);
+    }
     if (out->ps_means) /* [D][11][T]: rr[d].mags is one block of 11 rows (mags..energies2, then the six overlap rows) */
         for (int64_t d = 0; d < D; d++) memcpy(out->ps_means + (size_t)d * 11 * T, rr[d].mags, sizeof(double) * 11 * (size_t)T);
     for (int64_t d = 0; d < D; d++) {
         free(rr[d].mags);
         free(rr[d].m2_tau);
+        free(rr[d].equil);
         if (n_pairs > 0 && !out->ps_hist) { free(rr[d].hist); free(rr[d].ql); free(rr[d].ql2); }
     }
     free(rr);

@@ -66,6 +66,7 @@ typedef struct {
     int32_t n_threads;    /* threads over realizations (<=1: sequential) */
     int32_t force_log_form; /* 1: never use the +-J lookup (test of LUT == log form) */
     int64_t autocorr_max_lag; /* 0 = off; simulation/mod.rs:342-344: clamped to [1, recorded sweeps / 4] */
+    int32_t equil_diag;       /* 1: equilibration diagnostic (statistics/equilibration.rs; energies + link overlaps every sweep) */
 } orc_config;
 
 typedef struct {
@@ -88,6 +89,11 @@ typedef struct {
     double *mags2_tau, *overlap2_tau;
     /* [D][2][T] per-realization taus (m^2 row, q^2 row); may be NULL */
     double *ps_taus;
+    /* equil_diag: running averages at the checkpoints of orc_equil_checkpoints(n_sweeps): [n_ckpt][T] each, mean over
+     * realizations (statistics/results.rs:231-247, 275-282); may be NULL */
+    double *equil_energy_avg, *equil_link_overlap_avg;
+    /* [D][n_ckpt][2][T] per-realization checkpoints (energy row, link-overlap row); may be NULL */
+    double *ps_equil;
 } orc_results;
 
 /* ---- RNG primitives ---------------------------------------------------- */
@@ -152,6 +158,9 @@ void orc_pt_replay(int n_replicas, int n_temps, const float *temps, int n_attemp
 void orc_autocorr_gamma(const double *values, int64_t n_samples, int n_temps, int max_lag, double *gamma_out);
 /* sokal_tau (:201-210) over gamma[0..n) */
 double orc_sokal_tau(const double *gamma, int n);
+
+/* statistics/equilibration.rs:18-29: 128, 256, ... < n_sweeps, then n_sweeps.  Returns the count (out may be NULL). */
+int orc_equil_checkpoints(int64_t n_sweeps, int64_t *out);
 
 /* ---- full simulation (simulation/mod.rs:405-796, 865-939) -------------- */
 orc_sim *orc_sim_new(int n_dims, const int64_t *shape, int n_offsets, const int64_t *offsets,

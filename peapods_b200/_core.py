@@ -186,6 +186,18 @@ class IsingSimulation:
             taus = np.zeros((D, 2, T), dtype=np.float64)
             res.per_sample_taus = taus.ctypes.data_as(_lib._PD)
 
+        equil = None
+        if equilibration_diagnostic:  # src/lib.rs:559-574
+            buf = (C.c_int64 * 80)()
+            n_ckpt = self._lib.pp_equil_checkpoints(n_sweeps, buf)
+            out["equil_sweeps"] = np.asarray([buf[i] for i in range(n_ckpt)], dtype=np.uint64)
+            out["equil_energy_avg"] = np.zeros((n_ckpt, T), dtype=np.float64)
+            out["equil_link_overlap_avg"] = np.zeros((n_ckpt, T), dtype=np.float64)
+            res.equil_energy_avg = out["equil_energy_avg"].ctypes.data_as(_lib._PD)
+            res.equil_link_overlap_avg = out["equil_link_overlap_avg"].ctypes.data_as(_lib._PD)
+            equil = np.zeros((D, n_ckpt, 2, T), dtype=np.float64)
+            res.per_sample_equil = equil.ctypes.data_as(_lib._PD)
+
         cb = _lib.ON_SWEEP(lambda _user, sweep: on_sweep(int(sweep))) if on_sweep is not None else None
         flag_ptr = None
         if interrupt is not None:  # an int32 numpy scalar array the caller may set to non-zero
@@ -199,6 +211,7 @@ class IsingSimulation:
         self.last_sweep_kernel_launches = int(res.sweep_kernel_launches)
         self.last_per_sample_means = means
         self.last_per_sample_taus = taus
+        self.last_per_sample_equil = equil
         if R >= 2:
             out["overlap_histogram"] = [hist[t].copy() for t in range(T)]  # list of u64[N+1], src/lib.rs:358-366
         if pt is not None:

@@ -73,6 +73,7 @@ class Results(C.Structure):
         + [("per_sample_means", _PD), ("sweep_loop_ms", C.c_double), ("kernel_launches", C.c_int64),
            ("sweep_kernel_ms", C.c_double), ("sweep_kernel_launches", C.c_int64)]
         + [("mags2_tau", _PD), ("overlap2_tau", _PD), ("per_sample_taus", _PD)]
+        + [("equil_energy_avg", _PD), ("equil_link_overlap_avg", _PD), ("per_sample_equil", _PD)]
     )
 
 
@@ -82,6 +83,7 @@ ON_SWEEP = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64)
 SIGNATURES = {
     "pp_last_error": (C.c_char_p, []),
     "pp_abi_version": (C.c_int32, []),
+    "pp_equil_checkpoints": (C.c_int32, [C.c_int64, C.POINTER(C.c_int64)]),
     "pp_colouring": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pp_metropolis_lookup": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pp_realization_seed": (C.c_uint64, [C.c_uint64, C.c_uint64]),

@@ -96,6 +96,21 @@ extern "C" pp_status pp_metropolis_lookup(const float *temperatures, int32_t n_t
 
 extern "C" uint64_t pp_realization_seed(uint64_t root, uint64_t r) { return realization_seed(root, r); }
 
+extern "C" int32_t pp_equil_checkpoints(int64_t n_sweeps, int64_t *out) {  // equilibration.rs:18-29
+    int32_t n = 0;
+    int64_t last = -1;
+    for (int64_t p = 128; p < n_sweeps; p *= 2) {
+        if (out) out[n] = p;
+        last = p;
+        n++;
+    }
+    if (last != n_sweeps) {
+        if (out) out[n] = n_sweeps;
+        n++;
+    }
+    return n;
+}
+
 extern "C" pp_status pp_colouring(int32_t n_dims, const int64_t *shape, int32_t n_offsets, const int64_t *offsets,
                                   uint16_t *colour_out, int32_t *n_colours_out) {
     if (!shape) return fail(PP_ERR_INVALID, "shape is NULL");
@@ -1250,8 +1265,6 @@ static pp_status validate_cfg(const pp_sample_cfg *c) {
         return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep path");
     if (c->autocorrelation_max_lag < 0) return fail(PP_ERR_INVALID, "autocorrelation_max_lag must be >= 1");
     if (c->snapshot_interval != 0) return fail(PP_ERR_UNSUPPORTED, "snapshot_interval is not implemented on the GPU sweep path");
-    if (c->equilibration_diagnostic != 0)
-        return fail(PP_ERR_UNSUPPORTED, "equilibration_diagnostic is not implemented on the GPU sweep path");
     return PP_OK;
 }
 
@@ -1339,6 +1352,20 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         }
         CUDA_TRY(pool_alloc(s, (void **)&d_tau, sizeof(double) * ndt * 2));
     }
+    // equilibration diagnostic (mod.rs:373-383): running sums per (realization, temperature) + checkpoint snapshots
+    const bool want_eq = cfg->equilibration_diagnostic != 0;
+    std::vector<int64_t> ckpts;
+    double *d_eq_sum = nullptr, *d_eq_snap = nullptr;
+    if (want_eq) {
+        if (s->layout == PP_LAYOUT_SLAB) { free_ac(); return fail(PP_ERR_UNSUPPORTED, "equilibration_diagnostic is not implemented for the slab layout"); }
+        ckpts.resize(80);
+        ckpts.resize((size_t)pp_equil_checkpoints(cfg->n_sweeps, ckpts.data()));
+        const size_t ndt = (size_t)m.D * m.T;
+        CUDA_TRY(pool_alloc(s, (void **)&d_eq_sum, sizeof(double) * ndt * 2));
+        CUDA_TRY(pool_alloc(s, (void **)&d_eq_snap, sizeof(double) * ndt * 2 * ckpts.size()));
+        CUDA_TRY(cudaMemsetAsync(d_eq_sum, 0, sizeof(double) * ndt * 2, s->stream));
+        CUDA_TRY(cudaMemsetAsync(d_eq_snap, 0, sizeof(double) * ndt * 2 * ckpts.size(), s->stream));
+    }
     const int64_t launches0 = s->launches;
     s->profile = cfg->profile != 0;
     s->prof_used = 0;
@@ -1385,7 +1412,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     std::vector<Step> steps;
     int64_t sweep_id = 0;
     // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel, up to 256 sweeps per launch
-    if (s->rows && s->resident && !s->profile && !want_ac) {
+    if (s->rows && s->resident && !s->profile && !want_ac && !want_eq) {
         Ctx &c = chunks[0];
         RowsView v = s->rv;
         v.keys = s->d_keys;
@@ -1439,6 +1466,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             commit_ctx(s, chunks[0]);
             cudaDeviceSynchronize();
             free_ac();
+            pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
             return fail(PP_ERR_INTERRUPTED, "interrupted");
         }
         // the sequence of kernel steps of this macro batch (mod.rs:405-432, 486-509, 748-796), identical for every chunk
@@ -1454,7 +1482,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     const int64_t last = sid + batch - 1;
                     const bool rec = last >= cfg->warmup_sweeps;
                     const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
-                    if (rec || ptl || batch >= s->max_batch) break;
+                    if (rec || ptl || want_eq || batch >= s->max_batch) break;
                     batch++;
                 }
             }
@@ -1480,13 +1508,27 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         for (Ctx &c : chunks) {
             for (const Step &stp : steps) {
                 bool fused = false;
-                st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, stp.record || stp.pt_this,
-                                   stp.record, stp.record, stp.record, &fused);
+                st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, stp.record || stp.pt_this || want_eq,
+                                   stp.record, stp.record || want_eq, stp.record, &fused);
                 if (st != PP_OK) return st;
-                if (stp.record && !fused) {
-                    st = launch_overlap(s, c);                                         // mod.rs:527-529
-                    if (st != PP_OK) return st;
-                    fold_kernel<<<blocks_for(c.m.D * c.m.T, 128), 128, 0, c.stream>>>(c.m, c.st, c.m.P > 0);  // mod.rs:543-578
+                if ((stp.record || want_eq) && !fused) {
+                    if (c.m.P > 0 || stp.record) {
+                        st = launch_overlap(s, c);                                     // mod.rs:527-529
+                        if (st != PP_OK) return st;
+                    }
+                    if (stp.record) {
+                        fold_kernel<<<blocks_for(c.m.D * c.m.T, 128), 128, 0, c.stream>>>(c.m, c.st, c.m.P > 0);  // mod.rs:543-578
+                        s->launches++;
+                    }
+                }
+                if (want_eq) {                                                         // mod.rs:511-541 (pre-exchange system_ids)
+                    const int64_t d0 = c.m.sample_offset - s->mv.sample_offset, count_after = stp.sid_last + 1;
+                    int ck = -1;
+                    for (size_t i = 0; i < ckpts.size(); i++)
+                        if (ckpts[i] == count_after) ck = (int)i;
+                    equil_push_kernel<<<blocks_for(c.m.D * c.m.T, 128), 128, 0, c.stream>>>(
+                        c.m, c.dot_link, d_eq_sum + d0 * c.m.T, d_eq_sum + (size_t)m.D * m.T + d0 * c.m.T, (long long)count_after, ck,
+                        (int)ckpts.size(), d_eq_snap + (size_t)d0 * ckpts.size() * 2 * c.m.T);
                     s->launches++;
                 }
                 if (stp.record && want_ac) {                                           // mod.rs:580-594 (pre-exchange system_ids)
@@ -1550,6 +1592,12 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemcpy(taus.data(), d_tau, sizeof(double) * (size_t)ndt * (ac_q.ring ? 2 : 1), cudaMemcpyDeviceToHost));
         free_ac();
     }
+    std::vector<double> eq_snap;  // [D][n_ckpt][2][T]
+    if (want_eq) {
+        eq_snap.assign((size_t)m.D * ckpts.size() * 2 * m.T, 0.0);
+        CUDA_TRY(cudaMemcpy(eq_snap.data(), d_eq_snap, sizeof(double) * eq_snap.size(), cudaMemcpyDeviceToHost));
+        pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
+    }
     if (!out) return PP_OK;
     out->sweep_loop_ms = ms;
     out->kernel_launches = s->launches - launches0;
@@ -1575,6 +1623,20 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             for (int64_t d = 0; d < m.D; d++) acc += sums[((size_t)d * 11 + k) * T + t];
             dst[k][t] = acc / (double)m.D;
         }
+    }
+    if (want_eq) {  // results.rs:231-247, 275-282
+        double *edst[2] = {out->equil_energy_avg, out->equil_link_overlap_avg};
+        const size_t nck = ckpts.size();
+        for (int k = 0; k < 2; k++) {
+            if (!edst[k]) continue;
+            for (size_t cidx = 0; cidx < nck; cidx++)
+                for (int t = 0; t < T; t++) {
+                    double acc = 0.0;
+                    for (int64_t d = 0; d < m.D; d++) acc += eq_snap[(((size_t)d * nck + cidx) * 2 + k) * T + t];
+                    edst[k][cidx * T + t] = acc / (double)m.D;
+                }
+        }
+        if (out->per_sample_equil) memcpy(out->per_sample_equil, eq_snap.data(), sizeof(double) * eq_snap.size());
     }
     if (want_ac) {  // results.rs:217-231, 269-274: sum over realizations in order, divide by their number
         double *tdst[2] = {out->mags2_tau, m.P > 0 ? out->overlap2_tau : nullptr};

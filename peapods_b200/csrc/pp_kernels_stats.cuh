@@ -224,6 +224,35 @@ __global__ void autocorr_tau_kernel(int64_t n_dt, AutocorrView a, long long n_re
     tau_out[dt] = tau;
 }
 
+// Equilibration diagnostic (statistics/equilibration.rs; simulation/mod.rs:511-541): after EVERY sweep, thread (d, t) adds the
+// replica-mean energy and the pair-mean link overlap at slot t (f32 means, f64 running sums) and, at a checkpoint, stores
+// the running averages: snap[(d * n_ckpt + ckpt) * 2 * T + {0, 1} * T + t].
+__global__ void equil_push_kernel(ModelView m, const long long *dot_link, double *sum_e, double *sum_ql, long long count_after,
+                                  int ckpt, int n_ckpt, double *snap) {
+    const int64_t dt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (dt >= m.D * m.T) return;
+    const int64_t d = dt / m.T;
+    const int t = (int)(dt % m.T);
+    float e = 0.0f;
+    for (int r = 0; r < m.R; r++) e = __fadd_rn(e, m.energies[d * m.S + m.system_ids[d * m.S + r * m.T + t]]);
+    e = __fmul_rn(e, __fdiv_rn(1.0f, (float)m.R));
+    float ql = 0.0f;
+    if (m.P > 0) {
+        const float nb = (float)(m.N * m.z);
+        for (int p = 0; p < m.P; p++) ql = __fadd_rn(ql, __fdiv_rn((float)dot_link[(d * m.P + p) * m.T + t], nb));
+        ql = __fmul_rn(ql, __fdiv_rn(1.0f, (float)m.P));
+    }
+    const double se = __dadd_rn(sum_e[dt], (double)e), sq = __dadd_rn(sum_ql[dt], (double)ql);
+    sum_e[dt] = se;
+    sum_ql[dt] = sq;
+    if (ckpt >= 0) {
+        const double c = (double)count_after;
+        double *o = snap + ((size_t)d * n_ckpt + ckpt) * 2 * m.T;
+        o[t] = __ddiv_rn(se, c);
+        o[m.T + t] = __ddiv_rn(sq, c);
+    }
+}
+
 // realization.rs:109-120
 __device__ __forceinline__ void pt_record_arrival(const PtView &pt, int64_t base, int system, int slot) {
     if (slot == pt.hot_slot) {

@@ -67,6 +67,14 @@ def merge_results(parts):
             for d in range(D):
                 acc += taus[d, k]
             out[name] = acc / float(D)
+    if all(p.get("per_sample_equil") is not None for p in parts) and "equil_sweeps" in first:  # results.rs:231-247, 275-282
+        eq = np.concatenate([p["per_sample_equil"] for p in parts], axis=0)  # [D, n_ckpt, 2, T]
+        out["equil_sweeps"] = first["equil_sweeps"]
+        for k, name in enumerate(("equil_energy_avg", "equil_link_overlap_avg")):
+            acc = np.zeros(eq.shape[1:2] + (T,), dtype=np.float64)
+            for d in range(D):
+                acc += eq[d, :, k]
+            out[name] = acc / float(D)
     if "per_disorder" in first:
         pt = {}
         for name in ("edge_attempts", "edge_acceptances", "round_trips"):
@@ -75,13 +83,14 @@ def merge_results(parts):
     return out
 
 
-def gather_merge(result, per_sample_means, n_replicas, group=None, dst=0, per_sample_taus=None):
+def gather_merge(result, per_sample_means, n_replicas, group=None, dst=0, per_sample_taus=None, per_sample_equil=None):
     """Collective: gather every rank's part on ``dst`` and merge (returns None elsewhere).  Uses the object
     collectives of ``torch.distributed`` (a few MB of scalars; works on the NCCL and the gloo backend)."""
     import torch.distributed as dist
 
     part = {"result": result, "per_sample_means": np.asarray(per_sample_means), "n_replicas": int(n_replicas),
-            "per_sample_taus": None if per_sample_taus is None else np.asarray(per_sample_taus)}
+            "per_sample_taus": None if per_sample_taus is None else np.asarray(per_sample_taus),
+            "per_sample_equil": None if per_sample_equil is None else np.asarray(per_sample_equil)}
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merge_results([part])
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -116,7 +125,8 @@ class ShardedIsingSimulation:
         """Every rank samples its block; rank 0 returns the merged dict, the others None."""
         local = self.sim.sample(*args, **kwargs)
         return gather_merge(local, self.sim.last_per_sample_means, self.n_replicas,
-                            per_sample_taus=getattr(self.sim, "last_per_sample_taus", None))
+                            per_sample_taus=getattr(self.sim, "last_per_sample_taus", None),
+                            per_sample_equil=getattr(self.sim, "last_per_sample_equil", None))
 
 
 def slab_plan(extent0: int, world: int, rank: int):

@@ -140,8 +140,19 @@ class Ising:
             self.mags2_tau = result["mags2_tau"]
         if "overlap2_tau" in result:
             self.overlap2_tau = result["overlap2_tau"]
+        if "equil_sweeps" in result:  # spin_models.py:316-319
+            self._equil_sweeps = result["equil_sweeps"]
+            self._equil_energy_avg = result["equil_energy_avg"]
+            self._equil_link_overlap_avg = result["equil_link_overlap_avg"]
         self.per_disorder = result.get("per_disorder", {})
         return result
+
+    def equilibration_delta(self, j_squared=1.0):
+        """Delta(t) = e(t) - J^2 beta z (1 - q_l(t)) at the checkpoints (spin_models.py:322-341; sign convention
+        e = +sum J s s / N).  Returns (sweeps [n_ckpt], delta [n_ckpt, n_temps])."""
+        beta = 1.0 / self.temperatures
+        delta = self._equil_energy_avg - j_squared * beta * self.n_neighbors * (1 - self._equil_link_overlap_avg)
+        return self._equil_sweeps, delta
 
     def get_energies(self):
         """Mean energy per temperature of the last run (sign: e = +sum J s s / N, spin_models.py:343-344)."""

@@ -1,6 +1,6 @@
 """T1: the reference's interface tests (/root/reference/tests/test_sampling_interfaces.py) for the parts that touch the
 sweep path, run against `peapods_b200.Ising` — same constructor / sample keywords, result keys, shapes, dtypes, counters
-and error ordering.  Cases that exercise cluster moves, the equilibration diagnostic or the CLI are outside the path:
+and error ordering.  Cases that exercise cluster moves or the CLI are outside the path:
 here they must fail BEFORE any state mutation, as the reference orders its own validation."""
 import numpy as np
 import pytest
@@ -117,7 +117,6 @@ def test_invalid_autocorrelation_backend_fails_before_sampling():  # :197-206
 @pytest.mark.parametrize("kwargs", [
     dict(cluster_update_interval=1),                                   # Swendsen-Wang / Wolff
     dict(overlap_cluster_update_interval=1),                           # Houdayer / Jorg / CMR
-    dict(equilibration_diagnostic=True),
 ])
 def test_options_outside_the_sweep_path_are_rejected_before_mutation(kwargs):
     from peapods_b200 import Ising

@@ -469,3 +469,34 @@ def test_autocorrelation_taus_are_bit_exact(oracle, layout, shape, kind, offsets
         assert_results_equal(rg, rc)
         assert ("overlap2_tau" in rg) == (R >= 2) and "mags2_tau" in rg
         assert np.array_equal(gpu.last_per_sample_taus[:, : (2 if R >= 2 else 1)], cpu.last_per_sample_taus[:, : (2 if R >= 2 else 1)])
+
+
+# ---- equilibration diagnostic (statistics/equilibration.rs driven from simulation/mod.rs:511-541) ----
+@pytest.mark.parametrize("layout,shape,kind,offsets,temps,R,D", [
+    ("int8", (8, 8), "bimodal", None, [1.0, 1.8, 2.6], 2, 2),
+    ("int8", (6, 6), "bimodal", TRI, [1.0, 2.5], 3, 1),                 # table-driven kernels, unpaired replica
+    ("int8", (8, 8), "ferro", None, [2.0, 2.6], 1, 1),                  # one replica: link-overlap rows stay zero
+    ("msc", (8, 8, 8), "bimodal", None, np.linspace(0.8, 1.6, 3), 2, 40),
+    ("msc", (16, 16, 16), "bimodal", None, [0.9, 1.3], 4, 33),          # msc3d: overlap dots without the fold during warm-up
+])
+def test_equilibration_diagnostic_is_bit_exact(oracle, layout, shape, kind, offsets, temps, R, D):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets, layout=layout)
+    for n_sweeps, interval in ((300, 3), (128, None), (20, 1)):  # checkpoints 128, 256, 300 / 128 / 20
+        rg = gpu.sample(n_sweeps, "metropolis", pt_interval=interval, equilibration_diagnostic=True, autocorrelation_max_lag=3)
+        rc = cpu.sample(n_sweeps, "metropolis", pt_interval=interval, equilibration_diagnostic=True, autocorrelation_max_lag=3)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        assert rg["equil_sweeps"].dtype == np.uint64 and rg["equil_energy_avg"].shape == (len(rg["equil_sweeps"]), len(temps))
+        assert np.array_equal(gpu.last_per_sample_equil, cpu.last_per_sample_equil)
+
+
+def test_equilibration_delta_matches_the_reference_formula():
+    """spin_models.py:322-341 on a synthetic result (no sampling needed beyond the keys)."""
+    from peapods_b200 import Ising
+
+    model = Ising((4, 4), couplings="bimodal", temperatures=np.array([1.0, 2.0]), n_replicas=2, seed=9)
+    model.sample(130, equilibration_diagnostic=True)
+    sweeps, delta = model.equilibration_delta()
+    assert list(sweeps) == [128, 130]
+    expect = model._equil_energy_avg - (1.0 / model.temperatures) * 2 * (1 - model._equil_link_overlap_avg)
+    assert np.array_equal(delta, expect)
