@@ -82,6 +82,8 @@ typedef struct {
                                       slab_ranks > 1 and slab_rank >= 0 */
 } pp_model_desc;
 
+enum { PP_CLUSTER_SW = 0, PP_CLUSTER_WOLFF = 1 };  /* config.rs ClusterMode */
+
 /* sample() arguments (src/lib.rs:176-284). Zero means "None" for the optional intervals. */
 typedef struct {
     int64_t n_sweeps;
@@ -89,9 +91,11 @@ typedef struct {
     int32_t sweep_mode;                      /* PP_SWEEP_* */
     int64_t pt_interval;                     /* 0 = None */
     int32_t pt_schedule;                     /* PP_PT_* */
+    /* 0 = None; > 0: Fortuin-Kasteleyn cluster update (clusters/fk.rs, action "update") of every system after each
+     * cluster_update_interval-th sweep (simulation/mod.rs:434-470); int8 layouts with unit couplings, else PP_ERR_UNSUPPORTED */
+    int64_t cluster_update_interval;
     /* options of the reference that this path does not implement: must be 0, else
      * PP_ERR_UNSUPPORTED is returned before any state mutation */
-    int64_t cluster_update_interval;
     int64_t overlap_cluster_update_interval;
     /* 0 = None; > 0: integrated autocorrelation times of m^2 and q^2 over the recorded sweeps (statistics/autocorrelation.rs,
      * ring backend; the lag is clamped to [1, recorded sweeps / 4] as simulation/mod.rs:342-344) */
@@ -106,6 +110,7 @@ typedef struct {
     /* 1: bracket every sweep-kernel launch with CUDA events on the launch stream and report the summed
      * duration in pp_results.sweep_kernel_ms (measurement hook for the roofline figure) */
     int32_t profile;
+    int32_t cluster_mode;                    /* PP_CLUSTER_SW (0) or PP_CLUSTER_WOLFF (1); used when cluster_update_interval > 0 */
 } pp_sample_cfg;
 
 /* Result buffers; every pointer may be NULL (that output is skipped).

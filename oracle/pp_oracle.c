@@ -642,6 +642,48 @@ const float *orc_sim_energies(const orc_sim *sim, int64_t r) { return sim->reals
 /* ======================================================================
  * Sweep loop for one realization  (simulation/mod.rs:177-863, hot-path lines only)
  * ====================================================================== */
+/* ---- clusters/fk.rs:28-171 (union-find path), RNG-SPEC draws ------------------------------------ */
+uint32_t orc_fk_bond_count(float temperature) {
+    float p = 1.0f - expf(-2.0f * 1.0f / temperature); /* fk.rs:113 with interaction = 1 */
+    if (!(p > 0.0f)) return 0;
+    double c = ceil((double)p * 16777216.0);             /* u = draw * 2^-24 is exact: u < p <=> draw < ceil(p * 2^24) */
+    if (c > 16777216.0) c = 16777216.0;
+    return (uint32_t)c;
+}
+static int64_t uf_find(int64_t *parent, int64_t i) {
+    while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; }
+    return i;
+}
+void orc_fk_update(const orc_lattice *lat, int8_t *spins, const float *couplings, float temperature, uint64_t key,
+                   uint32_t sweep_index, uint32_t system_id, int wolff) {
+    int64_t N = lat->n_spins;
+    int z = lat->n_neighbors;
+    uint32_t count = orc_fk_bond_count(temperature);
+    int64_t *parent = malloc(sizeof(int64_t) * (size_t)N);
+    for (int64_t i = 0; i < N; i++) parent[i] = i;
+    for (int64_t i = 0; i < N; i++)
+        for (int d = 0; d < z; d++) { /* fk.rs:107-115: forward bonds, each once */
+            int64_t j = lat->fwd[i * z + d];
+            float inter = (float)spins[i] * (float)spins[j] * couplings[i * z + d];
+            if (inter <= 0.0f) continue;
+            if (orc_draw24(key, (uint32_t)(i * z + d), sweep_index, system_id, ORC_TAG_FK_BOND) >= count) continue;
+            int64_t a = uf_find(parent, i), b = uf_find(parent, j);
+            if (a < b) parent[b] = a; else if (b < a) parent[a] = b; /* the smallest site labels the cluster */
+        }
+    for (int64_t i = 0; i < N; i++) parent[i] = uf_find(parent, i);
+    if (wolff) { /* fk.rs:151-158 */
+        uint32_t ctr[4] = {0xFFFFFFFFu, sweep_index, system_id, ORC_TAG_FK_FLIP}, k[2] = {(uint32_t)key, (uint32_t)(key >> 32)}, o[4];
+        orc_philox4x32_10(ctr, k, o);
+        int64_t seed = (int64_t)(((uint64_t)o[1] * (uint64_t)N) >> 32);
+        int64_t root = parent[seed];
+        for (int64_t i = 0; i < N; i++) if (parent[i] == root) spins[i] = (int8_t)-spins[i];
+    } else { /* fk.rs:159-170: one fair draw per cluster */
+        for (int64_t i = 0; i < N; i++)
+            if (orc_draw24(key, (uint32_t)parent[i], sweep_index, system_id, ORC_TAG_FK_FLIP) < (1u << 23)) spins[i] = (int8_t)-spins[i];
+    }
+    free(parent);
+}
+
 /* ---- statistics/autocorrelation.rs: ring backend ------------------------------------------------ */
 typedef struct {
     int max_lag, n_temps, ring_len, ring_pos;
@@ -820,6 +862,14 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
             sweep_philox_impl(lat, re->spins, re->couplings, re->temperatures, re->system_ids, S, sim->colour,
                               sim->order, sim->rank, sweep_key, sweep_index, cfg->sweep_mode, table, msc);
         }
+
+        /* mod.rs:434-470: FK cluster update of every slot's system, after the sweep, before the measurements */
+        if (cfg->cluster_interval > 0 && sweep_id % cfg->cluster_interval == 0)
+            for (int slot = 0; slot < S; slot++) {
+                int64_t sys = re->system_ids[slot];
+                orc_fk_update(lat, re->spins + sys * N, re->couplings, re->temperatures[slot], re->base_seed, sweep_index,
+                              (uint32_t)sys, cfg->cluster_wolff);
+            }
 
         int pt_this_sweep = cfg->pt_interval > 0 && sweep_id % cfg->pt_interval == 0; /* mod.rs:486-488 */
 
@@ -1007,12 +1057,17 @@ static int validate(const orc_config *cfg) {
     if (cfg->n_sweeps < 1) { set_err("n_sweeps must be >= 1"); return -1; }
     if (cfg->warmup_sweeps > cfg->n_sweeps) { set_err("warmup_sweeps must be <= n_sweeps"); return -1; }
     if (cfg->pt_interval < 0) { set_err("pt_interval must be >= 1"); return -1; }
+    if (cfg->cluster_interval < 0) { set_err("cluster_update_interval must be >= 1"); return -1; }
     return 0;
 }
 
 /* simulation/mod.rs:865-939 + statistics/results.rs:165-180, 250-259 + statistics/overlap.rs:106-152 */
 int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
     if (validate(cfg) != 0) return -1;
+    if (cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX) {
+        set_err("cluster updates are restated for the int8 RNG-SPEC mode only");
+        return -1;
+    }
     int T = sim->n_temps, R = sim->n_replicas;
     int64_t N = sim->lat->n_spins, bins = N + 1, D = sim->n_real;
     int n_pairs = R / 2;

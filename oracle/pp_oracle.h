@@ -52,6 +52,8 @@ enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
 #define ORC_TAG_SWEEP     0x00020000u
 #define ORC_TAG_PT        0x00030000u
 #define ORC_TAG_SWEEP_MSC 0x00040000u
+#define ORC_TAG_FK_BOND   0x00050000u  /* counter = {bond >> 2, sweep index, system id, tag}; bond = site * z' + direction */
+#define ORC_TAG_FK_FLIP   0x00060000u  /* counter = {root >> 2 | 0xFFFFFFFF (Wolff seed), sweep index, system id, tag} */
 #define ORC_MSC_KEY_DOMAIN 0x6D73635F67726F75ull
 
 typedef struct orc_lattice orc_lattice;
@@ -66,6 +68,8 @@ typedef struct {
     int32_t n_threads;    /* threads over realizations (<=1: sequential) */
     int32_t force_log_form; /* 1: never use the +-J lookup (test of LUT == log form) */
     int64_t autocorr_max_lag; /* 0 = off; simulation/mod.rs:342-344: clamped to [1, recorded sweeps / 4] */
+    int64_t cluster_interval; /* 0 = off; Fortuin-Kasteleyn cluster update every this many sweeps (simulation/mod.rs:434-470) */
+    int32_t cluster_wolff;    /* 0: Swendsen-Wang (every cluster flips with probability 1/2); 1: Wolff (the seed's cluster flips) */
     int32_t equil_diag;       /* 1: equilibration diagnostic (statistics/equilibration.rs; energies + link overlaps every sweep) */
 } orc_config;
 
@@ -158,6 +162,15 @@ void orc_pt_replay(int n_replicas, int n_temps, const float *temps, int n_attemp
 void orc_autocorr_gamma(const double *values, int64_t n_samples, int n_temps, int max_lag, double *gamma_out);
 /* sokal_tau (:201-210) over gamma[0..n) */
 double orc_sokal_tau(const double *gamma, int n);
+
+/* ---- Fortuin-Kasteleyn cluster update (clusters/fk.rs:28-171, union-find path) under RNG-SPEC draws ---- */
+/* #{draw in [0, 2^24) : draw * 2^-24 < 1 - expf(-2 / T)}: the bond probability of an aligned unit-coupling pair (fk.rs:108-114) */
+uint32_t orc_fk_bond_count(float temperature);
+/* one system: bonds between aligned neighbours with s_i s_j J > 0 are activated by their own draw, clusters are the connected
+ * components (labelled by their smallest site), then SW flips each cluster whose root draw is < 1/2, Wolff flips the cluster of
+ * the drawn seed site.  Unit couplings (|J| in {0, 1}) only. */
+void orc_fk_update(const orc_lattice *lat, int8_t *spins, const float *couplings, float temperature, uint64_t key,
+                   uint32_t sweep_index, uint32_t system_id, int wolff);
 
 /* statistics/equilibration.rs:18-29: 128, 256, ... < n_sweeps, then n_sweeps.  Returns the count (out may be NULL). */
 int orc_equil_checkpoints(int64_t n_sweeps, int64_t *out);

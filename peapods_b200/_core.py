@@ -119,6 +119,10 @@ class IsingSimulation:
                 raise ValueError(f"unknown cluster action '{action}', expected 'update' or 'observe'")
             if action == "observe" and mode == "wolff":  # config.rs:191-195
                 raise ValueError("cluster_action='observe' requires cluster_mode='sw'")
+            if action == "observe":
+                raise ValueError("cluster_action='observe' is not implemented on the GPU sweep path")
+        if collect_cluster_stats:
+            raise ValueError("collect_cluster_stats is not implemented on the GPU sweep path")
         if pt_interval is not None and int(pt_interval) == 0:  # config.rs:197-199
             raise ValueError("pt_interval must be >= 1")
         if backend == "fft" and autocorrelation_max_lag is None:  # config.rs:200-206
@@ -136,6 +140,7 @@ class IsingSimulation:
         cfg.autocorrelation_max_lag = 0 if autocorrelation_max_lag is None else max(int(autocorrelation_max_lag), 1)
         cfg.snapshot_interval = 0 if snapshot_interval is None else max(int(snapshot_interval), 1)
         cfg.equilibration_diagnostic = int(bool(equilibration_diagnostic))
+        cfg.cluster_mode = 1 if (cluster_update_interval is not None and cluster_mode == "wolff") else 0
         cfg.exact_log = int(bool(exact_log))
         cfg.profile = int(bool(profile))
 

@@ -57,6 +57,7 @@ class SampleCfg(C.Structure):
         ("equilibration_diagnostic", C.c_int32),
         ("exact_log", C.c_int32),
         ("profile", C.c_int32),
+        ("cluster_mode", C.c_int32),
     ]
 
 

@@ -20,6 +20,7 @@
 
 #include "../../include/peapods_b200.h"
 #include "pp_device.cuh"
+#include "pp_kernels_fk.cuh"
 #include "pp_kernels_int8.cuh"
 #include "pp_kernels_msc.cuh"
 #include "pp_kernels_msc3d.cuh"
@@ -1259,8 +1260,9 @@ static pp_status validate_cfg(const pp_sample_cfg *c) {
         return fail(PP_ERR_INVALID, "unknown sweep_mode, expected 'metropolis' or 'gibbs'");
     if (c->pt_schedule != PP_PT_SINGLE_RANDOM_EDGE && c->pt_schedule != PP_PT_FULL_LADDER)
         return fail(PP_ERR_INVALID, "unknown pt_schedule, expected 'single_random_edge' or 'full_ladder'");
-    if (c->cluster_update_interval != 0)
-        return fail(PP_ERR_UNSUPPORTED, "cluster updates (cluster_update_interval) are not implemented on the GPU sweep path");
+    if (c->cluster_update_interval < 0) return fail(PP_ERR_INVALID, "cluster_update_interval must be >= 1");
+    if (c->cluster_mode != PP_CLUSTER_SW && c->cluster_mode != PP_CLUSTER_WOLFF)
+        return fail(PP_ERR_INVALID, "unknown cluster_mode, expected 'wolff' or 'sw'");
     if (c->overlap_cluster_update_interval != 0)
         return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep path");
     if (c->autocorrelation_max_lag < 0) return fail(PP_ERR_INVALID, "autocorrelation_max_lag must be >= 1");
@@ -1366,6 +1368,38 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemsetAsync(d_eq_sum, 0, sizeof(double) * ndt * 2, s->stream));
         CUDA_TRY(cudaMemsetAsync(d_eq_snap, 0, sizeof(double) * ndt * 2 * ckpts.size(), s->stream));
     }
+    // Fortuin-Kasteleyn cluster updates (mod.rs:434-470): int8 layouts with unit couplings
+    const bool want_fk = cfg->cluster_update_interval > 0;
+    uint32_t *d_fk_count = nullptr, *d_fk_lab = nullptr;
+    uint8_t *d_fk_bm = nullptr;
+    int64_t fk_smem_sites = 0;
+    size_t fk_smem = 0;
+    auto free_fk = [&]() { pool_free(s, d_fk_count); pool_free(s, d_fk_lab); pool_free(s, d_fk_bm); };
+    if (want_fk) {
+        if (s->layout != PP_LAYOUT_INT8 || m.coupling_class == COUP_F32) {
+            free_ac();
+            pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
+            return fail(PP_ERR_UNSUPPORTED, "cluster updates (cluster_update_interval) are not implemented on the GPU sweep path for "
+                                            "this handle: they need the int8 layout and couplings in {-1, 0, +1}");
+        }
+        std::vector<uint32_t> counts((size_t)m.T);
+        for (int t = 0; t < m.T; t++) {  // fk.rs:113 with interaction = 1: u < 1 - exp(-2 / T) on the 24-bit grid
+            const float p = 1.0f - expf(-2.0f * 1.0f / s->temps[(size_t)t]);
+            double cnt = p > 0.0f ? std::ceil((double)p * 16777216.0) : 0.0;
+            counts[(size_t)t] = (uint32_t)std::min(cnt, 16777216.0);
+        }
+        CUDA_TRY(pool_alloc(s, (void **)&d_fk_count, sizeof(uint32_t) * counts.size()));
+        CUDA_TRY(cudaMemcpyAsync(d_fk_count, counts.data(), sizeof(uint32_t) * counts.size(), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if ((size_t)m.N * 5 <= 200 * 1024) {  // labels (u32) + bond masks (u8) in shared memory
+            fk_smem_sites = m.N;
+            fk_smem = (size_t)m.N * 5 + 16;
+            CUDA_TRY(cudaFuncSetAttribute(fk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
+        } else {
+            CUDA_TRY(pool_alloc(s, (void **)&d_fk_lab, sizeof(uint32_t) * (size_t)(m.D * m.S * m.N)));
+            CUDA_TRY(pool_alloc(s, (void **)&d_fk_bm, (size_t)(m.D * m.S * m.N)));
+        }
+    }
     const int64_t launches0 = s->launches;
     s->profile = cfg->profile != 0;
     s->prof_used = 0;
@@ -1412,7 +1446,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     std::vector<Step> steps;
     int64_t sweep_id = 0;
     // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel, up to 256 sweeps per launch
-    if (s->rows && s->resident && !s->profile && !want_ac && !want_eq) {
+    if (s->rows && s->resident && !s->profile && !want_ac && !want_eq && !want_fk) {
         Ctx &c = chunks[0];
         RowsView v = s->rv;
         v.keys = s->d_keys;
@@ -1466,6 +1500,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             commit_ctx(s, chunks[0]);
             cudaDeviceSynchronize();
             free_ac();
+            free_fk();
             pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
             return fail(PP_ERR_INTERRUPTED, "interrupted");
         }
@@ -1508,9 +1543,22 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         for (Ctx &c : chunks) {
             for (const Step &stp : steps) {
                 bool fused = false;
-                st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, stp.record || stp.pt_this || want_eq,
+                const bool fk_this = want_fk && stp.sid_last % cfg->cluster_update_interval == 0;  // mod.rs:434-437
+                const bool energy_this = stp.record || stp.pt_this || want_eq;
+                st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, energy_this && !fk_this,
                                    stp.record, stp.record || want_eq, stp.record, &fused);
                 if (st != PP_OK) return st;
+                if (fk_this) {  // after the sweep, before the measurements (mod.rs:457-470)
+                    fk_cluster_kernel<<<(unsigned)(c.m.D * c.m.S), FK_THREADS, fk_smem, c.stream>>>(
+                        c.m, d_fk_count, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0,
+                        fk_smem_sites, d_fk_lab, d_fk_bm);
+                    s->launches++;
+                    CUDA_TRY(cudaGetLastError());
+                    if (energy_this) {
+                        st = launch_energy(s, c, stp.record);
+                        if (st != PP_OK) return st;
+                    }
+                }
                 if ((stp.record || want_eq) && !fused) {
                     if (c.m.P > 0 || stp.record) {
                         st = launch_overlap(s, c);                                     // mod.rs:527-529
@@ -1592,6 +1640,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemcpy(taus.data(), d_tau, sizeof(double) * (size_t)ndt * (ac_q.ring ? 2 : 1), cudaMemcpyDeviceToHost));
         free_ac();
     }
+    if (want_fk) free_fk();
     std::vector<double> eq_snap;  // [D][n_ckpt][2][T]
     if (want_eq) {
         eq_snap.assign((size_t)m.D * ckpts.size() * 2 * m.T, 0.0);

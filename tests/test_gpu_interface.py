@@ -115,7 +115,8 @@ def test_invalid_autocorrelation_backend_fails_before_sampling():  # :197-206
 
 
 @pytest.mark.parametrize("kwargs", [
-    dict(cluster_update_interval=1),                                   # Swendsen-Wang / Wolff
+    dict(cluster_update_interval=1, cluster_action="observe"),         # FK graph observation (cluster moves themselves run)
+    dict(cluster_update_interval=1, collect_cluster_stats=True),
     dict(overlap_cluster_update_interval=1),                           # Houdayer / Jorg / CMR
 ])
 def test_options_outside_the_sweep_path_are_rejected_before_mutation(kwargs):

@@ -500,3 +500,36 @@ def test_equilibration_delta_matches_the_reference_formula():
     assert list(sweeps) == [128, 130]
     expect = model._equil_energy_avg - (1.0 / model.temperatures) * 2 * (1 - model._equil_link_overlap_avg)
     assert np.array_equal(delta, expect)
+
+
+# ---- Fortuin-Kasteleyn cluster updates (clusters/fk.rs:28-171 driven from simulation/mod.rs:434-470).  Bond and
+# cluster draws are counter-based and clusters are named by their smallest site, so label propagation on the GPU and union-find
+# in the oracle must produce the same configurations ----
+@pytest.mark.parametrize("cluster_mode", ["sw", "wolff"])
+@pytest.mark.parametrize("shape,kind,offsets,temps,R,D", [
+    ((16, 16), "ferro", None, np.linspace(1.8, 2.8, 5), 2, 1),          # row-table kernels, labels in shared memory
+    ((8, 8, 8), "bimodal", None, [0.9, 1.5, 2.4], 2, 2),
+    ((6, 6), "diluted", TRI, [1.0, 2.5], 3, 2),                         # zeros in the couplings, table-driven kernels
+    ((5, 7), "bimodal", None, [0.8, 2.5], 2, 1),                        # odd extents
+    ((256, 256), "ferro", None, [2.1, 2.27, 2.5], 1, 1),                # labels in global scratch (64 Ki sites), critical clusters
+])
+def test_cluster_updates_are_bit_exact(oracle, cluster_mode, shape, kind, offsets, temps, R, D):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
+    big = int(np.prod(shape)) > 10000
+    for n_sweeps, interval, pt in ((6, 1, None), (12, 1, 1), (9, 2, 3)) if big else ((40, 1, None), (30, 1, 1), (25, 3, 2)):
+        kw = dict(cluster_update_interval=interval, cluster_mode=cluster_mode, pt_interval=pt)
+        rg = gpu.sample(n_sweeps, "metropolis", **kw)
+        rc = cpu.sample(n_sweeps, "metropolis", **kw)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+
+
+def test_cluster_updates_need_the_int8_layout_and_unit_couplings(oracle):
+    gpu, _ = make_pair(oracle, (4, 4, 8), "bimodal", [1.0, 2.0], 2, 32, layout="msc")
+    before = gpu.get_spins(0).copy()
+    with pytest.raises(ValueError, match="not implemented on the GPU sweep path"):
+        gpu.sample(4, "metropolis", cluster_update_interval=1)
+    assert np.array_equal(gpu.get_spins(0), before)
+    gauss, _ = make_pair(oracle, (4, 4, 8), "gaussian", [1.0, 2.0], 2, 1)
+    with pytest.raises(ValueError, match="not implemented on the GPU sweep path"):
+        gauss.sample(4, "metropolis", cluster_update_interval=1)

@@ -342,3 +342,59 @@ def test_autocorrelation_keys_and_lag_clamp(oracle):
     assert np.allclose(res["mags2_tau"], sim.last_per_sample_taus[:, 0, :].sum(axis=0) / 2)
     sim1 = oracle.Sim((4, 4), J[0], np.asarray([1.5, 2.5], np.float32), n_replicas=1, seed=3)
     assert "overlap2_tau" not in sim1.sample(40, "metropolis", autocorrelation_max_lag=5)
+
+
+# ---- clusters/fk.rs:28-171 restated under RNG-SPEC draws (oracle.fk_update) ----
+def _fk(oracle, shape, spins, J, temperature, wolff, key=0x1234ABCD5678EF01, sweep_index=7, system_id=3):
+    import ctypes as C
+
+    lat = oracle.Lattice(shape)
+    s = np.ascontiguousarray(spins, dtype=np.int8).copy()
+    Jc = np.ascontiguousarray(J, dtype=np.float32)
+    f = oracle.lib().orc_fk_update
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
+    f(lat.h, s.ctypes.data, Jc.ctypes.data, float(temperature), key, sweep_index, system_id, int(wolff))
+    return s.reshape(-1)
+
+
+def test_fk_bond_count_limits(oracle):
+    f = oracle.lib().orc_fk_bond_count
+    import ctypes as C
+    f.restype, f.argtypes = C.c_uint32, [C.c_float]
+    assert f(1e-3) == 1 << 24                                  # T -> 0: every satisfied bond is activated
+    assert f(1e9) == 0 or f(1e9) < 4                           # T -> inf: none
+    p = 1.0 - np.exp(np.float32(-2.0) / np.float32(2.269))
+    assert abs(f(2.269) / 2.0**24 - float(p)) < 2.0**-23       # fk.rs:113
+
+
+def test_fk_cold_limit_flips_whole_domains(oracle):
+    """T -> 0: clusters = connected domains of satisfied bonds.  A ferromagnet with one flipped 2x2 block has two domains;
+    Swendsen-Wang flips each as a whole (or not), Wolff flips exactly the seed's domain."""
+    shape = (6, 6)
+    spins = np.ones(shape, np.int8)
+    spins[1:3, 1:3] = -1
+    J = np.ones(shape + (2,), np.float32)
+    inside = spins.reshape(-1) == -1
+    for wolff in (0, 1):
+        seen = set()
+        for sweep in range(48 if wolff else 12):  # the Wolff seed lands in the small domain with probability 1/9
+            out = _fk(oracle, shape, spins, J, 1e-3, wolff, sweep_index=sweep)
+            a, b = out[inside] * spins.reshape(-1)[inside], out[~inside] * spins.reshape(-1)[~inside]
+            assert len(set(a)) == 1 and len(set(b)) == 1       # each domain moves as one
+            if wolff:
+                assert (a[0] == -1) != (b[0] == -1)            # exactly one domain flips
+            seen.add((int(a[0]), int(b[0])))
+        assert len(seen) >= 2                                  # the draws do differ from sweep to sweep
+
+
+def test_fk_hot_limit_is_independent_coin_flips_and_antiferro_bonds_never_join(oracle):
+    shape = (8, 8)
+    spins = np.ones(shape, np.int8)
+    J = np.ones(shape + (2,), np.float32)
+    out = _fk(oracle, shape, spins, J, 1e9, 0)
+    frac = np.mean(out == -1)
+    assert 0.3 < frac < 0.7 and len(set(out.tolist())) == 2    # single-site clusters, fair coins (fk.rs:159-170)
+    # all bonds unsatisfied (J = -1 on an aligned state): nothing joins even at T -> 0
+    out2 = _fk(oracle, shape, spins, -J, 1e-3, 0)
+    assert 0.3 < np.mean(out2 == -1) < 0.7
