@@ -94,8 +94,9 @@ typedef struct {
     /* 0 = None; > 0: Fortuin-Kasteleyn cluster update (clusters/fk.rs, action "update") of every system after each
      * cluster_update_interval-th sweep (simulation/mod.rs:434-470); int8 layouts with unit couplings, else PP_ERR_UNSUPPORTED */
     int64_t cluster_update_interval;
-    /* options of the reference that this path does not implement: must be 0, else
-     * PP_ERR_UNSUPPORTED is returned before any state mutation */
+    /* 0 = None; > 0: Houdayer isoenergetic cluster move, group size 2 (clusters/overlap.rs:146-339, action "update"), for every
+     * temperature after each overlap_cluster_update_interval-th sweep's measurements (simulation/mod.rs:596-746); int8 layout,
+     * n_replicas >= 2, else an error before any state mutation */
     int64_t overlap_cluster_update_interval;
     /* 0 = None; > 0: integrated autocorrelation times of m^2 and q^2 over the recorded sweeps (statistics/autocorrelation.rs,
      * ring backend; the lag is clamped to [1, recorded sweeps / 4] as simulation/mod.rs:342-344) */
@@ -111,6 +112,7 @@ typedef struct {
      * duration in pp_results.sweep_kernel_ms (measurement hook for the roofline figure) */
     int32_t profile;
     int32_t cluster_mode;                    /* PP_CLUSTER_SW (0) or PP_CLUSTER_WOLFF (1); used when cluster_update_interval > 0 */
+    int32_t overlap_cluster_mode;            /* PP_CLUSTER_*; used when overlap_cluster_update_interval > 0 (reference default: wolff) */
 } pp_sample_cfg;
 
 /* Result buffers; every pointer may be NULL (that output is skipped).

@@ -42,6 +42,8 @@ class _Config(C.Structure):
         ("autocorr_max_lag", C.c_int64),
         ("cluster_interval", C.c_int64),
         ("cluster_wolff", C.c_int32),
+        ("overlap_cluster_interval", C.c_int64),
+        ("overlap_cluster_wolff", C.c_int32),
         ("equil_diag", C.c_int32),
     ]
 
@@ -283,13 +285,16 @@ class Sim:
 
     def sample(self, n_sweeps, sweep_mode="metropolis", pt_interval=None, pt_schedule="single_random_edge",
                warmup_ratio=0.25, n_threads=1, force_log_form=False, per_sample=True, autocorrelation_max_lag=None,
-               equilibration_diagnostic=False, cluster_update_interval=None, cluster_mode="sw"):
+               equilibration_diagnostic=False, cluster_update_interval=None, cluster_mode="sw",
+               overlap_cluster_update_interval=None, overlap_cluster_mode="wolff"):
         # src/lib.rs:219-220 (Rust f64::round = half away from zero)
         warm = int(np.floor(n_sweeps * warmup_ratio + 0.5))
         cfg = _Config(n_sweeps, warm, {"metropolis": 0, "gibbs": 1}[sweep_mode], 0 if pt_interval is None else pt_interval,
                       {"single_random_edge": 0, "full_ladder": 1}[pt_schedule], n_threads, int(force_log_form),
                       0 if autocorrelation_max_lag is None else int(autocorrelation_max_lag),
                       0 if cluster_update_interval is None else int(cluster_update_interval), {"sw": 0, "wolff": 1}[cluster_mode],
+                      0 if overlap_cluster_update_interval is None else int(overlap_cluster_update_interval),
+                      {"sw": 0, "wolff": 1}[overlap_cluster_mode],
                       int(bool(equilibration_diagnostic)))
         T, R, D, N = self.T, self.R, self.D, self.N
         out = {k: np.zeros(T, dtype=np.float64) for k in ("mags", "mags2", "mags4", "energies", "energies2")}

@@ -684,6 +684,56 @@ void orc_fk_update(const orc_lattice *lat, int8_t *spins, const float *couplings
     free(parent);
 }
 
+/* ---- clusters/overlap.rs:34-56, 146-339 (Houdayer, group size 2), RNG-SPEC draws ------------------ */
+void orc_houdayer_slot(const orc_lattice *lat, int8_t *spins, const int64_t *system_ids, int n_temps, int n_replicas, int t,
+                       uint64_t key, uint32_t sweep_index, int wolff) {
+    int64_t N = lat->n_spins;
+    int z = lat->n_neighbors, R = n_replicas, P = R / 2;
+    int64_t sys[64];
+    for (int k = 0; k < R; k++) sys[k] = system_ids[k * n_temps + t]; /* overlap.rs:45-48 */
+    for (int i = R - 1; i >= 1; i--) { /* shuffle (overlap.rs:49): Fisher-Yates, step i draws j in [0, i] */
+        uint32_t ctr[4] = {(uint32_t)i, sweep_index, (uint32_t)t, ORC_TAG_OC_PAIR}, k2[2] = {(uint32_t)key, (uint32_t)(key >> 32)}, o[4];
+        orc_philox4x32_10(ctr, k2, o);
+        int j = (int)(((uint64_t)o[0] * (uint64_t)(i + 1)) >> 32);
+        int64_t tmp = sys[i]; sys[i] = sys[j]; sys[j] = tmp;
+    }
+    int64_t *parent = malloc(sizeof(int64_t) * (size_t)N);
+    uint8_t *active = malloc((size_t)N), *multi = malloc((size_t)N);
+    for (int g = 0; g < P; g++) {
+        int8_t *a = spins + sys[2 * g] * N, *b = spins + sys[2 * g + 1] * N;
+        uint32_t stream = (uint32_t)(t * P + g);
+        for (int64_t i = 0; i < N; i++) { parent[i] = i; active[i] = a[i] != b[i]; multi[i] = 0; } /* overlap.rs:222-228 */
+        for (int64_t i = 0; i < N; i++)
+            for (int d = 0; d < z; d++) { /* overlap.rs:231-234: deterministic bonds between active neighbours */
+                int64_t j = lat->fwd[i * z + d];
+                if (!(active[i] && active[j]) || i == j) continue;
+                multi[i] = multi[j] = 1;
+                int64_t ra = uf_find(parent, i), rb = uf_find(parent, j);
+                if (ra < rb) parent[rb] = ra; else if (rb < ra) parent[ra] = rb;
+            }
+        for (int64_t i = 0; i < N; i++) parent[i] = uf_find(parent, i);
+        if (wolff) { /* overlap.rs:245-256 */
+            uint64_t best = UINT64_MAX;
+            for (int64_t i = 0; i < N; i++)
+                if (active[i]) {
+                    uint64_t score = ((uint64_t)orc_draw24(key, (uint32_t)i, sweep_index, stream, ORC_TAG_OC_SEED) << 32) | (uint64_t)i;
+                    if (score < best) best = score;
+                }
+            if (best == UINT64_MAX) continue; /* no active site: nothing to do */
+            int64_t root = parent[best & 0xFFFFFFFFu];
+            for (int64_t i = 0; i < N; i++)
+                if (active[i] && parent[i] == root) { a[i] = (int8_t)-a[i]; b[i] = (int8_t)-b[i]; }
+        } else { /* overlap.rs:293-307: clusters of more than one site, fair coin each */
+            for (int64_t i = 0; i < N; i++)
+                if (active[i] && multi[i] &&
+                    orc_draw24(key, (uint32_t)parent[i], sweep_index, stream, ORC_TAG_OC_FLIP) < (1u << 23)) {
+                    a[i] = (int8_t)-a[i]; b[i] = (int8_t)-b[i];
+                }
+        }
+    }
+    free(parent); free(active); free(multi);
+}
+
 /* ---- statistics/autocorrelation.rs: ring backend ------------------------------------------------ */
 typedef struct {
     int max_lag, n_temps, ring_len, ring_pos;
@@ -959,6 +1009,13 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
             }
         }
 
+        /* mod.rs:596-746: overlap cluster move after the measurements; energies are refreshed only for PT (:748-756) */
+        if (cfg->overlap_cluster_interval > 0 && sweep_id % cfg->overlap_cluster_interval == 0) {
+            for (int t = 0; t < T; t++)
+                orc_houdayer_slot(lat, re->spins, re->system_ids, T, R, t, re->base_seed, sweep_index, cfg->overlap_cluster_wolff);
+            if (pt_this_sweep) orc_energies_mags(lat, re->spins, re->couplings, S, re->energies, NULL);
+        }
+
         /* mod.rs:748-796 */
         if (pt_this_sweep) {
             int first_parity = re->pt.next_parity;
@@ -1064,7 +1121,11 @@ static int validate(const orc_config *cfg) {
 /* simulation/mod.rs:865-939 + statistics/results.rs:165-180, 250-259 + statistics/overlap.rs:106-152 */
 int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
     if (validate(cfg) != 0) return -1;
-    if (cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX) {
+    if (cfg->overlap_cluster_interval > 0 && sim->n_replicas < 2) {
+        set_err("overlap cluster requires n_replicas >= max group_size"); /* mod.rs:207-213 */
+        return -1;
+    }
+    if ((cfg->cluster_interval > 0 || cfg->overlap_cluster_interval > 0) && sim->rng_mode != ORC_RNG_PHILOX) {
         set_err("cluster updates are restated for the int8 RNG-SPEC mode only");
         return -1;
     }

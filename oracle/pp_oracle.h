@@ -54,6 +54,9 @@ enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
 #define ORC_TAG_SWEEP_MSC 0x00040000u
 #define ORC_TAG_FK_BOND   0x00050000u  /* counter = {bond >> 2, sweep index, system id, tag}; bond = site * z' + direction */
 #define ORC_TAG_FK_FLIP   0x00060000u  /* counter = {root >> 2 | 0xFFFFFFFF (Wolff seed), sweep index, system id, tag} */
+#define ORC_TAG_OC_PAIR   0x00070000u  /* replica shuffle at a temperature: counter = {step, sweep index, slot t, tag} */
+#define ORC_TAG_OC_SEED   0x00080000u  /* Wolff seed scores: counter = {site >> 2, sweep index, t * P + g, tag} */
+#define ORC_TAG_OC_FLIP   0x00090000u  /* cluster coins:     counter = {root >> 2, sweep index, t * P + g, tag} */
 #define ORC_MSC_KEY_DOMAIN 0x6D73635F67726F75ull
 
 typedef struct orc_lattice orc_lattice;
@@ -70,6 +73,8 @@ typedef struct {
     int64_t autocorr_max_lag; /* 0 = off; simulation/mod.rs:342-344: clamped to [1, recorded sweeps / 4] */
     int64_t cluster_interval; /* 0 = off; Fortuin-Kasteleyn cluster update every this many sweeps (simulation/mod.rs:434-470) */
     int32_t cluster_wolff;    /* 0: Swendsen-Wang (every cluster flips with probability 1/2); 1: Wolff (the seed's cluster flips) */
+    int64_t overlap_cluster_interval; /* 0 = off; Houdayer isoenergetic cluster move (group size 2) every this many sweeps */
+    int32_t overlap_cluster_wolff;    /* 1: flip the cluster of one drawn active site (default); 0: every multi-site cluster w.p. 1/2 */
     int32_t equil_diag;       /* 1: equilibration diagnostic (statistics/equilibration.rs; energies + link overlaps every sweep) */
 } orc_config;
 
@@ -171,6 +176,14 @@ uint32_t orc_fk_bond_count(float temperature);
  * the drawn seed site.  Unit couplings (|J| in {0, 1}) only. */
 void orc_fk_update(const orc_lattice *lat, int8_t *spins, const float *couplings, float temperature, uint64_t key,
                    uint32_t sweep_index, uint32_t system_id, int wolff);
+
+/* ---- Houdayer isoenergetic cluster move, group size 2 (clusters/overlap.rs:34-56, 146-339) under RNG-SPEC draws ----
+ * One realization, temperature slot t: the R systems at the slot are shuffled (Fisher-Yates, draws of ORC_TAG_OC_PAIR) and paired;
+ * for pair g the active sites are those where the two replicas differ, bonds join active neighbours, clusters are named by
+ * their smallest site.  wolff: the active site with the smallest (score, index) is the seed (uniform over active sites) and its
+ * cluster flips in both replicas; else every cluster of more than one site flips iff its root draw is < 1/2. */
+void orc_houdayer_slot(const orc_lattice *lat, int8_t *spins /* [S][N] */, const int64_t *system_ids /* [S] */, int n_temps,
+                       int n_replicas, int t, uint64_t key, uint32_t sweep_index, int wolff);
 
 /* statistics/equilibration.rs:18-29: 128, 256, ... < n_sweeps, then n_sweeps.  Returns the count (out may be NULL). */
 int orc_equil_checkpoints(int64_t n_sweeps, int64_t *out);

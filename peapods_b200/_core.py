@@ -123,6 +123,22 @@ class IsingSimulation:
                 raise ValueError("cluster_action='observe' is not implemented on the GPU sweep path")
         if collect_cluster_stats:
             raise ValueError("collect_cluster_stats is not implemented on the GPU sweep path")
+        oc_wolff = True
+        if overlap_cluster_update_interval is not None:  # src/lib.rs:249-262
+            build = "houdayer" if overlap_cluster_build_mode is None else overlap_cluster_build_mode
+            oc_mode = "wolff" if overlap_cluster_mode is None else overlap_cluster_mode
+            oc_action = "update" if overlap_cluster_action is None else overlap_cluster_action
+            if oc_mode not in ("wolff", "sw"):
+                raise ValueError(f"unknown cluster_mode '{oc_mode}', expected 'wolff' or 'sw'")
+            if oc_action not in ("update", "observe"):
+                raise ValueError(f"unknown cluster action '{oc_action}', expected 'update' or 'observe'")
+            if build.strip() not in ("houdayer", "houd2"):  # config.rs:117-131: houdN, jorg, cmr, a+b round-robin
+                raise ValueError(f"overlap_cluster_build_mode '{build}' is not implemented on the GPU sweep path (only 'houdayer')")
+            if oc_action == "observe":
+                raise ValueError("overlap_cluster_action='observe' is not implemented on the GPU sweep path")
+            if snapshot_interval is not None:
+                raise ValueError("snapshot_interval is not implemented on the GPU sweep path")
+            oc_wolff = oc_mode == "wolff"
         if pt_interval is not None and int(pt_interval) == 0:  # config.rs:197-199
             raise ValueError("pt_interval must be >= 1")
         if backend == "fft" and autocorrelation_max_lag is None:  # config.rs:200-206
@@ -141,6 +157,7 @@ class IsingSimulation:
         cfg.snapshot_interval = 0 if snapshot_interval is None else max(int(snapshot_interval), 1)
         cfg.equilibration_diagnostic = int(bool(equilibration_diagnostic))
         cfg.cluster_mode = 1 if (cluster_update_interval is not None and cluster_mode == "wolff") else 0
+        cfg.overlap_cluster_mode = 1 if oc_wolff else 0
         cfg.exact_log = int(bool(exact_log))
         cfg.profile = int(bool(profile))
 

@@ -58,6 +58,7 @@ class SampleCfg(C.Structure):
         ("exact_log", C.c_int32),
         ("profile", C.c_int32),
         ("cluster_mode", C.c_int32),
+        ("overlap_cluster_mode", C.c_int32),
     ]
 
 

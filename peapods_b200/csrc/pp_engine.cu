@@ -1263,8 +1263,9 @@ static pp_status validate_cfg(const pp_sample_cfg *c) {
     if (c->cluster_update_interval < 0) return fail(PP_ERR_INVALID, "cluster_update_interval must be >= 1");
     if (c->cluster_mode != PP_CLUSTER_SW && c->cluster_mode != PP_CLUSTER_WOLFF)
         return fail(PP_ERR_INVALID, "unknown cluster_mode, expected 'wolff' or 'sw'");
-    if (c->overlap_cluster_update_interval != 0)
-        return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep path");
+    if (c->overlap_cluster_update_interval < 0) return fail(PP_ERR_INVALID, "overlap_cluster_update_interval must be >= 1");
+    if (c->overlap_cluster_mode != PP_CLUSTER_SW && c->overlap_cluster_mode != PP_CLUSTER_WOLFF)
+        return fail(PP_ERR_INVALID, "unknown cluster_mode, expected 'wolff' or 'sw'");
     if (c->autocorrelation_max_lag < 0) return fail(PP_ERR_INVALID, "autocorrelation_max_lag must be >= 1");
     if (c->snapshot_interval != 0) return fail(PP_ERR_UNSUPPORTED, "snapshot_interval is not implemented on the GPU sweep path");
     return PP_OK;
@@ -1369,12 +1370,21 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemsetAsync(d_eq_snap, 0, sizeof(double) * ndt * 2 * ckpts.size(), s->stream));
     }
     // Fortuin-Kasteleyn cluster updates (mod.rs:434-470): int8 layouts with unit couplings
+    const bool want_oc = cfg->overlap_cluster_update_interval > 0;
     const bool want_fk = cfg->cluster_update_interval > 0;
     uint32_t *d_fk_count = nullptr, *d_fk_lab = nullptr;
     uint8_t *d_fk_bm = nullptr;
     int64_t fk_smem_sites = 0;
     size_t fk_smem = 0;
     auto free_fk = [&]() { pool_free(s, d_fk_count); pool_free(s, d_fk_lab); pool_free(s, d_fk_bm); };
+    if (want_oc && (s->layout != PP_LAYOUT_INT8 || m.R < 2 || m.R > 64)) {
+        free_ac();
+        pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
+        if (s->layout == PP_LAYOUT_INT8 && m.R < 2)  // mod.rs:207-213
+            return fail(PP_ERR_INVALID, "overlap cluster requires n_replicas >= max group_size (" + std::to_string(m.R) + " < 2)");
+        return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep "
+                                        "path for this handle: they need the int8 layout");
+    }
     if (want_fk) {
         if (s->layout != PP_LAYOUT_INT8 || m.coupling_class == COUP_F32) {
             free_ac();
@@ -1391,10 +1401,13 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(pool_alloc(s, (void **)&d_fk_count, sizeof(uint32_t) * counts.size()));
         CUDA_TRY(cudaMemcpyAsync(d_fk_count, counts.data(), sizeof(uint32_t) * counts.size(), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        if ((size_t)m.N * 5 <= 200 * 1024) {  // labels (u32) + bond masks (u8) in shared memory
+    }
+    if (want_fk || want_oc) {
+        if ((size_t)m.N * 5 <= 200 * 1024) {  // labels (u32) + bond / activity masks (u8) in shared memory
             fk_smem_sites = m.N;
             fk_smem = (size_t)m.N * 5 + 16;
             CUDA_TRY(cudaFuncSetAttribute(fk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
+            CUDA_TRY(cudaFuncSetAttribute(houdayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fk_smem));
         } else {
             CUDA_TRY(pool_alloc(s, (void **)&d_fk_lab, sizeof(uint32_t) * (size_t)(m.D * m.S * m.N)));
             CUDA_TRY(pool_alloc(s, (void **)&d_fk_bm, (size_t)(m.D * m.S * m.N)));
@@ -1446,7 +1459,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     std::vector<Step> steps;
     int64_t sweep_id = 0;
     // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel, up to 256 sweeps per launch
-    if (s->rows && s->resident && !s->profile && !want_ac && !want_eq && !want_fk) {
+    if (s->rows && s->resident && !s->profile && !want_ac && !want_eq && !want_fk && !want_oc) {
         Ctx &c = chunks[0];
         RowsView v = s->rv;
         v.keys = s->d_keys;
@@ -1593,6 +1606,17 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                                                                                          (long long)(stp.sid_last - cfg->warmup_sweeps));
                     s->launches++;
                 }
+                if (want_oc && stp.sid_last % cfg->overlap_cluster_update_interval == 0) {  // mod.rs:596-746
+                    houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
+                        c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,
+                        d_fk_lab, d_fk_bm);
+                    s->launches++;
+                    CUDA_TRY(cudaGetLastError());
+                    if (stp.pt_this) {  // mod.rs:748-756: the move changed the replicas' energies
+                        st = launch_energy(s, c, false);
+                        if (st != PP_OK) return st;
+                    }
+                }
                 if (stp.pt_this) {                                                     // mod.rs:748-796
                     st = launch_pt(s, c, cfg->pt_schedule, stp.pt_event, stp.parity, true);
                     if (st != PP_OK) return st;
@@ -1640,7 +1664,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemcpy(taus.data(), d_tau, sizeof(double) * (size_t)ndt * (ac_q.ring ? 2 : 1), cudaMemcpyDeviceToHost));
         free_ac();
     }
-    if (want_fk) free_fk();
+    if (want_fk || want_oc) free_fk();
     std::vector<double> eq_snap;  // [D][n_ckpt][2][T]
     if (want_eq) {
         eq_snap.assign((size_t)m.D * ckpts.size() * 2 * m.T, 0.0);

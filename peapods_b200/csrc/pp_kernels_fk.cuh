@@ -1,4 +1,5 @@
-// pp_kernels_fk.cuh — Fortuin-Kasteleyn cluster update (Swendsen-Wang / Wolff) for the int8 layouts.
+// pp_kernels_fk.cuh — cluster moves for the int8 layouts: Fortuin-Kasteleyn update (Swendsen-Wang / Wolff) and the Houdayer
+// isoenergetic overlap move (second half of the file).
 //
 // Replaces  clusters/fk.rs:28-171 (fk_update, union-find path; called from simulation/mod.rs:434-470 after the sweep and before
 // the measurements).  Bonds between neighbours with s_i s_j J > 0 are activated with probability 1 - exp(-2 / T) (unit
@@ -98,6 +99,110 @@ fk_cluster_kernel(ModelView m, const uint32_t *bond_count /* [T] */, uint32_t sw
             flip = (pick(o, root & 3u) >> 8) < (1u << 23);
         }
         if (flip) s[i] = (int8_t)-s[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Houdayer isoenergetic cluster move, group size 2 (clusters/overlap.rs:34-56, 146-339; called from simulation/mod.rs:596-746
+// after the measurements, energies refreshed for PT only).  One CTA per (realization d, slot t, pair g): the R systems at the
+// slot are shuffled (Fisher-Yates on TAG_OC_PAIR draws) and paired; active sites are those where the two replicas differ, bonds
+// join active neighbours (no draws), clusters are named by their smallest site.  wolff: the active site with the smallest
+// (score, index) -- scores are TAG_OC_SEED draws, so the choice is uniform over the active sites -- is the seed and its cluster
+// flips in both replicas; else every cluster of more than one site flips iff its TAG_OC_FLIP draw is below 2^23.
+constexpr uint32_t TAG_OC_PAIR = 0x00070000u;
+constexpr uint32_t TAG_OC_SEED = 0x00080000u;
+constexpr uint32_t TAG_OC_FLIP = 0x00090000u;
+
+__global__ void __launch_bounds__(FK_THREADS)
+houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites, uint32_t *g_lab, uint8_t *g_bm) {
+    extern __shared__ __align__(16) uint32_t fk_sm[];
+    __shared__ unsigned long long best_sh;
+    __shared__ int sys_sh[2];
+    const int64_t N = m.N;
+    const int z = m.z, tid = threadIdx.x;
+    const int g = (int)(blockIdx.x % m.P);
+    const int t = (int)((blockIdx.x / m.P) % m.T);
+    const int64_t d = blockIdx.x / ((int64_t)m.P * m.T);
+    const bool in_smem = smem_sites >= N;
+    uint32_t *lab = in_smem ? fk_sm : g_lab + (int64_t)blockIdx.x * N;
+    uint8_t *act = in_smem ? reinterpret_cast<uint8_t *>(fk_sm + N) : g_bm + (int64_t)blockIdx.x * N;  // bit 0: active, bit 1: has an active neighbour
+    const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    const uint32_t stream = (uint32_t)(t * m.P + g);
+    if (tid == 0) {  // overlap.rs:45-49: the slot's systems in replica order, shuffled
+        int sys[64];
+        for (int k = 0; k < m.R; k++) sys[k] = m.system_ids[d * m.S + k * m.T + t];
+        for (int i = m.R - 1; i >= 1; i--) {
+            const u32x4 o = philox4x32_10((uint32_t)i, sweep_index, (uint32_t)t, TAG_OC_PAIR, k0, k1);
+            const int j = (int)(((uint64_t)o.x * (uint64_t)(i + 1)) >> 32);
+            const int tmp = sys[i]; sys[i] = sys[j]; sys[j] = tmp;
+        }
+        sys_sh[0] = sys[2 * g];
+        sys_sh[1] = sys[2 * g + 1];
+        best_sh = ~0ull;
+    }
+    __syncthreads();
+    int8_t *a = m.spins + (d * m.S + sys_sh[0]) * N, *b = m.spins + (d * m.S + sys_sh[1]) * N;
+    for (int64_t i = tid; i < N; i += FK_THREADS) {
+        act[i] = a[i] != b[i] ? 1 : 0;
+        lab[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < N; i += FK_THREADS) {  // sites with an active neighbour (clusters of more than one site)
+        if (!(act[i] & 1)) continue;
+        bool multi = false;
+        for (int dd = 0; dd < 2 * z; dd++) {
+            const uint32_t j = m.nbr[(size_t)i * 2 * z + dd];
+            multi = multi || (j != (uint32_t)i && (act[j] & 1));
+        }
+        if (multi) act[i] |= 2;
+    }
+    __syncthreads();
+    for (;;) {  // connected components of the active sites
+        int changed = 0;
+        for (int64_t i = tid; i < N; i += FK_THREADS) {
+            if (!(act[i] & 2)) continue;
+            const uint32_t old = lab[i];
+            uint32_t best = old;
+            for (int dd = 0; dd < 2 * z; dd++) {
+                const uint32_t j = m.nbr[(size_t)i * 2 * z + dd];
+                if (act[j] & 1) best = min(best, lab[j]);
+            }
+            best = min(best, lab[best]);
+            best = min(best, lab[best]);
+            if (best < old) {
+                atomicMin(&lab[i], best);
+                atomicMin(&lab[old], best);
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (wolff) {  // overlap.rs:245-256
+        unsigned long long best = ~0ull;
+        for (int64_t i = tid; i < N; i += FK_THREADS) {
+            if (!(act[i] & 1)) continue;
+            const u32x4 o = philox4x32_10((uint32_t)i >> 2, sweep_index, stream, TAG_OC_SEED, k0, k1);
+            const unsigned long long score = ((unsigned long long)(pick(o, (uint32_t)i & 3u) >> 8) << 32) | (unsigned long long)i;
+            best = score < best ? score : best;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            best = other < best ? other : best;
+        }
+        if ((tid & 31) == 0 && best != ~0ull) atomicMin(&best_sh, best);
+        __syncthreads();
+        if (best_sh == ~0ull) return;  // no active site
+        const uint32_t root = lab[(uint32_t)(best_sh & 0xFFFFFFFFull)];
+        for (int64_t i = tid; i < N; i += FK_THREADS)
+            if ((act[i] & 1) && lab[i] == root) { a[i] = (int8_t)-a[i]; b[i] = (int8_t)-b[i]; }
+    } else {  // overlap.rs:293-307
+        for (int64_t i = tid; i < N; i += FK_THREADS) {
+            if ((act[i] & 3) != 3) continue;
+            const uint32_t root = lab[i];
+            const u32x4 o = philox4x32_10(root >> 2, sweep_index, stream, TAG_OC_FLIP, k0, k1);
+            if ((pick(o, root & 3u) >> 8) < (1u << 23)) { a[i] = (int8_t)-a[i]; b[i] = (int8_t)-b[i]; }
+        }
     }
 }
 #endif  // __CUDACC__

@@ -117,7 +117,11 @@ def test_invalid_autocorrelation_backend_fails_before_sampling():  # :197-206
 @pytest.mark.parametrize("kwargs", [
     dict(cluster_update_interval=1, cluster_action="observe"),         # FK graph observation (cluster moves themselves run)
     dict(cluster_update_interval=1, collect_cluster_stats=True),
-    dict(overlap_cluster_update_interval=1),                           # Houdayer / Jorg / CMR
+    dict(overlap_cluster_update_interval=1, overlap_cluster_build_mode="jorg"),
+    dict(overlap_cluster_update_interval=1, overlap_cluster_build_mode="cmr+houdayer"),
+    dict(overlap_cluster_update_interval=1, overlap_cluster_build_mode="houd4"),
+    dict(overlap_cluster_update_interval=1, overlap_cluster_action="observe"),
+    dict(overlap_cluster_update_interval=1, snapshot_interval=2),
 ])
 def test_options_outside_the_sweep_path_are_rejected_before_mutation(kwargs):
     from peapods_b200 import Ising

@@ -533,3 +533,36 @@ def test_cluster_updates_need_the_int8_layout_and_unit_couplings(oracle):
     gauss, _ = make_pair(oracle, (4, 4, 8), "gaussian", [1.0, 2.0], 2, 1)
     with pytest.raises(ValueError, match="not implemented on the GPU sweep path"):
         gauss.sample(4, "metropolis", cluster_update_interval=1)
+
+
+# ---- Houdayer isoenergetic cluster move (clusters/overlap.rs:34-56, 146-339 from simulation/mod.rs:596-756) ----
+@pytest.mark.parametrize("oc_mode", ["wolff", "sw"])
+@pytest.mark.parametrize("shape,kind,offsets,temps,R,D", [
+    ((8, 8, 8), "bimodal", None, [0.7, 1.0, 1.4], 2, 2),
+    ((6, 6, 6), "bimodal", None, np.linspace(0.6, 1.6, 4), 4, 3),       # two pairs per temperature: shuffled pairing
+    ((8, 8), "gaussian", TRI, [0.8, 1.6], 3, 2),                        # unpaired third replica; no couplings involved
+    ((5, 7), "bimodal", None, [0.8, 2.5], 2, 1),
+    ((64, 64), "bimodal", None, [0.6, 1.2], 2, 1),                      # 4096 sites: 2-D spin glass, large overlap clusters
+])
+def test_houdayer_moves_are_bit_exact(oracle, oc_mode, shape, kind, offsets, temps, R, D):
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
+    gaussian = kind == "gaussian"
+    for n_sweeps, interval, pt in ((30, 1, None), (24, 1, 1), (25, 3, 2)):
+        pt = None if gaussian else pt  # f32 energies are tolerance-checked: PT (which branches on them) stays off there
+        kw = dict(overlap_cluster_update_interval=interval, overlap_cluster_mode=oc_mode, pt_interval=pt)
+        rg = gpu.sample(n_sweeps, "metropolis", exact_log=True, **kw)
+        rc = cpu.sample(n_sweeps, "metropolis", **kw)
+        assert_state_equal(gpu, cpu, D)
+        if not gaussian:
+            assert_results_equal(rg, rc)
+
+
+def test_houdayer_needs_two_replicas_and_the_int8_layout(oracle):
+    one, _ = make_pair(oracle, (4, 4, 8), "bimodal", [1.0, 2.0], 1, 1)
+    with pytest.raises(ValueError, match="overlap cluster requires n_replicas >= max group_size"):
+        one.sample(4, "metropolis", overlap_cluster_update_interval=1)
+    msc, _ = make_pair(oracle, (4, 4, 8), "bimodal", [1.0, 2.0], 2, 32, layout="msc")
+    before = msc.get_spins(0).copy()
+    with pytest.raises(ValueError, match="not implemented on the GPU sweep path"):
+        msc.sample(4, "metropolis", overlap_cluster_update_interval=1)
+    assert np.array_equal(msc.get_spins(0), before)
