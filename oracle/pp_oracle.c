@@ -1012,7 +1012,8 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
         /* mod.rs:596-746: overlap cluster move after the measurements; energies are refreshed only for PT (:748-756) */
         if (cfg->overlap_cluster_interval > 0 && sweep_id % cfg->overlap_cluster_interval == 0) {
             for (int t = 0; t < T; t++)
-                orc_houdayer_slot(lat, re->spins, re->system_ids, T, R, t, re->base_seed, sweep_index, cfg->overlap_cluster_wolff);
+                orc_houdayer_slot(lat, re->spins, re->system_ids, T, R, t, msc ? sweep_key : re->base_seed, sweep_index,
+                                  cfg->overlap_cluster_wolff); /* multispin layout: lane-uniform draws use the group key */
             if (pt_this_sweep) orc_energies_mags(lat, re->spins, re->couplings, S, re->energies, NULL);
         }
 
@@ -1125,8 +1126,9 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
         set_err("overlap cluster requires n_replicas >= max group_size"); /* mod.rs:207-213 */
         return -1;
     }
-    if ((cfg->cluster_interval > 0 || cfg->overlap_cluster_interval > 0) && sim->rng_mode != ORC_RNG_PHILOX) {
-        set_err("cluster updates are restated for the int8 RNG-SPEC mode only");
+    if ((cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX) ||
+        (cfg->overlap_cluster_interval > 0 && sim->rng_mode == ORC_RNG_XOSHIRO)) {
+        set_err("cluster updates are restated for the RNG-SPEC modes only (FK: int8 mode)");
         return -1;
     }
     int T = sim->n_temps, R = sim->n_replicas;

@@ -1377,14 +1377,20 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     int64_t fk_smem_sites = 0;
     size_t fk_smem = 0;
     auto free_fk = [&]() { pool_free(s, d_fk_count); pool_free(s, d_fk_lab); pool_free(s, d_fk_bm); };
-    if (want_oc && (s->layout != PP_LAYOUT_INT8 || m.R < 2 || m.R > 64)) {
+    // multispin layout: Wolff mode only (32 clusters grow as one bit-parallel flood fill), state of one pair in shared memory
+    const size_t oc_msc_smem = ((size_t)3 * m.N + (size_t)m.N * m.z) * 4 + 16;
+    const bool oc_msc_ok = s->layout == PP_LAYOUT_MSC && cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF && m.N <= 65536 &&
+                           oc_msc_smem <= 200 * 1024;
+    if (want_oc && ((s->layout != PP_LAYOUT_INT8 && !oc_msc_ok) || m.R < 2 || m.R > 64)) {
         free_ac();
         pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
-        if (s->layout == PP_LAYOUT_INT8 && m.R < 2)  // mod.rs:207-213
+        if (s->layout != PP_LAYOUT_SLAB && m.R < 2)  // mod.rs:207-213
             return fail(PP_ERR_INVALID, "overlap cluster requires n_replicas >= max group_size (" + std::to_string(m.R) + " < 2)");
         return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep "
-                                        "path for this handle: they need the int8 layout");
+                                        "path for this handle: int8 layout, or the multispin layout with overlap_cluster_mode='wolff'");
     }
+    if (want_oc && s->layout == PP_LAYOUT_MSC)
+        CUDA_TRY(cudaFuncSetAttribute(msc_houdayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_msc_smem));
     if (want_fk) {
         if (s->layout != PP_LAYOUT_INT8 || m.coupling_class == COUP_F32) {
             free_ac();
@@ -1402,7 +1408,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         CUDA_TRY(cudaMemcpyAsync(d_fk_count, counts.data(), sizeof(uint32_t) * counts.size(), cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     }
-    if (want_fk || want_oc) {
+    if (want_fk || (want_oc && s->layout == PP_LAYOUT_INT8)) {
         if ((size_t)m.N * 5 <= 200 * 1024) {  // labels (u32) + bond / activity masks (u8) in shared memory
             fk_smem_sites = m.N;
             fk_smem = (size_t)m.N * 5 + 16;
@@ -1530,7 +1536,8 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     const int64_t last = sid + batch - 1;
                     const bool rec = last >= cfg->warmup_sweeps;
                     const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
-                    if (rec || ptl || want_eq || batch >= s->max_batch) break;
+                    const bool ocl = want_oc && last % cfg->overlap_cluster_update_interval == 0;
+                    if (rec || ptl || ocl || want_eq || batch >= s->max_batch) break;
                     batch++;
                 }
             }
@@ -1607,9 +1614,16 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     s->launches++;
                 }
                 if (want_oc && stp.sid_last % cfg->overlap_cluster_update_interval == 0) {  // mod.rs:596-746
-                    houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
-                        c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,
-                        d_fk_lab, d_fk_bm);
+                    if (s->layout == PP_LAYOUT_MSC) {
+                        st = flush_swaps(s, c);  // the words must be final (the sweep launch normally consumed the last exchange)
+                        if (st != PP_OK) return st;
+                        msc_houdayer_kernel<<<(unsigned)(c.G * c.m.T * c.m.P), 256, oc_msc_smem, c.stream>>>(
+                            c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, c.m.sample_offset / 32);
+                    } else {
+                        houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
+                            c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,
+                            d_fk_lab, d_fk_bm);
+                    }
                     s->launches++;
                     CUDA_TRY(cudaGetLastError());
                     if (stp.pt_this) {  // mod.rs:748-756: the move changed the replicas' energies

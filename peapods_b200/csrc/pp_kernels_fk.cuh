@@ -205,6 +205,100 @@ houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// The same move for the multispin layout (Wolff mode): one CTA per (word group g, slot t, pair): 32 realizations at once.
+// Everything that is lane-uniform is drawn with the GROUP key (as the multispin sweeps do): the pairing of the replica ladders
+// at the slot and the per-site seed scores; the seed of lane l is its own active site with the smallest (score, site), found
+// by a per-lane scan, and the 32 clusters grow together as a bit-parallel flood fill: C |= X & (C of the 2z' neighbours) until
+// nothing changes.  Flipping the cluster in both replicas is an XOR of the two systems' words with C.
+// shared memory (u32 words): X[N] active masks | C[N] cluster masks | score[N] (by logical site) | nbr16[N * 2z'] (u16).
+__global__ void __launch_bounds__(256)
+msc_houdayer_kernel(ModelView m, uint32_t sweep_index, int64_t group_offset) {
+    extern __shared__ __align__(16) uint32_t fk_sm[];
+    __shared__ unsigned long long best_sh[8][32];
+    __shared__ int pair_sh[2];
+    const int64_t N = m.N;
+    const int z2 = 2 * m.z, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t *X = fk_sm, *Cm = fk_sm + N, *score = fk_sm + 2 * N;
+    uint16_t *nb = reinterpret_cast<uint16_t *>(fk_sm + 3 * N);
+    const int pg = (int)(blockIdx.x % m.P);
+    const int t = (int)((blockIdx.x / m.P) % m.T);
+    const int64_t g = blockIdx.x / ((int64_t)m.P * m.T);
+    const uint64_t key = msc_group_key(m.seed, (uint64_t)(group_offset + g));
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    const uint32_t stream = (uint32_t)(t * m.P + pg);
+    if (tid == 0) {  // overlap.rs:45-49: the slot's replica ladders, shuffled (the same pairing for the 32 lanes)
+        int idx[64];
+        for (int k = 0; k < m.R; k++) idx[k] = k;
+        for (int i = m.R - 1; i >= 1; i--) {
+            const u32x4 o = philox4x32_10((uint32_t)i, sweep_index, (uint32_t)t, TAG_OC_PAIR, k0, k1);
+            const int j = (int)(((uint64_t)o.x * (uint64_t)(i + 1)) >> 32);
+            const int tmp = idx[i]; idx[i] = idx[j]; idx[j] = tmp;
+        }
+        pair_sh[0] = idx[2 * pg];
+        pair_sh[1] = idx[2 * pg + 1];
+    }
+    __syncthreads();
+    uint32_t *A = m.words + ((g * m.S + (int64_t)pair_sh[0] * m.T + t) * N);
+    uint32_t *B = m.words + ((g * m.S + (int64_t)pair_sh[1] * m.T + t) * N);
+    for (int64_t i = tid; i < N; i += 256) {
+        X[i] = A[i] ^ B[i];
+        Cm[i] = 0u;
+        for (int k = 0; k < z2; k++) nb[i * z2 + k] = (uint16_t)m.nbr[(size_t)i * z2 + k];
+    }
+    for (int64_t q = tid; q < (N + 3) / 4; q += 256) {
+        const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, stream, TAG_OC_SEED, k0, k1);
+        for (int j = 0; j < 4; j++)
+            if (4 * q + j < N) score[4 * q + j] = pick(o, (uint32_t)j) >> 8;
+    }
+    __syncthreads();
+    {  // seed of lane `lane`: warp w scans its eighth of the (logical) sites
+        unsigned long long best = ~0ull;
+        const int64_t per = (N + 7) / 8, i0 = w * per, i1 = min(N, i0 + per);
+        for (int64_t i = i0; i < i1; i++) {
+            const uint32_t p = m.perm ? m.perm[i] : (uint32_t)i;
+            if ((X[p] >> lane) & 1u) {
+                const unsigned long long sc = ((unsigned long long)score[i] << 32) | (unsigned long long)i;
+                best = sc < best ? sc : best;
+            }
+        }
+        best_sh[w][lane] = best;
+    }
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long best = best_sh[0][lane];
+        for (int k = 1; k < 8; k++) best = best_sh[k][lane] < best ? best_sh[k][lane] : best;
+        if (best != ~0ull) {
+            const uint32_t site = (uint32_t)(best & 0xFFFFFFFFull);
+            atomicOr(&Cm[m.perm ? m.perm[site] : site], 1u << lane);
+        }
+    }
+    __syncthreads();
+    for (;;) {  // bit-parallel flood fill over the active sites (overlap.rs:316-327: the seed's connected component)
+        int changed = 0;
+        for (int64_t p = tid; p < N; p += 256) {
+            const uint32_t x = X[p], c = Cm[p];
+            if (x & ~c) {
+                uint32_t n = 0u;
+                for (int k = 0; k < z2; k++) n |= Cm[nb[p * z2 + k]];
+                const uint32_t c2 = c | (n & x);
+                if (c2 != c) {
+                    Cm[p] = c2;
+                    changed = 1;
+                }
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (int64_t p = tid; p < N; p += 256) {
+        const uint32_t c = Cm[p];
+        if (c) {
+            A[p] ^= c;
+            B[p] ^= c;
+        }
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace pp

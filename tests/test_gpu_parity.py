@@ -564,5 +564,23 @@ def test_houdayer_needs_two_replicas_and_the_int8_layout(oracle):
     msc, _ = make_pair(oracle, (4, 4, 8), "bimodal", [1.0, 2.0], 2, 32, layout="msc")
     before = msc.get_spins(0).copy()
     with pytest.raises(ValueError, match="not implemented on the GPU sweep path"):
-        msc.sample(4, "metropolis", overlap_cluster_update_interval=1)
+        msc.sample(4, "metropolis", overlap_cluster_update_interval=1, overlap_cluster_mode="sw")  # per-cluster coins need labels
     assert np.array_equal(msc.get_spins(0), before)
+
+
+@pytest.mark.parametrize("shape,kind,offsets,D,R,temps", [
+    ((8, 8), "bimodal", None, 40, 2, [0.7, 1.2, 2.0]),                  # generic multispin kernels, padded second word group
+    ((6, 6), "bimodal", TRI, 33, 3, [1.0, 2.5]),                        # unpaired third ladder
+    ((8, 8, 8), "bimodal", None, 45, 4, np.linspace(0.7, 1.5, 4)),      # msc3d, shuffled pairing of four ladders
+    ((16, 16, 16), "bimodal", None, 64, 4, [0.8, 1.1, 1.4]),            # headline geometry: in-sweep energy path + chunks
+])
+def test_multispin_houdayer_moves_are_bit_exact(oracle, shape, kind, offsets, D, R, temps):
+    """32 realizations per word: lane-uniform draws (pairing, seed scores) come from the group key, the clusters of the 32 lanes
+    grow as one bit-parallel flood fill; the oracle runs the realizations one by one with union-find."""
+    gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets, layout="msc")
+    for n_sweeps, interval, pt in ((12, 1, None), (16, 1, 1), (13, 3, 2)):
+        kw = dict(overlap_cluster_update_interval=interval, pt_interval=pt, pt_schedule="full_ladder" if pt == 2 else "single_random_edge")
+        rg = gpu.sample(n_sweeps, "metropolis", **kw)
+        rc = cpu.sample(n_sweeps, "metropolis", **kw)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)

@@ -17,6 +17,8 @@ pt = None if os.environ.get("KB_NOPT") else 1
 J = bench.make_couplings(0, D, D)
 sim = pb.IsingSimulation(list(bench.SHAPE), J, bench.temperatures(), 4, None, bench.dynamics_seed(), layout="msc")
 kw = dict(pt_interval=pt, pt_schedule="single_random_edge", warmup_ratio=warm, per_sample=False)
+if os.environ.get("KB_HOUDAYER"):  # Houdayer move every KB_HOUDAYER sweeps (the reference's spin-glass recipe)
+    kw["overlap_cluster_update_interval"] = int(os.environ["KB_HOUDAYER"])
 for _ in range(2):
     sim.sample(n, "metropolis", **kw)
 ms = []
