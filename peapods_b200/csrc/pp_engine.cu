@@ -488,10 +488,10 @@ static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags);
 template <int RPC, bool METRO, int NH, int NFIX = 0>
 static pp_status launch_msc3d_t(pp_sim *s, Ctx &c, const ModelView &m, uint32_t sweep_index, int n_sweeps,
                                 bool want_energy, bool want_mags, bool want_overlap, bool want_fold) {
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
+    if (s->device < 0 || s->device >= 64 || !configured[s->device]) {
         CUDA_TRY(cudaFuncSetAttribute(msc3d_kernel<RPC, METRO, NH, NFIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        if (s->device >= 0 && s->device < 64) configured[s->device] = true;
     }
     const unsigned grid = (unsigned)(c.G * ((m.T + NH - 1) / NH));
     msc3d_kernel<RPC, METRO, NH, NFIX><<<grid, MSC3D_NTH * NH, s->msc3d_smem, c.stream>>>(
