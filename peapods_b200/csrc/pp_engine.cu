@@ -212,6 +212,7 @@ struct pp_sim {
     SlabState *slab = nullptr;                         // PP_LAYOUT_SLAB (pp_slab.cuh)
     bool rows = false;                                 // int8 layout through the per-row stride tables (pp_kernels_rows.cuh)
     bool resident = false;                             // small realizations: one CTA per realization, many sweeps per launch
+    uint16_t *d_nbr16 = nullptr;                       // storage-space neighbour table as u16 (multispin Houdayer move), built on first use
     bool rows_esw = false;                             // two-colour lattice: the last colour pass also delivers the energies
     float rows_escale = 1.0f;                          // fp32 couplings: fixed-point unit of the in-sweep bond sums (power of two)
     size_t resident_smem = 0;
@@ -342,6 +343,7 @@ static void free_sim(pp_sim *s) {
         if (p) pool_free(s, p);
     for (void *b : s->rows_bufs) pool_free(s, b);
     if (s->d_keys) pool_free(s, s->d_keys);
+    if (s->d_nbr16) pool_free(s, s->d_nbr16);
     if (s->d_rows_acc) pool_free(s, s->d_rows_acc);
     if (s->d_rows_arrive) pool_free(s, s->d_rows_arrive);
     if (s->slab) {
@@ -1389,8 +1391,17 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep "
                                         "path for this handle: int8 layout, or the multispin layout with overlap_cluster_mode='wolff'");
     }
-    if (want_oc && s->layout == PP_LAYOUT_MSC)
-        CUDA_TRY(cudaFuncSetAttribute(msc_houdayer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_msc_smem));
+    if (want_oc && s->layout == PP_LAYOUT_MSC) {
+        CUDA_TRY(cudaFuncSetAttribute(msc_houdayer_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_msc_smem));
+        CUDA_TRY(cudaFuncSetAttribute(msc_houdayer_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_msc_smem));
+        CUDA_TRY(cudaFuncSetAttribute(msc_houdayer_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_msc_smem));
+        if (!s->d_nbr16) {
+            const int64_t n = m.N * 2 * m.z;
+            CUDA_TRY(pool_alloc(s, (void **)&s->d_nbr16, sizeof(uint16_t) * (size_t)n));
+            nbr_to_u16_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(m.nbr, s->d_nbr16, n);
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+        }
+    }
     if (want_fk) {
         if (s->layout != PP_LAYOUT_INT8 || m.coupling_class == COUP_F32) {
             free_ac();
@@ -1617,8 +1628,11 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     if (s->layout == PP_LAYOUT_MSC) {
                         st = flush_swaps(s, c);  // the words must be final (the sweep launch normally consumed the last exchange)
                         if (st != PP_OK) return st;
-                        msc_houdayer_kernel<<<(unsigned)(c.G * c.m.T * c.m.P), 256, oc_msc_smem, c.stream>>>(
-                            c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, c.m.sample_offset / 32);
+                        const unsigned oc_grid = (unsigned)(c.G * c.m.T * c.m.P);
+                        const uint32_t oc_sweep = stp.sweep_index + (uint32_t)stp.batch - 1u;
+                        if (c.m.z == 3) msc_houdayer_kernel<3><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, oc_sweep, c.m.sample_offset / 32);
+                        else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, oc_sweep, c.m.sample_offset / 32);
+                        else msc_houdayer_kernel<0><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, oc_sweep, c.m.sample_offset / 32);
                     } else {
                         houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
                             c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,

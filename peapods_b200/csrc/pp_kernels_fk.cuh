@@ -213,13 +213,21 @@ houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites
 // by a per-lane scan, and the 32 clusters grow together as a bit-parallel flood fill: C |= X & (C of the 2z' neighbours) until
 // nothing changes.  Flipping the cluster in both replicas is an XOR of the two systems' words with C.
 // shared memory (u32 words): X[N] active masks | C[N] cluster masks | score[N] (by logical site) | nbr16[N * 2z'] (u16).
+__global__ void nbr_to_u16_kernel(const uint32_t *nbr, uint16_t *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint16_t)nbr[i];
+}
+
+// ZT > 0: the number of forward directions is the compile-time constant ZT (the neighbour gathers unroll); 0: any z'.
+// nbr16 = the storage-space neighbour table as u16 [N][2z'] (built once per handle; N <= 65536).
+template <int ZT>
 __global__ void __launch_bounds__(256)
-msc_houdayer_kernel(ModelView m, uint32_t sweep_index, int64_t group_offset) {
+msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, uint32_t sweep_index, int64_t group_offset) {
     extern __shared__ __align__(16) uint32_t fk_sm[];
     __shared__ unsigned long long best_sh[8][32];
     __shared__ int pair_sh[2];
     const int64_t N = m.N;
-    const int z2 = 2 * m.z, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int z2 = ZT > 0 ? 2 * ZT : 2 * m.z, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint32_t *X = fk_sm, *Cm = fk_sm + N, *score = fk_sm + 2 * N;
     uint16_t *nb = reinterpret_cast<uint16_t *>(fk_sm + 3 * N);
     const int pg = (int)(blockIdx.x % m.P);
@@ -245,7 +253,11 @@ msc_houdayer_kernel(ModelView m, uint32_t sweep_index, int64_t group_offset) {
     for (int64_t i = tid; i < N; i += 256) {
         X[i] = A[i] ^ B[i];
         Cm[i] = 0u;
-        for (int k = 0; k < z2; k++) nb[i * z2 + k] = (uint16_t)m.nbr[(size_t)i * z2 + k];
+    }
+    {  // the neighbour table: N * 2z' u16 = a multiple of 4 bytes (N is even in every multispin layout)
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(nbr16);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(nb);
+        for (int64_t i = tid; i < N * z2 / 2; i += 256) dst[i] = __ldg(src + i);
     }
     for (int64_t q = tid; q < (N + 3) / 4; q += 256) {
         const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, stream, TAG_OC_SEED, k0, k1);
@@ -281,7 +293,9 @@ msc_houdayer_kernel(ModelView m, uint32_t sweep_index, int64_t group_offset) {
             const uint32_t x = X[p], c = Cm[p];
             if (x & ~c) {
                 uint32_t n = 0u;
-                for (int k = 0; k < z2; k++) n |= Cm[nb[p * z2 + k]];
+#pragma unroll
+                for (int k = 0; k < (ZT > 0 ? 2 * ZT : 16); k++)
+                    if (k < z2) n |= Cm[nb[p * z2 + k]];
                 const uint32_t c2 = c | (n & x);
                 if (c2 != c) {
                     Cm[p] = c2;
