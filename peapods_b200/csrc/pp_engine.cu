@@ -212,6 +212,7 @@ struct pp_sim {
     SlabState *slab = nullptr;                         // PP_LAYOUT_SLAB (pp_slab.cuh)
     bool rows = false;                                 // int8 layout through the per-row stride tables (pp_kernels_rows.cuh)
     bool resident = false;                             // small realizations: one CTA per realization, many sweeps per launch
+    uint16_t *d_site16 = nullptr;                      // storage index -> logical site (same use)
     uint16_t *d_nbr16 = nullptr;                       // storage-space neighbour table as u16 (multispin Houdayer move), built on first use
     bool rows_esw = false;                             // two-colour lattice: the last colour pass also delivers the energies
     float rows_escale = 1.0f;                          // fp32 couplings: fixed-point unit of the in-sweep bond sums (power of two)
@@ -344,6 +345,7 @@ static void free_sim(pp_sim *s) {
     for (void *b : s->rows_bufs) pool_free(s, b);
     if (s->d_keys) pool_free(s, s->d_keys);
     if (s->d_nbr16) pool_free(s, s->d_nbr16);
+    if (s->d_site16) pool_free(s, s->d_site16);
     if (s->d_rows_acc) pool_free(s, s->d_rows_acc);
     if (s->d_rows_arrive) pool_free(s, s->d_rows_arrive);
     if (s->slab) {
@@ -1399,6 +1401,11 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             const int64_t n = m.N * 2 * m.z;
             CUDA_TRY(pool_alloc(s, (void **)&s->d_nbr16, sizeof(uint16_t) * (size_t)n));
             nbr_to_u16_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(m.nbr, s->d_nbr16, n);
+            std::vector<uint16_t> site16((size_t)m.N);
+            const bool permuted = s->plan.compact && !s->plan.perm.empty();
+            for (int64_t i = 0; i < m.N; i++) site16[permuted ? s->plan.perm[(size_t)i] : (size_t)i] = (uint16_t)i;
+            CUDA_TRY(pool_alloc(s, (void **)&s->d_site16, sizeof(uint16_t) * (size_t)m.N));
+            CUDA_TRY(cudaMemcpyAsync(s->d_site16, site16.data(), sizeof(uint16_t) * (size_t)m.N, cudaMemcpyHostToDevice, s->stream));
             CUDA_TRY(cudaStreamSynchronize(s->stream));
         }
     }
@@ -1630,9 +1637,9 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                         if (st != PP_OK) return st;
                         const unsigned oc_grid = (unsigned)(c.G * c.m.T * c.m.P);
                         const uint32_t oc_sweep = stp.sweep_index + (uint32_t)stp.batch - 1u;
-                        if (c.m.z == 3) msc_houdayer_kernel<3><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, oc_sweep, c.m.sample_offset / 32);
-                        else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, oc_sweep, c.m.sample_offset / 32);
-                        else msc_houdayer_kernel<0><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, oc_sweep, c.m.sample_offset / 32);
+                        if (c.m.z == 3) msc_houdayer_kernel<3><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
+                        else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
+                        else msc_houdayer_kernel<0><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
                     } else {
                         houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
                             c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,

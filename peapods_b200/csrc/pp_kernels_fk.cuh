@@ -222,7 +222,8 @@ __global__ void nbr_to_u16_kernel(const uint32_t *nbr, uint16_t *out, int64_t n)
 // nbr16 = the storage-space neighbour table as u16 [N][2z'] (built once per handle; N <= 65536).
 template <int ZT>
 __global__ void __launch_bounds__(256)
-msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, uint32_t sweep_index, int64_t group_offset) {
+msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /* [N] storage index -> site */, uint32_t sweep_index,
+                    int64_t group_offset) {
     extern __shared__ __align__(16) uint32_t fk_sm[];
     __shared__ unsigned long long best_sh[8][32];
     __shared__ int pair_sh[2];
@@ -259,19 +260,19 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, uint32_t sweep_index, in
         uint32_t *dst = reinterpret_cast<uint32_t *>(nb);
         for (int64_t i = tid; i < N * z2 / 2; i += 256) dst[i] = __ldg(src + i);
     }
-    for (int64_t q = tid; q < (N + 3) / 4; q += 256) {
+    for (int64_t q = tid; q < (N + 3) / 4; q += 256) {  // scores are drawn per logical site and kept by storage position
         const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, stream, TAG_OC_SEED, k0, k1);
         for (int j = 0; j < 4; j++)
-            if (4 * q + j < N) score[4 * q + j] = pick(o, (uint32_t)j) >> 8;
+            if (4 * q + j < N) score[m.perm ? m.perm[4 * q + j] : (uint32_t)(4 * q + j)] = pick(o, (uint32_t)j) >> 8;
     }
     __syncthreads();
-    {  // seed of lane `lane`: warp w scans its eighth of the (logical) sites
+    {  // seed of lane `lane`: warp w scans its eighth of the words (every lane of the warp reads the same word: broadcasts)
         unsigned long long best = ~0ull;
-        const int64_t per = (N + 7) / 8, i0 = w * per, i1 = min(N, i0 + per);
-        for (int64_t i = i0; i < i1; i++) {
-            const uint32_t p = m.perm ? m.perm[i] : (uint32_t)i;
+        const int64_t per = (N + 7) / 8, p0 = w * per, p1 = min(N, p0 + per);
+#pragma unroll 4
+        for (int64_t p = p0; p < p1; p++) {
             if ((X[p] >> lane) & 1u) {
-                const unsigned long long sc = ((unsigned long long)score[i] << 32) | (unsigned long long)i;
+                const unsigned long long sc = ((unsigned long long)score[p] << 32) | (unsigned long long)__ldg(site16 + p);
                 best = sc < best ? sc : best;
             }
         }
