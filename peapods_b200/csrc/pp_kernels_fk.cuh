@@ -266,17 +266,50 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
             if (4 * q + j < N) score[m.perm ? m.perm[4 * q + j] : (uint32_t)(4 * q + j)] = pick(o, (uint32_t)j) >> 8;
     }
     __syncthreads();
-    {  // seed of lane `lane`: warp w scans its eighth of the words (every lane of the warp reads the same word: broadcasts)
-        unsigned long long best = ~0ull;
-        const int64_t per = (N + 7) / 8, p0 = w * per, p1 = min(N, p0 + per);
-#pragma unroll 4
-        for (int64_t p = p0; p < p1; p++) {
-            if ((X[p] >> lane) & 1u) {
-                const unsigned long long sc = ((unsigned long long)score[p] << 32) | (unsigned long long)__ldg(site16 + p);
-                best = sc < best ? sc : best;
-            }
+    // Seed of lane `lane` = its active site with the smallest (score, site).  The scores are lane-uniform, so the few hundred
+    // lowest-score positions are collected once and every lane looks for its first active one among them; a lane that has no
+    // active site there (few active sites at all) falls back to scanning every word.
+    __shared__ uint32_t cand_n;
+    __shared__ uint16_t cand[1024];
+    if (tid == 0) cand_n = 0u;
+    __syncthreads();
+    const uint32_t cut = (uint32_t)min((int64_t)(1 << 24), ((int64_t)256 << 24) / N);  // expect ~256 candidates
+    for (int64_t p = tid; p < N; p += 256)
+        if (score[p] < cut) {
+            const uint32_t k = atomicAdd(&cand_n, 1u);
+            if (k < 1024u) cand[k] = (uint16_t)p;
         }
+    __syncthreads();
+    {
+        unsigned long long best = ~0ull;
+        const uint32_t n_cand = cand_n;
+        if (n_cand <= 1024u)
+            for (uint32_t k = w; k < n_cand; k += 8) {
+                const uint32_t p = cand[k];
+                if ((X[p] >> lane) & 1u) {
+                    const unsigned long long sc = ((unsigned long long)score[p] << 32) | (unsigned long long)__ldg(site16 + p);
+                    best = sc < best ? sc : best;
+                }
+            }
         best_sh[w][lane] = best;
+    }
+    __syncthreads();
+    {  // fallback: lanes without a candidate (warp-uniform test, so whole warps skip the scan)
+        unsigned long long have = ~0ull;
+        for (int k = 0; k < 8; k++) have = best_sh[k][lane] < have ? best_sh[k][lane] : have;
+        const bool need = have == ~0ull;
+        __syncthreads();  // every warp has read the candidate minima before anyone overwrites its slot
+        if (__any_sync(0xFFFFFFFFu, need)) {
+            unsigned long long best = ~0ull;
+            const int64_t per = (N + 7) / 8, p0 = w * per, p1 = min(N, p0 + per);
+            for (int64_t p = p0; p < p1; p++) {
+                if (need && ((X[p] >> lane) & 1u)) {
+                    const unsigned long long sc = ((unsigned long long)score[p] << 32) | (unsigned long long)__ldg(site16 + p);
+                    best = sc < best ? sc : best;
+                }
+            }
+            if (need) best_sh[w][lane] = best;
+        }
     }
     __syncthreads();
     if (w == 0) {
