@@ -584,3 +584,29 @@ def test_multispin_houdayer_moves_are_bit_exact(oracle, shape, kind, offsets, D,
         rc = cpu.sample(n_sweeps, "metropolis", **kw)
         assert_state_equal(gpu, cpu, D)
         assert_results_equal(rg, rc)
+
+
+def test_multispin_houdayer_with_few_active_sites(oracle):
+    """Replicas that start identical and move at low temperature differ at a handful of sites: most lanes find no active site among the
+    low-score candidates and take the full-scan fallback (or have no active site at all: the move is skipped for them)."""
+    import ctypes as C
+
+    shape, temps, R, D = (16, 16, 16), [0.45, 0.5], 2, 40
+    gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, D, layout="msc")
+    S, N = R * len(temps), int(np.prod(shape))
+    for d in range(D):
+        spins = gpu.get_spins(d).reshape(S, N).copy()
+        spins[:] = spins[0]                                   # every system of the realization starts from the same configuration
+        gpu.set_spins(spins.reshape(-1), d)
+        ptr = oracle.lib().orc_sim_spins(cpu.h, d)
+        np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int8)), shape=(S * N,))[:] = spins.reshape(-1)
+    assert_state_equal(gpu, cpu, D)
+    n_active = []
+    for n_sweeps in (1, 3, 6):
+        rg = gpu.sample(n_sweeps, "metropolis", overlap_cluster_update_interval=1, pt_interval=2)
+        rc = cpu.sample(n_sweeps, "metropolis", overlap_cluster_update_interval=1, pt_interval=2)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        sp = gpu.get_spins(0).reshape(S, N)
+        n_active.append(int(np.sum(sp[0] != sp[len(temps)])))
+    assert 0 < max(n_active) < 200, n_active                    # the regime the test is about
