@@ -828,9 +828,12 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         // dots, and (want_fold) the recorded-sweep fold of simulation/mod.rs:543-578 + statistics/overlap.rs:283-306
         const int64_t d = g * 32 + lane;
         if (w == 0 && d < m.D) {
-            float Ev[RPC];
-            long long Mv[RPC], Sv[NP > 0 ? NP : 1], Lv[NP > 0 ? NP : 1];
-#pragma unroll
+            // Rolled loops on purpose: this runs once per CTA on one warp; unrolled (with four inlined f32 divisions per replica)
+            // it was ~1200 instructions of straight-line code streaming through the instruction cache the hot loops need.
+            // Same values, same order of the f64 reductions as fold_red (pp_kernels_stats.cuh): replica-major, then pair-major.
+            const float nf = (float)m.N, nb = (float)(m.N * m.z);
+            double *sums = st.sums + d * 11 * m.T + t;
+#pragma unroll 1
             for (int r = 0; r < RPC; r++) {
                 uint32_t e = 0, dn = 0;
                 for (int k = 0; k < fin_wpe; k++) {
@@ -838,30 +841,51 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                     if (want_mags) dn += fin_e[((r * 2 + 1) * fin_wpe + k) * 32 + lane];
                 }
                 // sum_i sum_d s s J = (#bonds) - 2 * unsatisfied, e = that / N in f32   (energy.rs:103-108)
-                Ev[r] = __fdiv_rn((float)(3ll * N - 2ll * e), (float)N);
-                Mv[r] = (long long)N - 2ll * dn;
+                const float ev = __fdiv_rn((float)(3ll * N - 2ll * e), (float)N);
+                const long long mv = (long long)N - 2ll * dn;
                 const int sys = m.system_ids[d * m.S + r * m.T + t];
-                if (want_energy) m.energies[d * m.S + sys] = Ev[r];
-                if (want_mags) m.mags[d * m.S + sys] = Mv[r];
+                if (want_energy) m.energies[d * m.S + sys] = ev;
+                if (want_mags) m.mags[d * m.S + sys] = mv;
+                if (want_fold) {  // simulation/mod.rs:555-578
+                    const float mag = __fdiv_rn((float)mv, nf);
+                    const float m2 = __fmul_rn(mag, mag);
+                    atomicAdd(sums + 0 * m.T, (double)mag);
+                    atomicAdd(sums + 1 * m.T, (double)m2);
+                    atomicAdd(sums + 2 * m.T, (double)__fmul_rn(m2, m2));
+                    atomicAdd(sums + 3 * m.T, (double)ev);
+                    atomicAdd(sums + 4 * m.T, __dmul_rn((double)ev, (double)ev));
+                }
             }
             if (NP > 0 && want_overlap) {
-#pragma unroll
+                const int64_t bins = m.N + 1;
+#pragma unroll 1
                 for (int p = 0; p < NP; p++) {
                     uint32_t cs = 0, cl = 0;
                     for (int k = 0; k < fin_wpp; k++) {
                         cs += fin_p[((p * 2 + 0) * fin_wpp + k) * 32 + lane];
                         cl += fin_p[((p * 2 + 1) * fin_wpp + k) * 32 + lane];
                     }
-                    Sv[p] = (long long)N - 2ll * cs;
-                    Lv[p] = 3ll * N - 2ll * cl;
+                    const long long sv = (long long)N - 2ll * cs, lv = 3ll * N - 2ll * cl;
                     const int64_t o = (d * m.P + p) * m.T + t;
-                    dot_spin[o] = Sv[p];
-                    dot_link[o] = Lv[p];
+                    dot_spin[o] = sv;
+                    dot_link[o] = lv;
+                    if (want_fold) {  // statistics/overlap.rs:283-306 + :318-324
+                        const float ql = __fdiv_rn((float)lv, nb);
+                        const float q = __fdiv_rn((float)sv, nf);
+                        const float q2 = __fmul_rn(q, q);
+                        const float ql2 = __fmul_rn(ql, ql);
+                        atomicAdd(sums + 5 * m.T, (double)q);
+                        atomicAdd(sums + 6 * m.T, (double)q2);
+                        atomicAdd(sums + 7 * m.T, (double)__fmul_rn(q2, q2));
+                        atomicAdd(sums + 8 * m.T, (double)ql);
+                        atomicAdd(sums + 9 * m.T, (double)ql2);
+                        atomicAdd(sums + 10 * m.T, (double)__fmul_rn(ql2, ql2));
+                        const int64_t h = (d * m.T + t) * bins + (sv + m.N) / 2;
+                        atomicAdd(st.hist + h, 1u);
+                        atomicAdd(st.ql_at_q + h, (double)ql);
+                        atomicAdd(st.ql2_at_q + h, (double)ql2);
+                    }
                 }
-            }
-            if (want_fold) {
-                if (NP > 0 && want_overlap) fold_red<RPC, NP>(m, st, d, t, Mv, Ev, Sv, Lv);
-                else fold_red<RPC, 0>(m, st, d, t, Mv, Ev, Sv, Lv);
             }
         }
     }
