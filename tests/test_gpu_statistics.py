@@ -118,3 +118,65 @@ def test_slab_lattice_3d_ising_energy_near_tc():
         res.append(sim.sample(3000, "metropolis", warmup_ratio=0.5)["energies"][0])
     assert res[0] == res[1]
     assert 0.96 < res[0] < 1.08, res
+
+
+# ---- cluster moves against exact enumeration: the oracle shares their algorithm, the partition function does not ----
+@pytest.mark.parametrize("cluster_mode", ["sw", "wolff"])
+def test_4x4_ising_with_fk_cluster_updates_matches_exact_enumeration(cluster_mode):
+    """Metropolis sweeps + a Fortuin-Kasteleyn update after every sweep (clusters/fk.rs): a wrong bond probability or a biased
+    cluster coin breaks detailed balance and shows up in <e>, <e^2>, <m^2>, <m^4> around T_c."""
+    import peapods_b200 as pb
+
+    temps = np.asarray([1.5, 2.269, 3.5], np.float32)
+    exact = exact_2d_ising(4, temps.astype(np.float64))
+    runs = []
+    for seed in range(12):
+        sim = pb.Ising((4, 4), "ferro", temps, n_replicas=1, seed=300 + seed, layout="int8")
+        r = sim.sample(20000, "metropolis", warmup_ratio=0.1, cluster_update_interval=1, cluster_mode=cluster_mode)
+        runs.append(np.stack([r["energies"], r["energies2"], r["mags2"], r["mags4"]], axis=1))
+    z = zscores(np.array(runs), exact)
+    assert np.abs(z).max() < 3.5, z
+    assert abs(z.mean()) < 2.0, z
+
+
+def exact_2d_pm_j(J, temps):
+    """<e>, <e^2>, <q^2> of one 4 x 4 +-J instance (two independent replicas: <q^2> = sum_ij <s_i s_j>^2 / N^2)."""
+    L = J.shape[0]
+    n = L * L
+    states = np.array(list(itertools.product([-1, 1], repeat=n)), dtype=np.int8).reshape(-1, L, L)
+    bonds = (states * np.roll(states, -1, axis=1) * J[None, :, :, 0]).sum(axis=(1, 2)) + \
+            (states * np.roll(states, -1, axis=2) * J[None, :, :, 1]).sum(axis=(1, 2))
+    e = bonds / n
+    flat = states.reshape(-1, n).astype(np.float64)
+    out = []
+    for t in temps:
+        w = np.exp((bonds - bonds.max()) / t)
+        w /= w.sum()
+        corr = flat.T @ (flat * w[:, None])
+        out.append(((w * e).sum(), (w * e * e).sum(), (corr ** 2).sum() / n ** 2))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("layout,oc_mode", [("int8", "wolff"), ("int8", "sw"), ("msc", "wolff")])
+def test_4x4_spin_glass_with_houdayer_moves_matches_exact_enumeration(layout, oc_mode):
+    """Metropolis + PT + the Houdayer move after every sweep on one +-J instance: the move must leave the product of the two
+    replicas' Boltzmann weights invariant, so <e>, <e^2> and <q^2> stay at their exact values."""
+    import peapods_b200 as pb
+
+    rng = np.random.default_rng(5)
+    J = (2 * rng.integers(0, 2, size=(4, 4, 2)) - 1).astype(np.float32)
+    temps = np.asarray([0.9, 1.6, 2.6], np.float32)
+    exact = exact_2d_pm_j(J.astype(np.float64), temps.astype(np.float64))
+    # multispin words hold 32 realizations: 32 copies of the instance.  They share every draw and every coupling, so their
+    # trajectories coalesce: one run is ONE independent estimate, whatever the number of lanes.
+    D = 32 if layout == "msc" else 1
+    coup = np.broadcast_to(J, (D,) + J.shape).copy() if D > 1 else J
+    runs = []
+    for seed in range(10):
+        sim = pb.IsingSimulation([4, 4], coup, temps, 2, None, 700 + seed, layout=layout)
+        r = sim.sample(12000, "metropolis", pt_interval=1, warmup_ratio=0.1, overlap_cluster_update_interval=1,
+                       overlap_cluster_mode=oc_mode)
+        runs.append(np.stack([r["energies"], r["energies2"], r["overlap2"]], axis=1))
+    z = zscores(np.array(runs), exact)
+    assert np.abs(z).max() < 3.5, z
+    assert abs(z.mean()) < 2.0, z
