@@ -146,6 +146,9 @@ typedef struct {
 
 const char *pp_last_error(void);
 int32_t pp_abi_version(void);
+/* sizeof(pp_model_desc / pp_sample_cfg / pp_results) as this library was compiled (which = 0 / 1 / 2): lets a binding that declares
+ * the structs by hand (ctypes, a Rust #[repr(C)] block) check its layout at load time */
+int64_t pp_struct_size(int32_t which);
 
 /* host-only helpers (no GPU needed) */
 pp_status pp_colouring(int32_t n_dims, const int64_t *shape, int32_t n_offsets, const int64_t *offsets,

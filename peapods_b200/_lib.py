@@ -85,6 +85,7 @@ ON_SWEEP = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64)
 SIGNATURES = {
     "pp_last_error": (C.c_char_p, []),
     "pp_abi_version": (C.c_int32, []),
+    "pp_struct_size": (C.c_int64, [C.c_int32]),
     "pp_equil_checkpoints": (C.c_int32, [C.c_int64, C.POINTER(C.c_int64)]),
     "pp_colouring": (C.c_int32, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "pp_metropolis_lookup": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -127,6 +128,10 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.pp_abi_version() != 3:
         raise ImportError("libpeapods_b200.so ABI version mismatch")
+    for which, struct in enumerate((ModelDesc, SampleCfg, Results)):
+        if lib.pp_struct_size(which) != C.sizeof(struct):
+            raise ImportError(f"libpeapods_b200.so: layout of {struct.__name__} differs from include/peapods_b200.h "
+                              f"({lib.pp_struct_size(which)} vs {C.sizeof(struct)} bytes)")
     _lib = lib
     return lib
 

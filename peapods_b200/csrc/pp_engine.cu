@@ -40,6 +40,14 @@ static pp_status fail(pp_status st, const std::string &msg) {
 }
 extern "C" const char *pp_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t pp_abi_version(void) { return PP_ABI_VERSION; }
+extern "C" int64_t pp_struct_size(int32_t which) {
+    switch (which) {
+        case 0: return (int64_t)sizeof(pp_model_desc);
+        case 1: return (int64_t)sizeof(pp_sample_cfg);
+        case 2: return (int64_t)sizeof(pp_results);
+    }
+    return -1;
+}
 
 #define CUDA_TRY(expr)                                                                              \
     do {                                                                                            \
