@@ -610,3 +610,22 @@ def test_multispin_houdayer_with_few_active_sites(oracle):
         sp = gpu.get_spins(0).reshape(S, N)
         n_active.append(int(np.sum(sp[0] != sp[len(temps)])))
     assert 0 < max(n_active) < 200, n_active                    # the regime the test is about
+
+
+def test_chunked_multistream_execution_of_the_widened_features_is_bit_exact(oracle, monkeypatch):
+    """Autocorrelation pushes, equilibration sums and Houdayer moves run per chunk on the chunk's stream with offset views of their
+    accumulators: five word groups in chunks of one or two over three streams must reproduce the unchunked oracle."""
+    monkeypatch.setenv("PP_STREAMS", "3")
+    monkeypatch.setenv("PP_CHUNK_GROUPS", "2")
+    monkeypatch.setenv("PP_MACRO_BATCH", "4")
+    shape, temps, R, D = (4, 4, 8), np.linspace(0.8, 1.6, 5), 4, 150   # 5 word groups, the last one padded
+    gpu, cpu = make_pair(oracle, shape, "bimodal", temps, R, D, layout="msc")
+    assert gpu.uses_msc3d
+    for n_sweeps, interval in ((140, 1), (37, 3)):
+        kw = dict(pt_interval=interval, autocorrelation_max_lag=6, equilibration_diagnostic=True, overlap_cluster_update_interval=2)
+        rg = gpu.sample(n_sweeps, "metropolis", **kw)
+        rc = cpu.sample(n_sweeps, "metropolis", **kw)
+        assert_state_equal(gpu, cpu, D)
+        assert_results_equal(rg, rc)
+        assert np.array_equal(gpu.last_per_sample_taus, cpu.last_per_sample_taus)
+        assert np.array_equal(gpu.last_per_sample_equil, cpu.last_per_sample_equil)
