@@ -543,11 +543,13 @@ def test_cluster_updates_need_the_int8_layout_and_unit_couplings(oracle):
     ((8, 8), "gaussian", TRI, [0.8, 1.6], 3, 2),                        # unpaired third replica; no couplings involved
     ((5, 7), "bimodal", None, [0.8, 2.5], 2, 1),
     ((64, 64), "bimodal", None, [0.6, 1.2], 2, 1),                      # 4096 sites: 2-D spin glass, large overlap clusters
+    ((256, 256), "bimodal", None, [0.7, 1.3], 2, 1),                    # 65 536 sites: labels in global scratch
 ])
 def test_houdayer_moves_are_bit_exact(oracle, oc_mode, shape, kind, offsets, temps, R, D):
     gpu, cpu = make_pair(oracle, shape, kind, temps, R, D, offsets)
     gaussian = kind == "gaussian"
-    for n_sweeps, interval, pt in ((30, 1, None), (24, 1, 1), (25, 3, 2)):
+    big = int(np.prod(shape)) > 10000
+    for n_sweeps, interval, pt in ((5, 1, None), (6, 1, 1), (7, 3, 2)) if big else ((30, 1, None), (24, 1, 1), (25, 3, 2)):
         pt = None if gaussian else pt  # f32 energies are tolerance-checked: PT (which branches on them) stays off there
         kw = dict(overlap_cluster_update_interval=interval, overlap_cluster_mode=oc_mode, pt_interval=pt)
         rg = gpu.sample(n_sweeps, "metropolis", exact_log=True, **kw)
