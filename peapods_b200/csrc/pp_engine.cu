@@ -1645,9 +1645,9 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                         if (st != PP_OK) return st;
                         const unsigned oc_grid = (unsigned)(c.G * c.m.T * c.m.P);
                         const uint32_t oc_sweep = stp.sweep_index + (uint32_t)stp.batch - 1u;
-                        if (c.m.z == 3) msc_houdayer_kernel<3><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
-                        else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
-                        else msc_houdayer_kernel<0><<<oc_grid, 256, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
+                        if (c.m.z == 3) msc_houdayer_kernel<3><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
+                        else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
+                        else msc_houdayer_kernel<0><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
                     } else {
                         houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
                             c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,

@@ -213,6 +213,12 @@ houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites
 // by a per-lane scan, and the 32 clusters grow together as a bit-parallel flood fill: C |= X & (C of the 2z' neighbours) until
 // nothing changes.  Flipping the cluster in both replicas is an XOR of the two systems' words with C.
 // shared memory (u32 words): X[N] active masks | C[N] cluster masks | score[N] (by logical site) | nbr16[N * 2z'] (u16).
+#ifndef PP_OC_THREADS
+#define PP_OC_THREADS 512
+#endif
+constexpr int OC_THREADS = PP_OC_THREADS;  // threads of msc_houdayer_kernel (the fill is bound by shared-memory latency: more warps)
+constexpr int OC_WARPS = OC_THREADS / 32;
+
 __global__ void nbr_to_u16_kernel(const uint32_t *nbr, uint16_t *out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint16_t)nbr[i];
@@ -221,11 +227,11 @@ __global__ void nbr_to_u16_kernel(const uint32_t *nbr, uint16_t *out, int64_t n)
 // ZT > 0: the number of forward directions is the compile-time constant ZT (the neighbour gathers unroll); 0: any z'.
 // nbr16 = the storage-space neighbour table as u16 [N][2z'] (built once per handle; N <= 65536).
 template <int ZT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(OC_THREADS)
 msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /* [N] storage index -> site */, uint32_t sweep_index,
                     int64_t group_offset) {
     extern __shared__ __align__(16) uint32_t fk_sm[];
-    __shared__ unsigned long long best_sh[8][32];
+    __shared__ unsigned long long best_sh[OC_WARPS][32];
     __shared__ int pair_sh[2];
     const int64_t N = m.N;
     const int z2 = ZT > 0 ? 2 * ZT : 2 * m.z, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -251,16 +257,16 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
     __syncthreads();
     uint32_t *A = m.words + ((g * m.S + (int64_t)pair_sh[0] * m.T + t) * N);
     uint32_t *B = m.words + ((g * m.S + (int64_t)pair_sh[1] * m.T + t) * N);
-    for (int64_t i = tid; i < N; i += 256) {
+    for (int64_t i = tid; i < N; i += OC_THREADS) {
         X[i] = A[i] ^ B[i];
         Cm[i] = 0u;
     }
     {  // the neighbour table: N * 2z' u16 = a multiple of 4 bytes (N is even in every multispin layout)
         const uint32_t *src = reinterpret_cast<const uint32_t *>(nbr16);
         uint32_t *dst = reinterpret_cast<uint32_t *>(nb);
-        for (int64_t i = tid; i < N * z2 / 2; i += 256) dst[i] = __ldg(src + i);
+        for (int64_t i = tid; i < N * z2 / 2; i += OC_THREADS) dst[i] = __ldg(src + i);
     }
-    for (int64_t q = tid; q < (N + 3) / 4; q += 256) {  // scores are drawn per logical site and kept by storage position
+    for (int64_t q = tid; q < (N + 3) / 4; q += OC_THREADS) {  // scores are drawn per logical site and kept by storage position
         const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, stream, TAG_OC_SEED, k0, k1);
         for (int j = 0; j < 4; j++)
             if (4 * q + j < N) score[m.perm ? m.perm[4 * q + j] : (uint32_t)(4 * q + j)] = pick(o, (uint32_t)j) >> 8;
@@ -274,7 +280,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
     if (tid == 0) cand_n = 0u;
     __syncthreads();
     const uint32_t cut = (uint32_t)min((int64_t)(1 << 24), ((int64_t)256 << 24) / N);  // expect ~256 candidates
-    for (int64_t p = tid; p < N; p += 256)
+    for (int64_t p = tid; p < N; p += OC_THREADS)
         if (score[p] < cut) {
             const uint32_t k = atomicAdd(&cand_n, 1u);
             if (k < 1024u) cand[k] = (uint16_t)p;
@@ -284,7 +290,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
         unsigned long long best = ~0ull;
         const uint32_t n_cand = cand_n;
         if (n_cand <= 1024u)
-            for (uint32_t k = w; k < n_cand; k += 8) {
+            for (uint32_t k = w; k < n_cand; k += OC_WARPS) {
                 const uint32_t p = cand[k];
                 if ((X[p] >> lane) & 1u) {
                     const unsigned long long sc = ((unsigned long long)score[p] << 32) | (unsigned long long)__ldg(site16 + p);
@@ -296,12 +302,12 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
     __syncthreads();
     {  // fallback: lanes without a candidate (warp-uniform test, so whole warps skip the scan)
         unsigned long long have = ~0ull;
-        for (int k = 0; k < 8; k++) have = best_sh[k][lane] < have ? best_sh[k][lane] : have;
+        for (int k = 0; k < OC_WARPS; k++) have = best_sh[k][lane] < have ? best_sh[k][lane] : have;
         const bool need = have == ~0ull;
         __syncthreads();  // every warp has read the candidate minima before anyone overwrites its slot
         if (__any_sync(0xFFFFFFFFu, need)) {
             unsigned long long best = ~0ull;
-            const int64_t per = (N + 7) / 8, p0 = w * per, p1 = min(N, p0 + per);
+            const int64_t per = (N + OC_WARPS - 1) / OC_WARPS, p0 = w * per, p1 = min(N, p0 + per);
             for (int64_t p = p0; p < p1; p++) {
                 if (need && ((X[p] >> lane) & 1u)) {
                     const unsigned long long sc = ((unsigned long long)score[p] << 32) | (unsigned long long)__ldg(site16 + p);
@@ -314,7 +320,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
     __syncthreads();
     if (w == 0) {
         unsigned long long best = best_sh[0][lane];
-        for (int k = 1; k < 8; k++) best = best_sh[k][lane] < best ? best_sh[k][lane] : best;
+        for (int k = 1; k < OC_WARPS; k++) best = best_sh[k][lane] < best ? best_sh[k][lane] : best;
         if (best != ~0ull) {
             const uint32_t site = (uint32_t)(best & 0xFFFFFFFFull);
             atomicOr(&Cm[m.perm ? m.perm[site] : site], 1u << lane);
@@ -323,7 +329,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
     __syncthreads();
     for (;;) {  // bit-parallel flood fill over the active sites (overlap.rs:316-327: the seed's connected component)
         int changed = 0;
-        for (int64_t p = tid; p < N; p += 256) {
+        for (int64_t p = tid; p < N; p += OC_THREADS) {
             const uint32_t x = X[p], c = Cm[p];
             if (x & ~c) {
                 uint32_t n = 0u;
@@ -339,7 +345,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
         }
         if (!__syncthreads_or(changed)) break;
     }
-    for (int64_t p = tid; p < N; p += 256) {
+    for (int64_t p = tid; p < N; p += OC_THREADS) {
         const uint32_t c = Cm[p];
         if (c) {
             A[p] ^= c;
