@@ -289,7 +289,7 @@ def run_ours(args):
                 "kernel": "msc3d_kernel (sweep + energy / magnetisation / overlap / fold)", "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes_per_launch, "launches_timed": k_n, "kernel_ms_mean": k_ms / k_n,
                 "kernel_share_of_step": k_ms / max(sim.last_sweep_loop_ms, 1e-9)}
-    # ---- context figure (untimed leg, same handle): sweeps alone -- no PT, nothing recorded, 64 sweeps per launch.  This is
+    # ---- context figure (untimed leg, same handle): sweeps alone -- no PT, nothing recorded, 16 sweeps per launch (macro_batch; PP_MACRO_BATCH raises it up to 64).  This is
     # the regime in which the sweep kernel approaches the HBM roofline; the headline above pays PT + reductions every sweep.
     kw_pure = dict(pt_interval=None, warmup_ratio=1.0, per_sample=False)
     sim.sample(64, "metropolis", **kw_pure)
@@ -297,7 +297,7 @@ def run_ours(args):
     pure_ms = max_over_ranks(sim.last_sweep_loop_ms)
     pure_value = sum_over_ranks(float(np.prod(SHAPE)) * N_TEMPS * N_REPLICAS * D * 256) / (pure_ms * 1e6)
     sweeps_only = {"value": pure_value, "unit": UNIT, "hbm_roofline_frac": pure_value * B_ALG_MSC / (world * peak),
-                   "note": "256 sweeps without parallel tempering or recording (64 sweeps per launch), device time"}
+                   "note": "256 sweeps without parallel tempering or recording (16 sweeps per launch), device time"}
     del sim
 
     # ---- end-to-end leg: host buffers in, result dict out, every step ----------------------------
