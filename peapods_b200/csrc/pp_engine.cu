@@ -1726,19 +1726,23 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     CUDA_TRY(cudaMemcpy(sums.data(), s->st.sums, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost));
     const double c_stat = n_rec > 0 ? (double)(n_rec * m.R) : 1.0;
     const double c_ov = (n_rec > 0 && m.P > 0) ? (double)(n_rec * m.P) : 1.0;
+    // one pass in storage order; every (k, t) accumulator still adds its realizations in order (results.rs:165-180)
+    std::vector<double> mean_acc((size_t)11 * T, 0.0);
     for (int64_t d = 0; d < m.D; d++)
-        for (int k = 0; k < 11; k++)
-            for (int t = 0; t < T; t++) sums[((size_t)d * 11 + k) * T + t] /= (k < 5 ? c_stat : c_ov);
+        for (int k = 0; k < 11; k++) {
+            const double c = k < 5 ? c_stat : c_ov;
+            double *row = &sums[((size_t)d * 11 + k) * T], *acc = &mean_acc[(size_t)k * T];
+            for (int t = 0; t < T; t++) {
+                row[t] /= c;
+                acc[t] += row[t];
+            }
+        }
     if (out->per_sample_means) memcpy(out->per_sample_means, sums.data(), sizeof(double) * sums.size());
     double *dst[11] = {out->mags, out->mags2, out->mags4, out->energies, out->energies2, out->overlap, out->overlap2,
                        out->overlap4, out->link_overlap, out->link_overlap2, out->link_overlap4};
     for (int k = 0; k < 11; k++) {
         if (!dst[k] || (k >= 5 && m.P == 0)) continue;
-        for (int t = 0; t < T; t++) {
-            double acc = 0.0;
-            for (int64_t d = 0; d < m.D; d++) acc += sums[((size_t)d * 11 + k) * T + t];
-            dst[k][t] = acc / (double)m.D;
-        }
+        for (int t = 0; t < T; t++) dst[k][t] = mean_acc[(size_t)k * T + t] / (double)m.D;
     }
     if (want_eq) {  // results.rs:231-247, 275-282
         double *edst[2] = {out->equil_energy_avg, out->equil_link_overlap_avg};
