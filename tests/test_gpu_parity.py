@@ -631,3 +631,58 @@ def test_chunked_multistream_execution_of_the_widened_features_is_bit_exact(orac
         assert_results_equal(rg, rc)
         assert np.array_equal(gpu.last_per_sample_taus, cpu.last_per_sample_taus)
         assert np.array_equal(gpu.last_per_sample_equil, cpu.last_per_sample_equil)
+
+
+def test_headline_full_size_properties_and_oracle_checked_shard(oracle):
+    """BASELINE configs[1] at its full size (16^3 +-J, 32 temperatures, 4 replicas, 4096 realizations: more than the oracle can
+    replay in seconds), checked through size-independent properties, plus one shard the oracle does replay:
+      * realizations are independent (simulation/mod.rs:887-903): the first 32 realizations of the full run equal a 32-realization
+        handle bit for bit (per-realization means, spins, PT counters), and that handle equals the oracle;
+      * every recorded sweep adds one count per (realization, temperature, pair) to the histogram (statistics/overlap.rs:300-310);
+      * single_random_edge attempts exactly one edge per replica ladder and PT event (mcmc/tempering.rs:29-41);
+      * the aggregated means are the in-order mean of the per-realization means (statistics/results.rs:165-180)."""
+    import peapods_b200 as pb
+
+    shape, T, R, D, n_sweeps, sub = (16, 16, 16), 32, 4, 4096, 12, 32
+    temps = np.linspace(0.8, 1.4, T).astype(np.float32)
+    rng = np.random.default_rng(2026)
+    J = (2 * rng.integers(0, 2, size=(D,) + shape + (3,), dtype=np.int8) - 1).astype(np.float32)
+    kw = dict(pt_interval=1, pt_schedule="single_random_edge", warmup_ratio=0.25, per_sample=False)
+    full = pb.IsingSimulation(list(shape), J, temps, R, None, 4242, layout="msc")
+    res = full.sample(n_sweeps, "metropolis", **kw)
+    means = full.last_per_sample_means.copy()  # [D, 11, T]
+    n_rec, P = n_sweeps - 3, R // 2
+
+    hist = np.stack(res["overlap_histogram"])
+    assert np.array_equal(hist.sum(axis=1), np.full(T, D * P * n_rec, np.uint64))
+    pt = res["per_disorder"]["parallel_tempering"]
+    assert np.array_equal(pt["edge_attempts"].sum(axis=1), np.full(D, R * n_sweeps, np.uint64))
+    assert np.all(pt["edge_acceptances"] <= pt["edge_attempts"])
+    keys = ("mags", "mags2", "mags4", "energies", "energies2", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2",
+            "link_overlap4")
+    for k, key in enumerate(keys):
+        acc = np.zeros(T)
+        for d in range(D):
+            acc += means[d, k]
+        assert np.array_equal(res[key], acc / D), key
+    # energy.rs:92-109 sums + s_i s_j J per bond: satisfied bonds count positive, at most z' = 3 per site
+    assert np.all(res["energies"] > 0.0) and np.all(res["energies"] < 3.0)
+    assert np.all(np.diff(res["energies"]) < 0.0)  # fewer satisfied bonds at higher temperature (4096-realization average)
+
+    part = pb.IsingSimulation(list(shape), J[:sub], temps, R, None, 4242, layout="msc")
+    rp = part.sample(n_sweeps, "metropolis", **kw)
+    assert np.array_equal(part.last_per_sample_means, means[:sub])
+    for k in pt:
+        assert np.array_equal(rp["per_disorder"]["parallel_tempering"][k], pt[k][:sub]), k
+    for d in (0, 17, sub - 1):
+        assert np.array_equal(part.get_spins(d), full.get_spins(d))
+        assert np.array_equal(part.get_system_ids(d), full.get_system_ids(d))
+
+    colour, _ = pb.colouring(shape, None)
+    cpu = oracle.Sim(shape, J[:sub], temps, n_replicas=R, offsets=None, seed=4242, rng_mode=oracle.RNG_PHILOX_MSC, colour=colour)
+    rc = cpu.sample(n_sweeps, "metropolis", pt_interval=1, pt_schedule="single_random_edge", warmup_ratio=0.25)
+    for key in keys:
+        assert np.array_equal(rp[key], rc[key]), key
+    assert np.array_equal(np.stack(rp["overlap_histogram"]), np.asarray(rc["overlap_histogram"]))
+    for d in (0, sub - 1):
+        assert np.array_equal(part.get_spins(d), cpu.spins(d))
