@@ -686,3 +686,63 @@ def test_headline_full_size_properties_and_oracle_checked_shard(oracle):
     assert np.array_equal(np.stack(rp["overlap_histogram"]), np.asarray(rc["overlap_histogram"]))
     for d in (0, sub - 1):
         assert np.array_equal(part.get_spins(d), cpu.spins(d))
+
+
+def test_config3_full_size_triangular_gibbs_is_bit_exact(oracle):
+    """BASELINE configs[2] at its full size: 256 x 256 triangular ferromagnet (custom neighbor_offsets), Gibbs sweeps, 64
+    temperatures around T_c = 4 / ln 3, 2 replicas — small enough for the oracle to replay a few sweeps outright."""
+    tc = 4.0 / np.log(3.0)
+    gpu, cpu = make_pair(oracle, (256, 256), "ferro", np.linspace(tc - 0.4, tc + 0.4, 64), 2, 1, TRI)
+    assert_state_equal(gpu, cpu, 1)
+    for n_sweeps, interval in ((3, None), (4, 1)):
+        kw = dict(warmup_ratio=0.25, pt_interval=interval, pt_schedule="single_random_edge")
+        rg = gpu.sample(n_sweeps, "gibbs", **kw)
+        rc = cpu.sample(n_sweeps, "gibbs", **kw)
+        assert_state_equal(gpu, cpu, 1)
+        assert_results_equal(rg, rc)
+
+
+def test_config4_full_size_gaussian_properties_and_oracle_checked_shard(oracle):
+    """BASELINE configs[3] at its full size (32^3 Gaussian couplings, 48 temperatures, 4 replicas, 512 realizations) through
+    size-independent properties, plus a 2-realization shard replayed by the oracle (spins bit-exact with exact_log, integer
+    observables exact, f32 energies within 1e-5 relative — the tolerance BASELINE.json states)."""
+    import peapods_b200 as pb
+
+    shape, T, R, D, n_sweeps, sub = (32, 32, 32), 48, 4, 512, 4, 2
+    temps = np.linspace(0.8, 1.8, T).astype(np.float32)
+    J = np.random.default_rng(44).standard_normal((D,) + shape + (3,), dtype=np.float32)
+    kw = dict(warmup_ratio=0.25, exact_log=True, per_sample=False)
+    full = pb.IsingSimulation(list(shape), J, temps, R, None, 77)
+    assert full.layout == "int8"
+    res = full.sample(n_sweeps, "metropolis", **kw)
+    means = full.last_per_sample_means.copy()
+    n_rec, P = n_sweeps - 1, R // 2
+    assert np.array_equal(np.stack(res["overlap_histogram"]).sum(axis=1), np.full(T, D * P * n_rec, np.uint64))
+    keys = ("mags", "mags2", "mags4", "energies", "energies2", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2",
+            "link_overlap4")
+    for k, key in enumerate(keys):
+        acc = np.zeros(T)
+        for d in range(D):
+            acc += means[d, k]
+        assert np.array_equal(res[key], acc / D), key
+    assert np.all(np.isfinite(res["energies"])) and np.all(res["energies"] > 0.0)
+    assert np.all(np.abs(res["overlap"]) <= 1.0) and np.all(res["overlap2"] <= 1.0)
+
+    part = pb.IsingSimulation(list(shape), J[:sub], temps, R, None, 77)
+    rp = part.sample(n_sweeps, "metropolis", **kw)
+    for d in range(sub):
+        assert np.array_equal(part.get_spins(d), full.get_spins(d))
+    exact_rows = [0, 1, 2, 5, 6, 7, 8, 9, 10]  # magnetisation and overlap moments come from integers
+    assert np.array_equal(part.last_per_sample_means[:, exact_rows], means[:sub][:, exact_rows])
+    # fp32-coupling energies are sums whose block partition depends on the handle's size: tolerance-checked, as against the oracle
+    np.testing.assert_allclose(part.last_per_sample_means[:, 3:5], means[:sub, 3:5], rtol=2e-5, atol=1e-7)
+
+    colour, _ = pb.colouring(shape, None)
+    cpu = oracle.Sim(shape, J[:sub], temps, n_replicas=R, offsets=None, seed=77, rng_mode=oracle.RNG_PHILOX, colour=colour)
+    rc = cpu.sample(n_sweeps, "metropolis", warmup_ratio=0.25)
+    assert_state_equal(part, cpu, sub)
+    for k in ("mags", "mags2", "mags4", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2", "link_overlap4"):
+        assert np.array_equal(rp[k], rc[k]), k
+    assert np.array_equal(np.stack(rp["overlap_histogram"]), np.asarray(rc["overlap_histogram"]))
+    np.testing.assert_allclose(rp["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(rp["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
