@@ -746,3 +746,38 @@ def test_config4_full_size_gaussian_properties_and_oracle_checked_shard(oracle):
     assert np.array_equal(np.stack(rp["overlap_histogram"]), np.asarray(rc["overlap_histogram"]))
     np.testing.assert_allclose(rp["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(rp["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
+
+
+def test_config5_full_size_slab_decomposition_properties(oracle):
+    """BASELINE configs[4]: the 1024^3 ferromagnet at T_c on the slab layout.  The oracle replays a 256^3 lattice cut into 8 slabs;
+    at the full size (2^30 sites) the checks are size-independent: the 8-slab decomposition (the ranks emulated on one GPU, halo
+    planes exchanged per colour half-step) leaves the same 2^30 spins as the undivided lattice, and the device's integer bond /
+    spin sums equal a host recount of the downloaded configuration (energy.rs:92-109 on integers)."""
+    import peapods_b200 as pb
+
+    temps = np.asarray([4.511], np.float32)
+    shape = (256, 256, 256)
+    colour, _ = pb.colouring(shape)
+    gpu = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 11, layout="slab", slab_ranks=8, slab_rank=-1)
+    cpu = oracle.Sim(shape, np.ones(shape + (3,), np.float32), temps, n_replicas=1, seed=11, rng_mode=oracle.RNG_PHILOX, colour=colour)
+    rg, rc = gpu.sample(2, "metropolis", warmup_ratio=0.5), cpu.sample(2, "metropolis", warmup_ratio=0.5)
+    assert_state_equal(gpu, cpu, 1)
+    assert_results_equal(rg, rc)
+    del gpu, cpu
+
+    shape = (1024, 1024, 1024)
+    whole = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 11, layout="slab", slab_ranks=1, slab_rank=-1)
+    slabs = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 11, layout="slab", slab_ranks=8, slab_rank=-1)
+    ra, rb = whole.sample(3, "metropolis", warmup_ratio=0.25), slabs.sample(3, "metropolis", warmup_ratio=0.25)
+    for k in ("mags", "mags2", "mags4", "energies", "energies2"):
+        assert np.array_equal(ra[k], rb[k]), k
+    spins = slabs.get_spins()
+    assert np.array_equal(whole.get_spins(), spins)
+    e, m = slabs.op_energies_mags()
+    s3 = spins.reshape(shape)
+    assert m[0, 0] == int(s3.sum(dtype=np.int64))
+    bonds = 0
+    for a in range(3):
+        bonds += int(np.multiply(s3, np.roll(s3, -1, axis=a), dtype=np.int8).sum(dtype=np.int64))
+    assert e[0, 0] == np.float32(bonds) / np.float32(s3.size)
+    assert 0.5 < float(e[0, 0]) < 3.0  # three sweeps from a random start at T_c: ordering has begun
