@@ -802,12 +802,8 @@ static pp_status launch_pt(pp_sim *s, Ctx &c, int schedule, uint32_t pt_event, i
     if (s->layout == PP_LAYOUT_MSC) {
         pp_status st = flush_swaps(s, c);
         if (st != PP_OK) return st;
-        static const int dbg = getenv("PP_DEBUG_PT") ? atoi(getenv("PP_DEBUG_PT")) : 0;  // timing experiments only
-        if (!(dbg == 1 && pt_event > 2)) {
-            pt_exchange_msc_kernel<<<blocks_for(c.G * m.R * 32, 128), 128, 0, c.stream>>>(m, c.pt, schedule, first_parity, pt_event);
-            s->launches++;
-        }
-        if (dbg == 2) return PP_OK;
+        pt_exchange_msc_kernel<<<blocks_for(c.G * m.R * 32, 128), 128, 0, c.stream>>>(m, c.pt, schedule, first_parity, pt_event);
+        s->launches++;
         c.swap_pending = true;
         c.pend_schedule = schedule;
         c.pend_parity = first_parity;
@@ -970,13 +966,20 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     }
 
     // layout
-    const bool msc_ok = m.coupling_class != COUP_F32 && !flags[1] && z <= 7;
+    // multispin eligibility: +-1 couplings without zeros, at most 7 forward directions, and the per-thread bit-sliced
+    // counters of the table-driven kernels (pp_kernels_msc.cuh, MSC_VC_PLANES planes) must hold ceil(N / 256) * z adds
+    const bool msc_ok = m.coupling_class != COUP_F32 && !flags[1] && z <= 7 &&
+                        ((N + MSC_BLOCK - 1) / MSC_BLOCK) * (int64_t)z < ((int64_t)1 << MSC_VC_PLANES);
+    // One draw serves the 32 realizations of a word (RNG-SPEC).  With distinct disorder that only
+    // correlates the noise of the realizations; with IDENTICAL couplings (a ferromagnet) two lanes that meet in a slot stay
+    // equal from then on, so the automatic choice never packs identical realizations into one word.
+    const bool msc_auto_ok = msc_ok && m.coupling_class == COUP_UNIT;
     if (want_slab) {
         s->layout = PP_LAYOUT_SLAB;
     } else if (desc->layout == PP_LAYOUT_MSC) {
         if (!msc_ok) {
             free_sim(s);
-            return fail(PP_ERR_UNSUPPORTED, "multispin layout needs +-1 couplings (no zeros), eligible temperatures and <= 7 forward directions");
+            return fail(PP_ERR_UNSUPPORTED, "multispin layout needs +-1 couplings (no zeros), eligible temperatures, <= 7 forward directions and ceil(N / 256) * z < 2^20");
         }
         if (desc->sample_offset % 32 != 0) {
             free_sim(s);
@@ -984,7 +987,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         }
         s->layout = PP_LAYOUT_MSC;
     } else if (desc->layout == PP_LAYOUT_AUTO) {
-        s->layout = (msc_ok && m.D >= 32 && desc->sample_offset % 32 == 0) ? PP_LAYOUT_MSC : PP_LAYOUT_INT8;
+        s->layout = (msc_auto_ok && m.D >= 32 && desc->sample_offset % 32 == 0) ? PP_LAYOUT_MSC : PP_LAYOUT_INT8;
     } else if (desc->layout == PP_LAYOUT_INT8) {
         s->layout = PP_LAYOUT_INT8;
     } else {

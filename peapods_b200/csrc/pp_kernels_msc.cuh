@@ -17,7 +17,7 @@
 namespace pp {
 
 constexpr int MSC_BLOCK = 256;
-constexpr int MSC_VC_PLANES = 12;  // per-thread vertical counter capacity 4095
+constexpr int MSC_VC_PLANES = 20;  // per-thread vertical counter capacity 2^20 - 1 adds (pp_create checks ceil(N / 256) * z against it)
 
 // ---- vertical (bit-sliced) counters ----------------------------------------------------------
 template <int K>
