@@ -16,10 +16,11 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_build" / "libpp_oracle.so"
 
-RNG_XOSHIRO, RNG_PHILOX, RNG_PHILOX_MSC = 0, 1, 2
+RNG_XOSHIRO, RNG_PHILOX, RNG_PHILOX_MSC, RNG_PHILOX_PACKED = 0, 1, 2, 3
 SWEEP_METROPOLIS, SWEEP_GIBBS = 0, 1
 PT_SINGLE_RANDOM_EDGE, PT_FULL_LADDER = 0, 1
 TAG_INIT, TAG_SWEEP, TAG_PT, TAG_SWEEP_MSC = 0x00010000, 0x00020000, 0x00030000, 0x00040000
+TAG_SWEEP_PACKED = 0x000A0000
 
 
 def build(force: bool = False) -> Path:
@@ -83,7 +84,10 @@ def lib():
         "orc_xoshiro_seed_from_u64": (None, [vp, u64]),
         "orc_xoshiro_next_u64": (u64, [vp]),
         "orc_philox4x32_10": (None, [vp, vp, vp]),
+        "orc_philox": (None, [vp, vp, vp]),
+        "orc_philox4x32_r": (None, [vp, vp, C.c_int, vp]),
         "orc_draw24": (u32, [u64, u32, u32, u32, u32]),
+        "orc_draw24_packed": (u32, [u64, u32, u32, u32, u32]),
         "orc_lattice_new": (vp, [i32, vp, i32, vp]),
         "orc_lattice_free": (None, [vp]),
         "orc_lattice_n_spins": (i64, [vp]),
@@ -125,10 +129,18 @@ def _p(a):
 
 
 def philox4x32_10(ctr, key):
+    return philox4x32(ctr, key, 10)
+
+
+def philox4x32(ctr, key, rounds=None):
+    """Philox4x32-R; rounds=None: the RNG-SPEC generator (ORC_PHILOX_ROUNDS = 7)."""
     c = np.asarray(ctr, dtype=np.uint32)
     k = np.asarray(key, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
-    lib().orc_philox4x32_10(_p(c), _p(k), _p(out))
+    if rounds is None:
+        lib().orc_philox(_p(c), _p(k), _p(out))
+    else:
+        lib().orc_philox4x32_r(_p(c), _p(k), int(rounds), _p(out))
     return out
 
 

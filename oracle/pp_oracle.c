@@ -91,11 +91,12 @@ static uint64_t xo_gen_range_usize(uint64_t s[4], uint64_t low, uint64_t high) {
     }
 }
 
-/* Philox4x32-10 (Salmon et al., SC'11), the RNG-SPEC generator. */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+/* Philox4x32-R (Salmon et al., SC'11).  RNG-SPEC v2 uses R = ORC_PHILOX_ROUNDS = 7, the smallest round count the paper reports as
+ * Crush-resistant (its Table 2; Random123 ships it as philox4x32_R(7, ...)); R = 10 is kept for the published test vectors. */
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int round = 0; round < 10; round++) {
+    for (int round = 0; round < rounds; round++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -108,6 +109,9 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc_philox4x32_r(ctr, key, 10, out); }
+/* the RNG-SPEC generator */
+void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc_philox4x32_r(ctr, key, ORC_PHILOX_ROUNDS, out); }
 
 /* RNG-SPEC: 24-bit draw number `index` of the (c1, c2, c3) stream:
  * one Philox call serves four consecutive indices. */
@@ -115,7 +119,7 @@ uint32_t orc_draw24(uint64_t key, uint32_t index, uint32_t c1, uint32_t c2, uint
     uint32_t ctr[4] = {index >> 2, c1, c2, c3};
     uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
     uint32_t out[4];
-    orc_philox4x32_10(ctr, k, out);
+    orc_philox(ctr, k, out);
     return out[index & 3] >> 8;
 }
 
@@ -328,13 +332,29 @@ static void colour_order(const orc_lattice *lat, const uint16_t *colour, int64_t
     *order_out = order; *rank_out = rank; *n_colours_out = nc;
 }
 
+/* RNG-SPEC packed mapping (bit-packed single-lattice kernels, pp_kernels_slabp.cuh): the 32 ranks of a block r >> 5 share
+ * SIX generator calls, counter = {r >> 5, sweep, stream, tag | call << 8 | colour}, whose 24 output words W[0..23] are cut into 32
+ * fields of 24 bits: for g = 0..7 and A, B, C = W[3g], W[3g+1], W[3g+2] the ranks 4g .. 4g+3 of the block draw
+ * A >> 8, B >> 8, C >> 8 and (A & 255) << 16 | (B & 255) << 8 | (C & 255).  Every generated bit is used once. */
+uint32_t orc_draw24_packed(uint64_t key, uint32_t rank, uint32_t sweep, uint32_t stream, uint32_t tag_colour) {
+    uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)}, w[24];
+    for (uint32_t call = 0; call < 6; call++) {
+        uint32_t ctr[4] = {rank >> 5, sweep, stream, tag_colour | (call << 8)};
+        orc_philox(ctr, k, w + 4 * call);
+    }
+    uint32_t b = rank & 31u, g = b >> 2, j = b & 3u;
+    const uint32_t *t = w + 3 * g;
+    if (j < 3) return t[j] >> 8;
+    return ((t[0] & 255u) << 16) | ((t[1] & 255u) << 8) | (t[2] & 255u);
+}
+
 static void sweep_philox_impl(const orc_lattice *lat, int8_t *spins, const float *couplings,
                               const float *temperatures, const int64_t *system_ids, int64_t n_systems,
                               const uint16_t *colour, const int64_t *order, const uint32_t *rank,
                               uint64_t key, uint32_t sweep_index, int sweep_mode,
-                              const uint32_t *table, int stream_is_slot) {
+                              const uint32_t *table, int stream_is_slot, int packed) {
     int z = lat->n_neighbors, offset = 2 * z, width = 4 * z + 1;
-    uint32_t tag = stream_is_slot ? ORC_TAG_SWEEP_MSC : ORC_TAG_SWEEP;
+    uint32_t tag = packed ? ORC_TAG_SWEEP_PACKED : stream_is_slot ? ORC_TAG_SWEEP_MSC : ORC_TAG_SWEEP;
     uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
     for (int64_t slot = 0; slot < n_systems; slot++) {
         int64_t sys = system_ids[slot];
@@ -342,18 +362,32 @@ static void sweep_philox_impl(const orc_lattice *lat, int8_t *spins, const float
         float temp = temperatures[slot];
         const uint32_t *row = table ? table + slot * width : NULL;
         uint32_t stream = (uint32_t)(stream_is_slot ? slot : sys);
-        uint32_t cached_c0 = 0xFFFFFFFFu, cached_c3 = 0, out[4] = {0, 0, 0, 0};
+        uint32_t cached_c0 = 0xFFFFFFFFu, cached_c3 = 0, out[24] = {0};
         for (int64_t p = 0; p < lat->n_spins; p++) {
             int64_t i = order[p];
             uint32_t c3 = tag | colour[i];
             uint32_t r = rank[i];
-            if ((r >> 2) != cached_c0 || c3 != cached_c3) {
-                uint32_t ctr[4] = {r >> 2, sweep_index, stream, c3};
-                orc_philox4x32_10(ctr, k, out);
-                cached_c0 = r >> 2; cached_c3 = c3;
+            uint32_t draw;
+            if (packed) {
+                if ((r >> 5) != cached_c0 || c3 != cached_c3) {
+                    for (uint32_t call = 0; call < 6; call++) {
+                        uint32_t ctr[4] = {r >> 5, sweep_index, stream, c3 | (call << 8)};
+                        orc_philox(ctr, k, out + 4 * call);
+                    }
+                    cached_c0 = r >> 5; cached_c3 = c3;
+                }
+                const uint32_t *t = out + 3 * ((r & 31u) >> 2);
+                draw = (r & 3u) < 3u ? t[r & 3u] >> 8 : ((t[0] & 255u) << 16) | ((t[1] & 255u) << 8) | (t[2] & 255u);
+            } else {
+                if ((r >> 2) != cached_c0 || c3 != cached_c3) {
+                    uint32_t ctr[4] = {r >> 2, sweep_index, stream, c3};
+                    orc_philox(ctr, k, out);
+                    cached_c0 = r >> 2; cached_c3 = c3;
+                }
+                draw = out[r & 3] >> 8;
             }
             float h = local_field(lat, s, couplings, i);
-            attempt(s, i, h, out[r & 3] >> 8, temp, sweep_mode, row, offset);
+            attempt(s, i, h, draw, temp, sweep_mode, row, offset);
         }
     }
 }
@@ -382,7 +416,7 @@ void orc_sweep_philox(const orc_lattice *lat, int8_t *spins, const float *coupli
                                                n_systems, lat->n_neighbors, sweep_mode)
                                  : NULL;
     sweep_philox_impl(lat, spins, couplings, temperatures, system_ids, n_systems, colour, order, rank,
-                      key, sweep_index, sweep_mode, table, stream_is_slot);
+                      key, sweep_index, sweep_mode, table, stream_is_slot & 1, (stream_is_slot >> 1) & 1);
     free(table); free(order); free(rank);
 }
 
@@ -673,7 +707,7 @@ void orc_fk_update(const orc_lattice *lat, int8_t *spins, const float *couplings
     for (int64_t i = 0; i < N; i++) parent[i] = uf_find(parent, i);
     if (wolff) { /* fk.rs:151-158 */
         uint32_t ctr[4] = {0xFFFFFFFFu, sweep_index, system_id, ORC_TAG_FK_FLIP}, k[2] = {(uint32_t)key, (uint32_t)(key >> 32)}, o[4];
-        orc_philox4x32_10(ctr, k, o);
+        orc_philox(ctr, k, o);
         int64_t seed = (int64_t)(((uint64_t)o[1] * (uint64_t)N) >> 32);
         int64_t root = parent[seed];
         for (int64_t i = 0; i < N; i++) if (parent[i] == root) spins[i] = (int8_t)-spins[i];
@@ -693,7 +727,7 @@ void orc_houdayer_slot(const orc_lattice *lat, int8_t *spins, const int64_t *sys
     for (int k = 0; k < R; k++) sys[k] = system_ids[k * n_temps + t]; /* overlap.rs:45-48 */
     for (int i = R - 1; i >= 1; i--) { /* shuffle (overlap.rs:49): Fisher-Yates, step i draws j in [0, i] */
         uint32_t ctr[4] = {(uint32_t)i, sweep_index, (uint32_t)t, ORC_TAG_OC_PAIR}, k2[2] = {(uint32_t)key, (uint32_t)(key >> 32)}, o[4];
-        orc_philox4x32_10(ctr, k2, o);
+        orc_philox(ctr, k2, o);
         int j = (int)(((uint64_t)o[0] * (uint64_t)(i + 1)) >> 32);
         int64_t tmp = sys[i]; sys[i] = sys[j]; sys[j] = tmp;
     }
@@ -910,7 +944,8 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
             }
         } else {
             sweep_philox_impl(lat, re->spins, re->couplings, re->temperatures, re->system_ids, S, sim->colour,
-                              sim->order, sim->rank, sweep_key, sweep_index, cfg->sweep_mode, table, msc);
+                              sim->order, sim->rank, sweep_key, sweep_index, cfg->sweep_mode, table, msc,
+                              sim->rng_mode == ORC_RNG_PHILOX_PACKED);
         }
 
         /* mod.rs:434-470: FK cluster update of every slot's system, after the sweep, before the measurements */
@@ -1034,7 +1069,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                     } else { /* RNG-SPEC PT domain */
                         uint32_t ctr[4] = {0xFFFFFFFFu, pt_event, (uint32_t)r, ORC_TAG_PT};
                         uint32_t k[2] = {(uint32_t)re->base_seed, (uint32_t)(re->base_seed >> 32)}, o[4];
-                        orc_philox4x32_10(ctr, k, o);
+                        orc_philox(ctr, k, o);
                         edge = (int)(((uint64_t)o[1] * (uint64_t)(T - 1)) >> 32);
                         log_rand = logf(u24_to_f32(o[0] >> 8));
                     }
@@ -1051,7 +1086,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
                             } else {
                                 uint32_t ctr[4] = {(uint32_t)edge, pt_event, (uint32_t)r, ORC_TAG_PT};
                                 uint32_t k[2] = {(uint32_t)re->base_seed, (uint32_t)(re->base_seed >> 32)}, o[4];
-                                orc_philox4x32_10(ctr, k, o);
+                                orc_philox(ctr, k, o);
                                 log_rand = logf(u24_to_f32(o[0] >> 8));
                             }
                             int64_t left, right;

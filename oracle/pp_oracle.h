@@ -29,6 +29,7 @@
  *                       colour classes ascending, counter-based Philox4x32-10
  *                       keyed by (seed, sweep, site-rank, stream); per-site
  *                       arithmetic and acceptance rule are the reference's.
+ *   ORC_RNG_PHILOX_PACKED as PHILOX with the sweep draws in the packed mapping (32 ranks per six calls: orc_draw24_packed)
  *   ORC_RNG_PHILOX_MSC  as PHILOX but one draw shared by the 32 disorder samples
  *                       of a multispin word (stream = replica*T + slot).
  */
@@ -43,7 +44,7 @@ extern "C" {
 
 #define ORC_MAX_DIMS 8
 
-enum { ORC_RNG_XOSHIRO = 0, ORC_RNG_PHILOX = 1, ORC_RNG_PHILOX_MSC = 2 };
+enum { ORC_RNG_XOSHIRO = 0, ORC_RNG_PHILOX = 1, ORC_RNG_PHILOX_MSC = 2, ORC_RNG_PHILOX_PACKED = 3 };
 enum { ORC_SWEEP_METROPOLIS = 0, ORC_SWEEP_GIBBS = 1 };
 enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
 
@@ -57,6 +58,7 @@ enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
 #define ORC_TAG_OC_PAIR   0x00070000u  /* replica shuffle at a temperature: counter = {step, sweep index, slot t, tag} */
 #define ORC_TAG_OC_SEED   0x00080000u  /* Wolff seed scores: counter = {site >> 2, sweep index, t * P + g, tag} */
 #define ORC_TAG_OC_FLIP   0x00090000u  /* cluster coins:     counter = {root >> 2, sweep index, t * P + g, tag} */
+#define ORC_TAG_SWEEP_PACKED 0x000A0000u  /* counter = {rank >> 5, sweep index, system id, tag | call << 8 | colour}, call = 0..5 */
 #define ORC_MSC_KEY_DOMAIN 0x6D73635F67726F75ull
 
 typedef struct orc_lattice orc_lattice;
@@ -111,8 +113,12 @@ uint64_t orc_child_seed(uint64_t root, uint64_t domain, uint64_t index); /* real
 uint64_t orc_realization_seed(uint64_t root, uint64_t r);  /* src/lib.rs:30-32 */
 void orc_xoshiro_seed_from_u64(uint64_t s[4], uint64_t seed);
 uint64_t orc_xoshiro_next_u64(uint64_t s[4]);
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+#define ORC_PHILOX_ROUNDS 7  /* RNG-SPEC v2 */
+void orc_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);  /* published test vectors */
+void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);         /* the RNG-SPEC generator (R = 7) */
 uint32_t orc_draw24(uint64_t key, uint32_t c0_index, uint32_t c1, uint32_t c2, uint32_t c3);
+uint32_t orc_draw24_packed(uint64_t key, uint32_t rank, uint32_t sweep, uint32_t stream, uint32_t tag_colour);
 
 /* ---- lattice (geometry/lattice.rs:44-109) ------------------------------ */
 orc_lattice *orc_lattice_new(int n_dims, const int64_t *shape, int n_offsets,

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1352,7 +1353,16 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         pool_free(s, ac_m.ring); pool_free(s, ac_m.sum_prod); pool_free(s, ac_m.sum_o);
         pool_free(s, ac_q.ring); pool_free(s, ac_q.sum_prod); pool_free(s, ac_q.sum_o);
         pool_free(s, d_tau);
+        ac_m = ac_q = AutocorrView{0, nullptr, nullptr, nullptr, nullptr};
+        d_tau = nullptr;
     };
+    // Every exit of this function runs `cleanup` (scope guard): per-call buffers go back to the pool, and once the sweep loop
+    // has started a pending multispin exchange is applied and the handle's word pointer is put on the current ping-pong buffer,
+    // so that an error or an interrupt never leaves the handle between two states.
+    struct ScopeExit {
+        std::function<void()> f;
+        ~ScopeExit() { if (f) f(); }
+    } cleanup;
     if (want_ac) {
         if (s->layout == PP_LAYOUT_SLAB) return fail(PP_ERR_UNSUPPORTED, "autocorrelation_max_lag is not implemented for the slab layout");
         const int K = (int)std::max<int64_t>(1, std::min<int64_t>(cfg->autocorrelation_max_lag, n_rec / 4));
@@ -1374,8 +1384,24 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     const bool want_eq = cfg->equilibration_diagnostic != 0;
     std::vector<int64_t> ckpts;
     double *d_eq_sum = nullptr, *d_eq_snap = nullptr;
+    auto free_eq = [&]() { pool_free(s, d_eq_sum); pool_free(s, d_eq_snap); d_eq_sum = d_eq_snap = nullptr; };
+    uint32_t *d_fk_count = nullptr, *d_fk_lab = nullptr;
+    uint8_t *d_fk_bm = nullptr;
+    auto free_fk = [&]() { pool_free(s, d_fk_count); pool_free(s, d_fk_lab); pool_free(s, d_fk_bm); d_fk_count = d_fk_lab = nullptr; d_fk_bm = nullptr; };
+    std::vector<Ctx> chunks;
+    bool loop_live = false;
+    cleanup.f = [&]() {
+        if (loop_live) {
+            for (Ctx &c : chunks) flush_swaps(s, c);
+            if (!chunks.empty()) commit_ctx(s, chunks[0]);
+            cudaDeviceSynchronize();
+        }
+        free_ac();
+        free_fk();
+        free_eq();
+    };
     if (want_eq) {
-        if (s->layout == PP_LAYOUT_SLAB) { free_ac(); return fail(PP_ERR_UNSUPPORTED, "equilibration_diagnostic is not implemented for the slab layout"); }
+        if (s->layout == PP_LAYOUT_SLAB) { return fail(PP_ERR_UNSUPPORTED, "equilibration_diagnostic is not implemented for the slab layout"); }
         ckpts.resize(80);
         ckpts.resize((size_t)pp_equil_checkpoints(cfg->n_sweeps, ckpts.data()));
         const size_t ndt = (size_t)m.D * m.T;
@@ -1387,18 +1413,13 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     // Fortuin-Kasteleyn cluster updates (mod.rs:434-470): int8 layouts with unit couplings
     const bool want_oc = cfg->overlap_cluster_update_interval > 0;
     const bool want_fk = cfg->cluster_update_interval > 0;
-    uint32_t *d_fk_count = nullptr, *d_fk_lab = nullptr;
-    uint8_t *d_fk_bm = nullptr;
     int64_t fk_smem_sites = 0;
     size_t fk_smem = 0;
-    auto free_fk = [&]() { pool_free(s, d_fk_count); pool_free(s, d_fk_lab); pool_free(s, d_fk_bm); };
     // multispin layout: Wolff mode only (32 clusters grow as one bit-parallel flood fill), state of one pair in shared memory
     const size_t oc_msc_smem = ((size_t)3 * m.N + (size_t)m.N * m.z) * 4 + 16;
     const bool oc_msc_ok = s->layout == PP_LAYOUT_MSC && cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF && m.N <= 65536 &&
                            oc_msc_smem <= 200 * 1024;
     if (want_oc && ((s->layout != PP_LAYOUT_INT8 && !oc_msc_ok) || m.R < 2 || m.R > 64)) {
-        free_ac();
-        pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
         if (s->layout != PP_LAYOUT_SLAB && m.R < 2)  // mod.rs:207-213
             return fail(PP_ERR_INVALID, "overlap cluster requires n_replicas >= max group_size (" + std::to_string(m.R) + " < 2)");
         return fail(PP_ERR_UNSUPPORTED, "overlap cluster moves (overlap_cluster_update_interval) are not implemented on the GPU sweep "
@@ -1422,8 +1443,6 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     }
     if (want_fk) {
         if (s->layout != PP_LAYOUT_INT8 || m.coupling_class == COUP_F32) {
-            free_ac();
-            pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
             return fail(PP_ERR_UNSUPPORTED, "cluster updates (cluster_update_interval) are not implemented on the GPU sweep path for "
                                             "this handle: they need the int8 layout and couplings in {-1, 0, +1}");
         }
@@ -1459,7 +1478,6 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     // between the sweep, exchange and swap kernels) and spreads the chunks over a few streams, so that the
     // latency-/bandwidth-bound exchange and swap kernels of one chunk overlap the ALU-bound sweep kernel of another.
     // Realizations are independent (mod.rs:887-903 runs them on different threads), so results do not depend on this.
-    std::vector<Ctx> chunks;
     int64_t macro_batch = 1;
     if (msc && s->msc3d && !s->profile && s->n_streams > 1) {
         const int64_t group_bytes = (int64_t)m.S * m.N * 4;
@@ -1482,6 +1500,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         }
     }
     if (chunks.empty()) chunks.push_back(whole_ctx(s));
+    loop_live = true;
 
     struct Step {
         uint32_t sweep_index;
@@ -1502,10 +1521,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         mk.lut = cfg->sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
         const bool gibbs = cfg->sweep_mode == PP_SWEEP_GIBBS;
         while (sweep_id < cfg->n_sweeps) {
-            if (interrupt && *interrupt) {
-                cudaDeviceSynchronize();
-                return fail(PP_ERR_INTERRUPTED, "interrupted");
-            }
+            if (interrupt && *interrupt) return fail(PP_ERR_INTERRUPTED, "interrupted");
             const int64_t mb_end = std::min<int64_t>(cfg->n_sweeps, sweep_id + 256);
             ResidentArgs a;
             a.sweep_id0 = sweep_id;
@@ -1543,15 +1559,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         }
     }
     while (sweep_id < cfg->n_sweeps) {
-        if (interrupt && *interrupt) {  // mod.rs:406-408 (polled once per macro batch)
-            for (Ctx &c : chunks) flush_swaps(s, c);
-            commit_ctx(s, chunks[0]);
-            cudaDeviceSynchronize();
-            free_ac();
-            free_fk();
-            pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
-            return fail(PP_ERR_INTERRUPTED, "interrupted");
-        }
+        if (interrupt && *interrupt) return fail(PP_ERR_INTERRUPTED, "interrupted");  // mod.rs:406-408 (polled once per macro batch)
         // the sequence of kernel steps of this macro batch (mod.rs:405-432, 486-509, 748-796), identical for every chunk
         const int64_t mb_end = std::min<int64_t>(cfg->n_sweeps, sweep_id + macro_batch);
         steps.clear();
@@ -1681,6 +1689,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         if (st != PP_OK) return st;
     }
     commit_ctx(s, chunks[0]);
+    loop_live = false;
     if (chunks.size() > 1) {
         for (size_t i = 0; i < s->xstreams.size(); i++) {
             CUDA_TRY(cudaEventRecord(s->xevents[i], s->xstreams[i]));
@@ -1708,14 +1717,11 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         taus.assign((size_t)ndt * 2, 0.0);
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         CUDA_TRY(cudaMemcpy(taus.data(), d_tau, sizeof(double) * (size_t)ndt * (ac_q.ring ? 2 : 1), cudaMemcpyDeviceToHost));
-        free_ac();
     }
-    if (want_fk || want_oc) free_fk();
     std::vector<double> eq_snap;  // [D][n_ckpt][2][T]
     if (want_eq) {
         eq_snap.assign((size_t)m.D * ckpts.size() * 2 * m.T, 0.0);
         CUDA_TRY(cudaMemcpy(eq_snap.data(), d_eq_snap, sizeof(double) * eq_snap.size(), cudaMemcpyDeviceToHost));
-        pool_free(s, d_eq_sum); pool_free(s, d_eq_snap);
     }
     if (!out) return PP_OK;
     out->sweep_loop_ms = ms;

@@ -52,7 +52,7 @@ fk_cluster_kernel(ModelView m, const uint32_t *bond_count /* [T] */, uint32_t sw
             if (inter > 0) {
                 if ((bond >> 2) != cached) {
                     cached = bond >> 2;
-                    o = philox4x32_10(cached, sweep_index, sys, TAG_FK_BOND, k0, k1);
+                    o = philox4x32(cached, sweep_index, sys, TAG_FK_BOND, k0, k1);
                 }
                 if ((pick(o, bond & 3u) >> 8) < count) mask |= 1u << dd;
             }
@@ -86,7 +86,7 @@ fk_cluster_kernel(ModelView m, const uint32_t *bond_count /* [T] */, uint32_t sw
     // ---- flips (fk.rs:151-170)
     uint32_t seed_root = 0u;
     if (wolff) {
-        const u32x4 o = philox4x32_10(0xFFFFFFFFu, sweep_index, sys, TAG_FK_FLIP, k0, k1);
+        const u32x4 o = philox4x32(0xFFFFFFFFu, sweep_index, sys, TAG_FK_FLIP, k0, k1);
         seed_root = lab[(uint32_t)(((uint64_t)o.y * (uint64_t)N) >> 32)];
     }
     for (int64_t i = tid; i < N; i += FK_THREADS) {
@@ -95,7 +95,7 @@ fk_cluster_kernel(ModelView m, const uint32_t *bond_count /* [T] */, uint32_t sw
         if (wolff) {
             flip = root == seed_root;
         } else {
-            const u32x4 o = philox4x32_10(root >> 2, sweep_index, sys, TAG_FK_FLIP, k0, k1);
+            const u32x4 o = philox4x32(root >> 2, sweep_index, sys, TAG_FK_FLIP, k0, k1);
             flip = (pick(o, root & 3u) >> 8) < (1u << 23);
         }
         if (flip) s[i] = (int8_t)-s[i];
@@ -133,7 +133,7 @@ houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites
         int sys[64];
         for (int k = 0; k < m.R; k++) sys[k] = m.system_ids[d * m.S + k * m.T + t];
         for (int i = m.R - 1; i >= 1; i--) {
-            const u32x4 o = philox4x32_10((uint32_t)i, sweep_index, (uint32_t)t, TAG_OC_PAIR, k0, k1);
+            const u32x4 o = philox4x32((uint32_t)i, sweep_index, (uint32_t)t, TAG_OC_PAIR, k0, k1);
             const int j = (int)(((uint64_t)o.x * (uint64_t)(i + 1)) >> 32);
             const int tmp = sys[i]; sys[i] = sys[j]; sys[j] = tmp;
         }
@@ -182,7 +182,7 @@ houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites
         unsigned long long best = ~0ull;
         for (int64_t i = tid; i < N; i += FK_THREADS) {
             if (!(act[i] & 1)) continue;
-            const u32x4 o = philox4x32_10((uint32_t)i >> 2, sweep_index, stream, TAG_OC_SEED, k0, k1);
+            const u32x4 o = philox4x32((uint32_t)i >> 2, sweep_index, stream, TAG_OC_SEED, k0, k1);
             const unsigned long long score = ((unsigned long long)(pick(o, (uint32_t)i & 3u) >> 8) << 32) | (unsigned long long)i;
             best = score < best ? score : best;
         }
@@ -200,7 +200,7 @@ houdayer_kernel(ModelView m, uint32_t sweep_index, int wolff, int64_t smem_sites
         for (int64_t i = tid; i < N; i += FK_THREADS) {
             if ((act[i] & 3) != 3) continue;
             const uint32_t root = lab[i];
-            const u32x4 o = philox4x32_10(root >> 2, sweep_index, stream, TAG_OC_FLIP, k0, k1);
+            const u32x4 o = philox4x32(root >> 2, sweep_index, stream, TAG_OC_FLIP, k0, k1);
             if ((pick(o, root & 3u) >> 8) < (1u << 23)) { a[i] = (int8_t)-a[i]; b[i] = (int8_t)-b[i]; }
         }
     }
@@ -247,7 +247,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
         int idx[64];
         for (int k = 0; k < m.R; k++) idx[k] = k;
         for (int i = m.R - 1; i >= 1; i--) {
-            const u32x4 o = philox4x32_10((uint32_t)i, sweep_index, (uint32_t)t, TAG_OC_PAIR, k0, k1);
+            const u32x4 o = philox4x32((uint32_t)i, sweep_index, (uint32_t)t, TAG_OC_PAIR, k0, k1);
             const int j = (int)(((uint64_t)o.x * (uint64_t)(i + 1)) >> 32);
             const int tmp = idx[i]; idx[i] = idx[j]; idx[j] = tmp;
         }
@@ -267,7 +267,7 @@ msc_houdayer_kernel(ModelView m, const uint16_t *nbr16, const uint16_t *site16 /
         for (int64_t i = tid; i < N * z2 / 2; i += OC_THREADS) dst[i] = __ldg(src + i);
     }
     for (int64_t q = tid; q < (N + 3) / 4; q += OC_THREADS) {  // scores are drawn per logical site and kept by storage position
-        const u32x4 o = philox4x32_10((uint32_t)q, sweep_index, stream, TAG_OC_SEED, k0, k1);
+        const u32x4 o = philox4x32((uint32_t)q, sweep_index, stream, TAG_OC_SEED, k0, k1);
         for (int j = 0; j < 4; j++)
             if (4 * q + j < N) score[m.perm ? m.perm[4 * q + j] : (uint32_t)(4 * q + j)] = pick(o, (uint32_t)j) >> 8;
     }

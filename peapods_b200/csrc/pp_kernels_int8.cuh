@@ -25,7 +25,7 @@ __global__ void init_spins_int8_kernel(ModelView m) {
     int64_t q = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (q * 4 >= m.N) return;
     uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
-    u32x4 o = philox4x32_10((uint32_t)q, 0u, sys, TAG_INIT, (uint32_t)key, (uint32_t)(key >> 32));
+    u32x4 o = philox4x32((uint32_t)q, 0u, sys, TAG_INIT, (uint32_t)key, (uint32_t)(key >> 32));
     int8_t *s = m.spins + sysg * m.N;
 #pragma unroll
     for (int l = 0; l < 4; l++) {
@@ -48,7 +48,7 @@ sweep_colour_int8_kernel(ModelView m, int colour, uint32_t sweep_index, int swee
     const uint32_t q = blockIdx.y * blockDim.x + threadIdx.x;
     if (cs + q * 4 >= ce) return;
     const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
-    const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
+    const u32x4 o = philox4x32(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
     int8_t *s = m.spins + (d * m.S + sys) * m.N;
     const int z = m.z, z2 = 2 * m.z;
     const int width = 4 * z + 1;

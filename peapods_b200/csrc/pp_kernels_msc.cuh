@@ -114,7 +114,7 @@ __global__ void msc_init_kernel(ModelView m) {
         const int64_t d = g * 32 + l;
         if (d >= m.D) break;  // padding lanes stay +1
         const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
-        const u32x4 o = philox4x32_10((uint32_t)q, 0u, pos, TAG_INIT, (uint32_t)key, (uint32_t)(key >> 32));
+        const u32x4 o = philox4x32((uint32_t)q, 0u, pos, TAG_INIT, (uint32_t)key, (uint32_t)(key >> 32));
 #pragma unroll
         for (int j = 0; j < 4; j++) w[j] |= ((pick(o, j) >> 8) < (1u << 23) ? 1u : 0u) << l;
     }
@@ -156,7 +156,7 @@ msc_sweep_kernel(ModelView m, uint32_t sweep_index, int n_sweeps, int want_energ
             const uint32_t cs = m.colour_start[c], ce = m.colour_start[c + 1];
             const uint32_t nq = (ce - cs + 3) >> 2;
             for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
-                const u32x4 o = philox4x32_10(q, sweep_index + (uint32_t)sw, pos, TAG_SWEEP_MSC | (uint32_t)c, k0, k1);
+                const u32x4 o = philox4x32(q, sweep_index + (uint32_t)sw, pos, TAG_SWEEP_MSC | (uint32_t)c, k0, k1);
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
                     const uint32_t p = cs + q * 4 + l;

@@ -19,7 +19,7 @@
 // words, which are read once per quad and reused by the R replicas.
 //
 // Per word update (Metropolis): 6 three-input XORs (bond words), two bit-sliced full adders and five
-// LOP3s give the masks [unsat >= 1], [>= 2], [>= 3]; the 24-bit draw (one Philox4x32-10 call per quad
+// LOP3s give the masks [unsat >= 1], [>= 2], [>= 3]; the 24-bit draw (one Philox call per quad
 // and replica, RNG-SPEC TAG_SWEEP_MSC) selects which of them is the flip mask:
 //   flip lane l  <=>  draw < table[t][2*unsat_l]   (sweep.rs:182-184 with ec + 2z' = 2*unsat).
 #pragma once
@@ -306,7 +306,7 @@ __device__ __forceinline__ void msc3d_sweep_item(uint32_t *sp, const uint32_t *J
 #pragma unroll
     for (int r = 0; r < RPC; r++) {
         uint32_t *sys = sp + (size_t)r * N;
-        const u32x4 rnd = philox4x32_10(self >> 2, sweep, pos0 + (uint32_t)r * pos_stride, tag, k0, k1);
+        const u32x4 rnd = philox4x32(self >> 2, sweep, pos0 + (uint32_t)r * pos_stride, tag, k0, k1);
         uint32_t s[4], zpv[4], zmv[4], ypv[4], ymv[4], xo[4], xs[4];
         to_arr(lds4(sys + so + self), s);
         to_arr(lds4(sys + oo + zp), zpv);

@@ -252,7 +252,7 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
         const uint32_t sys = sysv[ss % PF];
         const int t = slot % m.T;                                     // realization.rs:166
         int8_t *s = spins_d + (int64_t)sys * m.N;
-        const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
+        const u32x4 o = philox4x32(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
         const uint64_t C = Cv[ss % PF];
         uint64_t F[ZA], B[ZA];
 #pragma unroll

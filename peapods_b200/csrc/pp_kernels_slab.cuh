@@ -89,7 +89,7 @@ slab_sweep_kernel(ModelView m, SlabView v, int colour, uint32_t sweep_index, int
         const uint64_t left = (C << 8) | (off ? 0ull : E), right = (C >> 8) | (off ? E << 56 : 0ull);
         const uint64_t down = Xm + Xp + Ym + Yp + left + right;  // per byte: down-spin neighbours (<= 6, no carries)
         const uint32_t q = (gx0 * (uint32_t)v.L1 + (uint32_t)x1) * (uint32_t)kpr + (uint32_t)k;  // segment index = colour rank >> 2
-        const u32x4 o = philox4x32_10(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, v.k0, v.k1);
+        const u32x4 o = philox4x32(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, v.k0, v.k1);
         // ferromagnet: a bond is unsatisfied iff the two spins differ, so per byte unsat = s ? 6 - down : down
         // = (down ^ 7s) - s for all 8 sites at once; then the four active sites are brought to the even bytes and the two
         // 32-bit halves are read with constant shifts
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) slab_init_kernel(ModelView m, SlabView v)
     uint64_t out = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const u32x4 o = philox4x32_10((uint32_t)(2 * seg + h), 0u, sys, TAG_INIT, v.k0, v.k1);
+        const u32x4 o = philox4x32((uint32_t)(2 * seg + h), 0u, sys, TAG_INIT, v.k0, v.k1);
 #pragma unroll
         for (int l = 0; l < 4; l++)
             if ((pick(o, l) >> 8) < (1u << 23)) out |= 1ull << (8 * (4 * h + l));

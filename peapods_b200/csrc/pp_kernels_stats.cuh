@@ -292,14 +292,14 @@ __device__ __forceinline__ void pt_exchange_body(const ModelView &m, const PtVie
     const uint64_t key = realization_seed(m.seed, (uint64_t)(m.sample_offset + d));
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     if (schedule == 0) {  // tempering.rs:20-42
-        const u32x4 o = philox4x32_10(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+        const u32x4 o = philox4x32(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
         const int edge = (int)(((uint64_t)o.y * (uint64_t)(m.T - 1)) >> 32);
         pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
     } else {  // tempering.rs:45-70
         for (int pi = 0; pi < 2; pi++) {
             const int parity = pi == 0 ? first_parity : 1 - first_parity;
             for (int edge = parity; edge < m.T - 1; edge += 2) {
-                const u32x4 o = philox4x32_10((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+                const u32x4 o = philox4x32((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
                 pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
             }
         }
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) pt_exchange_msc_kernel(ModelView m, PtVie
         int edge = -1;
         bool acc = false;
         if (live) {
-            const u32x4 o = philox4x32_10(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+            const u32x4 o = philox4x32(0xFFFFFFFFu, pt_event, (uint32_t)r, TAG_PT, k0, k1);
             edge = (int)(((uint64_t)o.y * (uint64_t)(m.T - 1)) >> 32);
             acc = pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
         }
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(128) pt_exchange_msc_kernel(ModelView m, PtVie
             for (int edge = parity; edge < m.T - 1; edge += 2) {
                 bool acc = false;
                 if (live) {
-                    const u32x4 o = philox4x32_10((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
+                    const u32x4 o = philox4x32((uint32_t)edge, pt_event, (uint32_t)r, TAG_PT, k0, k1);
                     acc = pt_attempt_edge(m, pt, d, r, edge, o.x >> 8);
                 }
                 const uint32_t accepted = __ballot_sync(0xFFFFFFFFu, acc);

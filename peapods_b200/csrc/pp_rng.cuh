@@ -1,4 +1,10 @@
-// pp_rng.cuh — RNG-SPEC v1: counter-based Philox4x32-10 keyed by (seed, sweep, site-rank, stream).
+// pp_rng.cuh — RNG-SPEC v2: counter-based Philox4x32-7 keyed by (seed, sweep, site-rank, stream).
+//
+// v2 (round 2): 7 rounds instead of 10 — the smallest round count Salmon et al. (SC'11, Table 2) report as Crush-resistant,
+// shipped by Random123 as philox4x32_R(7, ...); the generator's 32x32->64 multiplies (IMAD.WIDE: 0.17 per cycle per SM
+// sub-partition on B200, profiles/r1_ubench_pipes.log) are the largest single cost of every sweep kernel.  Both round counts are
+// pinned by the published Random123 known-answer vectors (see tests/).  v2 also adds the packed draw mapping
+// of the bit-packed single-lattice kernels (pp_kernels_slabp.cuh: 32 ranks per six calls, every generated bit used).
 //
 // Replaces the per-system xoshiro256** streams of the reference
 // (spin-sim/src/simulation/realization.rs:168-175, spin-sim/src/parallel.rs:27-33): a draw is a pure
@@ -26,6 +32,7 @@ constexpr uint32_t TAG_INIT = 0x00010000u;
 constexpr uint32_t TAG_SWEEP = 0x00020000u;
 constexpr uint32_t TAG_PT = 0x00030000u;
 constexpr uint32_t TAG_SWEEP_MSC = 0x00040000u;
+constexpr uint32_t TAG_SWEEP_PACKED = 0x000A0000u;  // counter = {rank >> 5, sweep, system, tag | call << 8 | colour}, call = 0..5
 constexpr uint64_t MSC_KEY_DOMAIN = 0x6D73635F67726F75ull;
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
@@ -45,9 +52,11 @@ PP_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-PP_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+constexpr int PHILOX_ROUNDS = 7;
+
+PP_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int round = 0; round < 10; round++) {
+    for (int round = 0; round < PHILOX_ROUNDS; round++) {
         uint32_t hi0 = mulhi32(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
         uint32_t hi1 = mulhi32(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0;

@@ -88,9 +88,10 @@ def gather_merge(result, per_sample_means, n_replicas, group=None, dst=0, per_sa
     collectives of ``torch.distributed`` (a few MB of scalars; works on the NCCL and the gloo backend)."""
     import torch.distributed as dist
 
-    part = {"result": result, "per_sample_means": np.asarray(per_sample_means), "n_replicas": int(n_replicas),
-            "per_sample_taus": None if per_sample_taus is None else np.asarray(per_sample_taus),
-            "per_sample_equil": None if per_sample_equil is None else np.asarray(per_sample_equil)}
+    part = None if result is None else {  # None: a rank without realizations (it still takes part in the collective)
+        "result": result, "per_sample_means": np.asarray(per_sample_means), "n_replicas": int(n_replicas),
+        "per_sample_taus": None if per_sample_taus is None else np.asarray(per_sample_taus),
+        "per_sample_equil": None if per_sample_equil is None else np.asarray(per_sample_equil)}
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merge_results([part])
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -114,15 +115,30 @@ class ShardedIsingSimulation:
         self.world = (dist.get_world_size() if live else 1) if world is None else world
         self.n_disorder = int(n_disorder)
         self.first, self.count = shard_bounds(self.n_disorder, self.world, self.rank)
-        if self.count == 0:
-            raise ValueError("more ranks than 32-realization groups: nothing to do on this rank")
-        shard = couplings(self.first, self.count) if callable(couplings) else np.asarray(couplings)[self.first:self.first + self.count]
         self.n_replicas = 1 if n_replicas is None else int(n_replicas)
-        self.sim = IsingSimulation(lattice_shape, shard, temperatures, n_replicas, neighbor_offsets, seed, layout=layout,
-                                   device=self.rank if device is None else device, sample_offset=self.first)
+        self.sim = None
+        if self.count == 0:  # more ranks than 32-realization groups: this rank only takes part in the gather
+            return
+        shard = couplings(self.first, self.count) if callable(couplings) else np.asarray(couplings)[self.first:self.first + self.count]
+        dev = self.rank if device is None else device
+        if layout == "auto" and self.n_disorder >= 32 and not isinstance(shard, str) and np.any(np.asarray(shard) < 0):
+            # The layout is a property of the WHOLE batch (trajectories depend on it: word-group keys and shared draws in the
+            # multispin layout, per-realization keys in int8): a last shard of fewer than 32 realizations must not fall back
+            # to int8 on its own.  Partial word groups are supported by the multispin kernels.
+            try:
+                self.sim = IsingSimulation(lattice_shape, shard, temperatures, n_replicas, neighbor_offsets, seed, layout="msc",
+                                           device=dev, sample_offset=self.first)
+            except ValueError:  # not a +-1 model (or too many directions): what the unsharded handle would decide too
+                self.sim = None
+            layout = "int8"
+        if self.sim is None:
+            self.sim = IsingSimulation(lattice_shape, shard, temperatures, n_replicas, neighbor_offsets, seed, layout=layout,
+                                       device=dev, sample_offset=self.first)
 
     def sample(self, *args, **kwargs):
         """Every rank samples its block; rank 0 returns the merged dict, the others None."""
+        if self.sim is None:
+            return gather_merge(None, None, self.n_replicas)
         local = self.sim.sample(*args, **kwargs)
         return gather_merge(local, self.sim.last_per_sample_means, self.n_replicas,
                             per_sample_taus=getattr(self.sim, "last_per_sample_taus", None),

@@ -32,9 +32,30 @@ def test_philox4x32_10_random123_kats(oracle):
         0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
 
 
+def test_philox4x32_7_random123_kats(oracle):
+    # Random123 kat_vectors: philox4x32 7 rounds -- the RNG-SPEC v2 generator
+    f = 0xFFFFFFFF
+    for rounds in (7, None):
+        assert oracle.philox4x32([0, 0, 0, 0], [0, 0], rounds).tolist() == [0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48]
+        assert oracle.philox4x32([f, f, f, f], [f, f], rounds).tolist() == [0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662]
+        assert oracle.philox4x32([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], rounds).tolist() == [
+            0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A]
+
+
+def test_packed_draws_use_every_bit_of_six_calls_once(oracle):
+    key, sweep, stream, tagc = 0x0123456789ABCDEF, 11, 3, oracle.TAG_SWEEP_PACKED | 1
+    w = np.concatenate([oracle.philox4x32([9, sweep, stream, tagc | (call << 8)], [key & 0xFFFFFFFF, key >> 32]) for call in range(6)])
+    bits = "".join(format(int(x), "032b") for x in w)
+    got = [oracle.lib().orc_draw24_packed(key, 9 * 32 + b, sweep, stream, tagc) for b in range(32)]
+    for g in range(8):
+        a, b_, c = (int(w[3 * g + j]) for j in range(3))
+        assert got[4 * g:4 * g + 4] == [a >> 8, b_ >> 8, c >> 8, ((a & 255) << 16) | ((b_ & 255) << 8) | (c & 255)]
+    assert sum(bin(d).count("1") for d in got) == bits.count("1")  # a permutation of the 768 generated bits
+
+
 def test_draw24_serves_four_indices_per_call(oracle):
     key = 0x0123456789ABCDEF
-    out = oracle.philox4x32_10([5, 7, 9, oracle.TAG_SWEEP | 1], [key & 0xFFFFFFFF, key >> 32])
+    out = oracle.philox4x32([5, 7, 9, oracle.TAG_SWEEP | 1], [key & 0xFFFFFFFF, key >> 32])
     for lane in range(4):
         assert oracle.lib().orc_draw24(key, 20 + lane, 7, 9, oracle.TAG_SWEEP | 1) == int(out[lane]) >> 8
 

@@ -13,25 +13,25 @@ ROOT = Path(__file__).resolve().parent.parent
 SHAPE, TEMPS, R, D = (4, 4, 4), np.linspace(0.8, 1.6, 4).astype(np.float32), 2, 96
 
 
-def _couplings():
+def _couplings(n=D):
     rng = np.random.default_rng(5)
-    return (2 * rng.integers(0, 2, size=(D,) + SHAPE + (3,)) - 1).astype(np.float32)
+    return (2 * rng.integers(0, 2, size=(n,) + SHAPE + (3,)) - 1).astype(np.float32)
 
 
-def _run_block(first, count):
+def _run_block(first, count, n=D):
     import oracle
     import peapods_b200  # noqa: F401  (the package must import without a GPU)
     from peapods_b200 import colouring
 
     colour, _ = colouring(SHAPE)
-    sim = oracle.Sim(SHAPE, _couplings()[first:first + count], TEMPS, n_replicas=R, seed=77, rng_mode=oracle.RNG_PHILOX_MSC,
+    sim = oracle.Sim(SHAPE, _couplings(n)[first:first + count], TEMPS, n_replicas=R, seed=77, rng_mode=oracle.RNG_PHILOX_MSC,
                      colour=colour, sample_offset=first)
     res = sim.sample(30, "metropolis", pt_interval=1, pt_schedule="full_ladder", autocorrelation_max_lag=4)
     res["overlap_histogram"] = [h for h in res["overlap_histogram"]]
     return res, sim.last_per_sample_means, sim.last_per_sample_taus
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, n=D):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -39,9 +39,12 @@ def _worker(rank, world, port, out_path):
     from peapods_b200.sharded import gather_merge, shard_bounds
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    first, count = shard_bounds(D, world, rank)
-    res, means, taus = _run_block(first, count)
-    merged = gather_merge(res, means, R, per_sample_taus=taus)
+    first, count = shard_bounds(n, world, rank)
+    if count == 0:  # more ranks than 32-realization groups: the rank still takes part in the collective
+        merged = gather_merge(None, None, R)
+    else:
+        res, means, taus = _run_block(first, count, n)
+        merged = gather_merge(res, means, R, per_sample_taus=taus)
     if rank == 0:
         np.savez(out_path, **{k: np.asarray(v) for k, v in merged.items() if k != "per_disorder"},
                  **{"pt_" + k: v for k, v in merged["per_disorder"]["parallel_tempering"].items()})
@@ -80,6 +83,25 @@ def test_two_gloo_ranks_reproduce_the_unsharded_run(tmp_path):
         np.testing.assert_allclose(merged[k], ref[k], rtol=1e-12, atol=0)   # partial sums re-associated
     for k in ("per_sample_overlap_histogram", "per_sample_ql_at_q_sum"):
         assert np.array_equal(merged[k], ref[k]), k
+    for k, v in ref["per_disorder"]["parallel_tempering"].items():
+        assert np.array_equal(merged["pt_" + k], v), k
+
+
+def test_an_empty_rank_and_a_partial_word_group_still_merge_to_the_unsharded_run(tmp_path):
+    """40 realizations over 3 ranks: 32 + 8 + 0 (the empty rank used to raise while the others waited in the
+    gather, and the 8-realization shard must keep the batch's multispin keys)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out_path = str(tmp_path / "merged40.npz")
+    mp.spawn(_worker, args=(3, port, out_path, 40), nprocs=3, join=True)
+    merged = np.load(out_path)
+    sys.path.insert(0, str(ROOT))
+    ref, _, _ = _run_block(0, 40, 40)
+    for k in ("mags", "mags2", "energies", "energies2", "overlap2", "overlap4", "link_overlap", "mags2_tau"):
+        assert np.array_equal(merged[k], ref[k]), k
+    assert np.array_equal(merged["overlap_histogram"], np.stack(ref["overlap_histogram"]))
+    assert np.array_equal(merged["per_sample_overlap_histogram"], ref["per_sample_overlap_histogram"])
     for k, v in ref["per_disorder"]["parallel_tempering"].items():
         assert np.array_equal(merged["pt_" + k], v), k
 
