@@ -17,6 +17,12 @@ A "step" is one `sample(n_sweeps=SWEEPS_PER_STEP)` call.  Three measurements:
           dict back (D2H); wall clock bracketed by synchronize, max over ranks.
   roofline  the sweep kernel alone: algorithmic bytes per launch / its mean launch duration,
           measured live with CUDA events around every sweep-kernel launch (separate, untimed pass).
+The same JSON line carries sub-records measured in the same invocation (each with its own small, fixed step count):
+  c2_strong   BASELINE configs[1] at its NAMED size (4096 samples in total) split over the N ranks (strong scaling)
+  c5          BASELINE configs[4] (1024^3 ferromagnet at T_c) slab-decomposed over the N ranks: value, e2e, roofline, halo bytes,
+              and an N-rank parity check (NCCL ranks == the same slabs kept on one device, bit for bit)
+  c1, c3, c4  (N = 1) BASELINE configs[0], [2], [3] through the public API
+  e2e_default_api   the headline's e2e with the reference's default return set (per-realization histograms included)
 `--impl reference` times the CPU restatement of the reference's rayon path (oracle, typewriter order +
 xoshiro streams, threads over realizations) on the box's host cores, on a bounded sample of the same
 workload.  The Rust crate itself cannot be built in this image (no cargo/rustc).
@@ -201,6 +207,187 @@ def workload_config(args, samples_per_gpu):
     }
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# sub-records of the one JSON line
+TRI_OFFSETS = [[1, 0], [0, 1], [1, -1]]
+
+
+class Ranks:
+    """barrier / reductions over the ranks of the (already initialised) default process group"""
+
+    def __init__(self, world, rank, local_rank):
+        self.world, self.rank, self.local_rank = world, rank, local_rank
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def _reduce(self, x, op):
+        import torch
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        import torch.distributed as dist
+
+        return self._reduce(x, dist.ReduceOp.MAX)
+
+    def sum(self, x):
+        import torch.distributed as dist
+
+        return self._reduce(x, dist.ReduceOp.SUM)
+
+
+def slab_rank_parity(ranks: Ranks):
+    """The N-rank slab path (ncclSend / ncclRecv halos, ncclAllReduce of the bond counts) against the SAME decomposition kept on
+    one device (device copies instead of NCCL; that form is checked bit for bit against the CPU restatement by tests/): spins of
+    every rank, energies and the statistics must be identical.  Byte storage and bit-packed storage, PT over three temperatures."""
+    import torch
+    import torch.distributed as dist
+
+    import peapods_b200 as pb
+    from peapods_b200.sharded import SlabIsingSimulation
+
+    world, rank = ranks.world, ranks.rank
+    ok = True
+    for shape in ((8 * world, 6, 16), (4 * world, 16, 128)):
+        temps = np.asarray([4.0, 4.511, 5.0], np.float32)
+        kw = dict(warmup_ratio=0.25, pt_interval=1, pt_schedule="full_ladder")
+        sim = SlabIsingSimulation(shape, temps, 99)
+        res = sim.sample(25, "metropolis", **kw)
+        mine = torch.from_numpy(sim.get_spins().astype(np.int8)).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        if world > 1:
+            dist.gather(mine, parts, dst=0)
+        else:
+            parts = [mine]
+        if rank == 0:
+            one = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 99, layout="slab", slab_ranks=world, slab_rank=-1,
+                                     device=ranks.local_rank)
+            ref = one.sample(25, "metropolis", **kw)
+            T, per = len(temps), int(np.prod(shape)) // world
+            full = np.concatenate([p.cpu().numpy().reshape(T, per) for p in parts], axis=1).reshape(-1)
+            ok = ok and np.array_equal(full, one.get_spins(0))
+            ok = ok and all(np.array_equal(res[k], ref[k]) for k in ("mags", "mags2", "mags4", "energies", "energies2"))
+            del one
+        del sim
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.broadcast(flag, src=0)
+    return "PASS" if int(flag.item()) else "FAIL"
+
+
+def bench_c5(ranks: Ranks, extent: int, n_sweeps: int, steps: int, warmup: int, clock_index=None):
+    """BASELINE configs[4]: one extent^3 ferromagnet at T_c cut into one slab per rank; returns the sub-record (every rank)."""
+    from peapods_b200.sharded import SlabIsingSimulation
+
+    world = ranks.world
+    shape = (extent, extent, extent)
+    temps = np.asarray([4.511], dtype=np.float32)  # T_c of the 3-D Ising model (tests/utils.py:9 in the reference)
+    attempts_step = float(extent) ** 3 * n_sweeps
+    kw = dict(warmup_ratio=0.25)
+    sim = SlabIsingSimulation(shape, temps, dynamics_seed())
+    packed = bool(sim.sim.slab_packed)
+    for _ in range(warmup):
+        sim.sample(n_sweeps, "metropolis", **kw)
+    ranks.barrier()
+    dev_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.sample(n_sweeps, "metropolis", **kw)
+        dev_ms += sim.sim.last_sweep_loop_ms
+        launches += sim.sim.last_kernel_launches
+    ranks.barrier()
+    wall_ms = ranks.max(1e3 * (time.perf_counter() - t0))
+    dev_ms = ranks.max(dev_ms)
+    value = attempts_step * steps / (dev_ms * 1e6)
+    res = sim.sample(n_sweeps, "metropolis", profile=True, **kw)
+    k_ms = ranks.max(sim.sim.last_sweep_kernel_ms)
+    peak, peak_src = peaks()
+    b_alg = 0.25 if packed else 2.0  # SURVEY.md 8d: one bit (byte) read + one written per attempt
+    alg = b_alg * attempts_step / world
+    achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    energy = float(res["energies"][0])
+    del sim
+
+    def e2e_step():
+        s = SlabIsingSimulation(shape, temps, dynamics_seed())
+        out = s.sample(n_sweeps, "metropolis", **kw)
+        nb = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray))
+        del s
+        return nb
+
+    for _ in range(max(warmup, 1)):
+        e2e_step()
+    ranks.barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(steps):
+        d2h = e2e_step()
+    ranks.barrier()
+    e2e_ms = ranks.max(1e3 * (time.perf_counter() - t0))
+    half_plane = extent * extent // (16 if packed else 1)  # bytes of one colour of one plane (packed) / of one plane (bytes)
+    return {
+        "workload": f"C5: single 3-D Ising ferromagnet {extent}^3 at T_c=4.511, checkerboard Metropolis, slab-decomposed along x0 over "
+                    f"{world} GPU(s)" + (" with NCCL halo exchange" if world > 1 else ""),
+        "value": value, "unit": UNIT, "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup, "sweeps_per_step": n_sweeps,
+        "ms_per_step": dev_ms / steps, "wall_ms_per_step": wall_ms / steps,
+        "e2e": {"value": attempts_step * steps / (e2e_ms * 1e6), "unit": UNIT, "h2d_bytes_per_step": int(temps.nbytes),
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps},
+        "layout": "slab, one bit per spin (32 same-colour sites of a row per u32 word)" if packed else "slab (u8, stride geometry)",
+        "dtype": "u32 bit-sliced (packed draws, integer acceptance table)" if packed else "u8",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "alg_bytes_per_attempt": b_alg, "kernel": "slabp_sweep_kernel" if packed else "slab_sweep_kernel",
+                     "sweep_kernel_ms": k_ms, "peak_source": peak_src,
+                     "note": "the kernel is bound by the generator's multiplies and three compares per site, not by HBM (DESIGN.md)"},
+        "halo_bytes_per_half_step_per_rank": 0 if world == 1 else 2 * half_plane,
+        "gpu_launches": launches, "energy_per_spin_last_step": energy,
+        "l2": f"{extent ** 3 / world / (8 if packed else 1) / 2 ** 20:.0f} MiB of spins per GPU vs 126 MB L2",
+    }
+
+
+def bench_small_configs():
+    """BASELINE configs[0], [2], [3] through the public API on this GPU (N = 1 only): device time of the sweep loop, best of 2."""
+    import peapods_b200 as pb
+
+    peak, _ = peaks()
+    out = {}
+
+    def run(key, label, model, n_sweeps, mode, b_alg, **kw):
+        model.sample(max(4, n_sweeps // 4), mode, **kw)
+        best, launches = None, 0
+        for _ in range(2):
+            model.sample(n_sweeps, mode, **kw)
+            dev = model._sim.last_sweep_loop_ms
+            best, launches = (dev, model._sim.last_kernel_launches) if best is None or dev < best else (best, launches)
+        attempts = float(model.n_spins) * model.n_temps * model.n_replicas * model.n_disorder * n_sweeps
+        v = attempts / best / 1e6
+        out[key] = {"workload": label, "value": v, "unit": UNIT, "sweeps": n_sweeps, "ms": best, "gpu_launches": launches,
+                    "layout": model._sim.layout, "alg_bytes_per_attempt": b_alg, "hbm_roofline_frac": v * b_alg / peak}
+
+    m = pb.Ising((32, 32), "ferro", np.linspace(1.5, 3.0, 16), n_replicas=2, seed=SEED)
+    run("c1", "C1: 2-D Ising ferromagnet 32x32, Metropolis + PT every sweep, 16 temps 1.5-3.0, 2 replicas, 5000 sweeps (README quickstart)",
+        m, 5000, "metropolis", 2.0, pt_interval=1)
+    tc = 4.0 / np.log(3.0)
+    m = pb.Ising((256, 256), "ferro", np.linspace(tc - 0.4, tc + 0.4, 64), n_replicas=2, neighbor_offsets=TRI_OFFSETS, seed=SEED)
+    run("c3", "C3: 2-D triangular ferromagnet 256x256 (custom neighbor_offsets), Gibbs, 64 temps around 4/ln3, 2 replicas",
+        m, 400, "gibbs", 2.0)
+    m = pb.Ising((32, 32, 32), "gaussian", np.linspace(0.8, 1.8, 48), n_replicas=4, n_disorder=512, seed=SEED)
+    run("c4", "C4: 3-D EA Gaussian 32^3, 48 temps 0.8-1.8, 4 replicas, 512 disorder samples, Metropolis + PT + overlap",
+        m, 20, "metropolis", 2.0 + 4.0 * 3 / 192, pt_interval=1, per_sample=False)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -335,6 +522,62 @@ def run_ours(args):
             assert np.all(np.isfinite(merged["energies"])) and len(merged["overlap_histogram"]) == N_TEMPS
         del s
 
+    # ---- sub-records of the same line (module docstring) ---------------------------------------------
+    ranks = Ranks(world, rank, local_rank)
+    sub = {}
+    if not args.no_sub_records:
+        # BASELINE configs[1] at its named size, split over the ranks (strong scaling; N = 1 is the headline itself)
+        if world > 1:
+            Ds = SAMPLES_PER_GPU // world
+            Js = make_couplings(rank * Ds, Ds, SAMPLES_PER_GPU)
+            ssim = pb.IsingSimulation(list(SHAPE), Js, temps, N_REPLICAS, None, seed, layout="msc", device=local_rank,
+                                      sample_offset=rank * Ds)
+            for _ in range(2):
+                ssim.sample(n_sweeps, "metropolis", **kw)
+            barrier()
+            s_ms = 0.0
+            for _ in range(3):
+                ssim.sample(n_sweeps, "metropolis", **kw)
+                s_ms += ssim.last_sweep_loop_ms
+            barrier()
+            s_ms = max_over_ranks(s_ms)
+            s_val = float(np.prod(SHAPE)) * N_TEMPS * N_REPLICAS * SAMPLES_PER_GPU * n_sweeps * 3 / (s_ms * 1e6)
+            sub["c2_strong"] = {"workload": f"C2 at its named size: {SAMPLES_PER_GPU} disorder samples in total, {Ds} per GPU", "value": s_val,
+                                "unit": UNIT, "scaling": "strong", "n_gpus": world, "steps": 3, "warmup": 2, "ms_per_step": s_ms / 3,
+                                "hbm_roofline_frac": s_val * B_ALG_MSC / (world * peak)}
+            del ssim
+        else:
+            sub["c2_strong"] = {"workload": f"C2 at its named size: {SAMPLES_PER_GPU} disorder samples in total", "value": value, "unit": UNIT,
+                                "scaling": "strong", "n_gpus": 1, "note": "N = 1: the headline itself"}
+        sub["c5"] = bench_c5(ranks, args.c5_extent, 4, 2, 1)
+        sub["c5"]["rank_parity"] = slab_rank_parity(ranks)
+        sub["c5"]["rank_parity_note"] = ("N NCCL ranks == the same N slabs on one device (device copies), bit for bit: spins, energies, "
+                                         "statistics; byte and bit-packed storage, PT over three temperatures")
+        if world == 1:
+            sub.update(bench_small_configs())
+            # the reference API's default return set: per-realization histograms [D][T][N+1] x 3 (src/lib.rs:385-411), 12.9 GB at C2
+            kw_def = dict(kw, per_sample=True)
+
+            def e2e_default():
+                s = pb.IsingSimulation(list(SHAPE), J, temps, N_REPLICAS, None, seed, layout="msc", device=local_rank, sample_offset=first)
+                out = s.sample(n_sweeps, "metropolis", **kw_def)
+                nb = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray))
+                del s, out
+                return nb
+
+            e2e_default()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nb = 0
+            for _ in range(2):
+                nb = e2e_default()
+            torch.cuda.synchronize()
+            def_ms = 1e3 * (time.perf_counter() - t0) / 2
+            sub["e2e_default_api"] = {"value": attempts_step / (def_ms * 1e6), "unit": UNIT, "ms_per_step": def_ms, "steps": 2, "warmup": 1,
+                                      "d2h_bytes_per_step": nb, "h2d_bytes_per_step": h2d,
+                                      "note": "per_sample=True: what the reference returns by default when D > 1 and R >= 2; the headline "
+                                              "e2e above runs with per_sample=False (aggregated histograms only)"}
+
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -359,6 +602,8 @@ def run_ours(args):
             "roofline": roofline, "hbm_roofline_frac_whole_step": value * B_ALG_MSC / (world * peak),
             "sweeps_only": sweeps_only, "cpu_baseline": cpu,
         }
+        line["e2e"]["note"] = "per_sample=False (aggregated histograms); the default return set is timed in e2e_default_api"
+        line.update(sub)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -366,13 +611,12 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# --workload c5: BASELINE configs[4], one 3-D ferromagnet at T_c cut into slabs over the ranks (strong scaling)
+# --workload c5: BASELINE configs[4] alone, one 3-D ferromagnet at T_c cut into slabs over the ranks (strong scaling)
 def run_c5(args):
     import torch
     import torch.distributed as dist
 
     from peapods_b200 import _lib
-    from peapods_b200.sharded import SlabIsingSimulation
 
     _lib.load()
     if not torch.cuda.is_available():
@@ -383,74 +627,16 @@ def run_c5(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    L = args.c5_extent
-    shape = (L, L, L)
-    temps = np.asarray([4.511], dtype=np.float32)  # T_c of the 3-D Ising model (tests/utils.py:9 in the reference)
-    n_sweeps = args.sweeps_per_step
-    attempts_step = float(L) ** 3 * n_sweeps
-    kw = dict(warmup_ratio=0.25)
-    sim = SlabIsingSimulation(shape, temps, dynamics_seed())
-    for _ in range(args.warmup):
-        sim.sample(n_sweeps, "metropolis", **kw)
-    barrier()
-    dev_ms, launches = 0.0, 0
+    ranks = Ranks(world, rank, local_rank)
     with ClockSampler(local_rank) as clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            sim.sample(n_sweeps, "metropolis", **kw)
-            dev_ms += sim.sim.last_sweep_loop_ms
-            launches += sim.sim.last_kernel_launches
-        barrier()
-        wall_ms = 1e3 * (time.perf_counter() - t0)
-    dev_ms, wall_ms = max_over_ranks(dev_ms), max_over_ranks(wall_ms)
-    value = attempts_step * args.steps / (dev_ms * 1e6)
-    res = sim.sample(n_sweeps, "metropolis", profile=True, **kw)
-    k_ms, k_n = max_over_ranks(sim.sim.last_sweep_kernel_ms), max(sim.sim.last_sweep_kernel_launches, 1)
-    peak, peak_src = peaks()
-    alg = 2.0 * attempts_step / world  # int8: one byte read + one written per attempt, per rank
-    achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": args.traffic,
-                "kernel": "slab_sweep_kernel (all launches of one sample() call, halo waits included)", "peak_source": peak_src,
-                "alg_bytes_per_call_per_rank": alg, "sweep_kernel_ms": k_ms}
-    energy = float(res["energies"][0])
-    del sim
-
-    def e2e_step():
-        s = SlabIsingSimulation(shape, temps, dynamics_seed())
-        out = s.sample(n_sweeps, "metropolis", **kw)
-        nb = sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray))
-        del s
-        return nb
-
-    for _ in range(max(args.warmup, 1)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(args.steps):
-        d2h = e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-
+        rec = bench_c5(ranks, args.c5_extent, args.sweeps_per_step, args.steps, args.warmup)
+    rec["rank_parity"] = slab_rank_parity(ranks)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 
         Lc, nsw = 128, 4  # the reference runs one realization with one system on ONE core (mod.rs:874-885, parallel.rs:39)
+        temps = np.asarray([4.511], dtype=np.float32)
         o = oracle.Sim((Lc, Lc, Lc), np.ones((Lc, Lc, Lc, 3), np.float32), temps, n_replicas=1, seed=dynamics_seed(),
                        rng_mode=oracle.RNG_XOSHIRO)
         t0 = time.perf_counter()
@@ -459,18 +645,17 @@ def run_c5(args):
         cpu = {"value": float(Lc) ** 3 * nsw / (dt * 1e9), "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{Lc}^3 lattice x {nsw} sweeps ({dt:.1f} s): one system = one thread in the reference"}
     if rank == 0:
+        L = args.c5_extent
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8 (one byte per spin, SWAR neighbour counts; integer acceptance table)", "data": "synthetic",
-            "config": {"workload": f"C5: single 3-D Ising ferromagnet {L}^3 at T_c=4.511, checkerboard Metropolis, slab-decomposed along x0 "
-                                   f"over {world} GPU(s) with NCCL halo exchange", "lattice": list(shape), "n_temps": 1, "n_replicas": 1,
-                       "sweeps_per_step": n_sweeps, "warmup_ratio": 0.25, "layout": "slab (u8, stride geometry)",
-                       "l2": f"{L ** 3 / world / 2 ** 20:.0f} MiB of spins per GPU vs 126 MB L2"},
-            "e2e": {"value": attempts_step * args.steps / (e2e_ms * 1e6), "unit": UNIT, "h2d_bytes_per_step": int(temps.nbytes),
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks.summary(), "roofline": roofline,
-            "cpu_baseline": cpu, "energy_per_spin_last_step": energy,
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": rec["dtype"], "data": "synthetic",
+            "config": {"workload": rec["workload"], "lattice": [L, L, L], "n_temps": 1, "n_replicas": 1,
+                       "sweeps_per_step": args.sweeps_per_step, "warmup_ratio": 0.25, "layout": rec["layout"], "l2": rec["l2"]},
+            "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "wall_ms_per_step": rec["wall_ms_per_step"],
+            "clocks": clocks.summary(), "roofline": rec["roofline"], "cpu_baseline": cpu,
+            "halo_bytes_per_half_step_per_rank": rec["halo_bytes_per_half_step_per_rank"], "rank_parity": rec["rank_parity"],
+            "energy_per_spin_last_step": rec["energy_per_spin_last_step"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -488,6 +673,7 @@ def main():
                     help="sweeps of one sample() call = one step (default: 1024 for c2, 32 for c5; the CPU arm caps its steps at 256)")
     ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="only the headline (skip c2_strong / c5 / c1 / c3 / c4 / e2e_default_api)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
     ap.add_argument("--workload", choices=("c2", "c5"), default="c2", help="c2: BASELINE headline (default); c5: one large lattice in slabs")
     ap.add_argument("--c5-extent", type=int, default=1024)

@@ -176,6 +176,8 @@ pp_status pp_get_energies(pp_sim *sim, int64_t realization, float *out /* [S] by
 int32_t pp_get_layout(const pp_sim *sim);
 /* 1 when sweeps run through the stride-based 3-D multispin kernel (pp_kernels_msc3d.cuh), else 0 */
 int32_t pp_uses_msc3d(const pp_sim *sim);
+/* 1 when a PP_LAYOUT_SLAB handle stores one bit per spin (shape[2] % 64 == 0: pp_kernels_slabp.cuh, packed draw mapping), else 0 */
+int32_t pp_slab_packed(const pp_sim *sim);
 
 /* operator-level entry points with the reference's slice semantics (unit-level parity tests):
  * H2D -> kernel -> D2H on the handle's state. */

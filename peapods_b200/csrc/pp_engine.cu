@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -360,8 +361,10 @@ static void free_sim(pp_sim *s) {
     if (s->slab) {
         SlabState *sl = s->slab;
         if (sl->comm_stream) cudaStreamSynchronize(sl->comm_stream);
-        if (sl->comm) nccl_api().CommDestroy(sl->comm);
+        if (sl->comm && !sl->comm_cached) nccl_api().CommDestroy(sl->comm);
         for (uint8_t *b : sl->buffers) cudaFree(b);
+        for (SlabPView &v : sl->pparts) cudaFree(v.words);
+        if (sl->ev_main) cudaEventDestroy(sl->ev_main);
         if (sl->d_partial) cudaFree(sl->d_partial);
         if (sl->ev_boundary) cudaEventDestroy(sl->ev_boundary);
         if (sl->ev_halo) cudaEventDestroy(sl->ev_halo);
@@ -380,6 +383,7 @@ static void free_sim(pp_sim *s) {
 extern "C" void pp_destroy(pp_sim *sim) { free_sim(sim); }
 extern "C" int32_t pp_get_layout(const pp_sim *sim) { return sim ? sim->layout : 0; }
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
+extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
 extern "C" int64_t pp_local_spin_count(const pp_sim *sim) {
     if (!sim) return 0;
     return sim->slab ? sim->slab->local_planes() * sim->slab->plane : sim->mv.N;
@@ -556,10 +560,41 @@ static pp_status launch_msc3d(pp_sim *s, Ctx &c, const ModelView &m, int sweep_m
         if (_r != ncclSuccess) return fail(PP_ERR_NCCL, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
     } while (0)
 
-// boundary planes of every local slab -> the halo planes of their neighbours, enqueued on `stream`
-static pp_status slab_exchange(pp_sim *s, cudaStream_t stream) {
+// boundary planes of every local slab -> the halo planes of their neighbours, enqueued on `stream`.
+// Bit-packed storage: colour = 0 / 1 sends only that colour's half of the planes (what a colour half-step changed), -1 both.
+static pp_status slab_exchange(pp_sim *s, cudaStream_t stream, int colour = -1) {
     SlabState *sl = s->slab;
     const int S = s->mv.S;
+    if (sl->packed) {
+        const SlabPView &v0 = sl->pparts[0];
+        const int64_t first = colour == 1 ? v0.half : 0, count = colour < 0 ? v0.plane : v0.half;  // words inside a plane
+        const size_t bytes = sizeof(uint32_t) * (size_t)count;
+        if (sl->rank < 0 || sl->ranks == 1) {
+            const int n = (int)sl->pparts.size();
+            for (int r = 0; r < n; r++) {
+                const SlabPView &me = sl->pparts[(size_t)r], &lo = sl->pparts[(size_t)((r + n - 1) % n)], &up = sl->pparts[(size_t)((r + 1) % n)];
+                for (int sys = 0; sys < S; sys++) {
+                    const int64_t o = (int64_t)sys * me.sys_stride + first;
+                    CUDA_TRY(cudaMemcpyAsync(lo.words + o + (int64_t)(sl->P + 1) * me.plane, me.words + o + me.plane, bytes,
+                                             cudaMemcpyDeviceToDevice, stream));
+                    CUDA_TRY(cudaMemcpyAsync(up.words + o, me.words + o + (int64_t)sl->P * me.plane, bytes, cudaMemcpyDeviceToDevice, stream));
+                }
+            }
+            return PP_OK;
+        }
+        NcclApi &nc = nccl_api();
+        const int lo = (sl->rank + sl->ranks - 1) % sl->ranks, up = (sl->rank + 1) % sl->ranks;
+        NCCL_TRY(nc.GroupStart());
+        for (int sys = 0; sys < S; sys++) {
+            uint32_t *b = v0.words + (int64_t)sys * v0.sys_stride + first;
+            NCCL_TRY(nc.Send(b + v0.plane, bytes, ncclUint8, lo, sl->comm, stream));
+            NCCL_TRY(nc.Send(b + (int64_t)sl->P * v0.plane, bytes, ncclUint8, up, sl->comm, stream));
+            NCCL_TRY(nc.Recv(b + (int64_t)(sl->P + 1) * v0.plane, bytes, ncclUint8, up, sl->comm, stream));
+            NCCL_TRY(nc.Recv(b, bytes, ncclUint8, lo, sl->comm, stream));
+        }
+        NCCL_TRY(nc.GroupEnd());
+        return PP_OK;
+    }
     const size_t bytes = (size_t)sl->plane;
     if (sl->rank < 0 || sl->ranks == 1) {  // all slabs local: device copies
         const int n = (int)sl->parts.size();
@@ -587,6 +622,75 @@ static pp_status slab_exchange(pp_sim *s, cudaStream_t stream) {
     }
     NCCL_TRY(nc.GroupEnd());
     return PP_OK;
+}
+
+// totals of the per-slab partial sums -> energies / magnetisations of every system, identical on every rank
+static pp_status slab_finish_energy(pp_sim *s, const ModelView &m, cudaStream_t stream, bool want_mags) {
+    SlabState *sl = s->slab;
+    if (sl->comm)
+        NCCL_TRY(nccl_api().AllReduce(sl->d_partial, sl->d_partial, 2 * (size_t)m.S, ncclUint64, ncclSum, sl->comm, stream));
+    slab_finish_energy_kernel<<<blocks_for(m.S, 128), 128, 0, stream>>>(m, sl->d_partial, want_mags ? 1 : 0);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+// one launch of the bit-packed kernel over planes [pa, pa + np) (+ plane pb when pb > 0)
+static pp_status slabp_launch(pp_sim *s, const ModelView &m, const SlabPView &v, cudaStream_t stream, int colour, uint32_t sweep,
+                              int pa, int np, int pb, int nm, bool update, bool acc) {
+    const unsigned rows = (unsigned)(np + (pb > 0 ? 1 : 0));
+    if (rows == 0) return PP_OK;
+    const dim3 grid(blocks_for(v.half, SLABP_THREADS), rows, (unsigned)m.S);
+    unsigned long long *partial = s->slab->d_partial;
+#define PP_SLABP(NM_, U_, A_) slabp_sweep_kernel<NM_, U_, A_><<<grid, SLABP_THREADS, 0, stream>>>(m, v, colour, sweep, pa, np, pb, partial)
+    if (!update) PP_SLABP(3, false, true);
+    else if (nm == 3) { if (acc) PP_SLABP(3, true, true); else PP_SLABP(3, true, false); }
+    else { if (acc) PP_SLABP(7, true, true); else PP_SLABP(7, true, false); }
+#undef PP_SLABP
+    s->launches++;
+    return PP_OK;
+}
+
+// bit-packed sweeps; want_energy: the colour-1 pass of the last sweep also counts bonds and spins (n_sweeps = 0: a counting
+// pass over the current state), and the totals become energies / magnetisations
+static pp_status slabp_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream, uint32_t sweep_index, int n_sweeps, int sweep_mode,
+                              bool want_energy, bool want_mags) {
+    SlabState *sl = s->slab;
+    const int nm = sweep_mode == PP_SWEEP_GIBBS ? sl->nm_gibbs : sl->nm_metro;
+    if (n_sweeps > 0 && !(sweep_mode == PP_SWEEP_GIBBS ? sl->mono_gibbs : sl->mono_metro))
+        return fail(PP_ERR_UNSUPPORTED, "bit-packed slab kernel: the acceptance table does not grow with the number of unsatisfied bonds");
+    const uint64_t key = realization_seed(m.seed, (uint64_t)m.sample_offset);
+    for (SlabPView &v : sl->pparts) { v.k0 = (uint32_t)key; v.k1 = (uint32_t)(key >> 32); }
+    const bool multi = sl->pparts.size() > 1 || sl->comm;
+    pp_status st = PP_OK;
+    if (want_energy) CUDA_TRY(cudaMemsetAsync(sl->d_partial, 0, sizeof(unsigned long long) * 2 * (size_t)m.S, stream));
+    if (n_sweeps == 0 && want_energy) {
+        for (const SlabPView &v : sl->pparts)
+            if ((st = slabp_launch(s, m, v, stream, 1, 0u, 1, sl->P, 0, 3, false, true)) != PP_OK) return st;
+        return slab_finish_energy(s, m, stream, want_mags);
+    }
+    for (int sw = 0; sw < n_sweeps; sw++)
+        for (int colour = 0; colour < 2; colour++) {
+            const bool acc = want_energy && sw == n_sweeps - 1 && colour == 1;
+            const uint32_t sweep = sweep_index + (uint32_t)sw;
+            if (!multi) {  // one slab: every plane in one launch, then the periodic images
+                if ((st = slabp_launch(s, m, sl->pparts[0], stream, colour, sweep, 1, sl->P, 0, nm, true, acc)) != PP_OK) return st;
+                if ((st = slab_exchange(s, stream, colour)) != PP_OK) return st;
+                continue;
+            }
+            // boundary planes + their transfer on the comm stream, interior planes on the main stream, side by side
+            CUDA_TRY(cudaEventRecord(sl->ev_main, stream));
+            CUDA_TRY(cudaStreamWaitEvent(sl->comm_stream, sl->ev_main, 0));
+            for (const SlabPView &v : sl->pparts)
+                if ((st = slabp_launch(s, m, v, sl->comm_stream, colour, sweep, 1, 1, sl->P, nm, true, acc)) != PP_OK) return st;
+            if ((st = slab_exchange(s, sl->comm_stream, colour)) != PP_OK) return st;
+            CUDA_TRY(cudaEventRecord(sl->ev_halo, sl->comm_stream));
+            for (const SlabPView &v : sl->pparts)
+                if ((st = slabp_launch(s, m, v, stream, colour, sweep, 2, sl->P - 2, 0, nm, true, acc)) != PP_OK) return st;
+            CUDA_TRY(cudaStreamWaitEvent(stream, sl->ev_halo, 0));
+        }
+    CUDA_TRY(cudaGetLastError());
+    return want_energy ? slab_finish_energy(s, m, stream, want_mags) : PP_OK;
 }
 
 static pp_status slab_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream, uint32_t sweep_index, int n_sweeps) {
@@ -620,18 +724,14 @@ static pp_status slab_sweeps(pp_sim *s, const ModelView &m, cudaStream_t stream,
 
 static pp_status slab_energy(pp_sim *s, const ModelView &m, cudaStream_t stream, bool want_mags) {
     SlabState *sl = s->slab;
+    if (sl->packed) return slabp_sweeps(s, m, stream, 0u, 0, PP_SWEEP_METROPOLIS, true, want_mags);
     CUDA_TRY(cudaMemsetAsync(sl->d_partial, 0, sizeof(unsigned long long) * 2 * (size_t)m.S, stream));
     const unsigned bx = blocks_for(sl->parts[0].chunks_per_plane, 256);
     for (const SlabView &v : sl->parts) {
         slab_energy_kernel<<<dim3(bx, (unsigned)sl->P, (unsigned)m.S), 256, 0, stream>>>(v, sl->d_partial);
         s->launches++;
     }
-    if (sl->comm)
-        NCCL_TRY(nccl_api().AllReduce(sl->d_partial, sl->d_partial, 2 * (size_t)m.S, ncclUint64, ncclSum, sl->comm, stream));
-    slab_finish_energy_kernel<<<blocks_for(m.S, 128), 128, 0, stream>>>(m, sl->d_partial, want_mags ? 1 : 0);
-    s->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return PP_OK;
+    return slab_finish_energy(s, m, stream, want_mags);
 }
 
 // want_overlap / want_fold: the caller wants the replica-pair dots of the post-sweep state / the recorded-sweep fold;
@@ -645,10 +745,12 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
     if (fused) *fused = false;
     if (s->layout == PP_LAYOUT_SLAB) {
         if (n_sweeps > 0) prof_mark(s, c.stream);
-        pp_status st = slab_sweeps(s, m, c.stream, sweep_index, n_sweeps);
+        // bit-packed storage: bond / spin counts come out of the last colour pass (no second pass over the lattice)
+        pp_status st = s->slab->packed ? slabp_sweeps(s, m, c.stream, sweep_index, n_sweeps, sweep_mode, want_energy, want_mags)
+                                       : slab_sweeps(s, m, c.stream, sweep_index, n_sweeps);
         if (st != PP_OK) return st;
         if (n_sweeps > 0) prof_mark(s, c.stream);
-        return want_energy ? slab_energy(s, m, c.stream, want_mags) : PP_OK;
+        return want_energy && !s->slab->packed ? slab_energy(s, m, c.stream, want_mags) : PP_OK;
     }
     if (s->layout == PP_LAYOUT_MSC) {
         const bool timed = n_sweeps > 0;
@@ -843,6 +945,11 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
             v.k1 = (uint32_t)(key >> 32);
             slab_init_kernel<<<dim3(blocks_for(v.chunks_per_plane, 256), (unsigned)v.P, (unsigned)m.S), 256, 0, s->stream>>>(m, v);
         }
+        for (SlabPView &v : s->slab->pparts) {
+            v.k0 = (uint32_t)key;
+            v.k1 = (uint32_t)(key >> 32);
+            slabp_init_kernel<<<dim3(blocks_for(v.half, SLABP_THREADS), (unsigned)v.P, (unsigned)m.S), SLABP_THREADS, 0, s->stream>>>(m, v);
+        }
         pp_status stx = slab_exchange(s, s->stream);
         if (stx != PP_OK) return stx;
     } else if (s->layout == PP_LAYOUT_MSC) {
@@ -1028,7 +1135,20 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         sl->P = sl->L0 / slab_ranks;
         sl->plane = (int64_t)sl->L1 * sl->L2;
         const int n_local = sl->rank < 0 ? slab_ranks : 1;
-        for (int i = 0; i < n_local; i++) {
+        // one bit per spin whenever the rows split into whole 64-site word pairs (pp_kernels_slabp.cuh); PP_SLAB_BYTES=1 keeps
+        // the byte storage (A/B timing)
+        sl->packed = sl->L2 % 64 == 0 && !(getenv("PP_SLAB_BYTES") && atoi(getenv("PP_SLAB_BYTES")) != 0);
+        for (int i = 0; i < n_local && sl->packed; i++) {
+            SlabPView v{};
+            v.P = sl->P; v.L1 = sl->L1; v.W = sl->L2 / 64;
+            v.half = (int64_t)v.L1 * v.W;
+            v.plane = 2 * v.half;
+            v.sys_stride = (int64_t)(sl->P + 2) * v.plane;
+            v.first_plane = (int64_t)(sl->rank < 0 ? i : sl->rank) * sl->P;
+            CREATE_TRY(cudaMalloc((void **)&v.words, sizeof(uint32_t) * (size_t)(m.S * v.sys_stride)));
+            sl->pparts.push_back(v);
+        }
+        for (int i = 0; i < n_local && !sl->packed; i++) {
             SlabView v{};
             v.P = sl->P; v.L1 = sl->L1; v.L2 = sl->L2;
             v.plane = sl->plane;
@@ -1048,9 +1168,14 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             sl->parts.push_back(v);
         }
         CREATE_TRY(cudaMalloc((void **)&sl->d_partial, sizeof(unsigned long long) * 2 * (size_t)m.S));
-        CREATE_TRY(cudaStreamCreateWithFlags(&sl->comm_stream, cudaStreamNonBlocking));
+        {   // the boundary planes and their transfer run on a stream of their own, ahead of the interior launches
+            int prio_lo = 0, prio_hi = 0;
+            CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CREATE_TRY(cudaStreamCreateWithPriority(&sl->comm_stream, cudaStreamNonBlocking, prio_hi));
+        }
         CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_boundary, cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_halo, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_main, cudaEventDisableTiming));
         if (slab_ranks > 1 && sl->rank >= 0) {
             NcclApi &nc = nccl_api();
             if (!nc.error.empty()) {
@@ -1058,16 +1183,30 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 free_sim(s);
                 return fail(PP_ERR_NCCL, msg);
             }
-            ncclUniqueId id;
-            static_assert(sizeof(ncclUniqueId) == PP_NCCL_ID_BYTES, "ncclUniqueId size");
-            memcpy(&id, desc->nccl_unique_id, sizeof(id));
-            ncclResult_t r = nc.CommInitRank(&sl->comm, slab_ranks, id, sl->rank);
-            if (r != ncclSuccess) {
-                std::string msg = std::string("ncclCommInitRank: ") + nc.GetErrorString(r);
-                sl->comm = nullptr;
-                free_sim(s);
-                return fail(PP_ERR_NCCL, msg);
+            // One communicator per (process, device, world, rank), kept for the life of the process: ncclCommInitRank costs
+            // seconds, a handle is built per model.  Every rank takes the same branch, so the bootstrap token of a later
+            // handle is simply not used.
+            static std::mutex comm_mu;
+            static std::map<std::tuple<int, int, int>, ncclComm_t> comm_cache;
+            std::lock_guard<std::mutex> lock(comm_mu);
+            const std::tuple<int, int, int> ck{s->device, slab_ranks, sl->rank};
+            auto it = comm_cache.find(ck);
+            if (it != comm_cache.end()) {
+                sl->comm = it->second;
+            } else {
+                ncclUniqueId id;
+                static_assert(sizeof(ncclUniqueId) == PP_NCCL_ID_BYTES, "ncclUniqueId size");
+                memcpy(&id, desc->nccl_unique_id, sizeof(id));
+                ncclResult_t r = nc.CommInitRank(&sl->comm, slab_ranks, id, sl->rank);
+                if (r != ncclSuccess) {
+                    std::string msg = std::string("ncclCommInitRank: ") + nc.GetErrorString(r);
+                    sl->comm = nullptr;
+                    free_sim(s);
+                    return fail(PP_ERR_NCCL, msg);
+                }
+                comm_cache[ck] = sl->comm;
             }
+            sl->comm_cached = true;
         }
     } else if (s->layout == PP_LAYOUT_MSC) {
         s->G = (m.D + 31) / 32;
@@ -1172,6 +1311,25 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             uint32_t *&dst = mode == 0 ? s->d_lut_metro : s->d_lut_gibbs;
             CREATE_TRY(pool_alloc(s, (void **)&dst, sizeof(uint32_t) * lut.size()));
             CREATE_TRY(cudaMemcpy(dst, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice));
+        }
+    }
+
+    // bit-packed slab kernel: how many thresholds it compares per site, and whether the counts grow with unsat (they do for
+    // every finite positive temperature; checked because the kernel's carry chain relies on it)
+    if (s->layout == PP_LAYOUT_SLAB && s->slab->packed) {
+        SlabState *sl = s->slab;
+        std::vector<uint32_t> lut((size_t)m.T * 13);
+        for (int mode = 0; mode < 2; mode++) {
+            pp_metropolis_lookup(s->temps.data(), m.T, 3, mode, lut.data());
+            bool mono = true, fast = true;
+            for (int t = 0; t < m.T; t++)
+                for (int u = 0; u <= 6; u++) {
+                    const uint32_t c = lut[(size_t)t * 13 + 2 * u];
+                    if (u > 0 && c < lut[(size_t)t * 13 + 2 * (u - 1)]) mono = false;
+                    if (u >= 3 ? c != F24 : c >= F24) fast = false;
+                }
+            (mode == 0 ? sl->mono_metro : sl->mono_gibbs) = mono;
+            (mode == 0 ? sl->nm_metro : sl->nm_gibbs) = fast ? 3 : 7;
         }
     }
 
@@ -1854,6 +2012,11 @@ static pp_status slab_copy_spins(pp_sim *s, int8_t *host, int dir) {
         const SlabView &v = sl->parts[i];
         slab_convert_kernel<<<dim3(blocks_for((int64_t)v.P * v.plane, 256), (unsigned)m.S), 256, 0, s->stream>>>(
             v, tmp, per_sys, (int64_t)i * v.P * v.plane, dir);
+    }
+    for (size_t i = 0; i < sl->pparts.size(); i++) {
+        const SlabPView &v = sl->pparts[i];
+        slabp_convert_kernel<<<dim3(blocks_for((int64_t)v.P * v.half, SLABP_THREADS), (unsigned)m.S), SLABP_THREADS, 0, s->stream>>>(
+            v, tmp, per_sys, (int64_t)i * v.P * sl->plane, dir);
     }
     cudaError_t e = cudaStreamSynchronize(s->stream);
     if (e == cudaSuccess && dir == 0) e = cudaMemcpy(host, tmp, n, cudaMemcpyDeviceToHost);

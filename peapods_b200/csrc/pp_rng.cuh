@@ -52,7 +52,10 @@ PP_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-constexpr int PHILOX_ROUNDS = 7;
+#ifndef PP_PHILOX_ROUNDS
+#define PP_PHILOX_ROUNDS 7
+#endif
+constexpr int PHILOX_ROUNDS = PP_PHILOX_ROUNDS;
 
 PP_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll

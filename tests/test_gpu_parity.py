@@ -1,8 +1,12 @@
 """T2/T3: the CUDA path (through the C ABI) against the oracle under the shared Philox draws (RNG-SPEC).
 Bit-exact: spins, system_ids, +-J energies, magnetisations, overlap dots, histograms, PT counters, f64 means.
 fp32 couplings: bit-exact spins with exact_log (host-libm log table), energies within 1e-5 relative."""
+from pathlib import Path
+
 import numpy as np
 import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
 
 pytestmark = pytest.mark.gpu
 
@@ -334,6 +338,12 @@ SLAB_CASES = [
     ((8, 6, 16), [4.0, 4.51], 4),
     ((2, 2, 8), [4.51], 1),           # L = 2 along x0 and x1: fwd == bwd neighbour, both counted
     ((12, 4, 24), [2.0, 4.51, 9.0], 3),
+    # shape[2] % 64 == 0: one bit per spin (pp_kernels_slabp.cuh), packed draw mapping, bond counts inside the colour-1 pass
+    ((4, 4, 64), [3.5, 4.51, 5.5], 1),
+    ((8, 6, 128), [4.0, 4.51], 2),
+    ((8, 6, 64), [4.0, 4.51], 4),
+    ((2, 2, 64), [4.51], 1),
+    ((12, 4, 192), [2.0, 4.51, 9.0, 1e9], 3),   # T = 1e9: a threshold at 2^24 takes the 7-threshold form of the kernel
 ]
 
 
@@ -347,8 +357,10 @@ def test_slab_layout_is_bit_exact(oracle, shape, temps, ranks, mode):
     assert n_colours == 2
     gpu = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 4321, layout="slab", slab_ranks=ranks, slab_rank=-1)
     assert gpu.layout == "slab" and gpu.n_local_spins == int(np.prod(shape))
+    assert gpu.slab_packed == (shape[2] % 64 == 0)
     J = np.ones(tuple(shape) + (3,), np.float32)
-    cpu = oracle.Sim(shape, J, temps, n_replicas=1, seed=4321, rng_mode=oracle.RNG_PHILOX, colour=colour)
+    cpu = oracle.Sim(shape, J, temps, n_replicas=1, seed=4321, colour=colour,
+                     rng_mode=oracle.RNG_PHILOX_PACKED if gpu.slab_packed else oracle.RNG_PHILOX)
     assert_state_equal(gpu, cpu, 1)
     for n_sweeps, interval in ((1, None), (2, None), (17, 1), (40, 3)):
         kw = dict(warmup_ratio=0.25, pt_interval=interval, pt_schedule="full_ladder")
@@ -362,10 +374,11 @@ def test_slab_layout_is_bit_exact(oracle, shape, temps, ranks, mode):
     assert_state_equal(gpu, cpu, 1)
 
 
-def test_slab_set_spins_and_operator_entry_points(oracle):
+@pytest.mark.parametrize("shape", [(4, 6, 8), (4, 6, 64)])
+def test_slab_set_spins_and_operator_entry_points(oracle, shape):
     import peapods_b200 as pb
 
-    shape, temps = (4, 6, 8), np.asarray([4.51], np.float32)
+    temps = np.asarray([4.51], np.float32)
     gpu = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 5, layout="slab", slab_ranks=2, slab_rank=-1)
     rng = np.random.default_rng(0)
     spins = (2 * rng.integers(0, 2, size=int(np.prod(shape))) - 1).astype(np.int8)
@@ -759,7 +772,8 @@ def test_config5_full_size_slab_decomposition_properties(oracle):
     shape = (256, 256, 256)
     colour, _ = pb.colouring(shape)
     gpu = pb.IsingSimulation(list(shape), "ferro", temps, 1, None, 11, layout="slab", slab_ranks=8, slab_rank=-1)
-    cpu = oracle.Sim(shape, np.ones(shape + (3,), np.float32), temps, n_replicas=1, seed=11, rng_mode=oracle.RNG_PHILOX, colour=colour)
+    assert gpu.slab_packed
+    cpu = oracle.Sim(shape, np.ones(shape + (3,), np.float32), temps, n_replicas=1, seed=11, rng_mode=oracle.RNG_PHILOX_PACKED, colour=colour)
     rg, rc = gpu.sample(2, "metropolis", warmup_ratio=0.5), cpu.sample(2, "metropolis", warmup_ratio=0.5)
     assert_state_equal(gpu, cpu, 1)
     assert_results_equal(rg, rc)
@@ -781,3 +795,22 @@ def test_config5_full_size_slab_decomposition_properties(oracle):
         bonds += int(np.multiply(s3, np.roll(s3, -1, axis=a), dtype=np.int8).sum(dtype=np.int64))
     assert e[0, 0] == np.float32(bonds) / np.float32(s3.size)
     assert 0.5 < float(e[0, 0]) < 3.0  # three sweeps from a random start at T_c: ordering has begun
+
+
+def test_slab_layout_on_real_ranks_is_bit_exact():
+    """The ncclSend / ncclRecv halo exchange and the ncclAllReduce of the bond counts on REAL ranks (one process per GPU,
+    tools/slab_check.py under torchrun): spins, energies and result dicts of byte and bit-packed slabs equal the oracle's
+    whole-lattice run.  Needs at least two visible GPUs; the single-GPU tests above emulate the ranks on one device."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("one GPU visible: real-rank slab exchange needs >= 2 (bench.py --gpus N runs its own N-rank check)")
+    n = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(ROOT / "tools" / "slab_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SLAB_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

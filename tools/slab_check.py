@@ -24,7 +24,8 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     ok = True
-    for shape, temps in (((8 * world, 6, 16), [4.0, 4.511, 5.0]), ((4 * world, 16, 32), [4.511])):
+    for shape, temps in (((8 * world, 6, 16), [4.0, 4.511, 5.0]), ((4 * world, 16, 32), [4.511]),
+                         ((8 * world, 6, 64), [4.0, 4.511, 5.0]), ((2 * world, 16, 128), [4.511])):  # the last two: one bit per spin
         temps = np.asarray(temps, np.float32)
         sim = SlabIsingSimulation(shape, temps, 99)
         results = []
@@ -40,8 +41,8 @@ def main():
             per = int(np.prod(shape)) // world
             full = np.concatenate([p.cpu().numpy().reshape(T, per) for p in parts], axis=1).reshape(-1)
             colour, _ = pb.colouring(shape)
-            cpu = oracle.Sim(shape, np.ones(tuple(shape) + (3,), np.float32), temps, n_replicas=1, seed=99, rng_mode=oracle.RNG_PHILOX,
-                             colour=colour)
+            cpu = oracle.Sim(shape, np.ones(tuple(shape) + (3,), np.float32), temps, n_replicas=1, seed=99, colour=colour,
+                             rng_mode=oracle.RNG_PHILOX_PACKED if sim.sim.slab_packed else oracle.RNG_PHILOX)
             for (n_sweeps, interval), rg in zip(((3, None), (25, 1)), results):
                 rc = cpu.sample(n_sweeps, "metropolis", warmup_ratio=0.25, pt_interval=interval, pt_schedule="full_ladder")
                 for k in ("mags", "mags2", "mags4", "energies", "energies2"):
