@@ -549,7 +549,7 @@ def run_ours(args):
         else:
             sub["c2_strong"] = {"workload": f"C2 at its named size: {SAMPLES_PER_GPU} disorder samples in total", "value": value, "unit": UNIT,
                                 "scaling": "strong", "n_gpus": 1, "note": "N = 1: the headline itself"}
-        sub["c5"] = bench_c5(ranks, args.c5_extent, 4, 2, 1)
+        sub["c5"] = bench_c5(ranks, args.c5_extent, 32, 3, 2)
         sub["c5"]["rank_parity"] = slab_rank_parity(ranks)
         sub["c5"]["rank_parity_note"] = ("N NCCL ranks == the same N slabs on one device (device copies), bit for bit: spins, energies, "
                                          "statistics; byte and bit-packed storage, PT over three temperatures")

@@ -18,10 +18,14 @@ import sys
 import types
 
 
-def install(reference_python_dir: str | None = None) -> types.ModuleType:
+def install(reference_python_dir: str | None = None, backend=None) -> types.ModuleType:
     """Register ``peapods._core`` backed by this engine; optionally put the reference's ``python/`` directory on ``sys.path``.
-    Returns the registered module.  Must run before the first ``import peapods``."""
-    from ._core import IsingSimulation
+    Returns the registered module.  Must run before the first ``import peapods``.  ``backend``: another class with the
+    ``IsingSimulation`` interface (the test suite wires a CPU stand-in through the same door where there is no GPU)."""
+    if backend is None:
+        from ._core import IsingSimulation
+    else:
+        IsingSimulation = backend
 
     if reference_python_dir is not None and reference_python_dir not in sys.path:
         sys.path.insert(0, reference_python_dir)
