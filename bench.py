@@ -21,6 +21,8 @@ The same JSON line carries sub-records measured in the same invocation (each wit
   c2_strong   BASELINE configs[1] at its NAMED size (4096 samples in total) split over the N ranks (strong scaling)
   c5          BASELINE configs[4] (1024^3 ferromagnet at T_c) slab-decomposed over the N ranks: value, e2e, roofline, halo bytes,
               and an N-rank parity check (NCCL ranks == the same slabs kept on one device, bit for bit)
+  c3_split    (N > 1) BASELINE configs[2] with its 128 systems split over the N ranks (ncclAllGather of energies / configurations),
+              with a parity check against the unsplit run
   c1, c3, c4  (N = 1) BASELINE configs[0], [2], [3] through the public API
   e2e_default_api   the headline's e2e with the reference's default return set (per-realization histograms included)
 `--impl reference` times the CPU restatement of the reference's rayon path (oracle, typewriter order +
@@ -356,6 +358,62 @@ def bench_c5(ranks: Ranks, extent: int, n_sweeps: int, steps: int, warmup: int, 
     }
 
 
+def bench_c3_split(ranks: Ranks):
+    """BASELINE configs[2] (triangular 256^2, Gibbs, 64 temps, 2 replicas = 128 systems of 64 Ki sites) with the SYSTEMS split over the
+    N ranks: energies / magnetisations per measurement and configurations per recorded sweep travel with
+    ncclAllGather inside the engine.  Parity: the split run equals the unsplit run on one GPU (rank 0), result dict and spins."""
+    import torch
+    import torch.distributed as dist
+
+    import peapods_b200 as pb
+    from peapods_b200.sharded import SystemSplitIsingSimulation
+
+    world, rank = ranks.world, ranks.rank
+    tc = 4.0 / np.log(3.0)
+    temps = np.linspace(tc - 0.4, tc + 0.4, 64).astype(np.float32)
+    shape, R, n_sweeps = (256, 256), 2, 400
+    seed = dynamics_seed()
+    sim = SystemSplitIsingSimulation(shape, "ferro", temps, R, TRI_OFFSETS, seed)
+    sim.sample(100, "gibbs")
+    ranks.barrier()
+    best = None
+    for _ in range(2):
+        sim.sample(n_sweeps, "gibbs")
+        ms = ranks.max(sim.sim.last_sweep_loop_ms)
+        best = ms if best is None else min(best, ms)
+    value = float(np.prod(shape)) * len(temps) * R * n_sweeps / (best * 1e6)
+    # parity on the same lattice, with exchange events: every rank's dict and spins against the unsplit handle on rank 0
+    kw = dict(warmup_ratio=0.25, pt_interval=1, pt_schedule="full_ladder")
+    sim.reset()
+    res = sim.sample(24, "gibbs", **kw)
+    spins = sim.get_spins()
+    ok = True
+    if rank == 0:
+        one = pb.IsingSimulation(list(shape), "ferro", temps, R, TRI_OFFSETS, seed, layout="int8", device=ranks.local_rank)
+        ref = one.sample(24, "gibbs", **kw)
+        ok = np.array_equal(spins, one.get_spins(0))
+        for k, v in ref.items():
+            if k == "per_disorder":
+                ok = ok and all(np.array_equal(v["parallel_tempering"][f], res[k]["parallel_tempering"][f]) for f in v["parallel_tempering"])
+            elif k == "overlap_histogram":
+                ok = ok and np.array_equal(np.stack(v), np.stack(res[k]))
+            else:
+                ok = ok and np.array_equal(np.asarray(v), np.asarray(res[k]))
+        del one
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    if world > 1:
+        dist.broadcast(flag, src=0)
+    peak, _ = peaks()
+    del sim
+    return {"workload": f"C3: 2-D triangular ferromagnet 256x256, Gibbs, 64 temps around 4/ln3, 2 replicas; the 128 systems split over {world} GPU(s)",
+            "value": value, "unit": UNIT, "scaling": "strong", "n_gpus": world, "sweeps": n_sweeps, "ms": best,
+            "alg_bytes_per_attempt": 2.0, "hbm_roofline_frac": value * 2.0 / (world * peak),
+            "collectives_per_recorded_sweep": 0 if world == 1 else 3,
+            "rank_parity": "PASS" if int(flag.item()) else "FAIL",
+            "rank_parity_note": "split run == unsplit run on one GPU, bit for bit (spins, statistics, exchange counters), 24 Gibbs sweeps with "
+                                "full-ladder exchanges"}
+
+
 def bench_small_configs():
     """BASELINE configs[0], [2], [3] through the public API on this GPU (N = 1 only): device time of the sweep loop, best of 2."""
     import peapods_b200 as pb
@@ -553,6 +611,8 @@ def run_ours(args):
         sub["c5"]["rank_parity"] = slab_rank_parity(ranks)
         sub["c5"]["rank_parity_note"] = ("N NCCL ranks == the same N slabs on one device (device copies), bit for bit: spins, energies, "
                                          "statistics; byte and bit-packed storage, PT over three temperatures")
+        if world > 1:
+            sub["c3_split"] = bench_c3_split(ranks)
         if world == 1:
             sub.update(bench_small_configs())
             # the reference API's default return set: per-realization histograms [D][T][N+1] x 3 (src/lib.rs:385-411), 12.9 GB at C2

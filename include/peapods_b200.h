@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 3
+#define PP_ABI_VERSION 4
 #define PP_MAX_DIMS 8
 
 typedef enum {
@@ -79,7 +79,14 @@ typedef struct {
     int32_t slab_ranks;
     int32_t slab_rank;           /* this process's slab, or -1: keep all slabs on this device (single-GPU emulation, tests) */
     const uint8_t *nccl_unique_id; /* [PP_NCCL_ID_BYTES] from pp_nccl_unique_id() on rank 0, broadcast by the host; NULL unless
-                                      slab_ranks > 1 and slab_rank >= 0 */
+                                      (slab_ranks > 1 and slab_rank >= 0) or system_ranks > 1 */
+    /* int8 layout, ONE realization of many large systems (BASELINE configs[2]): the S = n_replicas * n_temps systems are split
+     * over system_ranks processes / GPUs in contiguous blocks of S / system_ranks systems (the reference parallelises over
+     * systems the same way: spin-sim/src/parallel.rs:36-40).  Every rank sweeps its own systems; energies and magnetisations are
+     * all-gathered per measurement / exchange event, configurations per recorded sweep when n_replicas >= 2, and every rank
+     * replays the same exchange decisions and statistics.  0 or 1 = off. */
+    int32_t system_ranks;
+    int32_t system_rank;
 } pp_model_desc;
 
 enum { PP_CLUSTER_SW = 0, PP_CLUSTER_WOLFF = 1 };  /* config.rs ClusterMode */

@@ -22,7 +22,8 @@ def _rust_round(x: float) -> int:
 
 class IsingSimulation:
     def __init__(self, lattice_shape, couplings, temperatures, n_replicas=None, neighbor_offsets=None, seed=None,
-                 *, layout="auto", device=0, sample_offset=0, slab_ranks=1, slab_rank=0, nccl_unique_id=None):
+                 *, layout="auto", device=0, sample_offset=0, slab_ranks=1, slab_rank=0, nccl_unique_id=None,
+                 system_ranks=1, system_rank=0):
         """``layout="slab"`` (or "auto" for one large ferromagnet) keeps ONE 3-D lattice without neighbour tables and
         can cut it along dimension 0 into ``slab_ranks`` slabs, one per process / GPU: pass this process's
         ``slab_rank`` and the bytes of ``nccl_unique_id()`` from rank 0 (``slab_rank=-1`` keeps every slab on this
@@ -74,6 +75,8 @@ class IsingSimulation:
         desc.device = int(device)
         desc.slab_ranks = int(slab_ranks)
         desc.slab_rank = int(slab_rank)
+        desc.system_ranks = int(system_ranks)
+        desc.system_rank = int(system_rank)
         id_buf = None
         if nccl_unique_id is not None:
             id_buf = np.frombuffer(bytes(nccl_unique_id), dtype=np.uint8).copy()

@@ -40,6 +40,8 @@ class ModelDesc(C.Structure):
         ("slab_ranks", C.c_int32),
         ("slab_rank", C.c_int32),
         ("nccl_unique_id", C.c_void_p),
+        ("system_ranks", C.c_int32),
+        ("system_rank", C.c_int32),
     ]
 
 
@@ -127,7 +129,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.pp_abi_version() != 3:
+    if lib.pp_abi_version() != 4:
         raise ImportError("libpeapods_b200.so ABI version mismatch")
     for which, struct in enumerate((ModelDesc, SampleCfg, Results)):
         if lib.pp_struct_size(which) != C.sizeof(struct):

@@ -20,6 +20,7 @@ struct ModelView {
     int T, R, S, P;     // temps, replicas, systems per realization, replica pairs
     int64_t D;          // realizations in this handle
     int64_t sample_offset;
+    int sys_lo, sys_hi; // systems this process updates (system-split handles: pp_model_desc.system_ranks); [0, S) otherwise
     int n_colours;
     int coupling_class;
     uint64_t seed;      // current dynamics root seed

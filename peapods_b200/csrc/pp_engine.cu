@@ -220,6 +220,10 @@ struct pp_sim {
     std::vector<cudaStream_t> xstreams;
     std::vector<cudaEvent_t> xevents;
     SlabState *slab = nullptr;                         // PP_LAYOUT_SLAB (pp_slab.cuh)
+    // system-split handle (pp_model_desc.system_ranks > 1): this process sweeps the systems [mv.sys_lo, mv.sys_hi) of the one
+    // realization; energies / magnetisations / configurations are all-gathered over sys_comm (cached, never destroyed here)
+    int sys_ranks = 1, sys_rank = 0;
+    ncclComm_t sys_comm = nullptr;
     bool rows = false;                                 // int8 layout through the per-row stride tables (pp_kernels_rows.cuh)
     bool resident = false;                             // small realizations: one CTA per realization, many sweeps per launch
     uint16_t *d_site16 = nullptr;                      // storage index -> logical site (same use)
@@ -551,6 +555,32 @@ static pp_status launch_msc3d(pp_sim *s, Ctx &c, const ModelView &m, int sweep_m
 #undef PP_M3
 #undef PP_M3A
     return fail(PP_ERR_UNSUPPORTED, "msc3d: unsupported replica count");
+}
+
+// One communicator per (process, device, world, rank), kept for the life of the process: ncclCommInitRank costs seconds and a handle
+// is built per model.  Every rank takes the same branch, so the bootstrap token of a later handle is simply not used.
+static pp_status cached_comm(int device, int ranks, int rank, const uint8_t *token, ncclComm_t *out) {
+    NcclApi &nc = nccl_api();
+    if (!nc.error.empty()) return fail(PP_ERR_NCCL, nc.error);
+    static std::mutex comm_mu;
+    static std::map<std::tuple<int, int, int>, ncclComm_t> comm_cache;
+    std::lock_guard<std::mutex> lock(comm_mu);
+    const std::tuple<int, int, int> ck{device, ranks, rank};
+    auto it = comm_cache.find(ck);
+    if (it != comm_cache.end()) {
+        *out = it->second;
+        return PP_OK;
+    }
+    if (!token) return fail(PP_ERR_INVALID, "nccl_unique_id is NULL");
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == PP_NCCL_ID_BYTES, "ncclUniqueId size");
+    memcpy(&id, token, sizeof(id));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = nc.CommInitRank(&comm, ranks, id, rank);
+    if (r != ncclSuccess) return fail(PP_ERR_NCCL, std::string("ncclCommInitRank: ") + nc.GetErrorString(r));
+    comm_cache[ck] = comm;
+    *out = comm;
+    return PP_OK;
 }
 
 // ---- slab layout (pp_slab.cuh) -----------------------------------------------------------------
@@ -922,6 +952,22 @@ static pp_status launch_pt(pp_sim *s, Ctx &c, int schedule, uint32_t pt_event, i
     return PP_OK;
 }
 
+// system-split handle: every rank contributes what it produced for its own systems (contiguous blocks, in place)
+static pp_status sys_allgather(pp_sim *s, cudaStream_t stream, bool energies, bool mags, bool spins) {
+    if (!s->sys_comm) return PP_OK;
+    NcclApi &nc = nccl_api();
+    const ModelView &m = s->mv;
+    const size_t per = (size_t)(m.S / s->sys_ranks);
+    if (energies)
+        NCCL_TRY(nc.AllGather((const char *)(s->d_energies + m.sys_lo), s->d_energies, per * sizeof(float), ncclUint8, s->sys_comm, stream));
+    if (mags)
+        NCCL_TRY(nc.AllGather((const char *)(s->d_mags + m.sys_lo), s->d_mags, per * sizeof(long long), ncclUint8, s->sys_comm, stream));
+    if (spins)
+        NCCL_TRY(nc.AllGather((const char *)(s->d_spins + (size_t)m.sys_lo * m.N), s->d_spins, per * (size_t)m.N, ncclUint8, s->sys_comm, stream));
+    s->launches += (energies ? 1 : 0) + (mags ? 1 : 0) + (spins ? 1 : 0);
+    return PP_OK;
+}
+
 // Realization::new / reset (realization.rs:166-207, 213-246) on the device
 static pp_status do_reset(pp_sim *s, uint64_t seed) {
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1003,6 +1049,14 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     } else if (desc->slab_ranks > 1) {
         return fail(PP_ERR_INVALID, "slab_ranks > 1 needs layout = PP_LAYOUT_SLAB");
     }
+    const int sys_ranks = std::max(1, (int)desc->system_ranks);
+    if (sys_ranks > 1) {
+        if (want_slab) return fail(PP_ERR_INVALID, "system_ranks > 1 and the slab layout are two different decompositions");
+        if (desc->n_disorder != 1) return fail(PP_ERR_UNSUPPORTED, "system_ranks > 1 splits the systems of ONE realization (shard realizations with sample_offset instead)");
+        if (desc->system_rank < 0 || desc->system_rank >= sys_ranks) return fail(PP_ERR_INVALID, "system_rank out of range");
+        if (((int64_t)desc->n_temps * desc->n_replicas) % sys_ranks != 0) return fail(PP_ERR_INVALID, "n_replicas * n_temps must be a multiple of system_ranks");
+        if (desc->layout != PP_LAYOUT_AUTO && desc->layout != PP_LAYOUT_INT8) return fail(PP_ERR_UNSUPPORTED, "system_ranks > 1 needs the int8 layout");
+    }
 
     pp_sim *s = new pp_sim();
     std::string err = build_plan(desc->n_dims, desc->shape, desc->n_offsets, desc->offsets, s->plan, !want_slab);
@@ -1028,6 +1082,8 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
     m.P = m.R / 2;
     m.D = desc->n_disorder;
     m.sample_offset = desc->sample_offset;
+    m.sys_lo = 0;
+    m.sys_hi = m.S;
     m.n_colours = s->plan.n_colours;
     m.seed = desc->seed;
 
@@ -1177,34 +1233,12 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_halo, cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&sl->ev_main, cudaEventDisableTiming));
         if (slab_ranks > 1 && sl->rank >= 0) {
-            NcclApi &nc = nccl_api();
-            if (!nc.error.empty()) {
-                std::string msg = nc.error;
+            pp_status cst = cached_comm(s->device, slab_ranks, sl->rank, desc->nccl_unique_id, &sl->comm);
+            if (cst != PP_OK) {
+                std::string keep = g_last_error;
+                sl->comm = nullptr;
                 free_sim(s);
-                return fail(PP_ERR_NCCL, msg);
-            }
-            // One communicator per (process, device, world, rank), kept for the life of the process: ncclCommInitRank costs
-            // seconds, a handle is built per model.  Every rank takes the same branch, so the bootstrap token of a later
-            // handle is simply not used.
-            static std::mutex comm_mu;
-            static std::map<std::tuple<int, int, int>, ncclComm_t> comm_cache;
-            std::lock_guard<std::mutex> lock(comm_mu);
-            const std::tuple<int, int, int> ck{s->device, slab_ranks, sl->rank};
-            auto it = comm_cache.find(ck);
-            if (it != comm_cache.end()) {
-                sl->comm = it->second;
-            } else {
-                ncclUniqueId id;
-                static_assert(sizeof(ncclUniqueId) == PP_NCCL_ID_BYTES, "ncclUniqueId size");
-                memcpy(&id, desc->nccl_unique_id, sizeof(id));
-                ncclResult_t r = nc.CommInitRank(&sl->comm, slab_ranks, id, sl->rank);
-                if (r != ncclSuccess) {
-                    std::string msg = std::string("ncclCommInitRank: ") + nc.GetErrorString(r);
-                    sl->comm = nullptr;
-                    free_sim(s);
-                    return fail(PP_ERR_NCCL, msg);
-                }
-                comm_cache[ck] = sl->comm;
+                return fail(cst, keep);
             }
             sl->comm_cached = true;
         }
@@ -1283,6 +1317,25 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                               (z == 2 || z == 3);
                 if (const char *e = getenv("PP_RESIDENT")) s->resident = s->resident && atoi(e) != 0;
             }
+        }
+    }
+    if (sys_ranks > 1) {
+        if (s->layout != PP_LAYOUT_INT8 || !s->rows) {
+            free_sim(s);
+            return fail(PP_ERR_UNSUPPORTED, "system_ranks > 1 needs the row-table int8 kernels (a linear colouring that alternates along the "
+                                            "rows, last extent a multiple of 8)");
+        }
+        s->resident = false;  // one CTA per realization would hold every system
+        s->sys_ranks = sys_ranks;
+        s->sys_rank = desc->system_rank;
+        const int per = m.S / sys_ranks;
+        m.sys_lo = s->sys_rank * per;
+        m.sys_hi = m.sys_lo + per;
+        pp_status cst = cached_comm(s->device, sys_ranks, s->sys_rank, desc->nccl_unique_id, &s->sys_comm);
+        if (cst != PP_OK) {
+            std::string keep = g_last_error;
+            free_sim(s);
+            return fail(cst, keep);
         }
     }
     m.J8 = s->d_J8;
@@ -1599,6 +1652,8 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             CUDA_TRY(cudaStreamSynchronize(s->stream));
         }
     }
+    if (s->sys_comm && (want_fk || want_oc))
+        return fail(PP_ERR_UNSUPPORTED, "cluster moves are not implemented for system-split handles (system_ranks > 1)");
     if (want_fk) {
         if (s->layout != PP_LAYOUT_INT8 || m.coupling_class == COUP_F32) {
             return fail(PP_ERR_UNSUPPORTED, "cluster updates (cluster_update_interval) are not implemented on the GPU sweep path for "
@@ -1763,6 +1818,10 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                 st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, energy_this && !fk_this,
                                    stp.record, stp.record || want_eq, stp.record, &fused);
                 if (st != PP_OK) return st;
+                if (s->sys_comm) {  // system-split handle: what the other processes produced for their systems
+                    st = sys_allgather(s, c.stream, energy_this, energy_this && stp.record, (stp.record || want_eq) && c.m.P > 0);
+                    if (st != PP_OK) return st;
+                }
                 if (fk_this) {  // after the sweep, before the measurements (mod.rs:457-470)
                     fk_cluster_kernel<<<(unsigned)(c.m.D * c.m.S), FK_THREADS, fk_smem, c.stream>>>(
                         c.m, d_fk_count, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0,
@@ -1844,6 +1903,10 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     }
     for (Ctx &c : chunks) {  // leave the canonical state behind: no pending exchange, handle pointer on the current buffer
         st = flush_swaps(s, c);
+        if (st != PP_OK) return st;
+    }
+    if (s->sys_comm) {  // every process ends the call with every system's configuration
+        st = sys_allgather(s, s->stream, false, false, true);
         if (st != PP_OK) return st;
     }
     commit_ctx(s, chunks[0]);

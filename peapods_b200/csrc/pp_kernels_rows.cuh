@@ -250,6 +250,7 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
         }
         long long e_sum = 0;
         const uint32_t sys = sysv[ss % PF];
+        if ((int)sys < m.sys_lo || (int)sys >= m.sys_hi) continue;     // system-split handle: another process updates this system
         const int t = slot % m.T;                                     // realization.rs:166
         int8_t *s = spins_d + (int64_t)sys * m.N;
         const u32x4 o = philox4x32(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
@@ -402,8 +403,9 @@ rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int
     if (threadIdx.x < NS * 2) {
         const int ss = threadIdx.x >> 1, slot = slot0 + ss;
         if (slot < m.S) {
-            const int64_t sysg = d * m.S + m.system_ids[d * m.S + slot];
-            atomicAdd((unsigned long long *)&acc[2 * sysg + (threadIdx.x & 1)], blk[ss][threadIdx.x & 1]);
+            const int sysl = m.system_ids[d * m.S + slot];
+            const int64_t sysg = d * m.S + sysl;
+            if (sysl >= m.sys_lo && sysl < m.sys_hi) atomicAdd((unsigned long long *)&acc[2 * sysg + (threadIdx.x & 1)], blk[ss][threadIdx.x & 1]);
         }
         __threadfence();
     }
@@ -414,8 +416,9 @@ rows_sweep_kernel(ModelView m, RowsView v, int colour, uint32_t sweep_index, int
     __threadfence();
     if (threadIdx.x < NS) {
         const int slot = slot0 + threadIdx.x;
-        if (slot < m.S) {
-            const int64_t sysg = d * m.S + m.system_ids[d * m.S + slot];
+        const int sysl = slot < m.S ? m.system_ids[d * m.S + slot] : -1;
+        if (sysl >= m.sys_lo && sysl < m.sys_hi) {
+            const int64_t sysg = d * m.S + sysl;
             const long long e_tot = (long long)atomicExch((unsigned long long *)&acc[2 * sysg], 0ull);
             const long long d_tot = (long long)atomicExch((unsigned long long *)&acc[2 * sysg + 1], 0ull);
             if (CLASS == COUP_F32) m.energies[sysg] = __fdiv_rn((float)((double)e_tot / (double)escale), (float)m.N);
@@ -438,6 +441,10 @@ __global__ void __launch_bounds__(256) rows_energy_kernel(ModelView m, RowsView 
     constexpr int ZA = ZT > 0 ? ZT : 16;
     const int64_t sysg = blockIdx.x;
     const int64_t d = sysg / m.S;
+    {
+        const int sysl = (int)(sysg - d * m.S);
+        if (sysl < m.sys_lo || sysl >= m.sys_hi) return;  // system-split handle: another process owns this system
+    }
     const int8_t *s = m.spins + sysg * m.N;
     const int z = ZT > 0 ? ZT : m.z, L = v.L;
     const uint32_t n_seg = (uint32_t)(v.n_rows * v.kpr);

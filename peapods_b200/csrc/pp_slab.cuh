@@ -35,6 +35,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     std::string error;
 };
@@ -64,6 +65,7 @@ inline NcclApi &nccl_api() {
     PP_NCCL_SYM(Send, "ncclSend")
     PP_NCCL_SYM(Recv, "ncclRecv")
     PP_NCCL_SYM(AllReduce, "ncclAllReduce")
+    PP_NCCL_SYM(AllGather, "ncclAllGather")
     PP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef PP_NCCL_SYM
     return api;

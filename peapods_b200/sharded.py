@@ -199,3 +199,48 @@ class SlabIsingSimulation:
 
     def reset(self, seed=None):
         self.sim.reset(seed)
+
+
+def system_plan(n_systems: int, world: int, rank: int):
+    """(first system, systems) of rank ``rank`` when the S = n_replicas * n_temps systems of one realization are split over
+    ``world`` processes in contiguous blocks (pp_model_desc.system_ranks; the reference parallelises over systems the same
+    way, spin-sim/src/parallel.rs:36-40)."""
+    if n_systems % world != 0:
+        raise ValueError(f"n_replicas * n_temps = {n_systems} must be a multiple of {world} ranks")
+    per = n_systems // world
+    return rank * per, per
+
+
+class SystemSplitIsingSimulation:
+    """ONE realization of many large systems (BASELINE config 3: 128 systems of 64 Ki sites) split by SYSTEM over the ranks of the
+    initialized ``torch.distributed`` group (one process per GPU).  Every rank sweeps its own block of systems; the engine
+    all-gathers energies / magnetisations per measurement or exchange event and configurations per recorded sweep (NCCL), and
+    every rank replays the same exchange decisions and statistics, so ``sample()`` returns the same dict on every rank — the dict
+    the unsplit run returns, bit for bit — and ``get_spins()`` the whole realization."""
+
+    def __init__(self, lattice_shape, couplings, temperatures, n_replicas=None, neighbor_offsets=None, seed=None, *, device=None,
+                 group=None):
+        import torch
+        import torch.distributed as dist
+
+        from ._core import IsingSimulation, nccl_unique_id
+
+        live = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if live else 0
+        self.world = dist.get_world_size(group) if live else 1
+        R = 1 if n_replicas is None else int(n_replicas)
+        self.first_system, self.n_systems = system_plan(R * len(np.asarray(temperatures).reshape(-1)), self.world, self.rank)
+        token = broadcast_token(nccl_unique_id, group) if self.world > 1 else None
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.sim = IsingSimulation(list(lattice_shape), couplings, temperatures, n_replicas, neighbor_offsets, seed, layout="int8",
+                                   device=device, system_ranks=self.world, system_rank=self.rank, nccl_unique_id=token)
+
+    def sample(self, *args, **kwargs):
+        return self.sim.sample(*args, **kwargs)
+
+    def get_spins(self):
+        return self.sim.get_spins(0)
+
+    def reset(self, seed=None):
+        self.sim.reset(seed)

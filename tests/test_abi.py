@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(pb):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert lib.pp_abi_version() == 3
+    assert lib.pp_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_a_gpu(pb):

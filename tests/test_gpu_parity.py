@@ -814,3 +814,35 @@ def test_slab_layout_on_real_ranks_is_bit_exact():
            "--master-port", "29533", str(ROOT / "tools" / "slab_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "SLAB_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_system_split_on_real_ranks_is_bit_exact():
+    """the systems of ONE realization split over real ranks (tools/system_split_check.py under torchrun):
+    energies / magnetisations / configurations all-gathered with NCCL, exchange decisions replayed on every rank; spins, system
+    ids and result dicts equal the oracle's unsplit run on every rank.  Needs at least two visible GPUs."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible: the system split needs >= 2 (bench.py --gpus N runs its own N-rank check)")
+    n = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", str(ROOT / "tools" / "system_split_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "SYSTEM_SPLIT_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_system_split_rejects_what_it_cannot_hold():
+    import peapods_b200 as pb
+
+    t = np.linspace(2.0, 3.0, 3).astype(np.float32)
+    with pytest.raises(ValueError):   # 3 temperatures x 1 replica over 2 ranks
+        pb.IsingSimulation([8, 8], "ferro", t, 1, None, 1, layout="int8", system_ranks=2, system_rank=0, nccl_unique_id=bytes(128))
+    with pytest.raises(ValueError):   # several realizations: shard those by sample instead
+        pb.IsingSimulation([8, 8], np.ones((2, 8, 8, 2), np.float32), t[:2], 1, None, 1, layout="int8", system_ranks=2, system_rank=0,
+                           nccl_unique_id=bytes(128))
+    with pytest.raises(ValueError):   # multispin layout
+        pb.IsingSimulation([8, 8], "ferro", t[:2], 1, None, 1, layout="msc", system_ranks=2, system_rank=0, nccl_unique_id=bytes(128))

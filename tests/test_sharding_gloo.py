@@ -120,6 +120,18 @@ def test_slab_plan_cuts_even_slabs():
         slab_plan(12, 4, 0)   # 3 planes per slab: odd, the colour of a site would depend on the cut
 
 
+def test_system_plan_cuts_contiguous_blocks_of_systems():
+    import pytest
+
+    sys.path.insert(0, str(ROOT))
+    from peapods_b200.sharded import system_plan
+
+    assert [system_plan(128, 8, r) for r in range(8)] == [(16 * r, 16) for r in range(8)]   # BASELINE configs[2]: 64 temps x 2 replicas
+    assert system_plan(6, 2, 1) == (3, 3)
+    with pytest.raises(ValueError):
+        system_plan(6, 4, 0)
+
+
 def _token_worker(rank, world, port, out_dir):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
