@@ -115,9 +115,6 @@ typedef struct {
     /* 1: fp32-coupling / Gibbs log thresholds are read from a host-libm logf table so that spin
      * trajectories are bit-identical to the CPU rule; 0: device logf (results agree to tolerance) */
     int32_t exact_log;
-    /* 1: bracket every sweep-kernel launch with CUDA events on the launch stream and report the summed
-     * duration in pp_results.sweep_kernel_ms (measurement hook for the roofline figure) */
-    int32_t profile;
     int32_t cluster_mode;                    /* PP_CLUSTER_SW (0) or PP_CLUSTER_WOLFF (1); used when cluster_update_interval > 0 */
     int32_t overlap_cluster_mode;            /* PP_CLUSTER_*; used when overlap_cluster_update_interval > 0 (reference default: wolff) */
 } pp_sample_cfg;
@@ -137,10 +134,6 @@ typedef struct {
     double *per_sample_means;  /* [D][11][T]: per-realization averages in the order mags, mags2, mags4, energies,
                                   energies2, overlap, overlap2, overlap4, link_overlap, link_overlap2, link_overlap4;
                                   lets a multi-GPU caller do the reference's ordered sum over realizations */
-    double sweep_loop_ms;      /* out: device time of the sweep loop (CUDA events on the launch stream) */
-    int64_t kernel_launches;   /* out: kernels launched by this call */
-    double sweep_kernel_ms;    /* out (cfg.profile): summed device time of the sweep-kernel launches */
-    int64_t sweep_kernel_launches; /* out (cfg.profile): how many launches that sum covers */
     /* cfg.autocorrelation_max_lag > 0 (src/lib.rs:545-556): [T] means over this handle's realizations of the per-realization
      * Sokal-windowed taus (statistics/results.rs:217-231, 269-274); overlap2_tau needs R >= 2 */
     double *mags2_tau, *overlap2_tau;
@@ -181,6 +174,17 @@ pp_status pp_nccl_unique_id(uint8_t *out /* [PP_NCCL_ID_BYTES] */);
 pp_status pp_get_system_ids(pp_sim *sim, int64_t realization, int64_t *out /* [S] */);
 pp_status pp_get_energies(pp_sim *sim, int64_t realization, float *out /* [S] by system */);
 int32_t pp_get_layout(const pp_sim *sim);
+/* Measurement hooks (bench.py, tools/): not part of the reference boundary, kept out of the production structs.
+ * pp_debug_set_profile(sim, 1): the NEXT pp_sample call brackets every sweep-kernel launch with CUDA events on the launch stream
+ * (one stream, one launch per sweep) — the roofline figure's kernel time.  pp_debug_last_timing: figures of the last pp_sample. */
+typedef struct {
+    double sweep_loop_ms;          /* device time of the sweep loop (CUDA events on the launch stream) */
+    int64_t kernel_launches;       /* kernels (and collectives) launched by the call */
+    double sweep_kernel_ms;        /* profile mode: summed device time of the sweep-kernel launches */
+    int64_t sweep_kernel_launches; /* profile mode: how many launches that sum covers */
+} pp_timing;
+pp_status pp_debug_set_profile(pp_sim *sim, int32_t on);
+pp_status pp_debug_last_timing(const pp_sim *sim, pp_timing *out);
 /* 1 when sweeps run through the stride-based 3-D multispin kernel (pp_kernels_msc3d.cuh), else 0 */
 int32_t pp_uses_msc3d(const pp_sim *sim);
 /* 1 when a PP_LAYOUT_SLAB handle stores one bit per spin (shape[2] % 64 == 0: pp_kernels_slabp.cuh, packed draw mapping), else 0 */

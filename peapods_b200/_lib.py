@@ -45,6 +45,11 @@ class ModelDesc(C.Structure):
     ]
 
 
+class Timing(C.Structure):
+    _fields_ = [("sweep_loop_ms", C.c_double), ("kernel_launches", C.c_int64), ("sweep_kernel_ms", C.c_double),
+                ("sweep_kernel_launches", C.c_int64)]
+
+
 class SampleCfg(C.Structure):
     _fields_ = [
         ("n_sweeps", C.c_int64),
@@ -58,7 +63,6 @@ class SampleCfg(C.Structure):
         ("snapshot_interval", C.c_int64),
         ("equilibration_diagnostic", C.c_int32),
         ("exact_log", C.c_int32),
-        ("profile", C.c_int32),
         ("cluster_mode", C.c_int32),
         ("overlap_cluster_mode", C.c_int32),
     ]
@@ -74,8 +78,7 @@ class Results(C.Structure):
         + [("overlap_histogram", _PU64), ("ql_at_q_sum", _PD), ("ql2_at_q_sum", _PD)]
         + [("per_sample_overlap_histogram", _PU64), ("per_sample_ql_at_q_sum", _PD), ("per_sample_ql2_at_q_sum", _PD)]
         + [("pt_edge_attempts", _PU64), ("pt_edge_acceptances", _PU64), ("pt_round_trips", _PU64)]
-        + [("per_sample_means", _PD), ("sweep_loop_ms", C.c_double), ("kernel_launches", C.c_int64),
-           ("sweep_kernel_ms", C.c_double), ("sweep_kernel_launches", C.c_int64)]
+        + [("per_sample_means", _PD)]
         + [("mags2_tau", _PD), ("overlap2_tau", _PD), ("per_sample_taus", _PD)]
         + [("equil_energy_avg", _PD), ("equil_link_overlap_avg", _PD), ("per_sample_equil", _PD)]
     )
@@ -103,6 +106,8 @@ SIGNATURES = {
     "pp_local_spin_count": (C.c_int64, [C.c_void_p]),
     "pp_nccl_unique_id": (C.c_int32, [C.c_void_p]),
     "pp_uses_msc3d": (C.c_int32, [C.c_void_p]),
+    "pp_debug_set_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pp_debug_last_timing": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pp_slab_packed": (C.c_int32, [C.c_void_p]),
     "pp_set_spins": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_set_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),

@@ -239,7 +239,8 @@ struct pp_sim {
     unsigned int *d_rows_arrive = nullptr;
     int rows_nb = 1;                                   // blocks per system / pair of the split reductions
     // measurement hook: event pairs around sweep-kernel launches
-    bool profile = false;
+    bool profile = false, profile_next = false;        // pp_debug_set_profile arms the next pp_sample
+    pp_timing last_timing{};
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
 };
@@ -386,6 +387,16 @@ static void free_sim(pp_sim *s) {
 
 extern "C" void pp_destroy(pp_sim *sim) { free_sim(sim); }
 extern "C" int32_t pp_get_layout(const pp_sim *sim) { return sim ? sim->layout : 0; }
+extern "C" pp_status pp_debug_set_profile(pp_sim *sim, int32_t on) {
+    if (!sim) return fail(PP_ERR_INVALID, "sim is NULL");
+    sim->profile_next = on != 0;
+    return PP_OK;
+}
+extern "C" pp_status pp_debug_last_timing(const pp_sim *sim, pp_timing *out) {
+    if (!sim || !out) return fail(PP_ERR_INVALID, "sim/out is NULL");
+    *out = sim->last_timing;
+    return PP_OK;
+}
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
 extern "C" int64_t pp_local_spin_count(const pp_sim *sim) {
@@ -1311,7 +1322,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             // CTA's shared memory, and few enough segments per thread that one CTA is not slower than a grid
             {
                 const size_t lut_words = ((size_t)m.T * (4 * z + 1) + 3) & ~size_t(3);
-                const size_t need = lut_words * 4 + (size_t)m.S * N;
+                const size_t need = lut_words * 4 + resident_scalar_bytes(m.S, m.T, m.P) + (size_t)m.S * N;
                 s->resident_smem = need;
                 s->resident = m.coupling_class != COUP_F32 && ((size_t)m.S * N) % 16 == 0 && need <= 200 * 1024 &&
                               (z == 2 || z == 3);
@@ -1532,6 +1543,170 @@ static pp_status ensure_hist(pp_sim *s) {
     return PP_OK;
 }
 
+// Small realizations (S * N bytes + the acceptance table + the scalar state fit one CTA's shared memory, integer coupling
+// classes): every sweep of the call inside rows_resident_kernel, up to 256 sweeps per launch.
+static pp_status run_rows_resident(pp_sim *s, Ctx &c, const pp_sample_cfg *cfg, const volatile int32_t *interrupt,
+                                   void (*on_sweep)(void *, uint64_t), void *user) {
+    int64_t sweep_id = 0;
+    RowsView v = s->rv;
+    v.keys = s->d_keys;
+    ModelView mk = c.m;
+    mk.lut = cfg->sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
+    const bool gibbs = cfg->sweep_mode == PP_SWEEP_GIBBS;
+    while (sweep_id < cfg->n_sweeps) {
+        if (interrupt && *interrupt) return fail(PP_ERR_INTERRUPTED, "interrupted");
+        const int64_t mb_end = std::min<int64_t>(cfg->n_sweeps, sweep_id + 256);
+        ResidentArgs a;
+        a.sweep_id0 = sweep_id;
+        a.n_sweeps = (int)(mb_end - sweep_id);
+        a.warmup_sweeps = cfg->warmup_sweeps;
+        a.pt_interval = cfg->pt_interval > 0 ? cfg->pt_interval : 0;
+        a.pt_schedule = cfg->pt_schedule == PP_PT_FULL_LADDER ? 1 : 0;
+        a.sweep_counter0 = s->sweep_counter;
+        a.pt_event0 = s->pt_event_counter;
+        a.parity0 = s->next_parity;
+        a.spins_in_smem = 1;
+        a.dot_spin = c.dot_spin;
+        a.dot_link = c.dot_link;
+#define PP_RES3(C_, Z_, G_)                                                                                                       \
+    do {                                                                                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(rows_resident_kernel<C_, Z_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->resident_smem)); \
+    rows_resident_kernel<C_, Z_, G_><<<(unsigned)mk.D, RESIDENT_THREADS, s->resident_smem, c.stream>>>(mk, v, c.st, c.pt, a);   \
+    } while (0)
+#define PP_RES2(C_, Z_) do { if (gibbs) PP_RES3(C_, Z_, true); else PP_RES3(C_, Z_, false); } while (0)
+        if (mk.coupling_class == COUP_FERRO) { if (mk.z == 2) PP_RES2(COUP_FERRO, 2); else PP_RES2(COUP_FERRO, 3); }
+        else { if (mk.z == 2) PP_RES2(COUP_UNIT, 2); else PP_RES2(COUP_UNIT, 3); }
+#undef PP_RES2
+#undef PP_RES3
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        for (int64_t sid = sweep_id; sid < mb_end; sid++) {
+            s->sweep_counter++;
+            if (cfg->pt_interval > 0 && sid % cfg->pt_interval == 0) {
+                s->pt_event_counter++;
+                if (mk.T >= 2 && cfg->pt_schedule == PP_PT_FULL_LADDER) s->next_parity = 1 - s->next_parity;
+            }
+            if (on_sweep) on_sweep(user, (uint64_t)sid);
+        }
+        sweep_id = mb_end;
+    }
+    return PP_OK;
+}
+
+// Device accumulators -> the caller's result arrays (statistics/stats.rs:29-35, results.rs:165-180, 250-259, overlap.rs:106-152):
+// per-realization means, their ordered sum over realizations, histograms, taus, equilibration checkpoints, PT counters.
+static pp_status collect_results(pp_sim *s, pp_results *out, int64_t n_rec, bool want_eq, bool want_ac, const std::vector<int64_t> &ckpts,
+                                 const std::vector<double> &eq_snap, const std::vector<double> &taus) {
+    const ModelView &m = s->mv;
+    const int T = m.T;
+    std::vector<double> sums((size_t)m.D * 11 * T);
+    CUDA_TRY(cudaMemcpy(sums.data(), s->st.sums, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost));
+    const double c_stat = n_rec > 0 ? (double)(n_rec * m.R) : 1.0;
+    const double c_ov = (n_rec > 0 && m.P > 0) ? (double)(n_rec * m.P) : 1.0;
+    // one pass in storage order; every (k, t) accumulator still adds its realizations in order (results.rs:165-180)
+    std::vector<double> mean_acc((size_t)11 * T, 0.0);
+    for (int64_t d = 0; d < m.D; d++)
+        for (int k = 0; k < 11; k++) {
+            const double c = k < 5 ? c_stat : c_ov;
+            double *row = &sums[((size_t)d * 11 + k) * T], *acc = &mean_acc[(size_t)k * T];
+            for (int t = 0; t < T; t++) {
+                row[t] /= c;
+                acc[t] += row[t];
+            }
+        }
+    if (out->per_sample_means) memcpy(out->per_sample_means, sums.data(), sizeof(double) * sums.size());
+    double *dst[11] = {out->mags, out->mags2, out->mags4, out->energies, out->energies2, out->overlap, out->overlap2,
+                       out->overlap4, out->link_overlap, out->link_overlap2, out->link_overlap4};
+    for (int k = 0; k < 11; k++) {
+        if (!dst[k] || (k >= 5 && m.P == 0)) continue;
+        for (int t = 0; t < T; t++) dst[k][t] = mean_acc[(size_t)k * T + t] / (double)m.D;
+    }
+    if (want_eq) {  // results.rs:231-247, 275-282
+        double *edst[2] = {out->equil_energy_avg, out->equil_link_overlap_avg};
+        const size_t nck = ckpts.size();
+        for (int k = 0; k < 2; k++) {
+            if (!edst[k]) continue;
+            for (size_t cidx = 0; cidx < nck; cidx++)
+                for (int t = 0; t < T; t++) {
+                    double acc = 0.0;
+                    for (int64_t d = 0; d < m.D; d++) acc += eq_snap[(((size_t)d * nck + cidx) * 2 + k) * T + t];
+                    edst[k][cidx * T + t] = acc / (double)m.D;
+                }
+        }
+        if (out->per_sample_equil) memcpy(out->per_sample_equil, eq_snap.data(), sizeof(double) * eq_snap.size());
+    }
+    if (want_ac) {  // results.rs:217-231, 269-274: sum over realizations in order, divide by their number
+        double *tdst[2] = {out->mags2_tau, m.P > 0 ? out->overlap2_tau : nullptr};
+        for (int k = 0; k < 2; k++) {
+            if (!tdst[k]) continue;
+            for (int t = 0; t < T; t++) {
+                double acc = 0.0;
+                for (int64_t d = 0; d < m.D; d++) acc += taus[(size_t)k * m.D * T + (size_t)d * T + t];
+                tdst[k][t] = acc / (double)m.D;
+            }
+        }
+        if (out->per_sample_taus)
+            for (int64_t d = 0; d < m.D; d++)
+                for (int k = 0; k < 2; k++)
+                    memcpy(out->per_sample_taus + ((size_t)d * 2 + k) * T, &taus[(size_t)k * m.D * T + (size_t)d * T], sizeof(double) * (size_t)T);
+    }
+    if (m.P > 0) {
+        const int64_t per = (int64_t)T * (m.N + 1);
+        if (out->overlap_histogram || out->ql_at_q_sum || out->ql2_at_q_sum) {
+            if (!s->hist_allocated) {
+                if (out->overlap_histogram) memset(out->overlap_histogram, 0, sizeof(uint64_t) * (size_t)per);
+                if (out->ql_at_q_sum) memset(out->ql_at_q_sum, 0, sizeof(double) * (size_t)per);
+                if (out->ql2_at_q_sum) memset(out->ql2_at_q_sum, 0, sizeof(double) * (size_t)per);
+            } else {
+                unsigned long long *d_h = nullptr;
+                double *d_a = nullptr, *d_b = nullptr;
+                CUDA_TRY(pool_alloc(s, (void **)&d_h, sizeof(uint64_t) * (size_t)per));
+                CUDA_TRY(pool_alloc(s, (void **)&d_a, sizeof(double) * (size_t)per));
+                CUDA_TRY(pool_alloc(s, (void **)&d_b, sizeof(double) * (size_t)per));
+                reduce_hist_kernel<<<blocks_for(per, 256), 256, 0, s->stream>>>(m, s->st, d_h, d_a, d_b);
+                CUDA_TRY(cudaStreamSynchronize(s->stream));
+                if (out->overlap_histogram) CUDA_TRY(cudaMemcpy(out->overlap_histogram, d_h, sizeof(uint64_t) * (size_t)per, cudaMemcpyDeviceToHost));
+                if (out->ql_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql_at_q_sum, d_a, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
+                if (out->ql2_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql2_at_q_sum, d_b, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
+                pool_free(s, d_h); pool_free(s, d_a); pool_free(s, d_b);
+            }
+        }
+        const size_t all = (size_t)m.D * per;
+        if (out->per_sample_overlap_histogram) {
+            if (!s->hist_allocated) memset(out->per_sample_overlap_histogram, 0, sizeof(uint64_t) * all);
+            else {
+                const int64_t chunk = std::min<int64_t>((int64_t)all, int64_t(1) << 26);
+                unsigned long long *d_w = nullptr;
+                CUDA_TRY(pool_alloc(s, (void **)&d_w, sizeof(uint64_t) * (size_t)chunk));
+                for (int64_t off = 0; off < (int64_t)all; off += chunk) {
+                    const int64_t n = std::min<int64_t>(chunk, (int64_t)all - off);
+                    widen_u32_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->st.hist + off, d_w, n);
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    CUDA_TRY(cudaMemcpy(out->per_sample_overlap_histogram + off, d_w, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+                }
+                pool_free(s, d_w);
+            }
+        }
+        if (out->per_sample_ql_at_q_sum) {
+            if (!s->hist_allocated) memset(out->per_sample_ql_at_q_sum, 0, sizeof(double) * all);
+            else CUDA_TRY(cudaMemcpy(out->per_sample_ql_at_q_sum, s->st.ql_at_q, sizeof(double) * all, cudaMemcpyDeviceToHost));
+        }
+        if (out->per_sample_ql2_at_q_sum) {
+            if (!s->hist_allocated) memset(out->per_sample_ql2_at_q_sum, 0, sizeof(double) * all);
+            else CUDA_TRY(cudaMemcpy(out->per_sample_ql2_at_q_sum, s->st.ql2_at_q, sizeof(double) * all, cudaMemcpyDeviceToHost));
+        }
+    }
+    if (T > 1) {
+        if (out->pt_edge_attempts)
+            CUDA_TRY(cudaMemcpy(out->pt_edge_attempts, s->pt.edge_attempts, sizeof(uint64_t) * (size_t)(m.D * (T - 1)), cudaMemcpyDeviceToHost));
+        if (out->pt_edge_acceptances)
+            CUDA_TRY(cudaMemcpy(out->pt_edge_acceptances, s->pt.edge_acceptances, sizeof(uint64_t) * (size_t)(m.D * (T - 1)), cudaMemcpyDeviceToHost));
+    }
+    if (out->pt_round_trips)
+        CUDA_TRY(cudaMemcpy(out->pt_round_trips, s->pt.round_trips, sizeof(uint64_t) * (size_t)(m.D * m.S), cudaMemcpyDeviceToHost));
+    return PP_OK;
+}
+
 extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *out, const volatile int32_t *interrupt,
                                void (*on_sweep)(void *, uint64_t), void *user) {
     if (!s || !cfg) return fail(PP_ERR_INVALID, "sim/cfg is NULL");
@@ -1681,7 +1856,8 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         }
     }
     const int64_t launches0 = s->launches;
-    s->profile = cfg->profile != 0;
+    s->profile = s->profile_next;
+    s->profile_next = false;
     s->prof_used = 0;
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
 
@@ -1725,51 +1901,11 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     };
     std::vector<Step> steps;
     int64_t sweep_id = 0;
-    // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel, up to 256 sweeps per launch
+    // ---- small realizations: the whole per-sweep sequence runs inside rows_resident_kernel (run_rows_resident)
     if (s->rows && s->resident && !s->profile && !want_ac && !want_eq && !want_fk && !want_oc) {
-        Ctx &c = chunks[0];
-        RowsView v = s->rv;
-        v.keys = s->d_keys;
-        ModelView mk = c.m;
-        mk.lut = cfg->sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
-        const bool gibbs = cfg->sweep_mode == PP_SWEEP_GIBBS;
-        while (sweep_id < cfg->n_sweeps) {
-            if (interrupt && *interrupt) return fail(PP_ERR_INTERRUPTED, "interrupted");
-            const int64_t mb_end = std::min<int64_t>(cfg->n_sweeps, sweep_id + 256);
-            ResidentArgs a;
-            a.sweep_id0 = sweep_id;
-            a.n_sweeps = (int)(mb_end - sweep_id);
-            a.warmup_sweeps = cfg->warmup_sweeps;
-            a.pt_interval = cfg->pt_interval > 0 ? cfg->pt_interval : 0;
-            a.pt_schedule = cfg->pt_schedule == PP_PT_FULL_LADDER ? 1 : 0;
-            a.sweep_counter0 = s->sweep_counter;
-            a.pt_event0 = s->pt_event_counter;
-            a.parity0 = s->next_parity;
-            a.spins_in_smem = 1;
-            a.dot_spin = c.dot_spin;
-            a.dot_link = c.dot_link;
-#define PP_RES3(C_, Z_, G_)                                                                                                       \
-    do {                                                                                                                          \
-        CUDA_TRY(cudaFuncSetAttribute(rows_resident_kernel<C_, Z_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->resident_smem)); \
-        rows_resident_kernel<C_, Z_, G_><<<(unsigned)mk.D, RESIDENT_THREADS, s->resident_smem, c.stream>>>(mk, v, c.st, c.pt, a);   \
-    } while (0)
-#define PP_RES2(C_, Z_) do { if (gibbs) PP_RES3(C_, Z_, true); else PP_RES3(C_, Z_, false); } while (0)
-            if (mk.coupling_class == COUP_FERRO) { if (mk.z == 2) PP_RES2(COUP_FERRO, 2); else PP_RES2(COUP_FERRO, 3); }
-            else { if (mk.z == 2) PP_RES2(COUP_UNIT, 2); else PP_RES2(COUP_UNIT, 3); }
-#undef PP_RES2
-#undef PP_RES3
-            s->launches++;
-            CUDA_TRY(cudaGetLastError());
-            for (int64_t sid = sweep_id; sid < mb_end; sid++) {
-                s->sweep_counter++;
-                if (cfg->pt_interval > 0 && sid % cfg->pt_interval == 0) {
-                    s->pt_event_counter++;
-                    if (mk.T >= 2 && cfg->pt_schedule == PP_PT_FULL_LADDER) s->next_parity = 1 - s->next_parity;
-                }
-                if (on_sweep) on_sweep(user, (uint64_t)sid);
-            }
-            sweep_id = mb_end;
-        }
+        st = run_rows_resident(s, chunks[0], cfg, interrupt, on_sweep, user);
+        if (st != PP_OK) return st;
+        sweep_id = cfg->n_sweeps;
     }
     while (sweep_id < cfg->n_sweeps) {
         if (interrupt && *interrupt) return fail(PP_ERR_INTERRUPTED, "interrupted");  // mod.rs:406-408 (polled once per macro batch)
@@ -1944,120 +2080,10 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         eq_snap.assign((size_t)m.D * ckpts.size() * 2 * m.T, 0.0);
         CUDA_TRY(cudaMemcpy(eq_snap.data(), d_eq_snap, sizeof(double) * eq_snap.size(), cudaMemcpyDeviceToHost));
     }
+    s->last_timing = pp_timing{ms, s->launches - launches0, prof_ms, prof_n};
     if (!out) return PP_OK;
-    out->sweep_loop_ms = ms;
-    out->kernel_launches = s->launches - launches0;
-    out->sweep_kernel_ms = prof_ms;
-    out->sweep_kernel_launches = prof_n;
 
-    // ---- results (statistics/stats.rs:29-35, results.rs:165-180, 250-259, overlap.rs:106-152)
-    const int T = m.T;
-    std::vector<double> sums((size_t)m.D * 11 * T);
-    CUDA_TRY(cudaMemcpy(sums.data(), s->st.sums, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost));
-    const double c_stat = n_rec > 0 ? (double)(n_rec * m.R) : 1.0;
-    const double c_ov = (n_rec > 0 && m.P > 0) ? (double)(n_rec * m.P) : 1.0;
-    // one pass in storage order; every (k, t) accumulator still adds its realizations in order (results.rs:165-180)
-    std::vector<double> mean_acc((size_t)11 * T, 0.0);
-    for (int64_t d = 0; d < m.D; d++)
-        for (int k = 0; k < 11; k++) {
-            const double c = k < 5 ? c_stat : c_ov;
-            double *row = &sums[((size_t)d * 11 + k) * T], *acc = &mean_acc[(size_t)k * T];
-            for (int t = 0; t < T; t++) {
-                row[t] /= c;
-                acc[t] += row[t];
-            }
-        }
-    if (out->per_sample_means) memcpy(out->per_sample_means, sums.data(), sizeof(double) * sums.size());
-    double *dst[11] = {out->mags, out->mags2, out->mags4, out->energies, out->energies2, out->overlap, out->overlap2,
-                       out->overlap4, out->link_overlap, out->link_overlap2, out->link_overlap4};
-    for (int k = 0; k < 11; k++) {
-        if (!dst[k] || (k >= 5 && m.P == 0)) continue;
-        for (int t = 0; t < T; t++) dst[k][t] = mean_acc[(size_t)k * T + t] / (double)m.D;
-    }
-    if (want_eq) {  // results.rs:231-247, 275-282
-        double *edst[2] = {out->equil_energy_avg, out->equil_link_overlap_avg};
-        const size_t nck = ckpts.size();
-        for (int k = 0; k < 2; k++) {
-            if (!edst[k]) continue;
-            for (size_t cidx = 0; cidx < nck; cidx++)
-                for (int t = 0; t < T; t++) {
-                    double acc = 0.0;
-                    for (int64_t d = 0; d < m.D; d++) acc += eq_snap[(((size_t)d * nck + cidx) * 2 + k) * T + t];
-                    edst[k][cidx * T + t] = acc / (double)m.D;
-                }
-        }
-        if (out->per_sample_equil) memcpy(out->per_sample_equil, eq_snap.data(), sizeof(double) * eq_snap.size());
-    }
-    if (want_ac) {  // results.rs:217-231, 269-274: sum over realizations in order, divide by their number
-        double *tdst[2] = {out->mags2_tau, m.P > 0 ? out->overlap2_tau : nullptr};
-        for (int k = 0; k < 2; k++) {
-            if (!tdst[k]) continue;
-            for (int t = 0; t < T; t++) {
-                double acc = 0.0;
-                for (int64_t d = 0; d < m.D; d++) acc += taus[(size_t)k * m.D * T + (size_t)d * T + t];
-                tdst[k][t] = acc / (double)m.D;
-            }
-        }
-        if (out->per_sample_taus)
-            for (int64_t d = 0; d < m.D; d++)
-                for (int k = 0; k < 2; k++)
-                    memcpy(out->per_sample_taus + ((size_t)d * 2 + k) * T, &taus[(size_t)k * m.D * T + (size_t)d * T], sizeof(double) * (size_t)T);
-    }
-    if (m.P > 0) {
-        const int64_t per = (int64_t)T * (m.N + 1);
-        if (out->overlap_histogram || out->ql_at_q_sum || out->ql2_at_q_sum) {
-            if (!s->hist_allocated) {
-                if (out->overlap_histogram) memset(out->overlap_histogram, 0, sizeof(uint64_t) * (size_t)per);
-                if (out->ql_at_q_sum) memset(out->ql_at_q_sum, 0, sizeof(double) * (size_t)per);
-                if (out->ql2_at_q_sum) memset(out->ql2_at_q_sum, 0, sizeof(double) * (size_t)per);
-            } else {
-                unsigned long long *d_h = nullptr;
-                double *d_a = nullptr, *d_b = nullptr;
-                CUDA_TRY(pool_alloc(s, (void **)&d_h, sizeof(uint64_t) * (size_t)per));
-                CUDA_TRY(pool_alloc(s, (void **)&d_a, sizeof(double) * (size_t)per));
-                CUDA_TRY(pool_alloc(s, (void **)&d_b, sizeof(double) * (size_t)per));
-                reduce_hist_kernel<<<blocks_for(per, 256), 256, 0, s->stream>>>(m, s->st, d_h, d_a, d_b);
-                CUDA_TRY(cudaStreamSynchronize(s->stream));
-                if (out->overlap_histogram) CUDA_TRY(cudaMemcpy(out->overlap_histogram, d_h, sizeof(uint64_t) * (size_t)per, cudaMemcpyDeviceToHost));
-                if (out->ql_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql_at_q_sum, d_a, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
-                if (out->ql2_at_q_sum) CUDA_TRY(cudaMemcpy(out->ql2_at_q_sum, d_b, sizeof(double) * (size_t)per, cudaMemcpyDeviceToHost));
-                pool_free(s, d_h); pool_free(s, d_a); pool_free(s, d_b);
-            }
-        }
-        const size_t all = (size_t)m.D * per;
-        if (out->per_sample_overlap_histogram) {
-            if (!s->hist_allocated) memset(out->per_sample_overlap_histogram, 0, sizeof(uint64_t) * all);
-            else {
-                const int64_t chunk = std::min<int64_t>((int64_t)all, int64_t(1) << 26);
-                unsigned long long *d_w = nullptr;
-                CUDA_TRY(pool_alloc(s, (void **)&d_w, sizeof(uint64_t) * (size_t)chunk));
-                for (int64_t off = 0; off < (int64_t)all; off += chunk) {
-                    const int64_t n = std::min<int64_t>(chunk, (int64_t)all - off);
-                    widen_u32_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->st.hist + off, d_w, n);
-                    CUDA_TRY(cudaStreamSynchronize(s->stream));
-                    CUDA_TRY(cudaMemcpy(out->per_sample_overlap_histogram + off, d_w, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost));
-                }
-                pool_free(s, d_w);
-            }
-        }
-        if (out->per_sample_ql_at_q_sum) {
-            if (!s->hist_allocated) memset(out->per_sample_ql_at_q_sum, 0, sizeof(double) * all);
-            else CUDA_TRY(cudaMemcpy(out->per_sample_ql_at_q_sum, s->st.ql_at_q, sizeof(double) * all, cudaMemcpyDeviceToHost));
-        }
-        if (out->per_sample_ql2_at_q_sum) {
-            if (!s->hist_allocated) memset(out->per_sample_ql2_at_q_sum, 0, sizeof(double) * all);
-            else CUDA_TRY(cudaMemcpy(out->per_sample_ql2_at_q_sum, s->st.ql2_at_q, sizeof(double) * all, cudaMemcpyDeviceToHost));
-        }
-    }
-    if (T > 1) {
-        if (out->pt_edge_attempts)
-            CUDA_TRY(cudaMemcpy(out->pt_edge_attempts, s->pt.edge_attempts, sizeof(uint64_t) * (size_t)(m.D * (T - 1)), cudaMemcpyDeviceToHost));
-        if (out->pt_edge_acceptances)
-            CUDA_TRY(cudaMemcpy(out->pt_edge_acceptances, s->pt.edge_acceptances, sizeof(uint64_t) * (size_t)(m.D * (T - 1)), cudaMemcpyDeviceToHost));
-    }
-    if (out->pt_round_trips)
-        CUDA_TRY(cudaMemcpy(out->pt_round_trips, s->pt.round_trips, sizeof(uint64_t) * (size_t)(m.D * m.S), cudaMemcpyDeviceToHost));
-    return PP_OK;
+    return collect_results(s, out, n_rec, want_eq, want_ac, ckpts, eq_snap, taus);
 }
 
 // ------------------------------------------------------------------------------------------

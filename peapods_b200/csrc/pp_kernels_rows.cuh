@@ -611,21 +611,88 @@ struct ResidentArgs {
 
 constexpr int RESIDENT_THREADS = 512;
 
+// bytes of the per-realization scalar state the resident kernel keeps in shared memory (8-byte aligned block)
+__host__ __device__ inline size_t resident_scalar_bytes(int S, int T, int P) {
+    const size_t n_edges = T > 1 ? (size_t)(T - 1) : 1;
+    size_t b = 8 * ((size_t)11 * T + (size_t)S + 2 * (size_t)P * T + 2 * n_edges + (size_t)S);  // sums, mags, dots, edge counters, round trips
+    b += 4 * ((size_t)S + (size_t)T + (size_t)S);                                              // energies, temps, system ids
+    b += (size_t)S;                                                                            // trip states
+    return (b + 15) & ~size_t(15);
+}
+
 template <int CLASS, int ZT, bool GIBBS>
 __global__ void __launch_bounds__(RESIDENT_THREADS)
-rows_resident_kernel(ModelView m, RowsView v, StatsView st, PtView pt, ResidentArgs a) {
+rows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, ResidentArgs a) {
     extern __shared__ __align__(16) uint32_t res_sm[];
-    const int z = ZT > 0 ? ZT : m.z, width = 4 * z + 1, L = v.L;
+    const int z = ZT > 0 ? ZT : mg.z, width = 4 * z + 1, L = vg.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = RESIDENT_THREADS / 32;
-    const int64_t d = blockIdx.x;
+    const int64_t dg = blockIdx.x;
+    const int S = mg.S, T = mg.T, P = mg.P, n_edges = T > 1 ? T - 1 : 1;
     uint32_t *lut_sm = res_sm;
-    int8_t *g_spins = m.spins + d * m.S * m.N;
-    const int64_t n_bytes = (int64_t)m.S * m.N;
-    int8_t *spins_d = a.spins_in_smem ? reinterpret_cast<int8_t *>(res_sm + ((m.T * width + 3) & ~3)) : g_spins;
-    for (int i = tid; i < m.T * width; i += RESIDENT_THREADS) lut_sm[i] = m.lut[i];
+    // ---- the realization's scalar state lives in shared memory for the whole launch: every phase of a sweep (colour passes,
+    // energies, overlap dots, fold, exchange) then waits on shared-memory latency, not on L2 round trips (the README quickstart
+    // spent 20 us per sweep on those: 7 dependent phases x ~3 us).  m / v / st / pt below are views of that copy with the
+    // realization index folded in (d = 0); the copy goes back to global memory at the end of the launch.
+    unsigned char *sc = reinterpret_cast<unsigned char *>(res_sm + ((T * width + 3) & ~3));
+    double *sums_sm = reinterpret_cast<double *>(sc);
+    long long *mag_sm = reinterpret_cast<long long *>(sums_sm + 11 * T);
+    long long *dsp_sm = mag_sm + S, *dlk_sm = dsp_sm + P * T;
+    unsigned long long *ea_sm = reinterpret_cast<unsigned long long *>(dlk_sm + P * T), *eacc_sm = ea_sm + n_edges, *rt_sm = eacc_sm + n_edges;
+    float *en_sm = reinterpret_cast<float *>(rt_sm + S), *temps_sm = en_sm + S;
+    int32_t *sid_sm = reinterpret_cast<int32_t *>(temps_sm + T);
+    uint8_t *trip_sm = reinterpret_cast<uint8_t *>(sid_sm + S);
+    int8_t *g_spins = mg.spins + dg * S * mg.N;
+    const int64_t n_bytes = (int64_t)S * mg.N;
+    int8_t *spins_d = a.spins_in_smem ? reinterpret_cast<int8_t *>(sc + resident_scalar_bytes(S, T, P)) : g_spins;
+    const int64_t bins = mg.N + 1;
+    for (int i = tid; i < T * width; i += RESIDENT_THREADS) lut_sm[i] = mg.lut[i];
+    for (int i = tid; i < 11 * T; i += RESIDENT_THREADS) sums_sm[i] = stg.sums[dg * 11 * T + i];
+    for (int i = tid; i < S; i += RESIDENT_THREADS) {
+        mag_sm[i] = mg.mags[dg * S + i];
+        en_sm[i] = mg.energies[dg * S + i];
+        sid_sm[i] = mg.system_ids[dg * S + i];
+        rt_sm[i] = ptg.round_trips[dg * S + i];
+        trip_sm[i] = ptg.trip_state[dg * S + i];
+    }
+    for (int i = tid; i < P * T; i += RESIDENT_THREADS) {
+        dsp_sm[i] = a.dot_spin[dg * P * T + i];
+        dlk_sm[i] = a.dot_link[dg * P * T + i];
+    }
+    for (int i = tid; i < T - 1; i += RESIDENT_THREADS) {
+        ea_sm[i] = ptg.edge_attempts[dg * (T - 1) + i];
+        eacc_sm[i] = ptg.edge_acceptances[dg * (T - 1) + i];
+    }
+    for (int i = tid; i < T; i += RESIDENT_THREADS) temps_sm[i] = mg.temps[i];
     if (a.spins_in_smem)
         for (int64_t i = tid; i < n_bytes / 16; i += RESIDENT_THREADS)
             reinterpret_cast<uint4 *>(spins_d)[i] = reinterpret_cast<const uint4 *>(g_spins)[i];
+    ModelView m = mg;
+    m.D = 1;
+    m.sample_offset = mg.sample_offset + dg;  // seeds stay those of the global realization index
+    m.system_ids = sid_sm;
+    m.energies = en_sm;
+    m.mags = mag_sm;
+    m.temps = temps_sm;
+    m.J8 = mg.J8 ? mg.J8 + (size_t)dg * mg.N * z : nullptr;
+    RowsView v = vg;
+    v.keys = vg.keys + dg;
+    StatsView st = stg;
+    st.sums = sums_sm;
+    if (stg.hist) {
+        st.hist = stg.hist + dg * T * bins;
+        st.ql_at_q = stg.ql_at_q + dg * T * bins;
+        st.ql2_at_q = stg.ql2_at_q + dg * T * bins;
+    }
+    st.dot_spin = dsp_sm;
+    st.dot_link = dlk_sm;
+    PtView pt = ptg;
+    pt.edge_attempts = ea_sm;
+    pt.edge_acceptances = eacc_sm;
+    pt.round_trips = rt_sm;
+    pt.trip_state = trip_sm;
+    a.dot_spin = dsp_sm;
+    a.dot_link = dlk_sm;
+    const int64_t d = 0;
     __syncthreads();
     constexpr int NS = rows_ns<CLASS>();
     const int sblocks = (m.S + NS - 1) / NS;
@@ -712,7 +779,7 @@ rows_resident_kernel(ModelView m, RowsView v, StatsView st, PtView pt, ResidentA
                 __syncthreads();
             }
             for (int t = tid; t < m.T; t += RESIDENT_THREADS)  // mod.rs:543-578
-                fold_one<0>(
+                fold_one<0, true>(
                     m, st, d, t, m.P > 0,
                     [&](int r) { return m.mags[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
                     [&](int r) { return m.energies[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
@@ -728,6 +795,24 @@ rows_resident_kernel(ModelView m, RowsView v, StatsView st, PtView pt, ResidentA
             }
             pt_event++;
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < 11 * T; i += RESIDENT_THREADS) stg.sums[dg * 11 * T + i] = sums_sm[i];
+    for (int i = tid; i < S; i += RESIDENT_THREADS) {
+        mg.mags[dg * S + i] = mag_sm[i];
+        mg.energies[dg * S + i] = en_sm[i];
+        mg.system_ids[dg * S + i] = sid_sm[i];
+        ptg.round_trips[dg * S + i] = rt_sm[i];
+        ptg.trip_state[dg * S + i] = trip_sm[i];
+    }
+    for (int i = tid; i < P * T; i += RESIDENT_THREADS) {
+        // (a.dot_spin / a.dot_link were redirected to the shared copy above: the handle's arrays are the StatsView's)
+        const_cast<long long *>(stg.dot_spin)[dg * P * T + i] = dsp_sm[i];
+        const_cast<long long *>(stg.dot_link)[dg * P * T + i] = dlk_sm[i];
+    }
+    for (int i = tid; i < T - 1; i += RESIDENT_THREADS) {
+        ptg.edge_attempts[dg * (T - 1) + i] = ea_sm[i];
+        ptg.edge_acceptances[dg * (T - 1) + i] = eacc_sm[i];
     }
     if (a.spins_in_smem)
         for (int64_t i = tid; i < n_bytes / 16; i += RESIDENT_THREADS)

@@ -89,12 +89,13 @@ slabp_sweep_kernel(ModelView m, SlabPView v, int colour, uint32_t sweep_index, i
             for (int u = 0; u < NM; u++) M[u] = 0u;
             const uint32_t q = (uint32_t)(((int64_t)gx0 * v.L1 + x1) * v.W + w);  // rank >> 5 of the word's sites
             const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
+            const PhiloxKeys ks = philox_keys(v.k0, v.k1);  // six calls, one key schedule
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 uint32_t wd[12];
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const u32x4 o = philox4x32(q, sweep_index, sys, tagc | ((uint32_t)(3 * h + c) << 8), v.k0, v.k1);
+                    const u32x4 o = philox4x32_k(q, sweep_index, sys, tagc | ((uint32_t)(3 * h + c) << 8), ks);
                     wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
                 }
 #pragma unroll

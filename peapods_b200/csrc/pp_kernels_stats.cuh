@@ -32,7 +32,9 @@ struct PtView {
 // Mv / Ev: magnetisation sums and energies of the R systems sitting at slot t (replica order);
 // dsp / dlk: the P pair dots at slot t.  All f64 accumulations in the reference's order.
 // RFIX > 0: the replica count is the compile-time constant RFIX (loops unroll, the getters may index registers).
-template <int RFIX, typename GetM, typename GetE, typename GetS, typename GetL>
+// RED_HIST: the three histogram cells are updated with fire-and-forget reductions instead of load-add-store (the thread does
+// not wait for the loads; one thread per (d, t) and stream order keep every cell's additions in the reference's order).
+template <int RFIX, bool RED_HIST = false, typename GetM, typename GetE, typename GetS, typename GetL>
 __device__ __forceinline__ void fold_one(const ModelView &m, const StatsView &st, int64_t d, int t, int with_overlap,
                                          GetM get_m, GetE get_e, GetS get_ds, GetL get_dl) {
     const float nf = (float)m.N;
@@ -75,9 +77,15 @@ __device__ __forceinline__ void fold_one(const ModelView &m, const StatsView &st
         o5 = __dadd_rn(o5, (double)__fmul_rn(ql2, ql2));
         const int64_t idx = (dsp + m.N) / 2;
         const int64_t h = (d * m.T + t) * bins + idx;
-        st.hist[h] += 1u;
-        st.ql_at_q[h] = __dadd_rn(st.ql_at_q[h], (double)ql);
-        st.ql2_at_q[h] = __dadd_rn(st.ql2_at_q[h], (double)ql2);
+        if (RED_HIST) {
+            atomicAdd(st.hist + h, 1u);
+            atomicAdd(st.ql_at_q + h, (double)ql);
+            atomicAdd(st.ql2_at_q + h, (double)ql2);
+        } else {
+            st.hist[h] += 1u;
+            st.ql_at_q[h] = __dadd_rn(st.ql_at_q[h], (double)ql);
+            st.ql2_at_q[h] = __dadd_rn(st.ql2_at_q[h], (double)ql2);
+        }
     }
     sums[5 * m.T] = o0; sums[6 * m.T] = o1; sums[7 * m.T] = o2; sums[8 * m.T] = o3; sums[9 * m.T] = o4;
     sums[10 * m.T] = o5;

@@ -71,6 +71,31 @@ PP_HD u32x4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
     return u32x4{c0, c1, c2, c3};
 }
 
+// the same generator with the round keys k + i * W precomputed once (a thread that makes several calls with one key)
+struct PhiloxKeys {
+    uint32_t k0[PHILOX_ROUNDS], k1[PHILOX_ROUNDS];
+};
+PP_HD PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys ks;
+#pragma unroll
+    for (int round = 0; round < PHILOX_ROUNDS; round++) {
+        ks.k0[round] = k0 + (uint32_t)round * PHILOX_W0;
+        ks.k1[round] = k1 + (uint32_t)round * PHILOX_W1;
+    }
+    return ks;
+}
+PP_HD u32x4 philox4x32_k(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &ks) {
+#pragma unroll
+    for (int round = 0; round < PHILOX_ROUNDS; round++) {
+        uint32_t hi0 = mulhi32(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        uint32_t hi1 = mulhi32(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ ks.k0[round];
+        uint32_t n2 = hi0 ^ c3 ^ ks.k1[round];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
 PP_HD uint64_t splitmix64(uint64_t value) {  // realization.rs:9-15
     value += 0x9E3779B97F4A7C15ull;
     uint64_t mixed = value;

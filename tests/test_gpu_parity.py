@@ -846,3 +846,34 @@ def test_system_split_rejects_what_it_cannot_hold():
                            nccl_unique_id=bytes(128))
     with pytest.raises(ValueError):   # multispin layout
         pb.IsingSimulation([8, 8], "ferro", t[:2], 1, None, 1, layout="msc", system_ranks=2, system_rank=0, nccl_unique_id=bytes(128))
+
+
+def test_generic_multispin_counters_hold_a_large_lattice():
+    """Round-1 advisor finding: the table-driven multispin kernels count per thread in bit-sliced planes; with 12 planes a thread
+    overflowed once ceil(N / 256) * z passed 4095 (2-D 1024^2: 8192 adds per thread).  20 planes now, guarded in pp_create:
+    energies, magnetisations and overlap dots of random configurations on 1024 x 1024 (N z = 2^21) against a host count."""
+    import peapods_b200 as pb
+
+    shape, D, R = (1024, 1024), 32, 2
+    rng = np.random.default_rng(21)
+    J = (2 * rng.integers(0, 2, size=(D,) + shape + (2,), dtype=np.int8) - 1).astype(np.float32)
+    gpu = pb.IsingSimulation(list(shape), J, np.asarray([2.0], np.float32), R, None, 5, layout="msc")
+    assert gpu.layout == "msc" and not gpu.uses_msc3d
+    N = shape[0] * shape[1]
+    check = (0, 17, 31)
+    spins = {}
+    for d in check:   # the other lanes keep their INIT-domain configuration
+        spins[d] = (2 * rng.integers(0, 2, size=(R, N), dtype=np.int8) - 1).astype(np.int8)
+        gpu.set_spins(spins[d], d)
+    e, m = gpu.op_energies_mags()
+    ds, dl = gpu.op_overlap()
+    for d in check:
+        s = spins[d].reshape((R,) + shape).astype(np.int64)
+        Jd = J[d].astype(np.int64)
+        for r in range(R):
+            bonds = int((s[r] * np.roll(s[r], -1, axis=0) * Jd[..., 0]).sum() + (s[r] * np.roll(s[r], -1, axis=1) * Jd[..., 1]).sum())
+            assert m[d, r] == int(s[r].sum())
+            assert e[d, r] == np.float32(bonds) / np.float32(N)
+        q = s[0] * s[1]
+        assert ds[d, 0, 0] == int(q.sum())
+        assert dl[d, 0, 0] == int((q * np.roll(q, -1, axis=0)).sum() + (q * np.roll(q, -1, axis=1)).sum())

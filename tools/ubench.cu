@@ -9,8 +9,8 @@
 constexpr int CH = 12;     // independent chains per thread
 constexpr int IT = 4096;  // loop iterations
 
-enum { K_LOP3, K_IMADW, K_IMAD, K_IADD3, K_SHF, K_SETSEL, K_MIX_LOP_IMADW_2_1, K_MIX_LOP_IMAD_1_1, K_MIX_LOP_IMADW_1_1, K_LDS128, K_PRMT, K_MIX_LOP_IMADW_4_1, K_IMADHI, K_MIX_LOP_IMAD_2_1, K_MIX_LOP_IMAD_3_1, K_MIX_LOP_VIADD_1_1, K_MIX_LOP_IMADW_3_1, K_LDS128_SEQ, K_N };
-const char *NAMES[] = {"lop3", "imad.wide.u32", "imad.lo", "iadd3", "shf", "isetp+sel", "lop3:imad.wide 2:1", "lop3:imad 1:1", "lop3:imad.wide 1:1", "lds.128", "prmt", "lop3:imad.wide 4:1", "imad.hi.s32", "lop3:imad 2:1", "lop3:imad 3:1", "lop3:add 1:1", "lop3:imad.wide 3:1", "lds.128 conflict-free"};
+enum { K_LOP3, K_IMADW, K_IMAD, K_IADD3, K_SHF, K_SETSEL, K_MIX_LOP_IMADW_2_1, K_MIX_LOP_IMAD_1_1, K_MIX_LOP_IMADW_1_1, K_LDS128, K_PRMT, K_MIX_LOP_IMADW_4_1, K_IMADHI, K_MIX_LOP_IMAD_2_1, K_MIX_LOP_IMAD_3_1, K_MIX_LOP_VIADD_1_1, K_MIX_LOP_IMADW_3_1, K_LDS128_SEQ, K_MULW, K_MULHILO, K_MIX_LOP_MULW_4_1, K_MIX_LOP_MULHILO_4_1, K_SETP_PLOP, K_POPC, K_VOTE, K_N };
+const char *NAMES[] = {"lop3", "imad.wide.u32", "imad.lo", "iadd3", "shf", "isetp+sel", "lop3:imad.wide 2:1", "lop3:imad 1:1", "lop3:imad.wide 1:1", "lds.128", "prmt", "lop3:imad.wide 4:1", "imad.hi.s32", "lop3:imad 2:1", "lop3:imad 3:1", "lop3:add 1:1", "lop3:imad.wide 3:1", "lds.128 conflict-free", "mul.wide.u32 (no addend)", "mul.hi + mul.lo", "lop3:mul.wide 4:1", "lop3:(mul.hi+mul.lo) 4:1", "setp + @p lop3", "popc", "vote.ballot"};
 
 template <int KIND>
 __global__ void __launch_bounds__(1024, 1) bench(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
@@ -67,6 +67,28 @@ __global__ void __launch_bounds__(1024, 1) bench(uint32_t *out, uint32_t seed, u
                 if (c % 2) asm("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
                 else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
             }
+            if (KIND == K_MULW) asm("mul.wide.u32 %0, %1, %2;" : "=l"(w[c]) : "r"((uint32_t)w[c] ^ (uint32_t)(w[c] >> 32)), "r"(b));
+            if (KIND == K_MULHILO) {
+                uint32_t hi, lo;
+                asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(x[c]), "r"(b));
+                asm("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(x[c]), "r"(b));
+                x[c] = hi ^ lo;
+            }
+            if (KIND == K_MIX_LOP_MULW_4_1) {
+                if (c % 5 == 4) asm("mul.wide.u32 %0, %1, %2;" : "=l"(w[c]) : "r"((uint32_t)w[c] ^ (uint32_t)(w[c] >> 32)), "r"(b));
+                else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_MIX_LOP_MULHILO_4_1) {
+                if (c % 5 == 4) {
+                    uint32_t hi, lo;
+                    asm("mul.hi.u32 %0, %1, %2;" : "=r"(hi) : "r"(x[c]), "r"(b));
+                    asm("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"(x[c]), "r"(b));
+                    x[c] = hi ^ lo;
+                } else asm("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
+            }
+            if (KIND == K_SETP_PLOP) asm("{.reg .pred p; setp.lt.u32 p, %0, %1; @p or.b32 %0, %0, 0x10; add.u32 %0, %0, %2;}" : "+r"(x[c]) : "r"(a), "r"(b));
+            if (KIND == K_POPC) asm("popc.b32 %0, %0;" : "+r"(x[c]));
+            if (KIND == K_VOTE) asm("{.reg .pred p; setp.lt.u32 p, %0, %1; vote.sync.ballot.b32 %0, p, 0xffffffff;}" : "+r"(x[c]) : "r"(a));
             if (KIND == K_LDS128_SEQ) {
                 uint4 v = sm[(threadIdx.x + (x[c] & 0x3e0)) & 1023];
                 x[c] = (v.x ^ v.y) + (v.z ^ v.w);
@@ -129,6 +151,13 @@ int main() {
         run<K_MIX_LOP_IMAD_3_1>(out, cyc, threads);
         run<K_MIX_LOP_IMADW_3_1>(out, cyc, threads);
         run<K_MIX_LOP_VIADD_1_1>(out, cyc, threads);
+        run<K_MULW>(out, cyc, threads);
+        run<K_MULHILO>(out, cyc, threads);
+        run<K_MIX_LOP_MULW_4_1>(out, cyc, threads);
+        run<K_MIX_LOP_MULHILO_4_1>(out, cyc, threads);
+        run<K_SETP_PLOP>(out, cyc, threads);
+        run<K_POPC>(out, cyc, threads);
+        run<K_VOTE>(out, cyc, threads);
         run<K_LDS128>(out, cyc, threads);
         run<K_LDS128_SEQ>(out, cyc, threads);
     }
