@@ -54,9 +54,10 @@ SAMPLES_PER_GPU = 4096
 Z = 3
 SEED = 42
 B_ALG_MSC = 0.125 + 0.125 + (Z / 8.0) / (N_TEMPS * N_REPLICAS)  # bytes per attempt
-# dram__bytes_read.sum + dram__bytes_write.sum of one msc3d_kernel launch covering 1024 samples, mean of the three launches of
-# the `ncu --set full` capture summarised in profiles/r1k_msc3d_summary.md; a launch over D samples moves D/1024 times that
-NCU_DRAM_BYTES_PER_1024_SAMPLES = 125.8e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one msc3d_kernel launch covering the FULL 4096 samples (recorded sweep), mean of the
+# two launches of the `ncu --set full` capture summarised in profiles/r2_summary.md (350.6 MB read + 273.6 MB written); a launch
+# over another sample count is scaled by it
+NCU_DRAM_BYTES_PER_4096_SAMPLES = 624.2e6
 
 
 def peaks():
@@ -529,8 +530,8 @@ def run_ours(args):
     alg_bytes_per_launch = B_ALG_MSC * attempts_step / k_n
     achieved = alg_bytes_per_launch / (k_ms / k_n * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": args.traffic if args.traffic is not None else NCU_DRAM_BYTES_PER_1024_SAMPLES * D / 1024.0 * (k_n_expected / k_n),
-                "traffic_source": "ncu --set full (profiles/r1k_msc3d_summary.md), scaled to this launch size",
+                "traffic": args.traffic if args.traffic is not None else NCU_DRAM_BYTES_PER_4096_SAMPLES * D / 4096.0 * (k_n_expected / k_n),
+                "traffic_source": "ncu --set full at D = 4096 in one launch (profiles/r2_summary.md), scaled by the sample count of this launch",
                 "kernel": "msc3d_kernel (sweep + energy / magnetisation / overlap / fold)", "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes_per_launch, "launches_timed": k_n, "kernel_ms_mean": k_ms / k_n,
                 "kernel_share_of_step": k_ms / max(sim.last_sweep_loop_ms, 1e-9)}
