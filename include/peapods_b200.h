@@ -171,6 +171,9 @@ pp_status pp_get_spins(pp_sim *sim, int64_t realization, int8_t *out /* [S*N], s
 int64_t pp_local_spin_count(const pp_sim *sim);
 /* NCCL bootstrap for PP_LAYOUT_SLAB across processes: rank 0 calls this, the host broadcasts the bytes */
 pp_status pp_nccl_unique_id(uint8_t *out /* [PP_NCCL_ID_BYTES] */);
+/* 1 when this process already holds the communicator of (device, world size, rank): handles created from now on reuse it and
+ * need no bootstrap token (every rank of the world must then pass nccl_unique_id = NULL, or every rank a fresh token) */
+int32_t pp_nccl_comm_cached(int32_t device, int32_t ranks, int32_t rank);
 pp_status pp_get_system_ids(pp_sim *sim, int64_t realization, int64_t *out /* [S] */);
 pp_status pp_get_energies(pp_sim *sim, int64_t realization, float *out /* [S] by system */);
 int32_t pp_get_layout(const pp_sim *sim);
@@ -189,6 +192,9 @@ pp_status pp_debug_last_timing(const pp_sim *sim, pp_timing *out);
 int32_t pp_uses_msc3d(const pp_sim *sim);
 /* 1 when a PP_LAYOUT_SLAB handle stores one bit per spin (shape[2] % 64 == 0: pp_kernels_slabp.cuh, packed draw mapping), else 0 */
 int32_t pp_slab_packed(const pp_sim *sim);
+/* 1 when an int8-layout handle keeps its ferromagnetic systems as one bit per spin, resident in shared memory per launch
+ * (pp_kernels_prows.cuh: row-alternating colouring, last extent % 64 == 0; packed draw mapping), else 0 */
+int32_t pp_rows_packed(const pp_sim *sim);
 
 /* operator-level entry points with the reference's slice semantics (unit-level parity tests):
  * H2D -> kernel -> D2H on the handle's state. */

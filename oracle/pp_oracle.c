@@ -1161,7 +1161,7 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
         set_err("overlap cluster requires n_replicas >= max group_size"); /* mod.rs:207-213 */
         return -1;
     }
-    if ((cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX) ||
+    if ((cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX && sim->rng_mode != ORC_RNG_PHILOX_PACKED) ||
         (cfg->overlap_cluster_interval > 0 && sim->rng_mode == ORC_RNG_XOSHIRO)) {
         set_err("cluster updates are restated for the RNG-SPEC modes only (FK: int8 mode)");
         return -1;

@@ -105,10 +105,12 @@ SIGNATURES = {
     "pp_get_layout": (C.c_int32, [C.c_void_p]),
     "pp_local_spin_count": (C.c_int64, [C.c_void_p]),
     "pp_nccl_unique_id": (C.c_int32, [C.c_void_p]),
+    "pp_nccl_comm_cached": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "pp_uses_msc3d": (C.c_int32, [C.c_void_p]),
     "pp_debug_set_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pp_debug_last_timing": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pp_slab_packed": (C.c_int32, [C.c_void_p]),
+    "pp_rows_packed": (C.c_int32, [C.c_void_p]),
     "pp_set_spins": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_set_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_op_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32]),

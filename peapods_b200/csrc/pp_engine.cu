@@ -27,6 +27,7 @@
 #include "pp_kernels_msc.cuh"
 #include "pp_kernels_msc3d.cuh"
 #include "pp_kernels_rows.cuh"
+#include "pp_kernels_prows.cuh"
 #include "pp_kernels_stats.cuh"
 #include "pp_plan.h"
 #include "pp_slab.cuh"
@@ -235,6 +236,11 @@ struct pp_sim {
     std::vector<void *> rows_bufs;
     std::vector<uint32_t> rows_class_start;
     uint64_t *d_keys = nullptr;
+    // ferromagnets with one bit per spin (pp_kernels_prows.cuh): the packed words are the state, `d_spins` is an int8 scratch view
+    // that the API and the int8-only kernels (cluster moves) see through prows_sync(): unpack before, pack after
+    bool prows = false;
+    PRowsView pv{};
+    int prows_nm[2] = {0, 0};                          // thresholds compared per site: [metropolis, gibbs]
     long long *d_rows_acc = nullptr;                   // [2 * max(D*S, D*P*T)] split-reduction scratch (kept zero between launches)
     unsigned int *d_rows_arrive = nullptr;
     int rows_nb = 1;                                   // blocks per system / pair of the split reductions
@@ -361,6 +367,7 @@ static void free_sim(pp_sim *s) {
     if (s->d_keys) pool_free(s, s->d_keys);
     if (s->d_nbr16) pool_free(s, s->d_nbr16);
     if (s->d_site16) pool_free(s, s->d_site16);
+    if (s->pv.words) pool_free(s, s->pv.words);
     if (s->d_rows_acc) pool_free(s, s->d_rows_acc);
     if (s->d_rows_arrive) pool_free(s, s->d_rows_arrive);
     if (s->slab) {
@@ -399,6 +406,7 @@ extern "C" pp_status pp_debug_last_timing(const pp_sim *sim, pp_timing *out) {
 }
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
+extern "C" int32_t pp_rows_packed(const pp_sim *sim) { return sim && sim->prows ? 1 : 0; }
 extern "C" int64_t pp_local_spin_count(const pp_sim *sim) {
     if (!sim) return 0;
     return sim->slab ? sim->slab->local_planes() * sim->slab->plane : sim->mv.N;
@@ -570,11 +578,15 @@ static pp_status launch_msc3d(pp_sim *s, Ctx &c, const ModelView &m, int sweep_m
 
 // One communicator per (process, device, world, rank), kept for the life of the process: ncclCommInitRank costs seconds and a handle
 // is built per model.  Every rank takes the same branch, so the bootstrap token of a later handle is simply not used.
+static std::mutex comm_mu;
+static std::map<std::tuple<int, int, int>, ncclComm_t> comm_cache;
+extern "C" int32_t pp_nccl_comm_cached(int32_t device, int32_t ranks, int32_t rank) {
+    std::lock_guard<std::mutex> lock(comm_mu);
+    return comm_cache.count(std::tuple<int, int, int>{device, ranks, rank}) ? 1 : 0;
+}
 static pp_status cached_comm(int device, int ranks, int rank, const uint8_t *token, ncclComm_t *out) {
     NcclApi &nc = nccl_api();
     if (!nc.error.empty()) return fail(PP_ERR_NCCL, nc.error);
-    static std::mutex comm_mu;
-    static std::map<std::tuple<int, int, int>, ncclComm_t> comm_cache;
     std::lock_guard<std::mutex> lock(comm_mu);
     const std::tuple<int, int, int> ck{device, ranks, rank};
     auto it = comm_cache.find(ck);
@@ -775,6 +787,44 @@ static pp_status slab_energy(pp_sim *s, const ModelView &m, cudaStream_t stream,
     return slab_finish_energy(s, m, stream, want_mags);
 }
 
+// ---- ferromagnets with one bit per spin (pp_kernels_prows.cuh) --------------------------------------------------------------
+// packed words <-> the int8 view; dir 0: pack (int8 -> words), 1: unpack
+static pp_status prows_sync(pp_sim *s, cudaStream_t stream, int dir) {
+    const ModelView &m = s->mv;
+    prows_convert_kernel<<<dim3((unsigned)(m.D * m.S), blocks_for(s->rv.n_rows * s->pv.W, PROWS_THREADS)), PROWS_THREADS, 0, stream>>>(m, s->rv, s->pv, dir);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+static pp_status launch_prows(pp_sim *s, Ctx &c, const ModelView &m_in, int sweep_mode, uint32_t sweep_index, int n_sweeps, bool want_energy,
+                              bool want_mags) {
+    ModelView m = m_in;
+    m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;  // (the energy-only call comes without a table)
+    RowsView v = s->rv;
+    v.keys = s->d_keys + (c.m.sample_offset - s->mv.sample_offset);
+    const int nm = s->prows_nm[sweep_mode == PP_SWEEP_GIBBS ? 1 : 0];
+    const size_t smem = sizeof(uint32_t) * (size_t)s->pv.sys_words;
+    const unsigned grid = (unsigned)(m.D * m.S);
+#define PP_PROWS(Z_, NM_)                                                                                                              \
+    do {                                                                                                                               \
+        static bool configured = false;                                                                                                \
+        if (!configured) {                                                                                                             \
+            CUDA_TRY(cudaFuncSetAttribute(prows_sweep_kernel<Z_, NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       \
+            configured = true;                                                                                                         \
+        }                                                                                                                              \
+        prows_sweep_kernel<Z_, NM_><<<grid, PROWS_THREADS, smem, c.stream>>>(m, v, s->pv, sweep_index, n_sweeps, want_energy ? 1 : 0,  \
+                                                                             want_mags ? 1 : 0);                                       \
+    } while (0)
+    if (m.z == 2) { if (nm == 2) PP_PROWS(2, 2); else PP_PROWS(2, 5); }
+    else if (m.z == 3) { if (nm == 3) PP_PROWS(3, 3); else PP_PROWS(3, 7); }
+    else { if (nm == 4) PP_PROWS(4, 4); else PP_PROWS(4, 9); }
+#undef PP_PROWS
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
 // want_overlap / want_fold: the caller wants the replica-pair dots of the post-sweep state / the recorded-sweep fold;
 // *fused is set when the sweep kernel did both itself (msc3d epilogue), otherwise the caller launches
 // launch_overlap() and fold_kernel.
@@ -820,6 +870,11 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
         return PP_OK;
     }
     if (n_sweeps > 0) prof_mark(s, c.stream);
+    if (s->prows) {  // every sweep of the batch in one launch, the system in shared memory; energies out of the same launch
+        pp_status st = launch_prows(s, c, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags);
+        if (n_sweeps > 0) prof_mark(s, c.stream);
+        return st;
+    }
     if (s->rows) {
         RowsView v = s->rv;
         v.keys = s->d_keys + (c.m.sample_offset - s->mv.sample_offset);
@@ -881,6 +936,7 @@ static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
     if (s->layout == PP_LAYOUT_MSC) return launch_sweeps(s, c, PP_SWEEP_METROPOLIS, 0, 0, 0, true, want_mags);
     if (s->layout == PP_LAYOUT_SLAB) return slab_energy(s, m, c.stream, want_mags);
     const unsigned grid = (unsigned)(m.D * m.S);
+    if (s->prows) return launch_prows(s, c, m, PP_SWEEP_METROPOLIS, 0u, 0, true, want_mags);
     if (s->rows) {
         const dim3 g2(grid, (unsigned)(m.coupling_class == COUP_F32 ? 1 : s->rows_nb));
 #define PP_RE(C_, Z_) rows_energy_kernel<C_, Z_><<<g2, 256, 0, c.stream>>>(m, s->rv, want_mags, s->d_rows_acc, s->d_rows_arrive)
@@ -915,7 +971,12 @@ static pp_status launch_overlap(pp_sim *s, Ctx &c) {
     }
     if (s->layout == PP_LAYOUT_MSC)
         msc_overlap_kernel<<<(unsigned)(c.G * m.P * m.T), MSC_BLOCK, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
-    else if (s->rows)
+    else if (s->prows) {
+        const unsigned grid = (unsigned)(m.D * m.P * m.T);
+        if (m.z == 2) prows_overlap_kernel<2><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.dot_spin, c.dot_link);
+        else if (m.z == 3) prows_overlap_kernel<3><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.dot_spin, c.dot_link);
+        else prows_overlap_kernel<4><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.dot_spin, c.dot_link);
+    } else if (s->rows)
         rows_overlap_kernel<<<dim3((unsigned)(m.D * m.P * m.T), (unsigned)s->rows_nb), 256, 0, c.stream>>>(m, s->rv, c.dot_spin, c.dot_link,
                                                                                                    s->d_rows_acc, s->d_rows_arrive);
     else
@@ -973,7 +1034,10 @@ static pp_status sys_allgather(pp_sim *s, cudaStream_t stream, bool energies, bo
         NCCL_TRY(nc.AllGather((const char *)(s->d_energies + m.sys_lo), s->d_energies, per * sizeof(float), ncclUint8, s->sys_comm, stream));
     if (mags)
         NCCL_TRY(nc.AllGather((const char *)(s->d_mags + m.sys_lo), s->d_mags, per * sizeof(long long), ncclUint8, s->sys_comm, stream));
-    if (spins)
+    if (spins && s->prows)
+        NCCL_TRY(nc.AllGather((const char *)(s->pv.words + (size_t)m.sys_lo * s->pv.sys_words), s->pv.words,
+                              per * (size_t)s->pv.sys_words * sizeof(uint32_t), ncclUint8, s->sys_comm, stream));
+    else if (spins)
         NCCL_TRY(nc.AllGather((const char *)(s->d_spins + (size_t)m.sys_lo * m.N), s->d_spins, per * (size_t)m.N, ncclUint8, s->sys_comm, stream));
     s->launches += (energies ? 1 : 0) + (mags ? 1 : 0) + (spins ? 1 : 0);
     return PP_OK;
@@ -1015,6 +1079,10 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
     } else {
         dim3 grid((unsigned)DS, blocks_for((m.N + 3) / 4, 128));
         init_spins_int8_kernel<<<grid, 128, 0, s->stream>>>(m);
+        if (s->prows) {  // the same site-indexed INIT draws as every layout, then one bit per spin
+            pp_status stp = prows_sync(s, s->stream, 0);
+            if (stp != PP_OK) return stp;
+        }
     }
     CUDA_TRY(cudaGetLastError());
     Ctx wc = whole_ctx(s);
@@ -1056,7 +1124,6 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         if (desc->n_disorder != 1 || desc->n_replicas != 1) return fail(PP_ERR_UNSUPPORTED, "slab layout holds one realization with one replica per temperature");
         if (desc->shape[0] % (2 * slab_ranks) != 0) return fail(PP_ERR_INVALID, "slab layout needs shape[0] to be a multiple of 2 * slab_ranks");
         if (desc->slab_rank >= slab_ranks) return fail(PP_ERR_INVALID, "slab_rank out of range");
-        if (slab_ranks > 1 && desc->slab_rank >= 0 && !desc->nccl_unique_id) return fail(PP_ERR_INVALID, "nccl_unique_id is NULL");
     } else if (desc->slab_ranks > 1) {
         return fail(PP_ERR_INVALID, "slab_ranks > 1 needs layout = PP_LAYOUT_SLAB");
     }
@@ -1328,6 +1395,21 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                               (z == 2 || z == 3);
                 if (const char *e = getenv("PP_RESIDENT")) s->resident = s->resident && atoi(e) != 0;
             }
+            // ferromagnets with one bit per spin, a system resident in one CTA's shared memory (pp_kernels_prows.cuh): rows that
+            // split into whole 64-site word pairs, offsets that move by at most one site along the rows, 2-4 forward directions
+            {
+                bool dl_ok = true;
+                for (int k = 0; k < z; k++) dl_ok = dl_ok && std::abs(rp.dl[(size_t)k]) <= 1;
+                const int64_t W = rp.L / 64, sys_words = rp.n_rows * 2 * W;
+                s->prows = m.coupling_class == COUP_FERRO && rp.L % 64 == 0 && dl_ok && z >= 2 && z <= PROWS_MAX_Z &&
+                           sys_words * 4 <= 160 * 1024 && !s->resident;
+                if (const char *e = getenv("PP_ROWS_PACKED")) s->prows = s->prows && atoi(e) != 0;
+                if (s->prows) {
+                    s->pv.W = (int)W;
+                    s->pv.sys_words = sys_words;
+                    CREATE_TRY(pool_alloc(s, (void **)&s->pv.words, sizeof(uint32_t) * (size_t)(m.D * m.S * sys_words)));
+                }
+            }
         }
     }
     if (sys_ranks > 1) {
@@ -1375,6 +1457,22 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             uint32_t *&dst = mode == 0 ? s->d_lut_metro : s->d_lut_gibbs;
             CREATE_TRY(pool_alloc(s, (void **)&dst, sizeof(uint32_t) * lut.size()));
             CREATE_TRY(cudaMemcpy(dst, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice));
+        }
+    }
+
+    // packed-row kernel: thresholds compared per site -- z' when the counts for unsat >= z' are 2^24 (energy change <= 0 always
+    // accepted) and the others are below 2^24, else all 2z' + 1
+    if (s->prows) {
+        std::vector<uint32_t> lut((size_t)m.T * (4 * z + 1));
+        for (int mode = 0; mode < 2; mode++) {
+            pp_metropolis_lookup(s->temps.data(), m.T, z, mode, lut.data());
+            bool fast = true;
+            for (int t = 0; t < m.T; t++)
+                for (int u = 0; u <= 2 * z; u++) {
+                    const uint32_t c = lut[(size_t)t * (4 * z + 1) + 2 * u];
+                    if (u >= z ? c != F24 : c >= F24) fast = false;
+                }
+            s->prows_nm[mode] = fast ? z : 2 * z + 1;
         }
     }
 
@@ -1889,6 +1987,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         }
     }
     if (chunks.empty()) chunks.push_back(whole_ctx(s));
+    if (s->prows) macro_batch = s->max_batch;  // plain sweeps between measurements run inside one launch
     loop_live = true;
 
     struct Step {
@@ -1917,13 +2016,14 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
         for (int64_t sid = sweep_id; sid < mb_end;) {
             // how many sweeps until (and including) the next one that needs a reduction or PT
             int64_t batch = 1;
-            if (msc) {
+            if (msc || s->prows) {  // kernels that run several sweeps per launch
                 while (sid + batch - 1 < mb_end - 1) {
                     const int64_t last = sid + batch - 1;
                     const bool rec = last >= cfg->warmup_sweeps;
                     const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
                     const bool ocl = want_oc && last % cfg->overlap_cluster_update_interval == 0;
-                    if (rec || ptl || ocl || want_eq || batch >= s->max_batch) break;
+                    const bool fkl = want_fk && last % cfg->cluster_update_interval == 0;
+                    if (rec || ptl || ocl || fkl || want_eq || batch >= s->max_batch) break;
                     batch++;
                 }
             }
@@ -1959,11 +2059,13 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     if (st != PP_OK) return st;
                 }
                 if (fk_this) {  // after the sweep, before the measurements (mod.rs:457-470)
+                    if (s->prows && (st = prows_sync(s, c.stream, 1)) != PP_OK) return st;  // the cluster kernels work on the int8 view
                     fk_cluster_kernel<<<(unsigned)(c.m.D * c.m.S), FK_THREADS, fk_smem, c.stream>>>(
                         c.m, d_fk_count, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0,
                         fk_smem_sites, d_fk_lab, d_fk_bm);
                     s->launches++;
                     CUDA_TRY(cudaGetLastError());
+                    if (s->prows && (st = prows_sync(s, c.stream, 0)) != PP_OK) return st;
                     if (energy_this) {
                         st = launch_energy(s, c, stp.record);
                         if (st != PP_OK) return st;
@@ -2013,9 +2115,11 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                         else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
                         else msc_houdayer_kernel<0><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
                     } else {
+                        if (s->prows && (st = prows_sync(s, c.stream, 1)) != PP_OK) return st;
                         houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
                             c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,
                             d_fk_lab, d_fk_bm);
+                        if (s->prows && (st = prows_sync(s, c.stream, 0)) != PP_OK) return st;
                     }
                     s->launches++;
                     CUDA_TRY(cudaGetLastError());
@@ -2129,6 +2233,10 @@ extern "C" pp_status pp_get_spins(pp_sim *s, int64_t r, int8_t *out) {
         CUDA_TRY(cudaMemcpy(out, tmp, n, cudaMemcpyDeviceToHost));
         pool_free(s, tmp);
     } else {
+        if (s->prows) {
+            pp_status st = prows_sync(s, s->stream, 1);
+            if (st != PP_OK) return st;
+        }
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         CUDA_TRY(cudaMemcpy(out, m.spins + (size_t)r * n, n, cudaMemcpyDeviceToHost));
     }
@@ -2158,7 +2266,17 @@ extern "C" pp_status pp_set_spins(pp_sim *s, int64_t r, const int8_t *spins) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         pool_free(s, tmp);
     } else {
+        if (s->prows) {  // the int8 view of the other realizations must be current before everything is packed again
+            pp_status st = prows_sync(s, s->stream, 1);
+            if (st != PP_OK) return st;
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+        }
         CUDA_TRY(cudaMemcpy(m.spins + (size_t)r * n, spins, n, cudaMemcpyHostToDevice));
+        if (s->prows) {
+            pp_status st = prows_sync(s, s->stream, 0);
+            if (st != PP_OK) return st;
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+        }
     }
     return PP_OK;
 }

@@ -179,15 +179,17 @@ class SlabIsingSimulation:
         import torch
         import torch.distributed as dist
 
-        from ._core import IsingSimulation, nccl_unique_id
+        from ._core import IsingSimulation, nccl_comm_cached, nccl_unique_id
 
         live = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if live else 0
         self.world = dist.get_world_size(group) if live else 1
         self.first_plane, self.planes = slab_plan(int(lattice_shape[0]), self.world, self.rank)
-        token = broadcast_token(nccl_unique_id, group) if self.world > 1 else None
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        # the engine keeps one communicator per (device, world, rank) for the life of the process: only the first handle of a
+        # world needs the bootstrap token (every rank builds its handles in the same order, so all of them agree on that)
+        token = broadcast_token(nccl_unique_id, group) if self.world > 1 and not nccl_comm_cached(device, self.world, self.rank) else None
         self.sim = IsingSimulation(list(lattice_shape), "ferro", temperatures, 1, None, seed, layout="slab", device=device,
                                    slab_ranks=self.world, slab_rank=self.rank if self.world > 1 else 0, nccl_unique_id=token)
 
@@ -223,16 +225,16 @@ class SystemSplitIsingSimulation:
         import torch
         import torch.distributed as dist
 
-        from ._core import IsingSimulation, nccl_unique_id
+        from ._core import IsingSimulation, nccl_comm_cached, nccl_unique_id
 
         live = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if live else 0
         self.world = dist.get_world_size(group) if live else 1
         R = 1 if n_replicas is None else int(n_replicas)
         self.first_system, self.n_systems = system_plan(R * len(np.asarray(temperatures).reshape(-1)), self.world, self.rank)
-        token = broadcast_token(nccl_unique_id, group) if self.world > 1 else None
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        token = broadcast_token(nccl_unique_id, group) if self.world > 1 and not nccl_comm_cached(device, self.world, self.rank) else None
         self.sim = IsingSimulation(list(lattice_shape), couplings, temperatures, n_replicas, neighbor_offsets, seed, layout="int8",
                                    device=device, system_ranks=self.world, system_rank=self.rank, nccl_unique_id=token)
 

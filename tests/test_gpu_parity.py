@@ -37,7 +37,8 @@ def make_pair(oracle, shape, kind, temps, R, D, offsets=None, layout="int8", see
     colour, _ = pb.colouring(shape, offsets)
     gpu = pb.IsingSimulation(list(shape), J, temps, R, offsets, seed, layout=layout)
     assert gpu.layout == layout
-    mode = oracle.RNG_PHILOX_MSC if layout == "msc" else oracle.RNG_PHILOX
+    # ferromagnets whose rows split into 64-site word pairs are kept as one bit per spin and draw through the packed mapping
+    mode = oracle.RNG_PHILOX_MSC if layout == "msc" else oracle.RNG_PHILOX_PACKED if gpu.rows_packed else oracle.RNG_PHILOX
     cpu = oracle.Sim(shape, J, temps, n_replicas=R, offsets=offsets, seed=seed, rng_mode=mode, colour=colour)
     return gpu, cpu
 
@@ -440,6 +441,63 @@ def test_row_table_kernels_are_bit_exact(oracle, monkeypatch, shape, kind, offse
             assert np.array_equal(rg[k], rc[k]), k
         np.testing.assert_allclose(rg["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(rg["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
+
+
+# ---- ferromagnets with rows of 64 k sites: one bit per spin, a system resident in shared memory per launch (pp_kernels_prows.cuh),
+# packed draw mapping; the small cases switch the one-CTA-per-realization kernel off, which would otherwise take them ----
+PROWS_CASES = [
+    # shape, offsets, temps, R
+    ((4, 64), None, [1.5, 2.27, 3.0, 1e9], 2),             # T = 1e9: a count at 2^24 takes the all-thresholds form
+    ((8, 128), TRI, [3.0, 3.64, 4.2], 2),                   # the geometry of BASELINE config 3 (4 colours, shifted neighbour rows)
+    ((4, 4, 64), None, [4.0, 4.51, 5.0], 2),
+    ((2, 64), None, [2.0, 2.5], 3),                         # two rows: fwd == bwd neighbour row; odd replica count
+    ((4, 2, 2, 64), None, [6.0, 6.7], 2),                   # 4-D: four forward directions
+]
+
+
+@pytest.mark.parametrize("shape,offsets,temps,R", PROWS_CASES)
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+def test_packed_row_kernels_are_bit_exact(oracle, monkeypatch, shape, offsets, temps, R, mode):
+    monkeypatch.setenv("PP_RESIDENT", "0")
+    gpu, cpu = make_pair(oracle, shape, "ferro", temps, R, 1, offsets)
+    assert gpu.rows_packed
+    assert_state_equal(gpu, cpu, 1)
+    seen = []
+    for n_sweeps, interval, schedule in ((1, None, "single_random_edge"), (19, 1, "full_ladder"), (70, 4, "single_random_edge"), (90, None, "full_ladder")):
+        kw = dict(warmup_ratio=0.25, pt_interval=interval, pt_schedule=schedule)
+        rg = gpu.sample(n_sweeps, mode, on_sweep=seen.append, **kw)
+        rc = cpu.sample(n_sweeps, mode, **kw)
+        assert_state_equal(gpu, cpu, 1)
+        assert_results_equal(rg, rc)
+        assert np.array_equal(gpu.get_energies(0), cpu.energies(0))
+    assert len(seen) == 180
+    # operator entry points and a caller-written configuration go through the packed words too
+    rng = np.random.default_rng(4)
+    spins = (2 * rng.integers(0, 2, size=gpu.n_spins * R * len(temps)) - 1).astype(np.int8)
+    gpu.set_spins(spins, 0)
+    assert np.array_equal(gpu.get_spins(0), spins)
+    lat = oracle.Lattice(shape, offsets)
+    z = len(shape) if offsets is None else len(offsets)
+    e_c, m_c = lat.energies_mags(spins.reshape(R * len(temps), -1), np.ones(tuple(shape) + (z,), np.float32))
+    e_g, m_g = gpu.op_energies_mags()
+    assert np.array_equal(e_g[0], e_c) and np.array_equal(m_g[0], m_c)
+    gpu.reset()
+    cpu.reset()
+    assert_state_equal(gpu, cpu, 1)
+
+
+@pytest.mark.parametrize("cluster_mode", ["sw", "wolff"])
+def test_packed_rows_run_cluster_moves_through_the_int8_view(oracle, monkeypatch, cluster_mode):
+    monkeypatch.setenv("PP_RESIDENT", "0")
+    gpu, cpu = make_pair(oracle, (8, 64), "ferro", [2.0, 2.27, 2.6], 2, 1)
+    assert gpu.rows_packed
+    for kw in (dict(cluster_update_interval=1, cluster_mode=cluster_mode, pt_interval=1),
+               dict(cluster_update_interval=3, cluster_mode=cluster_mode, pt_interval=2),
+               dict(overlap_cluster_update_interval=2, overlap_cluster_mode=cluster_mode, pt_interval=1)):
+        rg = gpu.sample(25, "metropolis", **kw)
+        rc = cpu.sample(25, "metropolis", **kw)
+        assert_state_equal(gpu, cpu, 1)
+        assert_results_equal(rg, rc)
 
 
 @pytest.mark.parametrize("schedule", ["single_random_edge", "full_ladder"])
