@@ -962,8 +962,21 @@ static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
     return PP_OK;
 }
 
-static pp_status launch_overlap(pp_sim *s, Ctx &c) {
+// fold_too / *folded: the packed-row overlap kernel also runs the recorded-sweep fold (also when there are no replica pairs)
+static pp_status launch_overlap(pp_sim *s, Ctx &c, bool fold_too = false, bool *folded = nullptr) {
     ModelView m = c.m;
+    if (folded) *folded = false;
+    if (s->prows && s->layout == PP_LAYOUT_INT8 && (m.P > 0 || fold_too)) {
+        const unsigned grid = (unsigned)(m.D * m.T);
+        const int wf = fold_too ? 1 : 0;
+        if (m.z == 2) prows_overlap_kernel<2><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.st, c.dot_spin, c.dot_link, wf);
+        else if (m.z == 3) prows_overlap_kernel<3><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.st, c.dot_spin, c.dot_link, wf);
+        else prows_overlap_kernel<4><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.st, c.dot_spin, c.dot_link, wf);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (folded) *folded = fold_too;
+        return PP_OK;
+    }
     if (m.P == 0) return PP_OK;
     if (s->layout == PP_LAYOUT_MSC && s->msc3d) {
         m.lut = s->d_lut_metro;
@@ -971,12 +984,7 @@ static pp_status launch_overlap(pp_sim *s, Ctx &c) {
     }
     if (s->layout == PP_LAYOUT_MSC)
         msc_overlap_kernel<<<(unsigned)(c.G * m.P * m.T), MSC_BLOCK, 0, c.stream>>>(m, c.dot_spin, c.dot_link);
-    else if (s->prows) {
-        const unsigned grid = (unsigned)(m.D * m.P * m.T);
-        if (m.z == 2) prows_overlap_kernel<2><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.dot_spin, c.dot_link);
-        else if (m.z == 3) prows_overlap_kernel<3><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.dot_spin, c.dot_link);
-        else prows_overlap_kernel<4><<<grid, PROWS_THREADS, 0, c.stream>>>(m, s->rv, s->pv, c.dot_spin, c.dot_link);
-    } else if (s->rows)
+    else if (s->rows)
         rows_overlap_kernel<<<dim3((unsigned)(m.D * m.P * m.T), (unsigned)s->rows_nb), 256, 0, c.stream>>>(m, s->rv, c.dot_spin, c.dot_link,
                                                                                                    s->d_rows_acc, s->d_rows_arrive);
     else
@@ -2072,11 +2080,12 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     }
                 }
                 if ((stp.record || want_eq) && !fused) {
+                    bool folded = false;
                     if (c.m.P > 0 || stp.record) {
-                        st = launch_overlap(s, c);                                     // mod.rs:527-529
+                        st = launch_overlap(s, c, stp.record, &folded);                // mod.rs:527-529
                         if (st != PP_OK) return st;
                     }
-                    if (stp.record) {
+                    if (stp.record && !folded) {
                         fold_kernel<<<blocks_for(c.m.D * c.m.T, 128), 128, 0, c.stream>>>(c.m, c.st, c.m.P > 0);  // mod.rs:543-578
                         s->launches++;
                     }

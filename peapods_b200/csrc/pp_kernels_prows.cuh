@@ -26,6 +26,7 @@
 #pragma once
 #include "pp_device.cuh"
 #include "pp_kernels_rows.cuh"
+#include "pp_kernels_stats.cuh"
 
 namespace pp {
 
@@ -180,41 +181,51 @@ prows_sweep_kernel(ModelView m, RowsView v, PRowsView pv, uint32_t sweep_index, 
         for (int64_t i = tid; i < pv.sys_words / 4; i += PROWS_THREADS) reinterpret_cast<uint4 *>(gw)[i] = reinterpret_cast<const uint4 *>(prows_sm)[i];
 }
 
-// integer overlap dots (overlap.rs:259-281) of the replica pairs: grid = D * P * T CTAs, words straight from global memory / L2
+// integer overlap dots (overlap.rs:259-281) of the replica pairs at one (realization, temperature), words straight from global
+// memory / L2, and — want_fold — the recorded-sweep fold of that (d, t) right behind them (simulation/mod.rs:543-578,
+// statistics/overlap.rs:283-306) by the CTA's first thread: one launch instead of two per recorded sweep.  grid = D * T CTAs.
 template <int Z>
 __global__ void __launch_bounds__(PROWS_THREADS)
-prows_overlap_kernel(ModelView m, RowsView v, PRowsView pv, long long *dot_spin, long long *dot_link) {
+prows_overlap_kernel(ModelView m, RowsView v, PRowsView pv, StatsView st, long long *dot_spin, long long *dot_link, int want_fold) {
     __shared__ long long red_sm[32];
-    const int64_t idx = blockIdx.x;  // (d*P + p)*T + t
-    const int t = (int)(idx % m.T);
-    const int pr = (int)((idx / m.T) % m.P);
-    const int64_t d = idx / ((int64_t)m.T * m.P);
-    const int sa = m.system_ids[d * m.S + (2 * pr) * m.T + t];
-    const int sb = m.system_ids[d * m.S + (2 * pr + 1) * m.T + t];
-    const uint32_t *a = pv.words + (d * m.S + sa) * pv.sys_words;
-    const uint32_t *b = pv.words + (d * m.S + sb) * pv.sys_words;
+    const int64_t d = blockIdx.x / m.T;
+    const int t = (int)(blockIdx.x % m.T);
     const int W = pv.W;
     int dls[Z];
 #pragma unroll
     for (int k = 0; k < Z; k++) dls[k] = v.dl[k];
-    long long neg_q = 0, neg_l = 0;
-    for (uint32_t i = threadIdx.x; i < (uint32_t)pv.sys_words; i += PROWS_THREADS) {
-        const uint32_t r = i / (uint32_t)(2 * W);
-        const int p = (int)((i / (uint32_t)W) & 1u), w = (int)(i % (uint32_t)W);
-        const uint32_t x = a[i] ^ b[i];  // bit set where the replicas differ
-        neg_q += __popc(x);
+    for (int pr = 0; pr < m.P; pr++) {
+        const int sa = m.system_ids[d * m.S + (2 * pr) * m.T + t];
+        const int sb = m.system_ids[d * m.S + (2 * pr + 1) * m.T + t];
+        const uint32_t *a = pv.words + (d * m.S + sa) * pv.sys_words;
+        const uint32_t *b = pv.words + (d * m.S + sb) * pv.sys_words;
+        long long neg_q = 0, neg_l = 0;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)pv.sys_words; i += PROWS_THREADS) {
+            const uint32_t r = i / (uint32_t)(2 * W);
+            const int p = (int)((i / (uint32_t)W) & 1u), w = (int)(i % (uint32_t)W);
+            const uint32_t x = a[i] ^ b[i];  // bit set where the replicas differ
+            neg_q += __popc(x);
 #pragma unroll
-        for (int k = 0; k < Z; k++) {
-            const uint32_t nr = v.nbr_row[((size_t)r * Z + k) * 2];
-            neg_l += __popc(x ^ prows_nbr_word(a, W, nr, p, w, dls[k]) ^ prows_nbr_word(b, W, nr, p, w, dls[k]));
+            for (int k = 0; k < Z; k++) {
+                const uint32_t nr = v.nbr_row[((size_t)r * Z + k) * 2];
+                neg_l += __popc(x ^ prows_nbr_word(a, W, nr, p, w, dls[k]) ^ prows_nbr_word(b, W, nr, p, w, dls[k]));
+            }
+        }
+        const long long tq = block_sum<long long>(neg_q, red_sm);
+        const long long tl = block_sum<long long>(neg_l, red_sm);
+        if (threadIdx.x == 0) {
+            const int64_t idx = (d * m.P + pr) * m.T + t;
+            dot_spin[idx] = m.N - 2 * tq;
+            dot_link[idx] = (long long)Z * m.N - 2 * tl;
         }
     }
-    const long long tq = block_sum<long long>(neg_q, red_sm);
-    const long long tl = block_sum<long long>(neg_l, red_sm);
-    if (threadIdx.x == 0) {
-        dot_spin[idx] = m.N - 2 * tq;
-        dot_link[idx] = (long long)Z * m.N - 2 * tl;
-    }
+    if (want_fold && threadIdx.x == 0)  // the dots above were written by this thread: program order makes them visible
+        fold_one<0, true>(
+            m, st, d, t, m.P > 0,
+            [&](int r) { return m.mags[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
+            [&](int r) { return m.energies[d * m.S + m.system_ids[d * m.S + r * m.T + t]]; },
+            [&](int p) { return dot_spin[(d * m.P + p) * m.T + t]; },
+            [&](int p) { return dot_link[(d * m.P + p) * m.T + t]; });
 }
 
 // int8 [D][S][N] (+-1, system-major: the layout every other kernel and the API use) <-> packed words; dir 0: pack, 1: unpack.
