@@ -408,7 +408,8 @@ def bench_c3_split(ranks: Ranks):
     del sim
     return {"workload": f"C3: 2-D triangular ferromagnet 256x256, Gibbs, 64 temps around 4/ln3, 2 replicas; the 128 systems split over {world} GPU(s)",
             "value": value, "unit": UNIT, "scaling": "strong", "n_gpus": world, "sweeps": n_sweeps, "ms": best,
-            "alg_bytes_per_attempt": 2.0, "hbm_roofline_frac": value * 2.0 / (world * peak),
+            "alg_bytes_per_attempt": 0.25, "hbm_roofline_frac": value * 0.25 / (world * peak),
+            "layout": "int8 API, one bit per spin in the engine (packed rows)",
             "collectives_per_recorded_sweep": 0 if world == 1 else 3,
             "rank_parity": "PASS" if int(flag.item()) else "FAIL",
             "rank_parity_note": "split run == unsplit run on one GPU, bit for bit (spins, statistics, exchange counters), 24 Gibbs sweeps with "
@@ -432,7 +433,9 @@ def bench_small_configs():
         attempts = float(model.n_spins) * model.n_temps * model.n_replicas * model.n_disorder * n_sweeps
         v = attempts / best / 1e6
         out[key] = {"workload": label, "value": v, "unit": UNIT, "sweeps": n_sweeps, "ms": best, "gpu_launches": launches,
-                    "layout": model._sim.layout, "alg_bytes_per_attempt": b_alg, "hbm_roofline_frac": v * b_alg / peak}
+                    "layout": model._sim.layout + (" (one bit per spin: packed rows, system resident in shared memory)" if model._sim.rows_packed else ""),
+                    "alg_bytes_per_attempt": b_alg if not model._sim.rows_packed else 0.25,
+                    "hbm_roofline_frac": v * (b_alg if not model._sim.rows_packed else 0.25) / peak}
 
     m = pb.Ising((32, 32), "ferro", np.linspace(1.5, 3.0, 16), n_replicas=2, seed=SEED)
     run("c1", "C1: 2-D Ising ferromagnet 32x32, Metropolis + PT every sweep, 16 temps 1.5-3.0, 2 replicas, 5000 sweeps (README quickstart)",
