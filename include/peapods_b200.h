@@ -205,6 +205,24 @@ pp_status pp_op_energies_mags(pp_sim *sim, float *energies /* [D][S] */, int64_t
 pp_status pp_op_overlap(pp_sim *sim, int64_t *dot_spin /* [D][P][T] */, int64_t *dot_link /* [D][P][T] */);
 pp_status pp_op_pt(pp_sim *sim, int32_t pt_schedule, uint32_t pt_event);
 
+/* The same operators with the reference's HOST-SLICE signatures: one realization (model->n_disorder = 1), the
+ * slices go to the device, one kernel runs, the result comes back; a temporary handle lives for the call.
+ *   pp_slice_sweep          <- metropolis_sweep / gibbs_sweep(lattice, spins, couplings, temperatures, system_ids, rngs, ..)
+ *                              spin-sim/src/mcmc/sweep.rs:220-229, 262-270 (draws: RNG-SPEC with model->seed and sweep_index)
+ *   pp_slice_energies_mags  <- compute_energies_and_magnetizations_into(lattice, spins, couplings, energies, mags)
+ *                              spin-sim/src/spins/energy.rs:59-65
+ *   pp_slice_overlap        <- OverlapAccum::collect(lattice, spins, system_ids, ..)   spin-sim/src/statistics/overlap.rs:251
+ *   pp_slice_pt             <- parallel_tempering(_full_ladder)(energies, temperatures, system_ids, n_spins, rng, ..)
+ *                              spin-sim/src/mcmc/tempering.rs:20-27, 45-53 */
+pp_status pp_slice_sweep(const pp_model_desc *model, int32_t sweep_mode, uint32_t sweep_index, int32_t exact_log,
+                         int8_t *spins /* [S*N] system-major, in/out */, const int64_t *system_ids /* [S] slot -> system, or NULL */);
+pp_status pp_slice_energies_mags(const pp_model_desc *model, const int8_t *spins /* [S*N] */, float *energies /* [S] */,
+                                 int64_t *mags /* [S] or NULL */);
+pp_status pp_slice_overlap(const pp_model_desc *model, const int8_t *spins /* [S*N] */, const int64_t *system_ids /* [S] or NULL */,
+                           int64_t *dot_spin /* [P][T] */, int64_t *dot_link /* [P][T] */);
+pp_status pp_slice_pt(const pp_model_desc *model, int32_t pt_schedule, uint32_t pt_event, int32_t first_parity,
+                      const float *energies /* [S] by system */, int64_t *system_ids /* [S] in/out */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,10 @@ SIGNATURES = {
     "pp_op_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32]),
     "pp_op_energies_mags": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pp_op_overlap": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_slice_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pp_slice_energies_mags": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_slice_overlap": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pp_slice_pt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pp_op_pt": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32]),
 }
 

@@ -2395,3 +2395,61 @@ extern "C" pp_status pp_op_pt(pp_sim *s, int32_t pt_schedule, uint32_t pt_event)
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return PP_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// The reference's operator signatures on HOST slices (SURVEY.md 8b "Granularity"): one realization, H2D -> kernel -> D2H around a
+// temporary handle.  Unit-level parity only: a caller that sweeps repeatedly keeps a handle (pp_create / pp_sample).
+struct SliceHandle {
+    pp_sim *sim = nullptr;
+    ~SliceHandle() { if (sim) free_sim(sim); }
+};
+
+static pp_status slice_open(const pp_model_desc *model, const int8_t *spins, const int64_t *system_ids, SliceHandle &h) {
+    if (!model) return fail(PP_ERR_INVALID, "model is NULL");
+    if (model->n_disorder != 1) return fail(PP_ERR_INVALID, "slice entry points take one realization (n_disorder = 1)");
+    pp_status st = pp_create(model, &h.sim);
+    if (st != PP_OK) return st;
+    if (system_ids && (st = pp_set_system_ids(h.sim, 0, system_ids)) != PP_OK) return st;
+    if (spins && (st = pp_set_spins(h.sim, 0, spins)) != PP_OK) return st;
+    return PP_OK;
+}
+
+extern "C" pp_status pp_slice_sweep(const pp_model_desc *model, int32_t sweep_mode, uint32_t sweep_index, int32_t exact_log, int8_t *spins,
+                                    const int64_t *system_ids) {
+    if (!spins) return fail(PP_ERR_INVALID, "spins is NULL");
+    SliceHandle h;
+    pp_status st = slice_open(model, spins, system_ids, h);
+    if (st != PP_OK) return st;
+    if ((st = pp_op_sweep(h.sim, sweep_mode, sweep_index, exact_log)) != PP_OK) return st;
+    return pp_get_spins(h.sim, 0, spins);
+}
+
+extern "C" pp_status pp_slice_energies_mags(const pp_model_desc *model, const int8_t *spins, float *energies, int64_t *mags) {
+    if (!spins) return fail(PP_ERR_INVALID, "spins is NULL");
+    SliceHandle h;
+    pp_status st = slice_open(model, spins, nullptr, h);
+    if (st != PP_OK) return st;
+    return pp_op_energies_mags(h.sim, energies, mags);
+}
+
+extern "C" pp_status pp_slice_overlap(const pp_model_desc *model, const int8_t *spins, const int64_t *system_ids, int64_t *dot_spin,
+                                      int64_t *dot_link) {
+    if (!spins) return fail(PP_ERR_INVALID, "spins is NULL");
+    SliceHandle h;
+    pp_status st = slice_open(model, spins, system_ids, h);
+    if (st != PP_OK) return st;
+    return pp_op_overlap(h.sim, dot_spin, dot_link);
+}
+
+extern "C" pp_status pp_slice_pt(const pp_model_desc *model, int32_t pt_schedule, uint32_t pt_event, int32_t first_parity, const float *energies,
+                                 int64_t *system_ids) {
+    if (!energies || !system_ids) return fail(PP_ERR_INVALID, "energies/system_ids is NULL");
+    SliceHandle h;
+    pp_status st = slice_open(model, nullptr, system_ids, h);
+    if (st != PP_OK) return st;
+    pp_sim *s = h.sim;
+    CUDA_TRY(cudaMemcpy(s->d_energies, energies, sizeof(float) * (size_t)s->mv.S, cudaMemcpyHostToDevice));
+    s->next_parity = first_parity ? 1 : 0;
+    if ((st = pp_op_pt(s, pt_schedule, pt_event)) != PP_OK) return st;
+    return pp_get_system_ids(s, 0, system_ids);
+}

@@ -74,8 +74,23 @@ class Ising:
         else:
             coup = make_couplings(couplings, self.lattice_shape, self.n_neighbors, n_disorder, coupling_seq)
         self.couplings = coup
+        self._neighbor_offsets = neighbor_offsets
+        self._layout_request, self._device, self._engine_kwargs = layout, device, dict(engine_kwargs)
         self._sim = IsingSimulation(list(lattice_shape), coup, self.temperatures, n_replicas, neighbor_offsets,
                                     self._constructor_dynamics_seed, layout=layout, device=device, **engine_kwargs)
+
+    def _fall_back_to_int8(self):
+        """The multispin layout (chosen by ``layout="auto"`` for >= 32 +-J realizations) has no cluster labels per lane, so
+        Swendsen-Wang / Wolff updates and SW-mode Houdayer moves run on the int8 layout only.  A model on the automatic layout
+        that asks for them is moved there: same configurations and system ids, a fresh handle (its sweep / exchange counters
+        start again, and its draws are the int8 layout's per-realization streams)."""
+        old = self._sim
+        new = IsingSimulation(list(self.lattice_shape), self.couplings, self.temperatures, self.n_replicas, self._neighbor_offsets,
+                              self._constructor_dynamics_seed, layout="int8", device=self._device, **self._engine_kwargs)
+        for d in range(self.n_disorder):
+            new.set_system_ids(old.get_system_ids(d), d)
+            new.set_spins(old.get_spins(d), d)
+        self._sim = new
 
     def reset(self, seed=None):
         """Replay the constructor's dynamics, or a one-off seeded reset (spin_models.py:138-144)."""
@@ -104,6 +119,11 @@ class Ising:
             raise ValueError("overlap_cluster_action='observe' requires overlap_cluster_update_interval")
 
         oci = overlap_cluster_update_interval
+        if (self._layout_request == "auto" and self._sim.layout == "msc"
+                and (cluster_update_interval is not None or (oci is not None and overlap_cluster_mode == "sw"))
+                and cluster_action == "update" and overlap_cluster_action == "update" and not collect_cluster_stats
+                and overlap_cluster_build_mode.strip() in ("houdayer", "houd2") and snapshot_interval is None):
+            self._fall_back_to_int8()
         result = self._sim.sample(
             n_sweeps, sweep_mode,
             cluster_update_interval=cluster_update_interval,

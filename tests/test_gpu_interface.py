@@ -157,3 +157,29 @@ def test_on_sweep_callback_counts_every_sweep():  # simulation/mod.rs:409
     seen = []
     sim.sample(37, "metropolis", pt_interval=2, on_sweep=seen.append)
     assert seen == list(range(37))
+
+
+def test_cluster_moves_on_an_automatic_multispin_model_fall_back_to_int8():
+    """Round-1 review: FK updates / SW-mode Houdayer moves need cluster labels per lane, which the multispin layout does not have.
+    A model built with the automatic layout is moved to int8 (configurations and system ids carried over) instead of raising;
+    an explicit layout="msc" still raises."""
+    import peapods_b200 as pb
+
+    temps = np.linspace(0.9, 1.6, 4)
+    model = pb.Ising((4, 4, 8), couplings="bimodal", temperatures=temps, n_replicas=2, n_disorder=32, seed=3)
+    assert model._sim.layout == "msc"
+    model.sample(20, pt_interval=1)
+    before = [model._sim.get_spins(d).copy() for d in (0, 31)]
+    ids = model._sim.get_system_ids(31).copy()
+    model._fall_back_to_int8()                                                       # what sample() does on such a request
+    assert model._sim.layout == "int8"
+    assert all(np.array_equal(model._sim.get_spins(d), b) for d, b in zip((0, 31), before))   # configurations carried over
+    assert np.array_equal(model._sim.get_system_ids(31), ids)
+    fresh = pb.Ising((4, 4, 8), couplings="bimodal", temperatures=temps, n_replicas=2, n_disorder=32, seed=3)
+    fresh.sample(10, cluster_update_interval=1, cluster_mode="sw", pt_interval=1)   # the automatic path: no error, int8 afterwards
+    assert fresh._sim.layout == "int8" and np.all(np.isfinite(fresh.binder_cumulant))
+    res = model.sample(30, pt_interval=1, overlap_cluster_update_interval=1, overlap_cluster_mode="sw")
+    assert np.all(np.isfinite(res["energies"])) and model.sg_binder.shape == (4,)
+    explicit = pb.Ising((4, 4, 8), couplings="bimodal", temperatures=temps, n_replicas=2, n_disorder=32, seed=3, layout="msc")
+    with pytest.raises(ValueError, match="not implemented on the GPU sweep path"):
+        explicit.sample(4, cluster_update_interval=1)

@@ -935,3 +935,53 @@ def test_generic_multispin_counters_hold_a_large_lattice():
         q = s[0] * s[1]
         assert ds[d, 0, 0] == int(q.sum())
         assert dl[d, 0, 0] == int((q * np.roll(q, -1, axis=0)).sum() + (q * np.roll(q, -1, axis=1)).sum())
+
+
+def test_slice_signature_operators_match_the_oracle(oracle):
+    """SURVEY 8b "Granularity": the reference's operator functions on HOST slices (peapods_b200.ops over pp_slice_*): sweep,
+    energies + magnetisations, overlap dots against the oracle's operators; exchange events against the handle-based operator."""
+    import peapods_b200 as pb
+    from peapods_b200 import ops
+
+    shape, temps, R = (6, 6, 6), np.asarray([0.9, 1.2, 1.5], np.float32), 4
+    T, S = len(temps), R * len(temps)
+    lat = oracle.Lattice(shape)
+    N = lat.n_spins
+    colour = pb.colouring(shape)[0]
+    rng = np.random.default_rng(9)
+    ids = np.concatenate([r * T + rng.permutation(T) for r in range(R)]).astype(np.int64)
+    for kind in ("bimodal", "gaussian"):
+        J = np.asarray(couplings(kind, shape, 3, 1, 3), np.float32).reshape(tuple(shape) + (3,))
+        spins = (2 * rng.integers(0, 2, size=(S, N)) - 1).astype(np.int8)
+        e_c, m_c = lat.energies_mags(spins, J)
+        e_g, m_g = ops.compute_energies_and_magnetizations(shape, spins, J, S)
+        assert np.array_equal(m_g, m_c)
+        if kind == "gaussian":
+            np.testing.assert_allclose(e_g, e_c, rtol=1e-5, atol=1e-6)
+        else:
+            assert np.array_equal(e_g, e_c)
+        ds, dl = ops.overlap_dots(shape, spins, temps, ids, n_replicas=R)
+        for p in range(R // 2):
+            for t in range(T):
+                assert (ds[p, t], dl[p, t]) == lat.overlap_dots(spins[ids[(2 * p) * T + t]], spins[ids[(2 * p + 1) * T + t]])
+        for fn, code in ((ops.metropolis_sweep, oracle.SWEEP_METROPOLIS), (ops.gibbs_sweep, oracle.SWEEP_GIBBS)):
+            mine, ref = spins.copy(), spins.copy()
+            fn(shape, mine, J, temps, ids, n_replicas=R, seed=1234, sweep_index=77)
+            lat.sweep_philox(ref, J, np.tile(temps, R), ids, colour, oracle.lib().orc_realization_seed(1234, 0), 77, code, use_lookup=True)
+            assert np.array_equal(mine, ref), (kind, code)
+    # exchange events: the slice form equals the handle form on the same energies
+    J = np.asarray(couplings("bimodal", shape, 3, 1, 3), np.float32).reshape(tuple(shape) + (3,))
+    spins = (2 * rng.integers(0, 2, size=(S, N)) - 1).astype(np.int8)
+    e_g, _ = ops.compute_energies_and_magnetizations(shape, spins, J, S)
+    for schedule, fn in (("single_random_edge", ops.parallel_tempering), ("full_ladder", ops.parallel_tempering_full_ladder)):
+        h = pb.IsingSimulation(list(shape), J, temps, R, None, 1234, layout="int8")
+        h.set_system_ids(ids, 0)
+        h.set_spins(spins, 0)
+        h.op_energies_mags()
+        cur = ids.copy()
+        for event in range(6):
+            h.op_pt(schedule, event)
+            kw = dict(first_parity=event % 2) if schedule == "full_ladder" else {}
+            cur = fn(shape, e_g, temps, cur, n_replicas=R, seed=1234, pt_event=event, **kw)
+            assert np.array_equal(cur, h.get_system_ids(0)), (schedule, event)
+        assert sorted(cur.tolist()) == list(range(S)) and not np.array_equal(cur, ids)
