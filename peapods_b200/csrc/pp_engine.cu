@@ -239,6 +239,8 @@ struct pp_sim {
     // ferromagnets with one bit per spin (pp_kernels_prows.cuh): the packed words are the state, `d_spins` is an int8 scratch view
     // that the API and the int8-only kernels (cluster moves) see through prows_sync(): unpack before, pack after
     bool prows = false;
+    bool resident_packed = false;                      // small ferromagnetic realizations: prows_resident_kernel instead of rows_resident_kernel
+    size_t resident_packed_smem = 0;
     PRowsView pv{};
     int prows_nm[2] = {0, 0};                          // thresholds compared per site: [metropolis, gibbs]
     long long *d_rows_acc = nullptr;                   // [2 * max(D*S, D*P*T)] split-reduction scratch (kept zero between launches)
@@ -406,7 +408,7 @@ extern "C" pp_status pp_debug_last_timing(const pp_sim *sim, pp_timing *out) {
 }
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
-extern "C" int32_t pp_rows_packed(const pp_sim *sim) { return sim && sim->prows ? 1 : 0; }
+extern "C" int32_t pp_rows_packed(const pp_sim *sim) { return sim && (sim->prows || sim->rv.packed_draws) ? 1 : 0; }
 extern "C" int64_t pp_local_spin_count(const pp_sim *sim) {
     if (!sim) return 0;
     return sim->slab ? sim->slab->local_planes() * sim->slab->plane : sim->mv.N;
@@ -1402,6 +1404,15 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 s->resident = m.coupling_class != COUP_F32 && ((size_t)m.S * N) % 16 == 0 && need <= 200 * 1024 &&
                               (z == 2 || z == 3);
                 if (const char *e = getenv("PP_RESIDENT")) s->resident = s->resident && atoi(e) != 0;
+                // ferromagnets whose rows are whole 32-site words: the bit-packed form of the same kernel (pp_kernels_prows.cuh);
+                // the handle then draws in the packed mapping whichever kernel runs a sweep
+                bool dl1 = true;
+                for (int k = 0; k < z; k++) dl1 = dl1 && std::abs(rp.dl[(size_t)k]) <= 1;
+                s->resident_packed_smem = prows_resident_smem(m.S, m.T, m.P, z, N);
+                s->resident_packed = s->resident && m.coupling_class == COUP_FERRO && rp.L % 32 == 0 && dl1 && (z == 2 || z == 3) &&
+                                     s->resident_packed_smem <= 200 * 1024;
+                if (const char *e = getenv("PP_RESIDENT_PACKED")) s->resident_packed = s->resident_packed && atoi(e) != 0;
+                v.packed_draws = s->resident_packed ? 1 : 0;
             }
             // ferromagnets with one bit per spin, a system resident in one CTA's shared memory (pp_kernels_prows.cuh): rows that
             // split into whole 64-site word pairs, offsets that move by at most one site along the rows, 2-4 forward directions
@@ -1426,7 +1437,8 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             return fail(PP_ERR_UNSUPPORTED, "system_ranks > 1 needs the row-table int8 kernels (a linear colouring that alternates along the "
                                             "rows, last extent a multiple of 8)");
         }
-        s->resident = false;  // one CTA per realization would hold every system
+        s->resident = false;  // one CTA per realization would hold every system (the draw mapping of the handle stays what it was)
+        s->resident_packed = false;
         s->sys_ranks = sys_ranks;
         s->sys_rank = desc->system_rank;
         const int per = m.S / sys_ranks;
@@ -1470,7 +1482,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
 
     // packed-row kernel: thresholds compared per site -- z' when the counts for unsat >= z' are 2^24 (energy change <= 0 always
     // accepted) and the others are below 2^24, else all 2z' + 1
-    if (s->prows) {
+    if (s->prows || s->resident_packed) {
         std::vector<uint32_t> lut((size_t)m.T * (4 * z + 1));
         for (int mode = 0; mode < 2; mode++) {
             pp_metropolis_lookup(s->temps.data(), m.T, z, mode, lut.data());
@@ -1680,8 +1692,18 @@ static pp_status run_rows_resident(pp_sim *s, Ctx &c, const pp_sample_cfg *cfg, 
     rows_resident_kernel<C_, Z_, G_><<<(unsigned)mk.D, RESIDENT_THREADS, s->resident_smem, c.stream>>>(mk, v, c.st, c.pt, a);   \
     } while (0)
 #define PP_RES2(C_, Z_) do { if (gibbs) PP_RES3(C_, Z_, true); else PP_RES3(C_, Z_, false); } while (0)
-        if (mk.coupling_class == COUP_FERRO) { if (mk.z == 2) PP_RES2(COUP_FERRO, 2); else PP_RES2(COUP_FERRO, 3); }
+#define PP_PRES(Z_, NM_)                                                                                                           \
+    do {                                                                                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(prows_resident_kernel<Z_, NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->resident_packed_smem)); \
+    prows_resident_kernel<Z_, NM_><<<(unsigned)mk.D, PRES_THREADS, s->resident_packed_smem, c.stream>>>(mk, v, c.st, c.pt, a);      \
+    } while (0)
+        if (s->resident_packed) {
+            const int nm = s->prows_nm[gibbs ? 1 : 0];
+            if (mk.z == 2) { if (nm == 2) PP_PRES(2, 2); else PP_PRES(2, 5); }
+            else { if (nm == 3) PP_PRES(3, 3); else PP_PRES(3, 7); }
+        } else if (mk.coupling_class == COUP_FERRO) { if (mk.z == 2) PP_RES2(COUP_FERRO, 2); else PP_RES2(COUP_FERRO, 3); }
         else { if (mk.z == 2) PP_RES2(COUP_UNIT, 2); else PP_RES2(COUP_UNIT, 3); }
+#undef PP_PRES
 #undef PP_RES2
 #undef PP_RES3
         s->launches++;

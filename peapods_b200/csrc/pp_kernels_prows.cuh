@@ -255,4 +255,310 @@ __global__ void __launch_bounds__(PROWS_THREADS) prows_convert_kernel(ModelView 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Small ferromagnetic realizations (README quickstart sizes: 32 systems of 32 x 32 sites): the bit-packed form of
+// rows_resident_kernel.  ONE CTA owns realization d for up to 256 sweeps per launch and runs the whole per-sweep sequence of
+// simulation/mod.rs:405-432, 486-509, 527-529, 748-796 in shared memory; the global state stays int8 (every other kernel and the
+// API keep working on it), the CTA packs it on the way in and unpacks it on the way out.
+//
+// Packing here is by FULL ROWS: word w of row r of a system = its sites x = 32 w .. 32 w + 31 (last extent a multiple of 32), so
+// the neighbour along the row is a one-bit funnel shift with the adjacent word (a rotate when the row is one word), the neighbours
+// in the other directions are the same word of row nbr_row[r][k] (shifted too when the offset's last component is +-1), and a
+// colour pass updates the sites under the row's parity mask 0x5555... << p.  The 16 active sites of a word are 16 consecutive
+// ranks of their colour class = half a block of the packed draw mapping: three Philox calls.  Energies and overlap dots are
+// popcounts over the packed words.  Measured at the quickstart (profiles/r2_summary.md): the int8 resident kernel issues 90
+// instructions per attempt (92 k warp instructions per sweep on its one SM: 19.6 us per sweep); this form runs a sweep in 8.5 us
+// (pure sweeps 4.9, exchange + 2.1, measurements + 3.0).  Prefetching the exchange's log-table lines under the colour passes
+// and 1024 threads per CTA were measured: no gain / 7 % slower.
+constexpr int PRES_THREADS = 512;  // measured at the quickstart: 512 threads 42.3 ms per 5000 sweeps, 1024 threads 45.5 ms
+
+template <int Z, int NM>
+__global__ void __launch_bounds__(PRES_THREADS)
+prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, ResidentArgs a) {
+    extern __shared__ __align__(16) uint32_t res_sm[];
+    constexpr int Z2 = 2 * Z, NTH = 2 * Z + 1, RESIDENT_THREADS = PRES_THREADS;  // (shadows the int8 kernel's block size below)
+    const int tid = threadIdx.x;
+    const int64_t dg = blockIdx.x;
+    const int S = mg.S, T = mg.T, P = mg.P, n_edges = T > 1 ? T - 1 : 1, L = vg.L, W = L / 32;
+    const int n_rows = (int)vg.n_rows, sysw = n_rows * W;  // words per system
+    uint32_t *thr_sm = res_sm;  // [T][NTH] acceptance counts (NM == Z: already shifted left by 8 for the compared ones)
+    unsigned char *sc = reinterpret_cast<unsigned char *>(res_sm + ((T * NTH + 3) & ~3));
+    double *sums_sm = reinterpret_cast<double *>(sc);
+    long long *mag_sm = reinterpret_cast<long long *>(sums_sm + 11 * T);
+    long long *dsp_sm = mag_sm + S, *dlk_sm = dsp_sm + P * T;
+    unsigned long long *ea_sm = reinterpret_cast<unsigned long long *>(dlk_sm + P * T), *eacc_sm = ea_sm + n_edges, *rt_sm = eacc_sm + n_edges;
+    float *en_sm = reinterpret_cast<float *>(rt_sm + S), *temps_sm = en_sm + S;
+    int32_t *sid_sm = reinterpret_cast<int32_t *>(temps_sm + T);
+    uint8_t *trip_sm = reinterpret_cast<uint8_t *>(sid_sm + S);
+    uint32_t *pw = reinterpret_cast<uint32_t *>(sc + resident_scalar_bytes(S, T, P));  // [S][rows][W] by system
+    int *cnt_sm = reinterpret_cast<int *>(pw + (size_t)S * sysw);                       // [2 * max(S, P * T)] integer partial sums
+    int8_t *g_spins = mg.spins + dg * S * mg.N;
+    const int64_t bins = mg.N + 1;
+    for (int i = tid; i < T * NTH; i += RESIDENT_THREADS) {
+        const int u = i % NTH;
+        const uint32_t c = mg.lut[(i / NTH) * (4 * Z + 1) + 2 * u];  // sweep.rs:162-166, index ec + 2z' = 2 * unsat
+        thr_sm[i] = (NM == Z && u < Z) ? c << 8 : c;
+    }
+    for (int i = tid; i < 11 * T; i += RESIDENT_THREADS) sums_sm[i] = stg.sums[dg * 11 * T + i];
+    for (int i = tid; i < S; i += RESIDENT_THREADS) {
+        mag_sm[i] = mg.mags[dg * S + i];
+        en_sm[i] = mg.energies[dg * S + i];
+        sid_sm[i] = mg.system_ids[dg * S + i];
+        rt_sm[i] = ptg.round_trips[dg * S + i];
+        trip_sm[i] = ptg.trip_state[dg * S + i];
+    }
+    for (int i = tid; i < P * T; i += RESIDENT_THREADS) {
+        dsp_sm[i] = a.dot_spin[dg * P * T + i];
+        dlk_sm[i] = a.dot_link[dg * P * T + i];
+    }
+    for (int i = tid; i < T - 1; i += RESIDENT_THREADS) {
+        ea_sm[i] = ptg.edge_attempts[dg * (T - 1) + i];
+        eacc_sm[i] = ptg.edge_acceptances[dg * (T - 1) + i];
+    }
+    for (int i = tid; i < T; i += RESIDENT_THREADS) temps_sm[i] = mg.temps[i];
+    for (int i = tid; i < S * sysw; i += RESIDENT_THREADS) {  // pack: 32 consecutive sites -> one word (bit = 1: spin -1)
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_spins + (int64_t)i * 32);
+        uint32_t word = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint4 q4 = src[h];
+            const uint32_t part[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t sg = part[j] & 0x80808080u;  // the sign bits of four int8 spins
+                word |= (((sg >> 7) & 1u) | ((sg >> 14) & 2u) | ((sg >> 21) & 4u) | ((sg >> 28) & 8u)) << (16 * h + 4 * j);
+            }
+        }
+        pw[i] = word;
+    }
+    ModelView m = mg;
+    m.D = 1;
+    m.sample_offset = mg.sample_offset + dg;  // seeds stay those of the global realization index
+    m.system_ids = sid_sm;
+    m.energies = en_sm;
+    m.mags = mag_sm;
+    m.temps = temps_sm;
+    StatsView st = stg;
+    st.sums = sums_sm;
+    if (stg.hist) {
+        st.hist = stg.hist + dg * T * bins;
+        st.ql_at_q = stg.ql_at_q + dg * T * bins;
+        st.ql2_at_q = stg.ql2_at_q + dg * T * bins;
+    }
+    st.dot_spin = dsp_sm;
+    st.dot_link = dlk_sm;
+    PtView pt = ptg;
+    pt.edge_attempts = ea_sm;
+    pt.edge_acceptances = eacc_sm;
+    pt.round_trips = rt_sm;
+    pt.trip_state = trip_sm;
+    const uint64_t key = vg.keys[dg];
+    const PhiloxKeys ks = philox_keys((uint32_t)key, (uint32_t)(key >> 32));
+    int dls[Z];
+#pragma unroll
+    for (int k = 0; k < Z; k++) dls[k] = vg.dl[k];
+    // word w of row nr of the system at `sys`, as seen by the sites of word w after moving `sh` sites along the row
+    auto nbr_word = [&](const uint32_t *sys, const uint32_t nr, const int w, const int sh) {
+        const uint32_t *row = sys + (size_t)nr * W;
+        const uint32_t c = row[w];
+        if (sh == 0) return c;
+        if (sh > 0) return (c >> 1) | (row[w + 1 == W ? 0 : w + 1] << 31);
+        return (c << 1) | (row[w ? w - 1 : W - 1] >> 31);
+    };
+    __syncthreads();
+    uint32_t pt_event = a.pt_event0;
+    int parity = a.parity0;
+    const int half_l = L / 2;
+    for (int sw = 0; sw < a.n_sweeps; sw++) {
+        const int64_t sid = a.sweep_id0 + sw;
+        const uint32_t sweep_index = a.sweep_counter0 + (uint32_t)sw;
+        for (int colour = 0; colour < m.n_colours; colour++) {
+            const int cls = colour % vg.m_half;
+            const uint32_t row0 = vg.class_start[cls], per_sys = (vg.class_start[cls + 1] - row0) * (uint32_t)W;
+            const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
+            for (uint32_t it = tid; it < (uint32_t)S * per_sys; it += RESIDENT_THREADS) {
+                const int slot = (int)(it / per_sys);
+                const uint32_t rem = it - (uint32_t)slot * per_sys, ri = rem / (uint32_t)W;
+                const int w = (int)(rem - ri * (uint32_t)W);
+                const uint32_t r = vg.class_rows[row0 + ri];
+                const int p = (int)vg.row_a[r] == colour ? 0 : 1;  // parity of the row's sites of this colour
+                const int sysl = sid_sm[slot];                        // parallel.rs:27-33
+                const uint32_t *thr = thr_sm + (slot % T) * NTH;      // realization.rs:166
+                uint32_t *sys = pw + (size_t)sysl * sysw;
+                const uint32_t C = sys[(size_t)r * W + w];
+                uint32_t b[Z2];
+#pragma unroll
+                for (int k = 0; k < Z; k++) {
+                    b[2 * k] = C ^ nbr_word(sys, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]);
+                    b[2 * k + 1] = C ^ nbr_word(sys, vg.nbr_row[((size_t)r * Z + k) * 2 + 1], w, -dls[k]);
+                }
+                uint32_t un[4];
+                prows_count<Z2>(b, un);
+                uint32_t Tm[NM], M[NM];
+#pragma unroll
+                for (int u = 0; u < NM; u++) { Tm[u] = thr[u]; M[u] = 0u; }
+                // the word's 16 sites of this colour are the ranks base .. base + 15: half h of block q of the packed mapping
+                const uint32_t base = vg.row_ord[r] * (uint32_t)half_l + 16u * (uint32_t)w;
+                const uint32_t q = base >> 5, h = (base >> 4) & 1u;
+                uint32_t wd[12];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const u32x4 o = philox4x32_k(q, sweep_index, (uint32_t)sysl, tagc | ((3u * h + (uint32_t)c) << 8), ks);
+                    wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t A = wd[3 * g], B = wd[3 * g + 1], Cw = wd[3 * g + 2];
+                    const uint32_t y3 = __byte_perm(__byte_perm(Cw, B, 0x0400), A, 0x4210);
+                    const uint32_t ys[4] = {A, B, Cw, y3};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t bit = 1u << (2 * (4 * g + j));  // site x = 2 (4 g + j) + p: shifted by p below
+                        const uint32_t y = NM == Z ? ys[j] : ys[j] >> 8;
+#pragma unroll
+                        for (int u = 0; u < NM; u++)
+                            if (y < Tm[u]) M[u] |= bit;
+                    }
+                }
+                uint32_t flip = 0u;
+#pragma unroll
+                for (int u = 0; u <= Z2; u++) {
+                    const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
+                    flip |= u < NM ? (eq & (M[u] << p)) : eq;
+                }
+                sys[(size_t)r * W + w] = C ^ (flip & (0x55555555u << p));
+            }
+            __syncthreads();
+        }
+        const bool record = sid >= a.warmup_sweeps;
+        const bool pt_this = a.pt_interval > 0 && sid % a.pt_interval == 0;
+        if (record || pt_this) {  // mod.rs:486-509; energy.rs:99-108: every bond once through its forward direction
+            for (int i = tid; i < 2 * S; i += RESIDENT_THREADS) cnt_sm[i] = 0;
+            __syncthreads();
+            for (int i0 = (tid & ~31); i0 < S * sysw; i0 += RESIDENT_THREADS) {  // whole warps: the sums of a warp that sits
+                const int i = i0 + (tid & 31);                                   // inside one system meet in one reduction
+                const bool live = i < S * sysw;
+                const int sysl = live ? i / sysw : -1;
+                int unsat = 0, dn = 0;
+                if (live) {
+                    const int rem = i - sysl * sysw, r = rem / W, w = rem - r * W;
+                    const uint32_t *sys = pw + (size_t)sysl * sysw;
+                    const uint32_t C = sys[rem];
+#pragma unroll
+                    for (int k = 0; k < Z; k++) unsat += __popc(C ^ nbr_word(sys, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]));
+                    dn = __popc(C);
+                }
+                if (__all_sync(0xFFFFFFFFu, sysl == __shfl_sync(0xFFFFFFFFu, sysl, 0))) {
+                    unsat = __reduce_add_sync(0xFFFFFFFFu, unsat);
+                    dn = __reduce_add_sync(0xFFFFFFFFu, dn);
+                    if ((tid & 31) == 0 && live) { atomicAdd(&cnt_sm[2 * sysl], unsat); atomicAdd(&cnt_sm[2 * sysl + 1], dn); }
+                } else if (live) {
+                    atomicAdd(&cnt_sm[2 * sysl], unsat);
+                    atomicAdd(&cnt_sm[2 * sysl + 1], dn);
+                }
+            }
+            __syncthreads();
+            for (int sysl = tid; sysl < S; sysl += RESIDENT_THREADS) {
+                en_sm[sysl] = __fdiv_rn((float)((long long)Z * m.N - 2ll * cnt_sm[2 * sysl]), (float)m.N);
+                if (record) mag_sm[sysl] = m.N - 2ll * cnt_sm[2 * sysl + 1];
+            }
+            __syncthreads();
+        }
+        if (record) {
+            if (P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids
+                for (int i = tid; i < 2 * P * T; i += RESIDENT_THREADS) cnt_sm[i] = 0;
+                __syncthreads();
+                for (int i0 = (tid & ~31); i0 < P * T * sysw; i0 += RESIDENT_THREADS) {
+                    const int i = i0 + (tid & 31);
+                    const bool live = i < P * T * sysw;
+                    const int idx = live ? i / sysw : -1;
+                    int neg_q = 0, neg_l = 0;
+                    if (live) {
+                        const int rem = i - idx * sysw, r = rem / W, w = rem - r * W;
+                        const int t = idx % T, pr = idx / T;
+                        const uint32_t *sa = pw + (size_t)sid_sm[(2 * pr) * T + t] * sysw, *sb = pw + (size_t)sid_sm[(2 * pr + 1) * T + t] * sysw;
+                        const uint32_t x = sa[rem] ^ sb[rem];
+#pragma unroll
+                        for (int k = 0; k < Z; k++) {
+                            const uint32_t nr = vg.nbr_row[((size_t)r * Z + k) * 2];
+                            neg_l += __popc(x ^ nbr_word(sa, nr, w, dls[k]) ^ nbr_word(sb, nr, w, dls[k]));
+                        }
+                        neg_q = __popc(x);
+                    }
+                    if (__all_sync(0xFFFFFFFFu, idx == __shfl_sync(0xFFFFFFFFu, idx, 0))) {
+                        neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
+                        neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
+                        if ((tid & 31) == 0 && live) { atomicAdd(&cnt_sm[2 * idx], neg_q); atomicAdd(&cnt_sm[2 * idx + 1], neg_l); }
+                    } else if (live) {
+                        atomicAdd(&cnt_sm[2 * idx], neg_q);
+                        atomicAdd(&cnt_sm[2 * idx + 1], neg_l);
+                    }
+                }
+                __syncthreads();
+                for (int idx = tid; idx < P * T; idx += RESIDENT_THREADS) {
+                    dsp_sm[idx] = m.N - 2ll * cnt_sm[2 * idx];
+                    dlk_sm[idx] = (long long)Z * m.N - 2ll * cnt_sm[2 * idx + 1];
+                }
+                __syncthreads();
+            }
+            for (int t = tid; t < T; t += RESIDENT_THREADS)  // mod.rs:543-578
+                fold_one<0, true>(
+                    m, st, 0, t, P > 0,
+                    [&](int r) { return mag_sm[sid_sm[r * T + t]]; },
+                    [&](int r) { return en_sm[sid_sm[r * T + t]]; },
+                    [&](int p) { return dsp_sm[p * T + t]; },
+                    [&](int p) { return dlk_sm[p * T + t]; });
+            __syncthreads();
+        }
+        if (pt_this) {  // mod.rs:748-796
+            if (T >= 2) {
+                if (tid < m.R) pt_exchange_body(m, pt, 0, tid, a.pt_schedule, parity, pt_event);
+                if (a.pt_schedule == 1) parity = 1 - parity;
+                __syncthreads();
+            }
+            pt_event++;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 11 * T; i += RESIDENT_THREADS) stg.sums[dg * 11 * T + i] = sums_sm[i];
+    for (int i = tid; i < S; i += RESIDENT_THREADS) {
+        mg.mags[dg * S + i] = mag_sm[i];
+        mg.energies[dg * S + i] = en_sm[i];
+        mg.system_ids[dg * S + i] = sid_sm[i];
+        ptg.round_trips[dg * S + i] = rt_sm[i];
+        ptg.trip_state[dg * S + i] = trip_sm[i];
+    }
+    for (int i = tid; i < P * T; i += RESIDENT_THREADS) {
+        const_cast<long long *>(stg.dot_spin)[dg * P * T + i] = dsp_sm[i];
+        const_cast<long long *>(stg.dot_link)[dg * P * T + i] = dlk_sm[i];
+    }
+    for (int i = tid; i < T - 1; i += RESIDENT_THREADS) {
+        ptg.edge_attempts[dg * (T - 1) + i] = ea_sm[i];
+        ptg.edge_acceptances[dg * (T - 1) + i] = eacc_sm[i];
+    }
+    for (int i = tid; i < S * sysw; i += RESIDENT_THREADS) {  // unpack: +1 = 0x01, -1 = 0xFF
+        const uint32_t word = pw[i];
+        uint4 *dst = reinterpret_cast<uint4 *>(g_spins + (int64_t)i * 32);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t part[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t nib = (word >> (16 * h + 4 * j)) & 15u;
+                const uint32_t spread = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);  // one bit per byte
+                part[j] = 0x01010101u ^ (spread * 0xFEu);  // 0x01 ^ 0xFE = 0xFF where the bit is set
+            }
+            dst[h] = make_uint4(part[0], part[1], part[2], part[3]);
+        }
+    }
+}
+
+// shared memory of prows_resident_kernel
+inline size_t prows_resident_smem(int S, int T, int P, int z, int64_t N) {
+    const size_t thr_words = ((size_t)T * (2 * z + 1) + 3) & ~size_t(3);
+    const size_t cnt = 2 * (size_t)std::max(S, P * T);
+    return thr_words * 4 + resident_scalar_bytes(S, T, P) + (size_t)S * (size_t)(N / 32) * 4 + cnt * 4 + 16;
+}
+
 }  // namespace pp

@@ -41,6 +41,7 @@ struct RowsView {
     const uint32_t *class_rows;  // rows sorted by class
     const uint32_t *class_start; // [m_half + 1]
     const uint64_t *keys;        // [D] realization_seed(seed, sample_offset + d)
+    int packed_draws;            // 1: draws in the packed mapping (a handle whose resident kernel is bit-packed, pp_kernels_prows.cuh)
 };
 
 struct RowsPlan {
@@ -253,7 +254,13 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
         if ((int)sys < m.sys_lo || (int)sys >= m.sys_hi) continue;     // system-split handle: another process updates this system
         const int t = slot % m.T;                                     // realization.rs:166
         int8_t *s = spins_d + (int64_t)sys * m.N;
-        const u32x4 o = philox4x32(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
+        uint32_t draws[4];
+        if (v.packed_draws) {
+            packed_draws4(q, sweep_index, sys, TAG_SWEEP_PACKED | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32), draws);
+        } else {
+            const u32x4 o = philox4x32(q, sweep_index, sys, TAG_SWEEP | (uint32_t)colour, (uint32_t)key, (uint32_t)(key >> 32));
+            draws[0] = o.x >> 8; draws[1] = o.y >> 8; draws[2] = o.z >> 8; draws[3] = o.w >> 8;
+        }
         const uint64_t C = Cv[ss % PF];
         uint64_t F[ZA], B[ZA];
 #pragma unroll
@@ -279,7 +286,7 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
                 const int nd = (int)((dw[l >> 1] >> (16 * (l & 1))) & 0xFFu);
                 const bool dn = ((cw[l >> 1] >> (16 * (l & 1))) & 0x80u) != 0;
                 const int idx = dn ? 4 * z - 2 * nd : 2 * nd;  // ec + 2z' with ec = -s h, h = 2z' - 2 nd (sweep.rs:178)
-                const bool flip = (pick(o, l) >> 8) < lut_sm[t * width + idx];
+                const bool flip = draws[l] < lut_sm[t * width + idx];
                 if (flip) fl[l >> 1] |= 0xFEu << (16 * (l & 1));
                 if (EACC) e_sum += flip ? idx - 2 * z : 2 * z - idx;  // s h after the update = ec if flipped, -ec if not
             }
@@ -299,7 +306,7 @@ __device__ __forceinline__ void rows_sweep_body(const ModelView &m, const RowsVi
             for (int l = 0; l < 4; l++) {
                 const int w = l >> 1, bs = 16 * (l & 1);
                 const uint32_t sbyte = (cw[w] >> bs) & 0xFFu;
-                const uint32_t draw = pick(o, l) >> 8;
+                const uint32_t draw = draws[l];
                 float h = 0.0f;
                 int hi = 0;
 #pragma unroll

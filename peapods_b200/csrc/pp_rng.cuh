@@ -116,4 +116,20 @@ PP_HD uint32_t pick(const u32x4 &v, uint32_t lane) {
     return lane == 0 ? v.x : lane == 1 ? v.y : lane == 2 ? v.z : v.w;
 }
 
+// The four 24-bit draws of the ranks 4 r4 .. 4 r4 + 3 in the PACKED mapping (32 ranks per six calls, counter = {rank >> 5, sweep,
+// stream, tag | call << 8 | colour}): for a kernel that owns four ranks at a time (the int8 row kernels of a handle whose other
+// kernels are bit-packed, so that the handle's trajectory does not depend on which kernel runs a sweep).  One or two calls.
+PP_HD void packed_draws4(uint32_t r4, uint32_t sweep, uint32_t stream, uint32_t tag_colour, uint32_t k0, uint32_t k1, uint32_t (&d)[4]) {
+    const uint32_t block = r4 >> 3, i0 = 3u * (r4 & 7u);
+    const uint32_t c0 = i0 >> 2, c1 = (i0 + 2u) >> 2;
+    const u32x4 a = philox4x32(block, sweep, stream, tag_colour | (c0 << 8), k0, k1);
+    u32x4 b = a;
+    if (c1 != c0) b = philox4x32(block, sweep, stream, tag_colour | (c1 << 8), k0, k1);
+    const uint32_t A = pick(a, i0 & 3u);
+    const uint32_t B = pick(((i0 + 1u) >> 2) == c0 ? a : b, (i0 + 1u) & 3u);
+    const uint32_t C = pick(b, (i0 + 2u) & 3u);
+    d[0] = A >> 8; d[1] = B >> 8; d[2] = C >> 8;
+    d[3] = ((A & 255u) << 16) | ((B & 255u) << 8) | (C & 255u);
+}
+
 }  // namespace pp
