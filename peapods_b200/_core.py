@@ -301,6 +301,11 @@ class IsingSimulation:
         _lib.check(self._lib.pp_op_pt(self._h, _lib.PT_SCHEDULES[pt_schedule], int(pt_event)))
 
 
+def nccl_comm_cached(device, world, rank) -> bool:
+    """True when this process already holds the engine's communicator of (device, world, rank): no bootstrap token is needed."""
+    return bool(_lib.load().pp_nccl_comm_cached(int(device), int(world), int(rank)))
+
+
 def nccl_unique_id() -> bytes:
     """Bootstrap token for a slab-decomposed lattice: call on rank 0, broadcast to the other ranks."""
     lib = _lib.load()
