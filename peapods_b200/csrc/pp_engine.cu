@@ -406,6 +406,12 @@ extern "C" pp_status pp_debug_last_timing(const pp_sim *sim, pp_timing *out) {
     *out = sim->last_timing;
     return PP_OK;
 }
+#ifdef PP_M3_TIMING
+extern "C" int32_t pp_debug_m3_clocks(unsigned long long *out, int64_t n) {  // variant builds only (tools/m3_phases.py)
+    cudaDeviceSynchronize();
+    return (int32_t)cudaMemcpyFromSymbol(out, pp::pp_m3_clk, (size_t)n * sizeof(unsigned long long));
+}
+#endif
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
 extern "C" int32_t pp_rows_packed(const pp_sim *sim) { return sim && (sim->prows || sim->rv.packed_draws) ? 1 : 0; }
@@ -1523,18 +1529,18 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
             // stages data while the other computes); NH = 2: two slots per CTA sharing the coupling words
             auto smem_words = [&](int nh) {
                 const size_t jw = 3 * (size_t)N;
-                return nh == 2 ? jw + 4 * (size_t)s->m3.n_items + 2 * (size_t)m.R * N + 8 + 2 * 512 : jw + (size_t)m.R * N + 8;
+                return nh == 2 ? jw + 4 * (size_t)s->m3.n_items + 2 * (size_t)m.R * N + 2 * MSC3D_NBAR + 2 * 64 + 2 * 512 : jw + (size_t)m.R * N + 2 * MSC3D_NBAR + 64;  // 64 words per half: parked system ids
             };
             const size_t sm_total = 227 * 1024, cta_reserved = 1024;
             int nh = 1;
             if (2 * (smem_words(1) * 4 + cta_reserved) > sm_total && smem_words(2) * 4 + cta_reserved <= sm_total) nh = 2;
-            if ((size_t)m.R * N < 1024) nh = 2;  // NH = 1 parks its 2 KB reduction scratch in the spin buffer
+            if ((size_t)m.R * N < 1152) nh = 2;  // NH = 1 parks its 2 KB reduction scratch + 2.3 KB of tail values in the spin buffer
             if (const char *e = getenv("PP_MSC3D_NH")) nh = atoi(e) == 2 ? 2 : 1;
             // per-thread counter capacity of the epilogue (MSC3D_KE / MSC3D_KM planes)
             const int64_t sites_em = N / (32 * (4 / m.R)), sites_pair = m.P > 0 ? N / (32 * (4 / m.P)) : 0;
             const bool cap_ok = 3 * sites_em < (1 << MSC3D_KE) - 8 && sites_em < (1 << MSC3D_KM) - 8 &&
                                 3 * sites_pair < (1 << MSC3D_KE) - 8;
-            if (cap_ok && smem_words(nh) * 4 + cta_reserved <= sm_total && (nh == 2 || (size_t)m.R * N >= 1024)) {
+            if (cap_ok && smem_words(nh) * 4 + cta_reserved <= sm_total && (nh == 2 || (size_t)m.R * N >= 1152)) {
                 CREATE_TRY(pool_alloc(s, (void **)&s->d_items, sizeof(uint16_t) * s->m3.items.size()));
                 CREATE_TRY(cudaMemcpy(s->d_items, s->m3.items.data(), sizeof(uint16_t) * s->m3.items.size(), cudaMemcpyHostToDevice));
                 s->gv.items = s->d_items;

@@ -243,6 +243,7 @@ __device__ __forceinline__ void to_arr(const uint4 v, uint32_t *a) { a[0] = v.x;
 constexpr int MSC3D_KE = 10;  // planes of the per-thread unsatisfied-bond counters (3*sites_per_thread < 1016)
 constexpr int MSC3D_KM = 9;   // planes of the per-thread down-spin / q counters     (sites_per_thread   < 504)
 constexpr int MSC3D_NTH = 256;  // threads per half
+constexpr int MSC3D_NBAR = 18;  // mbarriers in shared memory: [0] couplings (+ item table), [1 + half * 8 + r] the spin words of replica r of a half
 
 // One quad (four same-colour sites of one row segment) of all RPC replicas.  P = the quad's sites sit at x2 = 2j + P.
 //   sp: the half's [RPC][N] words; J: [3][N] coupling sign words in shared memory (all-zero words for a ferromagnet)
@@ -493,6 +494,15 @@ __device__ __noinline__ uint32_t merge_lane_total(const uint32_t *src, const int
     return warp_lane_total(acc);
 }
 
+#ifdef PP_M3_TIMING  // phase clocks of every CTA of the last launch (tools/m3_phases.py; never defined in the product build)
+__device__ unsigned long long pp_m3_clk[8192 * 32];
+#define M3_CLK(k) do { if (threadIdx.x == 0 && blockIdx.x < 8192) pp_m3_clk[blockIdx.x * 32 + (k)] = clock64(); } while (0)
+#define M3_T(k) M3_CLK(16 + (k))
+#else
+#define M3_CLK(k) do { } while (0)
+#define M3_T(k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // grid.x = G * ceil(T / NH); block = NH * 256 threads.  Half h of CTA (g, tp) owns temperature slot t = tp*NH + h of
 // word group g for all RPC replicas; the halves share the coupling words and the item table in shared memory and
@@ -514,7 +524,8 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     uint4 *items_sm = reinterpret_cast<uint4 *>(smem + 3 * N);
     uint32_t *sp_all = NH == 2 ? reinterpret_cast<uint32_t *>(items_sm + gv.n_items) : smem + 3 * N;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sp_all + (size_t)NH * RPC * N);
-    uint32_t *red_all = reinterpret_cast<uint32_t *>(bars + 4);
+    uint16_t *ids_all = reinterpret_cast<uint16_t *>(bars + MSC3D_NBAR);  // [NH][RPC][32] system ids of the CTA's realizations, fetched at the top
+    uint32_t *red_all = reinterpret_cast<uint32_t *>(ids_all + NH * 4 * 32);
     auto item_at = [&](int it) { return NH == 2 ? items_sm[it] : __ldg(gv.items + it); };
     const int tid = threadIdx.x;
     const int half = NH == 1 ? 0 : tid / MSC3D_NTH, ht = tid - half * MSC3D_NTH;
@@ -525,20 +536,19 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     uint32_t *sp = sp_all + (size_t)half * RPC * N;
     uint32_t *red = NH == 2 ? red_all + half * 512 : sp;
     const uint32_t *J = Jsm;
+#ifdef PP_M3_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 8192) {
+        unsigned long long gt; uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        pp_m3_clk[blockIdx.x * 32 + 10] = gt; pp_m3_clk[blockIdx.x * 32 + 11] = smid;
+    }
+#endif
+    M3_CLK(0);
 
-    // ---- stage in: bulk-async copies, completion on mbarriers (bars[0]: couplings + item table, bars[1+h]: spins)
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        for (int h = 0; h < NH; h++) mbar_init(&bars[1 + h], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], 3u * bytes + (NH == 2 ? (uint32_t)gv.n_items * 16u : 0u));
-        bulk_g2s(Jsm, m.Jw + g * 3 * (int64_t)N, 3u * bytes, &bars[0]);
-        if (NH == 2) bulk_g2s(items_sm, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
-    }
-    if (t >= m.T) return;  // odd T: the last CTA of a group has an idle half
+    // ---- the exchange masks and thresholds first: everything after the bulk copies hangs on them (masks -> gather loads), and a
+    // load that queues behind 112 KB of bulk requests comes back a microsecond later
+    const bool live = t < m.T;
     // Spin words: m.words is the input buffer, words_out the output buffer (ping-pong, so that a CTA may still read its
     // neighbours' pre-sweep words while they are being rewritten).  When a parallel-tempering event is pending
     // (swap_mask != nullptr) the lanes that crossed an edge are gathered from the neighbouring slots while loading:
@@ -548,43 +558,196 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     uint32_t bulk_mask = 0;  // bit r: replica r is staged by a bulk-async copy
     uint32_t mk[RPC][3];     // schedule 0: {mask[t-1], mask[t], -}; schedule 1: {m1(t), m2(t), m1(t2)}
     int t1 = -1, t2 = -1, t21 = -1;  // full ladder: first-pass partner of t, second-pass partner of t, first-pass partner of t2
-    {
+    // The mask words are loaded unconditionally from clamped edge indices, all loads back to back into their own registers, and
+    // only looked at after the bulk copies have been issued (a branch per replica and side made every load wait for the one before).
+    int edge[3] = {0, 0, 0};
+    bool edge_on[3] = {false, false, false};
+    const bool pend = swap_mask != nullptr && live && m.T > 1;
+    if (pend) {
         auto partner = [&](int x, int q) {  // slot exchanging with x over an edge of parity q (edges q, q+2, ...), or -1
             if (x >= q && ((x - q) & 1) == 0 && x + 1 < m.T) return x + 1;
             if (x - 1 >= q && ((x - 1 - q) & 1) == 0) return x - 1;
             return -1;
         };
-        if (swap_mask && pt_schedule == 1) {
+        if (pt_schedule == 0) {
+            edge_on[0] = t > 0;       edge[0] = max(t - 1, 0);
+            edge_on[1] = t + 1 < m.T; edge[1] = min(t, m.T - 2);
+        } else {
             t1 = partner(t, pt_parity);
             t2 = partner(t, 1 - pt_parity);
             t21 = t2 >= 0 ? partner(t2, pt_parity) : -1;
+            edge_on[0] = t1 >= 0;  edge[0] = t1 >= 0 ? min(t, t1) : 0;
+            edge_on[1] = t2 >= 0;  edge[1] = t2 >= 0 ? min(t, t2) : 0;
+            edge_on[2] = t21 >= 0; edge[2] = t21 >= 0 ? min(t2, t21) : 0;
         }
+    }
+    // One load per lane fetches every small word the CTA needs (lanes 0..23: mask k of replica r at lane r + 8k; lanes 24..30: the
+    // acceptance thresholds count[u] = table[t][2u], sweep.rs:162-166, index ec + 2z' = 2*unsat); the words are handed round
+    // by shuffles after the block-wide barrier below.  (Uniform loads per replica made the compiler move each word to a uniform
+    // register straight away: one memory round trip per replica instead of one.)
+    uint32_t small_word = 0u;
+    {
+        const int sl = ht & 31, sr = sl & 7, sk = sl >> 3;
+        const uint32_t *addr = nullptr;
+        if (sk < 3) {
+            if (pend && sr < RPC)
+                addr = swap_mask + (g * m.R + sr) * (int64_t)(m.T - 1) + (sk == 0 ? edge[0] : sk == 1 ? edge[1] : edge[2]);
+        } else if (sl < 31 && live) {
+            addr = m.lut + t * 13 + 2 * (sl - 24);
+        }
+        if (addr) small_word = __ldg(addr);
+    }
+    // ---- stage in: bulk-async copies (TMA engine), completion on mbarriers.  Issued right behind the one small load, each by the thread
+    // that initialises its barrier (no block-wide wait in front of the first byte): thread 0 the couplings (+ item table),
+    // lane 0 of warp (r + 1) & 7 of a half the spin words of replica r.
+    static_assert(RPC <= 8, "one spin barrier per replica and half");
+    auto spin_bar = [&](int r) { return &bars[1 + half * 8 + r]; };
+    auto wait_spins = [&]() {
 #pragma unroll
-        for (int r = 0; r < RPC; r++) {
-            mk[r][0] = mk[r][1] = mk[r][2] = 0u;
-            if (swap_mask) {
-                const uint32_t *mrow = swap_mask + (g * m.R + r) * (int64_t)(m.T - 1);
-                if (pt_schedule == 0) {
-                    if (t > 0) mk[r][0] = __ldg(mrow + t - 1);
-                    if (t + 1 < m.T) mk[r][1] = __ldg(mrow + t);
-                } else {
-                    if (t1 >= 0) mk[r][0] = __ldg(mrow + min(t, t1));
-                    if (t2 >= 0) mk[r][1] = __ldg(mrow + min(t, t2));
-                    if (t21 >= 0 && mk[r][1]) mk[r][2] = __ldg(mrow + min(t2, t21));
+        for (int r = 0; r < RPC; r++) mbar_wait(spin_bar(r), 0);
+    };
+    if ((tid & 31) == 0) {
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&bars[0], 3u * bytes + (NH == 2 ? (uint32_t)gv.n_items * 16u : 0u));
+            bulk_g2s(Jsm, m.Jw + g * 3 * (int64_t)N, 3u * bytes, &bars[0]);
+            if (NH == 2) bulk_g2s(items_sm, gv.items, (uint32_t)gv.n_items * 16u, &bars[0]);
+        }
+        if (t < m.T) {
+#pragma unroll
+            for (int r = 0; r < RPC; r++)
+                if (((r + 1) & 7) == (ht >> 5)) {
+                    mbar_init(spin_bar(r), 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    mbar_expect_tx(spin_bar(r), bytes);
+                    bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, spin_bar(r));
                 }
-            }
-            if ((mk[r][0] | mk[r][1]) == 0u) bulk_mask |= 1u << r;
         }
     }
-    if (ht == 0) {  // every system arrives by bulk-async copy
-        mbar_expect_tx(&bars[1 + half], bytes * (uint32_t)RPC);
+    M3_T(2);
+    // The epilogue's last step addresses per-system outputs through system_ids: fetched now (the labels do not move during a
+    // launch), parked in shared memory once the stage-in has waited anyway, so that the tail does not walk RPC cold loads.
+    uint16_t *ids = ids_all + half * 4 * 32;
+    int my_ids[RPC <= 4 ? RPC : 1];
+    const bool ids_ok = RPC <= 4 && m.S <= 65535;
+    const bool ids_pre = ids_ok && live && ht < 32 && g * 32 + ht < m.D;
+    if (ids_pre) {
 #pragma unroll
-        for (int r = 0; r < RPC; r++)
-            bulk_g2s(sp + (size_t)r * N, m.words + ((g * m.S + (int64_t)r * m.T + t) * (int64_t)N), bytes, &bars[1 + half]);
+        for (int r = 0; r < (RPC <= 4 ? RPC : 1); r++) my_ids[r] = __ldg(m.system_ids + (g * 32 + ht) * m.S + r * m.T + t);
     }
+    M3_T(0);
+    __syncthreads();  // the barriers initialised above are visible to every waiter
+    M3_CLK(15);
+    if (t >= m.T) return;  // odd T: the last CTA of a group has an idle half
+    M3_T(3);
+    uint32_t thr[7];
+#pragma unroll
+    for (int u = 0; u < 7; u++) {
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, small_word, 24 + u);
+        thr[u] = METRO ? (cnt << 8) : cnt;
+    }
+#pragma unroll
+    for (int r = 0; r < RPC; r++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) mk[r][k] = __shfl_sync(0xFFFFFFFFu, small_word, r + 8 * k);
+        if (!edge_on[0]) mk[r][0] = 0u;
+        if (!edge_on[1]) mk[r][1] = 0u;
+        if (!edge_on[2] || mk[r][1] == 0u) mk[r][2] = 0u;
+        if ((mk[r][0] | mk[r][1]) == 0u) bulk_mask |= 1u << r;
+    }
+#ifdef PP_M3_TIMING
+    { uint32_t acc = 0;
+#pragma unroll
+      for (int r = 0; r < RPC; r++) acc |= mk[r][0] | mk[r][1];
+      if (acc == 0x12345u) pp_m3_clk[0] = 1; }
+    M3_CLK(12);  // masks have arrived
+#endif
     // Systems with crossing lanes: the neighbouring slots' words are read with plain loads (two replicas per round, all loads
     // of a round in flight together, issued before the wait for the bulk copies) and merged into the staged words.
-    if (bulk_mask != (1u << RPC) - 1u) {
+    if (bulk_mask != (1u << RPC) - 1u && pt_schedule == 0) {
+        // single_random_edge: every (replica, side) with a crossing lane is one exchange  a ^= (a ^ nbr) & mask  (a lane attempts
+        // one edge, so the two masks of a replica are disjoint and the exchanges commute).  Up to four exchanges per round, the
+        // loads of a round all in flight before the first merge: one round for nearly every CTA.
+        const uint32_t n4 = N / 4;
+        uint32_t todo = 0;  // bit 2r + side
+#pragma unroll
+        for (int r = 0; r < RPC; r++) todo |= (mk[r][0] ? 1u << (2 * r) : 0u) | (mk[r][1] ? 2u << (2 * r) : 0u);
+        bool waited = false;
+        while (todo) {
+            int e[4];
+            uint32_t em[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                e[j] = todo ? __ffs((int)todo) - 1 : -1;
+                todo &= todo - 1u;
+                em[j] = 0u;
+#pragma unroll
+                for (int r = 0; r < RPC; r++) {
+                    if (e[j] == 2 * r) em[j] = mk[r][0];
+                    if (e[j] == 2 * r + 1) em[j] = mk[r][1];
+                }
+            }
+            if (NFIX == 16 * MSC3D_NTH) {  // four 128-bit words per thread and system: no loop, no bounds
+                uint4 nb[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (e[j] < 0) continue;
+                    const int r = e[j] >> 1, tn = t + ((e[j] & 1) ? 1 : -1);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(m.words + ((g * m.S + (int64_t)r * m.T + tn) * (int64_t)N)) + ht;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) nb[j][k] = __ldg(src + k * MSC3D_NTH);
+                }
+                if (!waited) { wait_spins(); waited = true; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (e[j] < 0) continue;
+                    uint4 *dst = reinterpret_cast<uint4 *>(sp + (size_t)(e[j] >> 1) * N) + ht;
+                    const uint32_t mm = em[j];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        uint4 a = dst[k * MSC3D_NTH];
+                        const uint4 b = nb[j][k];
+                        a.x ^= (a.x ^ b.x) & mm; a.y ^= (a.y ^ b.y) & mm; a.z ^= (a.z ^ b.z) & mm; a.w ^= (a.w ^ b.w) & mm;
+                        dst[k * MSC3D_NTH] = a;
+                    }
+                }
+            } else for (uint32_t i0 = 0; i0 < n4; i0 += 4 * MSC3D_NTH) {
+                uint4 nb[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (e[j] < 0) continue;
+                    const int r = e[j] >> 1, tn = t + ((e[j] & 1) ? 1 : -1);
+                    const uint4 *src = reinterpret_cast<const uint4 *>(m.words + ((g * m.S + (int64_t)r * m.T + tn) * (int64_t)N));
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t i = i0 + k * MSC3D_NTH + ht;
+                        if (i < n4) nb[j][k] = __ldg(src + i);
+                    }
+                }
+#ifdef PP_M3_TIMING
+                if (!waited) M3_CLK(13);  // gather loads issued
+#endif
+                if (!waited) { wait_spins(); waited = true; M3_CLK(14); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (e[j] < 0) continue;
+                    uint4 *dst = reinterpret_cast<uint4 *>(sp + (size_t)(e[j] >> 1) * N);
+                    const uint32_t mm = em[j];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t i = i0 + k * MSC3D_NTH + ht;
+                        if (i < n4) {
+                            uint4 a = dst[i];
+                            const uint4 b = nb[j][k];
+                            a.x ^= (a.x ^ b.x) & mm; a.y ^= (a.y ^ b.y) & mm; a.z ^= (a.z ^ b.z) & mm; a.w ^= (a.w ^ b.w) & mm;
+                            dst[i] = a;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (bulk_mask != (1u << RPC) - 1u) {
         const uint32_t n4 = N / 4;
         bool waited = false;
 #pragma unroll
@@ -617,7 +780,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                         }
                     }
                 }
-                if (!waited) { mbar_wait(&bars[1 + half], 0); waited = true; }
+                if (!waited) { wait_spins(); waited = true; }
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
                     const int r = rb + rr;
@@ -649,12 +812,10 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
             }
         }
     }
-    // acceptance thresholds of this temperature: count[u] = table[t][2u]  (sweep.rs:162-166, index ec + 2z' = 2*unsat)
-    uint32_t thr[7];
+    M3_CLK(1);
+    if (ids_pre) {
 #pragma unroll
-    for (int u = 0; u < 7; u++) {
-        const uint32_t cnt = m.lut[t * 13 + 2 * u];
-        thr[u] = METRO ? (cnt << 8) : cnt;
+        for (int r = 0; r < (RPC <= 4 ? RPC : 1); r++) ids[r * 32 + ht] = (uint16_t)my_ids[r];
     }
     uint64_t nthr[3];
 #pragma unroll
@@ -663,8 +824,9 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
     const uint64_t key = msc_group_key(m.seed, (uint64_t)(group_offset + g));
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
     mbar_wait(&bars[0], 0);
-    mbar_wait(&bars[1 + half], 0);
+    wait_spins();
     if (bulk_mask != (1u << RPC) - 1u) half_barrier(half, MSC3D_NTH);  // gathered words were written with plain stores
+    M3_CLK(2);
 
     // ---- sweeps: colour 0 then colour 1 (RNG-SPEC visit order)
     // In-sweep energy (esw, host-checked: one slot per CTA, an even number of replicas, at most two quads per thread and
@@ -699,6 +861,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                 }
             }
             half_barrier(half, MSC3D_NTH);
+            M3_CLK(3 + c);
         }
     }
 
@@ -714,6 +877,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         }
     }
 
+    M3_CLK(5);
     // ---- epilogue: per-lane unsatisfied forward bonds, down spins, replica-pair overlaps.
     // Warps 0..3 of the half: energy + magnetisation, 4/RPC warps per replica; warps 4..7: the P replica pairs,
     // 4/P warps per pair.  Each warp strides over the row segments, accumulates bit-sliced counters and reduces them
@@ -735,8 +899,10 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
             for (int r = 0; r < RPC; r++)
 #pragma unroll
                 for (int b = 0; b < MSC3D_KS; b++) scr[(r * MSC3D_KS + b) * MSC3D_NTH + ht] = ea[r].p[b];
+            M3_T(6);
             half_barrier(half, MSC3D_NTH);
             if (w < RPC) res[(w * 2 + 0) * 32 + lane] = merge_lane_total<MSC3D_KS, 8>(scr + w * MSC3D_KS * MSC3D_NTH, lane);
+            M3_T(7);
             if (NP > 0 && want_overlap) {
                 const int p = w / WPPX, sub = w % WPPX;
                 const uint32_t *A = sp + (size_t)(2 * p) * N, *B = sp + (size_t)(2 * p + 1) * N;
@@ -751,6 +917,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                     if (it + 32 * WPPX < gv.n_items) next = item_at(it + 32 * WPPX);
                     msc3d_pairm_item(A, B, N2, desc, vl, vq, vma, vmb);
                 }
+                M3_T(8);
                 half_barrier(half, MSC3D_NTH);  // the energy counters have been consumed
                 // park: pair p at scr + p * PW, quantities [q | ql | M_a | M_b], each [plane][WPPX * 32]
                 constexpr int QW = MSC3D_KQ * WPPX * 32, LW = MSC3D_KL * WPPX * 32, PW = 3 * QW + LW;
@@ -764,6 +931,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
 #pragma unroll
                 for (int b = 0; b < MSC3D_KL; b++) base[QW + b * WPPX * 32] = vl.p[b];
                 half_barrier(half, MSC3D_NTH);
+                M3_T(9);
                 if (w < NP * 4) {  // one warp per (pair, quantity)
                     const int p2 = w >> 2, qn = w & 3;
                     const uint32_t *src = scr + p2 * PW;
@@ -774,6 +942,7 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                 }
             }
             half_barrier(half, MSC3D_NTH);
+            M3_T(10);
             fin_e = res; fin_p = res_p;
         } else {
         constexpr int WPP = NP > 0 ? 4 / NP : 1; // warps per pair
@@ -824,17 +993,20 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
         half_barrier(half, MSC3D_NTH);
         fin_e = red; fin_p = red_p; fin_wpe = WPE; fin_wpp = WPP;
         }
-        // warp 0 of the half: lane l finishes realization 32g + l at slot t -- per-system energy / magnetisation, pair
-        // dots, and (want_fold) the recorded-sweep fold of simulation/mod.rs:543-578 + statistics/overlap.rs:283-306
+        // Lane l finishes realization 32g + l at slot t -- per-system energy / magnetisation, pair dots, and (want_fold) the
+        // recorded-sweep fold of simulation/mod.rs:543-578 + statistics/overlap.rs:283-306.  A "unit" is a replica (u < RPC) or a
+        // replica pair (u - RPC).  unit_values: lane totals -> f32 observables + the per-system / per-pair outputs; unit_fold: the
+        // f64 reductions, same values and same order as fold_red (pp_kernels_stats.cuh): replica-major, then pair-major.
+        // One slot per CTA: the units' values are worked out by one warp each (they are ~300 dependent instructions apiece),
+        // parked, and warp 0 only issues the ordered reductions; otherwise warp 0 walks the units.
+        // Rolled on purpose: unrolled (with inlined f32 divisions) this was ~1200 instructions of straight-line code
+        // streaming through the instruction cache the hot loops need.
         const int64_t d = g * 32 + lane;
-        if (w == 0 && d < m.D) {
-            // Rolled loops on purpose: this runs once per CTA on one warp; unrolled (with four inlined f32 divisions per replica)
-            // it was ~1200 instructions of straight-line code streaming through the instruction cache the hot loops need.
-            // Same values, same order of the f64 reductions as fold_red (pp_kernels_stats.cuh): replica-major, then pair-major.
-            const float nf = (float)m.N, nb = (float)(m.N * m.z);
-            double *sums = st.sums + d * 11 * m.T + t;
-#pragma unroll 1
-            for (int r = 0; r < RPC; r++) {
+        const float nf = (float)m.N, nb = (float)(m.N * m.z);
+        const int n_units = RPC + ((NP > 0 && want_overlap) ? NP : 0);
+        auto unit_values = [&](const int u, float &v0, float &v1, int &v2) {
+            if (u < RPC) {
+                const int r = u;
                 uint32_t e = 0, dn = 0;
                 for (int k = 0; k < fin_wpe; k++) {
                     if (want_energy) e += fin_e[((r * 2 + 0) * fin_wpe + k) * 32 + lane];
@@ -843,53 +1015,93 @@ msc3d_kernel(ModelView m, Msc3dView gv, StatsView st, uint32_t sweep_index, int 
                 // sum_i sum_d s s J = (#bonds) - 2 * unsatisfied, e = that / N in f32   (energy.rs:103-108)
                 const float ev = __fdiv_rn((float)(3ll * N - 2ll * e), (float)N);
                 const long long mv = (long long)N - 2ll * dn;
-                const int sys = m.system_ids[d * m.S + r * m.T + t];
+                const int sys = ids_ok ? (int)ids[r * 32 + lane] : m.system_ids[d * m.S + r * m.T + t];
                 if (want_energy) m.energies[d * m.S + sys] = ev;
                 if (want_mags) m.mags[d * m.S + sys] = mv;
-                if (want_fold) {  // simulation/mod.rs:555-578
-                    const float mag = __fdiv_rn((float)mv, nf);
-                    const float m2 = __fmul_rn(mag, mag);
-                    atomicAdd(sums + 0 * m.T, (double)mag);
-                    atomicAdd(sums + 1 * m.T, (double)m2);
-                    atomicAdd(sums + 2 * m.T, (double)__fmul_rn(m2, m2));
-                    atomicAdd(sums + 3 * m.T, (double)ev);
-                    atomicAdd(sums + 4 * m.T, __dmul_rn((double)ev, (double)ev));
+                v0 = ev;
+                v1 = want_fold ? __fdiv_rn((float)mv, nf) : 0.0f;
+                v2 = 0;
+            } else {
+                const int p = u - RPC;
+                uint32_t cs = 0, cl = 0;
+                for (int k = 0; k < fin_wpp; k++) {
+                    cs += fin_p[((p * 2 + 0) * fin_wpp + k) * 32 + lane];
+                    cl += fin_p[((p * 2 + 1) * fin_wpp + k) * 32 + lane];
+                }
+                const long long sv = (long long)N - 2ll * cs, lv = 3ll * N - 2ll * cl;
+                const int64_t o = (d * m.P + p) * m.T + t;
+                dot_spin[o] = sv;
+                dot_link[o] = lv;
+                v0 = want_fold ? __fdiv_rn((float)sv, nf) : 0.0f;
+                v1 = want_fold ? __fdiv_rn((float)lv, nb) : 0.0f;
+                v2 = (int)sv;
+            }
+        };
+        auto unit_fold = [&](const int u, const float v0, const float v1, const int v2) {
+            double *sums = st.sums + d * 11 * m.T + t;
+            if (u < RPC) {  // simulation/mod.rs:555-578
+                const float ev = v0, mag = v1;
+                const float m2 = __fmul_rn(mag, mag);
+                atomicAdd(sums + 0 * m.T, (double)mag);
+                atomicAdd(sums + 1 * m.T, (double)m2);
+                atomicAdd(sums + 2 * m.T, (double)__fmul_rn(m2, m2));
+                atomicAdd(sums + 3 * m.T, (double)ev);
+                atomicAdd(sums + 4 * m.T, __dmul_rn((double)ev, (double)ev));
+            } else {  // statistics/overlap.rs:283-306 + :318-324
+                const float q = v0, ql = v1;
+                const float q2 = __fmul_rn(q, q);
+                const float ql2 = __fmul_rn(ql, ql);
+                atomicAdd(sums + 5 * m.T, (double)q);
+                atomicAdd(sums + 6 * m.T, (double)q2);
+                atomicAdd(sums + 7 * m.T, (double)__fmul_rn(q2, q2));
+                atomicAdd(sums + 8 * m.T, (double)ql);
+                atomicAdd(sums + 9 * m.T, (double)ql2);
+                atomicAdd(sums + 10 * m.T, (double)__fmul_rn(ql2, ql2));
+                const int64_t h = (d * m.T + t) * (int64_t)(m.N + 1) + ((long long)v2 + m.N) / 2;
+                atomicAdd(st.hist + h, 1u);
+                atomicAdd(st.ql_at_q + h, (double)ql);
+                atomicAdd(st.ql2_at_q + h, (double)ql2);
+            }
+        };
+        if (NH == 1 && RPC <= 4) {
+            // parked values [unit][3][32]: the (dead) coupling words on the in-sweep-energy path, else behind the lane totals
+            float *park = reinterpret_cast<float *>((ESW_OK && esw_on) ? smem : red + 512);
+            if (d < m.D) {
+#pragma unroll 1
+                for (int u = w; u < n_units; u += 8) {
+                    float v0, v1;
+                    int v2;
+                    unit_values(u, v0, v1, v2);
+                    park[(u * 3 + 0) * 32 + lane] = v0;
+                    park[(u * 3 + 1) * 32 + lane] = v1;
+                    park[(u * 3 + 2) * 32 + lane] = __int_as_float(v2);
                 }
             }
-            if (NP > 0 && want_overlap) {
-                const int64_t bins = m.N + 1;
+            if (want_fold) {
+                M3_T(11);
+                half_barrier(half, MSC3D_NTH);
+                if (w == 0 && d < m.D) {
 #pragma unroll 1
-                for (int p = 0; p < NP; p++) {
-                    uint32_t cs = 0, cl = 0;
-                    for (int k = 0; k < fin_wpp; k++) {
-                        cs += fin_p[((p * 2 + 0) * fin_wpp + k) * 32 + lane];
-                        cl += fin_p[((p * 2 + 1) * fin_wpp + k) * 32 + lane];
-                    }
-                    const long long sv = (long long)N - 2ll * cs, lv = 3ll * N - 2ll * cl;
-                    const int64_t o = (d * m.P + p) * m.T + t;
-                    dot_spin[o] = sv;
-                    dot_link[o] = lv;
-                    if (want_fold) {  // statistics/overlap.rs:283-306 + :318-324
-                        const float ql = __fdiv_rn((float)lv, nb);
-                        const float q = __fdiv_rn((float)sv, nf);
-                        const float q2 = __fmul_rn(q, q);
-                        const float ql2 = __fmul_rn(ql, ql);
-                        atomicAdd(sums + 5 * m.T, (double)q);
-                        atomicAdd(sums + 6 * m.T, (double)q2);
-                        atomicAdd(sums + 7 * m.T, (double)__fmul_rn(q2, q2));
-                        atomicAdd(sums + 8 * m.T, (double)ql);
-                        atomicAdd(sums + 9 * m.T, (double)ql2);
-                        atomicAdd(sums + 10 * m.T, (double)__fmul_rn(ql2, ql2));
-                        const int64_t h = (d * m.T + t) * bins + (sv + m.N) / 2;
-                        atomicAdd(st.hist + h, 1u);
-                        atomicAdd(st.ql_at_q + h, (double)ql);
-                        atomicAdd(st.ql2_at_q + h, (double)ql2);
-                    }
+                    for (int u = 0; u < n_units; u++)
+                        unit_fold(u, park[(u * 3 + 0) * 32 + lane], park[(u * 3 + 1) * 32 + lane], __float_as_int(park[(u * 3 + 2) * 32 + lane]));
                 }
+            }
+        } else if (w == 0 && d < m.D) {
+#pragma unroll 1
+            for (int u = 0; u < n_units; u++) {
+                float v0, v1;
+                int v2;
+                unit_values(u, v0, v1, v2);
+                if (want_fold) unit_fold(u, v0, v1, v2);
             }
         }
     }
+    M3_CLK(6);
     if (n_sweeps > 0 && ht == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    M3_CLK(7);
+#ifdef PP_M3_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 8192) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); pp_m3_clk[blockIdx.x * 32 + 9] = gt; }
+#endif
 }
 #endif  // __CUDACC__
 

@@ -119,7 +119,7 @@ class Ising:
             raise ValueError("overlap_cluster_action='observe' requires overlap_cluster_update_interval")
 
         oci = overlap_cluster_update_interval
-        if (self._layout_request == "auto" and self._sim.layout == "msc"
+        if (self._layout_request == "auto" and getattr(self._sim, "layout", None) == "msc"
                 and (cluster_update_interval is not None or (oci is not None and overlap_cluster_mode == "sw"))
                 and cluster_action == "update" and overlap_cluster_action == "update" and not collect_cluster_stats
                 and overlap_cluster_build_mode.strip() in ("houdayer", "houd2") and snapshot_interval is None):
