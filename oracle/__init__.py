@@ -16,11 +16,12 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "_build" / "libpp_oracle.so"
 
-RNG_XOSHIRO, RNG_PHILOX, RNG_PHILOX_MSC, RNG_PHILOX_PACKED = 0, 1, 2, 3
+RNG_XOSHIRO, RNG_PHILOX, RNG_PHILOX_MSC, RNG_PHILOX_PACKED, RNG_PHILOX_SYSQ = 0, 1, 2, 3, 4
 SWEEP_METROPOLIS, SWEEP_GIBBS = 0, 1
 PT_SINGLE_RANDOM_EDGE, PT_FULL_LADDER = 0, 1
 TAG_INIT, TAG_SWEEP, TAG_PT, TAG_SWEEP_MSC = 0x00010000, 0x00020000, 0x00030000, 0x00040000
 TAG_SWEEP_PACKED = 0x000A0000
+TAG_SWEEP_SYSQ = 0x000B0000
 
 
 def build(force: bool = False) -> Path:

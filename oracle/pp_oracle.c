@@ -354,7 +354,9 @@ static void sweep_philox_impl(const orc_lattice *lat, int8_t *spins, const float
                               uint64_t key, uint32_t sweep_index, int sweep_mode,
                               const uint32_t *table, int stream_is_slot, int packed) {
     int z = lat->n_neighbors, offset = 2 * z, width = 4 * z + 1;
-    uint32_t tag = packed ? ORC_TAG_SWEEP_PACKED : stream_is_slot ? ORC_TAG_SWEEP_MSC : ORC_TAG_SWEEP;
+    int sysq = packed == 2; /* system-quad mapping (pp_kernels_swords.cuh): one call per (site rank, four consecutive systems) */
+    if (sysq) packed = 0;
+    uint32_t tag = sysq ? ORC_TAG_SWEEP_SYSQ : packed ? ORC_TAG_SWEEP_PACKED : stream_is_slot ? ORC_TAG_SWEEP_MSC : ORC_TAG_SWEEP;
     uint32_t k[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
     for (int64_t slot = 0; slot < n_systems; slot++) {
         int64_t sys = system_ids[slot];
@@ -368,7 +370,11 @@ static void sweep_philox_impl(const orc_lattice *lat, int8_t *spins, const float
             uint32_t c3 = tag | colour[i];
             uint32_t r = rank[i];
             uint32_t draw;
-            if (packed) {
+            if (sysq) {
+                uint32_t ctr[4] = {r, sweep_index, stream >> 2, c3};
+                orc_philox(ctr, k, out);
+                draw = out[stream & 3u] >> 8;
+            } else if (packed) {
                 if ((r >> 5) != cached_c0 || c3 != cached_c3) {
                     for (uint32_t call = 0; call < 6; call++) {
                         uint32_t ctr[4] = {r >> 5, sweep_index, stream, c3 | (call << 8)};
@@ -416,7 +422,7 @@ void orc_sweep_philox(const orc_lattice *lat, int8_t *spins, const float *coupli
                                                n_systems, lat->n_neighbors, sweep_mode)
                                  : NULL;
     sweep_philox_impl(lat, spins, couplings, temperatures, system_ids, n_systems, colour, order, rank,
-                      key, sweep_index, sweep_mode, table, stream_is_slot & 1, (stream_is_slot >> 1) & 1);
+                      key, sweep_index, sweep_mode, table, stream_is_slot & 1, (stream_is_slot & 4) ? 2 : (stream_is_slot >> 1) & 1);
     free(table); free(order); free(rank);
 }
 
@@ -945,7 +951,7 @@ static void run_realization(orc_sim *sim, int64_t ridx, const orc_config *cfg, r
         } else {
             sweep_philox_impl(lat, re->spins, re->couplings, re->temperatures, re->system_ids, S, sim->colour,
                               sim->order, sim->rank, sweep_key, sweep_index, cfg->sweep_mode, table, msc,
-                              sim->rng_mode == ORC_RNG_PHILOX_PACKED);
+                              sim->rng_mode == ORC_RNG_PHILOX_PACKED ? 1 : sim->rng_mode == ORC_RNG_PHILOX_SYSQ ? 2 : 0);
         }
 
         /* mod.rs:434-470: FK cluster update of every slot's system, after the sweep, before the measurements */
@@ -1161,7 +1167,8 @@ int orc_sim_sample(orc_sim *sim, const orc_config *cfg, orc_results *out) {
         set_err("overlap cluster requires n_replicas >= max group_size"); /* mod.rs:207-213 */
         return -1;
     }
-    if ((cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX && sim->rng_mode != ORC_RNG_PHILOX_PACKED) ||
+    if ((cfg->cluster_interval > 0 && sim->rng_mode != ORC_RNG_PHILOX && sim->rng_mode != ORC_RNG_PHILOX_PACKED &&
+         sim->rng_mode != ORC_RNG_PHILOX_SYSQ) ||
         (cfg->overlap_cluster_interval > 0 && sim->rng_mode == ORC_RNG_XOSHIRO)) {
         set_err("cluster updates are restated for the RNG-SPEC modes only (FK: int8 mode)");
         return -1;

@@ -30,6 +30,9 @@
  *                       keyed by (seed, sweep, site-rank, stream); per-site
  *                       arithmetic and acceptance rule are the reference's.
  *   ORC_RNG_PHILOX_PACKED as PHILOX with the sweep draws in the packed mapping (32 ranks per six calls: orc_draw24_packed)
+ *   ORC_RNG_PHILOX_SYSQ as PHILOX with the sweep draws in the system-quad mapping (kernels that keep the same site of 32 systems of a
+ *                       realization in one word): counter = {colour rank, sweep index, system >> 2, ORC_TAG_SWEEP_SYSQ | colour},
+ *                       the draw of system s is out[s & 3] >> 8
  *   ORC_RNG_PHILOX_MSC  as PHILOX but one draw shared by the 32 disorder samples
  *                       of a multispin word (stream = replica*T + slot).
  */
@@ -44,7 +47,7 @@ extern "C" {
 
 #define ORC_MAX_DIMS 8
 
-enum { ORC_RNG_XOSHIRO = 0, ORC_RNG_PHILOX = 1, ORC_RNG_PHILOX_MSC = 2, ORC_RNG_PHILOX_PACKED = 3 };
+enum { ORC_RNG_XOSHIRO = 0, ORC_RNG_PHILOX = 1, ORC_RNG_PHILOX_MSC = 2, ORC_RNG_PHILOX_PACKED = 3, ORC_RNG_PHILOX_SYSQ = 4 };
 enum { ORC_SWEEP_METROPOLIS = 0, ORC_SWEEP_GIBBS = 1 };
 enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
 
@@ -58,6 +61,7 @@ enum { ORC_PT_SINGLE_RANDOM_EDGE = 0, ORC_PT_FULL_LADDER = 1 };
 #define ORC_TAG_OC_PAIR   0x00070000u  /* replica shuffle at a temperature: counter = {step, sweep index, slot t, tag} */
 #define ORC_TAG_OC_SEED   0x00080000u  /* Wolff seed scores: counter = {site >> 2, sweep index, t * P + g, tag} */
 #define ORC_TAG_OC_FLIP   0x00090000u  /* cluster coins:     counter = {root >> 2, sweep index, t * P + g, tag} */
+#define ORC_TAG_SWEEP_SYSQ 0x000B0000u  /* counter = {colour rank, sweep index, system id >> 2, tag | colour}; system s draws out[s & 3] >> 8 */
 #define ORC_TAG_SWEEP_PACKED 0x000A0000u  /* counter = {rank >> 5, sweep index, system id, tag | call << 8 | colour}, call = 0..5 */
 #define ORC_MSC_KEY_DOMAIN 0x6D73635F67726F75ull
 

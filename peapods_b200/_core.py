@@ -89,6 +89,7 @@ class IsingSimulation:
         self.uses_msc3d = bool(lib.pp_uses_msc3d(self._h))
         self.slab_packed = bool(lib.pp_slab_packed(self._h))
         self.rows_packed = bool(lib.pp_rows_packed(self._h))
+        self.sys_words = bool(lib.pp_sys_words(self._h))
         self.last_sweep_loop_ms = 0.0
         self.last_kernel_launches = 0
 

@@ -111,6 +111,7 @@ SIGNATURES = {
     "pp_debug_last_timing": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pp_slab_packed": (C.c_int32, [C.c_void_p]),
     "pp_rows_packed": (C.c_int32, [C.c_void_p]),
+    "pp_sys_words": (C.c_int32, [C.c_void_p]),
     "pp_set_spins": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_set_system_ids": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pp_op_sweep": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_int32]),

@@ -28,6 +28,7 @@
 #include "pp_kernels_msc3d.cuh"
 #include "pp_kernels_rows.cuh"
 #include "pp_kernels_prows.cuh"
+#include "pp_kernels_swords.cuh"
 #include "pp_kernels_stats.cuh"
 #include "pp_plan.h"
 #include "pp_slab.cuh"
@@ -243,6 +244,10 @@ struct pp_sim {
     size_t resident_packed_smem = 0;
     PRowsView pv{};
     int prows_nm[2] = {0, 0};                          // thresholds compared per site: [metropolis, gibbs]
+    // fp32 couplings with the same site of 32 systems in one word (pp_kernels_swords.cuh); `d_spins` is a scratch view as above
+    bool swords = false;
+    bool sw_tbits_valid = false;                       // the transposed view matches the words
+    SWordsView swv{};
     long long *d_rows_acc = nullptr;                   // [2 * max(D*S, D*P*T)] split-reduction scratch (kept zero between launches)
     unsigned int *d_rows_arrive = nullptr;
     int rows_nb = 1;                                   // blocks per system / pair of the split reductions
@@ -414,6 +419,7 @@ extern "C" int32_t pp_debug_m3_clocks(unsigned long long *out, int64_t n) {  // 
 #endif
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
+extern "C" int32_t pp_sys_words(const pp_sim *sim) { return sim && sim->swords ? 1 : 0; }
 extern "C" int32_t pp_rows_packed(const pp_sim *sim) { return sim && (sim->prows || sim->rv.packed_draws) ? 1 : 0; }
 extern "C" int64_t pp_local_spin_count(const pp_sim *sim) {
     if (!sim) return 0;
@@ -833,6 +839,77 @@ static pp_status launch_prows(pp_sim *s, Ctx &c, const ModelView &m_in, int swee
     return PP_OK;
 }
 
+// ---- fp32 couplings, the same site of 32 systems in one word (pp_kernels_swords.cuh) -----------------------------------------
+static pp_status swords_sync(pp_sim *s, cudaStream_t stream, int dir) {
+    const ModelView &m = s->mv;
+    swords_convert_kernel<<<dim3((unsigned)(m.D * s->swv.SW), blocks_for(m.N, 256)), 256, 0, stream>>>(m, s->swv, dir);
+    s->launches++;
+    if (dir == 0) s->sw_tbits_valid = false;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+// the packed state <-> the int8 view that the API and the int8-only kernels (cluster moves) see; dir 0: pack, 1: unpack
+static pp_status view_sync(pp_sim *s, cudaStream_t stream, int dir) {
+    if (s->prows) return prows_sync(s, stream, dir);
+    if (s->swords) return swords_sync(s, stream, dir);
+    return PP_OK;
+}
+
+static SWordsView swords_view(pp_sim *s, const Ctx &c) {
+    SWordsView sv = s->swv;
+    const int64_t d0 = c.m.sample_offset - s->mv.sample_offset;
+    const size_t nq = (size_t)(c.m.N / 32);
+    sv.words += (size_t)d0 * sv.SW * c.m.N;
+    sv.tbits += (size_t)d0 * c.m.S * nq;
+    sv.acc_e += (size_t)d0 * sv.SW * 32;
+    sv.acc_m += (size_t)d0 * sv.SW * 32;
+    sv.arrive_e += (size_t)d0 * sv.SW;
+    sv.arrive_m += (size_t)d0 * sv.SW;
+    return sv;
+}
+
+static pp_status swords_transpose(pp_sim *s, Ctx &c, bool want_mags) {
+    const ModelView &m = c.m;
+    const SWordsView sv = swords_view(s, c);
+    swords_transpose_kernel<<<dim3((unsigned)(m.D * sv.SW), blocks_for(m.N / 32, SW_THREADS)), SW_THREADS, 0, c.stream>>>(m, sv, want_mags ? 1 : 0);
+    s->launches++;
+    s->sw_tbits_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    return PP_OK;
+}
+
+// n_sweeps colour-pass pairs; the last colour pass also delivers the energies when they are wanted (n_sweeps == 0: the bond sums of
+// the last colour's sites without an update); magnetisations come with the transposed view
+static pp_status launch_swords(pp_sim *s, Ctx &c, const ModelView &m, int sweep_mode, uint32_t sweep_index, int n_sweeps, int exact_log,
+                               bool want_energy, bool want_mags) {
+    RowsView v = s->rv;
+    v.keys = s->d_keys + (c.m.sample_offset - s->mv.sample_offset);
+    const SWordsView sv = swords_view(s, c);
+    const dim3 grid((unsigned)(m.D * sv.SW), blocks_for(m.N / 2, SW_THREADS * SW_SPT));
+    const bool gibbs = sweep_mode == PP_SWEEP_GIBBS;
+#define PP_SW5(Z_, G_, U_, E_, X_) swords_sweep_kernel<Z_, G_, U_, E_, X_><<<grid, SW_THREADS, 0, c.stream>>>(m, v, sv, col, sweep_index + (uint32_t)sw)
+#define PP_SW4(Z_, G_, U_, E_) do { if (exact_log) PP_SW5(Z_, G_, U_, E_, true); else PP_SW5(Z_, G_, U_, E_, false); } while (0)
+#define PP_SW3(Z_, G_) do { if (!update) PP_SW5(Z_, false, false, true, false); else if (eacc) PP_SW4(Z_, G_, true, true); else PP_SW4(Z_, G_, true, false); } while (0)
+#define PP_SW2(Z_) do { if (gibbs) PP_SW3(Z_, true); else PP_SW3(Z_, false); } while (0)
+    for (int sw = 0; sw < std::max(n_sweeps, 1); sw++)
+        for (int col = 0; col < 2; col++) {
+            const bool update = n_sweeps > 0;
+            const bool eacc = want_energy && sw == std::max(n_sweeps, 1) - 1 && col == 1;
+            if (!update && !eacc) continue;
+            if (m.z == 2) PP_SW2(2); else PP_SW2(3);
+            s->launches++;
+        }
+#undef PP_SW5
+#undef PP_SW4
+#undef PP_SW3
+#undef PP_SW2
+    if (n_sweeps > 0) s->sw_tbits_valid = false;
+    CUDA_TRY(cudaGetLastError());
+    if (want_mags) return swords_transpose(s, c, true);
+    return PP_OK;
+}
+
 // want_overlap / want_fold: the caller wants the replica-pair dots of the post-sweep state / the recorded-sweep fold;
 // *fused is set when the sweep kernel did both itself (msc3d epilogue), otherwise the caller launches
 // launch_overlap() and fold_kernel.
@@ -880,6 +957,11 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
     if (n_sweeps > 0) prof_mark(s, c.stream);
     if (s->prows) {  // every sweep of the batch in one launch, the system in shared memory; energies out of the same launch
         pp_status st = launch_prows(s, c, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags);
+        if (n_sweeps > 0) prof_mark(s, c.stream);
+        return st;
+    }
+    if (s->swords) {
+        pp_status st = launch_swords(s, c, m, sweep_mode, sweep_index, n_sweeps, exact_log, want_energy, want_mags);
         if (n_sweeps > 0) prof_mark(s, c.stream);
         return st;
     }
@@ -945,6 +1027,7 @@ static pp_status launch_energy(pp_sim *s, Ctx &c, bool want_mags) {
     if (s->layout == PP_LAYOUT_SLAB) return slab_energy(s, m, c.stream, want_mags);
     const unsigned grid = (unsigned)(m.D * m.S);
     if (s->prows) return launch_prows(s, c, m, PP_SWEEP_METROPOLIS, 0u, 0, true, want_mags);
+    if (s->swords) return launch_swords(s, c, m, PP_SWEEP_METROPOLIS, 0u, 0, 0, true, want_mags);
     if (s->rows) {
         const dim3 g2(grid, (unsigned)(m.coupling_class == COUP_F32 ? 1 : s->rows_nb));
 #define PP_RE(C_, Z_) rows_energy_kernel<C_, Z_><<<g2, 256, 0, c.stream>>>(m, s->rv, want_mags, s->d_rows_acc, s->d_rows_arrive)
@@ -986,6 +1069,20 @@ static pp_status launch_overlap(pp_sim *s, Ctx &c, bool fold_too = false, bool *
         return PP_OK;
     }
     if (m.P == 0) return PP_OK;
+    if (s->swords) {
+        if (!s->sw_tbits_valid) {
+            pp_status st = swords_transpose(s, c, false);
+            if (st != PP_OK) return st;
+        }
+        const SWordsView sv = swords_view(s, c);
+        const unsigned grid = (unsigned)(m.D * m.P * m.T);
+        const size_t smem = (size_t)(m.N / 32) * sizeof(uint32_t);
+        if (m.z == 2) swords_overlap_kernel<2><<<grid, 256, smem, c.stream>>>(m, s->rv, sv, c.dot_spin, c.dot_link);
+        else swords_overlap_kernel<3><<<grid, 256, smem, c.stream>>>(m, s->rv, sv, c.dot_spin, c.dot_link);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return PP_OK;
+    }
     if (s->layout == PP_LAYOUT_MSC && s->msc3d) {
         m.lut = s->d_lut_metro;
         return launch_msc3d(s, c, m, PP_SWEEP_METROPOLIS, 0, 0, false, false, true, false);
@@ -1095,8 +1192,8 @@ static pp_status do_reset(pp_sim *s, uint64_t seed) {
     } else {
         dim3 grid((unsigned)DS, blocks_for((m.N + 3) / 4, 128));
         init_spins_int8_kernel<<<grid, 128, 0, s->stream>>>(m);
-        if (s->prows) {  // the same site-indexed INIT draws as every layout, then one bit per spin
-            pp_status stp = prows_sync(s, s->stream, 0);
+        if (s->prows || s->swords) {  // the same site-indexed INIT draws as every layout, then one bit per spin
+            pp_status stp = view_sync(s, s->stream, 0);
             if (stp != PP_OK) return stp;
         }
     }
@@ -1433,6 +1530,38 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                     s->pv.W = (int)W;
                     s->pv.sys_words = sys_words;
                     CREATE_TRY(pool_alloc(s, (void **)&s->pv.words, sizeof(uint32_t) * (size_t)(m.D * m.S * sys_words)));
+                }
+            }
+            // fp32 couplings: the same site of 32 systems of a realization in one word (pp_kernels_swords.cuh)
+            {
+                bool dl_ok = true;
+                for (int k = 0; k < z; k++) dl_ok = dl_ok && std::abs(rp.dl[(size_t)k]) <= 1;
+                float jmax = 0.0f;
+                if (m.coupling_class == COUP_F32 && desc->couplings)
+                    for (int64_t i = 0; i < n_coup; i++) jmax = std::max(jmax, std::fabs(desc->couplings[i]));
+                s->swords = m.coupling_class == COUP_F32 && desc->couplings && s->plan.n_colours == 2 && rp.m_half == 1 && rp.L % 32 == 0 &&
+                            dl_ok && (z == 2 || z == 3) && m.S >= 16 && sys_ranks == 1 && std::isfinite(jmax) && jmax > 0.0f &&
+                            N / 8 <= 160 * 1024 && N < (int64_t(1) << 31);
+                if (const char *e = getenv("PP_SYS_WORDS")) s->swords = s->swords && atoi(e) != 0;
+                if (s->swords) {
+                    SWordsView &sv = s->swv;
+                    sv.SW = (m.S + 31) / 32;
+                    // fixed-point unit of the in-sweep bond sums: |s h| * escale stays below 2^21 (the 1.5 * 2^23 rounding addend holds
+                    // 2^22, a thread adds SW_SPT terms and a warp 32 threads into 32-bit integers)
+                    sv.escale = std::ldexp(1.0f, std::min(30, (int)std::floor(std::log2(std::ldexp(1.0, 21) / (2.0 * z * (double)jmax)))));
+                    const size_t n_acc = (size_t)m.D * (size_t)sv.SW;
+                    auto take = [&](void **p, size_t bytes, bool zero) -> cudaError_t {
+                        cudaError_t e = pool_alloc(s, p, bytes);
+                        if (e != cudaSuccess) return e;
+                        s->rows_bufs.push_back(*p);
+                        return zero ? cudaMemsetAsync(*p, 0, bytes, s->stream) : cudaSuccess;
+                    };
+                    CREATE_TRY(take((void **)&sv.words, sizeof(uint32_t) * n_acc * (size_t)N, true));
+                    CREATE_TRY(take((void **)&sv.tbits, sizeof(uint32_t) * (size_t)m.D * (size_t)m.S * (size_t)(N / 32), false));
+                    CREATE_TRY(take((void **)&sv.acc_e, sizeof(long long) * n_acc * 32, true));
+                    CREATE_TRY(take((void **)&sv.acc_m, sizeof(long long) * n_acc * 32, true));
+                    CREATE_TRY(take((void **)&sv.arrive_e, sizeof(unsigned int) * n_acc, true));
+                    CREATE_TRY(take((void **)&sv.arrive_m, sizeof(unsigned int) * n_acc, true));
                 }
             }
         }
@@ -2095,13 +2224,13 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     if (st != PP_OK) return st;
                 }
                 if (fk_this) {  // after the sweep, before the measurements (mod.rs:457-470)
-                    if (s->prows && (st = prows_sync(s, c.stream, 1)) != PP_OK) return st;  // the cluster kernels work on the int8 view
+                    if ((st = view_sync(s, c.stream, 1)) != PP_OK) return st;  // the cluster kernels work on the int8 view
                     fk_cluster_kernel<<<(unsigned)(c.m.D * c.m.S), FK_THREADS, fk_smem, c.stream>>>(
                         c.m, d_fk_count, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0,
                         fk_smem_sites, d_fk_lab, d_fk_bm);
                     s->launches++;
                     CUDA_TRY(cudaGetLastError());
-                    if (s->prows && (st = prows_sync(s, c.stream, 0)) != PP_OK) return st;
+                    if ((st = view_sync(s, c.stream, 0)) != PP_OK) return st;
                     if (energy_this) {
                         st = launch_energy(s, c, stp.record);
                         if (st != PP_OK) return st;
@@ -2152,11 +2281,11 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                         else if (c.m.z == 2) msc_houdayer_kernel<2><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
                         else msc_houdayer_kernel<0><<<oc_grid, OC_THREADS, oc_msc_smem, c.stream>>>(c.m, s->d_nbr16, s->d_site16, oc_sweep, c.m.sample_offset / 32);
                     } else {
-                        if (s->prows && (st = prows_sync(s, c.stream, 1)) != PP_OK) return st;
+                        if ((st = view_sync(s, c.stream, 1)) != PP_OK) return st;
                         houdayer_kernel<<<(unsigned)(c.m.D * c.m.T * c.m.P), FK_THREADS, fk_smem, c.stream>>>(
                             c.m, stp.sweep_index + (uint32_t)stp.batch - 1u, cfg->overlap_cluster_mode == PP_CLUSTER_WOLFF ? 1 : 0, fk_smem_sites,
                             d_fk_lab, d_fk_bm);
-                        if (s->prows && (st = prows_sync(s, c.stream, 0)) != PP_OK) return st;
+                        if ((st = view_sync(s, c.stream, 0)) != PP_OK) return st;
                     }
                     s->launches++;
                     CUDA_TRY(cudaGetLastError());
@@ -2270,8 +2399,8 @@ extern "C" pp_status pp_get_spins(pp_sim *s, int64_t r, int8_t *out) {
         CUDA_TRY(cudaMemcpy(out, tmp, n, cudaMemcpyDeviceToHost));
         pool_free(s, tmp);
     } else {
-        if (s->prows) {
-            pp_status st = prows_sync(s, s->stream, 1);
+        if (s->prows || s->swords) {
+            pp_status st = view_sync(s, s->stream, 1);
             if (st != PP_OK) return st;
         }
         CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -2303,14 +2432,14 @@ extern "C" pp_status pp_set_spins(pp_sim *s, int64_t r, const int8_t *spins) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         pool_free(s, tmp);
     } else {
-        if (s->prows) {  // the int8 view of the other realizations must be current before everything is packed again
-            pp_status st = prows_sync(s, s->stream, 1);
+        if (s->prows || s->swords) {  // the int8 view of the other realizations must be current before everything is packed again
+            pp_status st = view_sync(s, s->stream, 1);
             if (st != PP_OK) return st;
             CUDA_TRY(cudaStreamSynchronize(s->stream));
         }
         CUDA_TRY(cudaMemcpy(m.spins + (size_t)r * n, spins, n, cudaMemcpyHostToDevice));
-        if (s->prows) {
-            pp_status st = prows_sync(s, s->stream, 0);
+        if (s->prows || s->swords) {
+            pp_status st = view_sync(s, s->stream, 0);
             if (st != PP_OK) return st;
             CUDA_TRY(cudaStreamSynchronize(s->stream));
         }

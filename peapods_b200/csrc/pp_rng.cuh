@@ -33,6 +33,7 @@ constexpr uint32_t TAG_SWEEP = 0x00020000u;
 constexpr uint32_t TAG_PT = 0x00030000u;
 constexpr uint32_t TAG_SWEEP_MSC = 0x00040000u;
 constexpr uint32_t TAG_SWEEP_PACKED = 0x000A0000u;  // counter = {rank >> 5, sweep, system, tag | call << 8 | colour}, call = 0..5
+constexpr uint32_t TAG_SWEEP_SYSQ = 0x000B0000u;    // counter = {colour rank, sweep, system >> 2, tag | colour}; system s draws out[s & 3] >> 8
 constexpr uint64_t MSC_KEY_DOMAIN = 0x6D73635F67726F75ull;
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u;

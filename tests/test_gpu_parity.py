@@ -38,7 +38,9 @@ def make_pair(oracle, shape, kind, temps, R, D, offsets=None, layout="int8", see
     gpu = pb.IsingSimulation(list(shape), J, temps, R, offsets, seed, layout=layout)
     assert gpu.layout == layout
     # ferromagnets whose rows split into 64-site word pairs are kept as one bit per spin and draw through the packed mapping
-    mode = oracle.RNG_PHILOX_MSC if layout == "msc" else oracle.RNG_PHILOX_PACKED if gpu.rows_packed else oracle.RNG_PHILOX
+    # fp32 couplings with >= 16 systems on rows of 32 k sites keep the same site of 32 systems in one word (system-quad mapping)
+    mode = (oracle.RNG_PHILOX_MSC if layout == "msc" else oracle.RNG_PHILOX_PACKED if gpu.rows_packed
+            else oracle.RNG_PHILOX_SYSQ if gpu.sys_words else oracle.RNG_PHILOX)
     cpu = oracle.Sim(shape, J, temps, n_replicas=R, offsets=offsets, seed=seed, rng_mode=mode, colour=colour)
     return gpu, cpu
 
@@ -267,6 +269,90 @@ def test_gaussian_couplings_exact_log_spins_and_energy_tolerance(oracle, shape, 
             assert np.array_equal(rg[k], rc[k]), k
         np.testing.assert_allclose(rg["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(rg["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
+
+
+SYS_WORD_CASES = [
+    # shape, offsets, temps, R, D: fp32 couplings, two colours, rows of 32 k sites, >= 16 systems per realization
+    ((4, 4, 32), None, np.linspace(0.8, 1.8, 4), 4, 2),       # 16 systems: half a word
+    ((2, 6, 32), None, np.linspace(0.8, 1.8, 5), 4, 1),       # 20 systems, L0 = 2 (forward == backward neighbour row)
+    ((4, 32), None, np.linspace(0.7, 2.4, 9), 4, 3),          # 2-D, 36 systems: one full word + four lanes of a second
+    ((4, 2, 64), None, np.linspace(0.8, 1.8, 8), 4, 1),       # rows of two words, exactly one word of systems
+    ((6, 4, 32), None, np.linspace(0.8, 1.8, 11), 6, 2),      # 66 systems: three word slabs, three replica pairs
+]
+
+
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+@pytest.mark.parametrize("shape,offsets,temps,R,D", SYS_WORD_CASES)
+def test_sys_word_trajectory_exact_log_spins_and_energy_tolerance(oracle, shape, offsets, temps, R, D, mode):
+    """fp32 couplings with the same site of 32 systems in one word (pp_kernels_swords.cuh) against the oracle in the system-quad
+    draw mapping: spins, magnetisation and overlap observables bit for bit, f32 energies within 1e-5 relative."""
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, R, D, offsets)
+    assert gpu.sys_words
+    assert_state_equal(gpu, cpu, D)  # INIT domain through the pack / unpack of the int8 view
+    lat = oracle.Lattice(shape, offsets)
+    J = couplings("gaussian", shape, len(shape), D, 7).reshape((D, -1))
+    for n_sweeps in (1, 2, 13):
+        rg = gpu.sample(n_sweeps, mode, warmup_ratio=0.25, exact_log=True)
+        rc = cpu.sample(n_sweeps, mode, warmup_ratio=0.25)
+        assert_state_equal(gpu, cpu, D)
+        e_g, m_g = gpu.op_energies_mags()
+        ds, dl = gpu.op_overlap()
+        T = len(temps)
+        for d in range(D):
+            sp = cpu.spins(d).reshape(-1, lat.n_spins)
+            e_c, m_c = lat.energies_mags(sp, J[d])
+            np.testing.assert_allclose(e_g[d], e_c, rtol=1e-5, atol=1e-6)
+            assert np.array_equal(m_g[d], m_c)
+            ids = cpu.system_ids(d)
+            for p in range(R // 2):
+                for t in range(T):
+                    assert (ds[d, p, t], dl[d, p, t]) == lat.overlap_dots(sp[ids[(2 * p) * T + t]], sp[ids[(2 * p + 1) * T + t]])
+        for k in ("mags", "mags2", "mags4", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2", "link_overlap4"):
+            assert np.array_equal(rg[k], rc[k]), k
+        assert np.array_equal(np.stack(rg["overlap_histogram"]), np.asarray(rc["overlap_histogram"]))
+        np.testing.assert_allclose(rg["energies"], rc["energies"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(rg["energies2"], rc["energies2"], rtol=2e-5, atol=1e-7)
+
+
+def test_sys_word_set_spins_round_trip_and_cluster_moves(oracle):
+    """the int8 view of a system-word handle: set_spins / get_spins round trip, energies of a given configuration, and a
+    Houdayer move through the view equal to the oracle's."""
+    shape, temps, R, D = (4, 4, 32), np.linspace(0.9, 1.8, 4), 4, 2
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, R, D)
+    assert gpu.sys_words
+    lat = oracle.Lattice(shape)
+    J = couplings("gaussian", shape, 3, D, 7).reshape((D, -1))
+    rng = np.random.default_rng(3)
+    S = R * len(temps)
+    spins = (2 * rng.integers(0, 2, size=(D, S, lat.n_spins)) - 1).astype(np.int8)
+    for d in range(D):
+        gpu.set_spins(spins[d], d)
+    for d in range(D):
+        assert np.array_equal(gpu.get_spins(d).reshape(S, -1), spins[d])
+    e_g, m_g = gpu.op_energies_mags()
+    for d in range(D):
+        e_c, m_c = lat.energies_mags(spins[d], J[d])
+        np.testing.assert_allclose(e_g[d], e_c, rtol=1e-5, atol=1e-6)
+        assert np.array_equal(m_g[d], m_c)
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, R, D)
+    kw = dict(warmup_ratio=0.25, overlap_cluster_update_interval=2, overlap_cluster_mode="wolff")
+    rg = gpu.sample(9, "metropolis", exact_log=True, **kw)
+    rc = cpu.sample(9, "metropolis", **kw)
+    assert_state_equal(gpu, cpu, D)
+    for k in ("mags2", "overlap2", "link_overlap"):
+        assert np.array_equal(rg[k], rc[k]), k
+
+
+def test_sys_word_device_log_agrees_statistically(oracle):
+    # production mode (hardware log2): trajectories may differ from the host-libm tables in rare last-ulp cases, observables must not
+    shape, temps = (4, 4, 32), np.linspace(0.9, 1.8, 4)
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, 4, 4)
+    assert gpu.sys_words
+    for mode in ("metropolis", "gibbs"):
+        rg = gpu.sample(400, mode, exact_log=False, pt_interval=1)
+        rc = cpu.sample(400, mode, pt_interval=1)
+        np.testing.assert_allclose(rg["energies"], rc["energies"], atol=0.02)
+        np.testing.assert_allclose(rg["overlap2"], rc["overlap2"], atol=0.05)
 
 
 def gpu_couplings(shape, offsets, D):
@@ -809,7 +895,8 @@ def test_config4_full_size_gaussian_properties_and_oracle_checked_shard(oracle):
     np.testing.assert_allclose(part.last_per_sample_means[:, 3:5], means[:sub, 3:5], rtol=2e-5, atol=1e-7)
 
     colour, _ = pb.colouring(shape, None)
-    cpu = oracle.Sim(shape, J[:sub], temps, n_replicas=R, offsets=None, seed=77, rng_mode=oracle.RNG_PHILOX, colour=colour)
+    assert full.sys_words and part.sys_words  # the same site of 32 systems per word (pp_kernels_swords.cuh)
+    cpu = oracle.Sim(shape, J[:sub], temps, n_replicas=R, offsets=None, seed=77, rng_mode=oracle.RNG_PHILOX_SYSQ, colour=colour)
     rc = cpu.sample(n_sweeps, "metropolis", warmup_ratio=0.25)
     assert_state_equal(part, cpu, sub)
     for k in ("mags", "mags2", "mags4", "overlap", "overlap2", "overlap4", "link_overlap", "link_overlap2", "link_overlap4"):

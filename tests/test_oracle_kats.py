@@ -53,6 +53,46 @@ def test_packed_draws_use_every_bit_of_six_calls_once(oracle):
     assert sum(bin(d).count("1") for d in got) == bits.count("1")  # a permutation of the 768 generated bits
 
 
+def test_system_quad_mapping_one_call_serves_four_systems_at_a_site(oracle):
+    """RNG-SPEC system-quad mapping (kernels that keep the same site of 32 systems in one word): counter = {colour rank, sweep,
+    system >> 2, tag | colour}, system s draws out[s & 3] >> 8.  A Metropolis sweep of the oracle in that mode equals a replay of
+    the log-form rule (sweep.rs:35-48, 247-257) in numpy f32 with draws taken straight from the generator."""
+    shape, S, sweep = (4, 6), 7, 5
+    lat = oracle.Lattice(shape)
+    N, z = lat.n_spins, 2
+    rng = np.random.default_rng(2)
+    J = rng.standard_normal((N, z)).astype(np.float32)
+    temps = np.linspace(0.7, 2.0, S).astype(np.float32)
+    ids = rng.permutation(S).astype(np.int64)
+    colour = (np.indices(shape).sum(axis=0) % 2).astype(np.uint16).reshape(-1)
+    key = 0x0123456789ABCDEF
+    spins = (2 * rng.integers(0, 2, size=(S, N)) - 1).astype(np.int8)
+    got = spins.copy()
+    lat.sweep_philox(got, J, temps, ids, colour, key, sweep, oracle.SWEEP_METROPOLIS, use_lookup=False, stream_is_slot=4)
+    want = spins.copy()
+    rank = np.zeros(N, np.int64)
+    for c in range(2):
+        rank[colour == c] = np.arange(int((colour == c).sum()))
+    for slot in range(S):
+        sys, s = int(ids[slot]), want[int(ids[slot])]
+        for c in range(2):
+            for i in np.flatnonzero(colour == c):
+                h = np.float32(0.0)
+                for d in range(z):  # sweep.rs:10-17: forward then backward, f32
+                    h = np.float32(h + np.float32(s[lat.fwd(i, d)]) * J[i, d])
+                    jb = lat.bwd(i, d)
+                    h = np.float32(h + np.float32(s[jb]) * J[jb, d])
+                out = oracle.philox4x32([int(rank[i]), sweep, sys >> 2, oracle.TAG_SWEEP_SYSQ | c], [key & 0xFFFFFFFF, key >> 32])
+                u = np.float32(int(out[sys & 3]) >> 8) / np.float32(1 << 24)
+                ec = np.float32(-np.float32(s[i]) * h)
+                with np.errstate(divide="ignore"):
+                    thr = np.float32(temps[slot] / np.float32(2.0)) * np.log(u, dtype=np.float32)
+                if ec >= thr:
+                    s[i] = -s[i]
+    assert np.array_equal(got, want)
+    assert not np.array_equal(got, spins)
+
+
 def test_draw24_serves_four_indices_per_call(oracle):
     key = 0x0123456789ABCDEF
     out = oracle.philox4x32([5, 7, 9, oracle.TAG_SWEEP | 1], [key & 0xFFFFFFFF, key >> 32])
