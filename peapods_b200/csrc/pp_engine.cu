@@ -866,6 +866,7 @@ static SWordsView swords_view(pp_sim *s, const Ctx &c) {
     sv.acc_m += (size_t)d0 * sv.SW * 32;
     sv.arrive_e += (size_t)d0 * sv.SW;
     sv.arrive_m += (size_t)d0 * sv.SW;
+    sv.lane_t += (size_t)d0 * sv.SW * 32;
     return sv;
 }
 
@@ -888,6 +889,10 @@ static pp_status launch_swords(pp_sim *s, Ctx &c, const ModelView &m, int sweep_
     const SWordsView sv = swords_view(s, c);
     const dim3 grid((unsigned)(m.D * sv.SW), blocks_for(m.N / 2, SW_THREADS * SW_SPT));
     const bool gibbs = sweep_mode == PP_SWEEP_GIBBS;
+    if (n_sweeps > 0) {  // system_ids only change between launch sequences (parallel tempering, set_system_ids)
+        swords_lane_temps_kernel<<<blocks_for(m.D * m.S, 256), 256, 0, c.stream>>>(m, sv);
+        s->launches++;
+    }
 #define PP_SW5(Z_, G_, U_, E_, X_) swords_sweep_kernel<Z_, G_, U_, E_, X_><<<grid, SW_THREADS, 0, c.stream>>>(m, v, sv, col, sweep_index + (uint32_t)sw)
 #define PP_SW4(Z_, G_, U_, E_) do { if (exact_log) PP_SW5(Z_, G_, U_, E_, true); else PP_SW5(Z_, G_, U_, E_, false); } while (0)
 #define PP_SW3(Z_, G_) do { if (!update) PP_SW5(Z_, false, false, true, false); else if (eacc) PP_SW4(Z_, G_, true, true); else PP_SW4(Z_, G_, true, false); } while (0)
@@ -1075,10 +1080,16 @@ static pp_status launch_overlap(pp_sim *s, Ctx &c, bool fold_too = false, bool *
             if (st != PP_OK) return st;
         }
         const SWordsView sv = swords_view(s, c);
-        const unsigned grid = (unsigned)(m.D * m.P * m.T);
-        const size_t smem = (size_t)(m.N / 32) * sizeof(uint32_t);
-        if (m.z == 2) swords_overlap_kernel<2><<<grid, 256, smem, c.stream>>>(m, s->rv, sv, c.dot_spin, c.dot_link);
-        else swords_overlap_kernel<3><<<grid, 256, smem, c.stream>>>(m, s->rv, sv, c.dot_spin, c.dot_link);
+        const size_t per_warp = (size_t)(m.N / 32) * sizeof(uint32_t);
+        const int wpc = (int)std::max<size_t>(1, std::min<size_t>(8, (160 * 1024) / per_warp));  // warps (= pairs) per CTA
+        const unsigned grid = blocks_for(m.D * m.P * m.T, wpc);
+        const size_t smem = per_warp * (size_t)wpc;
+        if (smem > 48 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(swords_overlap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(swords_overlap_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
+        if (m.z == 2) swords_overlap_kernel<2><<<grid, 32 * wpc, smem, c.stream>>>(m, s->rv, sv, c.dot_spin, c.dot_link);
+        else swords_overlap_kernel<3><<<grid, 32 * wpc, smem, c.stream>>>(m, s->rv, sv, c.dot_spin, c.dot_link);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
         return PP_OK;
@@ -1541,7 +1552,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                     for (int64_t i = 0; i < n_coup; i++) jmax = std::max(jmax, std::fabs(desc->couplings[i]));
                 s->swords = m.coupling_class == COUP_F32 && desc->couplings && s->plan.n_colours == 2 && rp.m_half == 1 && rp.L % 32 == 0 &&
                             dl_ok && (z == 2 || z == 3) && m.S >= 16 && sys_ranks == 1 && std::isfinite(jmax) && jmax > 0.0f &&
-                            N / 8 <= 160 * 1024 && N < (int64_t(1) << 31);
+                            N / 8 <= 160 * 1024 && N < (int64_t(1) << 28);
                 if (const char *e = getenv("PP_SYS_WORDS")) s->swords = s->swords && atoi(e) != 0;
                 if (s->swords) {
                     SWordsView &sv = s->swv;
@@ -1562,6 +1573,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                     CREATE_TRY(take((void **)&sv.acc_m, sizeof(long long) * n_acc * 32, true));
                     CREATE_TRY(take((void **)&sv.arrive_e, sizeof(unsigned int) * n_acc, true));
                     CREATE_TRY(take((void **)&sv.arrive_m, sizeof(unsigned int) * n_acc, true));
+                    CREATE_TRY(take((void **)&sv.lane_t, sizeof(float4) * n_acc * 32, true));
                 }
             }
         }

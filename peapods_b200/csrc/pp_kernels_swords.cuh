@@ -15,8 +15,8 @@
 // rebuilds the lane -> temperature map of its word from system_ids at the start of every launch.
 //
 // Energies (needed by every exchange): the colour-1 pass of a two-colour lattice touches every bond exactly once, so it also adds up
-// s_i h_i after the update per lane (energy.rs:99-108) — as integers in units of 1 / escale (a power of two; round-to-nearest through
-// the 1.5 * 2^23 addend, the sum is then independent of the order of addition).  Magnetisations and replica overlaps work on a
+// s_i h_i after the update per lane (energy.rs:99-108): a thread adds its SW_SPT sites in f32 in a fixed order, rounds the sum to an
+// integer number of 1 / escale (a power of two) and everything above a thread is integer addition, independent of its order.  Magnetisations and replica overlaps work on a
 // TRANSPOSED view produced on recorded sweeps (swords_transpose_kernel: 32 x 32 bit transposes in registers -> `tbits[D][S][N / 32]`,
 // one bit per spin, system-major), where a replica pair's q and q_link are XORs and popcounts of whole row words
 // (overlap.rs:259-281).  The int8 array stays as a scratch VIEW for get_spins / set_spins / the cluster moves.
@@ -35,13 +35,22 @@ struct SWordsView {
     long long *acc_m;         // [D][SW][32] down-spin counts (kept zero between launches)
     unsigned int *arrive_e;   // [D][SW]
     unsigned int *arrive_m;   // [D][SW]
+    float4 *lane_t;           // [D][SW][32] per system: (T / 2, ln 2 * T / 2, -24 ln 2 * T / 2, 0) of the temperature it sits at
     int SW;
     float escale;
 };
 
-constexpr int SW_THREADS = 128;
+#ifndef PP_SW_THREADS
+#define PP_SW_THREADS 128
+#endif
+#ifndef PP_SW_MINB
+#define PP_SW_MINB 8   // resident blocks per SM the plain colour pass is compiled for (registers per thread follow)
+#endif
+#ifndef PP_SW_MINB_E
+#define PP_SW_MINB_E 6 // the same for the pass that also adds up the bond sums (32 more accumulators)
+#endif
+constexpr int SW_THREADS = PP_SW_THREADS;
 constexpr int SW_SPT = 4;  // sites per thread of a colour pass
-constexpr uint32_t SW_MAGIC_BITS = 0x4B400000u;  // 1.5 * 2^23: x * escale + magic has round(x * escale) in its low mantissa bits
 
 #if defined(__CUDACC__)
 
@@ -70,28 +79,21 @@ __host__ __device__ __forceinline__ void sw_transpose32(uint32_t (&a)[32]) {
 
 // One colour pass (UPDATE) and / or the bond sums of the colour's sites (EACC).  grid = (D * SW, ceil(N / 2 / (SW_THREADS * SW_SPT))).
 template <int Z, bool GIBBS, bool UPDATE, bool EACC, bool EXACT>
-__global__ void __launch_bounds__(SW_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, EACC ? PP_SW_MINB_E : PP_SW_MINB)
 swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t sweep_index) {
-    __shared__ float ht_sm[32], kt_sm[32];
+    __shared__ float ht_sm[32];
+    __shared__ float2 kt_sm[32];  // production-mode threshold of a lane: kt.x * log2(draw) + kt.y = (T / 2) ln u
     __shared__ int blk_sm[32];
     __shared__ int is_last;
     const int tid = threadIdx.x;
     const int64_t d = blockIdx.x / sv.SW;
     const int w = (int)(blockIdx.x % sv.SW);
     const int nl = min(32, m.S - 32 * w);
-    if (tid < 32) {
-        ht_sm[tid] = 1.0f;
-        kt_sm[tid] = 1.0f;
+    if (tid < 32) {  // lane -> temperature of this launch (swords_lane_temps_kernel)
+        const float4 lt = UPDATE ? sv.lane_t[((size_t)d * sv.SW + w) * 32 + tid] : make_float4(1.0f, 1.0f, -24.0f, 0.0f);
+        ht_sm[tid] = lt.x;
+        kt_sm[tid] = make_float2(lt.y, lt.z);
         blk_sm[tid] = 0;
-    }
-    __syncthreads();
-    for (int slot = tid; slot < m.S; slot += SW_THREADS) {  // lane -> temperature of this launch (parallel.rs:27-33, realization.rs:166)
-        const int sys = m.system_ids[d * m.S + slot];
-        if ((sys >> 5) == w) {
-            const float ht = __fdiv_rn(m.temps[slot % m.T], 2.0f);
-            ht_sm[sys & 31] = ht;
-            kt_sm[sys & 31] = ht * 0.693147180559945f;
-        }
     }
     __syncthreads();
     const int L = v.L, Lh = L >> 1;
@@ -103,10 +105,9 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
     const uint32_t vmask = nl == 32 ? 0xFFFFFFFFu : ((1u << nl) - 1u);
     const uint32_t tagc = TAG_SWEEP_SYSQ | (uint32_t)colour;
     const float escale = sv.escale;
-    int eacc[EACC ? 32 : 1];
+    float eacc[EACC ? 32 : 1];  // per lane: sum over this thread's sites of s h after the update
 #pragma unroll
-    for (int l = 0; l < (EACC ? 32 : 1); l++) eacc[l] = 0;
-    uint32_t nterms = 0;
+    for (int l = 0; l < (EACC ? 32 : 1); l++) eacc[l] = 0.0f;
     for (int it = 0; it < SW_SPT; it++) {
         const uint32_t c = (blockIdx.y * SW_SPT + it) * SW_THREADS + tid;  // = the site's rank inside its colour class
         if (c >= n_act) break;
@@ -130,7 +131,11 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
             Jf[kk] = J[(size_t)i * Z + kk];   // lattice.rs:4-8: bond (i, k) is stored at its lower site
             Jb[kk] = J[(size_t)jb * Z + kk];
         }
-        nterms++;
+#pragma unroll
+        for (int kk = 0; kk < Z; kk++) {  // bit l: the neighbour's spin differs from the site's own in system l
+            F[kk] ^= C;
+            B[kk] ^= C;
+        }
         uint32_t flips = 0u;
 #pragma unroll
         for (int g = 0; g < 8; g++) {
@@ -143,30 +148,33 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int l = 4 * g + q, sh = 31 - l;
-                    // sweep.rs:10-17: forward then backward per direction; the sign bit of the spin flips the coupling
-                    float h = __uint_as_float(__float_as_uint(Jf[0]) ^ ((F[0] << sh) & 0x80000000u));
-                    h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jb[0]) ^ ((B[0] << sh) & 0x80000000u)));
+                    // sweep.rs:10-17: forward then backward per direction; a product with a +-1 spin is the coupling with its sign
+                    // bit flipped.  The words were XORed with the site's own word, so the sum is s_i h (negation commutes with
+                    // every rounding of the sum): -eng_change of sweep.rs:43-44 without a per-lane sign flip of its own.
+                    float sh_ = __uint_as_float(__float_as_uint(Jf[0]) ^ ((F[0] << sh) & 0x80000000u));
+                    sh_ = __fadd_rn(sh_, __uint_as_float(__float_as_uint(Jb[0]) ^ ((B[0] << sh) & 0x80000000u)));
 #pragma unroll
                     for (int kk = 1; kk < Z; kk++) {
-                        h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jf[kk]) ^ ((F[kk] << sh) & 0x80000000u)));
-                        h = __fadd_rn(h, __uint_as_float(__float_as_uint(Jb[kk]) ^ ((B[kk] << sh) & 0x80000000u)));
+                        sh_ = __fadd_rn(sh_, __uint_as_float(__float_as_uint(Jf[kk]) ^ ((F[kk] << sh) & 0x80000000u)));
+                        sh_ = __fadd_rn(sh_, __uint_as_float(__float_as_uint(Jb[kk]) ^ ((B[kk] << sh) & 0x80000000u)));
                     }
-                    // eng_change = -s_i h (sweep.rs:43-44): h with its sign flipped when s_i = +1 (bit 0)
-                    const float ec = __uint_as_float(__float_as_uint(h) ^ ((~C << sh) & 0x80000000u));
                     bool flip = false;
                     if (UPDATE) {
                         float thr;
                         if (EXACT) {  // host-libm tables: bit-identical to a host replay
                             thr = __fmul_rn(ht_sm[l], GIBBS ? m.glogtab[dr[q]] : m.logtab[dr[q]]);
                         } else {      // ln u = ln 2 * (log2(draw) - 24); Gibbs: ln(u / (1 - u)) = ln 2 * (log2(draw) - log2(2^24 - draw))
+                            const float2 kt = kt_sm[l];
                             const float a = sw_lg2((float)dr[q]);
-                            const float b = GIBBS ? sw_lg2((float)(16777216u - dr[q])) : 24.0f;
-                            thr = kt_sm[l] * (a - b);
+                            thr = GIBBS ? kt.x * (a - sw_lg2((float)(16777216u - dr[q]))) : fmaf(kt.x, a, kt.y);
                         }
-                        flip = ec >= thr;  // sweep.rs:256 / 279-282
+                        flip = -sh_ >= thr;  // eng_change >= (T / 2) ln u: sweep.rs:256 / 279-282
                         if (flip) flips |= 1u << l;
                     }
-                    if (EACC) eacc[l] += __float_as_int(__fmaf_rn(flip ? ec : -ec, escale, 12582912.0f));  // s h after the update
+                    if (EACC) {  // s h after the update
+                        eacc[l] += sh_;
+                        if (flip) eacc[l] = fmaf(-2.0f, sh_, eacc[l]);
+                    }
                 }
             }
         }
@@ -175,8 +183,8 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
     if (EACC) {
 #pragma unroll
         for (int l = 0; l < 32; l++) {
-            const int mine = (int)((uint32_t)eacc[l] - nterms * SW_MAGIC_BITS);
-            const int ws = __reduce_add_sync(0xFFFFFFFFu, mine);
+            // the thread's sum (fixed order) rounded to an integer number of 1 / escale: every later addition is exact
+            const int ws = __reduce_add_sync(0xFFFFFFFFu, __float2int_rn(eacc[l] * escale));
             if ((tid & 31) == l) atomicAdd(&blk_sm[l], ws);
         }
         __syncthreads();
@@ -194,6 +202,18 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
         }
         if (tid == 0) sv.arrive_e[blockIdx.x] = 0u;
     }
+}
+
+// which temperature every system sits at (parallel.rs:27-33, realization.rs:166): rebuilt from system_ids before the colour passes of
+// a launch sequence, so that a colour-pass block reads its 32 lanes' thresholds with one load.  One thread per (realization, slot).
+__global__ void __launch_bounds__(256) swords_lane_temps_kernel(ModelView m, SWordsView sv) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= m.D * m.S) return;
+    const int64_t d = idx / m.S;
+    const int slot = (int)(idx - d * m.S);
+    const int sys = m.system_ids[idx];
+    const float ht = __fdiv_rn(m.temps[slot % m.T], 2.0f), kt = ht * 0.693147180559945f;
+    sv.lane_t[(size_t)d * sv.SW * 32 + sys] = make_float4(ht, kt, -24.0f * kt, 0.0f);
 }
 
 // words -> transposed view (+ magnetisation sums).  grid = (D * SW, ceil(N / 32 / SW_THREADS)); a thread owns 32 consecutive sites.
@@ -245,12 +265,15 @@ __global__ void __launch_bounds__(SW_THREADS) swords_transpose_kernel(ModelView 
     if (tid == 0) sv.arrive_m[blockIdx.x] = 0u;
 }
 
-// replica-pair dots on the transposed view (overlap.rs:259-281).  grid = D * P * T, one CTA per pair, dynamic smem = N / 8 bytes
+// replica-pair dots on the transposed view (overlap.rs:259-281).  One WARP per pair (d, p, t): the XOR of the two replicas' bit rows
+// goes to the warp's own shared-memory region (N / 8 bytes), then q and q_link are popcounts of whole row words against the
+// neighbour rows' words — no block-wide barrier.  grid = ceil(D * P * T / warps per CTA), dynamic smem = warps * N / 8 bytes.
 template <int Z>
 __global__ void __launch_bounds__(256) swords_overlap_kernel(ModelView m, RowsView v, SWordsView sv, long long *dot_spin, long long *dot_link) {
-    extern __shared__ uint32_t sw_x_sm[];  // [N / 32] bit = 1 where the two replicas differ
-    __shared__ long long sh[32];
-    const int64_t idx = blockIdx.x;  // (d * P + p) * T + t
+    extern __shared__ uint32_t sw_x_sm[];  // [warps][N / 32] bit = 1 where the two replicas differ
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * wpc + wid;  // (d * P + p) * T + t
+    if (idx >= m.D * m.P * m.T) return;
     const int t = (int)(idx % m.T);
     const int p = (int)((idx / m.T) % m.P);
     const int64_t d = idx / ((int64_t)m.T * m.P);
@@ -258,30 +281,31 @@ __global__ void __launch_bounds__(256) swords_overlap_kernel(ModelView m, RowsVi
     const int sb = m.system_ids[d * m.S + (2 * p + 1) * m.T + t];
     const uint32_t nq = (uint32_t)(m.N / 32);
     const uint32_t *a = sv.tbits + ((size_t)d * m.S + sa) * nq, *b = sv.tbits + ((size_t)d * m.S + sb) * nq;
-    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) sw_x_sm[q] = a[q] ^ b[q];
-    __syncthreads();
+    uint32_t *X = sw_x_sm + (size_t)wid * nq;
+    for (uint32_t q = lane; q < nq; q += 32) X[q] = a[q] ^ b[q];
+    __syncwarp();
     const int Wr = v.L / 32;  // words per row
-    long long neg_q = 0, neg_l = 0;
-    for (uint32_t q = threadIdx.x; q < nq; q += blockDim.x) {
+    int neg_q = 0, neg_l = 0;  // sites with q_i = -1, links with q_i q_j = -1 (each below 2^31: N < 2^31 / z at eligibility)
+    for (uint32_t q = lane; q < nq; q += 32) {
         const uint32_t r = q / (uint32_t)Wr;
         const int wj = (int)(q - r * (uint32_t)Wr);
-        const uint32_t X = sw_x_sm[q];
-        neg_q += __popc(X);
+        const uint32_t Xq = X[q];
+        neg_q += __popc(Xq);
 #pragma unroll
         for (int kk = 0; kk < Z; kk++) {
-            const uint32_t *row = sw_x_sm + (size_t)v.nbr_row[((size_t)r * Z + kk) * 2] * Wr;
+            const uint32_t *row = X + (size_t)v.nbr_row[((size_t)r * Z + kk) * 2] * Wr;
             const int dl = v.dl[kk];
             uint32_t Xn = row[wj];
             if (dl > 0) Xn = (Xn >> 1) | (row[wj + 1 == Wr ? 0 : wj + 1] << 31);
             else if (dl < 0) Xn = (Xn << 1) | (row[wj ? wj - 1 : Wr - 1] >> 31);
-            neg_l += __popc(X ^ Xn);
+            neg_l += __popc(Xq ^ Xn);
         }
     }
-    const long long tq = block_sum<long long>(neg_q, sh);
-    const long long tl = block_sum<long long>(neg_l, sh);
-    if (threadIdx.x == 0) {
-        dot_spin[idx] = m.N - 2 * tq;
-        dot_link[idx] = (long long)Z * m.N - 2 * tl;
+    neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
+    neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
+    if (lane == 0) {
+        dot_spin[idx] = m.N - 2ll * neg_q;
+        dot_link[idx] = (long long)Z * m.N - 2ll * neg_l;
     }
 }
 
