@@ -1557,9 +1557,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 if (s->swords) {
                     SWordsView &sv = s->swv;
                     sv.SW = (m.S + 31) / 32;
-                    // fixed-point unit of the in-sweep bond sums: |s h| * escale stays below 2^21 (the 1.5 * 2^23 rounding addend holds
-                    // 2^22, a thread adds SW_SPT terms and a warp 32 threads into 32-bit integers)
-                    sv.escale = std::ldexp(1.0f, std::min(30, (int)std::floor(std::log2(std::ldexp(1.0, 21) / (2.0 * z * (double)jmax)))));
+                    // fixed-point unit of the in-sweep bond sums: a thread's f32 sum over its SW_SPT sites, |.| <= SW_SPT * 2z' * max|J|,
+                    // is rounded to an integer number of 1 / escale; 32 threads of a warp and the warps of a block add up in 32 bits
+                    sv.escale = std::ldexp(1.0f, std::min(30, (int)std::floor(std::log2(std::ldexp(1.0, 23) / (SW_SPT * 2.0 * z * (double)jmax)))));
                     const size_t n_acc = (size_t)m.D * (size_t)sv.SW;
                     auto take = [&](void **p, size_t bytes, bool zero) -> cudaError_t {
                         cudaError_t e = pool_alloc(s, p, bytes);

@@ -50,7 +50,7 @@ struct SWordsView {
 #define PP_SW_MINB_E 6 // the same for the pass that also adds up the bond sums (32 more accumulators)
 #endif
 constexpr int SW_THREADS = PP_SW_THREADS;
-constexpr int SW_SPT = 4;  // sites per thread of a colour pass
+constexpr int SW_SPT = 8;  // sites per thread of a colour pass
 
 #if defined(__CUDACC__)
 
