@@ -432,10 +432,15 @@ def bench_small_configs():
             best, launches = (dev, model._sim.last_kernel_launches) if best is None or dev < best else (best, launches)
         attempts = float(model.n_spins) * model.n_temps * model.n_replicas * model.n_disorder * n_sweeps
         v = attempts / best / 1e6
+        sim = model._sim
+        note = ""
+        if sim.rows_packed:
+            note, b_alg = " (one bit per spin: packed rows, system resident in shared memory)", 0.25
+        elif sim.sys_words:  # fp32 couplings: 1 bit read + 1 bit written per attempt, 4 z' bytes of couplings per site shared by S systems
+            note = " (one bit per spin: the same site of 32 systems of a realization per word, couplings read once per 32 systems)"
+            b_alg = 0.25 + 4.0 * model.n_neighbors / (model.n_temps * model.n_replicas)
         out[key] = {"workload": label, "value": v, "unit": UNIT, "sweeps": n_sweeps, "ms": best, "gpu_launches": launches,
-                    "layout": model._sim.layout + (" (one bit per spin: packed rows, system resident in shared memory)" if model._sim.rows_packed else ""),
-                    "alg_bytes_per_attempt": b_alg if not model._sim.rows_packed else 0.25,
-                    "hbm_roofline_frac": v * (b_alg if not model._sim.rows_packed else 0.25) / peak}
+                    "layout": sim.layout + note, "alg_bytes_per_attempt": b_alg, "hbm_roofline_frac": v * b_alg / peak}
 
     m = pb.Ising((32, 32), "ferro", np.linspace(1.5, 3.0, 16), n_replicas=2, seed=SEED)
     run("c1", "C1: 2-D Ising ferromagnet 32x32, Metropolis + PT every sweep, 16 temps 1.5-3.0, 2 replicas, 5000 sweeps (README quickstart)",

@@ -196,7 +196,7 @@ int32_t pp_slab_packed(const pp_sim *sim);
  * (pp_kernels_prows.cuh: row-alternating colouring, last extent % 64 == 0; packed draw mapping), else 0 */
 int32_t pp_rows_packed(const pp_sim *sim);
 /* 1 when an int8-layout handle with fp32 couplings keeps the same site of 32 systems of a realization in one word, one bit per spin
- * (pp_kernels_swords.cuh: two-colour row-alternating lattice, last extent % 32 == 0, >= 16 systems; system-quad draw mapping), else 0 */
+ * (pp_kernels_swords.cuh: two-colour row-alternating lattice, last extent % 32 == 0 or 8 / 16 / 24 with N % 32 == 0, >= 16 systems; system-quad draw mapping), else 0 */
 int32_t pp_sys_words(const pp_sim *sim);
 
 /* operator-level entry points with the reference's slice semantics (unit-level parity tests):

@@ -1550,7 +1550,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 float jmax = 0.0f;
                 if (m.coupling_class == COUP_F32 && desc->couplings)
                     for (int64_t i = 0; i < n_coup; i++) jmax = std::max(jmax, std::fabs(desc->couplings[i]));
-                s->swords = m.coupling_class == COUP_F32 && desc->couplings && s->plan.n_colours == 2 && rp.m_half == 1 && rp.L % 32 == 0 &&
+                s->swords = m.coupling_class == COUP_F32 && desc->couplings && s->plan.n_colours == 2 && rp.m_half == 1 && (rp.L % 32 == 0 || (rp.L < 32 && N % 32 == 0)) &&
                             dl_ok && (z == 2 || z == 3) && m.S >= 16 && sys_ranks == 1 && std::isfinite(jmax) && jmax > 0.0f &&
                             N / 8 <= 160 * 1024 && N < (int64_t(1) << 28);
                 if (const char *e = getenv("PP_SYS_WORDS")) s->swords = s->swords && atoi(e) != 0;

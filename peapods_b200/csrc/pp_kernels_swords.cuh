@@ -21,7 +21,8 @@
 // one bit per spin, system-major), where a replica pair's q and q_link are XORs and popcounts of whole row words
 // (overlap.rs:259-281).  The int8 array stays as a scratch VIEW for get_spins / set_spins / the cluster moves.
 // Eligibility (pp_create): fp32 coupling class, two-colour row-alternating lattice (rows_plan), z' = 2 or 3, last extent a multiple
-// of 32, offsets that move by at most one site along the rows, at least 16 systems per realization.
+// of 32 or below 32 with N a multiple of 32 (8, 16, 24), offsets that move by at most one site along the rows, at least 16 systems
+// per realization.
 #pragma once
 #include "pp_device.cuh"
 #include "pp_kernels_rows.cuh"
@@ -284,21 +285,43 @@ __global__ void __launch_bounds__(256) swords_overlap_kernel(ModelView m, RowsVi
     uint32_t *X = sw_x_sm + (size_t)wid * nq;
     for (uint32_t q = lane; q < nq; q += 32) X[q] = a[q] ^ b[q];
     __syncwarp();
-    const int Wr = v.L / 32;  // words per row
-    int neg_q = 0, neg_l = 0;  // sites with q_i = -1, links with q_i q_j = -1 (each below 2^31: N < 2^31 / z at eligibility)
-    for (uint32_t q = lane; q < nq; q += 32) {
-        const uint32_t r = q / (uint32_t)Wr;
-        const int wj = (int)(q - r * (uint32_t)Wr);
-        const uint32_t Xq = X[q];
-        neg_q += __popc(Xq);
+    int neg_q = 0, neg_l = 0;  // sites with q_i = -1, links with q_i q_j = -1 (each below 2^31: N < 2^28 at eligibility)
+    if (v.L % 32 == 0) {
+        const int Wr = v.L / 32;  // words per row
+        for (uint32_t q = lane; q < nq; q += 32) {
+            const uint32_t r = q / (uint32_t)Wr;
+            const int wj = (int)(q - r * (uint32_t)Wr);
+            const uint32_t Xq = X[q];
+            neg_q += __popc(Xq);
 #pragma unroll
-        for (int kk = 0; kk < Z; kk++) {
-            const uint32_t *row = X + (size_t)v.nbr_row[((size_t)r * Z + kk) * 2] * Wr;
-            const int dl = v.dl[kk];
-            uint32_t Xn = row[wj];
-            if (dl > 0) Xn = (Xn >> 1) | (row[wj + 1 == Wr ? 0 : wj + 1] << 31);
-            else if (dl < 0) Xn = (Xn << 1) | (row[wj ? wj - 1 : Wr - 1] >> 31);
-            neg_l += __popc(Xq ^ Xn);
+            for (int kk = 0; kk < Z; kk++) {
+                const uint32_t *row = X + (size_t)v.nbr_row[((size_t)r * Z + kk) * 2] * Wr;
+                const int dl = v.dl[kk];
+                uint32_t Xn = row[wj];
+                if (dl > 0) Xn = (Xn >> 1) | (row[wj + 1 == Wr ? 0 : wj + 1] << 31);
+                else if (dl < 0) Xn = (Xn << 1) | (row[wj ? wj - 1 : Wr - 1] >> 31);
+                neg_l += __popc(Xq ^ Xn);
+            }
+        }
+    } else {  // rows shorter than a word (L = 8, 16, 24): a row is L bits starting at bit r * L, possibly across two words
+        const int L = v.L;
+        const uint32_t rmask = (1u << L) - 1u;
+        auto row_bits = [&](const uint32_t r) {
+            const uint32_t start = r * (uint32_t)L, w0 = start >> 5, sh = start & 31u;
+            const uint32_t lo = X[w0], hi = sh + (uint32_t)L > 32u ? X[w0 + 1] : 0u;
+            return __funnelshift_r(lo, hi, sh) & rmask;
+        };
+        for (uint32_t r = lane; r < (uint32_t)v.n_rows; r += 32) {
+            const uint32_t Xr = row_bits(r);
+            neg_q += __popc(Xr);
+#pragma unroll
+            for (int kk = 0; kk < Z; kk++) {
+                uint32_t Xn = row_bits(v.nbr_row[((size_t)r * Z + kk) * 2]);
+                const int dl = v.dl[kk];
+                if (dl > 0) Xn = ((Xn >> 1) | (Xn << (L - 1))) & rmask;       // site x looks at x + 1 (periodic in the row)
+                else if (dl < 0) Xn = ((Xn << 1) | (Xn >> (L - 1))) & rmask;
+                neg_l += __popc(Xr ^ Xn);
+            }
         }
     }
     neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);

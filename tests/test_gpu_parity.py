@@ -278,6 +278,10 @@ SYS_WORD_CASES = [
     ((4, 32), None, np.linspace(0.7, 2.4, 9), 4, 3),          # 2-D, 36 systems: one full word + four lanes of a second
     ((4, 2, 64), None, np.linspace(0.8, 1.8, 8), 4, 1),       # rows of two words, exactly one word of systems
     ((6, 4, 32), None, np.linspace(0.8, 1.8, 11), 6, 2),      # 66 systems: three word slabs, three replica pairs
+    ((8, 8, 8), None, np.linspace(0.8, 1.8, 8), 2, 2),        # rows of 8 sites: four rows per word of the transposed view
+    ((4, 6, 16), None, np.linspace(0.8, 1.8, 6), 4, 1),       # rows of 16 sites
+    ((4, 4, 24), None, np.linspace(0.8, 1.8, 5), 4, 1),       # rows of 24 sites straddle the words of the transposed view
+    ((12, 16), None, np.linspace(0.7, 2.4, 8), 2, 2),         # 2-D, rows of 16 sites
 ]
 
 
