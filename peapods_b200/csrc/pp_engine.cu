@@ -244,6 +244,8 @@ struct pp_sim {
     size_t resident_packed_smem = 0;
     PRowsView pv{};
     int prows_nm[2] = {0, 0};                          // thresholds compared per site: [metropolis, gibbs]
+    bool prows_cluster = false;                        // recorded sweeps folded inside the sweep kernel by clusters of R CTAs (launch_prows)
+    bool prows_bs[2] = {false, false};                 // z' = 3, all seven counts below 2^24 and growing with unsat: binary-search form
     // fp32 couplings with the same site of 32 systems in one word (pp_kernels_swords.cuh); `d_spins` is a scratch view as above
     bool swords = false;
     bool sw_tbits_valid = false;                       // the transposed view matches the words
@@ -417,6 +419,18 @@ extern "C" int32_t pp_debug_m3_clocks(unsigned long long *out, int64_t n) {  // 
     return (int32_t)cudaMemcpyFromSymbol(out, pp::pp_m3_clk, (size_t)n * sizeof(unsigned long long));
 }
 #endif
+extern "C" int32_t pp_debug_prows_clocks(unsigned long long *out, int32_t reset) {  // variant builds only (tools/c3_phases.py)
+#ifdef PP_PROWS_TIMING
+    if (reset) {
+        unsigned long long z[8] = {};
+        return cudaMemcpyToSymbol(pp::pp_prows_clk, z, sizeof(z)) == cudaSuccess ? 1 : 0;
+    }
+    return cudaMemcpyFromSymbol(out, pp::pp_prows_clk, sizeof(unsigned long long) * 8) == cudaSuccess ? 1 : 0;
+#else
+    (void)out; (void)reset;
+    return 0;
+#endif
+}
 extern "C" int32_t pp_uses_msc3d(const pp_sim *sim) { return sim && sim->msc3d ? 1 : 0; }
 extern "C" int32_t pp_slab_packed(const pp_sim *sim) { return sim && sim->slab && sim->slab->packed ? 1 : 0; }
 extern "C" int32_t pp_sys_words(const pp_sim *sim) { return sim && sim->swords ? 1 : 0; }
@@ -811,28 +825,51 @@ static pp_status prows_sync(pp_sim *s, cudaStream_t stream, int dir) {
     return PP_OK;
 }
 
+// rec_from >= 0 (cluster mode, s->prows_cluster): the sweeps sw >= rec_from of the batch are recorded inside the kernel (energies,
+// magnetisations, pair dots, fold) by thread-block clusters of R CTAs, one per temperature slot
 static pp_status launch_prows(pp_sim *s, Ctx &c, const ModelView &m_in, int sweep_mode, uint32_t sweep_index, int n_sweeps, bool want_energy,
-                              bool want_mags) {
+                              bool want_mags, int rec_from = -1) {
     ModelView m = m_in;
     m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;  // (the energy-only call comes without a table)
     RowsView v = s->rv;
     v.keys = s->d_keys + (c.m.sample_offset - s->mv.sample_offset);
     const int nm = s->prows_nm[sweep_mode == PP_SWEEP_GIBBS ? 1 : 0];
-    const size_t smem = sizeof(uint32_t) * (size_t)s->pv.sys_words;
-    const unsigned grid = (unsigned)(m.D * m.S);
-#define PP_PROWS(Z_, NM_)                                                                                                              \
+    const bool bs = m.z == 3 && nm == 7 && s->prows_bs[sweep_mode == PP_SWEEP_GIBBS ? 1 : 0];
+    PRowsCluster cl{};
+    cl.on = rec_from >= 0 ? 1 : 0;
+    cl.rec_from = rec_from >= 0 ? rec_from : 0x7FFFFFFF;
+    cl.st = c.st;
+    cl.dot_spin = c.dot_spin;
+    cl.dot_link = c.dot_link;
+    size_t smem = sizeof(uint32_t) * (size_t)s->pv.sys_words * (cl.on ? 2 : 1);
+    const size_t tab_bytes = (size_t)s->rv.n_rows * (2 * (size_t)m.z + 2) * sizeof(uint32_t) + (((size_t)s->rv.n_rows + 15) & ~size_t(15));
+    cl.stage_tables = tab_bytes <= 64 * 1024 && smem + tab_bytes <= 200 * 1024 ? 1 : 0;
+    if (cl.stage_tables) smem += tab_bytes;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(m.D * m.S));
+    cfg.blockDim = dim3(PROWS_SWEEP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)m.R;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl.on ? 1 : 0;
+    const int we = want_energy ? 1 : 0, wm = want_mags ? 1 : 0;
+#define PP_PROWS(Z_, NM_, BS_)                                                                                                         \
     do {                                                                                                                               \
         static bool configured = false;                                                                                                \
         if (!configured) {                                                                                                             \
-            CUDA_TRY(cudaFuncSetAttribute(prows_sweep_kernel<Z_, NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       \
+            CUDA_TRY(cudaFuncSetAttribute(prows_sweep_kernel<Z_, NM_, BS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  \
             configured = true;                                                                                                         \
         }                                                                                                                              \
-        prows_sweep_kernel<Z_, NM_><<<grid, PROWS_THREADS, smem, c.stream>>>(m, v, s->pv, sweep_index, n_sweeps, want_energy ? 1 : 0,  \
-                                                                             want_mags ? 1 : 0);                                       \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, prows_sweep_kernel<Z_, NM_, BS_>, m, v, s->pv, sweep_index, n_sweeps, we, wm, cl));           \
     } while (0)
-    if (m.z == 2) { if (nm == 2) PP_PROWS(2, 2); else PP_PROWS(2, 5); }
-    else if (m.z == 3) { if (nm == 3) PP_PROWS(3, 3); else PP_PROWS(3, 7); }
-    else { if (nm == 4) PP_PROWS(4, 4); else PP_PROWS(4, 9); }
+    if (m.z == 2) { if (nm == 2) PP_PROWS(2, 2, false); else PP_PROWS(2, 5, false); }
+    else if (m.z == 3) { if (nm == 3) PP_PROWS(3, 3, false); else if (bs) PP_PROWS(3, 7, true); else PP_PROWS(3, 7, false); }
+    else { if (nm == 4) PP_PROWS(4, 4, false); else PP_PROWS(4, 9, false); }
 #undef PP_PROWS
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -920,7 +957,7 @@ static pp_status launch_swords(pp_sim *s, Ctx &c, const ModelView &m, int sweep_
 // launch_overlap() and fold_kernel.
 static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep_index, int n_sweeps, int exact_log,
                                bool want_energy, bool want_mags, bool want_overlap = false, bool want_fold = false,
-                               bool *fused = nullptr) {
+                               bool *fused = nullptr, int rec_from = -1) {
     ModelView m = c.m;
     m.lut = sweep_mode == PP_SWEEP_GIBBS ? s->d_lut_gibbs : s->d_lut_metro;
     if (fused) *fused = false;
@@ -961,7 +998,9 @@ static pp_status launch_sweeps(pp_sim *s, Ctx &c, int sweep_mode, uint32_t sweep
     }
     if (n_sweeps > 0) prof_mark(s, c.stream);
     if (s->prows) {  // every sweep of the batch in one launch, the system in shared memory; energies out of the same launch
-        pp_status st = launch_prows(s, c, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags);
+        const bool cluster = s->prows_cluster && rec_from >= 0 && n_sweeps > 0 && want_fold;
+        pp_status st = launch_prows(s, c, m, sweep_mode, sweep_index, n_sweeps, want_energy, want_mags, cluster ? rec_from : -1);
+        if (cluster && fused) *fused = true;  // energies, magnetisations, pair dots and the fold of the recorded sweeps are done
         if (n_sweeps > 0) prof_mark(s, c.stream);
         return st;
     }
@@ -1538,6 +1577,7 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                            sys_words * 4 <= 160 * 1024 && !s->resident;
                 if (const char *e = getenv("PP_ROWS_PACKED")) s->prows = s->prows && atoi(e) != 0;
                 if (s->prows) {
+                    s->prows_cluster = m.R >= 1 && m.R <= 8 && sys_words * 8 <= 160 * 1024 && sys_ranks == 1 && !getenv("PP_PROWS_NO_CLUSTER");
                     s->pv.W = (int)W;
                     s->pv.sys_words = sys_words;
                     CREATE_TRY(pool_alloc(s, (void **)&s->pv.words, sizeof(uint32_t) * (size_t)(m.D * m.S * sys_words)));
@@ -1633,13 +1673,15 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
         std::vector<uint32_t> lut((size_t)m.T * (4 * z + 1));
         for (int mode = 0; mode < 2; mode++) {
             pp_metropolis_lookup(s->temps.data(), m.T, z, mode, lut.data());
-            bool fast = true;
+            bool fast = true, bs = z == 3;
             for (int t = 0; t < m.T; t++)
                 for (int u = 0; u <= 2 * z; u++) {
                     const uint32_t c = lut[(size_t)t * (4 * z + 1) + 2 * u];
                     if (u >= z ? c != F24 : c >= F24) fast = false;
+                    if (c >= F24 || (u > 0 && c < lut[(size_t)t * (4 * z + 1) + 2 * (u - 1)])) bs = false;
                 }
             s->prows_nm[mode] = fast ? z : 2 * z + 1;
+            s->prows_bs[mode] = bs && !fast && !getenv("PP_PROWS_NO_BS");
         }
     }
 
@@ -2167,8 +2209,12 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
     if (s->prows) macro_batch = s->max_batch;  // plain sweeps between measurements run inside one launch
     loop_live = true;
 
+    // packed rows in cluster mode: recorded sweeps are folded inside the sweep kernel, so a batch may run across them
+    const bool cl_fold = s->prows && s->prows_cluster && !want_eq && !s->profile;
+    const bool cl_batch = cl_fold && !want_ac && !want_oc && !want_fk;
     struct Step {
         uint32_t sweep_index;
+        int rec_from;  // cluster mode: sweeps of the batch from this one on are recorded inside the kernel (-1: none)
         int batch;
         bool record, pt_this;
         uint32_t pt_event;
@@ -2200,7 +2246,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                     const bool ptl = cfg->pt_interval > 0 && last % cfg->pt_interval == 0;
                     const bool ocl = want_oc && last % cfg->overlap_cluster_update_interval == 0;
                     const bool fkl = want_fk && last % cfg->cluster_update_interval == 0;
-                    if (rec || ptl || ocl || fkl || want_eq || batch >= s->max_batch) break;
+                    if ((rec && !cl_batch) || ptl || ocl || fkl || want_eq || batch >= s->max_batch) break;
                     batch++;
                 }
             }
@@ -2213,6 +2259,9 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
             stp.pt_event = pt_event;
             stp.parity = parity;
             stp.sid_last = last;
+            stp.rec_from = -1;
+            if (cl_fold && stp.record && !(want_fk && last % cfg->cluster_update_interval == 0))
+                stp.rec_from = (int)std::max<int64_t>(0, std::min<int64_t>(batch - 1, cfg->warmup_sweeps - sid));
             steps.push_back(stp);
             sweep_counter += (uint32_t)batch;
             if (stp.pt_this && m.T >= 2) {
@@ -2229,7 +2278,7 @@ extern "C" pp_status pp_sample(pp_sim *s, const pp_sample_cfg *cfg, pp_results *
                 const bool fk_this = want_fk && stp.sid_last % cfg->cluster_update_interval == 0;  // mod.rs:434-437
                 const bool energy_this = stp.record || stp.pt_this || want_eq;
                 st = launch_sweeps(s, c, cfg->sweep_mode, stp.sweep_index, stp.batch, cfg->exact_log, energy_this && !fk_this,
-                                   stp.record, stp.record || want_eq, stp.record, &fused);
+                                   stp.record, stp.record || want_eq, stp.record, &fused, stp.rec_from);
                 if (st != PP_OK) return st;
                 if (s->sys_comm) {  // system-split handle: what the other processes produced for their systems
                     st = sys_allgather(s, c.stream, energy_this, energy_this && stp.record, (stp.record || want_eq) && c.m.P > 0);

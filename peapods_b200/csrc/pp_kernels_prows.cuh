@@ -24,6 +24,10 @@
 // Draws: RNG-SPEC v2 packed mapping (pp_rng.cuh) — the 32 sites of a word are the ranks 32 q .. 32 q + 31 of their colour class,
 // q = row_ord[r] * W + w, and share six Philox calls.
 #pragma once
+#if defined(__CUDACC__)
+#include <cooperative_groups.h>
+#endif
+
 #include "pp_device.cuh"
 #include "pp_kernels_rows.cuh"
 #include "pp_kernels_stats.cuh"
@@ -37,6 +41,7 @@ struct PRowsView {
 };
 
 constexpr int PROWS_THREADS = 512;
+constexpr int PROWS_SWEEP_THREADS = 1024;  // sweep kernel: a word's two 16-site halves go to two threads (8 warps per scheduler)
 constexpr int PROWS_MAX_Z = 4;  // forward directions (z2 = 2z <= 8 bond words)
 
 // word of (row nr, the set / shift the neighbour in a direction with last component `dls` of the sites of set `p`, word w) needs
@@ -71,41 +76,141 @@ __device__ __forceinline__ void prows_count(const uint32_t *b, uint32_t (&u)[4])
 // colour class of each) and, when want_energy, leaves that system's energy (+ magnetisation sum) behind; n_sweeps = 0 with
 // want_energy is the plain energy evaluation.  Z = forward directions, NM = thresholds compared per site: Z (Metropolis: the
 // counts for unsat >= Z are 2^24 and the others are below 2^24, host-checked) or 2 Z + 1 (any table).
-// dynamic shared memory: sys_words words.
-template <int Z, int NM>
-__global__ void __launch_bounds__(PROWS_THREADS)
-prows_sweep_kernel(ModelView m, RowsView v, PRowsView pv, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags) {
+// BS (Z = 3, NM = 7; host-checked: the seven counts grow with unsat and stay below 2^24): the number L of thresholds above a site's
+// draw comes from a three-step binary search, and  draw < table[t][2 unsat]  <=>  unsat + L >= 7  is a three-LOP3 carry chain per word.
+// A work item is HALF a word (16 sites = half a block of the packed draw mapping = three Philox calls): 1024 threads per CTA keep
+// eight warps per scheduler busy where one word per thread left four (C3: one item per thread and colour class).
+// CLUSTER MODE (cl.on; launched as thread-block clusters of R CTAs = the R replicas sitting at one temperature slot, CTA rank =
+// replica): the sweeps sw >= cl.rec_from of the launch are RECORDED inside the kernel — energies and magnetisation sums per system,
+// the pair dots of replicas (2p, 2p + 1) by the even-ranked CTA, which reads its partner's words through distributed shared memory,
+// and the fold of simulation/mod.rs:543-578 / statistics/overlap.rs:283-306 by the first thread of rank 0, which collects the R
+// systems' scalars through distributed shared memory — with two cluster barriers per recorded sweep where the multi-launch path has
+// two kernel boundaries and a round trip of the words through global memory.  A whole sample() call without exchanges is ONE launch.
+// dynamic shared memory: sys_words words (cluster mode: twice that, the second half holds the pair's XOR words).
+struct PRowsCluster {
+    int on;             // 0: plain launch (grid = D * S, CTA = slot); 1: cluster launch (grid = D * T * R, CTA = (d, t, r))
+    int rec_from;       // sweeps sw >= rec_from of this launch are recorded
+    int stage_tables;   // the row tables (nbr_row, row_ord, class_rows, row_a) are copied into shared memory behind the words: a cluster
+                        // barrier invalidates L1, and every work item starts with two dependent table reads
+    StatsView st;
+    long long *dot_spin, *dot_link;
+};
+
+#ifdef PP_PROWS_TIMING  // phase clocks of CTA 0 (tools/c3_phases.py; never defined in the product build)
+__device__ unsigned long long pp_prows_clk[8];
+#define PROWS_CLK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long now_ = clock64(); pp_prows_clk[k] += now_ - clk_last_; clk_last_ = now_; } } while (0)
+#else
+#define PROWS_CLK(k) do { } while (0)
+#endif
+
+template <int Z, int NM, bool BS = false>
+__global__ void __launch_bounds__(PROWS_SWEEP_THREADS)
+prows_sweep_kernel(ModelView m, RowsView vg, PRowsView pv, uint32_t sweep_index, int n_sweeps, int want_energy, int want_mags, PRowsCluster cl) {
     extern __shared__ __align__(16) uint32_t prows_sm[];
     __shared__ uint32_t thr_sm[2 * PROWS_MAX_Z + 1];
-    __shared__ long long red_sm[32];
+    __shared__ unsigned int cnt_sm[4];                // integer partial sums of the reductions (zero between uses; below 2^31:
+                                                      // a system that fits shared memory has fewer than 2^22 sites)
+    __shared__ double sums_sm[11];                    // cluster mode, rank 0: running sums of (d, t) for the whole launch
+    // cluster mode, rank 0's copy: the R systems' energies and magnetisation sums and the P pairs' dots of up to FOLD_K recorded
+    // sweeps (two batches: one being filled, one being folded), stored into it by the owning CTAs through distributed shared memory
+    __shared__ float all_e[2][FOLD_K][8];
+    __shared__ long long all_m[2][FOLD_K][8], all_q[2][FOLD_K][4], all_l[2][FOLD_K][4];
+    __shared__ double fold_tab[FOLD_K][8][11];
+    RowsView v = vg;
     constexpr int Z2 = 2 * Z;
+    static_assert(!BS || (Z == 3 && NM == 7), "the binary search is written for seven thresholds");
+    constexpr bool SHIFTED = NM == Z || BS;  // every compared count is below 2^24: compare the 32-bit words against count << 8
     const int tid = threadIdx.x;
-    const int64_t d = blockIdx.x / m.S;
-    const int slot = (int)(blockIdx.x % m.S);
+    const int rank = cl.on ? (int)(blockIdx.x % m.R) : 0;  // cluster mode: the replica
+    const int64_t d = cl.on ? blockIdx.x / ((int64_t)m.R * m.T) : blockIdx.x / m.S;
+    const int slot = cl.on ? rank * m.T + (int)((blockIdx.x / m.R) % m.T) : (int)(blockIdx.x % m.S);
     const int t = slot % m.T;  // realization.rs:166
     const int sysl = m.system_ids[d * m.S + slot];  // parallel.rs:27-33: spins by system, temperature by slot
-    if (sysl < m.sys_lo || sysl >= m.sys_hi) return;  // system-split handle: another process updates this system
+    if (!cl.on && (sysl < m.sys_lo || sysl >= m.sys_hi)) return;  // system-split handle: another process updates this system
     const int64_t sysg = d * m.S + sysl;
     uint32_t *gw = pv.words + sysg * pv.sys_words;
     const int W = pv.W;
-    for (int64_t i = tid; i < pv.sys_words / 4; i += PROWS_THREADS) reinterpret_cast<uint4 *>(prows_sm)[i] = reinterpret_cast<const uint4 *>(gw)[i];
+    for (int64_t i = tid; i < pv.sys_words / 4; i += PROWS_SWEEP_THREADS) reinterpret_cast<uint4 *>(prows_sm)[i] = reinterpret_cast<const uint4 *>(gw)[i];
     if (tid <= Z2) thr_sm[tid] = m.lut[t * (4 * Z + 1) + 2 * tid];  // sweep.rs:162-166, index ec + 2z' = 2 * unsat
+    if (tid < 4) cnt_sm[tid] = 0u;
+    if (cl.stage_tables) {
+        const uint32_t nr = (uint32_t)vg.n_rows;
+        uint32_t *s_nbr = prows_sm + (size_t)pv.sys_words * (cl.on ? 2 : 1), *s_ord = s_nbr + (size_t)nr * Z2, *s_crow = s_ord + nr;
+        uint8_t *s_a = reinterpret_cast<uint8_t *>(s_crow + nr);
+        for (uint32_t i = tid; i < nr * (uint32_t)Z2; i += PROWS_SWEEP_THREADS) s_nbr[i] = vg.nbr_row[i];
+        for (uint32_t i = tid; i < nr; i += PROWS_SWEEP_THREADS) {
+            s_ord[i] = vg.row_ord[i];
+            s_crow[i] = vg.class_rows[i];
+            s_a[i] = vg.row_a[i];
+        }
+        v.nbr_row = s_nbr; v.row_ord = s_ord; v.class_rows = s_crow; v.row_a = s_a;
+    }
     __syncthreads();
+    // the thread's words of the passes over whole systems (energies, pair dots): i = tid + k * threads, row / set / word of the first
+    // one computed once; when 2 W divides the thread count the set and word stay and the row advances by a constant
+    const uint32_t W2 = 2u * (uint32_t)W, w_r0 = (uint32_t)tid / W2, w_p = ((uint32_t)tid / (uint32_t)W) & 1u, w_w = (uint32_t)tid % (uint32_t)W;
+    const bool w_regular = PROWS_SWEEP_THREADS % W2 == 0;
+    const uint32_t w_rstep = PROWS_SWEEP_THREADS / W2;
     uint32_t T[NM];
 #pragma unroll
-    for (int u = 0; u < NM; u++) T[u] = NM == Z ? thr_sm[u] << 8 : thr_sm[u];
+    for (int u = 0; u < NM; u++) T[u] = SHIFTED ? thr_sm[u] << 8 : thr_sm[u];
     const uint64_t key = v.keys[d];
     const PhiloxKeys ks = philox_keys((uint32_t)key, (uint32_t)(key >> 32));
     int dls[Z];
 #pragma unroll
     for (int k = 0; k < Z; k++) dls[k] = v.dl[k];
+    // energy.rs:99-108: every bond once through its forward direction; down spins of both sets.  Integer partial sums: warp
+    // REDUX, shared-memory atomics, one barrier (cnt_sm is left zeroed for the next use).
+    auto energy_phase = [&](const bool mags, const int fb, const int fs) {  // fb / fs: batch buffer and slot of a recorded sweep
+        int unsat = 0, dn = 0;
+        const uint32_t n_words = (uint32_t)pv.sys_words;
+        uint32_t rr = w_r0;
+        for (uint32_t i = tid; i < n_words; i += PROWS_SWEEP_THREADS, rr += w_rstep) {
+            const uint32_t r = w_regular ? rr : i / W2;
+            const int p = w_regular ? (int)w_p : (int)((i / (uint32_t)W) & 1u), w = w_regular ? (int)w_w : (int)(i % (uint32_t)W);
+            const uint32_t C = prows_sm[i];
+            dn += __popc(C);
+#pragma unroll
+            for (int k = 0; k < Z; k++) unsat += __popc(C ^ prows_nbr_word(prows_sm, W, v.nbr_row[((size_t)r * Z + k) * 2], p, w, dls[k]));
+        }
+        unsat = __reduce_add_sync(0xFFFFFFFFu, unsat);
+        dn = __reduce_add_sync(0xFFFFFFFFu, dn);
+        if ((tid & 31) == 0) {
+            atomicAdd(&cnt_sm[0], (unsigned int)unsat);
+            atomicAdd(&cnt_sm[1], (unsigned int)dn);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const long long tu = (long long)cnt_sm[0], td = (long long)cnt_sm[1];
+            cnt_sm[0] = cnt_sm[1] = 0u;
+            const float e = __fdiv_rn((float)((long long)Z * m.N - 2 * tu), (float)m.N);
+            m.energies[sysg] = e;
+            if (mags) m.mags[sysg] = m.N - 2 * td;
+            if (cl.on) {  // rank 0 folds: hand it the scalars (visible to it after the next cluster barrier)
+                cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+                *cluster.map_shared_rank(&all_e[fb][fs][rank], 0) = e;
+                *cluster.map_shared_rank(&all_m[fb][fs][rank], 0) = m.N - 2 * td;
+            }
+        }
+    };
+    double *my_sums = nullptr;  // cluster mode, rank 0: the 11 running sums of (d, t)
+    if (cl.on && rank == 0) {
+        for (int i = tid; i < 11; i += PROWS_SWEEP_THREADS) sums_sm[i] = cl.st.sums[d * 11 * m.T + t + (int64_t)i * m.T];
+        my_sums = sums_sm;
+    }
 
+#ifdef PP_PROWS_TIMING
+    unsigned long long clk_last_ = clock64();
+#endif
     for (int sw = 0; sw < n_sweeps; sw++) {
+        PROWS_CLK(7);
         for (int colour = 0; colour < m.n_colours; colour++) {
             const int cls = colour % v.m_half;
             const uint32_t row0 = v.class_start[cls], n_items = (v.class_start[cls + 1] - row0) * (uint32_t)W;
             const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
-            for (uint32_t it = tid; it < n_items; it += PROWS_THREADS) {
+            for (uint32_t ih = tid; ih < 2u * n_items; ih += PROWS_SWEEP_THREADS) {
+                const uint32_t it = ih >> 1;
+                const int h = (int)(ih & 1u);  // sites 16 h .. 16 h + 15 of the word
                 const uint32_t ri = it / (uint32_t)W;
                 const int w = (int)(it - ri * (uint32_t)W);
                 const uint32_t r = v.class_rows[row0 + ri];
@@ -120,65 +225,118 @@ prows_sweep_kernel(ModelView m, RowsView v, PRowsView pv, uint32_t sweep_index, 
                 }
                 uint32_t un[4];
                 prows_count<Z2>(b, un);
-                uint32_t M[NM];
+                uint32_t M[BS ? 3 : NM];  // BS: the bit planes of L
 #pragma unroll
-                for (int u = 0; u < NM; u++) M[u] = 0u;
+                for (int u = 0; u < (BS ? 3 : NM); u++) M[u] = 0u;
                 const uint32_t q = v.row_ord[r] * (uint32_t)W + (uint32_t)w;  // rank >> 5 of the word's sites
+                uint32_t wd[12];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t wd[12];
+                for (int c = 0; c < 3; c++) {
+                    const u32x4 o = philox4x32_k(q, sweep_index + (uint32_t)sw, (uint32_t)sysl, tagc | ((uint32_t)(3 * h + c) << 8), ks);
+                    wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
+                }
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const u32x4 o = philox4x32_k(q, sweep_index + (uint32_t)sw, (uint32_t)sysl, tagc | ((uint32_t)(3 * h + c) << 8), ks);
-                        wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
-                    }
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t A = wd[3 * g], B = wd[3 * g + 1], Cw = wd[3 * g + 2];
+                    const uint32_t y3 = __byte_perm(__byte_perm(Cw, B, 0x0400), A, 0x4210);
+                    const uint32_t ys[4] = {A, B, Cw, y3};
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const uint32_t A = wd[3 * g], B = wd[3 * g + 1], Cw = wd[3 * g + 2];
-                        const uint32_t y3 = __byte_perm(__byte_perm(Cw, B, 0x0400), A, 0x4210);
-                        const uint32_t ys[4] = {A, B, Cw, y3};
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t bit = 1u << (16 * h + 4 * g + j);
-                            const uint32_t y = NM == Z ? ys[j] : ys[j] >> 8;
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t bit = 1u << (4 * g + j);  // inside the half; moved to 16 h + . below
+                        const uint32_t y = SHIFTED ? ys[j] : ys[j] >> 8;
+                        if (BS) {
+                            const bool p1 = y < T[3];
+                            const bool p2 = y < (p1 ? T[1] : T[5]);
+                            const bool p3 = y < (p1 ? (p2 ? T[0] : T[2]) : (p2 ? T[4] : T[6]));
+                            if (p1) M[2] |= bit;  // L = 4 p1 + 2 p2 + p3 thresholds lie above the draw
+                            if (p2) M[1] |= bit;
+                            if (p3) M[0] |= bit;
+                        } else {
 #pragma unroll
                             for (int u = 0; u < NM; u++)
                                 if (y < T[u]) M[u] |= bit;
                         }
                     }
                 }
-                // flip = OR_u ([unsat == u] & M_u); unsat >= NM always flips when NM == Z (Metropolis, energy change <= 0)
+                const int hs = 16 * h;
                 uint32_t flip = 0u;
+                if (BS) {  // unsat + L + 1 >= 8: the carry out of a three-bit add with carry in
+                    const uint32_t c0 = un[0] | (M[0] << hs);
+                    const uint32_t l1 = M[1] << hs, l2 = M[2] << hs;
+                    const uint32_t c1 = (un[1] & l1) | (c0 & (un[1] | l1));
+                    flip = (un[2] & l2) | (c1 & (un[2] | l2));
+                } else {
+                    // flip = OR_u ([unsat == u] & M_u); unsat >= NM always flips when NM == Z (Metropolis, energy change <= 0)
 #pragma unroll
-                for (int u = 0; u <= Z2; u++) {
-                    const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
-                    flip |= u < NM ? (eq & M[u]) : eq;
+                    for (int u = 0; u <= Z2; u++) {
+                        const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
+                        flip |= u < NM ? (eq & (M[u] << hs)) : eq;
+                    }
                 }
-                *slf = C ^ flip;
+                reinterpret_cast<uint16_t *>(slf)[h] = (uint16_t)((C ^ flip) >> hs);  // this thread's half of the word
             }
             __syncthreads();
         }
-    }
-    if (want_energy) {  // energy.rs:99-108: every bond once through its forward direction; down spins of both sets
-        long long unsat = 0, dn = 0;
-        const uint32_t n_words = (uint32_t)pv.sys_words;
-        for (uint32_t i = tid; i < n_words; i += PROWS_THREADS) {
-            const uint32_t r = i / (uint32_t)(2 * W);
-            const int p = (int)((i / (uint32_t)W) & 1u), w = (int)(i % (uint32_t)W);
-            const uint32_t C = prows_sm[i];
-            dn += __popc(C);
+        const bool rec = cl.on && sw >= cl.rec_from, last = sw == n_sweeps - 1;
+        PROWS_CLK(0);
+        const int n_rec = rec ? sw - cl.rec_from : 0, fb = (n_rec / FOLD_K) & 1, fs = n_rec % FOLD_K;
+        if (rec || (last && want_energy)) energy_phase(rec || want_mags != 0, fb, fs);
+        PROWS_CLK(1);
+        if (rec) {  // mod.rs:527-529, 543-578 with this launch's (fixed) system_ids
+            namespace cg = cooperative_groups;
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();  // every replica of the slot has finished the sweep; its words and scalars are final
+            PROWS_CLK(2);
+            if (m.P > 0 && (rank & 1) == 0 && rank + 1 < m.R) {  // overlap.rs:259-281 for the pair (rank, rank + 1)
+                const uint32_t n_words = (uint32_t)pv.sys_words;
+                uint32_t *X = prows_sm + n_words;  // bit set where the two replicas differ
+                const uint32_t *other = cluster.map_shared_rank(prows_sm, rank + 1);
+                for (uint32_t i = tid; i < n_words; i += PROWS_SWEEP_THREADS) X[i] = prows_sm[i] ^ other[i];
+                __syncthreads();
+                int neg_q = 0, neg_l = 0;
+                uint32_t rr = w_r0;
+                for (uint32_t i = tid; i < n_words; i += PROWS_SWEEP_THREADS, rr += w_rstep) {
+                    const uint32_t r = w_regular ? rr : i / W2;
+                    const int p = w_regular ? (int)w_p : (int)((i / (uint32_t)W) & 1u), w = w_regular ? (int)w_w : (int)(i % (uint32_t)W);
+                    const uint32_t x = X[i];
+                    neg_q += __popc(x);
 #pragma unroll
-            for (int k = 0; k < Z; k++) unsat += __popc(C ^ prows_nbr_word(prows_sm, W, v.nbr_row[((size_t)r * Z + k) * 2], p, w, dls[k]));
-        }
-        const long long tu = block_sum<long long>(unsat, red_sm);
-        const long long td = block_sum<long long>(dn, red_sm);
-        if (tid == 0) {
-            m.energies[sysg] = __fdiv_rn((float)((long long)Z * m.N - 2 * tu), (float)m.N);
-            if (want_mags) m.mags[sysg] = m.N - 2 * td;
+                    for (int k = 0; k < Z; k++) neg_l += __popc(x ^ prows_nbr_word(X, W, v.nbr_row[((size_t)r * Z + k) * 2], p, w, dls[k]));
+                }
+                neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
+                neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
+                if ((tid & 31) == 0) {
+                    atomicAdd(&cnt_sm[2], (unsigned int)neg_q);
+                    atomicAdd(&cnt_sm[3], (unsigned int)neg_l);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const long long tq = (long long)cnt_sm[2], tl = (long long)cnt_sm[3];
+                    cnt_sm[2] = cnt_sm[3] = 0u;
+                    const int64_t idx = (d * m.P + rank / 2) * m.T + t;
+                    const long long dq = m.N - 2 * tq, dl = (long long)Z * m.N - 2 * tl;
+                    cl.dot_spin[idx] = dq;
+                    cl.dot_link[idx] = dl;
+                    *cluster.map_shared_rank(&all_q[fb][fs][rank / 2], 0) = dq;
+                    *cluster.map_shared_rank(&all_l[fb][fs][rank / 2], 0) = dl;
+                }
+            }
+            PROWS_CLK(3);
+            cluster.sync();  // the partner's words have been read (the next sweep may change them); dots and scalars are visible
+            PROWS_CLK(4);
+            if (rank == 0 && tid < 32 && (fs == FOLD_K - 1 || last))  // warp 0 folds a batch (the rest of the CTA is in the next sweep)
+                fold_batch(m, cl.st, d, t, tid, fs + 1, all_m[fb], all_e[fb], all_q[fb], all_l[fb], fold_tab, my_sums);
+            PROWS_CLK(5);
         }
     }
+    if (cl.on && n_sweeps > 0 && n_sweeps - 1 >= cl.rec_from) {
+        cooperative_groups::this_cluster().sync();  // no CTA leaves while another may still address its shared memory
+        if (rank == 0 && tid == 0)
+            for (int i = 0; i < 11; i++) cl.st.sums[d * 11 * m.T + t + (int64_t)i * m.T] = sums_sm[i];
+    }
+    if (want_energy && n_sweeps == 0) energy_phase(want_mags != 0, 0, 0);
     if (n_sweeps > 0)
-        for (int64_t i = tid; i < pv.sys_words / 4; i += PROWS_THREADS) reinterpret_cast<uint4 *>(gw)[i] = reinterpret_cast<const uint4 *>(prows_sm)[i];
+        for (int64_t i = tid; i < pv.sys_words / 4; i += PROWS_SWEEP_THREADS) reinterpret_cast<uint4 *>(gw)[i] = reinterpret_cast<const uint4 *>(prows_sm)[i];
 }
 
 // integer overlap dots (overlap.rs:259-281) of the replica pairs at one (realization, temperature), words straight from global

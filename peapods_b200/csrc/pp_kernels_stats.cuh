@@ -36,11 +36,14 @@ struct PtView {
 // not wait for the loads; one thread per (d, t) and stream order keep every cell's additions in the reference's order).
 template <int RFIX, bool RED_HIST = false, typename GetM, typename GetE, typename GetS, typename GetL>
 __device__ __forceinline__ void fold_one(const ModelView &m, const StatsView &st, int64_t d, int t, int with_overlap,
-                                         GetM get_m, GetE get_e, GetS get_ds, GetL get_dl) {
+                                         GetM get_m, GetE get_e, GetS get_ds, GetL get_dl, double *sums_local = nullptr) {
     const float nf = (float)m.N;
-    double *sums = st.sums + d * 11 * m.T + t;
+    // sums_local: the 11 running sums of (d, t) kept densely by the caller (a kernel that folds many sweeps of one (d, t) loads
+    // them once and stores them once)
+    double *sums = sums_local ? sums_local : st.sums + d * 11 * m.T + t;
+    const int64_t ST = sums_local ? 1 : m.T;
     // simulation/mod.rs:555-578: replica-inner order
-    double s0 = sums[0], s1 = sums[1 * m.T], s2 = sums[2 * m.T], s3 = sums[3 * m.T], s4 = sums[4 * m.T];
+    double s0 = sums[0], s1 = sums[1 * ST], s2 = sums[2 * ST], s3 = sums[3 * ST], s4 = sums[4 * ST];
     const int R = RFIX > 0 ? RFIX : m.R, P = RFIX > 0 ? RFIX / 2 : m.P;
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -54,13 +57,13 @@ __device__ __forceinline__ void fold_one(const ModelView &m, const StatsView &st
         s3 = __dadd_rn(s3, (double)e);
         s4 = __dadd_rn(s4, __dmul_rn((double)e, (double)e));  // stats.rs:23: powi(2) in f64
     }
-    sums[0] = s0; sums[1 * m.T] = s1; sums[2 * m.T] = s2; sums[3 * m.T] = s3; sums[4 * m.T] = s4;
+    sums[0] = s0; sums[1 * ST] = s1; sums[2 * ST] = s2; sums[3 * ST] = s3; sums[4 * ST] = s4;
     if (!with_overlap) return;
     // statistics/overlap.rs:283-306 + :318-324, pair order
     const float nb = (float)(m.N * m.z);
     const int64_t bins = m.N + 1;
-    double o0 = sums[5 * m.T], o1 = sums[6 * m.T], o2 = sums[7 * m.T], o3 = sums[8 * m.T], o4 = sums[9 * m.T],
-           o5 = sums[10 * m.T];
+    double o0 = sums[5 * ST], o1 = sums[6 * ST], o2 = sums[7 * ST], o3 = sums[8 * ST], o4 = sums[9 * ST],
+           o5 = sums[10 * ST];
 #pragma unroll
     for (int p = 0; p < P; p++) {
         const long long dsp = get_ds(p);
@@ -87,8 +90,65 @@ __device__ __forceinline__ void fold_one(const ModelView &m, const StatsView &st
             st.ql2_at_q[h] = __dadd_rn(st.ql2_at_q[h], (double)ql2);
         }
     }
-    sums[5 * m.T] = o0; sums[6 * m.T] = o1; sums[7 * m.T] = o2; sums[8 * m.T] = o3; sums[9 * m.T] = o4;
-    sums[10 * m.T] = o5;
+    sums[5 * ST] = o0; sums[6 * ST] = o1; sums[7 * ST] = o2; sums[8 * ST] = o3; sums[9 * ST] = o4;
+    sums[10 * ST] = o5;
+}
+
+// The same fold for a BATCH of up to FOLD_K recorded sweeps of one (d, t), by one warp.  Phase A: lane k derives the terms of
+// sweep k (the f32 arithmetic of fold_one, widened to f64) into a shared-memory table — the divisions of the sweeps run side by side
+// instead of one after the other.  Phase B: lane j < 11 adds column j to running sum j, sweeps in order, replicas / pairs in order,
+// so every sum receives exactly fold_one's additions in fold_one's order; lane 11 walks the histogram cells in the same order.
+// A single thread folding one sweep costs ~4000 cycles of dependent instructions; this costs a few hundred per sweep.
+// Mv / Ev: [n][8] by replica, Sv / Lv: [n][4] by pair; tab: [FOLD_K][8][11] doubles; sums: the 11 dense running sums of (d, t).
+constexpr int FOLD_K = 16;
+__device__ __forceinline__ void fold_batch(const ModelView &m, const StatsView &st, int64_t d, int t, int lane, int n,
+                                           const long long (*Mv)[8], const float (*Ev)[8], const long long (*Sv)[4],
+                                           const long long (*Lv)[4], double (*tab)[8][11], double *sums) {
+    const float nf = (float)m.N, nb = (float)(m.N * m.z);
+    if (lane < n) {
+        for (int r = 0; r < m.R; r++) {
+            const float mag = __fdiv_rn((float)Mv[lane][r], nf);
+            const float m2 = __fmul_rn(mag, mag);
+            const float e = Ev[lane][r];
+            double *o = tab[lane][r];
+            o[0] = (double)mag;
+            o[1] = (double)m2;
+            o[2] = (double)__fmul_rn(m2, m2);
+            o[3] = (double)e;
+            o[4] = __dmul_rn((double)e, (double)e);  // stats.rs:23: powi(2) in f64
+        }
+        for (int p = 0; p < m.P; p++) {
+            const float ql = __fdiv_rn((float)Lv[lane][p], nb);
+            const float q = __fdiv_rn((float)Sv[lane][p], nf);
+            const float q2 = __fmul_rn(q, q);
+            const float ql2 = __fmul_rn(ql, ql);
+            double *o = tab[lane][p];
+            o[5] = (double)q;
+            o[6] = (double)q2;
+            o[7] = (double)__fmul_rn(q2, q2);
+            o[8] = (double)ql;
+            o[9] = (double)ql2;
+            o[10] = (double)__fmul_rn(ql2, ql2);
+        }
+    }
+    __syncwarp();
+    if (lane < 11 && (lane < 5 || m.P > 0)) {
+        const int cnt = lane < 5 ? m.R : m.P;
+        double acc = sums[lane];
+        for (int k = 0; k < n; k++)
+            for (int i = 0; i < cnt; i++) acc = __dadd_rn(acc, tab[k][i][lane]);
+        sums[lane] = acc;
+    } else if (lane == 11 && m.P > 0) {
+        const int64_t bins = m.N + 1;
+        for (int k = 0; k < n; k++)
+            for (int p = 0; p < m.P; p++) {
+                const int64_t h = (d * m.T + t) * bins + (Sv[k][p] + m.N) / 2;
+                atomicAdd(st.hist + h, 1u);
+                atomicAdd(st.ql_at_q + h, tab[k][p][8]);
+                atomicAdd(st.ql2_at_q + h, tab[k][p][9]);
+            }
+    }
+    __syncwarp();
 }
 
 // Same fold as fire-and-forget reductions (RED.ADD.F64 / RED.ADD.U32): no load, so the warp that finishes 32
