@@ -451,6 +451,7 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
     uint8_t *trip_sm = reinterpret_cast<uint8_t *>(sid_sm + S);
     uint32_t *pw = reinterpret_cast<uint32_t *>(sc + resident_scalar_bytes(S, T, P));  // [S][rows][W] by system
     int *cnt_sm = reinterpret_cast<int *>(pw + (size_t)S * sysw);                       // [2 * max(S, P * T)] integer partial sums
+    float *dbeta_sm = reinterpret_cast<float *>(cnt_sm + 2 * (S > P * T ? S : P * T));  // [T - 1] 1 / T_e - 1 / T_e+1 (tempering.rs:85-88)
     int8_t *g_spins = mg.spins + dg * S * mg.N;
     const int64_t bins = mg.N + 1;
     for (int i = tid; i < T * NTH; i += RESIDENT_THREADS) {
@@ -475,6 +476,7 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
         eacc_sm[i] = ptg.edge_acceptances[dg * (T - 1) + i];
     }
     for (int i = tid; i < T; i += RESIDENT_THREADS) temps_sm[i] = mg.temps[i];
+    for (int i = tid; i < T - 1; i += RESIDENT_THREADS) dbeta_sm[i] = __fsub_rn(__fdiv_rn(1.0f, mg.temps[i]), __fdiv_rn(1.0f, mg.temps[i + 1]));
     for (int i = tid; i < S * sysw; i += RESIDENT_THREADS) {  // pack: 32 consecutive sites -> one word (bit = 1: spin -1)
         const uint4 *src = reinterpret_cast<const uint4 *>(g_spins + (int64_t)i * 32);
         uint32_t word = 0u;
@@ -528,13 +530,120 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
     uint32_t pt_event = a.pt_event0;
     int parity = a.parity0;
     const int half_l = L / 2;
+    // one word of one system: thresholds against the packed draws of its 16 active sites, flip, store
+    auto update_word = [&](const int slot, const int sysl, uint32_t *own, const uint32_t C, const uint32_t (&b)[Z2], const int p,
+                           const uint32_t q, const uint32_t h, const uint32_t sweep_index, const uint32_t tagc) {
+        const uint32_t *thr = thr_sm + (slot % T) * NTH;      // realization.rs:166
+        uint32_t un[4];
+        prows_count<Z2>(b, un);
+        uint32_t Tm[NM], M[NM];
+#pragma unroll
+        for (int u = 0; u < NM; u++) { Tm[u] = thr[u]; M[u] = 0u; }
+        uint32_t wd[12];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const u32x4 o = philox4x32_k(q, sweep_index, (uint32_t)sysl, tagc | ((3u * h + (uint32_t)c) << 8), ks);
+            wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t A = wd[3 * g], B = wd[3 * g + 1], Cw = wd[3 * g + 2];
+            const uint32_t y3 = __byte_perm(__byte_perm(Cw, B, 0x0400), A, 0x4210);
+            const uint32_t ys[4] = {A, B, Cw, y3};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t bit = 1u << (2 * (4 * g + j));  // site x = 2 (4 g + j) + p: shifted by p below
+                const uint32_t y = NM == Z ? ys[j] : ys[j] >> 8;
+#pragma unroll
+                for (int u = 0; u < NM; u++)
+                    if (y < Tm[u]) M[u] |= bit;
+            }
+        }
+        uint32_t flip = 0u;
+#pragma unroll
+        for (int u = 0; u <= Z2; u++) {
+            const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
+            flip |= u < NM ? (eq & (M[u] << p)) : eq;
+        }
+        *own = C ^ (flip & (0x55555555u << p));
+    };
+    // Two-colour lattices whose work items fit two per thread (the quickstart: 32 systems x 32 row words on 512 threads): a thread's
+    // items are the same words in every colour pass of every sweep (only the parity of the active sites alternates), so their slot,
+    // word offsets, neighbour-word offsets and rank block are worked out ONCE per launch instead of once per pass (two integer
+    // divisions and nine dependent table reads per item: the passes of one small realization on one SM are latency-bound).
+    constexpr int HOIST = 2;
+    const uint32_t per_sys0 = (vg.class_start[1] - vg.class_start[0]) * (uint32_t)W;
+    const bool hoist = m.n_colours == 2 && vg.m_half == 1 && (uint32_t)S * per_sys0 <= (uint32_t)(HOIST * RESIDENT_THREADS) && sysw <= 65535;
+    int h_slot[HOIST], h_a[HOIST];
+    uint32_t h_own[HOIST], h_q[HOIST], h_h[HOIST];
+    uint16_t h_n0[HOIST][Z2], h_n1[HOIST][Z2];  // word offsets inside a system: the neighbour row's word, and the adjacent one for a shift
+#pragma unroll
+    for (int j = 0; j < HOIST; j++) {
+        h_slot[j] = -1;
+        const uint32_t it = (uint32_t)tid + (uint32_t)j * RESIDENT_THREADS;
+        if (hoist && it < (uint32_t)S * per_sys0) {
+            const int slot = (int)(it / per_sys0);
+            const uint32_t rem = it - (uint32_t)slot * per_sys0, ri = rem / (uint32_t)W;
+            const int w = (int)(rem - ri * (uint32_t)W);
+            const uint32_t r = vg.class_rows[ri];
+            h_slot[j] = slot;
+            h_a[j] = (int)vg.row_a[r];
+            h_own[j] = r * (uint32_t)W + (uint32_t)w;
+            const uint32_t base = vg.row_ord[r] * (uint32_t)half_l + 16u * (uint32_t)w;
+            h_q[j] = base >> 5;
+            h_h[j] = (base >> 4) & 1u;
+#pragma unroll
+            for (int k = 0; k < Z; k++)
+#pragma unroll
+                for (int sgn = 0; sgn < 2; sgn++) {
+                    const uint32_t nr = vg.nbr_row[((size_t)r * Z + k) * 2 + sgn];
+                    const int sh = sgn ? -dls[k] : dls[k];
+                    const int wa = sh > 0 ? (w + 1 == W ? 0 : w + 1) : sh < 0 ? (w ? w - 1 : W - 1) : w;
+                    h_n0[j][2 * k + sgn] = (uint16_t)(nr * (uint32_t)W + (uint32_t)w);
+                    h_n1[j][2 * k + sgn] = (uint16_t)(nr * (uint32_t)W + (uint32_t)wa);
+                }
+        }
+    }
     for (int sw = 0; sw < a.n_sweeps; sw++) {
         const int64_t sid = a.sweep_id0 + sw;
         const uint32_t sweep_index = a.sweep_counter0 + (uint32_t)sw;
+        // single-edge exchange after this sweep: its edge and draw depend on (event, replica) only — generate them now and start the
+        // read of ln u (a 64 MiB table: a DRAM round trip) so that the exchange itself is a compare on values already here
+        int pt_edge = 0;
+        float pt_logu = 0.0f;
+        if (a.pt_schedule == 0 && T >= 2 && tid < m.R && a.pt_interval > 0 && sid % a.pt_interval == 0) {
+            const u32x4 o = philox4x32(0xFFFFFFFFu, pt_event, (uint32_t)tid, TAG_PT, (uint32_t)key, (uint32_t)(key >> 32));
+            pt_edge = (int)(((uint64_t)o.y * (uint64_t)(T - 1)) >> 32);
+            pt_logu = m.logtab[o.x >> 8];
+        }
         for (int colour = 0; colour < m.n_colours; colour++) {
+            const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
+            if (hoist) {
+#pragma unroll
+                for (int j = 0; j < HOIST; j++) {
+                    if (h_slot[j] < 0) continue;
+                    const int sysl = sid_sm[h_slot[j]];  // parallel.rs:27-33
+                    uint32_t *sys = pw + (size_t)sysl * sysw;
+                    const uint32_t C = sys[h_own[j]];
+                    uint32_t b[Z2];
+#pragma unroll
+                    for (int k = 0; k < Z; k++)
+#pragma unroll
+                        for (int sgn = 0; sgn < 2; sgn++) {
+                            const int sh = sgn ? -dls[k] : dls[k];
+                            const uint32_t c0 = sys[h_n0[j][2 * k + sgn]];
+                            uint32_t nw = c0;
+                            if (sh > 0) nw = (c0 >> 1) | (sys[h_n1[j][2 * k + sgn]] << 31);
+                            else if (sh < 0) nw = (c0 << 1) | (sys[h_n1[j][2 * k + sgn]] >> 31);
+                            b[2 * k + sgn] = C ^ nw;
+                        }
+                    update_word(h_slot[j], sysl, sys + h_own[j], C, b, h_a[j] == colour ? 0 : 1, h_q[j], h_h[j], sweep_index, tagc);
+                }
+                __syncthreads();
+                continue;
+            }
             const int cls = colour % vg.m_half;
             const uint32_t row0 = vg.class_start[cls], per_sys = (vg.class_start[cls + 1] - row0) * (uint32_t)W;
-            const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
             for (uint32_t it = tid; it < (uint32_t)S * per_sys; it += RESIDENT_THREADS) {
                 const int slot = (int)(it / per_sys);
                 const uint32_t rem = it - (uint32_t)slot * per_sys, ri = rem / (uint32_t)W;
@@ -542,7 +651,6 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
                 const uint32_t r = vg.class_rows[row0 + ri];
                 const int p = (int)vg.row_a[r] == colour ? 0 : 1;  // parity of the row's sites of this colour
                 const int sysl = sid_sm[slot];                        // parallel.rs:27-33
-                const uint32_t *thr = thr_sm + (slot % T) * NTH;      // realization.rs:166
                 uint32_t *sys = pw + (size_t)sysl * sysw;
                 const uint32_t C = sys[(size_t)r * W + w];
                 uint32_t b[Z2];
@@ -551,41 +659,9 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
                     b[2 * k] = C ^ nbr_word(sys, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]);
                     b[2 * k + 1] = C ^ nbr_word(sys, vg.nbr_row[((size_t)r * Z + k) * 2 + 1], w, -dls[k]);
                 }
-                uint32_t un[4];
-                prows_count<Z2>(b, un);
-                uint32_t Tm[NM], M[NM];
-#pragma unroll
-                for (int u = 0; u < NM; u++) { Tm[u] = thr[u]; M[u] = 0u; }
                 // the word's 16 sites of this colour are the ranks base .. base + 15: half h of block q of the packed mapping
                 const uint32_t base = vg.row_ord[r] * (uint32_t)half_l + 16u * (uint32_t)w;
-                const uint32_t q = base >> 5, h = (base >> 4) & 1u;
-                uint32_t wd[12];
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const u32x4 o = philox4x32_k(q, sweep_index, (uint32_t)sysl, tagc | ((3u * h + (uint32_t)c) << 8), ks);
-                    wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
-                }
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const uint32_t A = wd[3 * g], B = wd[3 * g + 1], Cw = wd[3 * g + 2];
-                    const uint32_t y3 = __byte_perm(__byte_perm(Cw, B, 0x0400), A, 0x4210);
-                    const uint32_t ys[4] = {A, B, Cw, y3};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t bit = 1u << (2 * (4 * g + j));  // site x = 2 (4 g + j) + p: shifted by p below
-                        const uint32_t y = NM == Z ? ys[j] : ys[j] >> 8;
-#pragma unroll
-                        for (int u = 0; u < NM; u++)
-                            if (y < Tm[u]) M[u] |= bit;
-                    }
-                }
-                uint32_t flip = 0u;
-#pragma unroll
-                for (int u = 0; u <= Z2; u++) {
-                    const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
-                    flip |= u < NM ? (eq & (M[u] << p)) : eq;
-                }
-                sys[(size_t)r * W + w] = C ^ (flip & (0x55555555u << p));
+                update_word(slot, sysl, sys + (size_t)r * W + w, C, b, p, base >> 5, (base >> 4) & 1u, sweep_index, tagc);
             }
             __syncthreads();
         }
@@ -660,19 +736,25 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
                 }
                 __syncthreads();
             }
-            for (int t = tid; t < T; t += RESIDENT_THREADS)  // mod.rs:543-578
-                fold_one<0, true>(
-                    m, st, 0, t, P > 0,
+            for (int idx = tid; idx < 12 * T; idx += RESIDENT_THREADS) {  // mod.rs:543-578: one thread per (temperature, running sum)
+                const int t = idx / 12;
+                fold_spread(
+                    m, st, 0, t, idx - 12 * t,
                     [&](int r) { return mag_sm[sid_sm[r * T + t]]; },
                     [&](int r) { return en_sm[sid_sm[r * T + t]]; },
                     [&](int p) { return dsp_sm[p * T + t]; },
                     [&](int p) { return dlk_sm[p * T + t]; });
+            }
             __syncthreads();
         }
         if (pt_this) {  // mod.rs:748-796
             if (T >= 2) {
-                if (tid < m.R) pt_exchange_body(m, pt, 0, tid, a.pt_schedule, parity, pt_event);
-                if (a.pt_schedule == 1) parity = 1 - parity;
+                if (a.pt_schedule == 0) {  // tempering.rs:20-42: edge, draw and ln u were prepared while the sweep ran
+                    if (tid < m.R) pt_attempt_edge_pre(m, pt, 0, tid, pt_edge, pt_logu, dbeta_sm[pt_edge]);
+                } else {
+                    if (tid < m.R) pt_exchange_body(m, pt, 0, tid, a.pt_schedule, parity, pt_event);
+                    parity = 1 - parity;
+                }
                 __syncthreads();
             }
             pt_event++;
@@ -716,7 +798,7 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
 inline size_t prows_resident_smem(int S, int T, int P, int z, int64_t N) {
     const size_t thr_words = ((size_t)T * (2 * z + 1) + 3) & ~size_t(3);
     const size_t cnt = 2 * (size_t)std::max(S, P * T);
-    return thr_words * 4 + resident_scalar_bytes(S, T, P) + (size_t)S * (size_t)(N / 32) * 4 + cnt * 4 + 16;
+    return thr_words * 4 + resident_scalar_bytes(S, T, P) + (size_t)S * (size_t)(N / 32) * 4 + cnt * 4 + (size_t)T * 4 + 16;
 }
 
 }  // namespace pp

@@ -151,6 +151,53 @@ __device__ __forceinline__ void fold_batch(const ModelView &m, const StatsView &
     __syncwarp();
 }
 
+// The same fold with one THREAD per running sum: thread j < 5 owns sum j of simulation/mod.rs:555-578, thread 5 + k sum k of
+// statistics/overlap.rs:283-306, thread 11 the histogram cells (12 consecutive threads per (d, t); the callers spread the (d, t)
+// over the block).  One uniform loop: every thread derives the terms of replica i and pair i and adds its own, so each sum receives
+// exactly fold_one's additions in fold_one's order — a thread's chain is R (or P) additions long instead of 5 R + 6 P.
+template <typename GetM, typename GetE, typename GetS, typename GetL>
+__device__ __forceinline__ void fold_spread(const ModelView &m, const StatsView &st, int64_t d, int t, int j, GetM get_m, GetE get_e,
+                                            GetS get_ds, GetL get_dl) {
+    const float nf = (float)m.N, nb = (float)(m.N * m.z);
+    const int64_t bins = m.N + 1;
+    const bool owns = j < 5 || (j < 11 && m.P > 0);
+    double *sum = st.sums + d * 11 * m.T + t + (int64_t)(j < 11 ? j : 0) * m.T;
+    double acc = owns ? *sum : 0.0;
+    const int n = m.R > m.P ? m.R : m.P;
+    for (int i = 0; i < n; i++) {
+        const bool hr = i < m.R, hp = i < m.P;
+        const float mag = __fdiv_rn((float)get_m(hr ? i : 0), nf);
+        const float m2 = __fmul_rn(mag, mag);
+        const float e = get_e(hr ? i : 0);
+        const long long dsp = m.P > 0 ? get_ds(hp ? i : 0) : 0ll;
+        const long long dlk = m.P > 0 ? get_dl(hp ? i : 0) : 0ll;
+        const float ql = __fdiv_rn((float)dlk, nb);
+        const float q = __fdiv_rn((float)dsp, nf);
+        const float q2 = __fmul_rn(q, q);
+        const float ql2 = __fmul_rn(ql, ql);
+        double term = 0.0;
+        term = j == 0 ? (double)mag : term;
+        term = j == 1 ? (double)m2 : term;
+        term = j == 2 ? (double)__fmul_rn(m2, m2) : term;
+        term = j == 3 ? (double)e : term;
+        term = j == 4 ? __dmul_rn((double)e, (double)e) : term;  // stats.rs:23: powi(2) in f64
+        term = j == 5 ? (double)q : term;
+        term = j == 6 ? (double)q2 : term;
+        term = j == 7 ? (double)__fmul_rn(q2, q2) : term;
+        term = j == 8 ? (double)ql : term;
+        term = j == 9 ? (double)ql2 : term;
+        term = j == 10 ? (double)__fmul_rn(ql2, ql2) : term;
+        if (owns && (j < 5 ? hr : hp)) acc = __dadd_rn(acc, term);
+        if (j == 11 && hp) {  // the histogram cells in pair order (two pairs of a sweep may hit the same cell)
+            const int64_t h = (d * m.T + t) * bins + (dsp + m.N) / 2;
+            atomicAdd(st.hist + h, 1u);
+            atomicAdd(st.ql_at_q + h, (double)ql);
+            atomicAdd(st.ql2_at_q + h, (double)ql2);
+        }
+    }
+    if (owns) *sum = acc;
+}
+
 // Same fold as fire-and-forget reductions (RED.ADD.F64 / RED.ADD.U32): no load, so the warp that finishes 32
 // realizations in the fused msc3d epilogue never waits on memory.  Every accumulator is touched by exactly one thread
 // per kernel and kernels of one chunk are stream-ordered, so each f64 cell still receives the reference's additions in
@@ -343,6 +390,26 @@ __device__ __forceinline__ bool pt_attempt_edge(const ModelView &m, const PtView
     const bool accepted = delta >= m.logtab[draw];
     const int64_t eb = d * (m.T - 1);
     // the T-1 edge counters of a realization are shared by its R replica threads
+    atomicAdd(&pt.edge_attempts[eb + edge], 1ull);
+    if (!accepted) return false;
+    sid[edge] = right;
+    sid[edge + 1] = left;
+    atomicAdd(&pt.edge_acceptances[eb + edge], 1ull);
+    pt_record_arrival(pt, d * m.S, left, edge + 1);   // realization.rs:80-81
+    pt_record_arrival(pt, d * m.S, right, edge);
+    return true;
+}
+
+// the same attempt with everything that does not depend on the energies prepared by the caller: log_u = logtab[draw] (fetched
+// while the sweep ran), dbeta = 1 / T_edge - 1 / T_edge+1 (the two f32 divisions and the subtraction of the expression above)
+__device__ __forceinline__ bool pt_attempt_edge_pre(const ModelView &m, const PtView &pt, int64_t d, int r, int edge, float log_u,
+                                                    float dbeta) {
+    int32_t *sid = m.system_ids + d * m.S + r * m.T;
+    const int left = sid[edge], right = sid[edge + 1];
+    const float energy_1 = m.energies[d * m.S + left], energy_2 = m.energies[d * m.S + right];
+    const float delta = __fmul_rn(__fmul_rn((float)m.N, __fsub_rn(energy_2, energy_1)), dbeta);
+    const bool accepted = delta >= log_u;
+    const int64_t eb = d * (m.T - 1);
     atomicAdd(&pt.edge_attempts[eb + edge], 1ull);
     if (!accepted) return false;
     sid[edge] = right;
