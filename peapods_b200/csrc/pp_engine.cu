@@ -241,6 +241,8 @@ struct pp_sim {
     // that the API and the int8-only kernels (cluster moves) see through prows_sync(): unpack before, pack after
     bool prows = false;
     bool resident_packed = false;                      // small ferromagnetic realizations: prows_resident_kernel instead of rows_resident_kernel
+    int resident_cluster = 0;                          // > 0: prows_cluster_resident_kernel, the systems of a realization over this many CTAs
+    int resident_cluster_threads = 0;
     size_t resident_packed_smem = 0;
     PRowsView pv{};
     int prows_nm[2] = {0, 0};                          // thresholds compared per site: [metropolis, gibbs]
@@ -1565,6 +1567,22 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 s->resident_packed = s->resident && m.coupling_class == COUP_FERRO && rp.L % 32 == 0 && dl1 && (z == 2 || z == 3) &&
                                      s->resident_packed_smem <= 200 * 1024;
                 if (const char *e = getenv("PP_RESIDENT_PACKED")) s->resident_packed = s->resident_packed && atoi(e) != 0;
+                // ... spread over a thread-block cluster: two colours, one row class, the systems divide evenly, <= 2 work items per thread
+                if (s->resident_packed && s->plan.n_colours == 2 && rp.m_half == 1 && !getenv("PP_NO_RESIDENT_CLUSTER")) {
+                    const int64_t sysw = rp.n_rows * (rp.L / 32);
+                    const int want_nc = getenv("PP_RESIDENT_CLUSTER") ? atoi(getenv("PP_RESIDENT_CLUSTER")) : 0;
+                    for (int nc : {8, 4, 2}) {
+                        if (want_nc > 0 && nc != want_nc) continue;
+                        if (m.S % nc != 0 || m.S / nc > 64 || sysw > 65535) continue;
+                        const int64_t items = (int64_t)(m.S / nc) * sysw;
+                        const int nt = (int)std::min<int64_t>(512, std::max<int64_t>(64, (items + 31) / 32 * 32));
+                        if (items > 2 * nt || nt < m.R) continue;
+                        if (cluster_resident_layout(m.S, m.T, m.P, z, nc, (int)sysw).total_bytes > 200 * 1024) continue;
+                        s->resident_cluster = nc;
+                        s->resident_cluster_threads = nt;
+                        break;
+                    }
+                }
                 v.packed_draws = s->resident_packed ? 1 : 0;
             }
             // ferromagnets with one bit per spin, a system resident in one CTA's shared memory (pp_kernels_prows.cuh): rows that
@@ -1886,7 +1904,30 @@ static pp_status run_rows_resident(pp_sim *s, Ctx &c, const pp_sample_cfg *cfg, 
     CUDA_TRY(cudaFuncSetAttribute(prows_resident_kernel<Z_, NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->resident_packed_smem)); \
     prows_resident_kernel<Z_, NM_><<<(unsigned)mk.D, PRES_THREADS, s->resident_packed_smem, c.stream>>>(mk, v, c.st, c.pt, a);      \
     } while (0)
-        if (s->resident_packed) {
+        if (s->resident_packed && s->resident_cluster > 0) {
+            const int nm = s->prows_nm[gibbs ? 1 : 0], nc = s->resident_cluster;
+            const size_t smem = cluster_resident_layout(mk.S, mk.T, mk.P, mk.z, nc, (int)(v.n_rows * (v.L / 32))).total_bytes;
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3((unsigned)(mk.D * nc));
+            lc.blockDim = dim3((unsigned)s->resident_cluster_threads);
+            lc.dynamicSmemBytes = smem;
+            lc.stream = c.stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)nc;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            lc.attrs = attr;
+            lc.numAttrs = 1;
+#define PP_CRES(Z_, NM_)                                                                                                              \
+    do {                                                                                                                              \
+    CUDA_TRY(cudaFuncSetAttribute(prows_cluster_resident_kernel<Z_, NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    CUDA_TRY(cudaLaunchKernelEx(&lc, prows_cluster_resident_kernel<Z_, NM_>, mk, v, c.st, c.pt, a, nc));                               \
+    } while (0)
+            if (mk.z == 2) { if (nm == 2) PP_CRES(2, 2); else PP_CRES(2, 5); }
+            else { if (nm == 3) PP_CRES(3, 3); else PP_CRES(3, 7); }
+#undef PP_CRES
+        } else if (s->resident_packed) {
             const int nm = s->prows_nm[gibbs ? 1 : 0];
             if (mk.z == 2) { if (nm == 2) PP_PRES(2, 2); else PP_PRES(2, 5); }
             else { if (nm == 3) PP_PRES(3, 3); else PP_PRES(3, 7); }

@@ -794,6 +794,403 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same small realizations spread over a thread-block CLUSTER (round 2; the one-CTA form above is bound by the instruction
+// throughput of its one SM: 13 instructions per attempt x 32 Ki attempts per sweep).  NC CTAs per realization, CTA c keeps the words
+// of the systems c S/NC .. (c + 1) S/NC - 1 in its shared memory for the whole launch; what crosses CTAs goes through distributed
+// shared memory:
+//   * after the colour passes a CTA counts bonds / down spins of its systems and stores energy (+ magnetisation sum) of each into the
+//     `en_all` / `mag_all` arrays of EVERY CTA of the cluster; one cluster barrier later every CTA holds all S values;
+//   * every CTA then replays the exchange on its own copy of system_ids / counters (same draws, same energies: identical decisions,
+//     tempering.rs:20-102) — no broadcast of the result is needed; rank 0's copy is written back at the end;
+//   * recorded sweeps: the pair (replica 2p, replica 2p + 1) at slot t is handled by a warp of the CTA that owns the first system,
+//     reading the partner's words through DSMEM (overlap.rs:259-281); the dots go to the CTA that folds temperature t (t mod NC), which
+//     keeps the 11 running sums of its temperatures in shared memory for the whole launch (mod.rs:543-578 as fold_spread);
+//   * one cluster barrier per sweep with an exchange, two per recorded sweep; everything that is stored remotely is double-buffered
+//     by sweep parity (a CTA may be most of a sweep ahead of another).
+// Requirements (host-checked): two colours, one row class (m_half = 1), S a multiple of NC, work items <= 2 per thread.
+struct ClusterResidentLayout {  // word offsets into the dynamic shared memory of one CTA (all 8-byte aligned blocks first)
+    size_t sums, mag_all, dsp_all, dlk_all, ea, eacc, rt, en_all, temps, dbeta, sid, cnt, thr, pw, trip, total_bytes;
+};
+__host__ __device__ inline ClusterResidentLayout cluster_resident_layout(int S, int T, int P, int z, int nc, int sysw) {
+    ClusterResidentLayout l;
+    const size_t n_edges = T > 1 ? (size_t)(T - 1) : 1;
+    size_t o = 0;  // in bytes
+    l.sums = o; o += 8 * (size_t)11 * T;
+    l.mag_all = o; o += 8 * 2 * (size_t)S;
+    l.dsp_all = o; o += 8 * 2 * (size_t)(P * T > 0 ? P * T : 1);
+    l.dlk_all = o; o += 8 * 2 * (size_t)(P * T > 0 ? P * T : 1);
+    l.ea = o; o += 8 * n_edges;
+    l.eacc = o; o += 8 * n_edges;
+    l.rt = o; o += 8 * (size_t)S;
+    l.en_all = o; o += 4 * 2 * (size_t)S;
+    l.temps = o; o += 4 * (size_t)T;
+    l.dbeta = o; o += 4 * n_edges;
+    l.sid = o; o += 4 * (size_t)S;
+    l.cnt = o; o += 4 * 2 * (size_t)(S / nc);
+    l.thr = o; o += 4 * (size_t)T * (2 * z + 1);
+    o = (o + 15) & ~size_t(15);
+    l.pw = o; o += 4 * (size_t)(S / nc) * sysw;
+    l.trip = o; o += (size_t)S;
+    l.total_bytes = (o + 15) & ~size_t(15);
+    return l;
+}
+
+template <int Z, int NM>
+__global__ void __launch_bounds__(512)
+prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, ResidentArgs a, int NC) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char cres_sm[];
+    constexpr int Z2 = 2 * Z, NTH = 2 * Z + 1;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = NT >> 5;
+    const int rank = (int)(blockIdx.x % NC);
+    const int64_t dg = blockIdx.x / NC;
+    const int S = mg.S, T = mg.T, P = mg.P, L = vg.L, W = L / 32;
+    const int n_rows = (int)vg.n_rows, sysw = n_rows * W, SPC = S / NC, sys0 = rank * SPC;  // this CTA owns systems sys0 .. sys0 + SPC - 1
+    const ClusterResidentLayout lay = cluster_resident_layout(S, T, P, Z, NC, sysw);
+    double *sums_sm = reinterpret_cast<double *>(cres_sm + lay.sums);
+    long long *mag_all = reinterpret_cast<long long *>(cres_sm + lay.mag_all);  // [2][S] by sweep parity
+    long long *dsp_all = reinterpret_cast<long long *>(cres_sm + lay.dsp_all);  // [2][P * T]
+    long long *dlk_all = reinterpret_cast<long long *>(cres_sm + lay.dlk_all);
+    unsigned long long *ea_sm = reinterpret_cast<unsigned long long *>(cres_sm + lay.ea);
+    unsigned long long *eacc_sm = reinterpret_cast<unsigned long long *>(cres_sm + lay.eacc);
+    unsigned long long *rt_sm = reinterpret_cast<unsigned long long *>(cres_sm + lay.rt);
+    float *en_all = reinterpret_cast<float *>(cres_sm + lay.en_all);            // [2][S]
+    float *temps_sm = reinterpret_cast<float *>(cres_sm + lay.temps), *dbeta_sm = reinterpret_cast<float *>(cres_sm + lay.dbeta);
+    int32_t *sid_sm = reinterpret_cast<int32_t *>(cres_sm + lay.sid);
+    int *cnt_sm = reinterpret_cast<int *>(cres_sm + lay.cnt);                   // [2 * SPC]
+    uint32_t *thr_sm = reinterpret_cast<uint32_t *>(cres_sm + lay.thr);
+    uint32_t *pw = reinterpret_cast<uint32_t *>(cres_sm + lay.pw);              // [SPC][rows][W]
+    uint8_t *trip_sm = cres_sm + lay.trip;
+    int8_t *g_spins = mg.spins + dg * S * mg.N;
+    const int64_t bins = mg.N + 1;
+    const int PT_ = P * T;
+
+    for (int i = tid; i < T * NTH; i += NT) {
+        const int u = i % NTH;
+        const uint32_t c = mg.lut[(i / NTH) * (4 * Z + 1) + 2 * u];  // sweep.rs:162-166, index ec + 2z' = 2 * unsat
+        thr_sm[i] = (NM == Z && u < Z) ? c << 8 : c;
+    }
+    for (int i = tid; i < 11 * T; i += NT) sums_sm[i] = stg.sums[dg * 11 * T + i];
+    for (int i = tid; i < S; i += NT) {
+        sid_sm[i] = mg.system_ids[dg * S + i];
+        rt_sm[i] = ptg.round_trips[dg * S + i];
+        trip_sm[i] = ptg.trip_state[dg * S + i];
+    }
+    for (int i = tid; i < T - 1; i += NT) {
+        ea_sm[i] = ptg.edge_attempts[dg * (T - 1) + i];
+        eacc_sm[i] = ptg.edge_acceptances[dg * (T - 1) + i];
+        dbeta_sm[i] = __fsub_rn(__fdiv_rn(1.0f, mg.temps[i]), __fdiv_rn(1.0f, mg.temps[i + 1]));
+    }
+    for (int i = tid; i < T; i += NT) temps_sm[i] = mg.temps[i];
+    for (int i = tid; i < SPC * sysw; i += NT) {  // pack the CTA's systems: 32 consecutive sites -> one word (bit = 1: spin -1)
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_spins + ((int64_t)sys0 * sysw + i) * 32);
+        uint32_t word = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint4 q4 = src[h];
+            const uint32_t part[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t sg = part[j] & 0x80808080u;
+                word |= (((sg >> 7) & 1u) | ((sg >> 14) & 2u) | ((sg >> 21) & 4u) | ((sg >> 28) & 8u)) << (16 * h + 4 * j);
+            }
+        }
+        pw[i] = word;
+    }
+    ModelView m = mg;
+    m.D = 1;
+    m.sample_offset = mg.sample_offset + dg;
+    m.system_ids = sid_sm;
+    m.temps = temps_sm;
+    StatsView st = stg;
+    st.sums = sums_sm;
+    if (stg.hist) {
+        st.hist = stg.hist + dg * T * bins;
+        st.ql_at_q = stg.ql_at_q + dg * T * bins;
+        st.ql2_at_q = stg.ql2_at_q + dg * T * bins;
+    }
+    PtView pt = ptg;
+    pt.edge_attempts = ea_sm;
+    pt.edge_acceptances = eacc_sm;
+    pt.round_trips = rt_sm;
+    pt.trip_state = trip_sm;
+    const uint64_t key = vg.keys[dg];
+    const PhiloxKeys ks = philox_keys((uint32_t)key, (uint32_t)(key >> 32));
+    int dls[Z];
+#pragma unroll
+    for (int k = 0; k < Z; k++) dls[k] = vg.dl[k];
+    auto nbr_word = [&](const uint32_t *sys, const uint32_t nr, const int w, const int sh) {
+        const uint32_t *row = sys + (size_t)nr * W;
+        const uint32_t c = row[w];
+        if (sh == 0) return c;
+        if (sh > 0) return (c >> 1) | (row[w + 1 == W ? 0 : w + 1] << 31);
+        return (c << 1) | (row[w ? w - 1 : W - 1] >> 31);
+    };
+    const int half_l = L / 2;
+    // the thread's work items (words of the CTA's systems): resolved once, the same in every colour pass (see prows_resident_kernel)
+    constexpr int HOIST = 2;
+    const uint32_t per_sys0 = (uint32_t)n_rows * (uint32_t)W;
+    int h_ls[HOIST], h_a[HOIST];  // local system, row phase
+    uint32_t h_own[HOIST], h_q[HOIST], h_h[HOIST];
+    uint16_t h_n0[HOIST][Z2], h_n1[HOIST][Z2];
+#pragma unroll
+    for (int j = 0; j < HOIST; j++) {
+        h_ls[j] = -1;
+        const uint32_t it = (uint32_t)tid + (uint32_t)j * (uint32_t)NT;
+        if (it < (uint32_t)SPC * per_sys0) {
+            const int ls = (int)(it / per_sys0);
+            const uint32_t rem = it - (uint32_t)ls * per_sys0, r = rem / (uint32_t)W;
+            const int w = (int)(rem - r * (uint32_t)W);
+            h_ls[j] = ls;
+            h_a[j] = (int)vg.row_a[r];
+            h_own[j] = rem;
+            const uint32_t base = vg.row_ord[r] * (uint32_t)half_l + 16u * (uint32_t)w;
+            h_q[j] = base >> 5;
+            h_h[j] = (base >> 4) & 1u;
+#pragma unroll
+            for (int k = 0; k < Z; k++)
+#pragma unroll
+                for (int sgn = 0; sgn < 2; sgn++) {
+                    const uint32_t nr = vg.nbr_row[((size_t)r * Z + k) * 2 + sgn];
+                    const int sh = sgn ? -dls[k] : dls[k];
+                    const int wa = sh > 0 ? (w + 1 == W ? 0 : w + 1) : sh < 0 ? (w ? w - 1 : W - 1) : w;
+                    h_n0[j][2 * k + sgn] = (uint16_t)(nr * (uint32_t)W + (uint32_t)w);
+                    h_n1[j][2 * k + sgn] = (uint16_t)(nr * (uint32_t)W + (uint32_t)wa);
+                }
+        }
+    }
+    __syncthreads();
+    // slot of each of the CTA's systems (the inverse of system_ids restricted to this CTA), rebuilt after every exchange
+    __shared__ int slot_of[64];
+    auto rebuild_slots = [&]() {
+        for (int slot = tid; slot < S; slot += NT) {
+            const int sy = sid_sm[slot] - sys0;
+            if (sy >= 0 && sy < SPC) slot_of[sy] = slot;
+        }
+    };
+    rebuild_slots();
+    cluster.sync();  // every CTA's shared memory is initialised before anyone stores into it
+    uint32_t pt_event = a.pt_event0;
+    int parity = a.parity0;
+    int last_e = -1, last_m = -1, last_d = -1;  // buffer of the last energies / magnetisations / pair dots of this launch
+    int sync_n = 0;  // sweeps with a cluster barrier so far: the remotely written buffers alternate with THEM (between two such
+                     // sweeps no barrier keeps a CTA from running ahead)
+    for (int sw = 0; sw < a.n_sweeps; sw++) {
+        const int64_t sid = a.sweep_id0 + sw;
+        const uint32_t sweep_index = a.sweep_counter0 + (uint32_t)sw;
+        const bool record = sid >= a.warmup_sweeps;
+        const bool pt_this = a.pt_interval > 0 && sid % a.pt_interval == 0;
+        const int par = sync_n & 1;
+        if (record || pt_this) sync_n++;
+        int pt_edge = 0;
+        float pt_logu = 0.0f;
+        if (a.pt_schedule == 0 && T >= 2 && tid < m.R && pt_this) {  // prepared while the sweep runs (see prows_resident_kernel)
+            const u32x4 o = philox4x32(0xFFFFFFFFu, pt_event, (uint32_t)tid, TAG_PT, (uint32_t)key, (uint32_t)(key >> 32));
+            pt_edge = (int)(((uint64_t)o.y * (uint64_t)(T - 1)) >> 32);
+            pt_logu = m.logtab[o.x >> 8];
+        }
+        for (int colour = 0; colour < 2; colour++) {
+            const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
+#pragma unroll
+            for (int j = 0; j < HOIST; j++) {
+                if (h_ls[j] < 0) continue;
+                const int slot = slot_of[h_ls[j]], sysl = sys0 + h_ls[j];
+                uint32_t *sys = pw + (size_t)h_ls[j] * sysw;
+                const uint32_t C = sys[h_own[j]];
+                uint32_t b[Z2];
+#pragma unroll
+                for (int k = 0; k < Z; k++)
+#pragma unroll
+                    for (int sgn = 0; sgn < 2; sgn++) {
+                        const int sh = sgn ? -dls[k] : dls[k];
+                        const uint32_t c0 = sys[h_n0[j][2 * k + sgn]];
+                        uint32_t nw = c0;
+                        if (sh > 0) nw = (c0 >> 1) | (sys[h_n1[j][2 * k + sgn]] << 31);
+                        else if (sh < 0) nw = (c0 << 1) | (sys[h_n1[j][2 * k + sgn]] >> 31);
+                        b[2 * k + sgn] = C ^ nw;
+                    }
+                const int p = h_a[j] == colour ? 0 : 1;
+                const uint32_t *thr = thr_sm + (slot % T) * NTH;  // realization.rs:166
+                uint32_t un[4];
+                prows_count<Z2>(b, un);
+                uint32_t Tm[NM], M[NM];
+#pragma unroll
+                for (int u = 0; u < NM; u++) { Tm[u] = thr[u]; M[u] = 0u; }
+                uint32_t wd[12];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const u32x4 o = philox4x32_k(h_q[j], sweep_index, (uint32_t)sysl, tagc | ((3u * h_h[j] + (uint32_t)c) << 8), ks);
+                    wd[4 * c] = o.x; wd[4 * c + 1] = o.y; wd[4 * c + 2] = o.z; wd[4 * c + 3] = o.w;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t A = wd[3 * g], B = wd[3 * g + 1], Cw = wd[3 * g + 2];
+                    const uint32_t y3 = __byte_perm(__byte_perm(Cw, B, 0x0400), A, 0x4210);
+                    const uint32_t ys[4] = {A, B, Cw, y3};
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        const uint32_t bit = 1u << (2 * (4 * g + jj));
+                        const uint32_t y = NM == Z ? ys[jj] : ys[jj] >> 8;
+#pragma unroll
+                        for (int u = 0; u < NM; u++)
+                            if (y < Tm[u]) M[u] |= bit;
+                    }
+                }
+                uint32_t flip = 0u;
+#pragma unroll
+                for (int u = 0; u <= Z2; u++) {
+                    const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
+                    flip |= u < NM ? (eq & (M[u] << p)) : eq;
+                }
+                sys[h_own[j]] = C ^ (flip & (0x55555555u << p));
+            }
+            __syncthreads();
+        }
+        if (record || pt_this) {  // mod.rs:486-509; energy.rs:99-108 for the CTA's systems, results to every CTA of the cluster
+            for (int i = tid; i < 2 * SPC; i += NT) cnt_sm[i] = 0;
+            __syncthreads();
+            for (int i0 = (tid & ~31); i0 < SPC * sysw; i0 += NT) {
+                const int i = i0 + lane;
+                const bool live = i < SPC * sysw;
+                const int ls = live ? i / sysw : -1;
+                int unsat = 0, dn = 0;
+                if (live) {
+                    const int rem = i - ls * sysw, r = rem / W, w = rem - r * W;
+                    const uint32_t *sys = pw + (size_t)ls * sysw;
+                    const uint32_t C = sys[rem];
+#pragma unroll
+                    for (int k = 0; k < Z; k++) unsat += __popc(C ^ nbr_word(sys, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]));
+                    dn = __popc(C);
+                }
+                if (__all_sync(0xFFFFFFFFu, ls == __shfl_sync(0xFFFFFFFFu, ls, 0))) {
+                    unsat = __reduce_add_sync(0xFFFFFFFFu, unsat);
+                    dn = __reduce_add_sync(0xFFFFFFFFu, dn);
+                    if (lane == 0 && live) { atomicAdd(&cnt_sm[2 * ls], unsat); atomicAdd(&cnt_sm[2 * ls + 1], dn); }
+                } else if (live) {
+                    atomicAdd(&cnt_sm[2 * ls], unsat);
+                    atomicAdd(&cnt_sm[2 * ls + 1], dn);
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < SPC * NC; i += NT) {  // (system, destination CTA)
+                const int ls = i / NC, dst = i - ls * NC;
+                const float e = __fdiv_rn((float)((long long)Z * m.N - 2ll * cnt_sm[2 * ls]), (float)m.N);
+                *cluster.map_shared_rank(&en_all[par * S + sys0 + ls], dst) = e;
+                if (record) *cluster.map_shared_rank(&mag_all[par * S + sys0 + ls], dst) = m.N - 2ll * cnt_sm[2 * ls + 1];
+            }
+            last_e = par;
+            if (record) last_m = par;
+            cluster.sync();  // A: all S energies (+ magnetisation sums) of this sweep are in every CTA
+        }
+        m.energies = en_all + par * S;
+        m.mags = mag_all + par * S;
+        if (record) {
+            if (P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids; one warp per pair, owner = first system's CTA
+                int mine = 0;
+                for (int idx = 0; idx < PT_; idx++) {
+                    const int t = idx % T, pr = idx / T;
+                    const int sa = sid_sm[(2 * pr) * T + t], sb = sid_sm[(2 * pr + 1) * T + t];
+                    if (sa < sys0 || sa >= sys0 + SPC) continue;
+                    if ((mine++ % n_warps) != warp) continue;
+                    const uint32_t *wa = pw + (size_t)(sa - sys0) * sysw;
+                    const int ob = sb / SPC;
+                    const uint32_t *wb = cluster.map_shared_rank(pw, ob) + (size_t)(sb - ob * SPC) * sysw;
+                    int neg_q = 0, neg_l = 0;
+                    for (int i = lane; i < sysw; i += 32) {
+                        const int r = i / W, w = i - r * W;
+                        const uint32_t x = wa[i] ^ wb[i];
+                        neg_q += __popc(x);
+#pragma unroll
+                        for (int k = 0; k < Z; k++) {
+                            const uint32_t nr = vg.nbr_row[((size_t)r * Z + k) * 2];
+                            neg_l += __popc(x ^ nbr_word(wa, nr, w, dls[k]) ^ nbr_word(wb, nr, w, dls[k]));
+                        }
+                    }
+                    neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
+                    neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
+                    if (lane == 0) {  // to the CTA that folds temperature t
+                        *cluster.map_shared_rank(&dsp_all[par * PT_ + idx], t % NC) = m.N - 2ll * neg_q;
+                        *cluster.map_shared_rank(&dlk_all[par * PT_ + idx], t % NC) = (long long)Z * m.N - 2ll * neg_l;
+                    }
+                }
+                last_d = par;
+                cluster.sync();  // B: the dots are with their folding CTAs; nobody reads another CTA's words any more
+            }
+            st.dot_spin = dsp_all + par * PT_;
+            st.dot_link = dlk_all + par * PT_;
+            const int n_own = (T - rank + NC - 1) / NC;  // temperatures rank, rank + NC, ...
+            for (int idx = tid; idx < 12 * n_own; idx += NT) {  // mod.rs:543-578: one thread per (temperature, running sum)
+                const int t = rank + (idx / 12) * NC;
+                fold_spread(
+                    m, st, 0, t, idx % 12,
+                    [&](int r) { return m.mags[sid_sm[r * T + t]]; },
+                    [&](int r) { return m.energies[sid_sm[r * T + t]]; },
+                    [&](int p) { return st.dot_spin[p * T + t]; },
+                    [&](int p) { return st.dot_link[p * T + t]; });
+            }
+            __syncthreads();  // the fold read system_ids: the exchange below changes them
+        }
+        if (pt_this) {  // mod.rs:748-796, replayed identically by every CTA on its own copy
+            if (T >= 2) {
+                if (a.pt_schedule == 0) {
+                    if (tid < m.R) pt_attempt_edge_pre(m, pt, 0, tid, pt_edge, pt_logu, dbeta_sm[pt_edge]);
+                } else {
+                    if (tid < m.R) pt_exchange_body(m, pt, 0, tid, a.pt_schedule, parity, pt_event);
+                    parity = 1 - parity;
+                }
+                __syncthreads();
+                rebuild_slots();
+                __syncthreads();
+            }
+            pt_event++;
+        }
+    }
+    cluster.sync();  // no CTA leaves (or rewrites global state) while another may still address its shared memory
+    const int n_own = (T - rank + NC - 1) / NC;
+    for (int i = tid; i < 11 * n_own; i += NT) {
+        const int t = rank + (i / 11) * NC, k = i % 11;
+        stg.sums[dg * 11 * T + (int64_t)k * T + t] = sums_sm[k * T + t];
+    }
+    if (last_d >= 0)
+        for (int i = tid; i < P * n_own; i += NT) {
+            const int t = rank + (i / P) * NC, pr = i % P;
+            const_cast<long long *>(stg.dot_spin)[dg * PT_ + pr * T + t] = dsp_all[last_d * PT_ + pr * T + t];
+            const_cast<long long *>(stg.dot_link)[dg * PT_ + pr * T + t] = dlk_all[last_d * PT_ + pr * T + t];
+        }
+    for (int i = tid; i < SPC; i += NT) {
+        if (last_e >= 0) mg.energies[dg * S + sys0 + i] = en_all[last_e * S + sys0 + i];
+        if (last_m >= 0) mg.mags[dg * S + sys0 + i] = mag_all[last_m * S + sys0 + i];
+    }
+    if (rank == 0) {
+        for (int i = tid; i < S; i += NT) {
+            mg.system_ids[dg * S + i] = sid_sm[i];
+            ptg.round_trips[dg * S + i] = rt_sm[i];
+            ptg.trip_state[dg * S + i] = trip_sm[i];
+        }
+        for (int i = tid; i < T - 1; i += NT) {
+            ptg.edge_attempts[dg * (T - 1) + i] = ea_sm[i];
+            ptg.edge_acceptances[dg * (T - 1) + i] = eacc_sm[i];
+        }
+    }
+    for (int i = tid; i < SPC * sysw; i += NT) {  // unpack: +1 = 0x01, -1 = 0xFF
+        const uint32_t word = pw[i];
+        uint4 *dst = reinterpret_cast<uint4 *>(g_spins + ((int64_t)sys0 * sysw + i) * 32);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t part[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t nib = (word >> (16 * h + 4 * j)) & 15u;
+                const uint32_t spread = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                part[j] = 0x01010101u ^ (spread * 0xFEu);
+            }
+            dst[h] = make_uint4(part[0], part[1], part[2], part[3]);
+        }
+    }
+}
+
 // shared memory of prows_resident_kernel
 inline size_t prows_resident_smem(int S, int T, int P, int z, int64_t N) {
     const size_t thr_words = ((size_t)T * (2 * z + 1) + 3) & ~size_t(3);
