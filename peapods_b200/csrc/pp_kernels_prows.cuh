@@ -738,7 +738,7 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
             }
             for (int idx = tid; idx < 12 * T; idx += RESIDENT_THREADS) {  // mod.rs:543-578: one thread per (temperature, running sum)
                 const int t = idx / 12;
-                fold_spread(
+                fold_spread<true>(
                     m, st, 0, t, idx - 12 * t,
                     [&](int r) { return mag_sm[sid_sm[r * T + t]]; },
                     [&](int r) { return en_sm[sid_sm[r * T + t]]; },
@@ -810,7 +810,7 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
 //     by sweep parity (a CTA may be most of a sweep ahead of another).
 // Requirements (host-checked): two colours, one row class (m_half = 1), S a multiple of NC, work items <= 2 per thread.
 struct ClusterResidentLayout {  // word offsets into the dynamic shared memory of one CTA (all 8-byte aligned blocks first)
-    size_t sums, mag_all, dsp_all, dlk_all, ea, eacc, rt, en_all, temps, dbeta, sid, cnt, thr, pw, trip, total_bytes;
+    size_t sums, mag_all, dsp_all, dlk_all, ea, eacc, rt, en_all, temps, dbeta, sid, cnt, thr, pw, xs, trip, total_bytes;
 };
 __host__ __device__ inline ClusterResidentLayout cluster_resident_layout(int S, int T, int P, int z, int nc, int sysw) {
     ClusterResidentLayout l;
@@ -831,6 +831,7 @@ __host__ __device__ inline ClusterResidentLayout cluster_resident_layout(int S, 
     l.thr = o; o += 4 * (size_t)T * (2 * z + 1);
     o = (o + 15) & ~size_t(15);
     l.pw = o; o += 4 * (size_t)(S / nc) * sysw;
+    l.xs = o; o += 4 * (size_t)16 * sysw;  // one XOR-word scratch per warp (<= 16 warps)
     l.trip = o; o += (size_t)S;
     l.total_bytes = (o + 15) & ~size_t(15);
     return l;
@@ -862,6 +863,7 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
     int *cnt_sm = reinterpret_cast<int *>(cres_sm + lay.cnt);                   // [2 * SPC]
     uint32_t *thr_sm = reinterpret_cast<uint32_t *>(cres_sm + lay.thr);
     uint32_t *pw = reinterpret_cast<uint32_t *>(cres_sm + lay.pw);              // [SPC][rows][W]
+    uint32_t *xs_sm = reinterpret_cast<uint32_t *>(cres_sm + lay.xs);           // [warps][rows][W]
     uint8_t *trip_sm = cres_sm + lay.trip;
     int8_t *g_spins = mg.spins + dg * S * mg.N;
     const int64_t bins = mg.N + 1;
@@ -961,6 +963,8 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                 }
         }
     }
+    // one work item per thread and a system per warp (the quickstart: 32 row words per system): the counts need no shared memory
+    const bool warp_is_system = sysw == 32 && NT == SPC * 32 && NC <= 32;
     __syncthreads();
     // slot of each of the CTA's systems (the inverse of system_ids restricted to this CTA), rebuilt after every exchange
     __shared__ int slot_of[64];
@@ -974,7 +978,21 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
     cluster.sync();  // every CTA's shared memory is initialised before anyone stores into it
     uint32_t pt_event = a.pt_event0;
     int parity = a.parity0;
+    // single-edge exchange: edge, draw and ln u (a read of the 64 MiB table: a DRAM round trip) depend on (event, replica) only; they
+    // are prepared for the NEXT event between the arrive and the wait of a cluster barrier, where the threads would only wait
+    int pt_edge = 0;
+    float pt_logu = 0.0f;
+    const bool pt_prep = a.pt_schedule == 0 && T >= 2 && tid < m.R && a.pt_interval > 0;
+    auto prepare_exchange = [&](const uint32_t event) {
+        const u32x4 o = philox4x32(0xFFFFFFFFu, event, (uint32_t)tid, TAG_PT, (uint32_t)key, (uint32_t)(key >> 32));
+        pt_edge = (int)(((uint64_t)o.y * (uint64_t)(T - 1)) >> 32);
+        pt_logu = m.logtab[o.x >> 8];
+    };
+    if (pt_prep) prepare_exchange(pt_event);
     int last_e = -1, last_m = -1, last_d = -1;  // buffer of the last energies / magnetisations / pair dots of this launch
+#ifdef PP_PROWS_TIMING
+    unsigned long long clk_last_ = clock64();
+#endif
     int sync_n = 0;  // sweeps with a cluster barrier so far: the remotely written buffers alternate with THEM (between two such
                      // sweeps no barrier keeps a CTA from running ahead)
     for (int sw = 0; sw < a.n_sweeps; sw++) {
@@ -984,13 +1002,10 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
         const bool pt_this = a.pt_interval > 0 && sid % a.pt_interval == 0;
         const int par = sync_n & 1;
         if (record || pt_this) sync_n++;
-        int pt_edge = 0;
-        float pt_logu = 0.0f;
-        if (a.pt_schedule == 0 && T >= 2 && tid < m.R && pt_this) {  // prepared while the sweep runs (see prows_resident_kernel)
-            const u32x4 o = philox4x32(0xFFFFFFFFu, pt_event, (uint32_t)tid, TAG_PT, (uint32_t)key, (uint32_t)(key >> 32));
-            pt_edge = (int)(((uint64_t)o.y * (uint64_t)(T - 1)) >> 32);
-            pt_logu = m.logtab[o.x >> 8];
-        }
+        int cur_edge = pt_edge;      // the exchange after THIS sweep (prepared before the loop or under an earlier barrier)
+        float cur_logu = pt_logu;
+        bool prepared_next = false;  // pt_edge / pt_logu already hold the event after this sweep's
+        PROWS_CLK(7);
         for (int colour = 0; colour < 2; colour++) {
             const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
 #pragma unroll
@@ -1048,7 +1063,30 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
             }
             __syncthreads();
         }
+        PROWS_CLK(0);
         if (record || pt_this) {  // mod.rs:486-509; energy.rs:99-108 for the CTA's systems, results to every CTA of the cluster
+            if (warp_is_system) {  // a warp's work items are exactly one system: totals by REDUX, lanes 0 .. NC - 1 deliver them
+                int unsat = 0, dn = 0;
+                const int ls = h_ls[0];
+                const uint32_t *sys = pw + (size_t)ls * sysw;
+                const uint32_t C = sys[h_own[0]];
+#pragma unroll
+                for (int k = 0; k < Z; k++) {
+                    const uint32_t c0 = sys[h_n0[0][2 * k]];
+                    uint32_t nw = c0;
+                    if (dls[k] > 0) nw = (c0 >> 1) | (sys[h_n1[0][2 * k]] << 31);
+                    else if (dls[k] < 0) nw = (c0 << 1) | (sys[h_n1[0][2 * k]] >> 31);
+                    unsat += __popc(C ^ nw);
+                }
+                dn = __popc(C);
+                unsat = __reduce_add_sync(0xFFFFFFFFu, unsat);
+                dn = __reduce_add_sync(0xFFFFFFFFu, dn);
+                if (lane < NC) {
+                    const float e = __fdiv_rn((float)((long long)Z * m.N - 2ll * unsat), (float)m.N);
+                    *cluster.map_shared_rank(&en_all[par * S + sys0 + ls], lane) = e;
+                    if (record) *cluster.map_shared_rank(&mag_all[par * S + sys0 + ls], lane) = m.N - 2ll * dn;
+                }
+            } else {
             for (int i = tid; i < 2 * SPC; i += NT) cnt_sm[i] = 0;
             __syncthreads();
             for (int i0 = (tid & ~31); i0 < SPC * sysw; i0 += NT) {
@@ -1080,33 +1118,44 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                 *cluster.map_shared_rank(&en_all[par * S + sys0 + ls], dst) = e;
                 if (record) *cluster.map_shared_rank(&mag_all[par * S + sys0 + ls], dst) = m.N - 2ll * cnt_sm[2 * ls + 1];
             }
+            }
             last_e = par;
             if (record) last_m = par;
-            cluster.sync();  // A: all S energies (+ magnetisation sums) of this sweep are in every CTA
+            PROWS_CLK(1);
+            // A: all S energies (+ magnetisation sums) of this sweep are in every CTA
+            if (record && P > 0) {  // (a recorded sweep has barrier B further down to prepare the next exchange under)
+                cluster.sync();
+            } else {
+                asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+                cur_edge = pt_edge; cur_logu = pt_logu;
+                if (pt_prep) prepare_exchange(pt_event + (pt_this ? 1u : 0u));
+                asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+                prepared_next = true;
+            }
+            PROWS_CLK(2);
         }
         m.energies = en_all + par * S;
         m.mags = mag_all + par * S;
         if (record) {
-            if (P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids; one warp per pair, owner = first system's CTA
-                int mine = 0;
-                for (int idx = 0; idx < PT_; idx++) {
+            if (P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids: pair idx goes to warp idx / NC of CTA idx % NC,
+                          // which fetches both replicas' words through DSMEM (two loads per lane in flight together), keeps the XOR
+                          // words in its own scratch and takes the link terms from there
+                uint32_t *X = xs_sm + (size_t)warp * sysw;
+                for (int idx = rank + NC * warp; idx < PT_; idx += NC * n_warps) {
                     const int t = idx % T, pr = idx / T;
                     const int sa = sid_sm[(2 * pr) * T + t], sb = sid_sm[(2 * pr + 1) * T + t];
-                    if (sa < sys0 || sa >= sys0 + SPC) continue;
-                    if ((mine++ % n_warps) != warp) continue;
-                    const uint32_t *wa = pw + (size_t)(sa - sys0) * sysw;
-                    const int ob = sb / SPC;
+                    const int oa = sa / SPC, ob = sb / SPC;
+                    const uint32_t *wa = cluster.map_shared_rank(pw, oa) + (size_t)(sa - oa * SPC) * sysw;
                     const uint32_t *wb = cluster.map_shared_rank(pw, ob) + (size_t)(sb - ob * SPC) * sysw;
+                    for (int i = lane; i < sysw; i += 32) X[i] = wa[i] ^ wb[i];
+                    __syncwarp();
                     int neg_q = 0, neg_l = 0;
                     for (int i = lane; i < sysw; i += 32) {
                         const int r = i / W, w = i - r * W;
-                        const uint32_t x = wa[i] ^ wb[i];
+                        const uint32_t x = X[i];
                         neg_q += __popc(x);
 #pragma unroll
-                        for (int k = 0; k < Z; k++) {
-                            const uint32_t nr = vg.nbr_row[((size_t)r * Z + k) * 2];
-                            neg_l += __popc(x ^ nbr_word(wa, nr, w, dls[k]) ^ nbr_word(wb, nr, w, dls[k]));
-                        }
+                        for (int k = 0; k < Z; k++) neg_l += __popc(x ^ nbr_word(X, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]));
                     }
                     neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
                     neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
@@ -1114,16 +1163,24 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                         *cluster.map_shared_rank(&dsp_all[par * PT_ + idx], t % NC) = m.N - 2ll * neg_q;
                         *cluster.map_shared_rank(&dlk_all[par * PT_ + idx], t % NC) = (long long)Z * m.N - 2ll * neg_l;
                     }
+                    __syncwarp();
                 }
                 last_d = par;
-                cluster.sync();  // B: the dots are with their folding CTAs; nobody reads another CTA's words any more
+                PROWS_CLK(3);
+                // B: the dots are with their folding CTAs; nobody reads another CTA's words any more
+                asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+                cur_edge = pt_edge; cur_logu = pt_logu;
+                if (pt_prep) prepare_exchange(pt_event + (pt_this ? 1u : 0u));
+                asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+                prepared_next = true;
+                PROWS_CLK(4);
             }
             st.dot_spin = dsp_all + par * PT_;
             st.dot_link = dlk_all + par * PT_;
             const int n_own = (T - rank + NC - 1) / NC;  // temperatures rank, rank + NC, ...
             for (int idx = tid; idx < 12 * n_own; idx += NT) {  // mod.rs:543-578: one thread per (temperature, running sum)
                 const int t = rank + (idx / 12) * NC;
-                fold_spread(
+                fold_spread<true>(
                     m, st, 0, t, idx % 12,
                     [&](int r) { return m.mags[sid_sm[r * T + t]]; },
                     [&](int r) { return m.energies[sid_sm[r * T + t]]; },
@@ -1131,21 +1188,30 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                     [&](int p) { return st.dot_link[p * T + t]; });
             }
             __syncthreads();  // the fold read system_ids: the exchange below changes them
+            PROWS_CLK(5);
         }
         if (pt_this) {  // mod.rs:748-796, replayed identically by every CTA on its own copy
             if (T >= 2) {
                 if (a.pt_schedule == 0) {
-                    if (tid < m.R) pt_attempt_edge_pre(m, pt, 0, tid, pt_edge, pt_logu, dbeta_sm[pt_edge]);
+                    if (tid < m.R && pt_attempt_edge_pre(m, pt, 0, tid, cur_edge, cur_logu, dbeta_sm[cur_edge])) {
+                        // the two systems changed slots (different replicas never touch the same systems)
+                        const int s_lo = sid_sm[tid * T + cur_edge] - sys0, s_hi = sid_sm[tid * T + cur_edge + 1] - sys0;
+                        if (s_lo >= 0 && s_lo < SPC) slot_of[s_lo] = tid * T + cur_edge;
+                        if (s_hi >= 0 && s_hi < SPC) slot_of[s_hi] = tid * T + cur_edge + 1;
+                    }
+                    __syncthreads();
                 } else {
                     if (tid < m.R) pt_exchange_body(m, pt, 0, tid, a.pt_schedule, parity, pt_event);
                     parity = 1 - parity;
+                    __syncthreads();
+                    rebuild_slots();
+                    __syncthreads();
                 }
-                __syncthreads();
-                rebuild_slots();
-                __syncthreads();
             }
             pt_event++;
+            if (!prepared_next && pt_prep) prepare_exchange(pt_event);
         }
+        PROWS_CLK(6);
     }
     cluster.sync();  // no CTA leaves (or rewrites global state) while another may still address its shared memory
     const int n_own = (T - rank + NC - 1) / NC;

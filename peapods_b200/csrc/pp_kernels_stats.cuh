@@ -155,7 +155,7 @@ __device__ __forceinline__ void fold_batch(const ModelView &m, const StatsView &
 // statistics/overlap.rs:283-306, thread 11 the histogram cells (12 consecutive threads per (d, t); the callers spread the (d, t)
 // over the block).  One uniform loop: every thread derives the terms of replica i and pair i and adds its own, so each sum receives
 // exactly fold_one's additions in fold_one's order — a thread's chain is R (or P) additions long instead of 5 R + 6 P.
-template <typename GetM, typename GetE, typename GetS, typename GetL>
+template <bool SMALL = false, typename GetM, typename GetE, typename GetS, typename GetL>
 __device__ __forceinline__ void fold_spread(const ModelView &m, const StatsView &st, int64_t d, int t, int j, GetM get_m, GetE get_e,
                                             GetS get_ds, GetL get_dl) {
     const float nf = (float)m.N, nb = (float)(m.N * m.z);
@@ -164,29 +164,31 @@ __device__ __forceinline__ void fold_spread(const ModelView &m, const StatsView 
     double *sum = st.sums + d * 11 * m.T + t + (int64_t)(j < 11 ? j : 0) * m.T;
     double acc = owns ? *sum : 0.0;
     const int n = m.R > m.P ? m.R : m.P;
+    // SMALL: every integer input fits 32 bits (systems that live in shared memory): same value, a one-instruction conversion
+    auto to_f = [](long long x) { return SMALL ? (float)(int)x : (float)x; };
     for (int i = 0; i < n; i++) {
         const bool hr = i < m.R, hp = i < m.P;
-        const float mag = __fdiv_rn((float)get_m(hr ? i : 0), nf);
+        const float mag = __fdiv_rn(to_f(get_m(hr ? i : 0)), nf);
         const float m2 = __fmul_rn(mag, mag);
         const float e = get_e(hr ? i : 0);
         const long long dsp = m.P > 0 ? get_ds(hp ? i : 0) : 0ll;
         const long long dlk = m.P > 0 ? get_dl(hp ? i : 0) : 0ll;
-        const float ql = __fdiv_rn((float)dlk, nb);
-        const float q = __fdiv_rn((float)dsp, nf);
+        const float ql = __fdiv_rn(to_f(dlk), nb);
+        const float q = __fdiv_rn(to_f(dsp), nf);
         const float q2 = __fmul_rn(q, q);
         const float ql2 = __fmul_rn(ql, ql);
-        double term = 0.0;
-        term = j == 0 ? (double)mag : term;
-        term = j == 1 ? (double)m2 : term;
-        term = j == 2 ? (double)__fmul_rn(m2, m2) : term;
-        term = j == 3 ? (double)e : term;
-        term = j == 4 ? __dmul_rn((double)e, (double)e) : term;  // stats.rs:23: powi(2) in f64
-        term = j == 5 ? (double)q : term;
-        term = j == 6 ? (double)q2 : term;
-        term = j == 7 ? (double)__fmul_rn(q2, q2) : term;
-        term = j == 8 ? (double)ql : term;
-        term = j == 9 ? (double)ql2 : term;
-        term = j == 10 ? (double)__fmul_rn(ql2, ql2) : term;
+        float tf = mag;  // the thread's f32 term, widened once (every term but e^2 is an f32 value)
+        tf = j == 1 ? m2 : tf;
+        tf = j == 2 ? __fmul_rn(m2, m2) : tf;
+        tf = j == 3 || j == 4 ? e : tf;
+        tf = j == 5 ? q : tf;
+        tf = j == 6 ? q2 : tf;
+        tf = j == 7 ? __fmul_rn(q2, q2) : tf;
+        tf = j == 8 ? ql : tf;
+        tf = j == 9 ? ql2 : tf;
+        tf = j == 10 ? __fmul_rn(ql2, ql2) : tf;
+        const double td = (double)tf;
+        const double term = j == 4 ? __dmul_rn(td, td) : td;  // stats.rs:23: powi(2) in f64
         if (owns && (j < 5 ? hr : hp)) acc = __dadd_rn(acc, term);
         if (j == 11 && hp) {  // the histogram cells in pair order (two pairs of a sweep may hit the same cell)
             const int64_t h = (d * m.T + t) * bins + (dsp + m.N) / 2;
