@@ -1150,12 +1150,26 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                     for (int i = lane; i < sysw; i += 32) X[i] = wa[i] ^ wb[i];
                     __syncwarp();
                     int neg_q = 0, neg_l = 0;
-                    for (int i = lane; i < sysw; i += 32) {
-                        const int r = i / W, w = i - r * W;
-                        const uint32_t x = X[i];
-                        neg_q += __popc(x);
+                    if (warp_is_system) {  // lane = word: the forward-neighbour offsets of the lane's own work item apply (no table reads:
+                                           // the cluster barrier in front of this phase invalidated L1)
+                        const uint32_t x = X[lane];
+                        neg_q = __popc(x);
 #pragma unroll
-                        for (int k = 0; k < Z; k++) neg_l += __popc(x ^ nbr_word(X, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]));
+                        for (int k = 0; k < Z; k++) {
+                            const uint32_t c0 = X[h_n0[0][2 * k]];
+                            uint32_t nw = c0;
+                            if (dls[k] > 0) nw = (c0 >> 1) | (X[h_n1[0][2 * k]] << 31);
+                            else if (dls[k] < 0) nw = (c0 << 1) | (X[h_n1[0][2 * k]] >> 31);
+                            neg_l += __popc(x ^ nw);
+                        }
+                    } else {
+                        for (int i = lane; i < sysw; i += 32) {
+                            const int r = i / W, w = i - r * W;
+                            const uint32_t x = X[i];
+                            neg_q += __popc(x);
+#pragma unroll
+                            for (int k = 0; k < Z; k++) neg_l += __popc(x ^ nbr_word(X, vg.nbr_row[((size_t)r * Z + k) * 2], w, dls[k]));
+                        }
                     }
                     neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
                     neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
