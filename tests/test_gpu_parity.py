@@ -576,6 +576,48 @@ def test_packed_row_kernels_are_bit_exact(oracle, monkeypatch, shape, offsets, t
     assert_state_equal(gpu, cpu, 1)
 
 
+CLUSTER_RESIDENT_CASES = [
+    # shape, temps, R: small ferromagnets with rows of 32 k sites -> one bit per spin, the systems of a realization spread over a
+    # thread-block cluster (prows_cluster_resident_kernel) whenever they divide evenly over 8 / 4 / 2 CTAs
+    ((4, 32), np.linspace(1.8, 2.8, 4), 2),            # 8 systems of 4 words: one system per CTA, warps that span no whole system
+    ((4, 4, 32), np.linspace(4.0, 5.0, 3), 2),         # three forward directions; 6 systems: a cluster of 2
+    ((8, 64), np.linspace(1.8, 2.8, 4), 4),            # rows of two words, two replica pairs per temperature
+    ((16, 32), [2.0, 2.27, 2.6, 3.0, 1e9], 2),         # 10 systems: a cluster of 2; T = 1e9: the all-thresholds form
+    ((32, 32), np.linspace(1.5, 3.0, 5), 1),           # 5 systems: no even split, the one-CTA form; a single replica: no pairs
+    ((32, 32), np.linspace(1.5, 3.0, 8), 1),           # 8 systems on 8 CTAs without replica pairs
+]
+
+
+@pytest.mark.parametrize("shape,temps,R", CLUSTER_RESIDENT_CASES)
+@pytest.mark.parametrize("mode", ["metropolis", "gibbs"])
+def test_cluster_resident_kernel_shapes_are_bit_exact(oracle, shape, temps, R, mode):
+    gpu, cpu = make_pair(oracle, shape, "ferro", temps, R, 1)
+    assert gpu.rows_packed
+    assert_state_equal(gpu, cpu, 1)
+    for n_sweeps, interval, schedule in ((1, None, "single_random_edge"), (23, 1, "full_ladder"), (61, 1, "single_random_edge"),
+                                         (40, 3, "single_random_edge"), (300, 2, "full_ladder")):
+        kw = dict(warmup_ratio=0.25, pt_interval=interval, pt_schedule=schedule)
+        rg = gpu.sample(n_sweeps, mode, **kw)
+        rc = cpu.sample(n_sweeps, mode, **kw)
+        assert_state_equal(gpu, cpu, 1)
+        assert_results_equal(rg, rc)
+        assert np.array_equal(gpu.get_energies(0), cpu.energies(0))
+
+
+def test_cluster_resident_kernel_equals_the_one_cta_form(oracle, monkeypatch):
+    import peapods_b200 as pb
+
+    shape, temps, R = (32, 32), np.linspace(1.5, 3.0, 16).astype(np.float32), 2
+    kw = dict(warmup_ratio=0.25, pt_interval=1)
+    many = pb.IsingSimulation(list(shape), "ferro", temps, R, None, 5, layout="int8")
+    monkeypatch.setenv("PP_NO_RESIDENT_CLUSTER", "1")
+    one = pb.IsingSimulation(list(shape), "ferro", temps, R, None, 5, layout="int8")
+    for n in (7, 400):
+        ra, rb = many.sample(n, "metropolis", **kw), one.sample(n, "metropolis", **kw)
+        assert np.array_equal(many.get_spins(0), one.get_spins(0)) and np.array_equal(many.get_system_ids(0), one.get_system_ids(0))
+        assert_results_equal(ra, rb)
+
+
 @pytest.mark.parametrize("cluster_mode", ["sw", "wolff"])
 def test_packed_rows_run_cluster_moves_through_the_int8_view(oracle, monkeypatch, cluster_mode):
     monkeypatch.setenv("PP_RESIDENT", "0")
