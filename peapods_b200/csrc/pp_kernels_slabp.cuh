@@ -84,7 +84,7 @@ slabp_sweep_kernel(ModelView m, SlabPView v, int colour, uint32_t sweep_index, i
                 const uint32_t cnt = m.lut[t * 13 + 2 * u];  // sweep.rs:162-166, index ec + 2z' = 2 * unsat
                 T[u] = NM == 3 ? cnt << 8 : cnt;             // NM == 3: cnt < 2^24, compare the 32-bit word against cnt << 8
             }
-            uint32_t M[NM];
+            uint32_t M[NM];  // NM == 3: M[0], M[1] = the two bit planes of L (the number of thresholds above the draw), M[2] unused
 #pragma unroll
             for (int u = 0; u < NM; u++) M[u] = 0u;
             const uint32_t q = (uint32_t)(((int64_t)gx0 * v.L1 + x1) * v.W + w);  // rank >> 5 of the word's sites
@@ -108,16 +108,25 @@ slabp_sweep_kernel(ModelView m, SlabPView v, int colour, uint32_t sweep_index, i
                     for (int j = 0; j < 4; j++) {
                         const uint32_t bit = 1u << (16 * h + 4 * g + j);
                         const uint32_t y = NM == 3 ? ys[j] : ys[j] >> 8;
+                        if (NM == 3) {  // T[0] <= T[1] <= T[2] (host-checked): two compares place the draw, L = 2 p1 + p2
+                            const bool p1 = y < T[1];
+                            const bool p2 = y < (p1 ? T[0] : T[2]);
+                            if (p1) M[1] |= bit;
+                            if (p2) M[0] |= bit;
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < NM; u++)
-                            if (y < T[u]) M[u] |= bit;
+                            for (int u = 0; u < NM; u++)
+                                if (y < T[u]) M[u] |= bit;
+                        }
                     }
                 }
             }
             const uint32_t kk = s1 & s2, oo = s1 | s2;
             if (NM == 3) {
-                // nested events M0 <= M1 <= M2, L = their number: flip <=> x + 2 y + L >= 3
-                flip = slabp_maj3(c1, c2, oo | M[2]) | (kk & M[2]) | (oo & M[1]) | M[0];
+                // L = L0 + 2 L1 thresholds lie above the draw: flip <=> x + 2 y + L >= 3, i.e. with a = x + L0, b = y + L1:
+                // b >= 2, or b = 1 and a >= 1, or b = 0 and a = 3 (x = 2 and L0)
+                const uint32_t L0 = M[0], L1 = M[1], y0 = c1 ^ c2, y1 = c1 & c2;
+                flip = y1 | (y0 & L1) | ((y0 ^ L1) & ~y1 & (oo | L0)) | (~(c1 | c2 | L1) & kk & L0);
             } else {
                 // unsat = x0 + 2 y1 + 4 y2, L = L0 + 2 L1 + 4 L2 from the nested masks M0 <= ... <= M6: flip <=> unsat + L + 1 >= 8
                 const uint32_t x0 = s1 ^ s2, y1 = slabp_xor3(c1, c2, kk), y2 = slabp_maj3(c1, c2, kk);
