@@ -1006,6 +1006,9 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
         float cur_logu = pt_logu;
         bool prepared_next = false;  // pt_edge / pt_logu already hold the event after this sweep's
         PROWS_CLK(7);
+        // a warp that holds exactly one system counts its bonds and down spins inside the colour-1 pass (no pass of its own)
+        const bool cnt_inpass = warp_is_system && (record || pt_this);
+        int ip_unsat = 0, ip_dn = 0;
         for (int colour = 0; colour < 2; colour++) {
             const uint32_t tagc = TAG_SWEEP_PACKED | (uint32_t)colour;
 #pragma unroll
@@ -1059,28 +1062,23 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                     const uint32_t eq = ((u & 1) ? un[0] : ~un[0]) & ((u & 2) ? un[1] : ~un[1]) & ((u & 4) ? un[2] : ~un[2]) & ((u & 8) ? un[3] : ~un[3]);
                     flip |= u < NM ? (eq & (M[u] << p)) : eq;
                 }
-                sys[h_own[j]] = C ^ (flip & (0x55555555u << p));
+                const uint32_t act = 0x55555555u << p, Cn = C ^ (flip & act);
+                sys[h_own[j]] = Cn;
+                if (cnt_inpass && colour == 1) {  // energy.rs:99-108 from the last pass: its sites' 2z' bonds are all bonds, each once; a
+                    const uint32_t fm = flip & act;  // flip inverts the bond words of its site
+#pragma unroll
+                    for (int k = 0; k < Z2; k++) ip_unsat += __popc((b[k] ^ fm) & act);
+                    ip_dn += __popc(Cn);
+                }
             }
             __syncthreads();
         }
         PROWS_CLK(0);
         if (record || pt_this) {  // mod.rs:486-509; energy.rs:99-108 for the CTA's systems, results to every CTA of the cluster
             if (warp_is_system) {  // a warp's work items are exactly one system: totals by REDUX, lanes 0 .. NC - 1 deliver them
-                int unsat = 0, dn = 0;
                 const int ls = h_ls[0];
-                const uint32_t *sys = pw + (size_t)ls * sysw;
-                const uint32_t C = sys[h_own[0]];
-#pragma unroll
-                for (int k = 0; k < Z; k++) {
-                    const uint32_t c0 = sys[h_n0[0][2 * k]];
-                    uint32_t nw = c0;
-                    if (dls[k] > 0) nw = (c0 >> 1) | (sys[h_n1[0][2 * k]] << 31);
-                    else if (dls[k] < 0) nw = (c0 << 1) | (sys[h_n1[0][2 * k]] >> 31);
-                    unsat += __popc(C ^ nw);
-                }
-                dn = __popc(C);
-                unsat = __reduce_add_sync(0xFFFFFFFFu, unsat);
-                dn = __reduce_add_sync(0xFFFFFFFFu, dn);
+                const int unsat = __reduce_add_sync(0xFFFFFFFFu, ip_unsat);
+                const int dn = __reduce_add_sync(0xFFFFFFFFu, ip_dn);
                 if (lane < NC) {
                     const float e = __fdiv_rn((float)((long long)Z * m.N - 2ll * unsat), (float)m.N);
                     *cluster.map_shared_rank(&en_all[par * S + sys0 + ls], lane) = e;
