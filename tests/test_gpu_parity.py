@@ -359,6 +359,30 @@ def test_sys_word_device_log_agrees_statistically(oracle):
         np.testing.assert_allclose(rg["overlap2"], rc["overlap2"], atol=0.05)
 
 
+def test_sys_word_autocorrelation_and_equilibration_diagnostic(oracle):
+    """The per-sweep consumers of magnetisations and pair dots on a system-word handle (integer inputs: exact) and of the f32
+    energies (tolerance); packed rows in cluster mode take the same options (the fold stays inside the kernel, the pushes read
+    what it left in global memory)."""
+    shape, temps, R, D = (4, 4, 32), np.linspace(0.9, 1.8, 4), 4, 2
+    gpu, cpu = make_pair(oracle, shape, "gaussian", temps, R, D)
+    assert gpu.sys_words
+    kw = dict(warmup_ratio=0.25, autocorrelation_max_lag=4, equilibration_diagnostic=True)
+    rg = gpu.sample(140, "metropolis", exact_log=True, **kw)
+    rc = cpu.sample(140, "metropolis", **kw)
+    assert_state_equal(gpu, cpu, D)
+    for k in ("mags2", "overlap2", "link_overlap", "mags2_tau", "overlap2_tau", "equil_sweeps", "equil_link_overlap_avg"):
+        assert np.array_equal(rg[k], rc[k]), k
+    np.testing.assert_allclose(rg["equil_energy_avg"], rc["equil_energy_avg"], rtol=1e-5, atol=1e-7)
+    # ferromagnet on packed rows, clusters of R CTAs: autocorrelation pushes after a fused recorded sweep
+    gpu, cpu = make_pair(oracle, (4, 64), "ferro", [1.8, 2.27, 2.8], 2, 1)
+    assert gpu.rows_packed
+    for kw in (dict(autocorrelation_max_lag=5), dict(autocorrelation_max_lag=3, equilibration_diagnostic=True, pt_interval=2)):
+        rg = gpu.sample(150, "gibbs", **kw)
+        rc = cpu.sample(150, "gibbs", **kw)
+        assert_state_equal(gpu, cpu, 1)
+        assert_results_equal(rg, rc)
+
+
 def gpu_couplings(shape, offsets, D):
     z = len(shape) if offsets is None else len(offsets)
     J = couplings("gaussian", shape, z, D, 7)
