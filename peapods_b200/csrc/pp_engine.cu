@@ -926,13 +926,16 @@ static pp_status launch_swords(pp_sim *s, Ctx &c, const ModelView &m, int sweep_
     RowsView v = s->rv;
     v.keys = s->d_keys + (c.m.sample_offset - s->mv.sample_offset);
     const SWordsView sv = swords_view(s, c);
-    const dim3 grid((unsigned)(m.D * sv.SW), blocks_for(m.N / 2, SW_THREADS * SW_SPT));
+    // sites per thread: SW_SPT when the batch is large, fewer while the grid would not fill the GPU a few times over
+    int spt = SW_SPT;
+    while (spt > 1 && (int64_t)m.D * sv.SW * (int64_t)blocks_for(m.N / 2, SW_THREADS * spt) < 4 * 148 * 8) spt /= 2;
+    const dim3 grid((unsigned)(m.D * sv.SW), blocks_for(m.N / 2, SW_THREADS * spt));
     const bool gibbs = sweep_mode == PP_SWEEP_GIBBS;
     if (n_sweeps > 0) {  // system_ids only change between launch sequences (parallel tempering, set_system_ids)
         swords_lane_temps_kernel<<<blocks_for(m.D * m.S, 256), 256, 0, c.stream>>>(m, sv);
         s->launches++;
     }
-#define PP_SW5(Z_, G_, U_, E_, X_) swords_sweep_kernel<Z_, G_, U_, E_, X_><<<grid, SW_THREADS, 0, c.stream>>>(m, v, sv, col, sweep_index + (uint32_t)sw)
+#define PP_SW5(Z_, G_, U_, E_, X_) swords_sweep_kernel<Z_, G_, U_, E_, X_><<<grid, SW_THREADS, 0, c.stream>>>(m, v, sv, col, sweep_index + (uint32_t)sw, spt)
 #define PP_SW4(Z_, G_, U_, E_) do { if (exact_log) PP_SW5(Z_, G_, U_, E_, true); else PP_SW5(Z_, G_, U_, E_, false); } while (0)
 #define PP_SW3(Z_, G_) do { if (!update) PP_SW5(Z_, false, false, true, false); else if (eacc) PP_SW4(Z_, G_, true, true); else PP_SW4(Z_, G_, true, false); } while (0)
 #define PP_SW2(Z_) do { if (gibbs) PP_SW3(Z_, true); else PP_SW3(Z_, false); } while (0)
@@ -1615,9 +1618,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 if (s->swords) {
                     SWordsView &sv = s->swv;
                     sv.SW = (m.S + 31) / 32;
-                    // fixed-point unit of the in-sweep bond sums: a thread's f32 sum over its SW_SPT sites, |.| <= SW_SPT * 2z' * max|J|,
-                    // is rounded to an integer number of 1 / escale; 32 threads of a warp and the warps of a block add up in 32 bits
-                    sv.escale = std::ldexp(1.0f, std::min(30, (int)std::floor(std::log2(std::ldexp(1.0, 23) / (SW_SPT * 2.0 * z * (double)jmax)))));
+                    // fixed-point unit of the in-sweep bond sums: |s h| escale <= 2z' max|J| escale stays below 2^20 (the rounding addend
+                    // 1.5 * 2^23 holds 2^22; a thread adds SW_SPT terms, a warp 32 threads, a block four warps into 32-bit integers)
+                    sv.escale = std::ldexp(1.0f, std::min(30, (int)std::floor(std::log2(std::ldexp(1.0, 20) / (2.0 * z * (double)jmax)))));
                     const size_t n_acc = (size_t)m.D * (size_t)sv.SW;
                     auto take = [&](void **p, size_t bytes, bool zero) -> cudaError_t {
                         cudaError_t e = pool_alloc(s, p, bytes);

@@ -15,8 +15,8 @@
 // rebuilds the lane -> temperature map of its word from system_ids at the start of every launch.
 //
 // Energies (needed by every exchange): the colour-1 pass of a two-colour lattice touches every bond exactly once, so it also adds up
-// s_i h_i after the update per lane (energy.rs:99-108): a thread adds its SW_SPT sites in f32 in a fixed order, rounds the sum to an
-// integer number of 1 / escale (a power of two) and everything above a thread is integer addition, independent of its order.  Magnetisations and replica overlaps work on a
+// s_i h_i after the update per lane (energy.rs:99-108), each term rounded to an integer number of 1 / escale (a power of two) on the
+// spot, so that every addition is an integer addition and the energies do not depend on threads, blocks or batch size.  Magnetisations and replica overlaps work on a
 // TRANSPOSED view produced on recorded sweeps (swords_transpose_kernel: 32 x 32 bit transposes in registers -> `tbits[D][S][N / 32]`,
 // one bit per spin, system-major), where a replica pair's q and q_link are XORs and popcounts of whole row words
 // (overlap.rs:259-281).  The int8 array stays as a scratch VIEW for get_spins / set_spins / the cluster moves.
@@ -51,7 +51,7 @@ struct SWordsView {
 #define PP_SW_MINB_E 6 // the same for the pass that also adds up the bond sums (32 more accumulators)
 #endif
 constexpr int SW_THREADS = PP_SW_THREADS;
-constexpr int SW_SPT = 8;  // sites per thread of a colour pass
+constexpr int SW_SPT = 8;  // sites per thread of a colour pass (at most; the host lowers it for small batches so that the grid fills the GPU)
 
 #if defined(__CUDACC__)
 
@@ -78,10 +78,11 @@ __host__ __device__ __forceinline__ void sw_transpose32(uint32_t (&a)[32]) {
     }
 }
 
-// One colour pass (UPDATE) and / or the bond sums of the colour's sites (EACC).  grid = (D * SW, ceil(N / 2 / (SW_THREADS * SW_SPT))).
+// One colour pass (UPDATE) and / or the bond sums of the colour's sites (EACC).  grid = (D * SW, ceil(N / 2 / (SW_THREADS * spt))),
+// spt <= SW_SPT sites per thread.
 template <int Z, bool GIBBS, bool UPDATE, bool EACC, bool EXACT>
 __global__ void __launch_bounds__(SW_THREADS, EACC ? PP_SW_MINB_E : PP_SW_MINB)
-swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t sweep_index) {
+swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t sweep_index, int spt) {
     __shared__ float ht_sm[32];
     __shared__ float2 kt_sm[32];  // production-mode threshold of a lane: kt.x * log2(draw) + kt.y = (T / 2) ln u
     __shared__ int blk_sm[32];
@@ -106,11 +107,15 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
     const uint32_t vmask = nl == 32 ? 0xFFFFFFFFu : ((1u << nl) - 1u);
     const uint32_t tagc = TAG_SWEEP_SYSQ | (uint32_t)colour;
     const float escale = sv.escale;
-    float eacc[EACC ? 32 : 1];  // per lane: sum over this thread's sites of s h after the update
+    // per lane: sum over this thread's sites of round(s h escale) after the update, every term carried by the low mantissa bits of
+    // s h * escale + 1.5 * 2^23 (round to nearest; |s h| escale < 2^21): integer sums from the first addition on, so the energies
+    // do not depend on how sites are grouped into threads, blocks or batches
+    int eacc[EACC ? 32 : 1];
 #pragma unroll
-    for (int l = 0; l < (EACC ? 32 : 1); l++) eacc[l] = 0.0f;
-    for (int it = 0; it < SW_SPT; it++) {
-        const uint32_t c = (blockIdx.y * SW_SPT + it) * SW_THREADS + tid;  // = the site's rank inside its colour class
+    for (int l = 0; l < (EACC ? 32 : 1); l++) eacc[l] = 0;
+    uint32_t nterms = 0;
+    for (int it = 0; it < spt; it++) {
+        const uint32_t c = (blockIdx.y * (uint32_t)spt + (uint32_t)it) * SW_THREADS + tid;  // = the site's rank inside its colour class
         if (c >= n_act) break;
         const uint32_t r = c / (uint32_t)Lh, j = c - r * (uint32_t)Lh;
         const int off = (int)v.row_a[r] == colour ? 0 : 1;
@@ -137,9 +142,13 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
             F[kk] ^= C;
             B[kk] ^= C;
         }
-        uint32_t flips = 0u;
+        nterms++;
+        // Lanes from 31 down to 0: the decision of a lane is the SIGN of  e = eng_change - (T / 2) ln u  (flip <=> e >= 0; the f32
+        // difference has the sign of the exact one, and exact equality gives +0), shifted into `keep` with one funnel shift per lane
+        // (bit = 1: the lane does not flip) instead of a compare, a select and an OR.
+        uint32_t keep = 0u;
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
+        for (int g = 7; g >= 0; g--) {
             if (4 * g < nl) {
                 uint32_t dr[4] = {0u, 0u, 0u, 0u};
                 if (UPDATE) {
@@ -147,7 +156,7 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
                     dr[0] = o.x >> 8; dr[1] = o.y >> 8; dr[2] = o.z >> 8; dr[3] = o.w >> 8;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 3; q >= 0; q--) {
                     const int l = 4 * g + q, sh = 31 - l;
                     // sweep.rs:10-17: forward then backward per direction; a product with a +-1 spin is the coupling with its sign
                     // bit flipped.  The words were XORed with the site's own word, so the sum is s_i h (negation commutes with
@@ -159,7 +168,7 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
                         sh_ = __fadd_rn(sh_, __uint_as_float(__float_as_uint(Jf[kk]) ^ ((F[kk] << sh) & 0x80000000u)));
                         sh_ = __fadd_rn(sh_, __uint_as_float(__float_as_uint(Jb[kk]) ^ ((B[kk] << sh) & 0x80000000u)));
                     }
-                    bool flip = false;
+                    uint32_t ebits = 0x80000000u;  // no update: every lane keeps its spin
                     if (UPDATE) {
                         float thr;
                         if (EXACT) {  // host-libm tables: bit-identical to a host replay
@@ -169,23 +178,23 @@ swords_sweep_kernel(ModelView m, RowsView v, SWordsView sv, int colour, uint32_t
                             const float a = sw_lg2((float)dr[q]);
                             thr = GIBBS ? kt.x * (a - sw_lg2((float)(16777216u - dr[q]))) : fmaf(kt.x, a, kt.y);
                         }
-                        flip = -sh_ >= thr;  // eng_change >= (T / 2) ln u: sweep.rs:256 / 279-282
-                        if (flip) flips |= 1u << l;
+                        ebits = __float_as_uint(__fadd_rn(-sh_, -thr));  // eng_change - (T / 2) ln u: sweep.rs:256 / 279-282
+                        keep = __funnelshift_l(ebits, keep, 1);
                     }
-                    if (EACC) {  // s h after the update
-                        eacc[l] += sh_;
-                        if (flip) eacc[l] = fmaf(-2.0f, sh_, eacc[l]);
-                    }
+                    // s h after the update: +s h where the lane keeps its spin, -s h where it flips
+                    if (EACC) eacc[l] += __float_as_int(fmaf(sh_, __uint_as_float(__float_as_uint(escale) ^ (~ebits & 0x80000000u)), 12582912.0f));
                 }
+            } else if (UPDATE) {
+                keep <<= 4;
             }
         }
+        const uint32_t flips = ~keep;
         if (UPDATE) W[i] = C ^ (flips & vmask);
     }
     if (EACC) {
 #pragma unroll
         for (int l = 0; l < 32; l++) {
-            // the thread's sum (fixed order) rounded to an integer number of 1 / escale: every later addition is exact
-            const int ws = __reduce_add_sync(0xFFFFFFFFu, __float2int_rn(eacc[l] * escale));
+            const int ws = __reduce_add_sync(0xFFFFFFFFu, (int)((uint32_t)eacc[l] - nterms * 0x4B400000u));  // minus the addends' bits
             if ((tid & 31) == l) atomicAdd(&blk_sm[l], ws);
         }
         __syncthreads();
