@@ -1574,8 +1574,9 @@ extern "C" pp_status pp_create(const pp_model_desc *desc, pp_sim **out) {
                 if (s->resident_packed && s->plan.n_colours == 2 && rp.m_half == 1 && !getenv("PP_NO_RESIDENT_CLUSTER")) {
                     const int64_t sysw = rp.n_rows * (rp.L / 32);
                     const int want_nc = getenv("PP_RESIDENT_CLUSTER") ? atoi(getenv("PP_RESIDENT_CLUSTER")) : 0;
-                    for (int nc : {8, 4, 2}) {
+                    for (int nc : {16, 8, 4, 2}) {
                         if (want_nc > 0 && nc != want_nc) continue;
+                        if (nc == 16 && want_nc != 16) continue;  // non-portable cluster size: only on request (PP_RESIDENT_CLUSTER=16)
                         if (m.S % nc != 0 || m.S / nc > 64 || sysw > 65535) continue;
                         const int64_t items = (int64_t)(m.S / nc) * sysw;
                         const int nt = (int)std::min<int64_t>(512, std::max<int64_t>(64, (items + 31) / 32 * 32));
@@ -1925,6 +1926,7 @@ static pp_status run_rows_resident(pp_sim *s, Ctx &c, const pp_sample_cfg *cfg, 
 #define PP_CRES(Z_, NM_)                                                                                                              \
     do {                                                                                                                              \
     CUDA_TRY(cudaFuncSetAttribute(prows_cluster_resident_kernel<Z_, NM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    if (nc > 8) CUDA_TRY(cudaFuncSetAttribute(prows_cluster_resident_kernel<Z_, NM_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
     CUDA_TRY(cudaLaunchKernelEx(&lc, prows_cluster_resident_kernel<Z_, NM_>, mk, v, c.st, c.pt, a, nc));                               \
     } while (0)
             if (mk.z == 2) { if (nm == 2) PP_CRES(2, 2); else PP_CRES(2, 5); }
