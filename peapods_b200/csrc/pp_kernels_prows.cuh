@@ -810,7 +810,7 @@ prows_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView ptg, Resi
 //     by sweep parity (a CTA may be most of a sweep ahead of another).
 // Requirements (host-checked): two colours, one row class (m_half = 1), S a multiple of NC, work items <= 2 per thread.
 struct ClusterResidentLayout {  // word offsets into the dynamic shared memory of one CTA (all 8-byte aligned blocks first)
-    size_t sums, mag_all, dsp_all, dlk_all, ea, eacc, rt, en_all, temps, dbeta, sid, cnt, thr, pw, xs, trip, total_bytes;
+    size_t sums, mag_all, dsp_all, dlk_all, ea, eacc, rt, en_all, temps, dbeta, sid, cnt, thr, pw, snap, xs, trip, total_bytes;
 };
 __host__ __device__ inline ClusterResidentLayout cluster_resident_layout(int S, int T, int P, int z, int nc, int sysw) {
     ClusterResidentLayout l;
@@ -831,6 +831,7 @@ __host__ __device__ inline ClusterResidentLayout cluster_resident_layout(int S, 
     l.thr = o; o += 4 * (size_t)T * (2 * z + 1);
     o = (o + 15) & ~size_t(15);
     l.pw = o; o += 4 * (size_t)(S / nc) * sysw;
+    l.snap = o; o += 4 * 2 * (size_t)(S / nc) * sysw;  // the words as the last two recorded sweeps left them (read by the pair dots)
     l.xs = o; o += 4 * (size_t)16 * sysw;  // one XOR-word scratch per warp (<= 16 warps)
     l.trip = o; o += (size_t)S;
     l.total_bytes = (o + 15) & ~size_t(15);
@@ -863,6 +864,7 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
     int *cnt_sm = reinterpret_cast<int *>(cres_sm + lay.cnt);                   // [2 * SPC]
     uint32_t *thr_sm = reinterpret_cast<uint32_t *>(cres_sm + lay.thr);
     uint32_t *pw = reinterpret_cast<uint32_t *>(cres_sm + lay.pw);              // [SPC][rows][W]
+    uint32_t *snap_sm = reinterpret_cast<uint32_t *>(cres_sm + lay.snap);       // [2][SPC][rows][W]
     uint32_t *xs_sm = reinterpret_cast<uint32_t *>(cres_sm + lay.xs);           // [warps][rows][W]
     uint8_t *trip_sm = cres_sm + lay.trip;
     int8_t *g_spins = mg.spins + dg * S * mg.N;
@@ -1074,6 +1076,8 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
             __syncthreads();
         }
         PROWS_CLK(0);
+        if (record && P > 0)  // the pair dots read these copies: the words themselves may move on once barrier A is passed
+            for (int i = tid; i < SPC * sysw; i += NT) snap_sm[(size_t)par * SPC * sysw + i] = pw[i];
         if (record || pt_this) {  // mod.rs:486-509; energy.rs:99-108 for the CTA's systems, results to every CTA of the cluster
             if (warp_is_system) {  // a warp's work items are exactly one system: totals by REDUX, lanes 0 .. NC - 1 deliver them
                 const int ls = h_ls[0];
@@ -1120,31 +1124,31 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
             last_e = par;
             if (record) last_m = par;
             PROWS_CLK(1);
-            // A: all S energies (+ magnetisation sums) of this sweep are in every CTA
-            if (record && P > 0) {  // (a recorded sweep has barrier B further down to prepare the next exchange under)
-                cluster.sync();
-            } else {
-                asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-                cur_edge = pt_edge; cur_logu = pt_logu;
-                if (pt_prep) prepare_exchange(pt_event + (pt_this ? 1u : 0u));
-                asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-                prepared_next = true;
-            }
+            // A: all S energies (+ magnetisation sums) of this sweep are in every CTA, and so are the word snapshots; the next
+            // exchange is prepared between the arrive and the wait
+            asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+            cur_edge = pt_edge; cur_logu = pt_logu;
+            if (pt_prep) prepare_exchange(pt_event + (pt_this ? 1u : 0u));
+            asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+            prepared_next = true;
             PROWS_CLK(2);
         }
         m.energies = en_all + par * S;
         m.mags = mag_all + par * S;
         if (record) {
-            if (P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids: pair idx goes to warp idx / NC of CTA idx % NC,
-                          // which fetches both replicas' words through DSMEM (two loads per lane in flight together), keeps the XOR
-                          // words in its own scratch and takes the link terms from there
+            if (P > 0) {  // overlap.rs:259-281 with this sweep's pre-exchange system_ids: the pairs of temperature t are handled by the CTA
+                          // that folds t (t mod NC), one warp per pair: it fetches both replicas' word snapshots through DSMEM (two
+                          // loads per lane in flight together), keeps the XOR words in its own scratch, takes the link terms from
+                          // there and leaves the dots in its own shared memory — no second cluster barrier
                 uint32_t *X = xs_sm + (size_t)warp * sysw;
-                for (int idx = rank + NC * warp; idx < PT_; idx += NC * n_warps) {
-                    const int t = idx % T, pr = idx / T;
+                const int n_mine = ((T - rank + NC - 1) / NC) * P;  // (temperature, pair) items of this CTA
+                for (int j = warp; j < n_mine; j += n_warps) {
+                    const int t = rank + (j / P) * NC, pr = j % P, idx = pr * T + t;
                     const int sa = sid_sm[(2 * pr) * T + t], sb = sid_sm[(2 * pr + 1) * T + t];
                     const int oa = sa / SPC, ob = sb / SPC;
-                    const uint32_t *wa = cluster.map_shared_rank(pw, oa) + (size_t)(sa - oa * SPC) * sysw;
-                    const uint32_t *wb = cluster.map_shared_rank(pw, ob) + (size_t)(sb - ob * SPC) * sysw;
+                    const uint32_t *snap_par = snap_sm + (size_t)par * SPC * sysw;
+                    const uint32_t *wa = cluster.map_shared_rank(snap_par, oa) + (size_t)(sa - oa * SPC) * sysw;
+                    const uint32_t *wb = cluster.map_shared_rank(snap_par, ob) + (size_t)(sb - ob * SPC) * sysw;
                     for (int i = lane; i < sysw; i += 32) X[i] = wa[i] ^ wb[i];
                     __syncwarp();
                     int neg_q = 0, neg_l = 0;
@@ -1171,20 +1175,15 @@ prows_cluster_resident_kernel(ModelView mg, RowsView vg, StatsView stg, PtView p
                     }
                     neg_q = __reduce_add_sync(0xFFFFFFFFu, neg_q);
                     neg_l = __reduce_add_sync(0xFFFFFFFFu, neg_l);
-                    if (lane == 0) {  // to the CTA that folds temperature t
-                        *cluster.map_shared_rank(&dsp_all[par * PT_ + idx], t % NC) = m.N - 2ll * neg_q;
-                        *cluster.map_shared_rank(&dlk_all[par * PT_ + idx], t % NC) = (long long)Z * m.N - 2ll * neg_l;
+                    if (lane == 0) {
+                        dsp_all[par * PT_ + idx] = m.N - 2ll * neg_q;
+                        dlk_all[par * PT_ + idx] = (long long)Z * m.N - 2ll * neg_l;
                     }
                     __syncwarp();
                 }
                 last_d = par;
                 PROWS_CLK(3);
-                // B: the dots are with their folding CTAs; nobody reads another CTA's words any more
-                asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-                cur_edge = pt_edge; cur_logu = pt_logu;
-                if (pt_prep) prepare_exchange(pt_event + (pt_this ? 1u : 0u));
-                asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-                prepared_next = true;
+                __syncthreads();  // the dots of this CTA's temperatures are in its shared memory
                 PROWS_CLK(4);
             }
             st.dot_spin = dsp_all + par * PT_;
